@@ -1,0 +1,419 @@
+// TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Driver for the UNMODIFIED reference (felpzOliveira/Bubbles) CPU path. Compiled by
+// oracle/build_ref.sh against the reference sources where they lie (headers by -I, objects from
+// /root/reference/src) -- nothing from the reference is copied into this repository.
+// Recipe: SURVEY.md Appendix D.  It (a) supplies a calloc shim for the managed-memory arena
+// (reference: src/cuda/memory.cpp:58-105 aborts without a CUDA driver), (b) re-runs the body of
+// BuildNeighborListKernel on the host (reference: src/core/grid.h:602-624; the launch silently fails
+// without a device), (c) runs AdvanceTimeStep (reference: src/solvers/pcisph_solver3.cpp:42-65) or the
+// same call sequence phase by phase, dumping every intermediate array as .npy.
+//
+// Usage: bbref <job.txt>     (commands documented in oracle/README.md)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <fstream>
+#include <sstream>
+#include <iostream>
+#include <chrono>
+
+#include <pcisph_solver.h>
+#include <sph_solver.h>
+#include <emitter.h>
+#include <collider.h>
+#include <shape.h>
+#include <grid.h>
+#include <util.h>
+#include <memory.h>
+
+// ---- shim for src/cuda/memory.cpp (signatures: src/cuda/cutil.h:134-136, src/cuda/memory.h:17-32)
+void *_cudaAllocate(size_t bytes, int, const char *, bool){ return calloc(1, bytes ? bytes : 1); }
+void *_cudaAllocateUnregister(size_t bytes, int, const char *, bool){ return calloc(1, bytes ? bytes : 1); }
+void *_cudaAllocateExclusive(size_t bytes, int, const char *, bool){ return calloc(1, bytes ? bytes : 1); }
+void CudaMemoryManagerStart(const char *){}
+std::string CudaGetCurrentKey(){ return std::string("oracle"); }
+void CudaMemoryManagerClearCurrent(){}
+void CudaMemoryManagerClearAll(){}
+// lives in the (excluded) 2D solver: src/solvers/pcisph_solver2.cpp:7
+extern const Float kDefaultTimeStepLimitScale = 5.0;
+
+// free functions defined (non-static) in the reference translation units
+void AdvanceTimeStep(PciSphSolver3 *solver, Float timeStep, int use_cpu);
+void AdvanceTimeStep(SphSolver3 *solver, Float timeStep, int use_cpu);
+void PredictVelocityAndPositionCPU(PciSphSolverData3 *data, Float dt, int is_first);
+void PredictPressureCPU(PciSphSolverData3 *data, Float delta);
+void PredictPressureForceCPU(PciSphSolverData3 *data);
+void AccumulateAndIntegrateCPU(PciSphSolverData3 *data, Float timeStep);
+
+// ---------------------------------------------------------------- npy writer
+template<typename T> struct NpyType;
+template<> struct NpyType<double>{ static const char *s(){ return "<f8"; } };
+template<> struct NpyType<int32_t>{ static const char *s(){ return "<i4"; } };
+template<> struct NpyType<int64_t>{ static const char *s(){ return "<i8"; } };
+
+template<typename T>
+static void WriteNpy(const std::string &path, const T *data, size_t rows, size_t cols){
+    FILE *fp = fopen(path.c_str(), "wb");
+    if(!fp){ fprintf(stderr, "cannot open %s\n", path.c_str()); exit(2); }
+    std::stringstream ss;
+    ss << "{'descr': '" << NpyType<T>::s() << "', 'fortran_order': False, 'shape': (" << rows;
+    if(cols > 0) ss << ", " << cols << "), }"; else ss << ",), }";
+    std::string h = ss.str();
+    size_t total = 10 + h.size() + 1;
+    size_t pad = (64 - total % 64) % 64;
+    h += std::string(pad, ' ');
+    h += "\n";
+    unsigned char magic[10] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0, 0, 0};
+    magic[8] = (unsigned char)(h.size() & 0xff);
+    magic[9] = (unsigned char)((h.size() >> 8) & 0xff);
+    fwrite(magic, 1, 10, fp);
+    fwrite(h.data(), 1, h.size(), fp);
+    fwrite(data, sizeof(T), rows * (cols ? cols : 1), fp);
+    fclose(fp);
+}
+
+static void DumpVec3(const std::string &path, vec3f *v, int n){
+    std::vector<double> buf(3 * (size_t)n);
+    for(int i = 0; i < n; i++){ buf[3*i] = v[i].x; buf[3*i+1] = v[i].y; buf[3*i+2] = v[i].z; }
+    WriteNpy<double>(path, buf.data(), n, 3);
+}
+static void DumpScalar(const std::string &path, Float *v, int n){
+    WriteNpy<double>(path, v, n, 0);
+}
+
+// ---------------------------------------------------------------- state
+struct Harness{
+    Float spacing = 0.02, scale = 1.8, density = WaterDensity;
+    Bounds3f domain;
+    bool hasDomain = false;
+    std::vector<Shape *> shapes;
+    std::vector<Float> frictions;
+    ParticleSetBuilder3 builder;
+    Grid3 *grid = nullptr;
+    PciSphSolver3 pci;
+    SphSolver3 sph;
+    SphSolverData3 *data = nullptr;
+    SphParticleSet3 *sphSet = nullptr;
+    ColliderSet3 *colliders = nullptr;
+    int solverKind = 0; // 0 = pcisph, 1 = sph
+    Float viscosity = -1, drag = -1;
+    int gravity = 1;
+};
+
+static Transform ReadTransform(std::istringstream &in){
+    Float m[4][4];
+    for(int i = 0; i < 4; i++) for(int j = 0; j < 4; j++) in >> m[i][j];
+    return Transform(m);
+}
+
+static void HostBuildNeighborLists(Grid3 *grid){
+    // body of BuildNeighborListKernel (src/core/grid.h:602-624) run on the host
+    for(unsigned int i = 0; i < grid->total; i++){
+        int neighbor[27];
+        Cell3 *cell = &grid->cells[i];
+        vec3ui u = grid->GetCellIndex(i);
+        vec3f center;
+        for(int k = 0; k < 3; k++)
+            center[k] = grid->minPoint[k] + u[k] * grid->cellsLen[k] + 0.5 * grid->cellsLen[k];
+        vec3f pMin = center - 0.5 * grid->cellsLen;
+        vec3f pMax = center + 0.5 * grid->cellsLen;
+        int count = grid->GetNeighborListFor(i, 1, &neighbor[0]);
+        cell->SetNeighborListPtr(&grid->neighborListPtr[27 * i]);
+        cell->Set(Bounds3f(pMin, pMax), i);
+        cell->SetNeighborList(&neighbor[0], count);
+    }
+}
+
+static void DumpGrid(Harness &H, const std::string &prefix){
+    Grid3 *g = H.grid;
+    ParticleSet3 *pSet = H.sphSet->GetParticleSet();
+    int n = pSet->GetParticleCount();
+    std::vector<int32_t> counts(g->total), order;
+    order.reserve(n);
+    for(unsigned int c = 0; c < g->total; c++){
+        Cell3 *cell = &g->cells[c];
+        int len = cell->GetChainLength();
+        counts[c] = len;
+        ParticleChain *p = cell->GetChain();
+        for(int j = 0; j < len; j++){ order.push_back((int32_t)p->pId); p = p->next; }
+    }
+    WriteNpy<int32_t>(prefix + "cell_count.npy", counts.data(), counts.size(), 0);
+    WriteNpy<int32_t>(prefix + "cell_order.npy", order.data(), order.size(), 0);
+    std::vector<int32_t> bcount(n), bids((size_t)n * MaximumParticlesPerBucket, -1);
+    for(int i = 0; i < n; i++){
+        Bucket *b = pSet->GetParticleBucket(i);
+        bcount[i] = b->Count();
+        for(int k = 0; k < b->Count(); k++) bids[(size_t)i * MaximumParticlesPerBucket + k] = b->Get(k);
+    }
+    WriteNpy<int32_t>(prefix + "nbr_count.npy", bcount.data(), n, 0);
+    WriteNpy<int32_t>(prefix + "nbr_ids.npy", bids.data(), n, MaximumParticlesPerBucket);
+}
+
+static void DumpState(Harness &H, const std::string &prefix){
+    ParticleSet3 *pSet = H.sphSet->GetParticleSet();
+    int n = pSet->GetParticleCount();
+    DumpVec3(prefix + "pos.npy", pSet->positions.data, n);
+    DumpVec3(prefix + "vel.npy", pSet->velocities.data, n);
+    DumpVec3(prefix + "force.npy", pSet->forces.data, n);
+    DumpScalar(prefix + "density.npy", pSet->densities.data, n);
+    DumpScalar(prefix + "pressure.npy", pSet->pressures.data, n);
+}
+
+static void Setup(Harness &H){
+    if(!H.hasDomain){ fprintf(stderr, "no domain\n"); exit(2); }
+    H.grid = UtilBuildGridForDomain(H.domain, H.spacing, H.scale);
+    HostBuildNeighborLists(H.grid);
+    ColliderSetBuilder3 cBuilder;
+    for(size_t i = 0; i < H.shapes.size(); i++) cBuilder.AddCollider3(H.shapes[i], H.frictions[i]);
+    H.colliders = cBuilder.GetColliderSet();
+    H.sphSet = SphParticleSet3FromBuilder(&H.builder);
+    H.sphSet->SetRelativeKernelRadius(H.scale);
+    H.data = DefaultSphSolverData3(H.gravity != 0);
+    if(H.solverKind == 0){
+        H.pci.Initialize(H.data);
+        H.pci.Setup(H.density, H.spacing, H.scale, H.grid, H.sphSet);
+        H.pci.SetColliders(H.colliders);
+        if(H.viscosity >= 0) H.pci.SetViscosityCoefficient(H.viscosity);
+    }else{
+        H.sph.Initialize(H.data);
+        H.sph.Setup(H.density, H.spacing, H.scale, H.grid, H.sphSet);
+        H.sph.SetColliders(H.colliders);
+        if(H.viscosity >= 0) H.sph.SetViscosityCoefficient(H.viscosity);
+    }
+    if(H.drag >= 0) H.data->dragCoefficient = H.drag;
+    ParticleSet3 *pSet = H.sphSet->GetParticleSet();
+    vec3ui res = H.grid->GetIndexCount();
+    printf("[bbref] N=%d cells=%u (%u x %u x %u) mass=%.17g h=%.17g\n", pSet->GetParticleCount(),
+           H.grid->GetCellCount(), res.x, res.y, res.z, pSet->GetMass(), H.sphSet->GetKernelRadius());
+    printf("[bbref] grid min=(%.17g %.17g %.17g) len=(%.17g %.17g %.17g)\n",
+           H.grid->minPoint.x, H.grid->minPoint.y, H.grid->minPoint.z,
+           H.grid->cellsLen.x, H.grid->cellsLen.y, H.grid->cellsLen.z);
+}
+
+// One PCISPH sub-step, phase by phase, same call sequence as
+// AdvanceTimeStep (pcisph_solver3.cpp:42-65) + ComputePressureForceAndIntegrate (pcisph_equations3.cpp:218-256)
+static void TraceStep(Harness &H, Float dt, const std::string &prefix){
+    SphSolverData3 *data = H.data;
+    PciSphSolverData3 *pd = H.pci.solverData;
+    ParticleSet3 *pSet = H.sphSet->GetParticleSet();
+    int n = pSet->GetParticleCount();
+    int32_t flag = data->sphpSet->requiresHigherLevelUpdate;
+    WriteNpy<int32_t>(prefix + "rebuild_flag.npy", &flag, 1, 0);
+    UpdateGridDistributionCPU(data);
+    data->sphpSet->ResetHigherLevel();
+    DumpGrid(H, prefix);
+    ComputeParticleInteractionCPU(data);
+    ComputeDensityCPU(data);
+    DumpScalar(prefix + "density.npy", pSet->densities.data, n);
+    ComputeNonPressureForceCPU(data);
+    DumpVec3(prefix + "force_np.npy", pSet->forces.data, n);
+    Float delta = H.pci.ComputeDelta(dt);
+    WriteNpy<double>(prefix + "delta.npy", &delta, 1, 0);
+    // k = 0 only: the reference's loop exits after one iteration
+    PredictVelocityAndPositionCPU(pd, dt, 1);
+    DumpVec3(prefix + "pos_pred.npy", pd->tempPositions, n);
+    PredictPressureCPU(pd, delta);
+    DumpScalar(prefix + "density_pred.npy", pd->densityPredicted, n);
+    DumpScalar(prefix + "pressure.npy", pSet->pressures.data, n);
+    PredictPressureForceCPU(pd);
+    DumpVec3(prefix + "force_p.npy", pd->pressureForces, n);
+    Float maxErr = 0;
+    for(int i = 0; i < n; i++){ Float e = pd->densityErrors[i]; if(e*e > maxErr*maxErr) maxErr = e; }
+    WriteNpy<double>(prefix + "max_density_error.npy", &maxErr, 1, 0);
+    AccumulateAndIntegrateCPU(pd, dt);
+    ComputePseudoViscosityInterpolationCPU(data, dt);
+    DumpVec3(prefix + "pos_out.npy", pSet->positions.data, n);
+    DumpVec3(prefix + "vel_out.npy", pSet->velocities.data, n);
+    DumpVec3(prefix + "force_out.npy", pSet->forces.data, n);
+    int32_t flag2 = data->sphpSet->requiresHigherLevelUpdate;
+    WriteNpy<int32_t>(prefix + "rebuild_flag_out.npy", &flag2, 1, 0);
+}
+
+int main(int argc, char **argv){
+    if(argc < 2){ fprintf(stderr, "usage: bbref job.txt\n"); return 2; }
+    cudaSetLaunchStrategy(CudaLaunchStrategy::CustomizedBlockSize, 16);
+    SetSystemUseCPU();
+    SetCPUThreads(1);
+    Harness H;
+    std::ifstream job(argv[1]);
+    if(!job){ fprintf(stderr, "cannot open job %s\n", argv[1]); return 2; }
+    std::string line;
+    while(std::getline(job, line)){
+        if(line.empty() || line[0] == '#') continue;
+        std::istringstream in(line);
+        std::string cmd; in >> cmd;
+        if(cmd == "threads"){ int t; in >> t; SetCPUThreads(t); }
+        else if(cmd == "solver"){ std::string s; in >> s; H.solverKind = (s == "sph") ? 1 : 0; }
+        else if(cmd == "spacing"){ in >> H.spacing; }
+        else if(cmd == "scale"){ in >> H.scale; }
+        else if(cmd == "density"){ in >> H.density; }
+        else if(cmd == "viscosity"){ in >> H.viscosity; }
+        else if(cmd == "drag"){ in >> H.drag; }
+        else if(cmd == "gravity"){ in >> H.gravity; }
+        else if(cmd == "domain"){
+            vec3f a, b; in >> a.x >> a.y >> a.z >> b.x >> b.y >> b.z;
+            H.domain = Bounds3f(a, b); H.hasDomain = true;
+        }
+        else if(cmd == "domain_from_collider"){
+            int idx; in >> idx; H.domain = H.shapes[idx]->GetBounds(); H.hasDomain = true;
+        }
+        else if(cmd == "collider"){
+            std::string kind; in >> kind;
+            if(kind == "box"){
+                Transform t = ReadTransform(in);
+                vec3f size; int rev; Float fr;
+                in >> size.x >> size.y >> size.z >> rev >> fr;
+                H.shapes.push_back(MakeBox(t, size, rev != 0)); H.frictions.push_back(fr);
+            }else if(kind == "sphere"){
+                Transform t = ReadTransform(in);
+                Float r; int rev; Float fr;
+                in >> r >> rev >> fr;
+                H.shapes.push_back(MakeSphere(t, r, rev != 0)); H.frictions.push_back(fr);
+            }else if(kind == "sdf"){
+                // SDF grid collider from a raw field file written by the test (analytic SDF sampled at
+                // the node positions this harness reports); mirrors Shape::InitSDFShape (shape.h:201-230)
+                vec3f a, b; Float dx, margin, fr; std::string file;
+                in >> a.x >> a.y >> a.z >> b.x >> b.y >> b.z >> dx >> margin >> fr >> file;
+                Shape *shape = (Shape *)calloc(1, sizeof(Shape));
+                Bounds3f bounds(a, b);
+                shape->bounds = bounds;
+                shape->type = ShapeType::ShapeSDF;
+                shape->WorldToObject = Transform();
+                shape->ObjectToWorld = Transform();
+                vec3f sc(bounds.ExtentOn(0), bounds.ExtentOn(1), bounds.ExtentOn(2));
+                shape->bounds.pMin -= margin * sc;
+                shape->bounds.pMax += margin * sc;
+                Float width = shape->bounds.ExtentOn(0), height = shape->bounds.ExtentOn(1);
+                Float depth = shape->bounds.ExtentOn(2);
+                int resolution = (int)std::ceil(width / dx);
+                dx = width / (Float)resolution;
+                int resolutionY = (int)std::ceil(resolution * height / width);
+                int resolutionZ = (int)std::ceil(resolution * depth / width);
+                shape->grid = (FieldGrid3f *)calloc(1, sizeof(FieldGrid3f));
+                shape->grid->Build(vec3ui(resolution, resolutionY, resolutionZ), vec3f(dx),
+                                   shape->bounds.pMin, VertexCentered);
+                FILE *fp = fopen(file.c_str(), "rb");
+                if(!fp){ fprintf(stderr, "cannot open sdf field %s\n", file.c_str()); return 2; }
+                size_t got = fread(shape->grid->field, sizeof(Float), shape->grid->total, fp);
+                fclose(fp);
+                if(got != shape->grid->total){
+                    fprintf(stderr, "sdf field size mismatch: file %zu, grid %u (%u %u %u)\n", got,
+                            shape->grid->total, shape->grid->resolution.x, shape->grid->resolution.y,
+                            shape->grid->resolution.z);
+                    return 2;
+                }
+                shape->grid->MarkFilled();
+                H.shapes.push_back(shape); H.frictions.push_back(fr);
+            }else{ fprintf(stderr, "unknown collider %s\n", kind.c_str()); return 2; }
+        }
+        else if(cmd == "emit_box"){
+            // reference emitter path (emitter.cpp:242-330): BCC lattice + libc rand() jitter
+            Transform t = ReadTransform(in);
+            vec3f size, v; Float jitter; unsigned seed;
+            in >> size.x >> size.y >> size.z >> v.x >> v.y >> v.z >> jitter >> seed;
+            srand(seed);
+            Shape *box = MakeBox(t, size);
+            VolumeParticleEmitterSet3 set;
+            VolumeParticleEmitter3 em(box, box->GetBounds(), H.spacing, v);
+            set.AddEmitter(&em);
+            set.SetJitter(jitter);
+            set.Emit(&H.builder);
+        }
+        else if(cmd == "particles"){
+            std::string file; in >> file;
+            FILE *fp = fopen(file.c_str(), "rb");
+            if(!fp){ fprintf(stderr, "cannot open %s\n", file.c_str()); return 2; }
+            int64_t n = 0;
+            if(fread(&n, sizeof(n), 1, fp) != 1) return 2;
+            std::vector<double> pos(3 * n), vel(3 * n);
+            if(fread(pos.data(), sizeof(double), 3 * n, fp) != (size_t)(3 * n)) return 2;
+            if(fread(vel.data(), sizeof(double), 3 * n, fp) != (size_t)(3 * n)) return 2;
+            fclose(fp);
+            for(int64_t i = 0; i < n; i++)
+                H.builder.AddParticle(vec3f(pos[3*i], pos[3*i+1], pos[3*i+2]),
+                                      vec3f(vel[3*i], vel[3*i+1], vel[3*i+2]));
+        }
+        else if(cmd == "setup"){ Setup(H); }
+        else if(cmd == "set_chains"){
+            // inject an explicit per-cell chain order (counts + concatenated ids), built with the
+            // reference's own Cell::AddToChain (grid.h:128-141) after a reset
+            std::string fc, fo; in >> fc >> fo;
+            Grid3 *g = H.grid; ParticleSet3 *pSet = H.sphSet->GetParticleSet();
+            std::vector<int32_t> counts(g->total), order(pSet->GetParticleCount());
+            FILE *fp = fopen(fc.c_str(), "rb"); size_t r = fread(counts.data(), 4, counts.size(), fp); fclose(fp);
+            fp = fopen(fo.c_str(), "rb"); r += fread(order.data(), 4, order.size(), fp); fclose(fp);
+            size_t at = 0;
+            for(unsigned int c = 0; c < g->total; c++){
+                g->DistributeResetCell(c);
+                for(int k = 0; k < counts[c]; k++){
+                    int pid = order[at++];
+                    ParticleChain *node = pSet->GetParticleChainNode(pid);
+                    node->cId = c; node->pId = pid; node->sId = pSet->GetFamilyId();
+                    g->cells[c].AddToChain(node);
+                }
+            }
+            H.sphSet->ResetHigherLevel();
+        }
+        else if(cmd == "round32"){
+            ParticleSet3 *pSet = H.sphSet->GetParticleSet();
+            for(int i = 0; i < pSet->GetParticleCount(); i++){
+                vec3f p = pSet->positions.data[i], v = pSet->velocities.data[i];
+                pSet->positions.data[i] = vec3f((float)p.x, (float)p.y, (float)p.z);
+                pSet->velocities.data[i] = vec3f((float)v.x, (float)v.y, (float)v.z);
+            }
+        }
+        else if(cmd == "step"){
+            Float dt; int n; in >> dt >> n;
+            auto t0 = std::chrono::steady_clock::now();
+            for(int s = 0; s < n; s++){
+                if(H.solverKind == 0) AdvanceTimeStep(&H.pci, dt, 1);
+                else AdvanceTimeStep(&H.sph, dt, 1);
+            }
+            double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            int np = H.sphSet->GetParticleSet()->GetParticleCount();
+            printf("[bbref] steps=%d dt=%g seconds=%.6f particle_updates_per_s=%.6e\n", n, (double)dt, sec,
+                   (double)np * n / sec);
+        }
+        else if(cmd == "advance"){
+            Float t; in >> t;
+            if(H.solverKind == 0) H.pci.Advance(t); else H.sph.Advance(t);
+        }
+        else if(cmd == "trace"){ Float dt; std::string prefix; in >> dt >> prefix; TraceStep(H, dt, prefix); }
+        else if(cmd == "dump"){ std::string prefix; in >> prefix; DumpState(H, prefix); }
+        else if(cmd == "dump_grid"){ std::string prefix; in >> prefix; DumpGrid(H, prefix); }
+        else if(cmd == "delta"){
+            Float dt; in >> dt;
+            printf("[bbref] delta(%.17g)=%.17g\n", (double)dt, (double)H.pci.ComputeDelta(dt));
+        }
+        else if(cmd == "collide"){
+            // apply ColliderSet3::ResolveCollision to a list of (pos, vel): file in, npy out
+            std::string file, prefix; Float radius, rest; in >> file >> radius >> rest >> prefix;
+            FILE *fp = fopen(file.c_str(), "rb");
+            int64_t n = 0; size_t r = fread(&n, sizeof(n), 1, fp);
+            std::vector<double> pos(3 * n), vel(3 * n);
+            r += fread(pos.data(), 8, 3 * n, fp); r += fread(vel.data(), 8, 3 * n, fp); fclose(fp);
+            std::vector<int32_t> hit(n);
+            for(int64_t i = 0; i < n; i++){
+                vec3f p(pos[3*i], pos[3*i+1], pos[3*i+2]), v(vel[3*i], vel[3*i+1], vel[3*i+2]);
+                hit[i] = H.colliders->ResolveCollision(radius, rest, &p, &v) ? 1 : 0;
+                pos[3*i] = p.x; pos[3*i+1] = p.y; pos[3*i+2] = p.z;
+                vel[3*i] = v.x; vel[3*i+1] = v.y; vel[3*i+2] = v.z;
+            }
+            WriteNpy<double>(prefix + "pos.npy", pos.data(), n, 3);
+            WriteNpy<double>(prefix + "vel.npy", vel.data(), n, 3);
+            WriteNpy<int32_t>(prefix + "hit.npy", hit.data(), n, 0);
+        }
+        else if(cmd == "sdf_nodes"){
+            // report the node layout of SDF collider idx so the test can sample its analytic SDF there
+            int idx; in >> idx; FieldGrid3f *g = H.shapes[idx]->grid;
+            printf("[bbref] sdf res=%u %u %u spacing=%.17g origin=%.17g %.17g %.17g\n", g->resolution.x,
+                   g->resolution.y, g->resolution.z, g->spacing.x, g->minPoint.x, g->minPoint.y, g->minPoint.z);
+        }
+        else{ fprintf(stderr, "unknown command: %s\n", cmd.c_str()); return 2; }
+    }
+    return 0;
+}
