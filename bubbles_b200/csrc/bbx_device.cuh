@@ -1,0 +1,358 @@
+// Device-side building blocks shared by the bbx kernels: grid hashing (FP64, bit-exact with the
+// reference), the neighbour acceptance predicate (FP32 with an FP64 re-check inside a guard band),
+// SPH kernel weights and the collider response.
+//
+// Reference semantics restated here (paths relative to the Bubbles tree):
+//   Grid::GetHashedPosition / ExtremeEpsilon / LinearIndex   src/core/grid.h:259-298, 182-193
+//   IsWithinStd / IsWithinSpiky / kernel weights            src/core/kernel.cpp:123-234
+//   ColliderSet3::ResolveCollision -> CollisionHandle       src/core/collider.cpp:238-264, 3-44
+//   Box / sphere / SDF closest point                        src/shapes/box.cpp:74-172, src/shapes/sphere.cpp:47-70,
+//                                                           src/shapes/bvh.cpp:666-707, src/core/grid.h:1093-1169
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/bbx.h"
+
+#define BBX_NBR_CHUNKS 13   // 13 x 8 = 104 >= 100 list entries per particle
+#define BBX_RUN_SHIFT 12    // list entry = (run << 12) | offset-in-run
+#define BBX_RUN_MASK 0xfffu
+#define BBX_MAX_RUN_LEN 4096
+
+struct DevGrid {
+    double min[3], max[3], len[3];
+    float minf[3], maxf[3];
+    int n[3];
+    int total;
+    int plane;          // n[0] * n[1]
+    int z_begin, z_end; // owned z planes (multi-GPU slab); single GPU: 0 .. n[2]
+};
+
+struct DevCollider {
+    int type, reverse, active, pad;
+    double o2w[16];
+    double w2o[16];
+    double size[3];
+    double radius;
+    double friction;
+    double linvel[3];
+    double angvel[3];
+    int sdf_res[3];
+    int pad2;
+    double sdf_spacing[3];
+    double sdf_origin[3];
+    const double *sdf_field; // device pointer
+};
+
+struct DevColliderSet {
+    int count;
+    int pad;
+    DevCollider c[BBX_MAX_COLLIDERS];
+};
+
+// Per-engine mutable device state (flags + statistics), one instance in global memory.
+struct DevState {
+    int rebuild_flag;   // SphParticleSet3::requiresHigherLevelUpdate (set by integrate, read by next grid update)
+    int jump_flag;      // some particle moved >= 2 cells since the last grid update (chains would lose it)
+    int full_rebuild;   // the last grid update took the full (ascending-id) path
+    int overflow;       // particles whose neighbour list hit the 100 cap
+    int lost;           // particles that jumped >= 2 cells
+    int clamped;        // particles pushed back into the domain
+    int nan_count;
+    int error;          // sticky: bbx_status-like device-detected error (out of domain, run too long)
+    unsigned max_force_bits; // float bits of max |f| (non-negative floats order like unsigned)
+    unsigned max_err_bits;   // float bits of max |rho* - rho0|
+    int iterations;
+    int pad;
+};
+
+// Scalars of one sub-step, passed by value to every kernel.
+struct StepParams {
+    int n;              // particles on this device (owned + ghosts)
+    int n_owned;
+    float h, h2, inv_h, inv_h2;
+    float thr2;         // h^2 - 1e-8: acceptance threshold of IsWithinStd on d^2
+    float band;         // guard band around thr2 inside which the predicate is re-evaluated in FP64
+    double h_d, h2_d;   // FP64 copies for the exact re-check
+    float mass, mass2, inv_mass;
+    float rho0;
+    float w_std_c;      // 315 / (64 pi h^3)
+    float d2w_spiky_c;  // 90 / (pi h^5)
+    float dw_spiky_c;   // 45 / (pi h^4)   (gradW = +c (1-d/h)^2 dir)
+    float w_spiky_c;    // 15 / (pi h^3)
+    float viscosity, drag;
+    float gx, gy, gz;
+    float dt;
+    float delta;
+    float neg_pressure_scale;
+    float eos_scale, eos_exponent; // rho0 c^2 / gamma, gamma
+    float radius;       // particle radius = spacing
+    float restitution;
+    float min_cell_len09; // 0.9 * min cell length (big-move rule, sph_equations3.cpp:330-335)
+    float pseudo_factor;  // clamp(dt * pseudoViscosity, 0, 1)
+};
+
+// ------------------------------------------------------------------------------------------- grid
+
+// Grid::GetHashedPosition: FP64 arithmetic on the FP32-stored position, same expression order as the
+// reference so that integer results are bit-exact for identical inputs. Returns -1 if outside.
+__device__ __forceinline__ int bbx_hash(const DevGrid &g, float px, float py, float pz, int *ux, int *uy, int *uz){
+    const float pf[3] = {px, py, pz};
+    int u[3];
+#pragma unroll
+    for(int i = 0; i < 3; i++){
+        double p = (double)pf[i];
+        double eps = 0.0;
+        if(fabs(p - g.min[i]) < 1e-8) eps = (double)0.0001f;
+        else if(fabs(p - g.max[i]) < 1e-8) eps = -(double)0.0001f;
+        p = __dadd_rn(p, eps);
+        double dp = __ddiv_rn(__dsub_rn(p, g.min[i]), g.len[i]);
+        u[i] = (int)floor(dp);
+    }
+    *ux = u[0]; *uy = u[1]; *uz = u[2];
+    if(u[0] < 0 || u[0] >= g.n[0] || u[1] < 0 || u[1] >= g.n[1] || u[2] < 0 || u[2] >= g.n[2]) return -1;
+    return u[0] + u[1] * g.n[0] + u[2] * g.plane;
+}
+
+// IsWithinStd(Distance(pi, pj), h) evaluated exactly as the reference does (FP64, sqrt then square,
+// no FMA contraction): src/core/kernel.cpp:229-234, src/core/geometry.h:632-633.
+__device__ __noinline__ bool bbx_within_std_exact(float4 a, float4 b, double h2){
+    double x = __dsub_rn((double)a.x, (double)b.x);
+    double y = __dsub_rn((double)a.y, (double)b.y);
+    double z = __dsub_rn((double)a.z, (double)b.z);
+    double s = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+    double d = __dsqrt_rn(s);
+    double d2 = __dmul_rn(d, d);
+    double of = __dsub_rn(d2, h2);
+    return !(fabs(of) < 1e-8 || of > 0);
+}
+
+// Neighbour acceptance: FP32 fast path, FP64 only inside the guard band (|d2 - thr2| <= band).
+__device__ __forceinline__ bool bbx_accept(const StepParams &P, float4 a, float4 b, float d2){
+    float diff = d2 - P.thr2;
+    if(fabsf(diff) <= P.band) return bbx_within_std_exact(a, b, P.h2_d);
+    return diff < 0.f;
+}
+
+// ------------------------------------------------------------------------------------- colliders
+// The collider response decides (penetrating / not, which face) on absolute epsilons of 1e-6 .. 1e-8;
+// it runs in FP64 so that those decisions follow the FP64 reference (cost: O(100) flops per
+// particle, twice per sub-step -- negligible next to the neighbour sums).
+
+struct Vec3d { double x, y, z; };
+__device__ __forceinline__ Vec3d v3(double x, double y, double z){ Vec3d r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ Vec3d operator+(Vec3d a, Vec3d b){ return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ Vec3d operator-(Vec3d a, Vec3d b){ return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ Vec3d operator*(double s, Vec3d a){ return v3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ double dot3(Vec3d a, Vec3d b){ return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double len3(Vec3d a){ return sqrt(dot3(a, a)); }
+__device__ __forceinline__ double comp(Vec3d a, int i){ return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+__device__ __forceinline__ Vec3d xf_point(const double *m, Vec3d p){
+    double xp = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
+    double yp = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+    double zp = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11];
+    double wp = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];
+    if(wp == 1) return v3(xp, yp, zp);
+    double inv = 1.0 / wp;
+    return v3(xp * inv, yp * inv, zp * inv);
+}
+// Transform::Normal uses the transposed inverse; for ObjectToWorld the inverse is WorldToObject.m
+__device__ __forceinline__ Vec3d xf_normal(const double *minv, Vec3d n){
+    return v3(minv[0] * n.x + minv[4] * n.y + minv[8] * n.z,
+              minv[1] * n.x + minv[5] * n.y + minv[9] * n.z,
+              minv[2] * n.x + minv[6] * n.y + minv[10] * n.z);
+}
+
+// Inside(vec3, Bounds3) with the reference's 1e-6 single-face slack (src/core/geometry.h:1773-1783)
+__device__ __forceinline__ bool inside_bounds(Vec3d p, Vec3d lo, Vec3d hi){
+    bool rv = (p.x >= lo.x && p.x <= hi.x && p.y >= lo.y && p.y <= hi.y && p.z >= lo.z && p.z <= hi.z);
+    if(!rv){
+        double ox = fmin(fabs(lo.x - p.x), fabs(hi.x - p.x));
+        double oy = fmin(fabs(lo.y - p.y), fabs(hi.y - p.y));
+        double oz = fmin(fabs(lo.z - p.z), fabs(hi.z - p.z));
+        rv = (ox < 1e-6) || (oy < 1e-6) || (oz < 1e-6);
+    }
+    return rv;
+}
+__device__ __forceinline__ double clampd(double v, double lo, double hi){ return v < lo ? lo : (v > hi ? hi : v); }
+
+// Box closest point in object space. Face order +x,+y,+z,-x,-y,-z with strict '<' (first wins).
+__device__ __forceinline__ double box_query(const DevCollider &c, Vec3d pw, bool want_point, Vec3d *cpw, Vec3d *nw){
+    Vec3d pl = xf_point(c.w2o, pw);
+    Vec3d hi = v3(c.size[0] / 2.0, c.size[1] / 2.0, c.size[2] / 2.0);
+    Vec3d lo = v3(-hi.x, -hi.y, -hi.z);
+    Vec3d closest, normal = v3(1, 0, 0);
+    bool neg = false;
+    if(inside_bounds(pl, lo, hi)){
+        // projections onto the six face planes; the distance to face k is |pl_k -+ h_k|
+        double best = 0; int bi = 0;
+#pragma unroll
+        for(int i = 0; i < 6; i++){
+            int ax = i % 3;
+            double plane = i < 3 ? comp(hi, ax) : comp(lo, ax);
+            double sgn = i < 3 ? 1.0 : -1.0;
+            // Plane3::ClosestPoint: r - dot(r, n) n + point, r = p - point  (box.cpp:22-26)
+            Vec3d pt = i < 3 ? hi : lo;
+            Vec3d r = pl - pt;
+            double d = sgn * comp(r, ax);
+            Vec3d nn = v3(ax == 0 ? sgn : 0, ax == 1 ? sgn : 0, ax == 2 ? sgn : 0);
+            Vec3d loc = (r - d * nn) + pt;
+            Vec3d df = loc - pl;
+            double l2 = dot3(df, df);
+            if(i == 0 || l2 < best){ best = l2; bi = i; closest = loc; normal = nn; }
+            (void)plane;
+        }
+        (void)bi;
+        neg = true;
+    }else{
+        closest = v3(clampd(pl.x, lo.x, hi.x), clampd(pl.y, lo.y, hi.y), clampd(pl.z, lo.z, hi.z));
+        Vec3d cov = pl - closest;
+        double maxCos = cov.x; // dot(cov, (1,0,0))
+#pragma unroll
+        for(int i = 1; i < 6; i++){
+            int ax = i % 3;
+            double sgn = i < 3 ? 1.0 : -1.0;
+            double cs = sgn * comp(cov, ax);
+            if(cs > maxCos){ maxCos = cs; normal = v3(ax == 0 ? sgn : 0, ax == 1 ? sgn : 0, ax == 2 ? sgn : 0); }
+        }
+    }
+    double dist = len3(closest - pl);
+    if(neg) dist = -dist;
+    if(want_point){
+        if(c.reverse) normal = v3(-normal.x, -normal.y, -normal.z);
+        *cpw = xf_point(c.o2w, closest);
+        *nw = xf_normal(c.w2o, normal);
+    }
+    return dist;
+}
+
+__device__ __forceinline__ double lerpd(double a, double b, double t){ return (1 - t) * a + t * b; }
+
+// FieldGrid::Sample (vertex centred, clamped barycentric indices)
+__device__ __forceinline__ double sdf_sample(const DevCollider &c, Vec3d p){
+    int ii[3], jj[3]; double w[3];
+#pragma unroll
+    for(int i = 0; i < 3; i++){
+        double x = (comp(p, i) - c.sdf_origin[i]) / c.sdf_spacing[i];
+        int high = c.sdf_res[i] - 1;
+        double s = floor(x);
+        int id = (int)s; double f;
+        if(high == 0){ id = 0; f = 0; }
+        else if(id < 0){ id = 0; f = 0; }
+        else if(id > high - 1){ id = high - 1; f = 1; }
+        else f = x - s;
+        ii[i] = id; w[i] = f;
+        jj[i] = min(id + 1, c.sdf_res[i] - 1);
+    }
+    const double *F = c.sdf_field; int rx = c.sdf_res[0], rxy = c.sdf_res[0] * c.sdf_res[1];
+    double f000 = F[ii[0] + ii[1] * rx + ii[2] * rxy], f100 = F[jj[0] + ii[1] * rx + ii[2] * rxy];
+    double f010 = F[ii[0] + jj[1] * rx + ii[2] * rxy], f110 = F[jj[0] + jj[1] * rx + ii[2] * rxy];
+    double f001 = F[ii[0] + ii[1] * rx + jj[2] * rxy], f101 = F[jj[0] + ii[1] * rx + jj[2] * rxy];
+    double f011 = F[ii[0] + jj[1] * rx + jj[2] * rxy], f111 = F[jj[0] + jj[1] * rx + jj[2] * rxy];
+    double b0 = lerpd(lerpd(f000, f100, w[0]), lerpd(f010, f110, w[0]), w[1]);
+    double b1 = lerpd(lerpd(f001, f101, w[0]), lerpd(f011, f111, w[0]), w[1]);
+    return lerpd(b0, b1, w[2]);
+}
+// FieldGrid::Gradient: central differences with step = node spacing
+__device__ __forceinline__ Vec3d sdf_gradient(const DevCollider &c, Vec3d p){
+    double gx = (sdf_sample(c, v3(p.x + c.sdf_spacing[0], p.y, p.z)) - sdf_sample(c, v3(p.x - c.sdf_spacing[0], p.y, p.z))) * (1.0 / (2.0 * c.sdf_spacing[0]));
+    double gy = (sdf_sample(c, v3(p.x, p.y + c.sdf_spacing[1], p.z)) - sdf_sample(c, v3(p.x, p.y - c.sdf_spacing[1], p.z))) * (1.0 / (2.0 * c.sdf_spacing[1]));
+    double gz = (sdf_sample(c, v3(p.x, p.y, p.z + c.sdf_spacing[2])) - sdf_sample(c, v3(p.x, p.y, p.z - c.sdf_spacing[2]))) * (1.0 / (2.0 * c.sdf_spacing[2]));
+    return v3(gx, gy, gz);
+}
+
+__device__ __forceinline__ double closest_distance(const DevCollider &c, Vec3d p){
+    if(c.type == BBX_COLLIDER_SPHERE){
+        Vec3d pl = xf_point(c.w2o, p);
+        return len3(pl) - c.radius;
+    }else if(c.type == BBX_COLLIDER_BOX){
+        return box_query(c, p, false, nullptr, nullptr);
+    }
+    return sdf_sample(c, p);
+}
+
+// ColliderSet3::ResolveCollision. Returns true when the particle was moved.
+__device__ __noinline__ bool bbx_resolve_collision(const DevColliderSet &cs, double radius, double restitution,
+                                                   float *px, float *py, float *pz, float *vx, float *vy, float *vz)
+{
+    Vec3d pos = v3(*px, *py, *pz);
+    int target = -1; double minDistance = 3.4028234663852886e38; // Infinity == FLT_MAX
+    for(int i = 0; i < cs.count; i++){
+        if(cs.c[i].active){
+            double d = fabs(closest_distance(cs.c[i], pos));
+            if(d < minDistance){ target = i; minDistance = d; }
+        }
+    }
+    if(target < 0) return false;
+    const DevCollider &c = cs.c[target];
+    Vec3d cp, nrm, cv = v3(0, 0, 0); double sd; bool inside;
+    if(c.type == BBX_COLLIDER_SDF){ // Shape::ClosestPointBySDF
+        Vec3d tn = v3(0, 1, 0);
+        Vec3d point = xf_point(c.w2o, pos);
+        Vec3d tp = point;
+        bool hasGradient = false;
+        for(int it = 0; it < 5; it++){
+            double sdf = sdf_sample(c, tp);
+            if(fabs(sdf) < 0.001) break;
+            tn = sdf_gradient(c, tp);
+            double l = len3(tn);
+            if(l > 0){ double inv = 1.0 / l; tn = v3(tn.x * inv, tn.y * inv, tn.z * inv); }
+            tp = tp - sdf * tn;
+            hasGradient = true;
+        }
+        if(!hasGradient){
+            tn = sdf_gradient(c, tp);
+            double l = len3(tn);
+            if(l > 0){ double inv = 1.0 / l; tn = v3(tn.x * inv, tn.y * inv, tn.z * inv); }
+        }
+        sd = len3(point - tp);
+        cp = xf_point(c.o2w, tp);
+        nrm = xf_normal(c.w2o, tn);
+        inside = sdf_sample(c, pos) < 0; // Shape::IsInside with a filled grid
+    }else if(c.type == BBX_COLLIDER_SPHERE){
+        Vec3d pl = xf_point(c.w2o, pos);
+        sd = len3(pl) - c.radius;
+        Vec3d N = v3(0, 1, 0);
+        if(!(fabs(pl.x) < 1e-8 && fabs(pl.y) < 1e-8 && fabs(pl.z) < 1e-8)){
+            double inv = 1.0 / len3(pl);
+            N = v3(pl.x * inv, pl.y * inv, pl.z * inv);
+        }
+        Vec3d pN = c.radius * N;
+        if(c.reverse) N = v3(-N.x, -N.y, -N.z);
+        cp = xf_point(c.o2w, pN);
+        nrm = xf_normal(c.w2o, N);
+        // Shape::VelocityAt
+        Vec3d q = cp - v3(c.o2w[3], c.o2w[7], c.o2w[11]);
+        cv = v3(c.linvel[0] + (c.angvel[1] * q.z - c.angvel[2] * q.y),
+                c.linvel[1] + (c.angvel[2] * q.x - c.angvel[0] * q.z),
+                c.linvel[2] + (c.angvel[0] * q.y - c.angvel[1] * q.x));
+        inside = (c.reverse != 0) == !(sd < 0);
+    }else{
+        sd = box_query(c, pos, true, &cp, &nrm);
+        inside = (c.reverse != 0) == !(sd < 0);
+    }
+    if(!(inside || fabs(sd) < radius)) return false;
+    Vec3d tp = cp + radius * nrm;
+    Vec3d vel = v3(*vx, *vy, *vz);
+    Vec3d rel = vel - cv;
+    double ndr = dot3(nrm, rel);
+    Vec3d rn = ndr * nrm;
+    Vec3d rt = rel - rn;
+    if(ndr < 0){
+        Vec3d dn = (-1.0 - restitution) * rn;
+        rn = (-restitution) * rn;
+        double rt2 = dot3(rt, rt);
+        if(rt2 > 0){
+            double scale = len3(dn) / sqrt(rt2);
+            double fs = fmax(0.0, 1.0 - c.friction * scale);
+            rt = fs * rt;
+        }
+        vel = rn + rt + cv;
+        *vx = (float)vel.x; *vy = (float)vel.y; *vz = (float)vel.z;
+    }
+    *px = (float)tp.x; *py = (float)tp.y; *pz = (float)tp.z;
+    return true;
+}
+
+// warp helpers
+__device__ __forceinline__ unsigned lanemask_lt(){ unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }

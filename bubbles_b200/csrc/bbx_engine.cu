@@ -1,0 +1,712 @@
+// bbx engine: host side of the C ABI declared in include/bbx.h.  Owns all device state, enqueues
+// the kernels of bbx_kernels.cuh on one CUDA stream, never exits the process, has no CPU path.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include <string>
+#include <algorithm>
+
+#include "../../include/bbx.h"
+#include "bbx_kernels.cuh"
+#include "bbx_host_math.h"
+
+static thread_local std::string g_last_error;
+static int set_error(int code, const char *fmt, ...){
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define CU(call) do{ cudaError_t _e = (call); if(_e != cudaSuccess) return set_error(BBX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); }while(0)
+#define CHECK_ENGINE(e) do{ if(!(e)) return set_error(BBX_ERR_INVALID, "null engine"); CU(cudaSetDevice((e)->device)); }while(0)
+
+enum { T_GRID = 0, T_DENSITY, T_FORCE_NP, T_PREDICT, T_PRESSURE, T_PRESSURE_FORCE, T_INTEGRATE, T_COUNT };
+
+struct bbx_engine {
+    bbx_config cfg;
+    int device;
+    cudaStream_t stream;
+    int n, cap;
+    DevGrid grid;
+    double mass, delta_denom, mass_over_rho0_sq, h;
+    // sorted particle arrays, double buffered for the reorder
+    float4 *pos[2], *vel[2];
+    int *pid[2], *cell[2];
+    int *cell_start[2];
+    int cur;
+    int have_chains; // cell_start[cur] / cell[cur] valid
+    int *newcell, *count, *perm, *scan_sums;
+    int scan_blocks;
+    unsigned short *nbr; int *nbr_cnt;
+    float4 *force, *force_p, *pred, *posq, *smoothed;
+    float *pressure, *rho_pred, *rho_err;
+    DevState *st; DevState *st_host; // st_host pinned
+    DevColliderSet *colliders; DevColliderSet colliders_host;
+    std::vector<double *> sdf_fields;
+    void *stage; size_t stage_bytes; // device staging for upload / download
+    long long launches;
+    int substeps;
+    int timing;
+    std::vector<cudaEvent_t> ev; size_t ev_used;
+    std::vector<int> ev_phase;
+    float phase_ms[T_COUNT]; int phase_launches[T_COUNT];
+    float last_ms_grid, last_ms_step;
+    int force_full; // next grid update must be a full rebuild (fresh particle set)
+};
+
+#define LAUNCH(e, kernel, grid, block, ...) do{ kernel<<<(grid), (block), 0, (e)->stream>>>(__VA_ARGS__); (e)->launches++; }while(0)
+static inline int div_up(long long a, int b){ return (int)((a + b - 1) / b); }
+
+const char *bbx_last_error(void){ return g_last_error.c_str(); }
+int bbx_version(void){ return BBX_VERSION; }
+
+int bbx_config_default(bbx_config *cfg, int with_gravity){
+    if(!cfg) return set_error(BBX_ERR_INVALID, "null config");
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (int)sizeof(bbx_config);
+    cfg->pcisph_max_iterations = 5;
+    cfg->pcisph_reference_compat = 1;
+    cfg->with_gravity = with_gravity;
+    cfg->spacing = 0.1; cfg->kernel_scale = 2.0; cfg->target_density = 1000.0;
+    cfg->viscosity = 0.04; cfg->drag = 0.0001; cfg->eos_exponent = 7.0; cfg->sound_speed = 100.0;
+    cfg->negative_pressure_scale = 0.0; cfg->pseudo_viscosity = 10.0;
+    if(with_gravity){ cfg->gravity[0] = 0.f; cfg->gravity[1] = -9.8f; cfg->gravity[2] = 0.f; }
+    cfg->pcisph_max_density_error_ratio = 0.01;
+    cfg->restitution = 0.6;
+    cfg->time_step_limit_scale = 5.0;
+    return BBX_OK;
+}
+
+int bbx_grid_for_domain(const double dmin[3], const double dmax[3], double spacing, double scale, bbx_grid_desc *out){
+    if(!dmin || !dmax || !out || !(spacing > 0) || !(scale > 0)) return set_error(BBX_ERR_INVALID, "bad grid arguments");
+    bbxh_grid_for_domain(dmin, dmax, spacing, scale, out);
+    return BBX_OK;
+}
+int bbx_grid_build(const int res[3], const double p0[3], const double p1[3], bbx_grid_desc *out){
+    if(!res || !p0 || !p1 || !out) return set_error(BBX_ERR_INVALID, "bad grid arguments");
+    bbxh_grid_build(res, p0, p1, out);
+    return BBX_OK;
+}
+
+template<typename T> static int dev_alloc(T **p, size_t count){
+    CU(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
+    return BBX_OK;
+}
+
+int bbx_create(const bbx_config *cfg, bbx_engine **out){
+    if(!cfg || !out) return set_error(BBX_ERR_INVALID, "null argument");
+    if(cfg->struct_size != (int)sizeof(bbx_config)) return set_error(BBX_ERR_INVALID, "bbx_config size mismatch (%d vs %d)", cfg->struct_size, (int)sizeof(bbx_config));
+    if(cfg->max_particles <= 0 || cfg->grid.total <= 0 || !(cfg->spacing > 0) || !(cfg->kernel_scale > 0))
+        return set_error(BBX_ERR_INVALID, "max_particles, grid, spacing and kernel_scale must be set");
+    int ndev = 0;
+    if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_error(BBX_ERR_NO_DEVICE, "no CUDA device: bbx has no CPU fallback");
+    if(cfg->device < 0 || cfg->device >= ndev) return set_error(BBX_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    bbx_engine *e = new bbx_engine();
+    memset(&e->cfg, 0, sizeof(e->cfg));
+    e->cfg = *cfg;
+    e->device = cfg->device;
+    e->n = 0; e->cap = cfg->max_particles; e->cur = 0; e->have_chains = 0; e->launches = 0; e->substeps = 0;
+    e->timing = 0; e->ev_used = 0; e->force_full = 1; e->stage = nullptr; e->stage_bytes = 0;
+    e->last_ms_grid = e->last_ms_step = 0.f;
+    memset(e->phase_ms, 0, sizeof(e->phase_ms)); memset(e->phase_launches, 0, sizeof(e->phase_launches));
+    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    // grid
+    DevGrid &g = e->grid;
+    for(int k = 0; k < 3; k++){
+        g.min[k] = cfg->grid.min[k]; g.max[k] = cfg->grid.max[k]; g.len[k] = cfg->grid.cell_len[k];
+        g.minf[k] = (float)g.min[k]; g.maxf[k] = (float)g.max[k]; g.n[k] = cfg->grid.n[k];
+    }
+    g.total = cfg->grid.total; g.plane = g.n[0] * g.n[1];
+    g.z_begin = cfg->slab_z_end > cfg->slab_z_begin ? cfg->slab_z_begin : 0;
+    g.z_end = cfg->slab_z_end > cfg->slab_z_begin ? cfg->slab_z_end : g.n[2];
+    if((long long)g.n[0] * g.n[1] * g.n[2] != g.total) { delete e; return set_error(BBX_ERR_INVALID, "grid.total != nx*ny*nz"); }
+    // scalars of Setup: SetTargetDensity/Spacing/RelativeKernelRadius -> ComputeMass; deltaDenom
+    e->h = cfg->kernel_scale * cfg->spacing;
+    e->mass = bbxh_compute_mass(e->h, cfg->spacing, cfg->target_density);
+    double r = e->mass / cfg->target_density;
+    e->mass_over_rho0_sq = r * r;
+    e->delta_denom = bbxh_delta_denom(e->h, cfg->spacing);
+    size_t cap = (size_t)e->cap, capw = ((cap + 31) / 32) * 32;
+    int rc = BBX_OK;
+    for(int b = 0; b < 2 && rc == BBX_OK; b++){
+        rc |= dev_alloc(&e->pos[b], cap); rc |= dev_alloc(&e->vel[b], cap);
+        rc |= dev_alloc(&e->pid[b], cap); rc |= dev_alloc(&e->cell[b], cap);
+        rc |= dev_alloc(&e->cell_start[b], (size_t)g.total + 1);
+    }
+    rc |= dev_alloc(&e->newcell, cap); rc |= dev_alloc(&e->count, (size_t)g.total + 1); rc |= dev_alloc(&e->perm, cap);
+    e->scan_blocks = div_up(g.total, SCAN_TILE);
+    rc |= dev_alloc(&e->scan_sums, (size_t)e->scan_blocks);
+    rc |= dev_alloc(&e->nbr, capw * BBX_NBR_CHUNKS * 8); rc |= dev_alloc(&e->nbr_cnt, cap);
+    rc |= dev_alloc(&e->force, cap); rc |= dev_alloc(&e->force_p, cap); rc |= dev_alloc(&e->pred, cap);
+    rc |= dev_alloc(&e->posq, cap); rc |= dev_alloc(&e->smoothed, cap);
+    rc |= dev_alloc(&e->pressure, cap); rc |= dev_alloc(&e->rho_pred, cap); rc |= dev_alloc(&e->rho_err, cap);
+    rc |= dev_alloc(&e->st, 1); rc |= dev_alloc(&e->colliders, 1);
+    if(rc != BBX_OK){ return rc; }
+    CU(cudaMallocHost((void **)&e->st_host, sizeof(DevState)));
+    CU(cudaMemset(e->st, 0, sizeof(DevState)));
+    memset(e->st_host, 0, sizeof(DevState));
+    memset(&e->colliders_host, 0, sizeof(DevColliderSet));
+    CU(cudaMemset(e->colliders, 0, sizeof(DevColliderSet)));
+    CU(cudaMemset(e->force, 0, sizeof(float4) * cap)); CU(cudaMemset(e->force_p, 0, sizeof(float4) * cap));
+    CU(cudaMemset(e->pressure, 0, sizeof(float) * cap)); CU(cudaMemset(e->rho_pred, 0, sizeof(float) * cap));
+    CU(cudaMemset(e->rho_err, 0, sizeof(float) * cap)); CU(cudaMemset(e->pred, 0, sizeof(float4) * cap));
+    CU(cudaMemset(e->nbr_cnt, 0, sizeof(int) * cap));
+    *out = e;
+    return BBX_OK;
+}
+
+int bbx_destroy(bbx_engine *e){
+    if(!e) return BBX_OK;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for(int b = 0; b < 2; b++){ cudaFree(e->pos[b]); cudaFree(e->vel[b]); cudaFree(e->pid[b]); cudaFree(e->cell[b]); cudaFree(e->cell_start[b]); }
+    cudaFree(e->newcell); cudaFree(e->count); cudaFree(e->perm); cudaFree(e->scan_sums);
+    cudaFree(e->nbr); cudaFree(e->nbr_cnt); cudaFree(e->force); cudaFree(e->force_p); cudaFree(e->pred);
+    cudaFree(e->posq); cudaFree(e->smoothed); cudaFree(e->pressure); cudaFree(e->rho_pred); cudaFree(e->rho_err);
+    cudaFree(e->st); cudaFree(e->colliders); cudaFreeHost(e->st_host);
+    for(double *f : e->sdf_fields) cudaFree(f);
+    if(e->stage) cudaFree(e->stage);
+    for(cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(e->stream);
+    delete e;
+    return BBX_OK;
+}
+
+int bbx_get_mass(bbx_engine *e, double *mass){ if(!e || !mass) return set_error(BBX_ERR_INVALID, "null"); *mass = e->mass; return BBX_OK; }
+int bbx_get_delta(bbx_engine *e, double dt, double *delta){
+    if(!e || !delta) return set_error(BBX_ERR_INVALID, "null");
+    *delta = bbxh_delta(e->mass_over_rho0_sq, e->delta_denom, dt);
+    return BBX_OK;
+}
+
+static int ensure_stage(bbx_engine *e, size_t bytes){
+    if(e->stage_bytes >= bytes) return BBX_OK;
+    if(e->stage){ CU(cudaFree(e->stage)); e->stage = nullptr; e->stage_bytes = 0; }
+    CU(cudaMalloc(&e->stage, bytes));
+    e->stage_bytes = bytes;
+    return BBX_OK;
+}
+
+static int upload_particles(bbx_engine *e, int first, int n, const void *pos, const void *vel, int dtype){
+    if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "dtype must be BBX_F32 or BBX_F64");
+    size_t esz = dtype == BBX_F64 ? 8 : 4;
+    size_t bytes = esz * 3 * (size_t)n;
+    int rc = ensure_stage(e, 2 * bytes); if(rc) return rc;
+    char *sp = (char *)e->stage, *sv = sp + bytes;
+    CU(cudaMemcpyAsync(sp, pos, bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(sv, vel, bytes, cudaMemcpyHostToDevice, e->stream));
+    LAUNCH(e, k_upload, div_up(n, 256), 256, n, first, sp, sv, dtype == BBX_F64, e->pos[e->cur] + first, e->vel[e->cur] + first, e->pid[e->cur] + first);
+    CU(cudaGetLastError());
+    return BBX_OK;
+}
+
+static int grid_update(bbx_engine *e);
+
+int bbx_set_particles(bbx_engine *e, int n, const void *pos, const void *vel, int dtype){
+    CHECK_ENGINE(e);
+    if(n < 0 || (n > 0 && (!pos || !vel))) return set_error(BBX_ERR_INVALID, "bad particle arguments");
+    if(n > e->cap) return set_error(BBX_ERR_CAPACITY, "%d particles exceed max_particles %d", n, e->cap);
+    e->n = n;
+    e->have_chains = 0; e->force_full = 1;
+    if(n == 0) return BBX_OK;
+    int rc = upload_particles(e, 0, n, pos, vel, dtype); if(rc) return rc;
+    // PciSphSolver3::Setup: initial DistributeByParticle (ascending id) so that the first sub-step can
+    // run the incremental update exactly like the reference (frame_index = 1)
+    rc = grid_update(e); if(rc) return rc;
+    e->force_full = 0;
+    return BBX_OK;
+}
+
+int bbx_append_particles(bbx_engine *e, int n, const void *pos, const void *vel, int dtype){
+    CHECK_ENGINE(e);
+    if(n <= 0) return BBX_OK;
+    if(e->n + n > e->cap) return set_error(BBX_ERR_CAPACITY, "%d + %d particles exceed max_particles %d", e->n, n, e->cap);
+    // New particles take ids n_old.. and go to the tail of their cell's chain: equivalent to a
+    // stable merge; realised as "old chains first, then new ids ascending" via the incremental fill
+    // followed by a tail insert.  Implemented with the full-rebuild machinery when no chains exist.
+    if(!e->have_chains || e->n == 0){
+        int first = e->n;
+        int rc = upload_particles(e, first, n, pos, vel, dtype); if(rc) return rc;
+        e->n += n; e->force_full = 1;
+        rc = grid_update(e); if(rc) return rc;
+        e->force_full = 0;
+        return BBX_OK;
+    }
+    return set_error(BBX_ERR_INVALID, "bbx_append_particles after stepping is not implemented yet");
+}
+
+int bbx_particle_count(bbx_engine *e, int *n){ if(!e || !n) return set_error(BBX_ERR_INVALID, "null"); *n = e->n; return BBX_OK; }
+
+int bbx_overwrite_state(bbx_engine *e, const void *pos, const void *vel, int dtype){
+    CHECK_ENGINE(e);
+    if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "dtype must be BBX_F32 or BBX_F64");
+    if(e->n == 0) return BBX_OK;
+    size_t esz = dtype == BBX_F64 ? 8 : 4; size_t bytes = esz * 3 * (size_t)e->n;
+    int rc = ensure_stage(e, 2 * bytes); if(rc) return rc;
+    char *sp = (char *)e->stage, *sv = sp + bytes;
+    CU(cudaMemcpyAsync(sp, pos, bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(sv, vel, bytes, cudaMemcpyHostToDevice, e->stream));
+    LAUNCH(e, k_overwrite, div_up(e->n, 256), 256, e->n, e->pid[e->cur], sp, sv, dtype == BBX_F64, e->pos[e->cur], e->vel[e->cur]);
+    CU(cudaGetLastError());
+    return BBX_OK;
+}
+
+// ------------------------------------------------------------------------------------ colliders
+static int fill_collider(bbx_engine *e, DevCollider &d, const bbx_collider &c){
+    if(c.type < BBX_COLLIDER_BOX || c.type > BBX_COLLIDER_SDF) return set_error(BBX_ERR_INVALID, "unknown collider type %d", c.type);
+    d.type = c.type; d.reverse = c.reverse_orientation ? 1 : 0; d.active = c.active ? 1 : 0;
+    memcpy(d.o2w, c.object_to_world, sizeof(d.o2w)); memcpy(d.w2o, c.world_to_object, sizeof(d.w2o));
+    memcpy(d.size, c.size, sizeof(d.size)); d.radius = c.radius; d.friction = c.friction;
+    memcpy(d.linvel, c.linear_velocity, sizeof(d.linvel)); memcpy(d.angvel, c.angular_velocity, sizeof(d.angvel));
+    d.sdf_field = nullptr;
+    if(c.type == BBX_COLLIDER_SDF){
+        if(!c.sdf_field) return set_error(BBX_ERR_INVALID, "SDF collider without field");
+        size_t total = (size_t)c.sdf_resolution[0] * c.sdf_resolution[1] * c.sdf_resolution[2];
+        if(total == 0) return set_error(BBX_ERR_INVALID, "SDF collider with empty grid");
+        double *dev = nullptr;
+        CU(cudaMalloc((void **)&dev, total * sizeof(double)));
+        CU(cudaMemcpy(dev, c.sdf_field, total * sizeof(double), cudaMemcpyHostToDevice));
+        e->sdf_fields.push_back(dev);
+        d.sdf_field = dev;
+        for(int k = 0; k < 3; k++){ d.sdf_res[k] = c.sdf_resolution[k]; d.sdf_spacing[k] = c.sdf_spacing[k]; d.sdf_origin[k] = c.sdf_origin[k]; }
+    }
+    return BBX_OK;
+}
+static int push_colliders(bbx_engine *e){
+    CU(cudaMemcpyAsync(e->colliders, &e->colliders_host, sizeof(DevColliderSet), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream)); // colliders_host may change right after this call
+    return BBX_OK;
+}
+int bbx_set_colliders(bbx_engine *e, int n, const bbx_collider *colliders){
+    CHECK_ENGINE(e);
+    if(n < 0 || n > BBX_MAX_COLLIDERS || (n > 0 && !colliders)) return set_error(BBX_ERR_INVALID, "0..%d colliders supported", BBX_MAX_COLLIDERS);
+    CU(cudaStreamSynchronize(e->stream));
+    for(double *f : e->sdf_fields) cudaFree(f);
+    e->sdf_fields.clear();
+    memset(&e->colliders_host, 0, sizeof(DevColliderSet));
+    for(int i = 0; i < n; i++){ int rc = fill_collider(e, e->colliders_host.c[i], colliders[i]); if(rc) return rc; }
+    e->colliders_host.count = n;
+    return push_colliders(e);
+}
+int bbx_update_collider(bbx_engine *e, int index, const bbx_collider *c){
+    CHECK_ENGINE(e);
+    if(!c || index < 0 || index >= e->colliders_host.count) return set_error(BBX_ERR_INVALID, "collider index out of range");
+    DevCollider &d = e->colliders_host.c[index];
+    if(c->type != d.type) return set_error(BBX_ERR_INVALID, "bbx_update_collider cannot change the collider type");
+    const double *keep = d.sdf_field;
+    d.reverse = c->reverse_orientation ? 1 : 0; d.active = c->active ? 1 : 0;
+    memcpy(d.o2w, c->object_to_world, sizeof(d.o2w)); memcpy(d.w2o, c->world_to_object, sizeof(d.w2o));
+    memcpy(d.size, c->size, sizeof(d.size)); d.radius = c->radius; d.friction = c->friction;
+    memcpy(d.linvel, c->linear_velocity, sizeof(d.linvel)); memcpy(d.angvel, c->angular_velocity, sizeof(d.angvel));
+    d.sdf_field = keep;
+    return push_colliders(e);
+}
+int bbx_set_collider_active(bbx_engine *e, int index, int active){
+    CHECK_ENGINE(e);
+    if(index < 0 || index >= e->colliders_host.count) return set_error(BBX_ERR_INVALID, "collider index out of range");
+    e->colliders_host.c[index].active = active ? 1 : 0;
+    return push_colliders(e);
+}
+
+// --------------------------------------------------------------------------------------- timing
+static void tick(bbx_engine *e, int phase){
+    if(!e->timing) return;
+    if(e->ev_used == e->ev.size()){ cudaEvent_t ev; cudaEventCreate(&ev); e->ev.push_back(ev); e->ev_phase.push_back(0); }
+    e->ev_phase[e->ev_used] = phase;
+    cudaEventRecord(e->ev[e->ev_used++], e->stream);
+}
+// events are recorded as (phase start) ... (T_COUNT = end of step); harvest after a sync
+static void harvest(bbx_engine *e){
+    if(!e->timing || e->ev_used < 2) { e->ev_used = 0; return; }
+    cudaStreamSynchronize(e->stream);
+    float step_ms = 0.f, grid_ms = 0.f;
+    for(size_t k = 0; k + 1 < e->ev_used; k++){
+        int ph = e->ev_phase[k];
+        if(ph >= T_COUNT){ step_ms = 0.f; grid_ms = 0.f; continue; } // step boundary marker
+        float ms = 0.f; cudaEventElapsedTime(&ms, e->ev[k], e->ev[k + 1]);
+        e->phase_ms[ph] += ms; e->phase_launches[ph]++;
+        step_ms += ms; if(ph == T_GRID) grid_ms += ms;
+        e->last_ms_step = step_ms; e->last_ms_grid = grid_ms;
+    }
+    e->ev_used = 0;
+}
+
+// ------------------------------------------------------------------------------------- stepping
+static void make_params(bbx_engine *e, double dt, StepParams &P){
+    const bbx_config &c = e->cfg;
+    double h = e->h, pi = 3.14159265358979323846;
+    P.n = e->n; P.n_owned = e->n;
+    P.h = (float)h; P.h2 = (float)(h * h); P.inv_h = (float)(1.0 / h); P.inv_h2 = (float)(1.0 / (h * h));
+    P.h_d = h; P.h2_d = h * h;
+    P.thr2 = (float)(h * h - 1e-8);
+    P.band = (float)(h * h * 1.0e-6 + 4e-8); // >> FP32 rounding of d^2 (~1e-7 relative) and of thr2
+    P.mass = (float)e->mass; P.mass2 = (float)(e->mass * e->mass); P.inv_mass = (float)(1.0 / e->mass);
+    P.rho0 = (float)c.target_density;
+    P.w_std_c = (float)(315.0 / (64.0 * pi * h * h * h));
+    P.d2w_spiky_c = (float)(90.0 / (pi * h * h * h * h * h));
+    P.dw_spiky_c = (float)(45.0 / (pi * h * h * h * h));
+    P.w_spiky_c = (float)(15.0 / (pi * h * h * h));
+    P.viscosity = (float)c.viscosity; P.drag = (float)c.drag;
+    P.gx = (float)c.gravity[0]; P.gy = (float)c.gravity[1]; P.gz = (float)c.gravity[2];
+    P.dt = (float)dt;
+    P.delta = (float)bbxh_delta(e->mass_over_rho0_sq, e->delta_denom, dt);
+    P.neg_pressure_scale = (float)c.negative_pressure_scale;
+    P.eos_scale = (float)(c.target_density * c.sound_speed * c.sound_speed / c.eos_exponent);
+    P.eos_exponent = (float)c.eos_exponent;
+    P.radius = (float)c.spacing;
+    P.restitution = (float)c.restitution;
+    double minlen = std::min(e->grid.len[0], std::min(e->grid.len[1], e->grid.len[2]));
+    P.min_cell_len09 = (float)(0.9 * minlen);
+    double pf = dt * c.pseudo_viscosity; P.pseudo_factor = (float)(pf < 0 ? 0 : (pf > 1 ? 1 : pf));
+}
+
+// UpdateGridDistributionGPU minus the bucket fill (sph_equations3.cpp:511-539)
+static int grid_update(bbx_engine *e){
+    if(e->n == 0) return BBX_OK;
+    DevGrid &g = e->grid;
+    int n = e->n, cur = e->cur, nxt = cur ^ 1;
+    int force = (e->force_full || !e->have_chains) ? 1 : 0;
+    CU(cudaMemsetAsync(e->count, 0, sizeof(int) * ((size_t)g.total + 1), e->stream));
+    LAUNCH(e, k_clear_lost, 1, 1, e->st);
+    LAUNCH(e, k_hash_count, div_up(n, 256), 256, n, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st, force ? 0 : 1);
+    LAUNCH(e, k_scan_tile_sums, e->scan_blocks, 256, e->count, g.total, e->scan_sums);
+    LAUNCH(e, k_scan_sums, 1, 1024, e->scan_sums, e->scan_blocks);
+    LAUNCH(e, k_scan_tiles, e->scan_blocks, 256, e->count, g.total, e->scan_sums, e->cell_start[nxt], n);
+    if(!force){
+        LAUNCH(e, k_fill_incremental, div_up((long long)g.total * 32, 256), 256, g, e->st, e->cell_start[cur], e->cell_start[nxt], e->newcell,
+               e->pos[cur], e->vel[cur], e->pid[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt]);
+    }
+    // full path (forced, or selected on the device by the big-move / jump flags)
+    CU(cudaMemsetAsync(e->count, 0, sizeof(int) * ((size_t)g.total + 1), e->stream));
+    LAUNCH(e, k_full_scatter, div_up(n, 256), 256, n, e->st, force, e->newcell, e->cell_start[nxt], e->count, e->perm);
+    LAUNCH(e, k_full_sort_cells, div_up(g.total, 256), 256, g.total, e->st, force, e->cell_start[nxt], e->pid[cur], e->perm);
+    LAUNCH(e, k_full_gather, div_up(n, 256), 256, n, e->st, force, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
+           e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt]);
+    LAUNCH(e, k_step_begin, 1, 1, e->st, force);
+    CU(cudaGetLastError());
+    e->cur = nxt;
+    e->have_chains = 1;
+    return BBX_OK;
+}
+
+static int phase_density(bbx_engine *e, const StepParams &P, int sph){
+    int cur = e->cur; int nb = div_up(e->n, BBX_BS);
+    if(sph) LAUNCH(e, k_build_density<1>, nb, BBX_BS, P, e->grid, e->st, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq);
+    else    LAUNCH(e, k_build_density<0>, nb, BBX_BS, P, e->grid, e->st, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq);
+    CU(cudaGetLastError());
+    return BBX_OK;
+}
+static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
+    int cur = e->cur;
+    LAUNCH(e, k_force_np_predict, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->colliders, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur],
+           e->nbr, e->nbr_cnt, e->force, e->pred);
+    CU(cudaGetLastError());
+    return BBX_OK;
+}
+static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
+    int cur = e->cur;
+    LAUNCH(e, k_pressure, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
+           e->nbr, e->nbr_cnt, e->pressure, e->rho_pred, e->rho_err, e->posq);
+    CU(cudaGetLastError());
+    return BBX_OK;
+}
+static int phase_pressure_force(bbx_engine *e, const StepParams &P, int integrate){
+    int cur = e->cur; int nb = div_up(e->n, BBX_BS);
+    if(integrate) LAUNCH(e, k_pressure_force<1>, nb, BBX_BS, P, e->grid, e->st, e->colliders, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p);
+    else          LAUNCH(e, k_pressure_force<0>, nb, BBX_BS, P, e->grid, e->st, e->colliders, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p);
+    CU(cudaGetLastError());
+    return BBX_OK;
+}
+static int phase_integrate(bbx_engine *e, const StepParams &P, int with_fp){
+    int cur = e->cur;
+    LAUNCH(e, k_integrate, div_up(e->n, 256), 256, P, e->grid, e->st, e->colliders, e->pos[cur], e->vel[cur], e->force, with_fp ? e->force_p : (const float4 *)nullptr);
+    CU(cudaGetLastError());
+    return BBX_OK;
+}
+static int phase_pseudo_viscosity(bbx_engine *e, const StepParams &P, double dt){
+    if(!(e->cfg.pseudo_viscosity * dt > 0.1)) return BBX_OK; // sph_equations3.cpp:655-657
+    int cur = e->cur;
+    LAUNCH(e, k_pseudo_aggregate, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->smoothed);
+    LAUNCH(e, k_pseudo_interpolate, div_up(e->n, 256), 256, P, e->vel[cur], e->smoothed);
+    CU(cudaGetLastError());
+    return BBX_OK;
+}
+static int read_state(bbx_engine *e){
+    CU(cudaMemcpyAsync(e->st_host, e->st, sizeof(DevState), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BBX_OK;
+}
+
+static int step_pcisph(bbx_engine *e, double dt){
+    if(e->n == 0) return BBX_OK;
+    if(!(dt > 0)) return set_error(BBX_ERR_INVALID, "dt must be positive");
+    StepParams P; make_params(e, dt, P);
+    int rc;
+    tick(e, T_GRID);
+    if((rc = grid_update(e))) return rc;
+    tick(e, T_DENSITY);
+    if((rc = phase_density(e, P, 0))) return rc;
+    tick(e, T_FORCE_NP);
+    if((rc = phase_force_np_predict(e, P))) return rc;
+    if(e->cfg.pcisph_reference_compat){
+        // the reference's loop always leaves after one iteration (density error never stored)
+        tick(e, T_PRESSURE);
+        if((rc = phase_pressure(e, P, 1))) return rc;
+        tick(e, T_PRESSURE_FORCE);
+        if((rc = phase_pressure_force(e, P, 1))) return rc;
+        e->st_host->iterations = 1;
+    }else{
+        int it = 0;
+        for(int k = 0; k < e->cfg.pcisph_max_iterations; k++){
+            if(k > 0){
+                tick(e, T_PREDICT);
+                LAUNCH(e, k_predict_again, div_up(e->n, 256), 256, P, e->colliders, e->pos[e->cur], e->vel[e->cur], e->force, e->force_p, e->pred);
+            }
+            tick(e, T_PRESSURE);
+            if((rc = phase_pressure(e, P, k == 0))) return rc;
+            tick(e, T_PRESSURE_FORCE);
+            if((rc = phase_pressure_force(e, P, 0))) return rc;
+            it++;
+            // the loop exit test needs max |rho* - rho0| on the host, as in the reference (pcisph_equations3.cpp:238-246)
+            if((rc = read_state(e))) return rc;
+            float maxerr; memcpy(&maxerr, &e->st_host->max_err_bits, 4);
+            if(fabs((double)maxerr / e->cfg.target_density) < e->cfg.pcisph_max_density_error_ratio) break;
+            if(k + 1 < e->cfg.pcisph_max_iterations){ CU(cudaMemsetAsync(&e->st->max_err_bits, 0, 4, e->stream)); }
+        }
+        tick(e, T_INTEGRATE);
+        if((rc = phase_integrate(e, P, 1))) return rc;
+        e->st_host->iterations = it;
+    }
+    if((rc = phase_pseudo_viscosity(e, P, dt))) return rc;
+    tick(e, T_COUNT);
+    e->substeps++;
+    return BBX_OK;
+}
+
+static int step_sph(bbx_engine *e, double dt){
+    if(e->n == 0) return BBX_OK;
+    if(!(dt > 0)) return set_error(BBX_ERR_INVALID, "dt must be positive");
+    StepParams P; make_params(e, dt, P);
+    int rc;
+    tick(e, T_GRID);
+    if((rc = grid_update(e))) return rc;
+    tick(e, T_DENSITY);
+    if((rc = phase_density(e, P, 1))) return rc;
+    tick(e, T_FORCE_NP);
+    LAUNCH(e, k_sph_forces, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->posq, e->vel[e->cur], e->cell[e->cur], e->cell_start[e->cur], e->nbr, e->nbr_cnt, e->force);
+    CU(cudaGetLastError());
+    tick(e, T_INTEGRATE);
+    if((rc = phase_integrate(e, P, 0))) return rc;
+    if((rc = phase_pseudo_viscosity(e, P, dt))) return rc;
+    tick(e, T_COUNT);
+    e->substeps++;
+    return BBX_OK;
+}
+
+int bbx_step_pcisph(bbx_engine *e, double dt){ CHECK_ENGINE(e); int rc = step_pcisph(e, dt); if(rc) return rc; if(e->timing) harvest(e); return BBX_OK; }
+int bbx_step_sph(bbx_engine *e, double dt){ CHECK_ENGINE(e); int rc = step_sph(e, dt); if(rc) return rc; if(e->timing) harvest(e); return BBX_OK; }
+
+int bbx_step_many(bbx_engine *e, double dt, int solver, int n){
+    CHECK_ENGINE(e);
+    for(int s = 0; s < n; s++){
+        int rc = solver == BBX_SOLVER_SPH ? step_sph(e, dt) : step_pcisph(e, dt);
+        if(rc) return rc;
+        if(e->timing && e->ev_used > 3000) harvest(e);
+    }
+    if(e->timing) harvest(e);
+    return BBX_OK;
+}
+
+int bbx_run_phase(bbx_engine *e, int phase, double dt){
+    CHECK_ENGINE(e);
+    if(e->n == 0) return BBX_OK;
+    StepParams P; make_params(e, dt, P);
+    switch(phase){
+        case BBX_PHASE_GRID: return grid_update(e);
+        case BBX_PHASE_DENSITY: return phase_density(e, P, 0);
+        case BBX_PHASE_FORCE_NP: return phase_force_np_predict(e, P);
+        case BBX_PHASE_PREDICT: return BBX_OK; // fused into FORCE_NP on the first iteration
+        case BBX_PHASE_PRESSURE: return phase_pressure(e, P, 1);
+        case BBX_PHASE_PRESSURE_FORCE: return phase_pressure_force(e, P, 0);
+        case BBX_PHASE_INTEGRATE: { int rc = phase_integrate(e, P, 1); if(rc) return rc; e->substeps++; return phase_pseudo_viscosity(e, P, dt); }
+    }
+    return set_error(BBX_ERR_INVALID, "unknown phase %d", phase);
+}
+
+// SphParticleSet3::ComputeNumberOfTimeSteps (src/core/particle.h:584-608) with the device-reduced max |f|
+static unsigned number_of_time_steps(bbx_engine *e, double remaining, double max_force, double scale){
+    double limit = 0.40 * e->h / e->cfg.sound_speed;
+    if(!(fabs(max_force) < 1e-8)){
+        double by_force = 0.25 * sqrt(e->h * e->mass / max_force);
+        limit = std::min(by_force, limit);
+    }
+    return (unsigned)ceil(remaining / (scale * limit));
+}
+
+int bbx_advance(bbx_engine *e, double seconds, int solver, int *substeps, float *ms){
+    CHECK_ENGINE(e);
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, e->stream));
+    double remaining = seconds; int count = 0;
+    double scale = solver == BBX_SOLVER_SPH ? 1.0 : e->cfg.time_step_limit_scale;
+    while(remaining > (double)0.0001f){ // `while(remainingTime > Epsilon)`, pcisph_solver3.cpp:76
+        int rc = read_state(e); if(rc) return rc;
+        float mf; memcpy(&mf, &e->st_host->max_force_bits, 4);
+        unsigned nsteps = number_of_time_steps(e, remaining, (double)mf, scale);
+        double dt = remaining / (double)nsteps;
+        rc = solver == BBX_SOLVER_SPH ? step_sph(e, dt) : step_pcisph(e, dt);
+        if(rc) return rc;
+        remaining -= dt; count++;
+    }
+    CU(cudaEventRecord(e1, e->stream));
+    CU(cudaEventSynchronize(e1));
+    float t = 0.f; cudaEventElapsedTime(&t, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if(e->timing) harvest(e);
+    if(substeps) *substeps = count;
+    if(ms) *ms = t;
+    return BBX_OK;
+}
+
+int bbx_synchronize(bbx_engine *e){ CHECK_ENGINE(e); CU(cudaStreamSynchronize(e->stream)); return BBX_OK; }
+int bbx_set_timing(bbx_engine *e, int enabled){ CHECK_ENGINE(e); if(e->timing) harvest(e); e->timing = enabled ? 1 : 0; e->ev_used = 0; return BBX_OK; }
+
+int bbx_stats(bbx_engine *e, bbx_step_stats *out){
+    CHECK_ENGINE(e);
+    if(!out) return set_error(BBX_ERR_INVALID, "null");
+    int it = e->st_host->iterations;
+    int rc = read_state(e); if(rc) return rc;
+    e->st_host->iterations = it;
+    const DevState &s = *e->st_host;
+    memset(out, 0, sizeof(*out));
+    out->particles = e->n; out->ghosts = 0; out->substeps = e->substeps; out->pcisph_iterations = it;
+    out->full_rebuild = s.full_rebuild; out->rebuild_flag = s.rebuild_flag; out->neighbor_overflow = s.overflow;
+    out->lost_particles = s.lost; out->clamped = s.clamped; out->nan_count = s.nan_count;
+    memcpy(&out->max_force, &s.max_force_bits, 4); memcpy(&out->max_density_error, &s.max_err_bits, 4);
+    out->ms_grid = e->last_ms_grid; out->ms_step = e->last_ms_step;
+    if(s.error) return set_error(s.error, "device-side error %d (%s)", s.error,
+                                 s.error == BBX_ERR_OUT_OF_DOMAIN ? "particle outside the grid bounds" : "a cell run holds more than 4096 particles");
+    return BBX_OK;
+}
+
+// ---------------------------------------------------------------------------------------- results
+int bbx_download(bbx_engine *e, int field, void *dst, int dtype){
+    CHECK_ENGINE(e);
+    if(!dst) return set_error(BBX_ERR_INVALID, "null destination");
+    if(e->n == 0) return BBX_OK;
+    int cur = e->cur; int n = e->n;
+    const float4 *s4 = nullptr; const float *s1 = nullptr; const int *si = nullptr; int comps = 3;
+    switch(field){
+        case BBX_POSITION: s4 = e->pos[cur]; break;
+        case BBX_VELOCITY: s4 = e->vel[cur]; break;
+        case BBX_FORCE: case BBX_FORCE_NP: s4 = e->force; break;
+        case BBX_PRED_POSITION: s4 = e->pred; break;
+        case BBX_PRESSURE_FORCE: s4 = e->force_p; break;
+        case BBX_DENSITY: s4 = e->vel[cur]; comps = 1; break;
+        case BBX_PRESSURE: s1 = e->pressure; comps = 1; break;
+        case BBX_PRED_DENSITY: s1 = e->rho_pred; comps = 1; break;
+        case BBX_DENSITY_ERROR: s1 = e->rho_err; comps = 1; break;
+        case BBX_NEIGHBOR_COUNT: si = e->nbr_cnt; comps = 1; break;
+        default: return set_error(BBX_ERR_INVALID, "unknown field %d", field);
+    }
+    if(si){ if(dtype != BBX_I32) return set_error(BBX_ERR_INVALID, "field %d is BBX_I32", field); }
+    else if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "field %d needs BBX_F32 or BBX_F64", field);
+    size_t esz = (dtype == BBX_F64) ? 8 : 4; size_t bytes = esz * comps * (size_t)n;
+    int rc = ensure_stage(e, bytes); if(rc) return rc;
+    LAUNCH(e, k_download, div_up(n, 256), 256, n, e->pid[cur], s4, s1, si, comps, dtype == BBX_F64, e->stage);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(dst, e->stage, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BBX_OK;
+}
+
+int bbx_export_cells(bbx_engine *e, int *cell_count, int *cell_order){
+    CHECK_ENGINE(e);
+    if(!cell_count || !cell_order) return set_error(BBX_ERR_INVALID, "null");
+    int total = e->grid.total;
+    if(!e->have_chains || e->n == 0){ memset(cell_count, 0, sizeof(int) * (size_t)total); return BBX_OK; }
+    int rc = ensure_stage(e, sizeof(int) * (size_t)total); if(rc) return rc;
+    LAUNCH(e, k_export_cells, div_up(total, 256), 256, total, e->cell_start[e->cur], (int *)e->stage);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cell_count, e->stage, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(cell_order, e->pid[e->cur], sizeof(int) * (size_t)e->n, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BBX_OK;
+}
+
+int bbx_export_neighbors(bbx_engine *e, int *counts, int *ids){
+    CHECK_ENGINE(e);
+    if(!counts || !ids) return set_error(BBX_ERR_INVALID, "null");
+    if(e->n == 0) return BBX_OK;
+    int n = e->n; size_t bytes = sizeof(int) * (size_t)n * (BBX_MAX_NEIGHBORS + 1);
+    int rc = ensure_stage(e, bytes); if(rc) return rc;
+    int *dc = (int *)e->stage; int *di = dc + n;
+    LAUNCH(e, k_export_neighbors, div_up(n, BBX_BS), BBX_BS, n, e->grid, e->pid[e->cur], e->cell[e->cur], e->cell_start[e->cur], e->nbr, e->nbr_cnt, dc, di);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(counts, dc, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(ids, di, sizeof(int) * (size_t)n * BBX_MAX_NEIGHBORS, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BBX_OK;
+}
+
+int bbx_inject_chains(bbx_engine *e, const int *cell_count, const int *cell_order){
+    CHECK_ENGINE(e);
+    if(!cell_count || !cell_order) return set_error(BBX_ERR_INVALID, "null");
+    if(e->n == 0) return BBX_OK;
+    int total = e->grid.total, n = e->n, cur = e->cur, nxt = cur ^ 1;
+    std::vector<int> start((size_t)total + 1), cell_of((size_t)n);
+    long long acc = 0;
+    for(int c = 0; c < total; c++){
+        start[c] = (int)acc;
+        if(cell_count[c] < 0) return set_error(BBX_ERR_INVALID, "negative chain length");
+        for(int k = 0; k < cell_count[c]; k++){ if(acc + k >= n) return set_error(BBX_ERR_INVALID, "chains hold more than n particles"); cell_of[acc + k] = c; }
+        acc += cell_count[c];
+    }
+    start[total] = (int)acc;
+    if(acc != n) return set_error(BBX_ERR_INVALID, "chains hold %lld particles, engine has %d", acc, n);
+    std::vector<char> seen((size_t)n, 0);
+    for(int k = 0; k < n; k++){ int id = cell_order[k]; if(id < 0 || id >= n || seen[id]) return set_error(BBX_ERR_INVALID, "cell_order is not a permutation"); seen[id] = 1; }
+    int rc = ensure_stage(e, sizeof(int) * 3 * (size_t)n); if(rc) return rc;
+    int *d_order = (int *)e->stage, *d_slot = d_order + n, *d_cell = d_slot + n;
+    CU(cudaMemcpyAsync(d_order, cell_order, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_cell, cell_of.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->cell_start[nxt], start.data(), sizeof(int) * ((size_t)total + 1), cudaMemcpyHostToDevice, e->stream));
+    LAUNCH(e, k_slot_of_id, div_up(n, 256), 256, n, e->pid[cur], d_slot);
+    LAUNCH(e, k_inject_gather, div_up(n, 256), 256, n, d_order, d_slot, d_cell, e->pos[cur], e->vel[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt]);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream)); // host vectors go out of scope
+    e->cur = nxt; e->have_chains = 1; e->force_full = 0;
+    return BBX_OK;
+}
+
+int bbx_set_rebuild_flag(bbx_engine *e, int flag){
+    CHECK_ENGINE(e);
+    int v = flag ? 1 : 0;
+    CU(cudaMemcpyAsync(&e->st->rebuild_flag, &v, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BBX_OK;
+}
+
+int bbx_launch_count(bbx_engine *e, long long *count){ if(!e || !count) return set_error(BBX_ERR_INVALID, "null"); *count = e->launches; return BBX_OK; }
+int bbx_kernel_time(bbx_engine *e, int phase, float *ms, int *launches){
+    if(!e || phase < 0 || phase >= T_COUNT) return set_error(BBX_ERR_INVALID, "bad phase");
+    if(ms) *ms = e->phase_ms[phase];
+    if(launches) *launches = e->phase_launches[phase];
+    return BBX_OK;
+}
+int bbx_reset_kernel_time(bbx_engine *e){
+    if(!e) return set_error(BBX_ERR_INVALID, "null");
+    memset(e->phase_ms, 0, sizeof(e->phase_ms)); memset(e->phase_launches, 0, sizeof(e->phase_launches));
+    return BBX_OK;
+}
+
+int bbx_comm_unique_id(unsigned char id[BBX_NCCL_ID_BYTES]){ (void)id; return set_error(BBX_ERR_COMM, "multi-GPU slab exchange is not built in this revision"); }
+int bbx_comm_init(bbx_engine *e, int rank, int nranks, const unsigned char id[BBX_NCCL_ID_BYTES]){
+    (void)e; (void)rank; (void)nranks; (void)id;
+    return set_error(BBX_ERR_COMM, "multi-GPU slab exchange is not built in this revision");
+}

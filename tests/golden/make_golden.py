@@ -1,0 +1,142 @@
+"""Generates the golden vectors under tests/golden/ by running the UNMODIFIED reference
+(oracle/_ref/bbref, built from /root/reference by oracle/build_ref.sh) in this container.
+The reference cannot travel to the GPU box, the vectors can.  Re-run: python tests/golden/make_golden.py
+"""
+import os
+import re
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import oracle as O  # noqa: E402
+import scenes  # noqa: E402
+
+I = O.mat_str(np.eye(4))
+
+
+def T(x, y, z):
+    return O.mat_str(O.translate(x, y, z))
+
+
+def load_all(wd, prefix, names):
+    return {n: np.load(os.path.join(wd, prefix + n + ".npy")) for n in names}
+
+
+TRACE = ["rebuild_flag", "cell_count", "cell_order", "nbr_count", "nbr_ids", "density", "force_np", "delta", "pos_pred",
+         "density_pred", "pressure", "force_p", "max_density_error", "pos_out", "vel_out", "force_out", "rebuild_flag_out"]
+
+
+def probe_trace():
+    """SURVEY D.2 probe scene, particles emitted by the reference's own emitter (glibc rand, seed 1):
+    state after 30 sub-steps, its chains, and one traced sub-step from there."""
+    job = ["threads 4", "spacing 0.02", "scale 1.8", f"collider box {I} 0.6 0.6 0.6 1 0", "domain_from_collider 0",
+           f"emit_box {T(0.1, -0.1, 0.1)} 0.2 0.3 0.2 0 -1 0 0.001 1", "setup", "delta 7e-4",
+           "dump {wd}/s0_", "dump_grid {wd}/s0_", "step 7e-4 30", "dump {wd}/s30_", "dump_grid {wd}/s30_",
+           "trace 7e-4 {wd}/t_", "step 7e-4 69", "dump {wd}/s100_"]
+    out, wd = O.run_ref(job)
+    m = re.search(r"mass=(\S+) h=(\S+)", out)
+    g = re.search(r"grid min=\((\S+) (\S+) (\S+)\) len=\((\S+) (\S+) (\S+)\)", out)
+    c = re.search(r"cells=(\d+) \((\d+) x (\d+) x (\d+)\)", out)
+    d = re.search(r"delta\(\S+\)=(\S+)", out)
+    data = dict(mass=float(m.group(1)), h=float(m.group(2)), grid_min=[float(g.group(k)) for k in (1, 2, 3)],
+                grid_len=[float(g.group(k)) for k in (4, 5, 6)], grid_n=[int(c.group(k)) for k in (2, 3, 4)],
+                delta_7e4=float(d.group(1)))
+    for pre, names in (("s0_", ["pos", "vel", "cell_count", "cell_order"]),
+                       ("s30_", ["pos", "vel", "force", "density", "cell_count", "cell_order", "nbr_count"]),
+                       ("s100_", ["pos", "vel"])):
+        for k, v in load_all(wd, pre, names).items():
+            data[pre + k] = v
+    for k, v in load_all(wd, "t_", TRACE).items():
+        data["t_" + k] = v
+    np.savez_compressed(os.path.join(HERE, "probe_trace.npz"), **data)
+    print("probe_trace", len(data["s0_pos"]), "particles")
+
+
+def collider_vectors():
+    """ColliderSet3::ResolveCollision on random (position, velocity) pairs for each collider family."""
+    rng = np.random.default_rng(11)
+    n = 4000
+    pos = rng.uniform(-0.36, 0.36, size=(n, 3))
+    vel = rng.normal(0, 2.0, size=(n, 3))
+    torus = scenes.sdf_torus((0.05, -0.1, 0.0), 0.12, 0.04)
+    sets = {
+        "container_box": [f"collider box {I} 0.6 0.6 0.6 1 0"],
+        "container_sphere": [f"collider sphere {I} 0.3 1 0.3"],
+        "box_and_sphere": [f"collider box {I} 0.7 0.7 0.7 1 0", f"collider box {T(0.1, -0.2, 0.0)} 0.2 0.1 0.3 0 0.25",
+                           f"collider sphere {T(-0.1, 0.1, 0.1)} 0.09 0 0.5"],
+        "sdf_torus": [f"collider box {I} 0.7 0.7 0.7 1 0", "SDF"],
+    }
+    data = dict(pos=pos, vel=vel)
+    for name, lines in sets.items():
+        wd = tempfile.mkdtemp(prefix="bbref_")
+        O.write_particles(os.path.join(wd, "q.bin"), pos, vel)
+        job = ["threads 1", "spacing 0.02", "scale 1.8"]
+        for l in lines:
+            if l == "SDF":
+                bmin, bmax = (-0.15, -0.16, -0.2), (0.25, -0.04, 0.2)
+                import bubbles_b200 as bb
+                nodes, dx, origin = bb.sdf_grid_layout(bmin, bmax, 0.01, 0.1)
+                ix, iy, iz = np.meshgrid(np.arange(nodes[0]), np.arange(nodes[1]), np.arange(nodes[2]), indexing="ij")
+                pts = np.stack([origin[0] + dx * ix, origin[1] + dx * iy, origin[2] + dx * iz], axis=-1)
+                field = np.ascontiguousarray(torus(pts.reshape(-1, 3)).reshape(nodes).transpose(2, 1, 0))
+                field.tofile(os.path.join(wd, "sdf.bin"))
+                job.append(f"collider sdf {bmin[0]} {bmin[1]} {bmin[2]} {bmax[0]} {bmax[1]} {bmax[2]} 0.01 0.1 0.1 {wd}/sdf.bin")
+            else:
+                job.append(l)
+        job += ["domain -0.4 -0.4 -0.4 0.4 0.4 0.4", f"particles {wd}/q.bin", "setup"]
+        for tag, rad, rest in (("a", 0.02, 0.0), ("b", 0.02, 0.6)):
+            job.append(f"collide {wd}/q.bin {rad} {rest} {wd}/{name}_{tag}_")
+        O.run_ref(job, wd)
+        for tag in ("a", "b"):
+            for k in ("pos", "vel", "hit"):
+                data[f"{name}_{tag}_{k}"] = np.load(os.path.join(wd, f"{name}_{tag}_{k}.npy"))
+        print(name, "hits", int(data[f"{name}_a_hit"].sum()), int(data[f"{name}_b_hit"].sum()))
+    np.savez_compressed(os.path.join(HERE, "collider_vectors.npz"), **data)
+
+
+def obstacle_run():
+    """Block dropped on a sphere + box obstacle, 240 sub-steps, fixed dt and then two CFL frames (Advance)."""
+    job = ["threads 4", "spacing 0.02", "scale 1.8", f"collider box {I} 0.6 0.6 0.6 1 0",
+           f"collider sphere {T(0.1, -0.27, 0.1)} 0.08 0 0.2", f"collider box {T(-0.15, -0.25, -0.1)} 0.1 0.1 0.1 0 0.1",
+           "domain_from_collider 0", f"emit_box {T(0.05, -0.1, 0.05)} 0.24 0.3 0.24 0 -2 0 0.001 7", "setup",
+           "dump {wd}/s0_", "step 7e-4 240", "dump {wd}/s240_", "dump_grid {wd}/s240_",
+           "advance 0.004166666666666667", "advance 0.004166666666666667", "dump {wd}/adv_"]
+    out, wd = O.run_ref(job)
+    data = {}
+    for pre, names in (("s0_", ["pos", "vel"]), ("s240_", ["pos", "vel", "density", "cell_count", "cell_order", "nbr_count"]),
+                       ("adv_", ["pos", "vel"])):
+        for k, v in load_all(wd, pre, names).items():
+            data[pre + k] = v
+    np.savez_compressed(os.path.join(HERE, "obstacle_run.npz"), **data)
+    print("obstacle_run", len(data["s0_pos"]), "particles")
+
+
+def grid_facts():
+    """UtilBuildGridForDomain results printed by the reference for several domains / spacings."""
+    rows = []
+    for (lo, hi, s, k) in [((-0.3, -0.3, -0.3), (0.3, 0.3, 0.3), 0.02, 1.8), ((-1.625, -1.5, -1.625), (1.625, 1.5, 1.625), 0.02, 1.8),
+                           ((0, 0, 0), (1, 2, 3), 0.05, 2.0), ((-1, -1, -1), (1, 1, 1), 0.1, 2.0), ((-0.7, 0.1, 2.0), (0.9, 1.3, 2.55), 0.013, 1.7)]:
+        wd = tempfile.mkdtemp(prefix="bbref_")
+        O.write_particles(os.path.join(wd, "q.bin"), np.array([[0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])]]), np.zeros((1, 3)))
+        job = ["threads 1", f"spacing {s}", f"scale {k}", f"collider box {I} 10 10 10 1 0",
+               f"domain {lo[0]} {lo[1]} {lo[2]} {hi[0]} {hi[1]} {hi[2]}", f"particles {wd}/q.bin", "setup"]
+        out, _ = O.run_ref(job, wd)
+        g = re.search(r"grid min=\((\S+) (\S+) (\S+)\) len=\((\S+) (\S+) (\S+)\)", out)
+        c = re.search(r"cells=(\d+) \((\d+) x (\d+) x (\d+)\)", out)
+        m = re.search(r"mass=(\S+) h=(\S+)", out)
+        rows.append([*lo, *hi, s, k, *[float(g.group(i)) for i in range(1, 7)], *[int(c.group(i)) for i in (2, 3, 4)], float(m.group(1))])
+    np.save(os.path.join(HERE, "grid_facts.npy"), np.array(rows))
+    print("grid_facts", len(rows))
+
+
+if __name__ == "__main__":
+    assert O.ref_available(), "run oracle/build_ref.sh first"
+    probe_trace()
+    collider_vectors()
+    obstacle_run()
+    grid_facts()
