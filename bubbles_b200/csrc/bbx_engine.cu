@@ -52,7 +52,7 @@ struct bbx_engine {
     int timing;
     std::vector<cudaEvent_t> ev; size_t ev_used;
     std::vector<int> ev_phase;
-    float phase_ms[T_COUNT]; int phase_launches[T_COUNT];
+    float phase_ms[T_COUNT + 1]; int phase_launches[T_COUNT + 1]; // [T_COUNT] = gaps between sub-steps
     float last_ms_grid, last_ms_step;
     int force_full; // next grid update must be a full rebuild (fresh particle set)
 };
@@ -327,8 +327,8 @@ static void harvest(bbx_engine *e){
     float step_ms = 0.f, grid_ms = 0.f;
     for(size_t k = 0; k + 1 < e->ev_used; k++){
         int ph = e->ev_phase[k];
-        if(ph >= T_COUNT){ step_ms = 0.f; grid_ms = 0.f; continue; } // step boundary marker
         float ms = 0.f; cudaEventElapsedTime(&ms, e->ev[k], e->ev[k + 1]);
+        if(ph >= T_COUNT){ step_ms = 0.f; grid_ms = 0.f; e->phase_ms[T_COUNT] += ms; e->phase_launches[T_COUNT]++; continue; } // gap between sub-steps
         e->phase_ms[ph] += ms; e->phase_launches[ph]++;
         step_ms += ms; if(ph == T_GRID) grid_ms += ms;
         e->last_ms_step = step_ms; e->last_ms_grid = grid_ms;
@@ -694,7 +694,7 @@ int bbx_set_rebuild_flag(bbx_engine *e, int flag){
 
 int bbx_launch_count(bbx_engine *e, long long *count){ if(!e || !count) return set_error(BBX_ERR_INVALID, "null"); *count = e->launches; return BBX_OK; }
 int bbx_kernel_time(bbx_engine *e, int phase, float *ms, int *launches){
-    if(!e || phase < 0 || phase >= T_COUNT) return set_error(BBX_ERR_INVALID, "bad phase");
+    if(!e || phase < 0 || phase > T_COUNT) return set_error(BBX_ERR_INVALID, "bad phase");
     if(ms) *ms = e->phase_ms[phase];
     if(launches) *launches = e->phase_launches[phase];
     return BBX_OK;

@@ -1,0 +1,69 @@
+"""CPU tests of the boundary: libbbx.so loads and exports every symbol include/bbx.h declares, the
+host-only entry points work without a GPU, and the compute entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import bubbles_b200 as bb
+from bubbles_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bbx.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bbx_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bbx.h but not exported by libbbx.so"
+        assert n in L.SYMBOLS, f"{n} has no ctypes signature in bubbles_b200/_lib.py"
+    assert lib.bbx_version() == 1
+
+
+def test_struct_layout_matches_header():
+    lib = L.load()
+    cfg = L.Config()
+    assert lib.bbx_config_default(C.byref(cfg), 1) == 0
+    assert cfg.struct_size == C.sizeof(L.Config)       # the library wrote its own sizeof(bbx_config)
+    assert cfg.viscosity == 0.04 and cfg.drag == 0.0001 and cfg.eos_exponent == 7.0
+    assert cfg.sound_speed == 100.0 and cfg.pseudo_viscosity == 10.0 and cfg.pcisph_max_iterations == 5
+    assert cfg.gravity[1] == float(np.float32(-9.8))    # vec3f(0.f, -9.8f, 0.f), sph_solver3.cpp:146
+    assert cfg.restitution == 0.6 and cfg.time_step_limit_scale == 5.0
+
+
+def test_grid_for_domain_matches_reference_facts():
+    rows = np.load(os.path.join(ROOT, "tests", "golden", "grid_facts.npy"))
+    for r in rows:
+        g = bb.UtilBuildGridForDomain(r[0:3], r[3:6], r[6], r[7])
+        assert np.array_equal(np.array(g.min[:]), r[8:11]) and np.array_equal(np.array(g.cell_len[:]), r[11:14])
+        assert list(g.n) == [int(x) for x in r[14:17]] and g.total == int(np.prod(r[14:17]))
+    g = bb.MakeGrid((10, 10, 10), (-1, -1, -1), (1, 1, 1))   # src/tests/test_grid.cpp:908-1007
+    assert list(g.n) == [10, 10, 10] and abs(g.cell_len[0] - 0.2) < 1e-15
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    g = bb.UtilBuildGridForDomain((-0.3,) * 3, (0.3,) * 3, 0.02, 1.8)
+    with pytest.raises(bb.BbxError) as ei:
+        bb.Engine(g, 0.02, 1.8, 100)
+    assert ei.value.code == L.ERR_NO_DEVICE
+
+
+def test_product_does_not_touch_the_oracle():
+    """The product path must not import, link or load anything under oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "bubbles_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), f"{f} mentions the oracle"
