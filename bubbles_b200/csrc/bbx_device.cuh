@@ -41,6 +41,8 @@ struct DevCollider {
     double sdf_spacing[3];
     double sdf_origin[3];
     const double *sdf_field; // device pointer
+    const float *sdf_field32; // FP32 shadow of the field (pre-check only)
+    double lipschitz;         // upper bound of |grad| of the trilinear field
 };
 
 struct DevColliderSet {
@@ -49,18 +51,44 @@ struct DevColliderSet {
     DevCollider c[BBX_MAX_COLLIDERS];
 };
 
+// FP32 shadow of the collider set, used by the conservative "certainly no collision" pre-check of the
+// neighbour sweeps (bbx_cull).  Particles that fail the pre-check are queued and finished by the FP64
+// restatement of ColliderSet3::ResolveCollision (bbx_resolve_collision) in a follow-up kernel.
+struct DevCullCollider {
+    int type, reverse, active, identity; // identity: object space == world space
+    float w2o[12];      // rows 0..2 of WorldToObject (affine)
+    float half[3];      // box half sizes
+    float radius;       // sphere
+    float lipschitz;    // SDF: upper bound of |grad f| of the trilinear field
+    int sdf_res[3];
+    float sdf_inv_spacing[3];
+    float sdf_origin[3];
+    const float *sdf_field32;
+};
+struct DevCullSet {
+    int count;
+    float margin;       // absolute slack covering the FP32 evaluation error
+    float dom_lo[3], dom_hi[3]; // domain bounds shrunk by margin (certainly-inside test of the domain clamp)
+    DevCullCollider c[BBX_MAX_COLLIDERS];
+};
+
 // Per-engine mutable device state (flags + statistics), one instance in global memory.
+// Flags that one sub-step writes and the next one reads are double-buffered by the parity of the grid
+// update ("epoch") that consumes them, so no kernel has to reset a flag another kernel of the same
+// sub-step may be setting.
 struct DevState {
-    int rebuild_flag;   // SphParticleSet3::requiresHigherLevelUpdate (set by integrate, read by next grid update)
-    int jump_flag;      // some particle moved >= 2 cells since the last grid update (chains would lose it)
-    int full_rebuild;   // the last grid update took the full (ascending-id) path
-    int overflow;       // particles whose neighbour list hit the 100 cap
-    int lost;           // particles that jumped >= 2 cells
-    int clamped;        // particles pushed back into the domain
+    int rebuild_flag[2]; // SphParticleSet3::requiresHigherLevelUpdate: written by integrate for the next epoch
+    int jump_flag[2];    // some particle moved >= 2 cells since the last grid update (chains would lose it)
+    int lost[2];         // particles that jumped >= 2 cells
+    int overflow;        // particles whose neighbour list hit the 100 cap
+    int clamped;         // particles pushed back into the domain
     int nan_count;
-    int error;          // sticky: bbx_status-like device-detected error (out of domain, run too long)
+    int error;           // sticky: bbx_status-like device-detected error (out of domain, run too long)
     unsigned max_force_bits; // float bits of max |f| (non-negative floats order like unsigned)
     unsigned max_err_bits;   // float bits of max |rho* - rho0|
+    int n_occ;           // occupied cells found by the last scan
+    int qn[2];           // collider slow-path queue lengths: [0] predict, [1] integrate
+    unsigned scan_ticket;
     int iterations;
     int pad;
 };
@@ -89,6 +117,8 @@ struct StepParams {
     float restitution;
     float min_cell_len09; // 0.9 * min cell length (big-move rule, sph_equations3.cpp:330-335)
     float pseudo_factor;  // clamp(dt * pseudoViscosity, 0, 1)
+    float thr_lo, thr_hi; // thr2 -+ band: below thr_lo certainly accepted, above thr_hi certainly rejected
+    int par;              // parity of the current grid epoch; integrate writes rebuild_flag[par ^ 1]
 };
 
 // ------------------------------------------------------------------------------------------- grid
@@ -352,6 +382,79 @@ __device__ __noinline__ bool bbx_resolve_collision(const DevColliderSet &cs, dou
     }
     *px = (float)tp.x; *py = (float)tp.y; *pz = (float)tp.z;
     return true;
+}
+
+// ------------------------------------------------------------------------- conservative FP32 pre-check
+// FieldGrid::Sample on the FP32 copy of the field (same clamped-index convention as sdf_sample)
+__device__ __forceinline__ float cull_sdf_sample(const DevCullCollider &c, float px, float py, float pz){
+    const float pf[3] = {px, py, pz};
+    int ii[3], jj[3]; float w[3];
+#pragma unroll
+    for(int i = 0; i < 3; i++){
+        float x = (pf[i] - c.sdf_origin[i]) * c.sdf_inv_spacing[i];
+        int high = c.sdf_res[i] - 1;
+        float s = floorf(x);
+        int id = (int)s; float f = x - s;
+        if(high == 0 || id < 0){ id = 0; f = 0.f; }
+        else if(id > high - 1){ id = high - 1; f = 1.f; }
+        ii[i] = id; w[i] = f; jj[i] = min(id + 1, high);
+    }
+    const float *F = c.sdf_field32; int rx = c.sdf_res[0], rxy = c.sdf_res[0] * c.sdf_res[1];
+    float f000 = __ldg(F + ii[0] + ii[1] * rx + ii[2] * rxy), f100 = __ldg(F + jj[0] + ii[1] * rx + ii[2] * rxy);
+    float f010 = __ldg(F + ii[0] + jj[1] * rx + ii[2] * rxy), f110 = __ldg(F + jj[0] + jj[1] * rx + ii[2] * rxy);
+    float f001 = __ldg(F + ii[0] + ii[1] * rx + jj[2] * rxy), f101 = __ldg(F + jj[0] + ii[1] * rx + jj[2] * rxy);
+    float f011 = __ldg(F + ii[0] + jj[1] * rx + jj[2] * rxy), f111 = __ldg(F + jj[0] + jj[1] * rx + jj[2] * rxy);
+    float a0 = f000 + w[0] * (f100 - f000), a1 = f010 + w[0] * (f110 - f010);
+    float a2 = f001 + w[0] * (f101 - f001), a3 = f011 + w[0] * (f111 - f011);
+    float b0 = a0 + w[1] * (a1 - a0), b1 = a2 + w[1] * (a3 - a2);
+    return b0 + w[2] * (b1 - b0);
+}
+
+// true  = no active collider can be penetrated by a particle of this radius at p (certain, FP32 error
+//         covered by cs.margin): ColliderSet3::ResolveCollision would leave position and velocity alone;
+// false = undecided: run the exact FP64 response.
+// Box / sphere: |signed distance| of the chosen collider decides (Collider3::IsPenetrating,
+// collider.cpp:123-133); if every active collider is clear, so is whichever one is picked as the target.
+// SDF grid: the projection moves the point by |f| per step and stops at |f| < 1e-3, so with L >= |grad f|
+// the returned distance is >= (f(p) - 1e-3) / L (assumes the <= 5 Newton steps converge, which holds for
+// any field close to a distance field; DESIGN.md states this).
+__device__ __forceinline__ bool bbx_cull(const DevCullSet &cs, float px, float py, float pz, float radius){
+    const float need = radius + cs.margin;
+    for(int i = 0; i < cs.count; i++){
+        const DevCullCollider &c = cs.c[i];
+        if(!c.active) continue;
+        float lx = px, ly = py, lz = pz;
+        if(!c.identity){
+            lx = fmaf(c.w2o[0], px, fmaf(c.w2o[1], py, fmaf(c.w2o[2], pz, c.w2o[3])));
+            ly = fmaf(c.w2o[4], px, fmaf(c.w2o[5], py, fmaf(c.w2o[6], pz, c.w2o[7])));
+            lz = fmaf(c.w2o[8], px, fmaf(c.w2o[9], py, fmaf(c.w2o[10], pz, c.w2o[11])));
+        }
+        float sd;
+        if(c.type == BBX_COLLIDER_BOX){
+            float qx = fabsf(lx) - c.half[0], qy = fabsf(ly) - c.half[1], qz = fabsf(lz) - c.half[2];
+            // Inside(vec3, Bounds3) counts a point within 1e-6 of ANY face plane as inside (geometry.h:1773-1783,
+            // mirrored by inside_bounds): near such a plane the box reports a tiny negative distance
+            const float slab = 1.0e-6f + cs.margin;
+            if(fminf(fabsf(qx), fminf(fabsf(qy), fabsf(qz))) < slab) return false;
+            float ox = fmaxf(qx, 0.f), oy = fmaxf(qy, 0.f), oz = fmaxf(qz, 0.f);
+            sd = sqrtf(fmaf(ox, ox, fmaf(oy, oy, oz * oz))) + fminf(fmaxf(qx, fmaxf(qy, qz)), 0.f);
+        }else if(c.type == BBX_COLLIDER_SPHERE){
+            sd = sqrtf(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - c.radius;
+        }else{
+            float s0 = cull_sdf_sample(c, lx, ly, lz);
+            float sw = c.identity ? s0 : cull_sdf_sample(c, px, py, pz); // Shape::IsInside samples at the world position
+            if(!(sw > cs.margin)) return false;
+            if(!((s0 - 0.001f) > need * c.lipschitz)) return false;
+            continue;
+        }
+        if(c.reverse){ if(!(sd < -need)) return false; }
+        else{ if(!(sd > need)) return false; }
+    }
+    return true;
+}
+// certainly inside the domain (no clamp): sph_equations3.cpp:317-326
+__device__ __forceinline__ bool bbx_inside_domain_certain(const DevCullSet &cs, float px, float py, float pz){
+    return px > cs.dom_lo[0] && px < cs.dom_hi[0] && py > cs.dom_lo[1] && py < cs.dom_hi[1] && pz > cs.dom_lo[2] && pz < cs.dom_hi[2];
 }
 
 // warp helpers

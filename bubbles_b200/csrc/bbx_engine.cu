@@ -38,14 +38,19 @@ struct bbx_engine {
     int *cell_start[2];
     int cur;
     int have_chains; // cell_start[cur] / cell[cur] valid
-    int *newcell, *count, *perm, *scan_sums;
-    int scan_blocks;
+    int *newcell, *count, *perm, *occ_cells, *queue;
+    unsigned long long *scan_status;
+    int scan_tiles;
+    int epoch;       // grid updates done so far; flags are double-buffered by its parity (DevState)
+    int masked;      // cells smaller than h: the list build must test the per-particle cell window
     unsigned short *nbr; int *nbr_cnt;
     float4 *force, *force_p, *pred, *posq, *smoothed;
     float *pressure, *rho_pred, *rho_err;
     DevState *st; DevState *st_host; // st_host pinned
     DevColliderSet *colliders; DevColliderSet colliders_host;
+    DevCullSet *cull; DevCullSet cull_host;
     std::vector<double *> sdf_fields;
+    std::vector<float *> sdf_fields32;
     void *stage; size_t stage_bytes; // device staging for upload / download
     long long launches;
     int substeps;
@@ -55,8 +60,11 @@ struct bbx_engine {
     float phase_ms[T_COUNT + 1]; int phase_launches[T_COUNT + 1]; // [T_COUNT] = gaps between sub-steps
     float last_ms_grid, last_ms_step;
     int force_full; // next grid update must be a full rebuild (fresh particle set)
+    int last_force; // the last grid update was forced to the full path by the host
 };
 
+#define BBX_PAD 64 // spare slots at the end of the particle arrays
+static int push_cull(bbx_engine *e);
 #define LAUNCH(e, kernel, grid, block, ...) do{ kernel<<<(grid), (block), 0, (e)->stream>>>(__VA_ARGS__); (e)->launches++; }while(0)
 static inline int div_up(long long a, int b){ return (int)((a + b - 1) / b); }
 
@@ -110,7 +118,7 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     memset(&e->cfg, 0, sizeof(e->cfg));
     e->cfg = *cfg;
     e->device = cfg->device;
-    e->n = 0; e->cap = cfg->max_particles; e->cur = 0; e->have_chains = 0; e->launches = 0; e->substeps = 0;
+    e->n = 0; e->cap = cfg->max_particles; e->cur = 0; e->have_chains = 0; e->launches = 0; e->substeps = 0; e->epoch = 0;
     e->timing = 0; e->ev_used = 0; e->force_full = 1; e->stage = nullptr; e->stage_bytes = 0;
     e->last_ms_grid = e->last_ms_step = 0.f;
     memset(e->phase_ms, 0, sizeof(e->phase_ms)); memset(e->phase_launches, 0, sizeof(e->phase_launches));
@@ -131,27 +139,38 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     double r = e->mass / cfg->target_density;
     e->mass_over_rho0_sq = r * r;
     e->delta_denom = bbxh_delta_denom(e->h, cfg->spacing);
-    size_t cap = (size_t)e->cap, capw = ((cap + 31) / 32) * 32;
+    // the list build tests candidates of cells two columns away only through the distance: exact as long
+    // as a cell is not (measurably) shorter than h, otherwise the explicit window test is compiled in
+    {
+        double minlen = std::min(g.len[0], std::min(g.len[1], g.len[2]));
+        e->masked = (minlen * minlen >= e->h * e->h - 0.5e-8) ? 0 : 1;
+    }
+    // particle arrays carry BBX_PAD spare slots: the list build reads (and discards) up to 7 slots past a run
+    size_t cap = (size_t)e->cap + BBX_PAD, capw = ((cap + 31) / 32) * 32;
     int rc = BBX_OK;
     for(int b = 0; b < 2 && rc == BBX_OK; b++){
         rc |= dev_alloc(&e->pos[b], cap); rc |= dev_alloc(&e->vel[b], cap);
         rc |= dev_alloc(&e->pid[b], cap); rc |= dev_alloc(&e->cell[b], cap);
         rc |= dev_alloc(&e->cell_start[b], (size_t)g.total + 1);
+        if(rc == BBX_OK){ CU(cudaMemset(e->pos[b], 0, sizeof(float4) * cap)); CU(cudaMemset(e->cell[b], 0, sizeof(int) * cap)); }
     }
-    rc |= dev_alloc(&e->newcell, cap); rc |= dev_alloc(&e->count, (size_t)g.total + 1); rc |= dev_alloc(&e->perm, cap);
-    e->scan_blocks = div_up(g.total, SCAN_TILE);
-    rc |= dev_alloc(&e->scan_sums, (size_t)e->scan_blocks);
+    rc |= dev_alloc(&e->newcell, cap); rc |= dev_alloc(&e->count, (size_t)g.total + 8); rc |= dev_alloc(&e->perm, cap);
+    rc |= dev_alloc(&e->occ_cells, (size_t)g.total); rc |= dev_alloc(&e->queue, cap);
+    e->scan_tiles = div_up(g.total, SCAN_TILE);
+    rc |= dev_alloc(&e->scan_status, (size_t)e->scan_tiles);
     rc |= dev_alloc(&e->nbr, capw * BBX_NBR_CHUNKS * 8); rc |= dev_alloc(&e->nbr_cnt, cap);
     rc |= dev_alloc(&e->force, cap); rc |= dev_alloc(&e->force_p, cap); rc |= dev_alloc(&e->pred, cap);
     rc |= dev_alloc(&e->posq, cap); rc |= dev_alloc(&e->smoothed, cap);
     rc |= dev_alloc(&e->pressure, cap); rc |= dev_alloc(&e->rho_pred, cap); rc |= dev_alloc(&e->rho_err, cap);
-    rc |= dev_alloc(&e->st, 1); rc |= dev_alloc(&e->colliders, 1);
+    rc |= dev_alloc(&e->st, 1); rc |= dev_alloc(&e->colliders, 1); rc |= dev_alloc(&e->cull, 1);
     if(rc != BBX_OK){ return rc; }
+    CU(cudaMemset(e->count, 0, sizeof(int) * ((size_t)g.total + 8)));
     CU(cudaMallocHost((void **)&e->st_host, sizeof(DevState)));
     CU(cudaMemset(e->st, 0, sizeof(DevState)));
     memset(e->st_host, 0, sizeof(DevState));
     memset(&e->colliders_host, 0, sizeof(DevColliderSet));
     CU(cudaMemset(e->colliders, 0, sizeof(DevColliderSet)));
+    { int rc2 = push_cull(e); if(rc2) return rc2; }
     CU(cudaMemset(e->force, 0, sizeof(float4) * cap)); CU(cudaMemset(e->force_p, 0, sizeof(float4) * cap));
     CU(cudaMemset(e->pressure, 0, sizeof(float) * cap)); CU(cudaMemset(e->rho_pred, 0, sizeof(float) * cap));
     CU(cudaMemset(e->rho_err, 0, sizeof(float) * cap)); CU(cudaMemset(e->pred, 0, sizeof(float4) * cap));
@@ -165,11 +184,12 @@ int bbx_destroy(bbx_engine *e){
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for(int b = 0; b < 2; b++){ cudaFree(e->pos[b]); cudaFree(e->vel[b]); cudaFree(e->pid[b]); cudaFree(e->cell[b]); cudaFree(e->cell_start[b]); }
-    cudaFree(e->newcell); cudaFree(e->count); cudaFree(e->perm); cudaFree(e->scan_sums);
+    cudaFree(e->newcell); cudaFree(e->count); cudaFree(e->perm); cudaFree(e->occ_cells); cudaFree(e->queue); cudaFree(e->scan_status);
     cudaFree(e->nbr); cudaFree(e->nbr_cnt); cudaFree(e->force); cudaFree(e->force_p); cudaFree(e->pred);
     cudaFree(e->posq); cudaFree(e->smoothed); cudaFree(e->pressure); cudaFree(e->rho_pred); cudaFree(e->rho_err);
-    cudaFree(e->st); cudaFree(e->colliders); cudaFreeHost(e->st_host);
+    cudaFree(e->st); cudaFree(e->colliders); cudaFree(e->cull); cudaFreeHost(e->st_host);
     for(double *f : e->sdf_fields) cudaFree(f);
+    for(float *f : e->sdf_fields32) cudaFree(f);
     if(e->stage) cudaFree(e->stage);
     for(cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(e->stream);
@@ -263,7 +283,7 @@ static int fill_collider(bbx_engine *e, DevCollider &d, const bbx_collider &c){
     memcpy(d.o2w, c.object_to_world, sizeof(d.o2w)); memcpy(d.w2o, c.world_to_object, sizeof(d.w2o));
     memcpy(d.size, c.size, sizeof(d.size)); d.radius = c.radius; d.friction = c.friction;
     memcpy(d.linvel, c.linear_velocity, sizeof(d.linvel)); memcpy(d.angvel, c.angular_velocity, sizeof(d.angvel));
-    d.sdf_field = nullptr;
+    d.sdf_field = nullptr; d.sdf_field32 = nullptr; d.lipschitz = 0.0;
     if(c.type == BBX_COLLIDER_SDF){
         if(!c.sdf_field) return set_error(BBX_ERR_INVALID, "SDF collider without field");
         size_t total = (size_t)c.sdf_resolution[0] * c.sdf_resolution[1] * c.sdf_resolution[2];
@@ -274,13 +294,70 @@ static int fill_collider(bbx_engine *e, DevCollider &d, const bbx_collider &c){
         e->sdf_fields.push_back(dev);
         d.sdf_field = dev;
         for(int k = 0; k < 3; k++){ d.sdf_res[k] = c.sdf_resolution[k]; d.sdf_spacing[k] = c.sdf_spacing[k]; d.sdf_origin[k] = c.sdf_origin[k]; }
+        // FP32 shadow + Lipschitz bound of the trilinear field for the conservative pre-check (bbx_cull)
+        std::vector<float> f32(total);
+        double gmax[3] = {0, 0, 0};
+        const int rx = c.sdf_resolution[0], ry = c.sdf_resolution[1], rz = c.sdf_resolution[2];
+        for(int z = 0; z < rz; z++) for(int y = 0; y < ry; y++) for(int x = 0; x < rx; x++){
+            size_t id = (size_t)x + (size_t)y * rx + (size_t)z * rx * ry;
+            double v = c.sdf_field[id];
+            f32[id] = (float)v;
+            if(x + 1 < rx) gmax[0] = std::max(gmax[0], fabs(c.sdf_field[id + 1] - v) / c.sdf_spacing[0]);
+            if(y + 1 < ry) gmax[1] = std::max(gmax[1], fabs(c.sdf_field[id + rx] - v) / c.sdf_spacing[1]);
+            if(z + 1 < rz) gmax[2] = std::max(gmax[2], fabs(c.sdf_field[id + (size_t)rx * ry] - v) / c.sdf_spacing[2]);
+        }
+        float *dev32 = nullptr;
+        CU(cudaMalloc((void **)&dev32, total * sizeof(float)));
+        CU(cudaMemcpy(dev32, f32.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+        e->sdf_fields32.push_back(dev32);
+        d.lipschitz = sqrt(gmax[0] * gmax[0] + gmax[1] * gmax[1] + gmax[2] * gmax[2]);
+        d.sdf_field32 = dev32;
     }
+    return BBX_OK;
+}
+// FP32 shadow of the collider set (+ domain faces) for the conservative pre-check of the sweeps
+static int push_cull(bbx_engine *e){
+    DevCullSet &q = e->cull_host;
+    memset(&q, 0, sizeof(q));
+    const DevColliderSet &cs = e->colliders_host;
+    q.count = cs.count;
+    double scale = 1.0;
+    for(int k = 0; k < 3; k++) scale = std::max(scale, std::max(fabs(e->grid.min[k]), fabs(e->grid.max[k])));
+    for(int i = 0; i < cs.count; i++){
+        const DevCollider &d = cs.c[i];
+        DevCullCollider &c = q.c[i];
+        c.type = d.type; c.reverse = d.reverse; c.active = d.active;
+        bool ident = true;
+        for(int r = 0; r < 3; r++) for(int k = 0; k < 4; k++){
+            c.w2o[r * 4 + k] = (float)d.w2o[r * 4 + k];
+            if(d.w2o[r * 4 + k] != (r == k ? 1.0 : 0.0)) ident = false;
+            scale = std::max(scale, fabs(d.w2o[r * 4 + k]) * (k == 3 ? 1.0 : 0.0));
+        }
+        // a projective last row would need the divide of Transform::Point: never cull such a collider
+        bool affine = d.w2o[12] == 0 && d.w2o[13] == 0 && d.w2o[14] == 0 && d.w2o[15] == 1;
+        c.identity = ident ? 1 : 0;
+        for(int k = 0; k < 3; k++){ c.half[k] = (float)(d.size[k] / 2.0); scale = std::max(scale, d.size[k]); }
+        c.radius = (float)d.radius; scale = std::max(scale, d.radius);
+        c.lipschitz = (float)(d.lipschitz * (1.0 + 1e-5) + 1e-12);
+        for(int k = 0; k < 3; k++){
+            c.sdf_res[k] = d.sdf_res[k];
+            c.sdf_inv_spacing[k] = d.sdf_spacing[k] > 0 ? (float)(1.0 / d.sdf_spacing[k]) : 0.f;
+            c.sdf_origin[k] = (float)d.sdf_origin[k];
+        }
+        c.sdf_field32 = d.sdf_field32;
+        if(!affine) c.type = -1; // never cleared by the pre-check
+    }
+    // FP32 evaluation error of the signed distances: a few ulp of the largest coordinate involved
+    q.margin = (float)(1.0e-5 * scale + 1.0e-3 * e->cfg.spacing);
+    for(int k = 0; k < 3; k++){ q.dom_lo[k] = (float)(e->grid.min[k] + q.margin); q.dom_hi[k] = (float)(e->grid.max[k] - q.margin); }
+    CU(cudaMemcpyAsync(e->cull, &q, sizeof(DevCullSet), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
     return BBX_OK;
 }
 static int push_colliders(bbx_engine *e){
     CU(cudaMemcpyAsync(e->colliders, &e->colliders_host, sizeof(DevColliderSet), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream)); // colliders_host may change right after this call
-    return BBX_OK;
+    return push_cull(e);
 }
 int bbx_set_colliders(bbx_engine *e, int n, const bbx_collider *colliders){
     CHECK_ENGINE(e);
@@ -288,6 +365,8 @@ int bbx_set_colliders(bbx_engine *e, int n, const bbx_collider *colliders){
     CU(cudaStreamSynchronize(e->stream));
     for(double *f : e->sdf_fields) cudaFree(f);
     e->sdf_fields.clear();
+    for(float *f : e->sdf_fields32) cudaFree(f);
+    e->sdf_fields32.clear();
     memset(&e->colliders_host, 0, sizeof(DevColliderSet));
     for(int i = 0; i < n; i++){ int rc = fill_collider(e, e->colliders_host.c[i], colliders[i]); if(rc) return rc; }
     e->colliders_host.count = n;
@@ -298,7 +377,7 @@ int bbx_update_collider(bbx_engine *e, int index, const bbx_collider *c){
     if(!c || index < 0 || index >= e->colliders_host.count) return set_error(BBX_ERR_INVALID, "collider index out of range");
     DevCollider &d = e->colliders_host.c[index];
     if(c->type != d.type) return set_error(BBX_ERR_INVALID, "bbx_update_collider cannot change the collider type");
-    const double *keep = d.sdf_field;
+    const double *keep = d.sdf_field; // the baked field (and its FP32 shadow, Lipschitz bound) stay
     d.reverse = c->reverse_orientation ? 1 : 0; d.active = c->active ? 1 : 0;
     memcpy(d.o2w, c->object_to_world, sizeof(d.o2w)); memcpy(d.w2o, c->world_to_object, sizeof(d.w2o));
     memcpy(d.size, c->size, sizeof(d.size)); d.radius = c->radius; d.friction = c->friction;
@@ -345,6 +424,8 @@ static void make_params(bbx_engine *e, double dt, StepParams &P){
     P.h_d = h; P.h2_d = h * h;
     P.thr2 = (float)(h * h - 1e-8);
     P.band = (float)(h * h * 1.0e-6 + 4e-8); // >> FP32 rounding of d^2 (~1e-7 relative) and of thr2
+    P.thr_lo = P.thr2 - P.band; P.thr_hi = P.thr2 + P.band;
+    P.par = (e->epoch + 1) & 1; // parity of the grid epoch this sub-step runs under (set right after its grid update)
     P.mass = (float)e->mass; P.mass2 = (float)(e->mass * e->mass); P.inv_mass = (float)(1.0 / e->mass);
     P.rho0 = (float)c.target_density;
     P.w_std_c = (float)(315.0 / (64.0 * pi * h * h * h));
@@ -366,45 +447,53 @@ static void make_params(bbx_engine *e, double dt, StepParams &P){
 }
 
 // UpdateGridDistributionGPU minus the bucket fill (sph_equations3.cpp:511-539)
+#define BBX_SMALL_GRID (148 * 4)
 static int grid_update(bbx_engine *e){
     if(e->n == 0) return BBX_OK;
     DevGrid &g = e->grid;
     int n = e->n, cur = e->cur, nxt = cur ^ 1;
     int force = (e->force_full || !e->have_chains) ? 1 : 0;
-    CU(cudaMemsetAsync(e->count, 0, sizeof(int) * ((size_t)g.total + 1), e->stream));
-    LAUNCH(e, k_clear_lost, 1, 1, e->st);
-    LAUNCH(e, k_hash_count, div_up(n, 256), 256, n, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st, force ? 0 : 1);
-    LAUNCH(e, k_scan_tile_sums, e->scan_blocks, 256, e->count, g.total, e->scan_sums);
-    LAUNCH(e, k_scan_sums, 1, 1024, e->scan_sums, e->scan_blocks);
-    LAUNCH(e, k_scan_tiles, e->scan_blocks, 256, e->count, g.total, e->scan_sums, e->cell_start[nxt], n);
+    int par = e->epoch & 1;
+    LAUNCH(e, k_hash_count, div_up(std::max(n, e->scan_tiles), 256), 256, n, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st,
+           force ? 0 : 1, par, e->scan_status, e->scan_tiles);
+    LAUNCH(e, k_scan_cells, e->scan_tiles, 256, e->count, g.total, n, e->scan_status, e->st, e->cell_start[nxt], e->occ_cells);
     if(!force){
-        LAUNCH(e, k_fill_incremental, div_up((long long)g.total * 32, 256), 256, g, e->st, e->cell_start[cur], e->cell_start[nxt], e->newcell,
+        // persistent grid: 8 lanes per occupied cell, grid-stride over the compact list of occupied cells
+        int groups = std::min(n, g.total);
+        int blocks = std::min(div_up((long long)groups * 8, 256), 148 * 8);
+        LAUNCH(e, k_fill_incremental, blocks, 256, g, e->st, par, e->occ_cells, e->cell_start[cur], e->cell_start[nxt], e->newcell,
                e->pos[cur], e->vel[cur], e->pid[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt]);
     }
-    // full path (forced, or selected on the device by the big-move / jump flags)
-    CU(cudaMemsetAsync(e->count, 0, sizeof(int) * ((size_t)g.total + 1), e->stream));
-    LAUNCH(e, k_full_scatter, div_up(n, 256), 256, n, e->st, force, e->newcell, e->cell_start[nxt], e->count, e->perm);
-    LAUNCH(e, k_full_sort_cells, div_up(g.total, 256), 256, g.total, e->st, force, e->cell_start[nxt], e->pid[cur], e->perm);
-    LAUNCH(e, k_full_gather, div_up(n, 256), 256, n, e->st, force, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
+    // full path (forced, or selected on the device by the big-move / jump flags); small grids when it is
+    // only a flag check
+    int fb_n = force ? div_up(n, 256) : std::min(div_up(n, 256), BBX_SMALL_GRID);
+    int fb_c = force ? div_up(g.total, 256) : std::min(div_up(g.total, 256), BBX_SMALL_GRID);
+    LAUNCH(e, k_full_scatter, fb_n, 256, n, e->st, par, force, e->newcell, e->cell_start[nxt], e->count, e->perm);
+    LAUNCH(e, k_full_sort_cells, fb_c, 256, g.total, e->st, par, force, e->cell_start[nxt], e->pid[cur], e->perm, e->count);
+    LAUNCH(e, k_full_gather, fb_n, 256, n, e->st, par, force, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
            e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt]);
-    LAUNCH(e, k_step_begin, 1, 1, e->st, force);
     CU(cudaGetLastError());
     e->cur = nxt;
     e->have_chains = 1;
+    e->last_force = force;
+    e->epoch++;
     return BBX_OK;
 }
 
 static int phase_density(bbx_engine *e, const StepParams &P, int sph){
-    int cur = e->cur; int nb = div_up(e->n, BBX_BS);
-    if(sph) LAUNCH(e, k_build_density<1>, nb, BBX_BS, P, e->grid, e->st, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq);
-    else    LAUNCH(e, k_build_density<0>, nb, BBX_BS, P, e->grid, e->st, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq);
+    int cur = e->cur; dim3 nb(e->grid.n[1] * e->grid.n[2], BBX_DSPLIT);
+#define BBX_DENS(S, M) LAUNCH(e, (k_density_lists<S, M>), nb, BBX_BS, P, e->grid, e->st, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq)
+    if(sph){ if(e->masked) BBX_DENS(1, 1); else BBX_DENS(1, 0); }
+    else{ if(e->masked) BBX_DENS(0, 1); else BBX_DENS(0, 0); }
+#undef BBX_DENS
     CU(cudaGetLastError());
     return BBX_OK;
 }
 static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
     int cur = e->cur;
-    LAUNCH(e, k_force_np_predict, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->colliders, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur],
-           e->nbr, e->nbr_cnt, e->force, e->pred);
+    LAUNCH(e, k_force_np_predict, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur],
+           e->nbr, e->nbr_cnt, e->force, e->pred, e->queue);
+    LAUNCH(e, k_collide_predict, BBX_SMALL_GRID, 128, P, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force, e->pred);
     CU(cudaGetLastError());
     return BBX_OK;
 }
@@ -417,14 +506,18 @@ static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
 }
 static int phase_pressure_force(bbx_engine *e, const StepParams &P, int integrate){
     int cur = e->cur; int nb = div_up(e->n, BBX_BS);
-    if(integrate) LAUNCH(e, k_pressure_force<1>, nb, BBX_BS, P, e->grid, e->st, e->colliders, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p);
-    else          LAUNCH(e, k_pressure_force<0>, nb, BBX_BS, P, e->grid, e->st, e->colliders, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p);
+    if(integrate){
+        LAUNCH(e, k_pressure_force<1>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue);
+        LAUNCH(e, k_collide_integrate, BBX_SMALL_GRID, 128, P, e->grid, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force);
+    }else{
+        LAUNCH(e, k_pressure_force<0>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue);
+    }
     CU(cudaGetLastError());
     return BBX_OK;
 }
 static int phase_integrate(bbx_engine *e, const StepParams &P, int with_fp){
     int cur = e->cur;
-    LAUNCH(e, k_integrate, div_up(e->n, 256), 256, P, e->grid, e->st, e->colliders, e->pos[cur], e->vel[cur], e->force, with_fp ? e->force_p : (const float4 *)nullptr);
+    LAUNCH(e, k_integrate, div_up(e->n, 256), 256, P, e->grid, e->st, e->colliders, e->cull, e->pos[cur], e->vel[cur], e->force, with_fp ? e->force_p : (const float4 *)nullptr);
     CU(cudaGetLastError());
     return BBX_OK;
 }
@@ -445,10 +538,11 @@ static int read_state(bbx_engine *e){
 static int step_pcisph(bbx_engine *e, double dt){
     if(e->n == 0) return BBX_OK;
     if(!(dt > 0)) return set_error(BBX_ERR_INVALID, "dt must be positive");
-    StepParams P; make_params(e, dt, P);
+    StepParams P;
     int rc;
     tick(e, T_GRID);
     if((rc = grid_update(e))) return rc;
+    make_params(e, dt, P);
     tick(e, T_DENSITY);
     if((rc = phase_density(e, P, 0))) return rc;
     tick(e, T_FORCE_NP);
@@ -465,7 +559,7 @@ static int step_pcisph(bbx_engine *e, double dt){
         for(int k = 0; k < e->cfg.pcisph_max_iterations; k++){
             if(k > 0){
                 tick(e, T_PREDICT);
-                LAUNCH(e, k_predict_again, div_up(e->n, 256), 256, P, e->colliders, e->pos[e->cur], e->vel[e->cur], e->force, e->force_p, e->pred);
+                LAUNCH(e, k_predict_again, div_up(e->n, 256), 256, P, e->colliders, e->cull, e->pos[e->cur], e->vel[e->cur], e->force, e->force_p, e->pred);
             }
             tick(e, T_PRESSURE);
             if((rc = phase_pressure(e, P, k == 0))) return rc;
@@ -477,6 +571,7 @@ static int step_pcisph(bbx_engine *e, double dt){
             float maxerr; memcpy(&maxerr, &e->st_host->max_err_bits, 4);
             if(fabs((double)maxerr / e->cfg.target_density) < e->cfg.pcisph_max_density_error_ratio) break;
             if(k + 1 < e->cfg.pcisph_max_iterations){ CU(cudaMemsetAsync(&e->st->max_err_bits, 0, 4, e->stream)); }
+            // (the queue of the predict pre-check is only used on the first iteration)
         }
         tick(e, T_INTEGRATE);
         if((rc = phase_integrate(e, P, 1))) return rc;
@@ -491,10 +586,11 @@ static int step_pcisph(bbx_engine *e, double dt){
 static int step_sph(bbx_engine *e, double dt){
     if(e->n == 0) return BBX_OK;
     if(!(dt > 0)) return set_error(BBX_ERR_INVALID, "dt must be positive");
-    StepParams P; make_params(e, dt, P);
+    StepParams P;
     int rc;
     tick(e, T_GRID);
     if((rc = grid_update(e))) return rc;
+    make_params(e, dt, P);
     tick(e, T_DENSITY);
     if((rc = phase_density(e, P, 1))) return rc;
     tick(e, T_FORCE_NP);
@@ -585,8 +681,10 @@ int bbx_stats(bbx_engine *e, bbx_step_stats *out){
     const DevState &s = *e->st_host;
     memset(out, 0, sizeof(*out));
     out->particles = e->n; out->ghosts = 0; out->substeps = e->substeps; out->pcisph_iterations = it;
-    out->full_rebuild = s.full_rebuild; out->rebuild_flag = s.rebuild_flag; out->neighbor_overflow = s.overflow;
-    out->lost_particles = s.lost; out->clamped = s.clamped; out->nan_count = s.nan_count;
+    const int done = (e->epoch + 1) & 1, next = e->epoch & 1; // flag slots of the last / the next grid update
+    out->full_rebuild = (e->epoch > 0 && (e->last_force | s.rebuild_flag[done] | s.jump_flag[done])) ? 1 : 0;
+    out->rebuild_flag = s.rebuild_flag[next]; out->neighbor_overflow = s.overflow;
+    out->lost_particles = s.lost[done]; out->clamped = s.clamped; out->nan_count = s.nan_count;
     memcpy(&out->max_force, &s.max_force_bits, 4); memcpy(&out->max_density_error, &s.max_err_bits, 4);
     out->ms_grid = e->last_ms_grid; out->ms_step = e->last_ms_step;
     if(s.error) return set_error(s.error, "device-side error %d (%s)", s.error,
@@ -687,7 +785,7 @@ int bbx_inject_chains(bbx_engine *e, const int *cell_count, const int *cell_orde
 int bbx_set_rebuild_flag(bbx_engine *e, int flag){
     CHECK_ENGINE(e);
     int v = flag ? 1 : 0;
-    CU(cudaMemcpyAsync(&e->st->rebuild_flag, &v, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(&e->st->rebuild_flag[e->epoch & 1], &v, sizeof(int), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return BBX_OK;
 }

@@ -22,12 +22,20 @@
 
 // ------------------------------------------------------------------------- A: neighbour-grid build
 
-// A1: cell hash per particle + histogram + jump detection.
+// A1: cell hash per particle + histogram + jump detection.  Thread 0 also resets the per-sub-step
+// statistics and the flag slots of the *next* epoch (see DevState).
 __global__ void __launch_bounds__(256) k_hash_count(int n, const float4 *__restrict__ pos, const int *__restrict__ oldcell,
                                                     int *__restrict__ newcell, int *__restrict__ count,
-                                                    DevGrid g, DevState *st, int have_old)
+                                                    DevGrid g, DevState *st, int have_old, int par,
+                                                    unsigned long long *__restrict__ scan_status, int scan_tiles)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i == 0){
+        st->rebuild_flag[par ^ 1] = 0; st->jump_flag[par ^ 1] = 0; st->lost[par ^ 1] = 0;
+        st->overflow = 0; st->clamped = 0; st->nan_count = 0; st->max_force_bits = 0; st->max_err_bits = 0;
+        st->qn[0] = 0; st->qn[1] = 0; st->scan_ticket = 0; st->n_occ = 0;
+    }
+    if(i < scan_tiles) scan_status[i] = 0ull;
     if(i >= n) return;
     float4 p = pos[i];
     int ux, uy, uz;
@@ -44,176 +52,209 @@ __global__ void __launch_bounds__(256) k_hash_count(int n, const float4 *__restr
     if(have_old){
         int oc = oldcell[i];
         int oz = oc / g.plane; int rem = oc - oz * g.plane; int oy = rem / g.n[0]; int ox = rem - oy * g.n[0];
-        if(abs(ox - ux) > 1 || abs(oy - uy) > 1 || abs(oz - uz) > 1){ st->jump_flag = 1; atomicAdd(&st->lost, 1); }
+        if(abs(ox - ux) > 1 || abs(oy - uy) > 1 || abs(oz - uz) > 1){ st->jump_flag[par] = 1; atomicAdd(&st->lost[par], 1); }
     }
 }
 
-// A2: exclusive scan of the per-cell counts (three small kernels: tile sums, scan of sums, tile scan)
+// A2: single-pass exclusive scan of the per-cell counts (decoupled look-back over tiles of 2048 cells).
+// The scanned value packs (occupied cells so far) << 31 | (particles so far), so that the same pass also
+// emits the compact list of occupied cells the fill kernel iterates over.  count[] is zeroed on the way
+// out (it is the histogram of the next sub-step and the cursor of the full rebuild).
 #define SCAN_TILE 2048
-__global__ void __launch_bounds__(256) k_scan_tile_sums(const int *__restrict__ count, int total, int *__restrict__ sums){
-    __shared__ int ws[8];
-    int base = blockIdx.x * SCAN_TILE;
-    int s = 0;
+#define SCAN_FLAG_AGG (1ull << 62)
+#define SCAN_FLAG_INC (2ull << 62)
+#define SCAN_VALUE_MASK ((1ull << 62) - 1)
+__global__ void __launch_bounds__(256) k_scan_cells(int *__restrict__ count, int total, int n_total,
+        unsigned long long *scan_status, DevState *st, int *__restrict__ start, int *__restrict__ occ_cells)
+{
+    __shared__ unsigned long long ws[8];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned s_tile;
+    if(threadIdx.x == 0) s_tile = atomicAdd(&st->scan_ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = tile * SCAN_TILE + threadIdx.x * (SCAN_TILE / 256);
+    int v[SCAN_TILE / 256];
+    unsigned long long s = 0;
+    if(base + SCAN_TILE / 256 <= total){
+        int4 a = *reinterpret_cast<const int4 *>(count + base), b = *reinterpret_cast<const int4 *>(count + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        *reinterpret_cast<int4 *>(count + base) = make_int4(0, 0, 0, 0);
+        *reinterpret_cast<int4 *>(count + base + 4) = make_int4(0, 0, 0, 0);
+    }else{
+#pragma unroll
+        for(int k = 0; k < SCAN_TILE / 256; k++){ int idx = base + k; v[k] = 0; if(idx < total){ v[k] = count[idx]; count[idx] = 0; } }
+    }
+#pragma unroll
+    for(int k = 0; k < SCAN_TILE / 256; k++) s += (unsigned long long)v[k] + (v[k] > 0 ? (1ull << 31) : 0ull);
+    unsigned long long x = s;
+    for(int o = 1; o < 32; o <<= 1){ unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if(lane >= o) x += y; }
+    if(lane == 31) ws[warp] = x;
+    __syncthreads();
+    unsigned long long woff = 0, tile_sum = 0;
+#pragma unroll
+    for(int k = 0; k < 8; k++){ unsigned long long w = ws[k]; if(k < warp) woff += w; tile_sum += w; }
+    if(warp == 0){
+        // publish the tile aggregate, then look back over the predecessors (one warp, 32 tiles per probe)
+        if(lane == 0){
+            unsigned long long pub = (tile == 0 ? SCAN_FLAG_INC : SCAN_FLAG_AGG) | tile_sum;
+            atomicExch(&scan_status[tile], pub);
+        }
+        unsigned long long prefix = 0;
+        int look = (int)tile - 1;
+        while(look >= 0){
+            int idx = look - lane;
+            unsigned long long stv = SCAN_FLAG_INC; // tiles before 0 count as an inclusive zero
+            if(idx >= 0){
+                do{ stv = *((volatile unsigned long long *)&scan_status[idx]); }while((stv >> 62) == 0);
+            }
+            unsigned inc = __ballot_sync(0xffffffffu, (stv >> 62) == 2);
+            int first_inc = inc ? (__ffs(inc) - 1) : 32;  // nearest predecessor with an inclusive prefix
+            unsigned long long val = (lane <= first_inc) ? (stv & SCAN_VALUE_MASK) : 0ull;
+            for(int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            prefix += val;
+            if(inc) break;
+            look -= 32;
+        }
+        if(lane == 0){
+            if(tile != 0) atomicExch(&scan_status[tile], SCAN_FLAG_INC | (prefix + tile_sum));
+            s_prefix = prefix;
+        }
+    }
+    __syncthreads();
+    unsigned long long run = s_prefix + woff + x - s;
 #pragma unroll
     for(int k = 0; k < SCAN_TILE / 256; k++){
-        int idx = base + k * 256 + threadIdx.x;
-        if(idx < total) s += count[idx];
-    }
-    for(int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if(threadIdx.x == 0){ int t = 0; for(int k = 0; k < 8; k++) t += ws[k]; sums[blockIdx.x] = t; }
-}
-__global__ void __launch_bounds__(1024) k_scan_sums(int *sums, int nb){
-    // single CTA, sequential over chunks of 1024 with a warp-shuffle scan inside
-    __shared__ int ws[32];
-    __shared__ int carry;
-    if(threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for(int base = 0; base < nb; base += 1024){
-        int idx = base + threadIdx.x;
-        int v = idx < nb ? sums[idx] : 0;
-        int x = v;
-        for(int o = 1; o < 32; o <<= 1){ int y = __shfl_up_sync(0xffffffffu, x, o); if((threadIdx.x & 31) >= o) x += y; }
-        if((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if(threadIdx.x < 32){
-            int w = ws[threadIdx.x];
-            for(int o = 1; o < 32; o <<= 1){ int y = __shfl_up_sync(0xffffffffu, w, o); if(threadIdx.x >= o) w += y; }
-            ws[threadIdx.x] = w;
+        int idx = base + k;
+        if(idx < total){
+            start[idx] = (int)(run & 0x7fffffffull);
+            if(v[k] > 0) occ_cells[(int)(run >> 31)] = idx;
+            run += (unsigned long long)v[k] + (v[k] > 0 ? (1ull << 31) : 0ull);
         }
-        __syncthreads();
-        int prefix = carry + (threadIdx.x >= 32 ? ws[(threadIdx.x >> 5) - 1] : 0) + x - v;
-        if(idx < nb) sums[idx] = prefix;
-        __syncthreads();
-        if(threadIdx.x == 1023) carry = prefix + v;
-        __syncthreads();
     }
-}
-__global__ void __launch_bounds__(256) k_scan_tiles(const int *__restrict__ count, int total, const int *__restrict__ sums,
-                                                    int *__restrict__ start, int n_total)
-{
-    __shared__ int ws[8];
-    int base = blockIdx.x * SCAN_TILE + threadIdx.x * (SCAN_TILE / 256);
-    int v[SCAN_TILE / 256]; int s = 0;
-#pragma unroll
-    for(int k = 0; k < SCAN_TILE / 256; k++){ int idx = base + k; v[k] = idx < total ? count[idx] : 0; s += v[k]; }
-    int x = s;
-    for(int o = 1; o < 32; o <<= 1){ int y = __shfl_up_sync(0xffffffffu, x, o); if((threadIdx.x & 31) >= o) x += y; }
-    if((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
-    __syncthreads();
-    int woff = 0;
-    for(int k = 0; k < (int)(threadIdx.x >> 5); k++) woff += ws[k];
-    int run = sums[blockIdx.x] + woff + x - s;
-#pragma unroll
-    for(int k = 0; k < SCAN_TILE / 256; k++){ int idx = base + k; if(idx < total){ start[idx] = run; run += v[k]; } }
-    if(blockIdx.x == 0 && threadIdx.x == 0) start[total] = n_total;
+    if(tile == gridDim.x - 1 && threadIdx.x == 255){
+        // the last tile's last thread holds the grand total
+        start[total] = n_total;
+        st->n_occ = (int)(run >> 31);
+    }
 }
 
-// A3 (incremental path): one warp per *new* cell c walks the <= 27 old segments in the reference's
-// neighbour order (y outer, x middle, z inner: Grid::GetNeighborListFor, grid.h:555-593) and appends, in
+// A3 (incremental path): 8 lanes per *occupied new* cell c walk the <= 27 old segments in the reference's
+// neighbour order (y outer, x middle, z inner: Grid::GetNeighborListFor, grid.h:555-593) and append, in
 // old chain order, the particles whose new cell is c (Grid::DistributeToCellOpt, grid.h:449-494) --
 // ballot/popc compaction, no atomics, so the order is deterministic and equal to the reference's.
 // The matching lanes move the particle payload straight into the new sorted arrays.
-__global__ void __launch_bounds__(256) k_fill_incremental(DevGrid g, const DevState *st,
+__global__ void __launch_bounds__(256) k_fill_incremental(DevGrid g, const DevState *st, int par,
+        const int *__restrict__ occ_cells,
         const int *__restrict__ start_old, const int *__restrict__ start_new, const int *__restrict__ newcell,
         const float4 *__restrict__ pos_old, const float4 *__restrict__ vel_old, const int *__restrict__ pid_old,
         float4 *__restrict__ pos_new, float4 *__restrict__ vel_new, int *__restrict__ pid_new, int *__restrict__ cell_new)
 {
-    if(st->rebuild_flag | st->jump_flag) return; // full rebuild path takes over
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if(warp >= g.total) return;
-    int c = warp;
-    int dst = start_new[c];
-    int want = start_new[c + 1] - dst;
-    if(want == 0) return;
-    int cz = c / g.plane; int rem = c - cz * g.plane; int cy = rem / g.n[0]; int cx = rem - cy * g.n[0];
-    // lane k < 27 owns neighbour k = (dy, dx, dz) in reference order
-    int seg_s = 0, seg_len = 0;
-    if(lane < 27){
-        int dy = lane / 9 - 1, dx = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
-        int x = cx + dx, y = cy + dy, z = cz + dz;
-        if(x >= 0 && x < g.n[0] && y >= 0 && y < g.n[1] && z >= 0 && z < g.n[2]){
-            int nb = x + y * g.n[0] + z * g.plane;
-            seg_s = start_old[nb];
-            seg_len = start_old[nb + 1] - seg_s;
-        }
-    }
-    int found = 0;
-    for(int k = 0; k < 27 && found < want; k++){
-        int s = __shfl_sync(0xffffffffu, seg_s, k);
-        int len = __shfl_sync(0xffffffffu, seg_len, k);
-        for(int b = 0; b < len; b += 32){
-            int j = s + b + lane;
-            bool m = (b + lane < len) && (newcell[j] == c);
-            unsigned bal = __ballot_sync(0xffffffffu, m);
-            if(m){
-                int d = dst + found + __popc(bal & lanemask_lt());
-                pos_new[d] = pos_old[j];
-                vel_new[d] = vel_old[j];
-                pid_new[d] = pid_old[j];
-                cell_new[d] = c;
+    if(st->rebuild_flag[par] | st->jump_flag[par]) return; // full rebuild path takes over
+    const int n_occ = st->n_occ;
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    const unsigned gshift = grp * 8;
+    const int groups_total = (gridDim.x * blockDim.x) >> 3;
+    // all four groups of a warp iterate together (ballots are warp wide); a group without work idles
+    for(int w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; w0 < n_occ; w0 += groups_total){
+        const int w = w0 + grp;
+        const bool have = w < n_occ;
+        int c = have ? occ_cells[w] : 0;
+        int dst = 0, want = 0;
+        if(have){ dst = start_new[c]; want = start_new[c + 1] - dst; }
+        int cz = c / g.plane; int rem = c - cz * g.plane; int cy = rem / g.n[0]; int cx = rem - cy * g.n[0];
+        // lane `sub` owns neighbours k = sub, sub + 8, sub + 16, sub + 24 (k < 27) in reference order
+        int seg_s[4], seg_len[4];
+#pragma unroll
+        for(int q = 0; q < 4; q++){
+            int k = sub + 8 * q;
+            seg_s[q] = 0; seg_len[q] = 0;
+            if(have && k < 27){
+                int dy = k / 9 - 1, dx = (k / 3) % 3 - 1, dz = k % 3 - 1;
+                int x = cx + dx, y = cy + dy, z = cz + dz;
+                if(x >= 0 && x < g.n[0] && y >= 0 && y < g.n[1] && z >= 0 && z < g.n[2]){
+                    int nb = x + y * g.n[0] + z * g.plane;
+                    seg_s[q] = start_old[nb];
+                    seg_len[q] = start_old[nb + 1] - seg_s[q];
+                }
             }
-            found += __popc(bal);
+        }
+        int found = 0;
+#pragma unroll
+        for(int q = 0; q < 4; q++){
+#pragma unroll 1
+            for(int kk = 0; kk < 8; kk++){
+                if(q * 8 + kk >= 27) break;
+                int s = __shfl_sync(0xffffffffu, seg_s[q], kk, 8);
+                int len = __shfl_sync(0xffffffffu, seg_len[q], kk, 8);
+                if(found >= want) len = 0;
+                // trip count = longest segment among the 4 groups
+                int maxlen = len;
+                maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 8));
+                maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 16));
+#pragma unroll 1
+                for(int b = 0; b < maxlen; b += 8){
+                    int j = s + b + sub;
+                    bool m = (b + sub < len) && (newcell[j] == c);
+                    unsigned bal = (__ballot_sync(0xffffffffu, m) >> gshift) & 0xffu;
+                    if(m){
+                        int d = dst + found + __popc(bal & ((1u << sub) - 1u));
+                        pos_new[d] = pos_old[j];
+                        vel_new[d] = vel_old[j];
+                        pid_new[d] = pid_old[j];
+                        cell_new[d] = c;
+                    }
+                    found += __popc(bal);
+                }
+            }
         }
     }
 }
 
 // A3' (full rebuild path, rare: Setup and the big-move rule): chains in ascending particle id
 // (Grid::DistributeByParticle, grid.h:390-407).  scatter with atomics -> per-cell sort by id -> gather.
-__global__ void __launch_bounds__(256) k_full_scatter(int n, const DevState *st, int force, const int *__restrict__ newcell,
+// Grid-stride kernels: launched with a small grid every sub-step, they return at once unless the flags
+// (device side, no host round trip) ask for the rebuild.
+__global__ void __launch_bounds__(256) k_full_scatter(int n, const DevState *st, int par, int force, const int *__restrict__ newcell,
         const int *__restrict__ start_new, int *__restrict__ cursor, int *__restrict__ perm)
 {
-    if(!force && !(st->rebuild_flag | st->jump_flag)) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= n) return;
-    int c = newcell[i];
-    int k = atomicAdd(&cursor[c], 1);
-    perm[start_new[c] + k] = i;
-}
-__global__ void __launch_bounds__(256) k_full_sort_cells(int total, const DevState *st, int force, const int *__restrict__ start_new,
-        const int *__restrict__ pid_old, int *__restrict__ perm)
-{
-    if(!force && !(st->rebuild_flag | st->jump_flag)) return;
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if(c >= total) return;
-    int s = start_new[c], e = start_new[c + 1];
-    for(int a = s + 1; a < e; a++){ // insertion sort by original id (segments are a dozen long)
-        int pa = perm[a]; int ka = pid_old[pa];
-        int b = a - 1;
-        while(b >= s && pid_old[perm[b]] > ka){ perm[b + 1] = perm[b]; b--; }
-        perm[b + 1] = pa;
+    if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
+    for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x){
+        int c = newcell[i];
+        int k = atomicAdd(&cursor[c], 1);
+        perm[start_new[c] + k] = i;
     }
 }
-__global__ void __launch_bounds__(256) k_full_gather(int n, const DevState *st, int force, const int *__restrict__ perm,
+__global__ void __launch_bounds__(256) k_full_sort_cells(int total, const DevState *st, int par, int force, const int *__restrict__ start_new,
+        const int *__restrict__ pid_old, int *__restrict__ perm, int *__restrict__ cursor)
+{
+    if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
+    for(int c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x){
+        cursor[c] = 0; // back to an all-zero histogram for the next sub-step
+        int s = start_new[c], e = start_new[c + 1];
+        for(int a = s + 1; a < e; a++){ // insertion sort by original id (segments are a dozen long)
+            int pa = perm[a]; int ka = pid_old[pa];
+            int b = a - 1;
+            while(b >= s && pid_old[perm[b]] > ka){ perm[b + 1] = perm[b]; b--; }
+            perm[b + 1] = pa;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_full_gather(int n, const DevState *st, int par, int force, const int *__restrict__ perm,
         const int *__restrict__ newcell,
         const float4 *__restrict__ pos_old, const float4 *__restrict__ vel_old, const int *__restrict__ pid_old,
         float4 *__restrict__ pos_new, float4 *__restrict__ vel_new, int *__restrict__ pid_new, int *__restrict__ cell_new)
 {
-    if(!force && !(st->rebuild_flag | st->jump_flag)) return;
-    int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if(d >= n) return;
-    int j = perm[d];
-    pos_new[d] = pos_old[j];
-    vel_new[d] = vel_old[j];
-    pid_new[d] = pid_old[j];
-    cell_new[d] = newcell[j];
+    if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
+    for(int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x){
+        int j = perm[d];
+        pos_new[d] = pos_old[j];
+        vel_new[d] = vel_old[j];
+        pid_new[d] = pid_old[j];
+        cell_new[d] = newcell[j];
+    }
 }
-
-// one thread: latch the flags of this grid update and clear the per-step statistics
-// (data->sphpSet->ResetHigherLevel(), pcisph_solver3.cpp:47/54)
-__global__ void k_step_begin(DevState *st, int force_full){
-    st->full_rebuild = (force_full | st->rebuild_flag | st->jump_flag) ? 1 : 0;
-    st->rebuild_flag = 0;
-    st->jump_flag = 0;
-    st->overflow = 0;
-    st->clamped = 0;
-    st->nan_count = 0;
-    st->max_force_bits = 0;
-    st->max_err_bits = 0;
-}
-__global__ void k_clear_lost(DevState *st){ st->lost = 0; }
 
 // ------------------------------------------------------------------ run table of a particle's cell
 // base[r] / end[r] of the 9 runs r = (dy+1)*3 + (dz+1) of cell c
@@ -236,81 +277,233 @@ __device__ __forceinline__ void bbx_store_entry(unsigned short *__restrict__ nbr
     size_t warp = (size_t)(i >> 5); int lane = i & 31;
     nbr[((warp * BBX_NBR_CHUNKS + (k >> 3)) * 32 + lane) * 8 + (k & 7)] = (unsigned short)e;
 }
+__device__ __forceinline__ uint4 *bbx_chunk_ptr(unsigned short *__restrict__ nbr, int i, int chunk){
+    return reinterpret_cast<uint4 *>(nbr) + ((size_t)(i >> 5) * BBX_NBR_CHUNKS + chunk) * 32 + (i & 31);
+}
 
 // ---------------------------------------------------------- B: neighbour lists + density (sweep 1)
-// One thread per particle.  Walks the 9 runs, tests every candidate with the reference's IsWithinStd
-// predicate (bit-exact, see bbx_accept), stores the accepted ones as compact list entries and
-// accumulates rho_i = m * sum W_std (ComputeDensityFor, sph_equations3.cpp:25-58).  The stored list is
-// the reference's per-particle Bucket (grid.h:422-447) up to ordering; when a particle has more than
-// 100 neighbours the slow path re-walks the 27 cells in the reference's order and keeps the first 100
-// exactly like Bucket::Insert (particle.h:44-50).
-template<int SPH_EOS>
-__global__ void __launch_bounds__(BBX_BS) k_build_density(StepParams P, DevGrid g, DevState *st,
-        const float4 *__restrict__ pos, float4 *__restrict__ vel, const int *__restrict__ cell,
-        const int *__restrict__ cell_start, unsigned short *__restrict__ nbr, int *__restrict__ nbr_cnt,
-        float *__restrict__ pressure, float4 *__restrict__ posq)
+// Slow path of one particle whose list would exceed 100 entries: re-walk the 27 cells in the reference's
+// order (y outer, x middle, z inner; chain order inside a cell) and keep the first 100 exactly like
+// Bucket::Insert (particle.h:44-50); the density is the sum over exactly those.
+__device__ __noinline__ void bbx_list_overflow(const StepParams &P, const DevGrid &g, DevState *st,
+        const float4 *__restrict__ pos, const int *__restrict__ cell_start, unsigned short *__restrict__ nbr,
+        int i, int c, float4 pi, int *cnt_out, float *sum_out)
 {
-    int i = blockIdx.x * BBX_BS + threadIdx.x;
-    if(i >= P.n) return;
-    float4 pi = pos[i];
-    int c = cell[i];
-    int base[9], end[9];
-    bbx_runs(g, cell_start, c, base, end);
-    int cnt = 0; bool over = false; float sum = 0.f;
-#pragma unroll 1
-    for(int r = 0; r < 9 && !over; r++){
-        int b = base[r], e = end[r];
-        if(e - b > BBX_MAX_RUN_LEN){ st->error = BBX_ERR_CAPACITY; e = b + BBX_MAX_RUN_LEN; }
-        for(int j = b; j < e; j++){
+    atomicAdd(&st->overflow, 1);
+    int cnt = 0; float sum = 0.f;
+    int cz = c / g.plane; int rem = c - cz * g.plane; int cy = rem / g.n[0]; int cx = rem - cy * g.n[0];
+    int xlo = max(cx - 1, 0);
+    for(int dy = -1; dy <= 1; dy++) for(int dx_ = -1; dx_ <= 1; dx_++) for(int dz = -1; dz <= 1; dz++){
+        int x = cx + dx_, y = cy + dy, z = cz + dz;
+        if(x < 0 || x >= g.n[0] || y < 0 || y >= g.n[1] || z < 0 || z >= g.n[2]) continue;
+        int nb = x + y * g.n[0] + z * g.plane;
+        int r = (dy + 1) * 3 + (dz + 1);
+        int rb = cell_start[xlo + y * g.n[0] + z * g.plane];
+        int s = cell_start[nb], e = cell_start[nb + 1];
+        for(int j = s; j < e && cnt < BBX_MAX_NEIGHBORS; j++){
+            if(j - rb >= BBX_MAX_RUN_LEN) break;
             float4 pj = pos[j];
-            float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-            float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            float ddx = pi.x - pj.x, ddy = pi.y - pj.y, ddz = pi.z - pj.z;
+            float d2 = fmaf(ddx, ddx, fmaf(ddy, ddy, ddz * ddz));
             if(bbx_accept(P, pi, pj, d2)){
-                if(cnt == BBX_MAX_NEIGHBORS){ over = true; break; }
-                float x = fmaxf(0.f, 1.f - d2 * P.inv_h2);
-                sum += x * x * x;
-                bbx_store_entry(nbr, i, cnt, ((unsigned)r << BBX_RUN_SHIFT) | (unsigned)(j - b));
+                float xx = fmaxf(0.f, 1.f - d2 * P.inv_h2);
+                sum += xx * xx * xx;
+                bbx_store_entry(nbr, i, cnt, ((unsigned)r << BBX_RUN_SHIFT) | (unsigned)(j - rb));
                 cnt++;
             }
         }
     }
-    if(over){
-        // reference order: y outer, x middle, z inner; chain order inside a cell; first 100 kept
-        atomicAdd(&st->overflow, 1);
-        cnt = 0; sum = 0.f;
-        int cz = c / g.plane; int rem = c - cz * g.plane; int cy = rem / g.n[0]; int cx = rem - cy * g.n[0];
-        int xlo = max(cx - 1, 0);
-        for(int dy = -1; dy <= 1; dy++) for(int dx_ = -1; dx_ <= 1; dx_++) for(int dz = -1; dz <= 1; dz++){
-            int x = cx + dx_, y = cy + dy, z = cz + dz;
-            if(x < 0 || x >= g.n[0] || y < 0 || y >= g.n[1] || z < 0 || z >= g.n[2]) continue;
-            int nb = x + y * g.n[0] + z * g.plane;
-            int r = (dy + 1) * 3 + (dz + 1);
-            int rb = cell_start[xlo + y * g.n[0] + z * g.plane];
-            int s = cell_start[nb], e = cell_start[nb + 1];
-            for(int j = s; j < e && cnt < BBX_MAX_NEIGHBORS; j++){
-                if(j - rb >= BBX_MAX_RUN_LEN) break;
-                float4 pj = pos[j];
-                float ddx = pi.x - pj.x, ddy = pi.y - pj.y, ddz = pi.z - pj.z;
-                float d2 = fmaf(ddx, ddx, fmaf(ddy, ddy, ddz * ddz));
-                if(bbx_accept(P, pi, pj, d2)){
-                    float xx = fmaxf(0.f, 1.f - d2 * P.inv_h2);
-                    sum += xx * xx * xx;
-                    bbx_store_entry(nbr, i, cnt, ((unsigned)r << BBX_RUN_SHIFT) | (unsigned)(j - rb));
-                    cnt++;
+    *cnt_out = cnt; *sum_out = sum;
+}
+
+// One thread owns BBX_DR consecutive particles (same cell, or x-adjacent cells of one row, in the common
+// case) and walks the union of their 27-cell windows ONCE: every candidate position read from the staged
+// tile is tested against all BBX_DR particles (register blocking), branch-free: the accept decisions go into
+// bit masks, rho_i = m * sum W_std (ComputeDensityFor, sph_equations3.cpp:25-58) is accumulated with the
+// clamped kernel for every candidate (W = 0 outside the support).  After each block of 32 candidates the
+// masks are turned into compact list entries (run, offset) -- the reference's per-particle Bucket
+// (grid.h:422-447) up to ordering -- packed 8 to a uint4 and stored coalesced.  The IsWithinStd decision
+// is bit-exact: FP32 away from the threshold, FP64 re-check inside a guard band (bbx_within_std_exact).
+// A candidate outside a particle's own 27 cells (but inside the union window) is at least one cell
+// length away, so the distance test rejects it; MASKED = 1 adds the explicit window test for grids
+// whose cells are smaller than h.
+#define BBX_DR 4
+struct DensityAcc {
+    unsigned long long acc, lo;
+    int cnt;
+    float sum;
+    bool over;
+};
+__device__ __forceinline__ void bbx_append(DensityAcc &a, unsigned short *__restrict__ nbr, int i, unsigned e16){
+    a.acc |= (unsigned long long)e16 << ((a.cnt & 3) * 16);
+    a.cnt++;
+    if((a.cnt & 3) == 0){
+        if(a.cnt & 4){ a.lo = a.acc; }
+        else{
+            *bbx_chunk_ptr(nbr, i, (a.cnt >> 3) - 1) = make_uint4((unsigned)a.lo, (unsigned)(a.lo >> 32), (unsigned)a.acc, (unsigned)(a.acc >> 32));
+        }
+        a.acc = 0ull;
+    }
+}
+
+// Work decomposition: CTA (row, k) owns the particles [row_start + 512 k, +512) of one cell row (same y, z;
+// x fastest), 4 consecutive particles per thread.  For each of the 9 runs the union window of the CTA's
+// particles is one contiguous slot range; it is staged through shared memory in tiles of BBX_DTILE
+// positions (coalesced float4 loads) so that the divergent per-lane window walks hit shared memory
+// (conflict-light broadcast reads) instead of costing one L1 wavefront per distinct cell.
+#define BBX_DTILE 512
+#define BBX_DSPLIT 4
+template<int SPH_EOS, int MASKED>
+__global__ void __launch_bounds__(BBX_BS) k_density_lists(StepParams P, DevGrid g, DevState *st,
+        const float4 *__restrict__ pos, float4 *__restrict__ vel, const int *__restrict__ cell,
+        const int *__restrict__ cell_start, unsigned short *__restrict__ nbr, int *__restrict__ nbr_cnt,
+        float *__restrict__ pressure, float4 *__restrict__ posq)
+{
+    __shared__ float4 tile[BBX_DTILE + 8];
+    const int row = blockIdx.x;                       // y + z * ny
+    const int rowbase = row * g.n[0];                 // first cell of the row
+    const int rs = cell_start[rowbase], re = cell_start[rowbase + g.n[0]];
+    if(rs == re) return;
+    const int cy = row % g.n[1], cz = row / g.n[1];
+    const float far = 1.0e30f;
+    for(int p0 = rs + blockIdx.y * (BBX_BS * BBX_DR); p0 < re; p0 += BBX_DSPLIT * BBX_BS * BBX_DR){
+        const int p1 = min(p0 + BBX_BS * BBX_DR, re);
+        const int first = p0 + threadIdx.x * BBX_DR;
+        const int m = max(0, min(BBX_DR, p1 - first));
+        // window of the whole CTA chunk (uniform): cells xf-1 .. xl+1
+        const int xf = cell[p0] - rowbase, xl = cell[p1 - 1] - rowbase;
+        const int wlo = max(xf - 1, 0), whi = min(xl + 1, g.n[0] - 1);
+        float xi[BBX_DR], yi[BBX_DR], zi[BBX_DR]; int ci[BBX_DR];
+        DensityAcc A[BBX_DR];
+#pragma unroll
+        for(int r = 0; r < BBX_DR; r++){
+            int i = min(first + min(r, max(m - 1, 0)), p1 - 1);
+            float4 p = pos[i];
+            xi[r] = p.x; yi[r] = p.y; zi[r] = p.z; ci[r] = cell[i];
+            A[r].acc = 0ull; A[r].lo = 0ull; A[r].cnt = 0; A[r].sum = 0.f; A[r].over = false;
+        }
+        // groups of this thread: particles of x-span <= 2 walk one union window (usually a single group)
+        unsigned todo0 = (1u << m) - 1u;
+#pragma unroll 1
+        for(int run = 0; run < 9; run++){
+            const int y = cy + run / 3 - 1, z = cz + run % 3 - 1;
+            if(y < 0 || y >= g.n[1] || z < 0 || z >= g.n[2]) continue;   // uniform over the CTA
+            const int rr = (y + z * g.n[1]) * g.n[0];
+            const int S = cell_start[rr + wlo], E = cell_start[rr + whi + 1];
+#pragma unroll 1
+            for(int ts = S; ts < E; ts += BBX_DTILE){
+                const int te = min(ts + BBX_DTILE, E);
+                __syncthreads();
+                for(int k = threadIdx.x; k < te - ts; k += BBX_BS) tile[k] = pos[ts + k];
+                __syncthreads();
+                unsigned todo = todo0;
+                while(todo){
+                    const int lead = __ffs(todo) - 1;
+                    int cl = ci[0];
+#pragma unroll
+                    for(int r = 1; r < BBX_DR; r++) if(lead == r) cl = ci[r];
+                    const int cx0 = cl - rowbase;
+                    unsigned gm = 0; int span = 0;
+                    int cxr[BBX_DR];
+#pragma unroll
+                    for(int r = 0; r < BBX_DR; r++){
+                        int dx = ci[r] - cl;
+                        cxr[r] = cx0; // non-members keep a valid column (their results are never used)
+                        if(((todo >> r) & 1u) && dx >= 0 && dx <= 2){ gm |= 1u << r; span = max(span, dx); cxr[r] = cx0 + dx; }
+                    }
+                    todo &= ~gm;
+                    float xe[BBX_DR];
+#pragma unroll
+                    for(int r = 0; r < BBX_DR; r++) xe[r] = ((gm >> r) & 1u) ? xi[r] : far;
+                    const int xlo = max(cx0 - 1, 0), xhi = min(cx0 + span + 1, g.n[0] - 1);
+                    const int b = max(cell_start[rr + xlo], ts), e = min(cell_start[rr + xhi + 1], te);
+                    if(b >= e) continue;
+                    // own run base (list entries are relative to it) and, MASKED, own window
+                    int ob[BBX_DR], oe[BBX_DR];
+#pragma unroll
+                    for(int r = 0; r < BBX_DR; r++){
+                        ob[r] = cell_start[rr + max(cxr[r] - 1, 0)];
+                        oe[r] = cell_start[rr + min(cxr[r] + 1, g.n[0] - 1) + 1];
+                        if(((gm >> r) & 1u) && oe[r] - ob[r] > BBX_MAX_RUN_LEN) st->error = BBX_ERR_CAPACITY;
+                    }
+#pragma unroll 1
+                    for(int jb = b; jb < e; jb += 32){
+                        unsigned mlo[BBX_DR], mhi[BBX_DR];
+#pragma unroll
+                        for(int r = 0; r < BBX_DR; r++){ mlo[r] = 0u; mhi[r] = 0u; }
+                        const int left = e - jb;
+                        const float4 *tp = tile + (jb - ts);
+#pragma unroll
+                        for(int q = 0; q < 4; q++){
+                            if(q * 8 < left){
+#pragma unroll
+                                for(int u = 0; u < 8; u++){
+                                    const int t = q * 8 + u;
+                                    float4 pj = tp[t];                  // the tile is padded: reads past `left` stay inside
+                                    if(t >= left) pj.x = -far;          // ... and are pushed out of every support
+#pragma unroll
+                                    for(int r = 0; r < BBX_DR; r++){
+                                        float dx = pj.x - xe[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
+                                        float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                                        if(d2 < P.thr_lo) mlo[r] |= 1u << t;
+                                        if(d2 <= P.thr_hi) mhi[r] |= 1u << t;
+                                        float x = fmaxf(0.f, fmaf(-d2, P.inv_h2, 1.f));
+                                        A[r].sum = fmaf(x * x, x, A[r].sum);
+                                    }
+                                }
+                            }
+                        }
+                        // masks -> list entries
+#pragma unroll
+                        for(int r = 0; r < BBX_DR; r++){
+                            if(MASKED){
+                                // keep only candidates of the particle's own 3 cells of this row
+                                int lo_t = ob[r] - jb, hi_t = oe[r] - jb; // valid t: lo_t <= t < hi_t
+                                unsigned wm = (hi_t <= 0 || lo_t >= 32) ? 0u : ((hi_t >= 32 ? 0xffffffffu : ((1u << hi_t) - 1u)) & (lo_t <= 0 ? 0xffffffffu : ~((1u << lo_t) - 1u)));
+                                mlo[r] &= wm; mhi[r] &= wm;
+                            }
+                            unsigned acc_m = mlo[r];
+                            unsigned unc = mhi[r] & ~mlo[r];
+                            while(unc){ // inside the guard band: decide exactly as the reference does (FP64)
+                                int t = __ffs(unc) - 1; unc &= unc - 1u;
+                                if(bbx_within_std_exact(make_float4(xi[r], yi[r], zi[r], 0.f), tp[t], P.h2_d)) acc_m |= 1u << t;
+                            }
+                            if(A[r].over || A[r].cnt + __popc(acc_m) > BBX_MAX_NEIGHBORS){ A[r].over = true; acc_m = 0u; }
+                            const unsigned ebase = ((unsigned)run << BBX_RUN_SHIFT) + (unsigned)(jb - ob[r]);
+                            while(acc_m){
+                                int t = __ffs(acc_m) - 1; acc_m &= acc_m - 1u;
+                                bbx_append(A[r], nbr, first + r, ebase + (unsigned)t);
+                            }
+                        }
+                    }
                 }
             }
         }
-    }
-    nbr_cnt[i] = cnt;
-    float rho = P.mass * P.w_std_c * sum;
-    // density rides in vel.w (nobody reads vel in this kernel)
-    reinterpret_cast<float *>(vel)[4 * (size_t)i + 3] = rho;
-    if(SPH_EOS){
-        // Tait EOS, ComputePressureValue (sph_equations3.cpp:7-18)
-        float p = P.eos_scale * (powf(rho / P.rho0, P.eos_exponent) - 1.f);
-        if(p < 0.f) p *= P.neg_pressure_scale;
-        pressure[i] = p;
-        posq[i] = make_float4(pi.x, pi.y, pi.z, p / (rho * rho));
+        // epilogue: flush the partial chunk, cap-100 slow path, density (rides in vel.w), optional Tait EOS
+#pragma unroll
+        for(int r = 0; r < BBX_DR; r++){
+            if(r < m){
+                const int i = first + r;
+                int cnt = A[r].cnt; float sum = A[r].sum;
+                if(A[r].over){
+                    bbx_list_overflow(P, g, st, pos, cell_start, nbr, i, ci[r], make_float4(xi[r], yi[r], zi[r], 0.f), &cnt, &sum);
+                }else if(cnt & 7){
+                    uint4 v = (cnt & 4) ? make_uint4((unsigned)A[r].lo, (unsigned)(A[r].lo >> 32), (unsigned)A[r].acc, (unsigned)(A[r].acc >> 32))
+                                        : make_uint4((unsigned)A[r].acc, (unsigned)(A[r].acc >> 32), 0u, 0u);
+                    *bbx_chunk_ptr(nbr, i, cnt >> 3) = v;
+                }
+                nbr_cnt[i] = cnt;
+                float rho = P.mass * P.w_std_c * sum;
+                reinterpret_cast<float *>(vel)[4 * (size_t)i + 3] = rho;
+                if(SPH_EOS){
+                    // Tait EOS, ComputePressureValue (sph_equations3.cpp:7-18)
+                    float p = P.eos_scale * (powf(rho / P.rho0, P.eos_exponent) - 1.f);
+                    if(p < 0.f) p *= P.neg_pressure_scale;
+                    pressure[i] = p;
+                    posq[i] = make_float4(xi[r], yi[r], zi[r], p / (rho * rho));
+                }
+            }
+        }
     }
 }
 
@@ -346,14 +539,27 @@ __device__ __forceinline__ void bbx_for_each_neighbor(const uint4 *__restrict__ 
 }
 #define BBX_LIST_FOREACH(J, ...) bbx_for_each_neighbor(lp, cnt, sbase + threadIdx.x, [&](int J) __VA_ARGS__ );
 
+// max over the sub-step of a non-negative float (its bits order like unsigned): warp max first, then one
+// atomic per warp; a partially active warp falls back to one atomic per thread
+__device__ __forceinline__ void bbx_atomic_max_warp(unsigned *addr, float v){
+    if(__activemask() == 0xffffffffu){
+        for(int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if((threadIdx.x & 31) == 0) atomicMax(addr, __float_as_uint(v));
+    }else atomicMax(addr, __float_as_uint(v));
+}
+
+// d and 1/d of a squared distance without the IEEE sqrt sequence: MUFU.RSQ + 1 multiply (2 ulp)
+__device__ __forceinline__ float bbx_rsqrt_safe(float d2){ return rsqrtf(fmaxf(d2, 1.0e-30f)); }
+
 // --------------------------------- C+D: non-pressure forces + first prediction (sweep 2)
 // f_i = m g - c_drag v_i + mu m^2 sum_j (v_j - v_i) d2W_spiky(d) / rho_j   (ComputeNonPressureForceFor,
 // sph_equations3.cpp:80-110), then x* = x + dt (v + dt/m f), collide (restitution 0)
-// (PredictVelocityAndPositionFor with is_first, pcisph_equations3.cpp:3-28).
-__global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGrid g, const DevColliderSet *__restrict__ cs,
+// (PredictVelocityAndPositionFor with is_first, pcisph_equations3.cpp:3-28).  A particle the FP32
+// pre-check cannot clear of every collider is queued for k_collide_predict.
+__global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGrid g, DevState *st, const DevCullSet *__restrict__ cull,
         const float4 *__restrict__ pos, const float4 *__restrict__ vel, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
-        float4 *__restrict__ force, float4 *__restrict__ pred)
+        float4 *__restrict__ force, float4 *__restrict__ pred, int *__restrict__ queue)
 {
     BBX_LIST_PROLOGUE();
     if(!live) return;
@@ -363,8 +569,8 @@ __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGr
         float4 pj = pos[j]; float4 vj = vel[j];
         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
         float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        float d = sqrtf(d2);
-        float x = fmaxf(0.f, 1.f - d * P.inv_h);
+        float d = d2 * bbx_rsqrt_safe(d2);
+        float x = fmaxf(0.f, fmaf(-d, P.inv_h, 1.f));
         float w = __fdividef(x, vj.w);
         ax = fmaf(vj.x - vi.x, w, ax); ay = fmaf(vj.y - vi.y, w, ay); az = fmaf(vj.z - vi.z, w, az);
     })
@@ -376,23 +582,45 @@ __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGr
     float k = P.dt * P.inv_mass;
     float tvx = vi.x + k * fx, tvy = vi.y + k * fy, tvz = vi.z + k * fz;
     float tpx = pi.x + P.dt * tvx, tpy = pi.y + P.dt * tvy, tpz = pi.z + P.dt * tvz;
-    bbx_resolve_collision(*cs, (double)P.radius, 0.0, &tpx, &tpy, &tpz, &tvx, &tvy, &tvz);
     pred[i] = make_float4(tpx, tpy, tpz, 0.f);
+    if(!bbx_cull(*cull, tpx, tpy, tpz, P.radius)) queue[atomicAdd(&st->qn[0], 1)] = i;
+}
+
+// x* of one particle from its forces + the exact collider response (restitution 0)
+__device__ __forceinline__ float4 bbx_predict_exact(const StepParams &P, const DevColliderSet &cs, float4 pi, float4 vi, float fx, float fy, float fz){
+    float k = P.dt * P.inv_mass;
+    float tvx = vi.x + k * fx, tvy = vi.y + k * fy, tvz = vi.z + k * fz;
+    float tpx = pi.x + P.dt * tvx, tpy = pi.y + P.dt * tvy, tpz = pi.z + P.dt * tvz;
+    bbx_resolve_collision(cs, (double)P.radius, 0.0, &tpx, &tpy, &tpz, &tvx, &tvy, &tvz);
+    return make_float4(tpx, tpy, tpz, 0.f);
+}
+// queued particles of k_force_np_predict: redo the prediction with the exact FP64 response
+__global__ void __launch_bounds__(128) k_collide_predict(StepParams P, const DevState *st, const DevColliderSet *__restrict__ cs,
+        const int *__restrict__ queue, const float4 *__restrict__ pos, const float4 *__restrict__ vel,
+        const float4 *__restrict__ force, float4 *__restrict__ pred)
+{
+    const int qn = st->qn[0];
+    for(int q = blockIdx.x * blockDim.x + threadIdx.x; q < qn; q += gridDim.x * blockDim.x){
+        int i = queue[q];
+        float4 f = force[i];
+        pred[i] = bbx_predict_exact(P, *cs, pos[i], vel[i], f.x, f.y, f.z);
+    }
 }
 
 // later iterations of the predict-correct loop ("correct" mode): x* from f_np + f_p, no neighbour sum
-__global__ void __launch_bounds__(256) k_predict_again(StepParams P, const DevColliderSet *__restrict__ cs,
+__global__ void __launch_bounds__(256) k_predict_again(StepParams P, const DevColliderSet *__restrict__ cs, const DevCullSet *__restrict__ cull,
         const float4 *__restrict__ pos, const float4 *__restrict__ vel, const float4 *__restrict__ force,
         const float4 *__restrict__ force_p, float4 *__restrict__ pred)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= P.n) return;
     float4 pi = pos[i], vi = vel[i], f = force[i], fp = force_p[i];
+    float fx = f.x + fp.x, fy = f.y + fp.y, fz = f.z + fp.z;
     float k = P.dt * P.inv_mass;
-    float tvx = vi.x + k * (f.x + fp.x), tvy = vi.y + k * (f.y + fp.y), tvz = vi.z + k * (f.z + fp.z);
+    float tvx = vi.x + k * fx, tvy = vi.y + k * fy, tvz = vi.z + k * fz;
     float tpx = pi.x + P.dt * tvx, tpy = pi.y + P.dt * tvy, tpz = pi.z + P.dt * tvz;
-    bbx_resolve_collision(*cs, (double)P.radius, 0.0, &tpx, &tpy, &tpz, &tvx, &tvy, &tvz);
-    pred[i] = make_float4(tpx, tpy, tpz, 0.f);
+    if(bbx_cull(*cull, tpx, tpy, tpz, P.radius)) pred[i] = make_float4(tpx, tpy, tpz, 0.f);
+    else pred[i] = bbx_predict_exact(P, *cs, pi, vi, fx, fy, fz);
 }
 
 // ----------------------------------------------------------- E: predicted density -> pressure (sweep 3)
@@ -412,7 +640,7 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure(StepParams P, DevGrid g, De
         float4 pj = pred[j];
         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
         float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        float x = fmaxf(0.f, 1.f - d2 * P.inv_h2);
+        float x = fmaxf(0.f, fmaf(-d2, P.inv_h2, 1.f));
         sum = fmaf(x * x, x, sum);
     })
     float rho = P.mass * P.w_std_c * sum;
@@ -427,7 +655,41 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure(StepParams P, DevGrid g, De
     float rho2 = rho * rho;
     // the reference skips a neighbour whose rho*^2 is ~0 (pcisph_equations3.cpp:137): NaN marks it
     posq[i] = make_float4(x0.x, x0.y, x0.z, (rho2 < 1e-8f) ? __int_as_float(0x7fc00000) : p / rho2);
-    atomicMax(&st->max_err_bits, __float_as_uint(fabsf(err)));
+    bbx_atomic_max_warp(&st->max_err_bits, fabsf(err));
+}
+
+// integration of one particle: v += dt f/m, x += dt v, collide (restitution), domain clamp
+// (TimeIntegrationFor, sph_equations3.cpp:283-328).  EXACT = 0 is the FP32 fast path, valid when the
+// pre-checks cleared the colliders and the domain faces.
+template<int EXACT>
+__device__ __forceinline__ void bbx_integrate_one(const StepParams &P, const DevGrid &g, DevState *st, const DevColliderSet *cs,
+        float4 pi, float4 v, float fx, float fy, float fz, float4 *pos_out, float4 *vel_out)
+{
+    float vx = v.x + P.dt * (fx * P.inv_mass), vy = v.y + P.dt * (fy * P.inv_mass), vz = v.z + P.dt * (fz * P.inv_mass);
+    float px = pi.x + P.dt * vx, py = pi.y + P.dt * vy, pz = pi.z + P.dt * vz;
+    if(EXACT){
+        bbx_resolve_collision(*cs, (double)P.radius, (double)P.restitution, &px, &py, &pz, &vx, &vy, &vz);
+        // domain clamp (sph_equations3.cpp:317-326)
+        if(!inside_bounds(v3(px, py, pz), v3(g.min[0], g.min[1], g.min[2]), v3(g.max[0], g.max[1], g.max[2]))){
+            double r = (double)P.radius;
+            px = (float)clampd(px, g.min[0] + r, g.max[0] - r);
+            py = (float)clampd(py, g.min[1] + r, g.max[1] - r);
+            pz = (float)clampd(pz, g.min[2] + r, g.max[2] - r);
+            atomicAdd(&st->clamped, 1);
+        }
+    }
+    *pos_out = make_float4(px, py, pz, 0.f);
+    *vel_out = make_float4(vx, vy, vz, v.w);
+}
+// big-move rule (sph_equations3.cpp:330-335) and the non-finite counter, on the final position
+__device__ __forceinline__ void bbx_integrate_flags(const StepParams &P, DevState *st, float4 pi, float4 po){
+    float mx = po.x - pi.x, my = po.y - pi.y, mz = po.z - pi.z;
+    if(sqrtf(mx * mx + my * my + mz * mz) >= P.min_cell_len09) st->rebuild_flag[P.par ^ 1] = 1;
+    if(!(isfinite(po.x) && isfinite(po.y) && isfinite(po.z))) atomicAdd(&st->nan_count, 1);
+}
+// max |f| of the sub-step for the CFL scan (particle.h:591-597)
+__device__ __forceinline__ void bbx_reduce_max_force(DevState *st, float f2){
+    bbx_atomic_max_warp(&st->max_force_bits, sqrtf(f2));
 }
 
 // -------------------------------------- F+G: pressure force (+ accumulate, integrate, collide) (sweep 4)
@@ -435,12 +697,13 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure(StepParams P, DevGrid g, De
 // (PredictPressureForceFor, pcisph_equations3.cpp:114-155); INTEGRATE: f += f_p, v += dt f/m, x += dt v,
 // collide (restitution 0.6), domain clamp, big-move flag (AccumulateForcesFor + TimeIntegrationFor,
 // pcisph_equations3.cpp:179-197, sph_equations3.cpp:283-339).  Positions are updated in place: neighbours
-// are read from posq, never from pos, so there is no read/write race.
+// are read from posq, never from pos, so there is no read/write race.  Particles near a collider or a
+// domain face (FP32 pre-check undecided) are queued for k_collide_integrate.
 template<int INTEGRATE>
-__global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid g, DevState *st, const DevColliderSet *__restrict__ cs,
+__global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid g, DevState *st, const DevCullSet *__restrict__ cull,
         float4 *__restrict__ pos, float4 *__restrict__ vel, const float4 *__restrict__ posq, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
-        float4 *__restrict__ force, float4 *__restrict__ force_p)
+        float4 *__restrict__ force, float4 *__restrict__ force_p, int *__restrict__ queue)
 {
     BBX_LIST_PROLOGUE();
     if(!live) return;
@@ -451,11 +714,11 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid
         float4 pj = posq[j];
         float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
         float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        float d = sqrtf(d2);
-        float x = fmaxf(0.f, 1.f - d * P.inv_h);
-        // j == i, coincident points and NaN-marked neighbours contribute nothing
-        bool ok = (j != i) && (d > 1e-8f) && (pj.w == pj.w);
-        float w = ok ? __fdividef((qi + pj.w) * x * x, d) : 0.f;
+        // j == i and coincident points (d ~ 0) and NaN-marked neighbours contribute nothing
+        float inv_d = (d2 > 1.0e-16f && pj.w == pj.w) ? rsqrtf(d2) : 0.f;
+        float x = fmaxf(0.f, fmaf(-d2 * inv_d, P.inv_h, 1.f));
+        float w = (qi + pj.w) * (x * x) * inv_d;
+        w = (inv_d > 0.f) ? w : 0.f;
         tx = fmaf(dx, w, tx); ty = fmaf(dy, w, ty); tz = fmaf(dz, w, tz);
     })
     float s = -P.mass2 * P.dw_spiky_c;
@@ -465,28 +728,35 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid
         float4 f = force[i]; float4 v = vel[i];
         float fx = f.x + fpx, fy = f.y + fpy, fz = f.z + fpz;
         force[i] = make_float4(fx, fy, fz, 0.f);
-        float vx = v.x + P.dt * (fx * P.inv_mass), vy = v.y + P.dt * (fy * P.inv_mass), vz = v.z + P.dt * (fz * P.inv_mass);
-        float px = pi.x + P.dt * vx, py = pi.y + P.dt * vy, pz = pi.z + P.dt * vz;
-        bbx_resolve_collision(*cs, (double)P.radius, (double)P.restitution, &px, &py, &pz, &vx, &vy, &vz);
-        // domain clamp (sph_equations3.cpp:317-326)
-        if(!inside_bounds(v3(px, py, pz), v3(g.min[0], g.min[1], g.min[2]), v3(g.max[0], g.max[1], g.max[2]))){
-            double r = (double)P.radius;
-            px = (float)clampd(px, g.min[0] + r, g.max[0] - r);
-            py = (float)clampd(py, g.min[1] + r, g.max[1] - r);
-            pz = (float)clampd(pz, g.min[2] + r, g.max[2] - r);
-            atomicAdd(&st->clamped, 1);
+        bbx_reduce_max_force(st, fmaf(fx, fx, fmaf(fy, fy, fz * fz)));
+        float4 po, vo;
+        bbx_integrate_one<0>(P, g, st, nullptr, pi, v, fx, fy, fz, &po, &vo);
+        if(bbx_cull(*cull, po.x, po.y, po.z, P.radius) && bbx_inside_domain_certain(*cull, po.x, po.y, po.z)){
+            bbx_integrate_flags(P, st, pi, po);
+            pos[i] = po; vel[i] = vo;
+        }else{
+            queue[atomicAdd(&st->qn[1], 1)] = i; // pos / vel stay untouched: the exact kernel redoes the update
         }
-        float mx = px - pi.x, my = py - pi.y, mz = pz - pi.z;
-        if(sqrtf(mx * mx + my * my + mz * mz) >= P.min_cell_len09) st->rebuild_flag = 1;
-        if(!(isfinite(px) && isfinite(py) && isfinite(pz))) atomicAdd(&st->nan_count, 1);
-        pos[i] = make_float4(px, py, pz, 0.f);
-        vel[i] = make_float4(vx, vy, vz, v.w);
-        atomicMax(&st->max_force_bits, __float_as_uint(sqrtf(fx * fx + fy * fy + fz * fz)));
+    }
+}
+// queued particles of k_pressure_force<1>: the exact FP64 collider response + domain clamp
+__global__ void __launch_bounds__(128) k_collide_integrate(StepParams P, DevGrid g, DevState *st, const DevColliderSet *__restrict__ cs,
+        const int *__restrict__ queue, float4 *__restrict__ pos, float4 *__restrict__ vel, const float4 *__restrict__ force)
+{
+    const int qn = st->qn[1];
+    for(int q = blockIdx.x * blockDim.x + threadIdx.x; q < qn; q += gridDim.x * blockDim.x){
+        int i = queue[q];
+        float4 f = force[i];
+        float4 po, vo;
+        float4 pi = pos[i];
+        bbx_integrate_one<1>(P, g, st, cs, pi, vel[i], f.x, f.y, f.z, &po, &vo);
+        bbx_integrate_flags(P, st, pi, po);
+        pos[i] = po; vel[i] = vo;
     }
 }
 
 // integrate alone ("correct" mode after the loop, and the SPH step)
-__global__ void __launch_bounds__(256) k_integrate(StepParams P, DevGrid g, DevState *st, const DevColliderSet *__restrict__ cs,
+__global__ void __launch_bounds__(256) k_integrate(StepParams P, DevGrid g, DevState *st, const DevColliderSet *__restrict__ cs, const DevCullSet *__restrict__ cull,
         float4 *__restrict__ pos, float4 *__restrict__ vel, float4 *__restrict__ force, const float4 *__restrict__ force_p)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -494,22 +764,13 @@ __global__ void __launch_bounds__(256) k_integrate(StepParams P, DevGrid g, DevS
     float4 pi = pos[i], v = vel[i], f = force[i];
     float fx = f.x, fy = f.y, fz = f.z;
     if(force_p){ float4 fp = force_p[i]; fx += fp.x; fy += fp.y; fz += fp.z; force[i] = make_float4(fx, fy, fz, 0.f); }
-    float vx = v.x + P.dt * (fx * P.inv_mass), vy = v.y + P.dt * (fy * P.inv_mass), vz = v.z + P.dt * (fz * P.inv_mass);
-    float px = pi.x + P.dt * vx, py = pi.y + P.dt * vy, pz = pi.z + P.dt * vz;
-    bbx_resolve_collision(*cs, (double)P.radius, (double)P.restitution, &px, &py, &pz, &vx, &vy, &vz);
-    if(!inside_bounds(v3(px, py, pz), v3(g.min[0], g.min[1], g.min[2]), v3(g.max[0], g.max[1], g.max[2]))){
-        double r = (double)P.radius;
-        px = (float)clampd(px, g.min[0] + r, g.max[0] - r);
-        py = (float)clampd(py, g.min[1] + r, g.max[1] - r);
-        pz = (float)clampd(pz, g.min[2] + r, g.max[2] - r);
-        atomicAdd(&st->clamped, 1);
-    }
-    float mx = px - pi.x, my = py - pi.y, mz = pz - pi.z;
-    if(sqrtf(mx * mx + my * my + mz * mz) >= P.min_cell_len09) st->rebuild_flag = 1;
-    if(!(isfinite(px) && isfinite(py) && isfinite(pz))) atomicAdd(&st->nan_count, 1);
-    pos[i] = make_float4(px, py, pz, 0.f);
-    vel[i] = make_float4(vx, vy, vz, v.w);
-    atomicMax(&st->max_force_bits, __float_as_uint(sqrtf(fx * fx + fy * fy + fz * fz)));
+    bbx_reduce_max_force(st, fmaf(fx, fx, fmaf(fy, fy, fz * fz)));
+    float4 po, vo;
+    bbx_integrate_one<0>(P, g, st, nullptr, pi, v, fx, fy, fz, &po, &vo);
+    if(!(bbx_cull(*cull, po.x, po.y, po.z, P.radius) && bbx_inside_domain_certain(*cull, po.x, po.y, po.z)))
+        bbx_integrate_one<1>(P, g, st, cs, pi, v, fx, fy, fz, &po, &vo);
+    bbx_integrate_flags(P, st, pi, po);
+    pos[i] = po; vel[i] = vo;
 }
 
 // ------------------------------------------------------------------ SPH (non-PCI) force sweep
@@ -529,9 +790,9 @@ __global__ void __launch_bounds__(BBX_BS) k_sph_forces(StepParams P, DevGrid g,
         float4 pj = posq[j]; float4 vj = vel[j];
         float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
         float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        float d = sqrtf(d2);
-        float x = (j != i) ? fmaxf(0.f, 1.f - d * P.inv_h) : 0.f;
-        float w = (d > 1e-8f) ? __fdividef((qi + pj.w) * x * x, d) : 0.f;
+        float inv_d = (d2 > 1.0e-16f) ? rsqrtf(d2) : 0.f;
+        float x = (j != i) ? fmaxf(0.f, fmaf(-d2 * inv_d, P.inv_h, 1.f)) : 0.f;
+        float w = (qi + pj.w) * (x * x) * inv_d;
         tx = fmaf(dx, w, tx); ty = fmaf(dy, w, ty); tz = fmaf(dz, w, tz);
         float wv = __fdividef(x, vj.w);
         ax = fmaf(vj.x - vi.x, wv, ax); ay = fmaf(vj.y - vi.y, wv, ay); az = fmaf(vj.z - vi.z, wv, az);
@@ -638,10 +899,11 @@ __global__ void __launch_bounds__(BBX_BS) k_export_neighbors(int n, DevGrid g, c
     int base[9], end[9];
     bbx_runs(g, cell_start, c, base, end);
     int cz = c / g.plane; int rem = c - cz * g.plane; int cy = rem / g.n[0]; int cx = rem - cy * g.n[0];
+    (void)cz; (void)cy;
     int cnt = nbr_cnt[i];
     size_t id = (size_t)pid[i];
     int *out = ids + id * BBX_MAX_NEIGHBORS;
-    // key = (reference rank of the neighbour cell) << 20 | slot: sort ascending (insertion, <= 100 items)
+    // key = (reference rank of the neighbour cell) << 40 | slot: sort ascending (insertion, <= 100 items)
     unsigned long long keys[BBX_MAX_NEIGHBORS];
     for(int k = 0; k < cnt; k++){
         size_t warp = (size_t)(i >> 5); int lane = i & 31;
