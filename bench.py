@@ -94,6 +94,21 @@ def make_scene(n_target):
     return scenes.dam_break_scene(n_target=n_target, jitter=0.0)
 
 
+def plan_for_ranks(grid, pos, world):
+    """z-slab plan every rank derives identically from the (deterministic, synthetic) scene."""
+    import bubbles_b200 as bb
+    hist = bb.plane_histogram(grid, pos)
+    return bb.plan_slabs(hist, world), hist
+
+
+def broadcast_bytes(blob, src):
+    """rank src's bytes on every rank (used once: the NCCL unique id of the slab group)."""
+    import torch.distributed as dist
+    box = [blob]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def run_reference(args, rank):
     """Reference arm: unmodified reference CPU path (oracle/_ref/bbref) -- or, if that binary is absent, the
     C port (oracle/liboracle.so) -- on a bounded sample of the workload, all host threads."""
@@ -211,12 +226,24 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    sc = make_scene(args.particles)
-    n = len(sc["pos"])
-    eng = scenes.make_engine(sc, device=local_rank)
+    # weak scaling: ONE dam-break scene of (particles per GPU) x N particles, cut into N z-slabs of whole cell
+    # planes balanced by particle count; ghost planes / migration / per-phase halos travel over NCCL
+    sc = make_scene(args.particles * world)
+    n_global = len(sc["pos"])
     pos32 = sc["pos"].astype(np.float32)
     vel32 = sc["vel"].astype(np.float32)
-    eng.set_particles(pos32, vel32)
+    if world > 1:
+        grid = bb.UtilBuildGridForDomain(sc["domain_min"], sc["domain_max"], sc["spacing"], sc["scale"])
+        zb, hist = plan_for_ranks(grid, pos32, world)
+        cap, gcap = bb.slab_capacity(hist, zb, rank, slack=2.0)
+        slab = bb.NcclSlab(grid, sc["spacing"], sc["scale"], zb, rank, world, broadcast_bytes, cap, gcap, device=local_rank)
+        eng = slab.engine
+        eng.set_colliders(scenes.engine_colliders(sc))
+        eng.set_particles_ids(pos32, vel32)
+    else:
+        eng = scenes.make_engine(sc, device=local_rank)
+        eng.set_particles(pos32, vel32)
+    n = n_global // world  # nominal particles per GPU (the slabs hold about this many each)
     dt = sc["dt"]
     state_bytes = n * (16 * 8 + 4 * 8 + 208)  # float4 arrays, scalars/indices, neighbour list
 
@@ -257,7 +284,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step, wall_ms = float(t[0]), float(t[1])
-    value = n * world / (ms_per_step * 1e-3)
+    value = n_global / (ms_per_step * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------
     hp = torch.from_numpy(pos32.copy()).pin_memory()
@@ -266,18 +293,41 @@ def main():
     ov = torch.empty_like(hv).pin_memory()
     lib = eng.lib
 
+    hid = torch.zeros(len(pos32), dtype=torch.int32).pin_memory()
+    cnt = C.c_int()
+    h2d = [0]
+
     def e2e_step():
-        rc = lib.bbx_overwrite_state(eng.h, hp.data_ptr(), hv.data_ptr(), bb.F32)
-        rc |= lib.bbx_step_pcisph(eng.h, dt)
-        rc |= lib.bbx_download(eng.h, bb.POSITION, op.data_ptr(), bb.F32)
-        rc |= lib.bbx_download(eng.h, bb.VELOCITY, ov.data_ptr(), bb.F32)
+        if world == 1:
+            rc = lib.bbx_overwrite_state(eng.h, hp.data_ptr(), hv.data_ptr(), bb.F32)
+            rc |= lib.bbx_step_pcisph(eng.h, dt)
+            rc |= lib.bbx_download(eng.h, bb.POSITION, op.data_ptr(), bb.F32)
+            rc |= lib.bbx_download(eng.h, bb.VELOCITY, ov.data_ptr(), bb.F32)
+            m = len(pos32)
+            h2d[0] = 24 * m
+        else:
+            # slab engines: every rank hands over the particles it holds (host buffers, global ids), steps, and
+            # reads its owned particles back with their ids -- the per-rank share of what a host run loop does
+            m = cnt.value
+            rc = lib.bbx_set_particles_ids(eng.h, m, hp.data_ptr(), hv.data_ptr(), hid.data_ptr(), bb.F32)
+            rc |= lib.bbx_step_pcisph(eng.h, dt)
+            rc |= lib.bbx_download_owned(eng.h, bb.POSITION, op.data_ptr(), bb.F32, hid.data_ptr(), C.byref(cnt))
+            rc |= lib.bbx_download_owned(eng.h, bb.VELOCITY, ov.data_ptr(), bb.F32, None, None)
+            h2d[0] = 28 * m
         if rc:
             raise SystemExit("bbx error: " + lib.bbx_last_error().decode())
         hp.copy_(op); hv.copy_(ov)  # next step's input is this step's output (host side)
 
     # restart from the initial block so that the e2e run simulates the same thing
-    hp.copy_(torch.from_numpy(pos32)); hv.copy_(torch.from_numpy(vel32))
-    eng.set_particles(pos32, vel32)
+    if world == 1:
+        hp.copy_(torch.from_numpy(pos32)); hv.copy_(torch.from_numpy(vel32))
+        eng.set_particles(pos32, vel32)
+    else:
+        eng.set_particles_ids(pos32, vel32)
+        rc = lib.bbx_download_owned(eng.h, bb.POSITION, hp.data_ptr(), bb.F32, hid.data_ptr(), C.byref(cnt))
+        rc |= lib.bbx_download_owned(eng.h, bb.VELOCITY, hv.data_ptr(), bb.F32, None, None)
+        if rc:
+            raise SystemExit("bbx error: " + lib.bbx_last_error().decode())
     for _ in range(3):
         e2e_step()
     barrier()
@@ -289,13 +339,13 @@ def main():
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n * world / float(t[0])
+    e2e_value = n_global / float(t[0])
 
     if rank == 0:
         peak, peak_src = peaks()
         dom = max(phase, key=lambda k: phase[k][0])
         dom_ms = phase[dom][0] / max(1, phase[dom][1])
-        cells = eng.grid.total
+        cells = eng.grid.total // world
         dom_bytes = PHASE_BYTES[dom] * n + (8 * cells if dom == "grid" else 0)
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         traffic = None
@@ -309,15 +359,18 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"PCISPH 3D dam break, {n} particles per GPU (BASELINE configs[1]), spacing 0.02, h = 1.8 s, "
-                                   f"{cells} cells, fixed dt 7.2e-4, reference-compat (1 predict-correct iteration)",
-                       "particles_per_gpu": n, "cells": cells, "dt": dt,
+            "config": {"workload": f"PCISPH 3D dam break, {n_global} particles = {n} per GPU (BASELINE configs[1] per GPU), spacing 0.02, h = 1.8 s, "
+                                   f"{cells} cells, fixed dt 7.2e-4, reference-compat (1 predict-correct iteration)"
+                                   + (f", {world} z-slabs with NCCL ghost-plane exchange and migration" if world > 1 else ""),
+                       "particles_per_gpu": n, "particles": n_global, "cells": cells, "dt": dt,
+                       "parallelism": f"slab{world}" if world > 1 else "single",
                        "l2_policy": f"working set {state_bytes / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
                        "timing": "CUDA events on the engine stream between kernels, summed over phases, max over ranks",
                        "wall_ms_per_step": wall_ms},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n,
-                    "api": "bbx_overwrite_state + bbx_step_pcisph + bbx_download(POSITION, VELOCITY), pinned host buffers",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d[0] * world, "d2h_bytes_per_step": h2d[0] * world,
+                    "api": ("bbx_overwrite_state + bbx_step_pcisph + bbx_download(POSITION, VELOCITY), pinned host buffers" if world == 1 else
+                            "per rank: bbx_set_particles_ids(owned, host) + bbx_step_pcisph + bbx_download_owned(POSITION, VELOCITY, ids), pinned host buffers"),
                     "steps": args.e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

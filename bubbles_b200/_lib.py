@@ -46,7 +46,8 @@ class Config(C.Structure):
                 ("pseudo_viscosity", C.c_double), ("gravity", C.c_double * 3),
                 ("pcisph_max_density_error_ratio", C.c_double), ("restitution", C.c_double),
                 ("time_step_limit_scale", C.c_double), ("grid", GridDesc),
-                ("slab_z_begin", C.c_int), ("slab_z_end", C.c_int)]
+                ("slab_z_begin", C.c_int), ("slab_z_end", C.c_int),
+                ("ghost_capacity", C.c_int), ("reserved", C.c_int)]
 
 
 class StepStats(C.Structure):
@@ -70,6 +71,7 @@ SYMBOLS = {
     "bbx_get_mass": (C.c_int, [_E, C.POINTER(C.c_double)]),
     "bbx_get_delta": (C.c_int, [_E, C.c_double, C.POINTER(C.c_double)]),
     "bbx_set_particles": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "bbx_set_particles_ids": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bbx_append_particles": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "bbx_particle_count": (C.c_int, [_E, C.POINTER(C.c_int)]),
     "bbx_overwrite_state": (C.c_int, [_E, C.c_void_p, C.c_void_p, C.c_int]),
@@ -85,8 +87,10 @@ SYMBOLS = {
     "bbx_set_timing": (C.c_int, [_E, C.c_int]),
     "bbx_stats": (C.c_int, [_E, C.POINTER(StepStats)]),
     "bbx_download": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_int]),
+    "bbx_download_owned": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "bbx_export_cells": (C.c_int, [_E, C.c_void_p, C.c_void_p]),
     "bbx_export_neighbors": (C.c_int, [_E, C.c_void_p, C.c_void_p]),
+    "bbx_export_neighbors_owned": (C.c_int, [_E, C.c_void_p, C.c_void_p]),
     "bbx_inject_chains": (C.c_int, [_E, C.c_void_p, C.c_void_p]),
     "bbx_set_rebuild_flag": (C.c_int, [_E, C.c_int]),
     "bbx_launch_count": (C.c_int, [_E, C.POINTER(C.c_longlong)]),
@@ -94,6 +98,9 @@ SYMBOLS = {
     "bbx_reset_kernel_time": (C.c_int, [_E]),
     "bbx_comm_unique_id": (C.c_int, [C.c_void_p]),
     "bbx_comm_init": (C.c_int, [_E, C.c_int, C.c_int, C.c_void_p]),
+    "bbx_comm_init_local": (C.c_int, [_E, C.c_int, C.c_int, C.c_char_p]),
+    "bbx_slab_plan": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_int)]),
+    "bbx_plane_histogram": (C.c_int, [C.POINTER(GridDesc), C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]),
 }
 
 _lib = None

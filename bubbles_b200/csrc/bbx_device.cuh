@@ -18,13 +18,22 @@
 #define BBX_RUN_MASK 0xfffu
 #define BBX_MAX_RUN_LEN 4096
 
+// The grid an engine works on is the LOCAL grid of its z-slab: whole cell planes [zoff, zoff + n[2]) of
+// the global grid (z is the slowest index of LinearIndex, so a slab is a contiguous range of global
+// cell ids and local id = global id - zoff * plane).  Owned planes are local [own_z0, own_z1); a slab
+// with a lower / upper neighbour carries one ghost plane on that side.  Single domain: zoff = 0,
+// n[2] = gnz, everything owned.  Geometry (min, max, len) is always the global grid's, so hashing is
+// bit-identical to the single-domain engine.
 struct DevGrid {
     double min[3], max[3], len[3];
     float minf[3], maxf[3];
-    int n[3];
-    int total;
+    int n[3];           // local cell counts (n[2] = local planes incl. ghost planes)
+    int total;          // local cells
     int plane;          // n[0] * n[1]
-    int z_begin, z_end; // owned z planes (multi-GPU slab); single GPU: 0 .. n[2]
+    int zoff;           // global z of local plane 0
+    int gnz;            // global n[2]
+    int own_z0, own_z1; // owned local planes
+    int c_own0, c_own1; // owned local cells [own_z0 * plane, own_z1 * plane)
 };
 
 struct DevCollider {
@@ -90,6 +99,8 @@ struct DevState {
     int qn[2];           // collider slow-path queue lengths: [0] predict, [1] integrate
     unsigned scan_ticket;
     int iterations;
+    int n_own;           // owned particles after the last grid update / upload (slab engines)
+    int n_first, n_last; // particles in the first / last owned plane (what the slab neighbours hold as ghosts)
     int pad;
 };
 
@@ -138,6 +149,7 @@ __device__ __forceinline__ int bbx_hash(const DevGrid &g, float px, float py, fl
         double dp = __ddiv_rn(__dsub_rn(p, g.min[i]), g.len[i]);
         u[i] = (int)floor(dp);
     }
+    u[2] -= g.zoff; // local plane
     *ux = u[0]; *uy = u[1]; *uz = u[2];
     if(u[0] < 0 || u[0] >= g.n[0] || u[1] < 0 || u[1] >= g.n[1] || u[2] < 0 || u[2] >= g.n[2]) return -1;
     return u[0] + u[1] * g.n[0] + u[2] * g.plane;

@@ -12,6 +12,7 @@
 #include "../../include/bbx.h"
 #include "bbx_kernels.cuh"
 #include "bbx_host_math.h"
+#include "bbx_comm.h"
 
 static thread_local std::string g_last_error;
 static int set_error(int code, const char *fmt, ...){
@@ -29,7 +30,16 @@ struct bbx_engine {
     bbx_config cfg;
     int device;
     cudaStream_t stream;
-    int n, cap;
+    int n, cap;      // owned particles / capacity
+    // slab engines: ghost capacity per side and the current ghost / boundary-plane counts (host copies).
+    // Every slot-indexed array that neighbours are read from (pos, vel, pid, cell, newcell, pred, posq) is
+    // allocated with gcap slots in front: pointers are offset so that owned slots are [0, n), the lower
+    // ghost plane is [-n_glo, 0) and the upper one [n, n + n_ghi).
+    int gcap, n_glo, n_ghi, n_first, n_last;
+    int has_lo, has_hi; // a slab neighbour exists below / above
+    BbxComm *comm;
+    int *gtab;          // received cell-table slices of the two ghost planes, 2 x (plane + 1)
+    std::vector<void *> raw; // allocation bases (for cudaFree)
     DevGrid grid;
     double mass, delta_denom, mass_over_rho0_sq, h;
     // sorted particle arrays, double buffered for the reorder
@@ -129,10 +139,26 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
         g.min[k] = cfg->grid.min[k]; g.max[k] = cfg->grid.max[k]; g.len[k] = cfg->grid.cell_len[k];
         g.minf[k] = (float)g.min[k]; g.maxf[k] = (float)g.max[k]; g.n[k] = cfg->grid.n[k];
     }
-    g.total = cfg->grid.total; g.plane = g.n[0] * g.n[1];
-    g.z_begin = cfg->slab_z_end > cfg->slab_z_begin ? cfg->slab_z_begin : 0;
-    g.z_end = cfg->slab_z_end > cfg->slab_z_begin ? cfg->slab_z_end : g.n[2];
-    if((long long)g.n[0] * g.n[1] * g.n[2] != g.total) { delete e; return set_error(BBX_ERR_INVALID, "grid.total != nx*ny*nz"); }
+    g.plane = g.n[0] * g.n[1];
+    if((long long)g.n[0] * g.n[1] * g.n[2] != cfg->grid.total) { delete e; return set_error(BBX_ERR_INVALID, "grid.total != nx*ny*nz"); }
+    // z-slab: owned global planes [zb, ze); one ghost plane towards each existing neighbour
+    g.gnz = g.n[2];
+    int zb = 0, ze = g.gnz;
+    if(cfg->slab_z_end > cfg->slab_z_begin){
+        zb = cfg->slab_z_begin; ze = cfg->slab_z_end;
+        if(zb < 0 || ze > g.gnz){ delete e; return set_error(BBX_ERR_INVALID, "slab [%d, %d) outside the grid's %d planes", zb, ze, g.gnz); }
+    }
+    e->has_lo = zb > 0; e->has_hi = ze < g.gnz;
+    g.zoff = zb - (e->has_lo ? 1 : 0);
+    g.n[2] = (ze - zb) + (e->has_lo ? 1 : 0) + (e->has_hi ? 1 : 0);
+    g.own_z0 = e->has_lo ? 1 : 0; g.own_z1 = g.own_z0 + (ze - zb);
+    g.c_own0 = g.own_z0 * g.plane; g.c_own1 = g.own_z1 * g.plane;
+    if((long long)g.plane * g.n[2] > 0x7fffffffLL){ delete e; return set_error(BBX_ERR_INVALID, "more than 2^31 local cells"); }
+    g.total = g.plane * g.n[2];
+    e->gcap = 0; e->n_glo = e->n_ghi = e->n_first = e->n_last = 0; e->comm = nullptr; e->gtab = nullptr;
+    if(e->has_lo || e->has_hi){
+        e->gcap = cfg->ghost_capacity > 0 ? cfg->ghost_capacity : std::max(4096, cfg->max_particles / 4);
+    }
     // scalars of Setup: SetTargetDensity/Spacing/RelativeKernelRadius -> ComputeMass; deltaDenom
     e->h = cfg->kernel_scale * cfg->spacing;
     e->mass = bbxh_compute_mass(e->h, cfg->spacing, cfg->target_density);
@@ -146,23 +172,27 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
         e->masked = (minlen * minlen >= e->h * e->h - 0.5e-8) ? 0 : 1;
     }
     // particle arrays carry BBX_PAD spare slots: the list build reads (and discards) up to 7 slots past a run
-    size_t cap = (size_t)e->cap + BBX_PAD, capw = ((cap + 31) / 32) * 32;
+    const size_t gc = (size_t)e->gcap;
+    size_t cap = (size_t)e->cap + BBX_PAD, capw = ((cap + 31) / 32) * 32, capg = cap + 2 * gc;
     int rc = BBX_OK;
+#define BBX_ALLOC_G(ptr) do{ rc |= dev_alloc(&(ptr), capg); if(rc == BBX_OK){ e->raw.push_back((void *)(ptr)); CU(cudaMemset((ptr), 0, sizeof(*(ptr)) * capg)); (ptr) += gc; } }while(0)
     for(int b = 0; b < 2 && rc == BBX_OK; b++){
-        rc |= dev_alloc(&e->pos[b], cap); rc |= dev_alloc(&e->vel[b], cap);
-        rc |= dev_alloc(&e->pid[b], cap); rc |= dev_alloc(&e->cell[b], cap);
+        BBX_ALLOC_G(e->pos[b]); BBX_ALLOC_G(e->vel[b]); BBX_ALLOC_G(e->pid[b]); BBX_ALLOC_G(e->cell[b]);
         rc |= dev_alloc(&e->cell_start[b], (size_t)g.total + 1);
-        if(rc == BBX_OK){ CU(cudaMemset(e->pos[b], 0, sizeof(float4) * cap)); CU(cudaMemset(e->cell[b], 0, sizeof(int) * cap)); }
+        if(rc == BBX_OK) CU(cudaMemset(e->cell_start[b], 0, sizeof(int) * ((size_t)g.total + 1)));
     }
-    rc |= dev_alloc(&e->newcell, cap); rc |= dev_alloc(&e->count, (size_t)g.total + 8); rc |= dev_alloc(&e->perm, cap);
+    BBX_ALLOC_G(e->newcell); BBX_ALLOC_G(e->pred); BBX_ALLOC_G(e->posq);
+#undef BBX_ALLOC_G
+    rc |= dev_alloc(&e->count, (size_t)g.total + 8); rc |= dev_alloc(&e->perm, cap);
     rc |= dev_alloc(&e->occ_cells, (size_t)g.total); rc |= dev_alloc(&e->queue, cap);
-    e->scan_tiles = div_up(g.total, SCAN_TILE);
+    e->scan_tiles = div_up(g.c_own1 - g.c_own0, SCAN_TILE);
     rc |= dev_alloc(&e->scan_status, (size_t)e->scan_tiles);
     rc |= dev_alloc(&e->nbr, capw * BBX_NBR_CHUNKS * 8); rc |= dev_alloc(&e->nbr_cnt, cap);
-    rc |= dev_alloc(&e->force, cap); rc |= dev_alloc(&e->force_p, cap); rc |= dev_alloc(&e->pred, cap);
-    rc |= dev_alloc(&e->posq, cap); rc |= dev_alloc(&e->smoothed, cap);
+    rc |= dev_alloc(&e->force, cap); rc |= dev_alloc(&e->force_p, cap);
+    rc |= dev_alloc(&e->smoothed, cap);
     rc |= dev_alloc(&e->pressure, cap); rc |= dev_alloc(&e->rho_pred, cap); rc |= dev_alloc(&e->rho_err, cap);
     rc |= dev_alloc(&e->st, 1); rc |= dev_alloc(&e->colliders, 1); rc |= dev_alloc(&e->cull, 1);
+    if(e->gcap) rc |= dev_alloc(&e->gtab, 2 * ((size_t)g.plane + 1));
     if(rc != BBX_OK){ return rc; }
     CU(cudaMemset(e->count, 0, sizeof(int) * ((size_t)g.total + 8)));
     CU(cudaMallocHost((void **)&e->st_host, sizeof(DevState)));
@@ -173,7 +203,7 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     { int rc2 = push_cull(e); if(rc2) return rc2; }
     CU(cudaMemset(e->force, 0, sizeof(float4) * cap)); CU(cudaMemset(e->force_p, 0, sizeof(float4) * cap));
     CU(cudaMemset(e->pressure, 0, sizeof(float) * cap)); CU(cudaMemset(e->rho_pred, 0, sizeof(float) * cap));
-    CU(cudaMemset(e->rho_err, 0, sizeof(float) * cap)); CU(cudaMemset(e->pred, 0, sizeof(float4) * cap));
+    CU(cudaMemset(e->rho_err, 0, sizeof(float) * cap));
     CU(cudaMemset(e->nbr_cnt, 0, sizeof(int) * cap));
     *out = e;
     return BBX_OK;
@@ -183,10 +213,13 @@ int bbx_destroy(bbx_engine *e){
     if(!e) return BBX_OK;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    for(int b = 0; b < 2; b++){ cudaFree(e->pos[b]); cudaFree(e->vel[b]); cudaFree(e->pid[b]); cudaFree(e->cell[b]); cudaFree(e->cell_start[b]); }
-    cudaFree(e->newcell); cudaFree(e->count); cudaFree(e->perm); cudaFree(e->occ_cells); cudaFree(e->queue); cudaFree(e->scan_status);
-    cudaFree(e->nbr); cudaFree(e->nbr_cnt); cudaFree(e->force); cudaFree(e->force_p); cudaFree(e->pred);
-    cudaFree(e->posq); cudaFree(e->smoothed); cudaFree(e->pressure); cudaFree(e->rho_pred); cudaFree(e->rho_err);
+    if(e->comm){ delete e->comm; e->comm = nullptr; }
+    for(void *p : e->raw) cudaFree(p);
+    for(int b = 0; b < 2; b++) cudaFree(e->cell_start[b]);
+    cudaFree(e->count); cudaFree(e->perm); cudaFree(e->occ_cells); cudaFree(e->queue); cudaFree(e->scan_status);
+    cudaFree(e->nbr); cudaFree(e->nbr_cnt); cudaFree(e->force); cudaFree(e->force_p);
+    cudaFree(e->smoothed); cudaFree(e->pressure); cudaFree(e->rho_pred); cudaFree(e->rho_err);
+    if(e->gtab) cudaFree(e->gtab);
     cudaFree(e->st); cudaFree(e->colliders); cudaFree(e->cull); cudaFreeHost(e->st_host);
     for(double *f : e->sdf_fields) cudaFree(f);
     for(float *f : e->sdf_fields32) cudaFree(f);
@@ -212,46 +245,72 @@ static int ensure_stage(bbx_engine *e, size_t bytes){
     return BBX_OK;
 }
 
-static int upload_particles(bbx_engine *e, int first, int n, const void *pos, const void *vel, int dtype){
+static int read_state(bbx_engine *e);
+static int grid_update(bbx_engine *e);
+#define IS_SLAB(e) ((e)->has_lo || (e)->has_hi)
+#define COMM(call) do{ if((call)) return set_error(BBX_ERR_COMM, "%s", e->comm->err.c_str()); }while(0)
+
+static int upload_particles(bbx_engine *e, int first, int n, const void *pos, const void *vel, const int *ids, int dtype){
     if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "dtype must be BBX_F32 or BBX_F64");
     size_t esz = dtype == BBX_F64 ? 8 : 4;
-    size_t bytes = esz * 3 * (size_t)n;
-    int rc = ensure_stage(e, 2 * bytes); if(rc) return rc;
-    char *sp = (char *)e->stage, *sv = sp + bytes;
+    size_t bytes = esz * 3 * (size_t)n, idb = (IS_SLAB(e) && ids) ? sizeof(int) * (size_t)n : 0;
+    int rc = ensure_stage(e, 2 * bytes + idb); if(rc) return rc;
+    char *sp = (char *)e->stage, *sv = sp + bytes; int *si = idb ? (int *)(sv + bytes) : nullptr;
     CU(cudaMemcpyAsync(sp, pos, bytes, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(sv, vel, bytes, cudaMemcpyHostToDevice, e->stream));
+    if(IS_SLAB(e)){
+        // keep the particles of the owned planes (the caller may pass any superset, e.g. the whole scene)
+        if(si) CU(cudaMemcpyAsync(si, ids, idb, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemsetAsync(&e->st->n_own, 0, sizeof(int), e->stream));
+        LAUNCH(e, k_upload_slab, div_up(n, 256), 256, n, sp, sv, si, dtype == BBX_F64, e->grid, e->cap, e->st, e->pos[e->cur], e->vel[e->cur], e->pid[e->cur]);
+        CU(cudaGetLastError());
+        rc = read_state(e); if(rc) return rc;
+        if(e->st_host->error == BBX_ERR_CAPACITY) return set_error(BBX_ERR_CAPACITY, "slab holds more than max_particles = %d particles", e->cap);
+        e->n = e->st_host->n_own;
+        return BBX_OK;
+    }
     LAUNCH(e, k_upload, div_up(n, 256), 256, n, first, sp, sv, dtype == BBX_F64, e->pos[e->cur] + first, e->vel[e->cur] + first, e->pid[e->cur] + first);
     CU(cudaGetLastError());
     return BBX_OK;
 }
 
-static int grid_update(bbx_engine *e);
-
-int bbx_set_particles(bbx_engine *e, int n, const void *pos, const void *vel, int dtype){
-    CHECK_ENGINE(e);
+static int set_particles(bbx_engine *e, int n, const void *pos, const void *vel, const int *ids, int dtype){
     if(n < 0 || (n > 0 && (!pos || !vel))) return set_error(BBX_ERR_INVALID, "bad particle arguments");
-    if(n > e->cap) return set_error(BBX_ERR_CAPACITY, "%d particles exceed max_particles %d", n, e->cap);
-    e->n = n;
+    if(IS_SLAB(e) && !e->comm) return set_error(BBX_ERR_INVALID, "slab engine without a communicator: call bbx_comm_init / bbx_comm_init_local first");
+    if(!IS_SLAB(e) && n > e->cap) return set_error(BBX_ERR_CAPACITY, "%d particles exceed max_particles %d", n, e->cap);
+    e->n = IS_SLAB(e) ? 0 : n;
+    e->n_glo = e->n_ghi = e->n_first = e->n_last = 0;
     e->have_chains = 0; e->force_full = 1;
-    if(n == 0) return BBX_OK;
-    int rc = upload_particles(e, 0, n, pos, vel, dtype); if(rc) return rc;
+    if(n == 0 && !IS_SLAB(e)) return BBX_OK;
+    int rc;
+    if(n > 0){ rc = upload_particles(e, 0, n, pos, vel, ids, dtype); if(rc) return rc; }
     // PciSphSolver3::Setup: initial DistributeByParticle (ascending id) so that the first sub-step can
     // run the incremental update exactly like the reference (frame_index = 1)
     rc = grid_update(e); if(rc) return rc;
     e->force_full = 0;
     return BBX_OK;
 }
+int bbx_set_particles(bbx_engine *e, int n, const void *pos, const void *vel, int dtype){
+    CHECK_ENGINE(e);
+    return set_particles(e, n, pos, vel, nullptr, dtype);
+}
+int bbx_set_particles_ids(bbx_engine *e, int n, const void *pos, const void *vel, const int *ids, int dtype){
+    CHECK_ENGINE(e);
+    if(!IS_SLAB(e) && ids) return set_error(BBX_ERR_INVALID, "explicit particle ids are only meaningful for slab engines");
+    return set_particles(e, n, pos, vel, ids, dtype);
+}
 
 int bbx_append_particles(bbx_engine *e, int n, const void *pos, const void *vel, int dtype){
     CHECK_ENGINE(e);
     if(n <= 0) return BBX_OK;
+    if(IS_SLAB(e)) return set_error(BBX_ERR_INVALID, "bbx_append_particles is not available on slab engines");
     if(e->n + n > e->cap) return set_error(BBX_ERR_CAPACITY, "%d + %d particles exceed max_particles %d", e->n, n, e->cap);
     // New particles take ids n_old.. and go to the tail of their cell's chain: equivalent to a
     // stable merge; realised as "old chains first, then new ids ascending" via the incremental fill
     // followed by a tail insert.  Implemented with the full-rebuild machinery when no chains exist.
     if(!e->have_chains || e->n == 0){
         int first = e->n;
-        int rc = upload_particles(e, first, n, pos, vel, dtype); if(rc) return rc;
+        int rc = upload_particles(e, first, n, pos, vel, nullptr, dtype); if(rc) return rc;
         e->n += n; e->force_full = 1;
         rc = grid_update(e); if(rc) return rc;
         e->force_full = 0;
@@ -264,6 +323,7 @@ int bbx_particle_count(bbx_engine *e, int *n){ if(!e || !n) return set_error(BBX
 
 int bbx_overwrite_state(bbx_engine *e, const void *pos, const void *vel, int dtype){
     CHECK_ENGINE(e);
+    if(IS_SLAB(e)) return set_error(BBX_ERR_INVALID, "bbx_overwrite_state is not available on slab engines");
     if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "dtype must be BBX_F32 or BBX_F64");
     if(e->n == 0) return BBX_OK;
     size_t esz = dtype == BBX_F64 ? 8 : 4; size_t bytes = esz * 3 * (size_t)e->n;
@@ -446,33 +506,78 @@ static void make_params(bbx_engine *e, double dt, StepParams &P){
     double pf = dt * c.pseudo_viscosity; P.pseudo_factor = (float)(pf < 0 ? 0 : (pf > 1 ? 1 : pf));
 }
 
+// ---- slab engines: exchange the boundary planes of slot-indexed arrays with the two neighbours.
+// Send: my first owned plane [0, n_first) to the lower neighbour, my last owned plane [n - n_last, n) to
+// the upper one.  Receive: the lower ghost plane [-n_glo, 0) and the upper one [n, n + n_ghi).  The ranges
+// are contiguous because slots are sorted by cell id and z is the slowest cell index -- no pack kernels.
+static int exchange_planes(bbx_engine *e, void *const *arr, const size_t *esz, int narr){
+    if(!IS_SLAB(e)) return BBX_OK;
+    BbxSeg slo[BBX_MAX_SEGS], rlo[BBX_MAX_SEGS], shi[BBX_MAX_SEGS], rhi[BBX_MAX_SEGS];
+    for(int k = 0; k < narr; k++){
+        char *base = (char *)arr[k]; size_t z = esz[k];
+        slo[k].ptr = base; slo[k].bytes = z * (size_t)e->n_first;
+        rlo[k].ptr = base - z * (size_t)e->n_glo; rlo[k].bytes = z * (size_t)e->n_glo;
+        shi[k].ptr = base + z * (size_t)(e->n - e->n_last); shi[k].bytes = z * (size_t)e->n_last;
+        rhi[k].ptr = base + z * (size_t)e->n; rhi[k].bytes = z * (size_t)e->n_ghi;
+    }
+    COMM(e->comm->exchange(e->stream, slo, rlo, narr, shi, rhi, narr));
+    return BBX_OK;
+}
+static int exchange1(bbx_engine *e, float4 *a){ void *arr[1] = {a}; size_t z[1] = {sizeof(float4)}; return exchange_planes(e, arr, z, 1); }
+static int exchange2(bbx_engine *e, float4 *a, float4 *b){ void *arr[2] = {a, b}; size_t z[2] = {sizeof(float4), sizeof(float4)}; return exchange_planes(e, arr, z, 2); }
+
 // UpdateGridDistributionGPU minus the bucket fill (sph_equations3.cpp:511-539)
 #define BBX_SMALL_GRID (148 * 4)
 static int grid_update(bbx_engine *e){
-    if(e->n == 0) return BBX_OK;
+    const bool slab = IS_SLAB(e);
+    if(e->n == 0 && !slab) return BBX_OK;
     DevGrid &g = e->grid;
-    int n = e->n, cur = e->cur, nxt = cur ^ 1;
+    int n_all = e->n_glo + e->n + e->n_ghi, cur = e->cur, nxt = cur ^ 1;
     int force = (e->force_full || !e->have_chains) ? 1 : 0;
     int par = e->epoch & 1;
-    LAUNCH(e, k_hash_count, div_up(std::max(n, e->scan_tiles), 256), 256, n, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st,
+    const int own_cells = g.c_own1 - g.c_own0;
+    LAUNCH(e, k_hash_count, div_up(std::max(std::max(n_all, e->scan_tiles), 1), 256), 256, n_all, e->n_glo, e->n, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st,
            force ? 0 : 1, par, e->scan_status, e->scan_tiles);
-    LAUNCH(e, k_scan_cells, e->scan_tiles, 256, e->count, g.total, n, e->scan_status, e->st, e->cell_start[nxt], e->occ_cells);
+    // the big-move rule and the jump detection are global decisions (the reference rebuilds ALL chains)
+    if(slab) COMM(e->comm->allreduce_max_u32(e->stream, (unsigned *)e->st, 4)); // rebuild_flag[2], jump_flag[2]
+    LAUNCH(e, k_scan_cells, e->scan_tiles, 256, e->count + g.c_own0, own_cells, g.c_own0, e->scan_status, e->st, e->cell_start[nxt] + g.c_own0, e->occ_cells);
     if(!force){
         // persistent grid: 8 lanes per occupied cell, grid-stride over the compact list of occupied cells
-        int groups = std::min(n, g.total);
+        int groups = std::max(1, std::min(n_all, own_cells));
         int blocks = std::min(div_up((long long)groups * 8, 256), 148 * 8);
         LAUNCH(e, k_fill_incremental, blocks, 256, g, e->st, par, e->occ_cells, e->cell_start[cur], e->cell_start[nxt], e->newcell,
                e->pos[cur], e->vel[cur], e->pid[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt]);
     }
     // full path (forced, or selected on the device by the big-move / jump flags); small grids when it is
     // only a flag check
-    int fb_n = force ? div_up(n, 256) : std::min(div_up(n, 256), BBX_SMALL_GRID);
-    int fb_c = force ? div_up(g.total, 256) : std::min(div_up(g.total, 256), BBX_SMALL_GRID);
-    LAUNCH(e, k_full_scatter, fb_n, 256, n, e->st, par, force, e->newcell, e->cell_start[nxt], e->count, e->perm);
-    LAUNCH(e, k_full_sort_cells, fb_c, 256, g.total, e->st, par, force, e->cell_start[nxt], e->pid[cur], e->perm, e->count);
-    LAUNCH(e, k_full_gather, fb_n, 256, n, e->st, par, force, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
+    int fb_n = force ? div_up(std::max(n_all, 1), 256) : std::min(div_up(std::max(n_all, 1), 256), BBX_SMALL_GRID);
+    int fb_c = force ? div_up(own_cells, 256) : std::min(div_up(own_cells, 256), BBX_SMALL_GRID);
+    LAUNCH(e, k_full_scatter, fb_n, 256, n_all, e->n_glo, g, e->st, par, force, e->newcell, e->cell_start[nxt], e->count, e->perm);
+    LAUNCH(e, k_full_sort_cells, fb_c, 256, g, e->st, par, force, e->cell_start[nxt], e->pid[cur], e->perm, e->count);
+    LAUNCH(e, k_full_gather, fb_n, 256, e->st, par, force, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
            e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt]);
     CU(cudaGetLastError());
+    if(slab){
+        // migration happened implicitly: particles that crossed into my planes were found in my ghost
+        // planes' old chains (in the reference's order), particles that left simply were not placed.
+        // Now the ghost planes are replaced by the neighbours' freshly ordered boundary planes.
+        LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi);
+        int rc = read_state(e); if(rc) return rc;
+        const int n_new = e->st_host->n_own, nf = e->st_host->n_first, nl = e->st_host->n_last;
+        if(n_new > e->cap) return set_error(BBX_ERR_CAPACITY, "slab now owns %d particles, max_particles is %d", n_new, e->cap);
+        int glo = 0, ghi = 0;
+        COMM(e->comm->neighbor_counts(e->stream, nf, nl, &glo, &ghi));
+        if(glo > e->gcap || ghi > e->gcap) return set_error(BBX_ERR_CAPACITY, "ghost plane of %d particles exceeds ghost_capacity %d", std::max(glo, ghi), e->gcap);
+        const size_t tb = sizeof(int) * ((size_t)g.plane + 1);
+        BbxSeg slo[4] = {{e->cell_start[nxt] + g.c_own0, tb}, {e->pos[nxt], sizeof(float4) * (size_t)nf}, {e->vel[nxt], sizeof(float4) * (size_t)nf}, {e->pid[nxt], sizeof(int) * (size_t)nf}};
+        BbxSeg rlo[4] = {{e->gtab, tb}, {e->pos[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->vel[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->pid[nxt] - glo, sizeof(int) * (size_t)glo}};
+        BbxSeg shi[4] = {{e->cell_start[nxt] + g.c_own1 - g.plane, tb}, {e->pos[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->vel[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->pid[nxt] + (n_new - nl), sizeof(int) * (size_t)nl}};
+        BbxSeg rhi[4] = {{e->gtab + g.plane + 1, tb}, {e->pos[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->vel[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->pid[nxt] + n_new, sizeof(int) * (size_t)ghi}};
+        COMM(e->comm->exchange(e->stream, slo, rlo, 4, shi, rhi, 4));
+        LAUNCH(e, k_ghost_table, div_up(g.plane, 256), 256, g, n_new, e->has_lo, e->has_hi, e->gtab, e->gtab + g.plane + 1, e->cell_start[nxt], e->cell[nxt], e->count);
+        CU(cudaGetLastError());
+        e->n = n_new; e->n_first = nf; e->n_last = nl; e->n_glo = glo; e->n_ghi = ghi;
+    }
     e->cur = nxt;
     e->have_chains = 1;
     e->last_force = force;
@@ -481,53 +586,70 @@ static int grid_update(bbx_engine *e){
 }
 
 static int phase_density(bbx_engine *e, const StepParams &P, int sph){
-    int cur = e->cur; dim3 nb(e->grid.n[1] * e->grid.n[2], BBX_DSPLIT);
+    int cur = e->cur; dim3 nb(e->grid.n[1] * (e->grid.own_z1 - e->grid.own_z0), BBX_DSPLIT);
+    if(e->n > 0){
 #define BBX_DENS(S, M) LAUNCH(e, (k_density_lists<S, M>), nb, BBX_BS, P, e->grid, e->st, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq)
-    if(sph){ if(e->masked) BBX_DENS(1, 1); else BBX_DENS(1, 0); }
-    else{ if(e->masked) BBX_DENS(0, 1); else BBX_DENS(0, 0); }
+        if(sph){ if(e->masked) BBX_DENS(1, 1); else BBX_DENS(1, 0); }
+        else{ if(e->masked) BBX_DENS(0, 1); else BBX_DENS(0, 0); }
 #undef BBX_DENS
-    CU(cudaGetLastError());
-    return BBX_OK;
+        CU(cudaGetLastError());
+    }
+    // ghost rho (rides in vel.w); the SPH step also needs the ghosts' p / rho^2 (posq.w)
+    if(sph) return exchange2(e, e->vel[cur], e->posq);
+    return exchange1(e, e->vel[cur]);
 }
 static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
     int cur = e->cur;
-    LAUNCH(e, k_force_np_predict, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur],
-           e->nbr, e->nbr_cnt, e->force, e->pred, e->queue);
-    LAUNCH(e, k_collide_predict, BBX_SMALL_GRID, 128, P, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force, e->pred);
-    CU(cudaGetLastError());
-    return BBX_OK;
+    if(e->n > 0){
+        LAUNCH(e, k_force_np_predict, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur],
+               e->nbr, e->nbr_cnt, e->force, e->pred, e->queue);
+        LAUNCH(e, k_collide_predict, BBX_SMALL_GRID, 128, P, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force, e->pred);
+        CU(cudaGetLastError());
+    }
+    return exchange1(e, e->pred); // ghost x*
 }
 static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
     int cur = e->cur;
-    LAUNCH(e, k_pressure, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
-           e->nbr, e->nbr_cnt, e->pressure, e->rho_pred, e->rho_err, e->posq);
-    CU(cudaGetLastError());
-    return BBX_OK;
+    if(e->n > 0){
+        LAUNCH(e, k_pressure, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
+               e->nbr, e->nbr_cnt, e->pressure, e->rho_pred, e->rho_err, e->posq);
+        CU(cudaGetLastError());
+    }
+    return exchange1(e, e->posq); // ghost (x, p / rho*^2)
 }
 static int phase_pressure_force(bbx_engine *e, const StepParams &P, int integrate){
     int cur = e->cur; int nb = div_up(e->n, BBX_BS);
-    if(integrate){
-        LAUNCH(e, k_pressure_force<1>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue);
-        LAUNCH(e, k_collide_integrate, BBX_SMALL_GRID, 128, P, e->grid, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force);
-    }else{
-        LAUNCH(e, k_pressure_force<0>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue);
+    if(e->n > 0){
+        if(integrate){
+            LAUNCH(e, k_pressure_force<1>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue);
+            LAUNCH(e, k_collide_integrate, BBX_SMALL_GRID, 128, P, e->grid, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force);
+        }else{
+            LAUNCH(e, k_pressure_force<0>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue);
+        }
+        CU(cudaGetLastError());
     }
-    CU(cudaGetLastError());
+    // after the integration the neighbours need the new x, v of my boundary planes (in the old order) to
+    // run their own grid update: that is where migrating particles change owner
+    if(integrate) return exchange2(e, e->pos[cur], e->vel[cur]);
     return BBX_OK;
 }
 static int phase_integrate(bbx_engine *e, const StepParams &P, int with_fp){
     int cur = e->cur;
-    LAUNCH(e, k_integrate, div_up(e->n, 256), 256, P, e->grid, e->st, e->colliders, e->cull, e->pos[cur], e->vel[cur], e->force, with_fp ? e->force_p : (const float4 *)nullptr);
-    CU(cudaGetLastError());
-    return BBX_OK;
+    if(e->n > 0){
+        LAUNCH(e, k_integrate, div_up(e->n, 256), 256, P, e->grid, e->st, e->colliders, e->cull, e->pos[cur], e->vel[cur], e->force, with_fp ? e->force_p : (const float4 *)nullptr);
+        CU(cudaGetLastError());
+    }
+    return exchange2(e, e->pos[cur], e->vel[cur]);
 }
 static int phase_pseudo_viscosity(bbx_engine *e, const StepParams &P, double dt){
     if(!(e->cfg.pseudo_viscosity * dt > 0.1)) return BBX_OK; // sph_equations3.cpp:655-657
     int cur = e->cur;
-    LAUNCH(e, k_pseudo_aggregate, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->smoothed);
-    LAUNCH(e, k_pseudo_interpolate, div_up(e->n, 256), 256, P, e->vel[cur], e->smoothed);
-    CU(cudaGetLastError());
-    return BBX_OK;
+    if(e->n > 0){
+        LAUNCH(e, k_pseudo_aggregate, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->smoothed);
+        LAUNCH(e, k_pseudo_interpolate, div_up(e->n, 256), 256, P, e->vel[cur], e->smoothed);
+        CU(cudaGetLastError());
+    }
+    return exchange1(e, e->vel[cur]);
 }
 static int read_state(bbx_engine *e){
     CU(cudaMemcpyAsync(e->st_host, e->st, sizeof(DevState), cudaMemcpyDeviceToHost, e->stream));
@@ -536,7 +658,7 @@ static int read_state(bbx_engine *e){
 }
 
 static int step_pcisph(bbx_engine *e, double dt){
-    if(e->n == 0) return BBX_OK;
+    if(e->n == 0 && !IS_SLAB(e)) return BBX_OK;
     if(!(dt > 0)) return set_error(BBX_ERR_INVALID, "dt must be positive");
     StepParams P;
     int rc;
@@ -559,7 +681,8 @@ static int step_pcisph(bbx_engine *e, double dt){
         for(int k = 0; k < e->cfg.pcisph_max_iterations; k++){
             if(k > 0){
                 tick(e, T_PREDICT);
-                LAUNCH(e, k_predict_again, div_up(e->n, 256), 256, P, e->colliders, e->cull, e->pos[e->cur], e->vel[e->cur], e->force, e->force_p, e->pred);
+                if(e->n > 0) LAUNCH(e, k_predict_again, div_up(e->n, 256), 256, P, e->colliders, e->cull, e->pos[e->cur], e->vel[e->cur], e->force, e->force_p, e->pred);
+                if((rc = exchange1(e, e->pred))) return rc;
             }
             tick(e, T_PRESSURE);
             if((rc = phase_pressure(e, P, k == 0))) return rc;
@@ -567,6 +690,7 @@ static int step_pcisph(bbx_engine *e, double dt){
             if((rc = phase_pressure_force(e, P, 0))) return rc;
             it++;
             // the loop exit test needs max |rho* - rho0| on the host, as in the reference (pcisph_equations3.cpp:238-246)
+            if(IS_SLAB(e)) COMM(e->comm->allreduce_max_u32(e->stream, &e->st->max_err_bits, 1));
             if((rc = read_state(e))) return rc;
             float maxerr; memcpy(&maxerr, &e->st_host->max_err_bits, 4);
             if(fabs((double)maxerr / e->cfg.target_density) < e->cfg.pcisph_max_density_error_ratio) break;
@@ -584,7 +708,7 @@ static int step_pcisph(bbx_engine *e, double dt){
 }
 
 static int step_sph(bbx_engine *e, double dt){
-    if(e->n == 0) return BBX_OK;
+    if(e->n == 0 && !IS_SLAB(e)) return BBX_OK;
     if(!(dt > 0)) return set_error(BBX_ERR_INVALID, "dt must be positive");
     StepParams P;
     int rc;
@@ -594,8 +718,10 @@ static int step_sph(bbx_engine *e, double dt){
     tick(e, T_DENSITY);
     if((rc = phase_density(e, P, 1))) return rc;
     tick(e, T_FORCE_NP);
-    LAUNCH(e, k_sph_forces, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->posq, e->vel[e->cur], e->cell[e->cur], e->cell_start[e->cur], e->nbr, e->nbr_cnt, e->force);
-    CU(cudaGetLastError());
+    if(e->n > 0){
+        LAUNCH(e, k_sph_forces, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->posq, e->vel[e->cur], e->cell[e->cur], e->cell_start[e->cur], e->nbr, e->nbr_cnt, e->force);
+        CU(cudaGetLastError());
+    }
     tick(e, T_INTEGRATE);
     if((rc = phase_integrate(e, P, 0))) return rc;
     if((rc = phase_pseudo_viscosity(e, P, dt))) return rc;
@@ -620,7 +746,7 @@ int bbx_step_many(bbx_engine *e, double dt, int solver, int n){
 
 int bbx_run_phase(bbx_engine *e, int phase, double dt){
     CHECK_ENGINE(e);
-    if(e->n == 0) return BBX_OK;
+    if(e->n == 0 && !IS_SLAB(e)) return BBX_OK;
     StepParams P; make_params(e, dt, P);
     switch(phase){
         case BBX_PHASE_GRID: return grid_update(e);
@@ -651,6 +777,7 @@ int bbx_advance(bbx_engine *e, double seconds, int solver, int *substeps, float 
     double remaining = seconds; int count = 0;
     double scale = solver == BBX_SOLVER_SPH ? 1.0 : e->cfg.time_step_limit_scale;
     while(remaining > (double)0.0001f){ // `while(remainingTime > Epsilon)`, pcisph_solver3.cpp:76
+        if(IS_SLAB(e)) COMM(e->comm->allreduce_max_u32(e->stream, &e->st->max_force_bits, 1)); // same dt on every slab
         int rc = read_state(e); if(rc) return rc;
         float mf; memcpy(&mf, &e->st_host->max_force_bits, 4);
         unsigned nsteps = number_of_time_steps(e, remaining, (double)mf, scale);
@@ -680,7 +807,7 @@ int bbx_stats(bbx_engine *e, bbx_step_stats *out){
     e->st_host->iterations = it;
     const DevState &s = *e->st_host;
     memset(out, 0, sizeof(*out));
-    out->particles = e->n; out->ghosts = 0; out->substeps = e->substeps; out->pcisph_iterations = it;
+    out->particles = e->n; out->ghosts = e->n_glo + e->n_ghi; out->substeps = e->substeps; out->pcisph_iterations = it;
     const int done = (e->epoch + 1) & 1, next = e->epoch & 1; // flag slots of the last / the next grid update
     out->full_rebuild = (e->epoch > 0 && (e->last_force | s.rebuild_flag[done] | s.jump_flag[done])) ? 1 : 0;
     out->rebuild_flag = s.rebuild_flag[next]; out->neighbor_overflow = s.overflow;
@@ -693,8 +820,7 @@ int bbx_stats(bbx_engine *e, bbx_step_stats *out){
 }
 
 // ---------------------------------------------------------------------------------------- results
-int bbx_download(bbx_engine *e, int field, void *dst, int dtype){
-    CHECK_ENGINE(e);
+static int download(bbx_engine *e, int field, void *dst, int dtype, int compact){
     if(!dst) return set_error(BBX_ERR_INVALID, "null destination");
     if(e->n == 0) return BBX_OK;
     int cur = e->cur; int n = e->n;
@@ -716,45 +842,72 @@ int bbx_download(bbx_engine *e, int field, void *dst, int dtype){
     else if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "field %d needs BBX_F32 or BBX_F64", field);
     size_t esz = (dtype == BBX_F64) ? 8 : 4; size_t bytes = esz * comps * (size_t)n;
     int rc = ensure_stage(e, bytes); if(rc) return rc;
-    LAUNCH(e, k_download, div_up(n, 256), 256, n, e->pid[cur], s4, s1, si, comps, dtype == BBX_F64, e->stage);
+    LAUNCH(e, k_download, div_up(n, 256), 256, n, compact ? (const int *)nullptr : e->pid[cur], s4, s1, si, comps, dtype == BBX_F64, e->stage);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(dst, e->stage, bytes, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return BBX_OK;
 }
+int bbx_download(bbx_engine *e, int field, void *dst, int dtype){
+    CHECK_ENGINE(e);
+    if(IS_SLAB(e)) return set_error(BBX_ERR_INVALID, "bbx_download scatters by particle id over the whole set: use bbx_download_owned on a slab engine");
+    return download(e, field, dst, dtype, 0);
+}
+int bbx_download_owned(bbx_engine *e, int field, void *dst, int dtype, int *ids, int *count){
+    CHECK_ENGINE(e);
+    if(count) *count = e->n;
+    if(e->n == 0) return BBX_OK;
+    if(ids){
+        CU(cudaMemcpyAsync(ids, e->pid[e->cur], sizeof(int) * (size_t)e->n, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    if(!dst) return BBX_OK;
+    return download(e, field, dst, dtype, 1);
+}
 
 int bbx_export_cells(bbx_engine *e, int *cell_count, int *cell_order){
     CHECK_ENGINE(e);
     if(!cell_count || !cell_order) return set_error(BBX_ERR_INVALID, "null");
-    int total = e->grid.total;
-    if(!e->have_chains || e->n == 0){ memset(cell_count, 0, sizeof(int) * (size_t)total); return BBX_OK; }
-    int rc = ensure_stage(e, sizeof(int) * (size_t)total); if(rc) return rc;
-    LAUNCH(e, k_export_cells, div_up(total, 256), 256, total, e->cell_start[e->cur], (int *)e->stage);
+    // cell_count covers the GLOBAL grid; a slab engine fills the cells it owns (others 0) and cell_order holds
+    // its owned particles: the single-domain order is the concatenation of the slabs' orders
+    const DevGrid &g = e->grid;
+    size_t gtotal = (size_t)g.plane * g.gnz;
+    memset(cell_count, 0, sizeof(int) * gtotal);
+    if(!e->have_chains || e->n == 0) return BBX_OK;
+    int own_cells = g.c_own1 - g.c_own0;
+    int rc = ensure_stage(e, sizeof(int) * (size_t)own_cells); if(rc) return rc;
+    LAUNCH(e, k_export_cells, div_up(own_cells, 256), 256, own_cells, e->cell_start[e->cur] + g.c_own0, (int *)e->stage);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(cell_count, e->stage, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(cell_count + (size_t)(g.zoff + g.own_z0) * g.plane, e->stage, sizeof(int) * (size_t)own_cells, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaMemcpyAsync(cell_order, e->pid[e->cur], sizeof(int) * (size_t)e->n, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return BBX_OK;
 }
 
-int bbx_export_neighbors(bbx_engine *e, int *counts, int *ids){
-    CHECK_ENGINE(e);
+static int export_neighbors(bbx_engine *e, int *counts, int *ids, int compact){
     if(!counts || !ids) return set_error(BBX_ERR_INVALID, "null");
     if(e->n == 0) return BBX_OK;
     int n = e->n; size_t bytes = sizeof(int) * (size_t)n * (BBX_MAX_NEIGHBORS + 1);
     int rc = ensure_stage(e, bytes); if(rc) return rc;
     int *dc = (int *)e->stage; int *di = dc + n;
-    LAUNCH(e, k_export_neighbors, div_up(n, BBX_BS), BBX_BS, n, e->grid, e->pid[e->cur], e->cell[e->cur], e->cell_start[e->cur], e->nbr, e->nbr_cnt, dc, di);
+    LAUNCH(e, k_export_neighbors, div_up(n, BBX_BS), BBX_BS, n, e->grid, e->pid[e->cur], e->cell[e->cur], e->cell_start[e->cur], e->nbr, e->nbr_cnt, dc, di, compact);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(counts, dc, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaMemcpyAsync(ids, di, sizeof(int) * (size_t)n * BBX_MAX_NEIGHBORS, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return BBX_OK;
 }
+int bbx_export_neighbors(bbx_engine *e, int *counts, int *ids){
+    CHECK_ENGINE(e);
+    if(IS_SLAB(e)) return set_error(BBX_ERR_INVALID, "use bbx_export_neighbors_owned on a slab engine");
+    return export_neighbors(e, counts, ids, 0);
+}
+int bbx_export_neighbors_owned(bbx_engine *e, int *counts, int *ids){ CHECK_ENGINE(e); return export_neighbors(e, counts, ids, 1); }
 
 int bbx_inject_chains(bbx_engine *e, const int *cell_count, const int *cell_order){
     CHECK_ENGINE(e);
     if(!cell_count || !cell_order) return set_error(BBX_ERR_INVALID, "null");
+    if(IS_SLAB(e)) return set_error(BBX_ERR_INVALID, "bbx_inject_chains is not available on slab engines");
     if(e->n == 0) return BBX_OK;
     int total = e->grid.total, n = e->n, cur = e->cur, nxt = cur ^ 1;
     std::vector<int> start((size_t)total + 1), cell_of((size_t)n);
@@ -803,8 +956,74 @@ int bbx_reset_kernel_time(bbx_engine *e){
     return BBX_OK;
 }
 
-int bbx_comm_unique_id(unsigned char id[BBX_NCCL_ID_BYTES]){ (void)id; return set_error(BBX_ERR_COMM, "multi-GPU slab exchange is not built in this revision"); }
+// ------------------------------------------------------------------------------------ slab groups
+int bbx_comm_unique_id(unsigned char id[BBX_NCCL_ID_BYTES]){
+    if(!id) return set_error(BBX_ERR_INVALID, "null");
+    if(!g_nccl.load()) return set_error(BBX_ERR_COMM, "%s", g_nccl.load_error.c_str());
+    ncclUniqueId uid;
+    ncclResult_t r = g_nccl.GetUniqueId(&uid);
+    if(r != ncclSuccess) return set_error(BBX_ERR_COMM, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    static_assert(sizeof(ncclUniqueId) == BBX_NCCL_ID_BYTES, "ncclUniqueId size");
+    memcpy(id, &uid, BBX_NCCL_ID_BYTES);
+    return BBX_OK;
+}
 int bbx_comm_init(bbx_engine *e, int rank, int nranks, const unsigned char id[BBX_NCCL_ID_BYTES]){
-    (void)e; (void)rank; (void)nranks; (void)id;
-    return set_error(BBX_ERR_COMM, "multi-GPU slab exchange is not built in this revision");
+    CHECK_ENGINE(e);
+    if(!id || nranks < 1 || rank < 0 || rank >= nranks) return set_error(BBX_ERR_INVALID, "bad rank / nranks");
+    if(e->comm) return set_error(BBX_ERR_INVALID, "engine already has a communicator");
+    if((rank > 0) != (e->has_lo != 0) || (rank + 1 < nranks) != (e->has_hi != 0))
+        return set_error(BBX_ERR_INVALID, "rank %d of %d does not match the slab [%d, %d) of %d planes (slabs must be ordered by z)", rank, nranks,
+                         e->cfg.slab_z_begin, e->cfg.slab_z_end, e->grid.gnz);
+    NcclComm *c = new NcclComm();
+    if(c->init(rank, nranks, id)){ std::string m = c->err; delete c; return set_error(BBX_ERR_COMM, "%s", m.c_str()); }
+    e->comm = c;
+    return BBX_OK;
+}
+int bbx_comm_init_local(bbx_engine *e, int rank, int nranks, const char *group){
+    CHECK_ENGINE(e);
+    if(e->comm) return set_error(BBX_ERR_INVALID, "engine already has a communicator");
+    if((rank > 0) != (e->has_lo != 0) || (rank + 1 < nranks) != (e->has_hi != 0))
+        return set_error(BBX_ERR_INVALID, "rank %d of %d does not match the slab [%d, %d) of %d planes (slabs must be ordered by z)", rank, nranks,
+                         e->cfg.slab_z_begin, e->cfg.slab_z_end, e->grid.gnz);
+    LocalComm *c = new LocalComm();
+    if(c->init(group, rank, nranks)){ std::string m = c->err; delete c; return set_error(BBX_ERR_COMM, "%s", m.c_str()); }
+    e->comm = c;
+    return BBX_OK;
+}
+// ParticleSet3 has no notion of slabs: this is the planner a multi-GPU host uses.  plane_counts[z] =
+// particles per global cell plane; z_bounds[r] .. z_bounds[r+1] = planes of rank r, balanced by count with
+// at least one plane per rank.
+int bbx_slab_plan(int nplanes, const long long *plane_counts, int nranks, int *z_bounds){
+    if(!plane_counts || !z_bounds || nranks < 1 || nplanes < nranks) return set_error(BBX_ERR_INVALID, "need at least one plane per rank");
+    long long total = 0;
+    for(int z = 0; z < nplanes; z++){ if(plane_counts[z] < 0) return set_error(BBX_ERR_INVALID, "negative plane count"); total += plane_counts[z]; }
+    z_bounds[0] = 0;
+    long long acc = 0; int z = 0;
+    for(int r = 1; r < nranks; r++){
+        // smallest z with prefix(z) >= r/nranks of the total, leaving a plane for every rank on both sides
+        long long want = (total * r + nranks / 2) / nranks;
+        int lo = z_bounds[r - 1] + 1, hi = nplanes - (nranks - r);
+        while(z < lo){ acc += plane_counts[z]; z++; }
+        while(z < hi && acc < want){ acc += plane_counts[z]; z++; }
+        // step back one plane if that lands closer to the target
+        if(z > lo && acc - want > want - (acc - plane_counts[z - 1])){ z--; acc -= plane_counts[z]; }
+        z_bounds[r] = z;
+    }
+    z_bounds[nranks] = nplanes;
+    return BBX_OK;
+}
+// global cell plane of each particle (the hash of Grid::GetHashedPosition, z component), host arithmetic
+int bbx_plane_histogram(const bbx_grid_desc *grid, int n, const void *pos, int dtype, long long *plane_counts){
+    if(!grid || !plane_counts || (n > 0 && !pos) || (dtype != BBX_F32 && dtype != BBX_F64)) return set_error(BBX_ERR_INVALID, "bad arguments");
+    for(int z = 0; z < grid->n[2]; z++) plane_counts[z] = 0;
+    for(int i = 0; i < n; i++){
+        double p = dtype == BBX_F64 ? ((const double *)pos)[3 * (size_t)i + 2] : (double)((const float *)pos)[3 * (size_t)i + 2];
+        double eps = 0.0;
+        if(fabs(p - grid->min[2]) < 1e-8) eps = (double)0.0001f;
+        else if(fabs(p - grid->max[2]) < 1e-8) eps = -(double)0.0001f;
+        int u = (int)floor((p + eps - grid->min[2]) / grid->cell_len[2]);
+        u = u < 0 ? 0 : (u >= grid->n[2] ? grid->n[2] - 1 : u);
+        plane_counts[u]++;
+    }
+    return BBX_OK;
 }

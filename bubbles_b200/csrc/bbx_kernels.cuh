@@ -24,32 +24,46 @@
 
 // A1: cell hash per particle + histogram + jump detection.  Thread 0 also resets the per-sub-step
 // statistics and the flag slots of the *next* epoch (see DevState).
-__global__ void __launch_bounds__(256) k_hash_count(int n, const float4 *__restrict__ pos, const int *__restrict__ oldcell,
+__global__ void __launch_bounds__(256) k_hash_count(int n_all, int n_lo, int n_own, const float4 *__restrict__ pos, const int *__restrict__ oldcell,
                                                     int *__restrict__ newcell, int *__restrict__ count,
                                                     DevGrid g, DevState *st, int have_old, int par,
                                                     unsigned long long *__restrict__ scan_status, int scan_tiles)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i == 0){
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if(idx == 0){
         st->rebuild_flag[par ^ 1] = 0; st->jump_flag[par ^ 1] = 0; st->lost[par ^ 1] = 0;
         st->overflow = 0; st->clamped = 0; st->nan_count = 0; st->max_force_bits = 0; st->max_err_bits = 0;
         st->qn[0] = 0; st->qn[1] = 0; st->scan_ticket = 0; st->n_occ = 0;
     }
-    if(i < scan_tiles) scan_status[i] = 0ull;
-    if(i >= n) return;
+    if(idx < scan_tiles) scan_status[idx] = 0ull;
+    if(idx >= n_all) return;
+    // slots [-n_lo, 0) hold the lower ghost plane, [0, n_own) the owned particles, [n_own, ...) the upper ghosts
+    const int i = idx - n_lo;
+    const bool owned = i >= 0 && i < n_own;
     float4 p = pos[i];
     int ux, uy, uz;
     int c = bbx_hash(g, p.x, p.y, p.z, &ux, &uy, &uz);
     if(c < 0){
-        // outside the domain: the reference would index out of bounds here (AssertA compiled out);
-        // clamp to the nearest cell and raise the sticky error flag
-        ux = min(max(ux, 0), g.n[0] - 1); uy = min(max(uy, 0), g.n[1] - 1); uz = min(max(uz, 0), g.n[2] - 1);
+        int gz = uz + g.zoff;
+        if(ux < 0 || ux >= g.n[0] || uy < 0 || uy >= g.n[1] || gz < 0 || gz >= g.gnz){
+            // outside the domain: the reference would index out of bounds here (AssertA compiled out);
+            // clamp to the nearest cell and raise the sticky error flag
+            ux = min(max(ux, 0), g.n[0] - 1); uy = min(max(uy, 0), g.n[1] - 1); gz = min(max(gz, 0), g.gnz - 1);
+            uz = gz - g.zoff;
+            if(owned) st->error = BBX_ERR_OUT_OF_DOMAIN;
+        }
+        if(uz < 0 || uz >= g.n[2]){
+            // beyond the slab's halo: a ghost that left towards its owner's side is simply dropped; an owned
+            // particle can only get here by moving two planes in one sub-step, which the halo cannot follow
+            if(owned) st->error = BBX_ERR_OUT_OF_DOMAIN;
+            newcell[i] = -1;
+            return;
+        }
         c = ux + uy * g.n[0] + uz * g.plane;
-        st->error = BBX_ERR_OUT_OF_DOMAIN;
     }
     newcell[i] = c;
     atomicAdd(&count[c], 1);
-    if(have_old){
+    if(have_old && owned){
         int oc = oldcell[i];
         int oz = oc / g.plane; int rem = oc - oz * g.plane; int oy = rem / g.n[0]; int ox = rem - oy * g.n[0];
         if(abs(ox - ux) > 1 || abs(oy - uy) > 1 || abs(oz - uz) > 1){ st->jump_flag[par] = 1; atomicAdd(&st->lost[par], 1); }
@@ -59,12 +73,14 @@ __global__ void __launch_bounds__(256) k_hash_count(int n, const float4 *__restr
 // A2: single-pass exclusive scan of the per-cell counts (decoupled look-back over tiles of 2048 cells).
 // The scanned value packs (occupied cells so far) << 31 | (particles so far), so that the same pass also
 // emits the compact list of occupied cells the fill kernel iterates over.  count[] is zeroed on the way
-// out (it is the histogram of the next sub-step and the cursor of the full rebuild).
+// out (it is the histogram of the next sub-step and the cursor of the full rebuild).  count / start are
+// passed offset to the first OWNED cell c0 of a slab engine (c0 = 0 for a single domain): owned slots
+// start at 0, the ghost planes are laid out around them by k_ghost_table.
 #define SCAN_TILE 2048
 #define SCAN_FLAG_AGG (1ull << 62)
 #define SCAN_FLAG_INC (2ull << 62)
 #define SCAN_VALUE_MASK ((1ull << 62) - 1)
-__global__ void __launch_bounds__(256) k_scan_cells(int *__restrict__ count, int total, int n_total,
+__global__ void __launch_bounds__(256) k_scan_cells(int *__restrict__ count, int total, int c0,
         unsigned long long *scan_status, DevState *st, int *__restrict__ start, int *__restrict__ occ_cells)
 {
     __shared__ unsigned long long ws[8];
@@ -77,7 +93,7 @@ __global__ void __launch_bounds__(256) k_scan_cells(int *__restrict__ count, int
     const int base = tile * SCAN_TILE + threadIdx.x * (SCAN_TILE / 256);
     int v[SCAN_TILE / 256];
     unsigned long long s = 0;
-    if(base + SCAN_TILE / 256 <= total){
+    if(base + SCAN_TILE / 256 <= total && (((size_t)count) & 15) == 0){ // (a slab's first owned cell may be unaligned)
         int4 a = *reinterpret_cast<const int4 *>(count + base), b = *reinterpret_cast<const int4 *>(count + base + 4);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         *reinterpret_cast<int4 *>(count + base) = make_int4(0, 0, 0, 0);
@@ -129,13 +145,14 @@ __global__ void __launch_bounds__(256) k_scan_cells(int *__restrict__ count, int
         int idx = base + k;
         if(idx < total){
             start[idx] = (int)(run & 0x7fffffffull);
-            if(v[k] > 0) occ_cells[(int)(run >> 31)] = idx;
+            if(v[k] > 0) occ_cells[(int)(run >> 31)] = idx + c0;
             run += (unsigned long long)v[k] + (v[k] > 0 ? (1ull << 31) : 0ull);
         }
     }
     if(tile == gridDim.x - 1 && threadIdx.x == 255){
-        // the last tile's last thread holds the grand total
-        start[total] = n_total;
+        // the last tile's last thread holds the grand total = owned particles after this update
+        start[total] = (int)(run & 0x7fffffffull);
+        st->n_own = (int)(run & 0x7fffffffull);
         st->n_occ = (int)(run >> 31);
     }
 }
@@ -216,21 +233,23 @@ __global__ void __launch_bounds__(256) k_fill_incremental(DevGrid g, const DevSt
 // (Grid::DistributeByParticle, grid.h:390-407).  scatter with atomics -> per-cell sort by id -> gather.
 // Grid-stride kernels: launched with a small grid every sub-step, they return at once unless the flags
 // (device side, no host round trip) ask for the rebuild.
-__global__ void __launch_bounds__(256) k_full_scatter(int n, const DevState *st, int par, int force, const int *__restrict__ newcell,
+__global__ void __launch_bounds__(256) k_full_scatter(int n_all, int n_lo, DevGrid g, const DevState *st, int par, int force, const int *__restrict__ newcell,
         const int *__restrict__ start_new, int *__restrict__ cursor, int *__restrict__ perm)
 {
     if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
-    for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x){
+    for(int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_all; idx += gridDim.x * blockDim.x){
+        int i = idx - n_lo;
         int c = newcell[i];
+        if(c < g.c_own0 || c >= g.c_own1) continue; // left the slab (its new owner picks it up from its ghost plane)
         int k = atomicAdd(&cursor[c], 1);
         perm[start_new[c] + k] = i;
     }
 }
-__global__ void __launch_bounds__(256) k_full_sort_cells(int total, const DevState *st, int par, int force, const int *__restrict__ start_new,
+__global__ void __launch_bounds__(256) k_full_sort_cells(DevGrid g, const DevState *st, int par, int force, const int *__restrict__ start_new,
         const int *__restrict__ pid_old, int *__restrict__ perm, int *__restrict__ cursor)
 {
     if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
-    for(int c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x){
+    for(int c = g.c_own0 + blockIdx.x * blockDim.x + threadIdx.x; c < g.c_own1; c += gridDim.x * blockDim.x){
         cursor[c] = 0; // back to an all-zero histogram for the next sub-step
         int s = start_new[c], e = start_new[c + 1];
         for(int a = s + 1; a < e; a++){ // insertion sort by original id (segments are a dozen long)
@@ -241,18 +260,49 @@ __global__ void __launch_bounds__(256) k_full_sort_cells(int total, const DevSta
         }
     }
 }
-__global__ void __launch_bounds__(256) k_full_gather(int n, const DevState *st, int par, int force, const int *__restrict__ perm,
+__global__ void __launch_bounds__(256) k_full_gather(const DevState *st, int par, int force, const int *__restrict__ perm,
         const int *__restrict__ newcell,
         const float4 *__restrict__ pos_old, const float4 *__restrict__ vel_old, const int *__restrict__ pid_old,
         float4 *__restrict__ pos_new, float4 *__restrict__ vel_new, int *__restrict__ pid_new, int *__restrict__ cell_new)
 {
     if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
+    const int n = st->n_own;
     for(int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x){
         int j = perm[d];
         pos_new[d] = pos_old[j];
         vel_new[d] = vel_old[j];
         pid_new[d] = pid_old[j];
         cell_new[d] = newcell[j];
+    }
+}
+
+// ---- slab engines: sizes of the boundary planes after the scan, and the ghost planes' part of the cell table
+__global__ void k_slab_counts(DevGrid g, DevState *st, const int *__restrict__ start_new, int has_lo, int has_hi){
+    const int n = st->n_own;
+    st->n_first = has_lo ? start_new[g.c_own0 + g.plane] : 0;
+    st->n_last = has_hi ? n - start_new[g.c_own1 - g.plane] : 0;
+}
+// recv_lo / recv_hi: the neighbour's slice of ITS cell table over the plane it sent (plane + 1 entries each).
+// Lower ghost cells end at slot 0 (negative starts), upper ghost cells begin at n_own.
+__global__ void __launch_bounds__(256) k_ghost_table(DevGrid g, int n_own, int has_lo, int has_hi,
+        const int *__restrict__ recv_lo, const int *__restrict__ recv_hi,
+        int *__restrict__ start_new, int *__restrict__ cell_new, int *__restrict__ count)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if(c >= g.plane) return;
+    if(has_lo){
+        int s = recv_lo[c] - recv_lo[g.plane], e = recv_lo[c + 1] - recv_lo[g.plane];
+        start_new[c] = s;
+        count[c] = 0;
+        for(int j = s; j < e; j++) cell_new[j] = c;
+    }
+    if(has_hi){
+        int cc = g.c_own1 + c;
+        int s = n_own + recv_hi[c] - recv_hi[0], e = n_own + recv_hi[c + 1] - recv_hi[0];
+        start_new[cc] = s;
+        count[cc] = 0;
+        for(int j = s; j < e; j++) cell_new[j] = cc;
+        if(c == g.plane - 1) start_new[cc + 1] = e;
     }
 }
 
@@ -360,7 +410,7 @@ __global__ void __launch_bounds__(BBX_BS) k_density_lists(StepParams P, DevGrid 
         float *__restrict__ pressure, float4 *__restrict__ posq)
 {
     __shared__ float4 tile[BBX_DTILE + 8];
-    const int row = blockIdx.x;                       // y + z * ny
+    const int row = blockIdx.x + g.own_z0 * g.n[1];   // y + z * ny over the owned planes
     const int rowbase = row * g.n[0];                 // first cell of the row
     const int rs = cell_start[rowbase], re = cell_start[rowbase + g.n[0]];
     if(rs == re) return;
@@ -850,6 +900,29 @@ __global__ void __launch_bounds__(256) k_upload(int n, int first_id, const void 
     dvel[i] = make_float4(v[0], v[1], v[2], 0.f);
     pid[i] = first_id + i;
 }
+// slab engines: keep only the particles whose cell plane this slab owns (any superset of them may be passed,
+// e.g. the whole scene); ids = global particle ids (null: the index in the arrays).  The slot order is
+// arbitrary -- the full rebuild that follows orders every cell by ascending id.
+__global__ void __launch_bounds__(256) k_upload_slab(int n, const void *__restrict__ pos, const void *__restrict__ vel, const int *__restrict__ ids,
+        int is_f64, DevGrid g, int cap, DevState *st, float4 *__restrict__ dpos, float4 *__restrict__ dvel, int *__restrict__ pid)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    float p[3], v[3];
+    for(int k = 0; k < 3; k++){
+        if(is_f64){ p[k] = (float)((const double *)pos)[3 * (size_t)i + k]; v[k] = (float)((const double *)vel)[3 * (size_t)i + k]; }
+        else{ p[k] = ((const float *)pos)[3 * (size_t)i + k]; v[k] = ((const float *)vel)[3 * (size_t)i + k]; }
+    }
+    int ux, uy, uz;
+    bbx_hash(g, p[0], p[1], p[2], &ux, &uy, &uz);
+    int gz = min(max(uz + g.zoff, 0), g.gnz - 1) - g.zoff; // out-of-domain z is clamped like k_hash_count does
+    if(gz < g.own_z0 || gz >= g.own_z1) return;
+    int slot = atomicAdd(&st->n_own, 1);
+    if(slot >= cap){ st->error = BBX_ERR_CAPACITY; return; }
+    dpos[slot] = make_float4(p[0], p[1], p[2], 0.f);
+    dvel[slot] = make_float4(v[0], v[1], v[2], 0.f);
+    pid[slot] = ids ? ids[i] : i;
+}
 // overwrite pos/vel of existing particles: slot i holds particle pid[i]
 __global__ void __launch_bounds__(256) k_overwrite(int n, const int *__restrict__ pid, const void *__restrict__ pos, const void *__restrict__ vel,
                                                    int is_f64, float4 *__restrict__ dpos, float4 *__restrict__ dvel)
@@ -867,12 +940,13 @@ __global__ void __launch_bounds__(256) k_overwrite(int n, const int *__restrict_
 }
 // scatter a sorted-order field back to original-id order. comp: 3 = xyz of a float4 array, 1 = .w of a
 // float4 array (src4) or a plain float array (src1)
+// (pid = null: keep the slot order -- bbx_download_owned)
 __global__ void __launch_bounds__(256) k_download(int n, const int *__restrict__ pid, const float4 *__restrict__ src4,
                                                   const float *__restrict__ src1, const int *__restrict__ srci, int comps, int is_f64, void *__restrict__ dst)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
-    size_t id = (size_t)pid[i];
+    size_t id = pid ? (size_t)pid[i] : (size_t)i;
     if(srci){ ((int *)dst)[id] = srci[i]; return; }
     if(comps == 3){
         float4 v = src4[i];
@@ -891,7 +965,7 @@ __global__ void __launch_bounds__(256) k_export_cells(int total, const int *__re
 // order inside a cell) with original ids: what Bucket::pids holds after UpdateParticlesBuckets.
 __global__ void __launch_bounds__(BBX_BS) k_export_neighbors(int n, DevGrid g, const int *__restrict__ pid, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
-        int *__restrict__ counts, int *__restrict__ ids)
+        int *__restrict__ counts, int *__restrict__ ids, int compact)
 {
     int i = blockIdx.x * BBX_BS + threadIdx.x;
     if(i >= n) return;
@@ -901,7 +975,7 @@ __global__ void __launch_bounds__(BBX_BS) k_export_neighbors(int n, DevGrid g, c
     int cz = c / g.plane; int rem = c - cz * g.plane; int cy = rem / g.n[0]; int cx = rem - cy * g.n[0];
     (void)cz; (void)cy;
     int cnt = nbr_cnt[i];
-    size_t id = (size_t)pid[i];
+    size_t id = compact ? (size_t)i : (size_t)pid[i]; // output row: slot order (slab engines) or particle id
     int *out = ids + id * BBX_MAX_NEIGHBORS;
     // key = (reference rank of the neighbour cell) << 40 | slot: sort ascending (insertion, <= 100 items)
     unsigned long long keys[BBX_MAX_NEIGHBORS];

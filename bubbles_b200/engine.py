@@ -130,7 +130,7 @@ class Engine:
     """One bbx_engine handle."""
 
     def __init__(self, grid, spacing, kernel_scale, max_particles, device=0, with_gravity=True,
-                 reference_compat=True, **overrides):
+                 reference_compat=True, slab=None, **overrides):
         self.lib = L.load()
         cfg = L.Config()
         _check(self.lib.bbx_config_default(C.byref(cfg), int(with_gravity)))
@@ -140,6 +140,8 @@ class Engine:
         cfg.kernel_scale = kernel_scale
         cfg.pcisph_reference_compat = int(reference_compat)
         cfg.grid = grid
+        if slab is not None:  # owned global cell planes [z0, z1) of a multi-GPU slab decomposition
+            cfg.slab_z_begin, cfg.slab_z_end = int(slab[0]), int(slab[1])
         for k, v in overrides.items():
             if k == "gravity":
                 cfg.gravity[:] = v
@@ -186,6 +188,22 @@ class Engine:
         pos, dt = self._arr(pos)
         vel = np.ascontiguousarray(vel, dtype=pos.dtype)
         _check(self.lib.bbx_set_particles(self.h, len(pos), pos.ctypes.data, vel.ctypes.data, dt))
+
+    def set_particles_ids(self, pos, vel, ids=None):
+        """Slab engines: keeps the particles of the owned planes; collective over the slab group."""
+        pos, dt = self._arr(pos)
+        vel = np.ascontiguousarray(vel, dtype=pos.dtype)
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int32)
+        _check(self.lib.bbx_set_particles_ids(self.h, len(pos), pos.ctypes.data, vel.ctypes.data,
+                                              None if ids is None else ids.ctypes.data, dt))
+
+    def comm_init_local(self, rank, nranks, group):
+        _check(self.lib.bbx_comm_init_local(self.h, rank, nranks, group.encode()))
+
+    def comm_init(self, rank, nranks, unique_id):
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        _check(self.lib.bbx_comm_init(self.h, rank, nranks, buf))
 
     def append_particles(self, pos, vel):
         pos, dt = self._arr(pos)
@@ -255,6 +273,32 @@ class Engine:
             code = L.F64 if out.dtype == np.float64 else L.F32
         _check(self.lib.bbx_download(self.h, field, out.ctypes.data, code))
         return out
+
+    _VEC = (L.POSITION, L.VELOCITY, L.FORCE, L.PRED_POSITION, L.PRESSURE_FORCE, L.FORCE_NP)
+
+    def download_owned(self, field=None, dtype=np.float64):
+        """(ids, values) of the owned particles in the engine's cell order; field None: ids only."""
+        n = self.n
+        ids = np.zeros(n, dtype=np.int32)
+        cnt = C.c_int()
+        if field is None:
+            _check(self.lib.bbx_download_owned(self.h, 0, None, L.F32, ids.ctypes.data, C.byref(cnt)))
+            return ids, None
+        if field == L.NEIGHBOR_COUNT:
+            out = np.zeros(n, dtype=np.int32)
+            code = L.I32
+        else:
+            out = np.zeros((n, 3) if field in self._VEC else n, dtype=dtype)
+            code = L.F64 if out.dtype == np.float64 else L.F32
+        _check(self.lib.bbx_download_owned(self.h, field, out.ctypes.data, code, ids.ctypes.data, C.byref(cnt)))
+        return ids, out
+
+    def export_neighbors_owned(self):
+        n = self.n
+        counts = np.zeros(n, dtype=np.int32)
+        ids = np.full((n, L.MAX_NEIGHBORS), -1, dtype=np.int32)
+        _check(self.lib.bbx_export_neighbors_owned(self.h, counts.ctypes.data, ids.ctypes.data))
+        return counts, ids
 
     def export_cells(self):
         count = np.zeros(self.grid.total, dtype=np.int32)

@@ -127,8 +127,11 @@ typedef struct bbx_config {
     double restitution;       /* 0.6 in TimeIntegrationFor (sph_equations3.cpp:307)          */
     double time_step_limit_scale; /* kDefaultTimeStepLimitScale = 5 (pcisph_solver2.cpp:7)   */
     bbx_grid_desc grid;       /* domain grid                                                 */
-    /* multi-GPU slab decomposition (z planes); single GPU: z_begin = 0, z_end = grid.n[2]   */
+    /* multi-GPU slab decomposition: this engine owns the global cell planes [slab_z_begin, slab_z_end)
+     * of `grid` (which always describes the WHOLE domain).  0, 0 (or 0, grid.n[2]) = single domain.      */
     int slab_z_begin, slab_z_end;
+    int ghost_capacity;       /* slab engines: particle slots per ghost plane (0 = max_particles / 4)  */
+    int reserved;
 } bbx_config;
 
 typedef struct bbx_step_stats {
@@ -171,6 +174,10 @@ int bbx_get_delta(bbx_engine *e, double dt, double *delta);
 /* SphParticleSet3FromBuilder + Setup's initial DistributeByParticle: replaces all particles;
  * pos / vel are n x 3 (AoS), dtype BBX_F32 or BBX_F64 */
 int bbx_set_particles(bbx_engine *e, int n, const void *pos, const void *vel, int dtype);
+/* slab engines: same, with explicit global particle ids (NULL = the index in the arrays).  A slab engine
+ * keeps the particles whose cell plane it owns and ignores the rest, so every rank may pass the whole
+ * scene or just its share.  Collective over the slab group (ends with the first ghost exchange).        */
+int bbx_set_particles_ids(bbx_engine *e, int n, const void *pos, const void *vel, const int *ids, int dtype);
 /* ContinuousParticleSetBuilder3-style append: new ids continue from the current count, new
  * particles go to the tail of their cell's chain (DistributeByParticleList, grid.h:358-387) */
 int bbx_append_particles(bbx_engine *e, int n, const void *pos, const void *vel, int dtype);
@@ -200,10 +207,15 @@ int bbx_stats(bbx_engine *e, bbx_step_stats *out);
 
 /* -- results ----------------------------------------------------------------------------------- */
 int bbx_download(bbx_engine *e, int field, void *dst, int dtype);
+/* slab engines (works on any engine): the owned particles in the engine's cell order; ids[k] = global id
+ * of row k of dst, *count = owned particles.  dst or ids may be NULL.                                   */
+int bbx_download_owned(bbx_engine *e, int field, void *dst, int dtype, int *ids, int *count);
 /* active chains: cell_count[total], cell_order[n] (concatenated chains, original ids) */
 int bbx_export_cells(bbx_engine *e, int *cell_count, int *cell_order);
 /* stored neighbour lists in the reference's bucket order: counts[n], ids[n*100] (unused = -1) */
 int bbx_export_neighbors(bbx_engine *e, int *counts, int *ids);
+/* same for the owned particles of a slab engine, rows in the order of bbx_download_owned (ids are global) */
+int bbx_export_neighbors_owned(bbx_engine *e, int *counts, int *ids);
 /* replace the chain order (parity tests: reproduce a history-dependent order) */
 int bbx_inject_chains(bbx_engine *e, const int *cell_count, const int *cell_order);
 /* set SphParticleSet3::requiresHigherLevelUpdate */
@@ -214,10 +226,24 @@ int bbx_launch_count(bbx_engine *e, long long *count);
 int bbx_kernel_time(bbx_engine *e, int phase, float *ms, int *launches);
 int bbx_reset_kernel_time(bbx_engine *e);
 
-/* -- multi-GPU (z-slab decomposition, NCCL over NVLink) ------------------------------------------ */
+/* -- multi-GPU (z-slab decomposition, NCCL over NVLink) ------------------------------------------
+ * The reference is single-GPU; this part of the ABI is new.  One engine per GPU / process
+ * owns a contiguous range of cell planes (bbx_config.slab_z_begin/end) plus one ghost plane per neighbour.
+ * After bbx_comm_init every stepping call is COLLECTIVE over the group (all ranks call it with the same
+ * arguments): the engine exchanges migrating particles, ghost planes (in the reference's chain order) and
+ * the per-phase ghost fields with rank-1 / rank+1 through ncclSend/ncclRecv, and the global flags (big-move
+ * rule, CFL force maximum, density error) through ncclAllReduce.  Cell orderings and neighbour lists of
+ * the slabs concatenate to exactly the single-domain ones. */
 #define BBX_NCCL_ID_BYTES 128
 int bbx_comm_unique_id(unsigned char id[BBX_NCCL_ID_BYTES]);
 int bbx_comm_init(bbx_engine *e, int rank, int nranks, const unsigned char id[BBX_NCCL_ID_BYTES]);
+/* several slab engines of one process on one device, each driven by its own host thread (same code path,
+ * copies instead of NCCL): lets the slab logic be verified against the single-domain engine on one GPU */
+int bbx_comm_init_local(bbx_engine *e, int rank, int nranks, const char *group);
+/* plane_counts[nplanes] -> z_bounds[nranks + 1]: slabs of whole planes balanced by particle count */
+int bbx_slab_plan(int nplanes, const long long *plane_counts, int nranks, int *z_bounds);
+/* particles per global cell plane (host arithmetic, same hash as the engine) */
+int bbx_plane_histogram(const bbx_grid_desc *grid, int n, const void *pos, int dtype, long long *plane_counts);
 
 #ifdef __cplusplus
 }
