@@ -379,7 +379,8 @@ def main():
                          "whole_step": {"bytes_per_update": BYTES_PER_UPDATE, "achieved": step_gbs, "frac": step_gbs / peak},
                          "phases_ms_per_step": {k: v[0] / args.steps for k, v in phase.items()},
                          "gap_ms_per_step": gap_ms / args.steps},
-            "stats": {"neighbor_overflow": st.neighbor_overflow, "clamped": st.clamped, "rebuild_flag": st.rebuild_flag},
+            "stats": {"neighbor_overflow": st.neighbor_overflow, "clamped": st.clamped, "rebuild_flag": st.rebuild_flag,
+                      "occupied_cells": st.occupied_cells, "max_candidates": st.max_candidates, "exact_passes": st.exact_passes},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(n)

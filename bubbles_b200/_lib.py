@@ -55,7 +55,8 @@ class StepStats(C.Structure):
                 ("pcisph_iterations", C.c_int), ("full_rebuild", C.c_int), ("rebuild_flag", C.c_int),
                 ("neighbor_overflow", C.c_int), ("lost_particles", C.c_int), ("clamped", C.c_int),
                 ("nan_count", C.c_int), ("max_force", C.c_float), ("max_density_error", C.c_float),
-                ("ms_grid", C.c_float), ("ms_step", C.c_float)]
+                ("ms_grid", C.c_float), ("ms_step", C.c_float),
+                ("exact_passes", C.c_int), ("max_candidates", C.c_int), ("occupied_cells", C.c_int), ("reserved", C.c_int)]
 
 
 # every symbol include/bbx.h declares: name -> (restype, argtypes)

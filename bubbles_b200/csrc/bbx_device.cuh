@@ -101,7 +101,9 @@ struct DevState {
     int iterations;
     int n_own;           // owned particles after the last grid update / upload (slab engines)
     int n_first, n_last; // particles in the first / last owned plane (what the slab neighbours hold as ghosts)
-    int pad;
+    int exact_passes;    // list-build passes repeated with the FP64 predicate (a candidate inside the guard band)
+    int max_candidates;  // largest 27-cell neighbourhood seen in the last list build
+
 };
 
 // Scalars of one sub-step, passed by value to every kernel.

@@ -52,7 +52,8 @@ struct bbx_engine {
     unsigned long long *scan_status;
     int scan_tiles;
     int epoch;       // grid updates done so far; flags are double-buffered by its parity (DevState)
-    int masked;      // cells smaller than h: the list build must test the per-particle cell window
+    int masked;      // cells smaller than h (informational; the cell-centric list build needs no window test)
+    int list_ctas_per_sm;
     unsigned short *nbr; int *nbr_cnt;
     float4 *force, *force_p, *pred, *posq, *smoothed;
     float *pressure, *rho_pred, *rho_err;
@@ -133,6 +134,8 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     e->last_ms_grid = e->last_ms_step = 0.f;
     memset(e->phase_ms, 0, sizeof(e->phase_ms)); memset(e->phase_launches, 0, sizeof(e->phase_launches));
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->list_ctas_per_sm, k_cell_lists_density<0>, BBX_LT, 0));
+    if(e->list_ctas_per_sm < 1) e->list_ctas_per_sm = 1;
     // grid
     DevGrid &g = e->grid;
     for(int k = 0; k < 3; k++){
@@ -585,13 +588,16 @@ static int grid_update(bbx_engine *e){
     return BBX_OK;
 }
 
+// persistent grid of the list build: one warp per occupied cell, grid-stride over the occupied-cell list
+static int list_blocks(bbx_engine *e){
+    long long cells = std::min<long long>(e->n, e->grid.c_own1 - e->grid.c_own0);
+    return (int)std::max<long long>(1, std::min<long long>((cells + BBX_LW - 1) / BBX_LW, (long long)148 * e->list_ctas_per_sm));
+}
 static int phase_density(bbx_engine *e, const StepParams &P, int sph){
-    int cur = e->cur; dim3 nb(e->grid.n[1] * (e->grid.own_z1 - e->grid.own_z0), BBX_DSPLIT);
+    int cur = e->cur;
     if(e->n > 0){
-#define BBX_DENS(S, M) LAUNCH(e, (k_density_lists<S, M>), nb, BBX_BS, P, e->grid, e->st, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq)
-        if(sph){ if(e->masked) BBX_DENS(1, 1); else BBX_DENS(1, 0); }
-        else{ if(e->masked) BBX_DENS(0, 1); else BBX_DENS(0, 0); }
-#undef BBX_DENS
+        if(sph) LAUNCH(e, k_cell_lists_density<1>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq);
+        else LAUNCH(e, k_cell_lists_density<0>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq);
         CU(cudaGetLastError());
     }
     // ghost rho (rides in vel.w); the SPH step also needs the ghosts' p / rho^2 (posq.w)
@@ -814,6 +820,7 @@ int bbx_stats(bbx_engine *e, bbx_step_stats *out){
     out->lost_particles = s.lost[done]; out->clamped = s.clamped; out->nan_count = s.nan_count;
     memcpy(&out->max_force, &s.max_force_bits, 4); memcpy(&out->max_density_error, &s.max_err_bits, 4);
     out->ms_grid = e->last_ms_grid; out->ms_step = e->last_ms_step;
+    out->exact_passes = s.exact_passes; out->max_candidates = s.max_candidates; out->occupied_cells = s.n_occ;
     if(s.error) return set_error(s.error, "device-side error %d (%s)", s.error,
                                  s.error == BBX_ERR_OUT_OF_DOMAIN ? "particle outside the grid bounds" : "a cell run holds more than 4096 particles");
     return BBX_OK;

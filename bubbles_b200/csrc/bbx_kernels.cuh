@@ -17,6 +17,7 @@
 // (LinearIndex, src/core/grid.h:182-193).  A list entry addresses a neighbour as (run, offset).
 #pragma once
 #include "bbx_device.cuh"
+#include "bbx_lists.cuh"
 
 #define BBX_BS 128  // threads per CTA of the particle kernels
 
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(256) k_hash_count(int n_all, int n_lo, int n_o
         st->rebuild_flag[par ^ 1] = 0; st->jump_flag[par ^ 1] = 0; st->lost[par ^ 1] = 0;
         st->overflow = 0; st->clamped = 0; st->nan_count = 0; st->max_force_bits = 0; st->max_err_bits = 0;
         st->qn[0] = 0; st->qn[1] = 0; st->scan_ticket = 0; st->n_occ = 0;
+        st->exact_passes = 0; st->max_candidates = 0;
     }
     if(idx < scan_tiles) scan_status[idx] = 0ull;
     if(idx >= n_all) return;
@@ -329,232 +331,6 @@ __device__ __forceinline__ void bbx_store_entry(unsigned short *__restrict__ nbr
 }
 __device__ __forceinline__ uint4 *bbx_chunk_ptr(unsigned short *__restrict__ nbr, int i, int chunk){
     return reinterpret_cast<uint4 *>(nbr) + ((size_t)(i >> 5) * BBX_NBR_CHUNKS + chunk) * 32 + (i & 31);
-}
-
-// ---------------------------------------------------------- B: neighbour lists + density (sweep 1)
-// Slow path of one particle whose list would exceed 100 entries: re-walk the 27 cells in the reference's
-// order (y outer, x middle, z inner; chain order inside a cell) and keep the first 100 exactly like
-// Bucket::Insert (particle.h:44-50); the density is the sum over exactly those.
-__device__ __noinline__ void bbx_list_overflow(const StepParams &P, const DevGrid &g, DevState *st,
-        const float4 *__restrict__ pos, const int *__restrict__ cell_start, unsigned short *__restrict__ nbr,
-        int i, int c, float4 pi, int *cnt_out, float *sum_out)
-{
-    atomicAdd(&st->overflow, 1);
-    int cnt = 0; float sum = 0.f;
-    int cz = c / g.plane; int rem = c - cz * g.plane; int cy = rem / g.n[0]; int cx = rem - cy * g.n[0];
-    int xlo = max(cx - 1, 0);
-    for(int dy = -1; dy <= 1; dy++) for(int dx_ = -1; dx_ <= 1; dx_++) for(int dz = -1; dz <= 1; dz++){
-        int x = cx + dx_, y = cy + dy, z = cz + dz;
-        if(x < 0 || x >= g.n[0] || y < 0 || y >= g.n[1] || z < 0 || z >= g.n[2]) continue;
-        int nb = x + y * g.n[0] + z * g.plane;
-        int r = (dy + 1) * 3 + (dz + 1);
-        int rb = cell_start[xlo + y * g.n[0] + z * g.plane];
-        int s = cell_start[nb], e = cell_start[nb + 1];
-        for(int j = s; j < e && cnt < BBX_MAX_NEIGHBORS; j++){
-            if(j - rb >= BBX_MAX_RUN_LEN) break;
-            float4 pj = pos[j];
-            float ddx = pi.x - pj.x, ddy = pi.y - pj.y, ddz = pi.z - pj.z;
-            float d2 = fmaf(ddx, ddx, fmaf(ddy, ddy, ddz * ddz));
-            if(bbx_accept(P, pi, pj, d2)){
-                float xx = fmaxf(0.f, 1.f - d2 * P.inv_h2);
-                sum += xx * xx * xx;
-                bbx_store_entry(nbr, i, cnt, ((unsigned)r << BBX_RUN_SHIFT) | (unsigned)(j - rb));
-                cnt++;
-            }
-        }
-    }
-    *cnt_out = cnt; *sum_out = sum;
-}
-
-// One thread owns BBX_DR consecutive particles (same cell, or x-adjacent cells of one row, in the common
-// case) and walks the union of their 27-cell windows ONCE: every candidate position read from the staged
-// tile is tested against all BBX_DR particles (register blocking), branch-free: the accept decisions go into
-// bit masks, rho_i = m * sum W_std (ComputeDensityFor, sph_equations3.cpp:25-58) is accumulated with the
-// clamped kernel for every candidate (W = 0 outside the support).  After each block of 32 candidates the
-// masks are turned into compact list entries (run, offset) -- the reference's per-particle Bucket
-// (grid.h:422-447) up to ordering -- packed 8 to a uint4 and stored coalesced.  The IsWithinStd decision
-// is bit-exact: FP32 away from the threshold, FP64 re-check inside a guard band (bbx_within_std_exact).
-// A candidate outside a particle's own 27 cells (but inside the union window) is at least one cell
-// length away, so the distance test rejects it; MASKED = 1 adds the explicit window test for grids
-// whose cells are smaller than h.
-#define BBX_DR 4
-struct DensityAcc {
-    unsigned long long acc, lo;
-    int cnt;
-    float sum;
-    bool over;
-};
-__device__ __forceinline__ void bbx_append(DensityAcc &a, unsigned short *__restrict__ nbr, int i, unsigned e16){
-    a.acc |= (unsigned long long)e16 << ((a.cnt & 3) * 16);
-    a.cnt++;
-    if((a.cnt & 3) == 0){
-        if(a.cnt & 4){ a.lo = a.acc; }
-        else{
-            *bbx_chunk_ptr(nbr, i, (a.cnt >> 3) - 1) = make_uint4((unsigned)a.lo, (unsigned)(a.lo >> 32), (unsigned)a.acc, (unsigned)(a.acc >> 32));
-        }
-        a.acc = 0ull;
-    }
-}
-
-// Work decomposition: CTA (row, k) owns the particles [row_start + 512 k, +512) of one cell row (same y, z;
-// x fastest), 4 consecutive particles per thread.  For each of the 9 runs the union window of the CTA's
-// particles is one contiguous slot range; it is staged through shared memory in tiles of BBX_DTILE
-// positions (coalesced float4 loads) so that the divergent per-lane window walks hit shared memory
-// (conflict-light broadcast reads) instead of costing one L1 wavefront per distinct cell.
-#define BBX_DTILE 512
-#define BBX_DSPLIT 4
-template<int SPH_EOS, int MASKED>
-__global__ void __launch_bounds__(BBX_BS) k_density_lists(StepParams P, DevGrid g, DevState *st,
-        const float4 *__restrict__ pos, float4 *__restrict__ vel, const int *__restrict__ cell,
-        const int *__restrict__ cell_start, unsigned short *__restrict__ nbr, int *__restrict__ nbr_cnt,
-        float *__restrict__ pressure, float4 *__restrict__ posq)
-{
-    __shared__ float4 tile[BBX_DTILE + 8];
-    const int row = blockIdx.x + g.own_z0 * g.n[1];   // y + z * ny over the owned planes
-    const int rowbase = row * g.n[0];                 // first cell of the row
-    const int rs = cell_start[rowbase], re = cell_start[rowbase + g.n[0]];
-    if(rs == re) return;
-    const int cy = row % g.n[1], cz = row / g.n[1];
-    const float far = 1.0e30f;
-    for(int p0 = rs + blockIdx.y * (BBX_BS * BBX_DR); p0 < re; p0 += BBX_DSPLIT * BBX_BS * BBX_DR){
-        const int p1 = min(p0 + BBX_BS * BBX_DR, re);
-        const int first = p0 + threadIdx.x * BBX_DR;
-        const int m = max(0, min(BBX_DR, p1 - first));
-        // window of the whole CTA chunk (uniform): cells xf-1 .. xl+1
-        const int xf = cell[p0] - rowbase, xl = cell[p1 - 1] - rowbase;
-        const int wlo = max(xf - 1, 0), whi = min(xl + 1, g.n[0] - 1);
-        float xi[BBX_DR], yi[BBX_DR], zi[BBX_DR]; int ci[BBX_DR];
-        DensityAcc A[BBX_DR];
-#pragma unroll
-        for(int r = 0; r < BBX_DR; r++){
-            int i = min(first + min(r, max(m - 1, 0)), p1 - 1);
-            float4 p = pos[i];
-            xi[r] = p.x; yi[r] = p.y; zi[r] = p.z; ci[r] = cell[i];
-            A[r].acc = 0ull; A[r].lo = 0ull; A[r].cnt = 0; A[r].sum = 0.f; A[r].over = false;
-        }
-        // groups of this thread: particles of x-span <= 2 walk one union window (usually a single group)
-        unsigned todo0 = (1u << m) - 1u;
-#pragma unroll 1
-        for(int run = 0; run < 9; run++){
-            const int y = cy + run / 3 - 1, z = cz + run % 3 - 1;
-            if(y < 0 || y >= g.n[1] || z < 0 || z >= g.n[2]) continue;   // uniform over the CTA
-            const int rr = (y + z * g.n[1]) * g.n[0];
-            const int S = cell_start[rr + wlo], E = cell_start[rr + whi + 1];
-#pragma unroll 1
-            for(int ts = S; ts < E; ts += BBX_DTILE){
-                const int te = min(ts + BBX_DTILE, E);
-                __syncthreads();
-                for(int k = threadIdx.x; k < te - ts; k += BBX_BS) tile[k] = pos[ts + k];
-                __syncthreads();
-                unsigned todo = todo0;
-                while(todo){
-                    const int lead = __ffs(todo) - 1;
-                    int cl = ci[0];
-#pragma unroll
-                    for(int r = 1; r < BBX_DR; r++) if(lead == r) cl = ci[r];
-                    const int cx0 = cl - rowbase;
-                    unsigned gm = 0; int span = 0;
-                    int cxr[BBX_DR];
-#pragma unroll
-                    for(int r = 0; r < BBX_DR; r++){
-                        int dx = ci[r] - cl;
-                        cxr[r] = cx0; // non-members keep a valid column (their results are never used)
-                        if(((todo >> r) & 1u) && dx >= 0 && dx <= 2){ gm |= 1u << r; span = max(span, dx); cxr[r] = cx0 + dx; }
-                    }
-                    todo &= ~gm;
-                    float xe[BBX_DR];
-#pragma unroll
-                    for(int r = 0; r < BBX_DR; r++) xe[r] = ((gm >> r) & 1u) ? xi[r] : far;
-                    const int xlo = max(cx0 - 1, 0), xhi = min(cx0 + span + 1, g.n[0] - 1);
-                    const int b = max(cell_start[rr + xlo], ts), e = min(cell_start[rr + xhi + 1], te);
-                    if(b >= e) continue;
-                    // own run base (list entries are relative to it) and, MASKED, own window
-                    int ob[BBX_DR], oe[BBX_DR];
-#pragma unroll
-                    for(int r = 0; r < BBX_DR; r++){
-                        ob[r] = cell_start[rr + max(cxr[r] - 1, 0)];
-                        oe[r] = cell_start[rr + min(cxr[r] + 1, g.n[0] - 1) + 1];
-                        if(((gm >> r) & 1u) && oe[r] - ob[r] > BBX_MAX_RUN_LEN) st->error = BBX_ERR_CAPACITY;
-                    }
-#pragma unroll 1
-                    for(int jb = b; jb < e; jb += 32){
-                        unsigned mlo[BBX_DR], mhi[BBX_DR];
-#pragma unroll
-                        for(int r = 0; r < BBX_DR; r++){ mlo[r] = 0u; mhi[r] = 0u; }
-                        const int left = e - jb;
-                        const float4 *tp = tile + (jb - ts);
-#pragma unroll
-                        for(int q = 0; q < 4; q++){
-                            if(q * 8 < left){
-#pragma unroll
-                                for(int u = 0; u < 8; u++){
-                                    const int t = q * 8 + u;
-                                    float4 pj = tp[t];                  // the tile is padded: reads past `left` stay inside
-                                    if(t >= left) pj.x = -far;          // ... and are pushed out of every support
-#pragma unroll
-                                    for(int r = 0; r < BBX_DR; r++){
-                                        float dx = pj.x - xe[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
-                                        float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                                        if(d2 < P.thr_lo) mlo[r] |= 1u << t;
-                                        if(d2 <= P.thr_hi) mhi[r] |= 1u << t;
-                                        float x = fmaxf(0.f, fmaf(-d2, P.inv_h2, 1.f));
-                                        A[r].sum = fmaf(x * x, x, A[r].sum);
-                                    }
-                                }
-                            }
-                        }
-                        // masks -> list entries
-#pragma unroll
-                        for(int r = 0; r < BBX_DR; r++){
-                            if(MASKED){
-                                // keep only candidates of the particle's own 3 cells of this row
-                                int lo_t = ob[r] - jb, hi_t = oe[r] - jb; // valid t: lo_t <= t < hi_t
-                                unsigned wm = (hi_t <= 0 || lo_t >= 32) ? 0u : ((hi_t >= 32 ? 0xffffffffu : ((1u << hi_t) - 1u)) & (lo_t <= 0 ? 0xffffffffu : ~((1u << lo_t) - 1u)));
-                                mlo[r] &= wm; mhi[r] &= wm;
-                            }
-                            unsigned acc_m = mlo[r];
-                            unsigned unc = mhi[r] & ~mlo[r];
-                            while(unc){ // inside the guard band: decide exactly as the reference does (FP64)
-                                int t = __ffs(unc) - 1; unc &= unc - 1u;
-                                if(bbx_within_std_exact(make_float4(xi[r], yi[r], zi[r], 0.f), tp[t], P.h2_d)) acc_m |= 1u << t;
-                            }
-                            if(A[r].over || A[r].cnt + __popc(acc_m) > BBX_MAX_NEIGHBORS){ A[r].over = true; acc_m = 0u; }
-                            const unsigned ebase = ((unsigned)run << BBX_RUN_SHIFT) + (unsigned)(jb - ob[r]);
-                            while(acc_m){
-                                int t = __ffs(acc_m) - 1; acc_m &= acc_m - 1u;
-                                bbx_append(A[r], nbr, first + r, ebase + (unsigned)t);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        // epilogue: flush the partial chunk, cap-100 slow path, density (rides in vel.w), optional Tait EOS
-#pragma unroll
-        for(int r = 0; r < BBX_DR; r++){
-            if(r < m){
-                const int i = first + r;
-                int cnt = A[r].cnt; float sum = A[r].sum;
-                if(A[r].over){
-                    bbx_list_overflow(P, g, st, pos, cell_start, nbr, i, ci[r], make_float4(xi[r], yi[r], zi[r], 0.f), &cnt, &sum);
-                }else if(cnt & 7){
-                    uint4 v = (cnt & 4) ? make_uint4((unsigned)A[r].lo, (unsigned)(A[r].lo >> 32), (unsigned)A[r].acc, (unsigned)(A[r].acc >> 32))
-                                        : make_uint4((unsigned)A[r].acc, (unsigned)(A[r].acc >> 32), 0u, 0u);
-                    *bbx_chunk_ptr(nbr, i, cnt >> 3) = v;
-                }
-                nbr_cnt[i] = cnt;
-                float rho = P.mass * P.w_std_c * sum;
-                reinterpret_cast<float *>(vel)[4 * (size_t)i + 3] = rho;
-                if(SPH_EOS){
-                    // Tait EOS, ComputePressureValue (sph_equations3.cpp:7-18)
-                    float p = P.eos_scale * (powf(rho / P.rho0, P.eos_exponent) - 1.f);
-                    if(p < 0.f) p *= P.neg_pressure_scale;
-                    pressure[i] = p;
-                    posq[i] = make_float4(xi[r], yi[r], zi[r], p / (rho * rho));
-                }
-            }
-        }
-    }
 }
 
 // ------------------------------------------------------------- list walking used by sweeps 2, 3, 4

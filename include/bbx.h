@@ -149,6 +149,10 @@ typedef struct bbx_step_stats {
     float max_density_error;  /* max |rho* - rho0| of the last iteration                     */
     float ms_grid;            /* device ms of the last sub-step's grid phase (when timing on)*/
     float ms_step;            /* device ms of the last sub-step                              */
+    int exact_passes;         /* list-build passes redone with the FP64 IsWithinStd predicate  */
+    int max_candidates;       /* largest 27-cell neighbourhood of the last list build          */
+    int occupied_cells;       /* occupied (owned) cells of the last grid update                */
+    int reserved;
 } bbx_step_stats;
 
 typedef struct bbx_engine bbx_engine;
