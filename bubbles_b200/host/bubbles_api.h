@@ -1,0 +1,432 @@
+// bubbles_api.h -- C++ host facade over the bbx C ABI (include/bbx.h) with the class / function names of
+// felpzOliveira/Bubbles, so that a scene script ports by switching includes:
+//
+//   reference (src/...)                                   here (namespace bbx)
+//   core/pcisph_solver.h:56-83   PciSphSolver3             PciSphSolver3   {Initialize, Setup, SetColliders, SetViscosityCoefficient,
+//                                                                           Advance, GetSphSolverData, GetSphParticleSet, GetAdvanceTime,
+//                                                                           GetParticleCount, ComputeDelta}
+//   core/sph_solver.h:76-96      SphSolver3                SphSolver3
+//   solvers/sph_solver3.cpp:124  DefaultSphSolverData3     DefaultSphSolverData3
+//   core/particle.h:611-720      ParticleSetBuilder3, SphParticleSet3FromBuilder
+//   core/emitter.h:39-128        VolumeParticleEmitter3, VolumeParticleEmitterSet3
+//   core/shape.h:273-286         MakeBox, MakeSphere, MakeSDFShape
+//   core/collider.h:113-122      ColliderSetBuilder3
+//   core/util.cpp:269            UtilBuildGridForDomain
+//   third/serializer.h:36        SerializerSaveSphDataSet3 (text frames bbtool reads), SERIALIZER_* flags
+//   core/pcisph_solver.h:95      PciSphRunSimulation3 (the run loop, without the viewer)
+//
+// Differences by design: objects are ordinary C++ values / unique_ptrs (the reference bump-allocates from a
+// managed-memory arena and never frees, src/cuda/memory.h); errors throw bbx::Error instead of
+// getchar() + exit(0) (src/cuda/cutil.cpp:15-26); all device work happens inside libbbx.so -- this header is
+// host-only and needs no nvcc.  Particle data lives on the device between steps; Advance() refreshes the
+// host copies of positions / velocities / densities (what the reference's callbacks read through managed
+// memory).
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/bbx.h"
+
+namespace bbx {
+
+typedef double Float; // src/core/geometry.h:68-69
+const Float WaterDensity = 1000.0;
+const Float Pi = 3.14159265358979323846;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error("bbx error " + std::to_string(c) + ": " + m), code(c) {}
+};
+inline void Check(int rc){ if(rc != BBX_OK) throw Error(rc, bbx_last_error()); }
+
+struct vec3f {
+    Float x, y, z;
+    vec3f() : x(0), y(0), z(0) {}
+    explicit vec3f(Float a) : x(a), y(a), z(a) {}
+    vec3f(Float a, Float b, Float c) : x(a), y(b), z(c) {}
+    Float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+    vec3f operator+(const vec3f &o) const { return vec3f(x + o.x, y + o.y, z + o.z); }
+    vec3f operator-(const vec3f &o) const { return vec3f(x - o.x, y - o.y, z - o.z); }
+    vec3f operator*(Float s) const { return vec3f(x * s, y * s, z * s); }
+    Float Length() const { return std::sqrt(x * x + y * y + z * z); }
+};
+inline vec3f operator*(Float s, const vec3f &v){ return v * s; }
+
+struct Bounds3f {
+    vec3f pMin, pMax;
+    Bounds3f() {}
+    Bounds3f(const vec3f &a, const vec3f &b)
+        : pMin(std::fmin(a.x, b.x), std::fmin(a.y, b.y), std::fmin(a.z, b.z)), pMax(std::fmax(a.x, b.x), std::fmax(a.y, b.y), std::fmax(a.z, b.z)) {}
+    Float ExtentOn(int i) const { return std::fabs(pMax[i] - pMin[i]); }
+};
+
+// 4x4 transform with its inverse, row-major (src/core/transform.h:399-468)
+struct Transform {
+    Float m[4][4], mInv[4][4];
+    Transform(){ for(int i = 0; i < 4; i++) for(int j = 0; j < 4; j++) m[i][j] = mInv[i][j] = (i == j) ? 1.0 : 0.0; }
+    vec3f Point(const vec3f &p) const {
+        Float xp = m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z + m[0][3];
+        Float yp = m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z + m[1][3];
+        Float zp = m[2][0] * p.x + m[2][1] * p.y + m[2][2] * p.z + m[2][3];
+        Float wp = m[3][0] * p.x + m[3][1] * p.y + m[3][2] * p.z + m[3][3];
+        if(wp == 1) return vec3f(xp, yp, zp);
+        return vec3f(xp, yp, zp) * (1.0 / wp);
+    }
+    vec3f InversePoint(const vec3f &p) const { Transform t; std::memcpy(t.m, mInv, sizeof(m)); std::memcpy(t.mInv, m, sizeof(m)); return t.Point(p); }
+};
+inline Transform Translate(Float x, Float y, Float z){ // analytic inverse, src/core/transform.cpp:286-292
+    Transform t; t.m[0][3] = x; t.m[1][3] = y; t.m[2][3] = z; t.mInv[0][3] = -x; t.mInv[1][3] = -y; t.mInv[2][3] = -z; return t;
+}
+inline Transform Translate(const vec3f &v){ return Translate(v.x, v.y, v.z); }
+inline Transform Scale(Float x, Float y, Float z){
+    Transform t; t.m[0][0] = x; t.m[1][1] = y; t.m[2][2] = z; t.mInv[0][0] = 1 / x; t.mInv[1][1] = 1 / y; t.mInv[2][2] = 1 / z; return t;
+}
+
+// ------------------------------------------------------------------------------------------ shapes
+enum ShapeType { ShapeSphere = BBX_COLLIDER_SPHERE, ShapeBox = BBX_COLLIDER_BOX, ShapeSDF = BBX_COLLIDER_SDF };
+
+struct Shape {
+    ShapeType type = ShapeBox;
+    Transform ObjectToWorld;
+    bool reverseOrientation = false;
+    Float radius = 0, sizex = 0, sizey = 0, sizez = 0;
+    vec3f linearVelocity, angularVelocity;
+    // baked SDF (FieldGrid3f, vertex centred): node counts, spacing, position of node (0, 0, 0), x-fastest values
+    int sdfResolution[3] = {0, 0, 0};
+    Float sdfSpacing = 0;
+    vec3f sdfOrigin;
+    std::vector<Float> sdfField;
+    Bounds3f sdfBounds;
+
+    Bounds3f GetBounds() const {
+        if(type == ShapeSDF) return sdfBounds;
+        vec3f h = type == ShapeSphere ? vec3f(radius) : vec3f(sizex / 2, sizey / 2, sizez / 2);
+        // transformed corners (Transform::operator()(Bounds3f))
+        Bounds3f b(ObjectToWorld.Point(vec3f(-h.x, -h.y, -h.z)), ObjectToWorld.Point(vec3f(-h.x, -h.y, -h.z)));
+        for(int k = 1; k < 8; k++){
+            vec3f c = ObjectToWorld.Point(vec3f((k & 1) ? h.x : -h.x, (k & 2) ? h.y : -h.y, (k & 4) ? h.z : -h.z));
+            b = Bounds3f(vec3f(std::fmin(b.pMin.x, c.x), std::fmin(b.pMin.y, c.y), std::fmin(b.pMin.z, c.z)),
+                         vec3f(std::fmax(b.pMax.x, c.x), std::fmax(b.pMax.y, c.y), std::fmax(b.pMax.z, c.z)));
+        }
+        return b;
+    }
+    // Shape::SignedDistance for the analytic shapes (emitter acceptance test, src/core/shape.cpp:284-288)
+    Float SignedDistance(const vec3f &p) const {
+        vec3f q = ObjectToWorld.InversePoint(p);
+        Float d;
+        if(type == ShapeSphere) d = q.Length() - radius;
+        else if(type == ShapeBox){
+            vec3f a(std::fabs(q.x) - sizex / 2, std::fabs(q.y) - sizey / 2, std::fabs(q.z) - sizez / 2);
+            vec3f o(std::fmax(a.x, 0.0), std::fmax(a.y, 0.0), std::fmax(a.z, 0.0));
+            d = o.Length() + std::fmin(std::fmax(a.x, std::fmax(a.y, a.z)), 0.0);
+        }else d = SampleSDF(p);
+        return reverseOrientation ? -d : d;
+    }
+    // FieldGrid::Sample (src/core/grid.h:1093-1131): trilinear, clamped indices
+    Float SampleSDF(const vec3f &p) const {
+        int ii[3], jj[3]; Float w[3];
+        for(int a = 0; a < 3; a++){
+            Float x = (p[a] - sdfOrigin[a]) / sdfSpacing; int high = sdfResolution[a] - 1;
+            Float s = std::floor(x); int id = (int)s; Float f;
+            if(high == 0 || id < 0){ id = 0; f = 0; }else if(id > high - 1){ id = high - 1; f = 1; }else f = x - s;
+            ii[a] = id; w[a] = f; jj[a] = id + 1 < sdfResolution[a] ? id + 1 : sdfResolution[a] - 1;
+        }
+        const int rx = sdfResolution[0], rxy = sdfResolution[0] * sdfResolution[1];
+        auto F = [&](int x, int y, int z){ return sdfField[(size_t)x + (size_t)y * rx + (size_t)z * rxy]; };
+        auto L = [](Float a, Float b, Float t){ return (1 - t) * a + t * b; };
+        Float b0 = L(L(F(ii[0], ii[1], ii[2]), F(jj[0], ii[1], ii[2]), w[0]), L(F(ii[0], jj[1], ii[2]), F(jj[0], jj[1], ii[2]), w[0]), w[1]);
+        Float b1 = L(L(F(ii[0], ii[1], jj[2]), F(jj[0], ii[1], jj[2]), w[0]), L(F(ii[0], jj[1], jj[2]), F(jj[0], jj[1], jj[2]), w[0]), w[1]);
+        return L(b0, b1, w[2]);
+    }
+};
+typedef std::shared_ptr<Shape> ShapePtr;
+
+inline ShapePtr MakeBox(const Transform &toWorld, const vec3f &size, bool reverseOrientation = false){
+    ShapePtr s = std::make_shared<Shape>(); s->type = ShapeBox; s->ObjectToWorld = toWorld;
+    s->sizex = size.x; s->sizey = size.y; s->sizez = size.z; s->reverseOrientation = reverseOrientation; return s;
+}
+inline ShapePtr MakeSphere(const Transform &toWorld, Float radius, bool reverseOrientation = false){
+    ShapePtr s = std::make_shared<Shape>(); s->type = ShapeSphere; s->ObjectToWorld = toWorld; s->radius = radius;
+    s->reverseOrientation = reverseOrientation; return s;
+}
+// MakeSDFShape(bounds, sdf) (src/core/shape.h:281-286): bakes an analytic signed-distance function on the
+// vertex grid of Shape::InitSDFShape (shape.h:201-230: bounds grown by `margin`, node spacing ~dx)
+inline ShapePtr MakeSDFShape(const Bounds3f &bounds, const std::function<Float(vec3f)> &sdf, Float dx = 0.01, Float margin = 0.1){
+    ShapePtr s = std::make_shared<Shape>(); s->type = ShapeSDF;
+    vec3f lo = bounds.pMin, hi = bounds.pMax;
+    vec3f sc(std::fabs(hi.x - lo.x), std::fabs(hi.y - lo.y), std::fabs(hi.z - lo.z));
+    lo = lo - sc * margin; hi = hi + sc * margin;
+    Float width = std::fabs(hi.x - lo.x), height = std::fabs(hi.y - lo.y), depth = std::fabs(hi.z - lo.z);
+    int res = (int)std::ceil(width / dx); dx = width / (Float)res;
+    int ry = (int)std::ceil(res * height / width), rz = (int)std::ceil(res * depth / width);
+    s->sdfResolution[0] = res + 1; s->sdfResolution[1] = ry + 1; s->sdfResolution[2] = rz + 1;
+    s->sdfSpacing = dx; s->sdfOrigin = lo; s->sdfBounds = Bounds3f(lo, hi);
+    s->sdfField.resize((size_t)(res + 1) * (ry + 1) * (rz + 1));
+    size_t k = 0;
+    for(int z = 0; z <= rz; z++) for(int y = 0; y <= ry; y++) for(int x = 0; x <= res; x++)
+        s->sdfField[k++] = sdf(vec3f(lo.x + dx * x, lo.y + dx * y, lo.z + dx * z));
+    return s;
+}
+
+// --------------------------------------------------------------------------------------- colliders
+struct ColliderSet3 {
+    std::vector<ShapePtr> shapes;
+    std::vector<Float> friction;
+    std::vector<bool> active;
+    int nColiders() const { return (int)shapes.size(); }
+    void SetActive(int which, bool on){ active.at(which) = on; }
+    std::vector<bbx_collider> ToABI() const {
+        std::vector<bbx_collider> out(shapes.size());
+        for(size_t i = 0; i < shapes.size(); i++){
+            const Shape &s = *shapes[i]; bbx_collider &b = out[i];
+            std::memset(&b, 0, sizeof(b));
+            b.type = (int)s.type; b.reverse_orientation = s.reverseOrientation ? 1 : 0; b.active = active[i] ? 1 : 0; b.friction = friction[i];
+            for(int r = 0; r < 4; r++) for(int c = 0; c < 4; c++){ b.object_to_world[4 * r + c] = s.ObjectToWorld.m[r][c]; b.world_to_object[4 * r + c] = s.ObjectToWorld.mInv[r][c]; }
+            b.size[0] = s.sizex; b.size[1] = s.sizey; b.size[2] = s.sizez; b.radius = s.radius;
+            for(int k = 0; k < 3; k++){ b.linear_velocity[k] = s.linearVelocity[k]; b.angular_velocity[k] = s.angularVelocity[k]; }
+            if(s.type == ShapeSDF){
+                for(int k = 0; k < 3; k++){ b.sdf_resolution[k] = s.sdfResolution[k]; b.sdf_spacing[k] = s.sdfSpacing; b.sdf_origin[k] = s.sdfOrigin[k]; }
+                b.sdf_field = s.sdfField.data();
+            }
+        }
+        return out;
+    }
+};
+struct ColliderSetBuilder3 {
+    std::shared_ptr<ColliderSet3> set = std::make_shared<ColliderSet3>();
+    void AddCollider3(const ShapePtr &shape, Float frictionCoefficient = 0.0){ // MakeCollider3 defaults, src/core/collider.cpp:340-348
+        set->shapes.push_back(shape); set->friction.push_back(frictionCoefficient); set->active.push_back(true);
+    }
+    std::shared_ptr<ColliderSet3> GetColliderSet(){ return set; }
+};
+
+// ---------------------------------------------------------------------------------------- particles
+struct ParticleSetBuilder3 {
+    std::vector<vec3f> positions, velocities;
+    int AddParticle(const vec3f &pos, const vec3f &vel = vec3f(0)){ positions.push_back(pos); velocities.push_back(vel); return 1; }
+    void SetVelocityForAll(const vec3f &vel){ for(auto &v : velocities) v = vel; }
+    int GetParticleCount() const { return (int)positions.size(); }
+    void Commit(){}
+};
+
+// ParticleSet3 + SphParticleSet3 (src/core/particle.h:154-213, 480-608): host mirror of the device state
+struct ParticleSet3 {
+    std::vector<vec3f> positions, velocities;
+    std::vector<Float> densities;
+    Float mass = 0;
+    int GetParticleCount() const { return (int)positions.size(); }
+    vec3f GetParticlePosition(int i) const { return positions[i]; }
+    vec3f GetParticleVelocity(int i) const { return velocities[i]; }
+    Float GetParticleDensity(int i) const { return densities[i]; }
+    Float GetMass() const { return mass; }
+};
+struct SphParticleSet3 {
+    ParticleSet3 set;
+    Float targetSpacing = 0.1, kernelRadiusOverSpacing = 2.0, targetDensity = WaterDensity;
+    ParticleSet3 *GetParticleSet(){ return &set; }
+    void SetRelativeKernelRadius(Float r){ kernelRadiusOverSpacing = r; }
+    void SetTargetSpacing(Float s){ targetSpacing = s; }
+    Float GetTargetSpacing() const { return targetSpacing; }
+    Float GetKernelRadius() const { return kernelRadiusOverSpacing * targetSpacing; }
+};
+inline std::shared_ptr<SphParticleSet3> SphParticleSet3FromBuilder(ParticleSetBuilder3 *b){
+    auto s = std::make_shared<SphParticleSet3>();
+    s->set.positions = b->positions; s->set.velocities = b->velocities; s->set.densities.assign(b->positions.size(), 0.0);
+    return s;
+}
+
+// ----------------------------------------------------------------------------------------- emitters
+// BccLatticePointGenerator::ForEach (src/generator/bcclattice.cpp:5-36)
+template<typename F> inline void BccLatticeForEach(const Bounds3f &b, Float spacing, F &&fn){
+    const Float half = spacing / 2;
+    const Float ex = b.ExtentOn(0), ey = b.ExtentOn(1), ez = b.ExtentOn(2);
+    bool shifted = false;
+    for(int k = 0; k * half <= ez; k++){
+        const Float off = shifted ? half : 0.0, z = k * half + b.pMin.z;
+        for(int j = 0; j * spacing + off <= ey; j++){
+            const Float y = j * spacing + off + b.pMin.y;
+            for(int i = 0; i * spacing + off <= ex; i++) if(!fn(vec3f(i * spacing + off + b.pMin.x, y, z))) return;
+        }
+        shifted = !shifted;
+    }
+}
+// VolumeParticleEmitter3 (src/core/emitter.h:39-69, emitter.cpp:242-330): BCC lattice over `bound`, each point
+// jittered by 0.5 * jitter * spacing * SampleSphere(rand, rand) (libc rand(), like the reference), kept when
+// shape->SignedDistance(target) <= 0.
+struct VolumeParticleEmitter3 {
+    ShapePtr shape; Bounds3f bound; Float spacing; vec3f initVel; Float jitter = 0; int maxParticles = 0x7fffffff; int emittedParticles = 0;
+    std::function<bool(const vec3f &)> validator;
+    VolumeParticleEmitter3(const ShapePtr &s, const Bounds3f &b, Float sp, const vec3f &v = vec3f(0)) : shape(s), bound(b), spacing(sp), initVel(v) {}
+    void SetJitter(Float j){ jitter = j < 0 ? 0 : (j > 1 ? 1 : j); }
+    void SetValidator(std::function<bool(const vec3f &)> f){ validator = std::move(f); }
+    void Emit(ParticleSetBuilder3 *builder){
+        const Float maxJitter = 0.5 * jitter * spacing;
+        BccLatticeForEach(bound, spacing, [&](const vec3f &point) -> bool {
+            if(validator && !validator(point)) return true;
+            const float u0 = rand() / (RAND_MAX + 1.f), u1 = rand() / (RAND_MAX + 1.f);
+            const Float usqrt = 2 * std::sqrt((Float)u1 * (1 - (Float)u1)), utheta = 2 * Pi * (Float)u0;
+            const vec3f target = point + maxJitter * vec3f(std::cos(utheta) * usqrt, std::sin(utheta) * usqrt, 1 - 2 * (Float)u1);
+            if(shape->SignedDistance(target) <= 0){
+                if(emittedParticles >= maxParticles) return false;
+                builder->AddParticle(target, initVel); emittedParticles++;
+            }
+            return true;
+        });
+    }
+};
+struct VolumeParticleEmitterSet3 {
+    std::vector<VolumeParticleEmitter3 *> emitters;
+    void AddEmitter(VolumeParticleEmitter3 *e){ emitters.push_back(e); }
+    void SetJitter(Float j){ for(auto *e : emitters) e->SetJitter(j); }
+    void Emit(ParticleSetBuilder3 *b){ for(auto *e : emitters) e->Emit(b); }
+};
+
+// --------------------------------------------------------------------------------------------- grid
+struct Grid3 { bbx_grid_desc desc; Bounds3f GetBounds() const { return Bounds3f(vec3f(desc.min[0], desc.min[1], desc.min[2]), vec3f(desc.max[0], desc.max[1], desc.max[2])); }
+               int GetCellCount() const { return desc.total; } };
+inline std::shared_ptr<Grid3> UtilBuildGridForDomain(const Bounds3f &domain, Float spacing, Float spacingScale){
+    auto g = std::make_shared<Grid3>();
+    double lo[3] = {domain.pMin.x, domain.pMin.y, domain.pMin.z}, hi[3] = {domain.pMax.x, domain.pMax.y, domain.pMax.z};
+    Check(bbx_grid_for_domain(lo, hi, spacing, spacingScale, &g->desc));
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------ solvers
+// SphSolverData3 constants (src/core/sph_solver.h:31-50); the arrays live in the engine
+struct SphSolverData3 {
+    bbx_config cfg;
+    std::shared_ptr<SphParticleSet3> sphpSet;
+    std::shared_ptr<Grid3> domain;
+    std::shared_ptr<ColliderSet3> collider;
+};
+inline std::shared_ptr<SphSolverData3> DefaultSphSolverData3(bool with_gravity = true){
+    auto d = std::make_shared<SphSolverData3>();
+    Check(bbx_config_default(&d->cfg, with_gravity ? 1 : 0));
+    return d;
+}
+
+class SolverBase3 {
+  protected:
+    std::shared_ptr<SphSolverData3> data;
+    bbx_engine *engine = nullptr;
+    int solverKind;
+    Float stepInterval = 0;
+    explicit SolverBase3(int kind) : solverKind(kind) {}
+    void Pull(){
+        ParticleSet3 &ps = data->sphpSet->set;
+        if(ps.positions.empty()) return;
+        static_assert(sizeof(vec3f) == 3 * sizeof(double), "vec3f must be 3 packed doubles");
+        Check(bbx_download(engine, BBX_POSITION, ps.positions.data(), BBX_F64));
+        Check(bbx_download(engine, BBX_VELOCITY, ps.velocities.data(), BBX_F64));
+        Check(bbx_download(engine, BBX_DENSITY, ps.densities.data(), BBX_F64));
+    }
+  public:
+    SolverBase3(const SolverBase3 &) = delete;
+    SolverBase3 &operator=(const SolverBase3 &) = delete;
+    ~SolverBase3(){ if(engine) bbx_destroy(engine); }
+    void Initialize(const std::shared_ptr<SphSolverData3> &d){ data = d; }
+    void Setup(Float targetDensity, Float targetSpacing, Float relativeRadius, const std::shared_ptr<Grid3> &domain,
+               const std::shared_ptr<SphParticleSet3> &pSet, int maxParticles = 0){
+        if(!data) throw Error(BBX_ERR_INVALID, "Initialize() before Setup()");
+        data->sphpSet = pSet; data->domain = domain;
+        pSet->targetDensity = targetDensity; pSet->targetSpacing = targetSpacing; pSet->kernelRadiusOverSpacing = relativeRadius;
+        bbx_config &c = data->cfg;
+        c.spacing = targetSpacing; c.kernel_scale = relativeRadius; c.target_density = targetDensity; c.grid = domain->desc;
+        const int n = pSet->set.GetParticleCount();
+        c.max_particles = maxParticles > n ? maxParticles : (n > 0 ? n : 1);
+        if(engine){ bbx_destroy(engine); engine = nullptr; }
+        Check(bbx_create(&c, &engine));
+        Check(bbx_get_mass(engine, &pSet->set.mass));
+        if(n > 0) Check(bbx_set_particles(engine, n, pSet->set.positions.data(), pSet->set.velocities.data(), BBX_F64));
+        if(data->collider) SetColliders(data->collider);
+    }
+    void SetColliders(const std::shared_ptr<ColliderSet3> &colliders){
+        data->collider = colliders;
+        if(!engine) return; // applied by Setup
+        std::vector<bbx_collider> abi = colliders->ToABI();
+        Check(bbx_set_colliders(engine, (int)abi.size(), abi.data()));
+    }
+    std::shared_ptr<ColliderSet3> GetColliders(){ return data->collider; }
+    void SetViscosityCoefficient(Float v){ data->cfg.viscosity = v > 0 ? v : 0; }
+    SphSolverData3 *GetSphSolverData(){ return data.get(); }
+    SphParticleSet3 *GetSphParticleSet(){ return data->sphpSet.get(); }
+    Float GetKernelRadius(){ return data->sphpSet->GetKernelRadius(); }
+    Float GetAdvanceTime() const { return stepInterval; }
+    int GetParticleCount(){ int n = 0; Check(bbx_particle_count(engine, &n)); return n; }
+    bbx_engine *Engine(){ return engine; }
+    // Advance(timeIntervalInSeconds): CFL sub-stepping on the device, then the host copies are refreshed
+    int Advance(Float timeIntervalInSeconds){
+        int substeps = 0; float ms = 0;
+        Check(bbx_advance(engine, timeIntervalInSeconds, solverKind, &substeps, &ms));
+        stepInterval = ms;
+        Pull();
+        return substeps;
+    }
+    // fixed-dt sub-steps (AdvanceTimeStep), without the CFL loop
+    void AdvanceTimeStep(Float dt, int count = 1){ Check(bbx_step_many(engine, dt, solverKind, count)); Pull(); }
+    bbx_step_stats Stats(){ bbx_step_stats s; Check(bbx_stats(engine, &s)); return s; }
+};
+class PciSphSolver3 : public SolverBase3 {
+  public:
+    PciSphSolver3() : SolverBase3(BBX_SOLVER_PCISPH) {}
+    Float ComputeDelta(Float timeIntervalInSeconds){ double d = 0; Check(bbx_get_delta(engine, timeIntervalInSeconds, &d)); return d; }
+    // 1: the reference's effective behaviour (one predict-correct iteration); 0: iterate to tolerance
+    void SetReferenceCompat(bool on){ data->cfg.pcisph_reference_compat = on ? 1 : 0; }
+};
+class SphSolver3 : public SolverBase3 {
+  public:
+    SphSolver3() : SolverBase3(BBX_SOLVER_SPH) {}
+    void SetPseudoViscosityCoefficient(Float v){ data->cfg.pseudo_viscosity = v; }
+};
+
+// --------------------------------------------------------------------------------------- serializer
+enum { SERIALIZER_POSITION = 0x01, SERIALIZER_VELOCITY = 0x02, SERIALIZER_DENSITY = 0x04, SERIALIZER_BOUNDARY = 0x08,
+       SERIALIZER_NORMAL = 0x10, SERIALIZER_MASS = 0x20 };
+inline std::string SerializerStringFromFlags(int flags){
+    std::string s;
+    if(flags & SERIALIZER_POSITION) s += "p";
+    if(flags & SERIALIZER_VELOCITY) s += "v";
+    if(flags & SERIALIZER_DENSITY) s += "d";
+    if(flags & SERIALIZER_MASS) s += "m";
+    return s;
+}
+// SaveSphParticleSet (src/third/serializer.cpp:884-921): the "FluidBegin ... DataEnd / FluidEnd" text frame, one
+// line per particle in id order, fields p v d m, "%g"; appended to `filename` like the reference ("a+").
+inline void SerializerSaveSphDataSet3(SphSolverData3 *data, const char *filename, int flags){
+    ParticleSet3 *ps = data->sphpSet->GetParticleSet();
+    FILE *fp = std::fopen(filename, "a+");
+    if(!fp){ std::printf("Error: Failed to open %s\n", filename); return; }
+    flags &= SERIALIZER_POSITION | SERIALIZER_VELOCITY | SERIALIZER_DENSITY | SERIALIZER_MASS;
+    std::fprintf(fp, "FluidBegin\n\t\"Type\" particles\n\t\"Count\" %d\n\t\"Format\" %s\n\t\"Spacing\" %g\n\tDataBegin\n",
+                 ps->GetParticleCount(), SerializerStringFromFlags(flags).c_str(), data->sphpSet->GetTargetSpacing());
+    for(int i = 0; i < ps->GetParticleCount(); i++){
+        int sp = 0;
+        std::fprintf(fp, "\t\t");
+        if(flags & SERIALIZER_POSITION){ vec3f p = ps->GetParticlePosition(i); std::fprintf(fp, "%g %g %g", p.x, p.y, p.z); sp = 1; }
+        if(flags & SERIALIZER_VELOCITY){ vec3f v = ps->GetParticleVelocity(i); std::fprintf(fp, sp ? " %g %g %g" : "%g %g %g", v.x, v.y, v.z); sp = 1; }
+        if(flags & SERIALIZER_DENSITY){ std::fprintf(fp, sp ? " %g" : "%g", ps->GetParticleDensity(i)); sp = 1; }
+        if(flags & SERIALIZER_MASS){ std::fprintf(fp, sp ? " %g" : "%g", ps->GetMass()); sp = 1; }
+        std::fprintf(fp, "\n");
+    }
+    std::fprintf(fp, "\tDataEnd\nFluidEnd\n");
+    std::fclose(fp);
+}
+
+// PciSphRunSimulation3 / UtilRunSimulation3 (src/core/util.h:539-599) without the viewer: callback(step) before the
+// first frame with step = 0, then after every Advance; it returns 0 to stop.
+template<typename Solver>
+inline void RunSimulation3(Solver *solver, Float targetInterval, const std::function<int(int)> &callback){
+    int step = 0;
+    if(!callback(step)) return;
+    for(;;){ solver->Advance(targetInterval); step++; if(!callback(step)) break; }
+}
+inline void PciSphRunSimulation3(PciSphSolver3 *solver, Float targetInterval, const std::function<int(int)> &callback){ RunSimulation3(solver, targetInterval, callback); }
+
+} // namespace bbx

@@ -1,0 +1,119 @@
+// dam_break_demo -- the reference's test_pcisph3_dam_break scene (src/tests/test_pcisph_extra.cpp:1102-1169)
+// written against the bbx C++ facade (bubbles_api.h): same constants, same call sequence
+// (MakeBox / VolumeParticleEmitter3 / UtilBuildGridForDomain / ColliderSetBuilder3 / PciSphSolver3 /
+// SerializerSaveSphDataSet3 / PciSphRunSimulation3), host code only -- every kernel runs inside libbbx.so.
+//
+//   dam_break_demo [--scaling S] [--frames N] [--steps N --dt X] [--jitter J] [--out DIR] [--dump FILE] [--sph]
+//     --scaling  domainScaling of the reference scene (2.5 there: ~0.9 M particles; default 0.6: ~12 k)
+//     --frames   frames of 1/240 s through Advance() (CFL sub-stepping), default 2
+//     --steps    instead of frames: N fixed-dt sub-steps (AdvanceTimeStep)
+//     --out      directory for the text frames bbtool reads (out_<frame>.txt), off by default
+//     --dump     raw little-endian doubles: n, then n x 3 positions, n x 3 velocities (for the parity test)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "bubbles_api.h"
+
+using namespace bbx;
+
+int main(int argc, char **argv){
+    Float domainScaling = 0.6f, jitter = 0.001, dt = 0;
+    int frames = 2, steps = 0; bool sph = false;
+    std::string out, dump;
+    for(int i = 1; i < argc; i++){
+        std::string a = argv[i];
+        auto next = [&](){ if(i + 1 >= argc){ std::fprintf(stderr, "missing value for %s\n", a.c_str()); std::exit(2); } return std::string(argv[++i]); };
+        if(a == "--scaling") domainScaling = std::atof(next().c_str());
+        else if(a == "--frames") frames = std::atoi(next().c_str());
+        else if(a == "--steps") steps = std::atoi(next().c_str());
+        else if(a == "--dt") dt = std::atof(next().c_str());
+        else if(a == "--jitter") jitter = std::atof(next().c_str());
+        else if(a == "--out") out = next();
+        else if(a == "--dump") dump = next();
+        else if(a == "--sph") sph = true;
+        else{ std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+    try{
+        std::printf("===== PCISPH Solver 3D -- Dam Break (bbx)\n");
+        Float spacing = 0.02f;        // float literals as in the reference scene
+        Float spacingScale = 1.8f;
+        Float boxFluidLen = 0.5 * domainScaling, boxFluidYLen = 0.9 * domainScaling;
+        Float boxLen = 1.3 * domainScaling, boxYLen = 1.2 * domainScaling;
+        vec3f containerSize(boxLen, boxYLen, boxLen);
+        Float xof = (containerSize.x - boxFluidLen) / 2.0; xof -= spacing;
+        Float zof = (containerSize.z - boxFluidLen) / 2.0; zof -= spacing;
+        Float yof = (containerSize.y - boxFluidYLen) / 2.0; yof -= spacing;
+        vec3f boxSize(boxFluidLen, boxFluidYLen, boxFluidLen);
+
+        ShapePtr container = MakeBox(Transform(), containerSize, true);
+        ShapePtr boxp = MakeBox(Translate(xof, -yof, zof), boxSize);
+
+        ParticleSetBuilder3 pBuilder;
+        VolumeParticleEmitterSet3 emitterSet;
+        VolumeParticleEmitter3 emitterp(boxp, boxp->GetBounds(), spacing, vec3f(0, -6, 0));
+        emitterSet.AddEmitter(&emitterp);
+        emitterSet.SetJitter(jitter);
+        emitterSet.Emit(&pBuilder);
+
+        auto domainGrid = UtilBuildGridForDomain(container->GetBounds(), spacing, spacingScale);
+        ColliderSetBuilder3 cBuilder;
+        cBuilder.AddCollider3(container);
+        auto colliders = cBuilder.GetColliderSet();
+
+        auto sphSet = SphParticleSet3FromBuilder(&pBuilder);
+        sphSet->SetRelativeKernelRadius(spacingScale);
+        std::printf("particles %d, cells %d (%d x %d x %d)\n", pBuilder.GetParticleCount(), domainGrid->desc.total,
+                    domainGrid->desc.n[0], domainGrid->desc.n[1], domainGrid->desc.n[2]);
+
+        PciSphSolver3 pci; SphSolver3 sphSolver;
+        auto run = [&](auto &solver){
+            solver.Initialize(DefaultSphSolverData3());
+            solver.Setup(WaterDensity, spacing, spacingScale, domainGrid, sphSet);
+            solver.SetColliders(colliders);
+            auto save = [&](int frame){
+                if(out.empty()) return;
+                std::string path = out + "/out_" + std::to_string(frame) + ".txt";
+                std::remove(path.c_str());
+                SerializerSaveSphDataSet3(solver.GetSphSolverData(), path.c_str(), SERIALIZER_POSITION);
+            };
+            if(steps > 0){
+                if(!(dt > 0)) dt = sph ? 1.44e-4 : 7.2e-4;
+                save(0);
+                solver.AdvanceTimeStep(dt, steps);
+                save(1);
+                std::printf("%d fixed sub-steps of %g s\n", steps, dt);
+            }else{
+                Float targetInterval = 1.0 / 240.0;
+                RunSimulation3(&solver, targetInterval, [&](int step) -> int {
+                    if(step == 0){ save(0); return 1; }
+                    std::printf("Step (%d) : %g ms - Particles %d\n", step - 1, solver.GetAdvanceTime(), solver.GetParticleCount());
+                    save(step);
+                    return step >= frames ? 0 : 1;
+                });
+            }
+            bbx_step_stats st = solver.Stats();
+            std::printf("substeps %d, neighbour overflow %d, clamped %d, non-finite %d\n", st.substeps, st.neighbor_overflow, st.clamped, st.nan_count);
+        };
+        if(sph) run(sphSolver); else run(pci);
+
+        ParticleSet3 *ps = sphSet->GetParticleSet();
+        vec3f p0 = ps->GetParticlePosition(0);
+        std::printf("p[0] = %.17g %.17g %.17g  rho[0] = %.9g\n", p0.x, p0.y, p0.z, ps->GetParticleDensity(0));
+        if(!dump.empty()){
+            FILE *fp = std::fopen(dump.c_str(), "wb");
+            if(!fp){ std::fprintf(stderr, "cannot open %s\n", dump.c_str()); return 1; }
+            double n = ps->GetParticleCount();
+            std::fwrite(&n, sizeof(double), 1, fp);
+            std::fwrite(ps->positions.data(), sizeof(vec3f), ps->positions.size(), fp);
+            std::fwrite(ps->velocities.data(), sizeof(vec3f), ps->velocities.size(), fp);
+            std::fclose(fp);
+        }
+        std::printf("===== OK\n");
+    }catch(const std::exception &ex){
+        std::fprintf(stderr, "%s\n", ex.what());
+        return 1;
+    }
+    return 0;
+}
