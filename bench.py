@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="bbx", choices=["bbx", "reference"])
     ap.add_argument("--particles", type=float, default=1.0e6, help="particles per GPU (weak scaling)")
+    ap.add_argument("--workload", default="dam", choices=["dam", "sdf"],
+                    help="dam: PCISPH dam break in a box (configs 2, 4, 5); sdf: same plus a baked-SDF torus collider (config 3)")
     ap.add_argument("--ref-particles", type=float, default=2.5e5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
@@ -227,19 +229,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # weak scaling: ONE dam-break scene of (particles per GPU) x N particles, cut into N z-slabs of whole cell
-    # planes balanced by particle count; ghost planes / migration / per-phase halos travel over NCCL
-    sc = make_scene(args.particles * world)
-    n_global = len(sc["pos"])
-    pos32 = sc["pos"].astype(np.float32)
-    vel32 = sc["vel"].astype(np.float32)
+    # planes balanced by particle count; ghost planes / migration / per-phase halos travel over NCCL.  Every rank
+    # generates only its own share of the (deterministic) BCC block.
+    sc = scenes.dam_break_scene_slab(args.particles * world, rank, world,
+                                     obstacle=scenes.torus_obstacle if args.workload == "sdf" else None)
+    n_global = sc["n_global"]
+    pos32, vel32 = sc["pos"], sc["vel"]
     if world > 1:
-        grid = bb.UtilBuildGridForDomain(sc["domain_min"], sc["domain_max"], sc["spacing"], sc["scale"])
-        zb, hist = plan_for_ranks(grid, pos32, world)
+        grid, zb, hist = sc["grid"], sc["z_bounds"], sc["hist"]
         cap, gcap = bb.slab_capacity(hist, zb, rank, slack=2.0)
         slab = bb.NcclSlab(grid, sc["spacing"], sc["scale"], zb, rank, world, broadcast_bytes, cap, gcap, device=local_rank)
         eng = slab.engine
         eng.set_colliders(scenes.engine_colliders(sc))
-        eng.set_particles_ids(pos32, vel32)
+        eng.set_particles_ids(pos32, vel32, sc["ids"])
     else:
         eng = scenes.make_engine(sc, device=local_rank)
         eng.set_particles(pos32, vel32)
@@ -287,13 +289,15 @@ def main():
     value = n_global / (ms_per_step * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------
-    hp = torch.from_numpy(pos32.copy()).pin_memory()
-    hv = torch.from_numpy(vel32.copy()).pin_memory()
+    hcap0 = max(len(pos32), int(eng.cfg.max_particles))
+    hp = torch.zeros((hcap0, 3), dtype=torch.float32).pin_memory(); hp[:len(pos32)] = torch.from_numpy(pos32)
+    hv = torch.zeros((hcap0, 3), dtype=torch.float32).pin_memory(); hv[:len(vel32)] = torch.from_numpy(vel32)
     op = torch.empty_like(hp).pin_memory()
     ov = torch.empty_like(hv).pin_memory()
     lib = eng.lib
 
-    hid = torch.zeros(len(pos32), dtype=torch.int32).pin_memory()
+    hcap = max(len(pos32), int(eng.cfg.max_particles))  # slabs gain particles through migration
+    hid = torch.zeros(hcap, dtype=torch.int32).pin_memory()
     cnt = C.c_int()
     h2d = [0]
 
@@ -320,10 +324,10 @@ def main():
 
     # restart from the initial block so that the e2e run simulates the same thing
     if world == 1:
-        hp.copy_(torch.from_numpy(pos32)); hv.copy_(torch.from_numpy(vel32))
+        hp[:len(pos32)] = torch.from_numpy(pos32); hv[:len(vel32)] = torch.from_numpy(vel32)
         eng.set_particles(pos32, vel32)
     else:
-        eng.set_particles_ids(pos32, vel32)
+        eng.set_particles_ids(pos32, vel32, sc["ids"])
         rc = lib.bbx_download_owned(eng.h, bb.POSITION, hp.data_ptr(), bb.F32, hid.data_ptr(), C.byref(cnt))
         rc |= lib.bbx_download_owned(eng.h, bb.VELOCITY, hv.data_ptr(), bb.F32, None, None)
         if rc:
@@ -359,7 +363,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"PCISPH 3D dam break, {n_global} particles = {n} per GPU (BASELINE configs[1] per GPU), spacing 0.02, h = 1.8 s, "
+            "config": {"workload": ("PCISPH 3D dam break + baked-SDF torus collider (BASELINE configs[2] stand-in), " if args.workload == "sdf" else "") +
+                                   f"PCISPH 3D dam break, {n_global} particles = {n} per GPU (BASELINE configs[1] per GPU), spacing 0.02, h = 1.8 s, "
                                    f"{cells} cells, fixed dt 7.2e-4, reference-compat (1 predict-correct iteration)"
                                    + (f", {world} z-slabs with NCCL ghost-plane exchange and migration" if world > 1 else ""),
                        "particles_per_gpu": n, "particles": n_global, "cells": cells, "dt": dt,

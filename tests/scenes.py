@@ -46,6 +46,70 @@ def dam_break_scene(n_target=1.0e6, spacing=0.02, scale=1.8, jitter=0.0, seed=1)
     return block_scene(container, fluid, (xof, -yof, zof), (0, -6, 0), spacing, scale, jitter, seed, dt=7.2e-4)
 
 
+def dam_break_geometry(n_target=1.0e6, spacing=0.02):
+    """Container / fluid box of test_pcisph3_dam_break scaled to ~n_target BCC particles."""
+    v_ref = 1.25 * 2.25 * 1.25
+    k = (n_target * spacing ** 3 / 2.0 / v_ref) ** (1.0 / 3.0)
+    container = np.array([3.25, 3.0, 3.25]) * k
+    fluid = np.array([1.25, 2.25, 1.25]) * k
+    center = np.array([(container[0] - fluid[0]) / 2 - spacing, -((container[1] - fluid[1]) / 2 - spacing),
+                       (container[2] - fluid[2]) / 2 - spacing])
+    return container, fluid, center
+
+
+def dam_break_scene_slab(n_target, rank, world, spacing=0.02, scale=1.8, obstacle=None):
+    """The jitter-free dam-break block WITHOUT materialising all of it on every rank: the BCC lattice is built
+    layer by layer (z), the per-plane histogram comes from the layer sizes, and a rank only generates the
+    layers whose cell plane it owns.  Returns the scene dict with pos / vel / ids of this rank's share, the
+    global count `n_global`, the grid, the z plan and the plane histogram.  Same points, same ids (lattice
+    order) as dam_break_scene(jitter=0)."""
+    container, fluid, center = dam_break_geometry(n_target, spacing)
+    half = container / 2
+    colliders = [dict(kind="box", size=tuple(container), reverse=True, friction=0.0)]
+    if obstacle is not None:
+        colliders.append(obstacle(container, fluid, center))
+    sc = dict(spacing=spacing, scale=scale, dt=7.2e-4, domain_min=-half, domain_max=half, colliders=colliders)
+    grid = bb.UtilBuildGridForDomain(sc["domain_min"], sc["domain_max"], spacing, scale)
+    lo, hi = center - fluid / 2, center + fluid / 2
+    ext = np.abs(hi - lo)
+    hs = spacing / 2
+    layers = []  # (z, x values, y values, first id, count, cell plane); the keep tests are emitter.box_inside per axis
+    k, shifted, first = 0, False, 0
+    hist = np.zeros(grid.n[2], dtype=np.int64)
+    gmin, glen = grid.min[2], grid.cell_len[2]
+    while k * hs <= ext[2]:
+        off = hs if shifted else 0.0
+        z = k * hs + lo[2]
+        ny = int(np.floor((ext[1] - off) / spacing + 1e-9)) + 2
+        nx = int(np.floor((ext[0] - off) / spacing + 1e-9)) + 2
+        x = np.arange(nx) * spacing + off
+        y = np.arange(ny) * spacing + off
+        x, y = x[x <= ext[0]] + lo[0], y[y <= ext[1]] + lo[1]
+        zf = float(np.float32(z))
+        xk = x[np.abs(x - center[0]) <= fluid[0] / 2]
+        yk = y[np.abs(y - center[1]) <= fluid[1] / 2]
+        cnt = len(xk) * len(yk) if abs(z - center[2]) <= fluid[2] / 2 else 0
+        plane = int(np.floor((zf - gmin) / glen))
+        plane = min(max(plane, 0), grid.n[2] - 1)
+        layers.append((z, xk, yk, first, cnt, plane))
+        hist[plane] += cnt
+        first += cnt
+        shifted = not shifted
+        k += 1
+    zb = bb.plan_slabs(hist, world)
+    pos, ids = [], []
+    for z, xk, yk, f0, cnt, plane in layers:
+        if cnt and zb[rank] <= plane < zb[rank + 1]:
+            yy, xx = np.meshgrid(yk, xk, indexing="ij")
+            pos.append(np.stack([xx, yy, np.full_like(xx, z)], axis=-1).reshape(-1, 3).astype(np.float32))
+            ids.append(np.arange(f0, f0 + cnt, dtype=np.int32))
+    sc["pos"] = np.concatenate(pos) if pos else np.zeros((0, 3), np.float32)
+    sc["ids"] = np.concatenate(ids) if ids else np.zeros(0, np.int32)
+    sc["vel"] = np.tile(np.array([0, -6, 0], dtype=np.float32), (len(sc["pos"]), 1))
+    sc.update(n_global=int(first), grid=grid, z_bounds=zb, hist=hist)
+    return sc
+
+
 def _xf(c):
     t = c.get("translate")
     return bb.Translate(*t) if t is not None else None
@@ -90,6 +154,16 @@ def make_oracle(sc, **kw):
             cols.append(O.make_collider("sdf", friction=c.get("friction", 0.0),
                                         sdf=dict(res=nodes, spacing=(dx, dx, dx), origin=origin, field=field)))
     return O.Oracle(sc["spacing"], sc["scale"], sc["domain_min"], sc["domain_max"], cols, **kw)
+
+
+def torus_obstacle(container, fluid, center):
+    """Config 3 stand-in for the absent whale / dragon meshes: an analytic SDF torus
+    (SDF_Torus, src/shapes/sdfs.h:17-22) baked with MakeSDFShape at dx = 0.01, lying on the floor right beside
+    the fluid block so that the collapsing front runs into it."""
+    R, r = 0.30 * fluid[0], 0.08 * fluid[0]
+    c = np.array([center[0] - fluid[0] / 2 - R - r - 0.05, -container[1] / 2 + r + 0.02, center[2]])
+    return dict(kind="sdf", bounds_min=tuple(c - np.array([R + r, r, R + r])), bounds_max=tuple(c + np.array([R + r, r, R + r])),
+                sdf=sdf_torus(c, R, r), dx=0.01, margin=0.1, friction=0.0)
 
 
 def sdf_torus(center, R, r):
