@@ -56,6 +56,7 @@ struct bbx_engine {
     int list_ctas_per_sm;
     unsigned short *nbr; int *nbr_cnt;
     float4 *force, *force_p, *pred, *posq, *smoothed;
+    float4 *rec;     // 32-byte gather records (x, y, z, rho | vx, vy, vz, -), 2 float4 per slot, written by the list build
     float *pressure, *rho_pred, *rho_err;
     DevState *st; DevState *st_host; // st_host pinned
     DevColliderSet *colliders; DevColliderSet colliders_host;
@@ -186,6 +187,11 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     }
     BBX_ALLOC_G(e->newcell); BBX_ALLOC_G(e->pred); BBX_ALLOC_G(e->posq);
 #undef BBX_ALLOC_G
+    {   // records: 2 float4 per slot, ghost slots in front like the other slot-indexed arrays (32-byte aligned)
+        float4 *raw = nullptr;
+        rc |= dev_alloc(&raw, 2 * capg);
+        if(rc == BBX_OK){ e->raw.push_back((void *)raw); CU(cudaMemset(raw, 0, sizeof(float4) * 2 * capg)); e->rec = raw + 2 * gc; }
+    }
     rc |= dev_alloc(&e->count, (size_t)g.total + 8); rc |= dev_alloc(&e->perm, cap);
     rc |= dev_alloc(&e->occ_cells, (size_t)g.total); rc |= dev_alloc(&e->queue, cap);
     e->scan_tiles = div_up(g.c_own1 - g.c_own0, SCAN_TILE);
@@ -549,7 +555,7 @@ static int grid_update(bbx_engine *e){
         int groups = std::max(1, std::min(n_all, own_cells));
         int blocks = std::min(div_up((long long)groups * 8, 256), 148 * 8);
         LAUNCH(e, k_fill_incremental, blocks, 256, g, e->st, par, e->occ_cells, e->cell_start[cur], e->cell_start[nxt], e->newcell,
-               e->pos[cur], e->vel[cur], e->pid[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt]);
+               e->pos[cur], e->vel[cur], e->pid[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec);
     }
     // full path (forced, or selected on the device by the big-move / jump flags); small grids when it is
     // only a flag check
@@ -558,7 +564,7 @@ static int grid_update(bbx_engine *e){
     LAUNCH(e, k_full_scatter, fb_n, 256, n_all, e->n_glo, g, e->st, par, force, e->newcell, e->cell_start[nxt], e->count, e->perm);
     LAUNCH(e, k_full_sort_cells, fb_c, 256, g, e->st, par, force, e->cell_start[nxt], e->pid[cur], e->perm, e->count);
     LAUNCH(e, k_full_gather, fb_n, 256, e->st, par, force, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
-           e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt]);
+           e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec);
     CU(cudaGetLastError());
     if(slab){
         // migration happened implicitly: particles that crossed into my planes were found in my ghost
@@ -596,18 +602,21 @@ static int list_blocks(bbx_engine *e){
 static int phase_density(bbx_engine *e, const StepParams &P, int sph){
     int cur = e->cur;
     if(e->n > 0){
-        if(sph) LAUNCH(e, k_cell_lists_density<1>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq);
-        else LAUNCH(e, k_cell_lists_density<0>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq);
+        if(sph) LAUNCH(e, k_cell_lists_density<1>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec);
+        else LAUNCH(e, k_cell_lists_density<0>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec);
         CU(cudaGetLastError());
     }
-    // ghost rho (rides in vel.w); the SPH step also needs the ghosts' p / rho^2 (posq.w)
+    // ghost rho: the PCISPH viscosity sweep reads the 32-byte records (x, rho | v); the SPH step reads rho from
+    // vel.w and also needs the ghosts' p / rho^2 (posq.w)
     if(sph) return exchange2(e, e->vel[cur], e->posq);
-    return exchange1(e, e->vel[cur]);
+    { void *arr[1] = {e->rec}; size_t z[1] = {2 * sizeof(float4)}; return exchange_planes(e, arr, z, 1); }
 }
+// grid of a list sweep: one thread per particle
+static int sweep_grid(bbx_engine *e){ return div_up(e->n, BBX_BS); }
 static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
     int cur = e->cur;
     if(e->n > 0){
-        LAUNCH(e, k_force_np_predict, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur],
+        LAUNCH(e, k_force_np_predict, sweep_grid(e), BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->rec, e->cell[cur], e->cell_start[cur],
                e->nbr, e->nbr_cnt, e->force, e->pred, e->queue);
         LAUNCH(e, k_collide_predict, BBX_SMALL_GRID, 128, P, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force, e->pred);
         CU(cudaGetLastError());
@@ -617,14 +626,14 @@ static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
 static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
     int cur = e->cur;
     if(e->n > 0){
-        LAUNCH(e, k_pressure, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
+        LAUNCH(e, k_pressure, sweep_grid(e), BBX_BS, P, e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
                e->nbr, e->nbr_cnt, e->pressure, e->rho_pred, e->rho_err, e->posq);
         CU(cudaGetLastError());
     }
     return exchange1(e, e->posq); // ghost (x, p / rho*^2)
 }
 static int phase_pressure_force(bbx_engine *e, const StepParams &P, int integrate){
-    int cur = e->cur; int nb = div_up(e->n, BBX_BS);
+    int cur = e->cur; int nb = sweep_grid(e);
     if(e->n > 0){
         if(integrate){
             LAUNCH(e, k_pressure_force<1>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue);
@@ -651,7 +660,7 @@ static int phase_pseudo_viscosity(bbx_engine *e, const StepParams &P, double dt)
     if(!(e->cfg.pseudo_viscosity * dt > 0.1)) return BBX_OK; // sph_equations3.cpp:655-657
     int cur = e->cur;
     if(e->n > 0){
-        LAUNCH(e, k_pseudo_aggregate, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->smoothed);
+        LAUNCH(e, k_pseudo_aggregate, sweep_grid(e), BBX_BS, P, e->grid, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->smoothed);
         LAUNCH(e, k_pseudo_interpolate, div_up(e->n, 256), 256, P, e->vel[cur], e->smoothed);
         CU(cudaGetLastError());
     }
@@ -725,7 +734,7 @@ static int step_sph(bbx_engine *e, double dt){
     if((rc = phase_density(e, P, 1))) return rc;
     tick(e, T_FORCE_NP);
     if(e->n > 0){
-        LAUNCH(e, k_sph_forces, div_up(e->n, BBX_BS), BBX_BS, P, e->grid, e->posq, e->vel[e->cur], e->cell[e->cur], e->cell_start[e->cur], e->nbr, e->nbr_cnt, e->force);
+        LAUNCH(e, k_sph_forces, sweep_grid(e), BBX_BS, P, e->grid, e->posq, e->vel[e->cur], e->cell[e->cur], e->cell_start[e->cur], e->nbr, e->nbr_cnt, e->force);
         CU(cudaGetLastError());
     }
     tick(e, T_INTEGRATE);
@@ -935,7 +944,7 @@ int bbx_inject_chains(bbx_engine *e, const int *cell_count, const int *cell_orde
     CU(cudaMemcpyAsync(d_cell, cell_of.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->cell_start[nxt], start.data(), sizeof(int) * ((size_t)total + 1), cudaMemcpyHostToDevice, e->stream));
     LAUNCH(e, k_slot_of_id, div_up(n, 256), 256, n, e->pid[cur], d_slot);
-    LAUNCH(e, k_inject_gather, div_up(n, 256), 256, n, d_order, d_slot, d_cell, e->pos[cur], e->vel[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt]);
+    LAUNCH(e, k_inject_gather, div_up(n, 256), 256, n, d_order, d_slot, d_cell, e->pos[cur], e->vel[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream)); // host vectors go out of scope
     e->cur = nxt; e->have_chains = 1; e->force_full = 0;

@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(256) k_fill_incremental(DevGrid g, const DevSt
         const int *__restrict__ occ_cells,
         const int *__restrict__ start_old, const int *__restrict__ start_new, const int *__restrict__ newcell,
         const float4 *__restrict__ pos_old, const float4 *__restrict__ vel_old, const int *__restrict__ pid_old,
-        float4 *__restrict__ pos_new, float4 *__restrict__ vel_new, int *__restrict__ pid_new, int *__restrict__ cell_new)
+        float4 *__restrict__ pos_new, float4 *__restrict__ vel_new, int *__restrict__ pid_new, int *__restrict__ cell_new,
+        float4 *__restrict__ rec)
 {
     if(st->rebuild_flag[par] | st->jump_flag[par]) return; // full rebuild path takes over
     const int n_occ = st->n_occ;
@@ -219,8 +220,10 @@ __global__ void __launch_bounds__(256) k_fill_incremental(DevGrid g, const DevSt
                     unsigned bal = (__ballot_sync(0xffffffffu, m) >> gshift) & 0xffu;
                     if(m){
                         int d = dst + found + __popc(bal & ((1u << sub) - 1u));
-                        pos_new[d] = pos_old[j];
-                        vel_new[d] = vel_old[j];
+                        const float4 pp = pos_old[j], vv = vel_old[j];
+                        pos_new[d] = pp;
+                        vel_new[d] = vv;
+                        rec[2 * (size_t)d] = pp; rec[2 * (size_t)d + 1] = vv; // gather record (rho follows in the list build)
                         pid_new[d] = pid_old[j];
                         cell_new[d] = c;
                     }
@@ -265,14 +268,17 @@ __global__ void __launch_bounds__(256) k_full_sort_cells(DevGrid g, const DevSta
 __global__ void __launch_bounds__(256) k_full_gather(const DevState *st, int par, int force, const int *__restrict__ perm,
         const int *__restrict__ newcell,
         const float4 *__restrict__ pos_old, const float4 *__restrict__ vel_old, const int *__restrict__ pid_old,
-        float4 *__restrict__ pos_new, float4 *__restrict__ vel_new, int *__restrict__ pid_new, int *__restrict__ cell_new)
+        float4 *__restrict__ pos_new, float4 *__restrict__ vel_new, int *__restrict__ pid_new, int *__restrict__ cell_new,
+        float4 *__restrict__ rec)
 {
     if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
     const int n = st->n_own;
     for(int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x){
         int j = perm[d];
-        pos_new[d] = pos_old[j];
-        vel_new[d] = vel_old[j];
+        const float4 pp = pos_old[j], vv = vel_old[j];
+        pos_new[d] = pp;
+        vel_new[d] = vv;
+        rec[2 * (size_t)d] = pp; rec[2 * (size_t)d + 1] = vv;
         pid_new[d] = pid_old[j];
         cell_new[d] = newcell[j];
     }
@@ -348,16 +354,32 @@ __device__ __forceinline__ uint4 *bbx_chunk_ptr(unsigned short *__restrict__ nbr
     }                                                                                              \
     const uint4 *lp = reinterpret_cast<const uint4 *>(nbr) + ((size_t)(i >> 5) * BBX_NBR_CHUNKS) * 32 + (i & 31);
 
+// Full 8-entry chunks run without per-entry guards (the next chunk is requested before the current one is
+// consumed); only the last, partial chunk tests k < cnt.
 template<typename F>
 __device__ __forceinline__ void bbx_for_each_neighbor(const uint4 *__restrict__ lp, int cnt, const int *sbase_col, F &&body){
-    for(int c0 = 0; c0 < cnt; c0 += 8){
-        uint4 ch = lp[(size_t)(c0 >> 3) * 32];
-        unsigned wv[4] = {ch.x, ch.y, ch.z, ch.w};
+    const int full = cnt >> 3;
+    uint4 ch = make_uint4(0u, 0u, 0u, 0u);
+    if(cnt > 0) ch = lp[0];
+    for(int c = 0; c < full; c++){
+        const uint4 cur = ch;
+        if((c + 1) * 8 < cnt) ch = lp[(size_t)(c + 1) * 32];
+        const unsigned wv[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
         for(int t = 0; t < 8; t++){
-            if(c0 + t < cnt){
-                unsigned e = (wv[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
-                int j = sbase_col[(e >> BBX_RUN_SHIFT) * BBX_BS] + (int)(e & BBX_RUN_MASK);
+            const unsigned e = (t & 1) ? (wv[t >> 1] >> 16) : (wv[t >> 1] & 0xffffu);
+            const int j = sbase_col[(e >> BBX_RUN_SHIFT) * BBX_BS] + (int)(e & BBX_RUN_MASK);
+            body(j);
+        }
+    }
+    const int rest = cnt & 7;
+    if(rest){
+        const unsigned wv[4] = {ch.x, ch.y, ch.z, ch.w};
+#pragma unroll
+        for(int t = 0; t < 7; t++){
+            if(t < rest){
+                const unsigned e = (t & 1) ? (wv[t >> 1] >> 16) : (wv[t >> 1] & 0xffffu);
+                const int j = sbase_col[(e >> BBX_RUN_SHIFT) * BBX_BS] + (int)(e & BBX_RUN_MASK);
                 body(j);
             }
         }
@@ -375,7 +397,10 @@ __device__ __forceinline__ void bbx_atomic_max_warp(unsigned *addr, float v){
 }
 
 // d and 1/d of a squared distance without the IEEE sqrt sequence: MUFU.RSQ + 1 multiply (2 ulp)
-__device__ __forceinline__ float bbx_rsqrt_safe(float d2){ return rsqrtf(fmaxf(d2, 1.0e-30f)); }
+// (raw MUFU through PTX: rsqrtf / __fdividef without fast-math carry denormal fix-up code, ~6 instructions)
+__device__ __forceinline__ float bbx_rsqrt_approx(float x){ float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float bbx_rcp_approx(float x){ float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float bbx_rsqrt_safe(float d2){ return bbx_rsqrt_approx(fmaxf(d2, 1.0e-30f)); }
 
 // --------------------------------- C+D: non-pressure forces + first prediction (sweep 2)
 // f_i = m g - c_drag v_i + mu m^2 sum_j (v_j - v_i) d2W_spiky(d) / rho_j   (ComputeNonPressureForceFor,
@@ -383,7 +408,7 @@ __device__ __forceinline__ float bbx_rsqrt_safe(float d2){ return rsqrtf(fmaxf(d
 // (PredictVelocityAndPositionFor with is_first, pcisph_equations3.cpp:3-28).  A particle the FP32
 // pre-check cannot clear of every collider is queued for k_collide_predict.
 __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGrid g, DevState *st, const DevCullSet *__restrict__ cull,
-        const float4 *__restrict__ pos, const float4 *__restrict__ vel, const int *__restrict__ cell,
+        const float4 *__restrict__ pos, const float4 *__restrict__ vel, const float4 *__restrict__ rec, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
         float4 *__restrict__ force, float4 *__restrict__ pred, int *__restrict__ queue)
 {
@@ -392,12 +417,15 @@ __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGr
     float4 pi = pos[i]; float4 vi = vel[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
     BBX_LIST_FOREACH(j, {
-        float4 pj = pos[j]; float4 vj = vel[j];
+        // x_j, rho_j, v_j in ONE 256-bit gather (LDG.E.256) from the 32-byte records the list build wrote
+        float4 pj, vj;
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(pj.x), "=f"(pj.y), "=f"(pj.z), "=f"(vj.w), "=f"(vj.x), "=f"(vj.y), "=f"(vj.z), "=f"(pj.w) : "l"(rec + 2 * (ptrdiff_t)j));
         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
         float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
         float d = d2 * bbx_rsqrt_safe(d2);
         float x = fmaxf(0.f, fmaf(-d, P.inv_h, 1.f));
-        float w = __fdividef(x, vj.w);
+        float w = x * bbx_rcp_approx(vj.w);
         ax = fmaf(vj.x - vi.x, w, ax); ay = fmaf(vj.y - vi.y, w, ay); az = fmaf(vj.z - vi.z, w, az);
     })
     float s = P.viscosity * P.mass2 * P.d2w_spiky_c;
@@ -541,7 +569,7 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid
         float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
         float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
         // j == i and coincident points (d ~ 0) and NaN-marked neighbours contribute nothing
-        float inv_d = (d2 > 1.0e-16f && pj.w == pj.w) ? rsqrtf(d2) : 0.f;
+        float inv_d = (d2 > 1.0e-16f && pj.w == pj.w) ? bbx_rsqrt_approx(d2) : 0.f;
         float x = fmaxf(0.f, fmaf(-d2 * inv_d, P.inv_h, 1.f));
         float w = (qi + pj.w) * (x * x) * inv_d;
         w = (inv_d > 0.f) ? w : 0.f;
@@ -616,11 +644,11 @@ __global__ void __launch_bounds__(BBX_BS) k_sph_forces(StepParams P, DevGrid g,
         float4 pj = posq[j]; float4 vj = vel[j];
         float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
         float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        float inv_d = (d2 > 1.0e-16f) ? rsqrtf(d2) : 0.f;
+        float inv_d = (d2 > 1.0e-16f) ? bbx_rsqrt_approx(d2) : 0.f;
         float x = (j != i) ? fmaxf(0.f, fmaf(-d2 * inv_d, P.inv_h, 1.f)) : 0.f;
         float w = (qi + pj.w) * (x * x) * inv_d;
         tx = fmaf(dx, w, tx); ty = fmaf(dy, w, ty); tz = fmaf(dz, w, tz);
-        float wv = __fdividef(x, vj.w);
+        float wv = x * bbx_rcp_approx(vj.w);
         ax = fmaf(vj.x - vi.x, wv, ax); ay = fmaf(vj.y - vi.y, wv, ay); az = fmaf(vj.z - vi.z, wv, az);
     })
     float sp = -P.mass2 * P.dw_spiky_c;
@@ -779,10 +807,13 @@ __global__ void __launch_bounds__(256) k_slot_of_id(int n, const int *__restrict
 __global__ void __launch_bounds__(256) k_inject_gather(int n, const int *__restrict__ order, const int *__restrict__ slot_of,
         const int *__restrict__ cell_of_slot_new,
         const float4 *__restrict__ pos_old, const float4 *__restrict__ vel_old,
-        float4 *__restrict__ pos_new, float4 *__restrict__ vel_new, int *__restrict__ pid_new, int *__restrict__ cell_new)
+        float4 *__restrict__ pos_new, float4 *__restrict__ vel_new, int *__restrict__ pid_new, int *__restrict__ cell_new,
+        float4 *__restrict__ rec)
 {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if(d >= n) return;
     int id = order[d]; int j = slot_of[id];
-    pos_new[d] = pos_old[j]; vel_new[d] = vel_old[j]; pid_new[d] = id; cell_new[d] = cell_of_slot_new[d];
+    const float4 pp = pos_old[j], vv = vel_old[j];
+    pos_new[d] = pp; vel_new[d] = vv; rec[2 * (size_t)d] = pp; rec[2 * (size_t)d + 1] = vv;
+    pid_new[d] = id; cell_new[d] = cell_of_slot_new[d];
 }

@@ -153,7 +153,8 @@ __device__ __forceinline__ bool bbx_list_pass(const StepParams &P, DevState *st,
 template<int SPH_EOS>
 __global__ void __launch_bounds__(BBX_LT) k_cell_lists_density(StepParams P, DevGrid g, DevState *st, const int *__restrict__ occ_cells,
         const float4 *__restrict__ pos, float4 *__restrict__ vel, const int *__restrict__ cell_start,
-        unsigned short *__restrict__ nbr, int *__restrict__ nbr_cnt, float *__restrict__ pressure, float4 *__restrict__ posq)
+        unsigned short *__restrict__ nbr, int *__restrict__ nbr_cnt, float *__restrict__ pressure, float4 *__restrict__ posq,
+        float4 *__restrict__ rec)
 {
     __shared__ float4 s_pi[BBX_LW][BBX_BP];
     __shared__ __align__(16) unsigned short s_rows[BBX_LW][BBX_BP * BBX_ROW];
@@ -247,7 +248,10 @@ __global__ void __launch_bounds__(BBX_LT) k_cell_lists_density(StepParams P, Dev
                 if(cn < 0){ cn = -cn; sum = sovs[idx]; }
                 nbr_cnt[i] = cn;
                 const float rho = P.mass * P.w_std_c * sum;
+                // rho rides in vel.w and in the 32-byte gather record (x, y, z, rho | vx, vy, vz, -) of the viscosity
+                // sweep; the grid fill wrote the record's x and v
                 reinterpret_cast<float *>(vel)[4 * (size_t)i + 3] = rho;
+                reinterpret_cast<float *>(rec)[8 * (size_t)i + 3] = rho;
                 if(SPH_EOS){
                     // Tait EOS, ComputePressureValue (sph_equations3.cpp:7-18)
                     float p = P.eos_scale * (powf(rho / P.rho0, P.eos_exponent) - 1.f);
