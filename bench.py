@@ -294,6 +294,7 @@ def main():
     hv = torch.zeros((hcap0, 3), dtype=torch.float32).pin_memory(); hv[:len(vel32)] = torch.from_numpy(vel32)
     op = torch.empty_like(hp).pin_memory()
     ov = torch.empty_like(hv).pin_memory()
+    buf = {"ip": hp, "iv": hv, "op": op, "ov": ov}  # pinned input / output buffers, swapped after every step
     lib = eng.lib
 
     hcap = max(len(pos32), int(eng.cfg.max_particles))  # slabs gain particles through migration
@@ -303,24 +304,26 @@ def main():
 
     def e2e_step():
         if world == 1:
-            rc = lib.bbx_overwrite_state(eng.h, hp.data_ptr(), hv.data_ptr(), bb.F32)
+            rc = lib.bbx_overwrite_state(eng.h, buf["ip"].data_ptr(), buf["iv"].data_ptr(), bb.F32)
             rc |= lib.bbx_step_pcisph(eng.h, dt)
-            rc |= lib.bbx_download(eng.h, bb.POSITION, op.data_ptr(), bb.F32)
-            rc |= lib.bbx_download(eng.h, bb.VELOCITY, ov.data_ptr(), bb.F32)
+            rc |= lib.bbx_download(eng.h, bb.POSITION, buf["op"].data_ptr(), bb.F32)
+            rc |= lib.bbx_download(eng.h, bb.VELOCITY, buf["ov"].data_ptr(), bb.F32)
             m = len(pos32)
             h2d[0] = 24 * m
         else:
             # slab engines: every rank hands over the particles it holds (host buffers, global ids), steps, and
             # reads its owned particles back with their ids -- the per-rank share of what a host run loop does
             m = cnt.value
-            rc = lib.bbx_set_particles_ids(eng.h, m, hp.data_ptr(), hv.data_ptr(), hid.data_ptr(), bb.F32)
+            rc = lib.bbx_set_particles_ids(eng.h, m, buf["ip"].data_ptr(), buf["iv"].data_ptr(), hid.data_ptr(), bb.F32)
             rc |= lib.bbx_step_pcisph(eng.h, dt)
-            rc |= lib.bbx_download_owned(eng.h, bb.POSITION, op.data_ptr(), bb.F32, hid.data_ptr(), C.byref(cnt))
-            rc |= lib.bbx_download_owned(eng.h, bb.VELOCITY, ov.data_ptr(), bb.F32, None, None)
+            rc |= lib.bbx_download_owned(eng.h, bb.POSITION, buf["op"].data_ptr(), bb.F32, hid.data_ptr(), C.byref(cnt))
+            rc |= lib.bbx_download_owned(eng.h, bb.VELOCITY, buf["ov"].data_ptr(), bb.F32, None, None)
             h2d[0] = 28 * m
         if rc:
             raise SystemExit("bbx error: " + lib.bbx_last_error().decode())
-        hp.copy_(op); hv.copy_(ov)  # next step's input is this step's output (host side)
+        # next step's input is this step's output: swap the pinned host buffers
+        buf["ip"], buf["op"] = buf["op"], buf["ip"]
+        buf["iv"], buf["ov"] = buf["ov"], buf["iv"]
 
     # restart from the initial block so that the e2e run simulates the same thing
     if world == 1:
