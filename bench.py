@@ -301,6 +301,7 @@ def main():
     hid = torch.zeros(hcap, dtype=torch.int32).pin_memory()
     cnt = C.c_int()
     h2d = [0]
+    d2h = [0]
 
     def e2e_step():
         if world == 1:
@@ -309,16 +310,17 @@ def main():
             rc |= lib.bbx_download(eng.h, bb.POSITION, buf["op"].data_ptr(), bb.F32)
             rc |= lib.bbx_download(eng.h, bb.VELOCITY, buf["ov"].data_ptr(), bb.F32)
             m = len(pos32)
-            h2d[0] = 24 * m
+            h2d[0] = 24 * m; d2h[0] = 24 * m
         else:
             # slab engines: every rank hands over the particles it holds (host buffers, global ids), steps, and
             # reads its owned particles back with their ids -- the per-rank share of what a host run loop does
+            # (rows travel in the engine's cell order, the order of the previous download)
             m = cnt.value
-            rc = lib.bbx_set_particles_ids(eng.h, m, buf["ip"].data_ptr(), buf["iv"].data_ptr(), hid.data_ptr(), bb.F32)
+            rc = lib.bbx_overwrite_owned(eng.h, buf["ip"].data_ptr(), buf["iv"].data_ptr(), bb.F32)
             rc |= lib.bbx_step_pcisph(eng.h, dt)
             rc |= lib.bbx_download_owned(eng.h, bb.POSITION, buf["op"].data_ptr(), bb.F32, hid.data_ptr(), C.byref(cnt))
             rc |= lib.bbx_download_owned(eng.h, bb.VELOCITY, buf["ov"].data_ptr(), bb.F32, None, None)
-            h2d[0] = 28 * m
+            h2d[0] = 24 * m; d2h[0] = 28 * m  # ids come back with the positions
         if rc:
             raise SystemExit("bbx error: " + lib.bbx_last_error().decode())
         # next step's input is this step's output: swap the pinned host buffers
@@ -376,9 +378,9 @@ def main():
                        "timing": "CUDA events on the engine stream between kernels, summed over phases, max over ranks",
                        "wall_ms_per_step": wall_ms},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d[0] * world, "d2h_bytes_per_step": h2d[0] * world,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d[0] * world, "d2h_bytes_per_step": d2h[0] * world,
                     "api": ("bbx_overwrite_state + bbx_step_pcisph + bbx_download(POSITION, VELOCITY), pinned host buffers" if world == 1 else
-                            "per rank: bbx_set_particles_ids(owned, host) + bbx_step_pcisph + bbx_download_owned(POSITION, VELOCITY, ids), pinned host buffers"),
+                            "per rank: bbx_overwrite_owned(host) + bbx_step_pcisph + bbx_download_owned(POSITION, VELOCITY, ids), pinned host buffers"),
                     "steps": args.e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -388,7 +390,7 @@ def main():
                          "phases_ms_per_step": {k: v[0] / args.steps for k, v in phase.items()},
                          "gap_ms_per_step": gap_ms / args.steps},
             "stats": {"neighbor_overflow": st.neighbor_overflow, "clamped": st.clamped, "rebuild_flag": st.rebuild_flag,
-                      "occupied_cells": st.occupied_cells, "max_candidates": st.max_candidates, "exact_passes": st.exact_passes},
+                      "occupied_cells": st.occupied_cells, "max_candidates": st.max_candidates, "exact_passes": st.exact_passes, "unstaged_tiles": st.unstaged_tiles},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(n)

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libbbx.so")
+# BBX_LIB: development aid (A/B runs of kernel variants built from the same sources); default = the in-tree build
+LIB_PATH = os.environ.get("BBX_LIB") or os.path.join(HERE, "lib", "libbbx.so")
 
 MAX_NEIGHBORS = 100
 MAX_COLLIDERS = 16
@@ -56,7 +57,7 @@ class StepStats(C.Structure):
                 ("neighbor_overflow", C.c_int), ("lost_particles", C.c_int), ("clamped", C.c_int),
                 ("nan_count", C.c_int), ("max_force", C.c_float), ("max_density_error", C.c_float),
                 ("ms_grid", C.c_float), ("ms_step", C.c_float),
-                ("exact_passes", C.c_int), ("max_candidates", C.c_int), ("occupied_cells", C.c_int), ("reserved", C.c_int)]
+                ("exact_passes", C.c_int), ("max_candidates", C.c_int), ("occupied_cells", C.c_int), ("unstaged_tiles", C.c_int)]
 
 
 # every symbol include/bbx.h declares: name -> (restype, argtypes)
@@ -76,6 +77,7 @@ SYMBOLS = {
     "bbx_append_particles": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "bbx_particle_count": (C.c_int, [_E, C.POINTER(C.c_int)]),
     "bbx_overwrite_state": (C.c_int, [_E, C.c_void_p, C.c_void_p, C.c_int]),
+    "bbx_overwrite_owned": (C.c_int, [_E, C.c_void_p, C.c_void_p, C.c_int]),
     "bbx_set_colliders": (C.c_int, [_E, C.c_int, C.POINTER(Collider)]),
     "bbx_update_collider": (C.c_int, [_E, C.c_int, C.POINTER(Collider)]),
     "bbx_set_collider_active": (C.c_int, [_E, C.c_int, C.c_int]),

@@ -26,7 +26,7 @@
 // bit-identical to the single-domain engine.
 struct DevGrid {
     double min[3], max[3], len[3];
-    float minf[3], maxf[3];
+    float minf[3], maxf[3], lenf[3];
     int n[3];           // local cell counts (n[2] = local planes incl. ghost planes)
     int total;          // local cells
     int plane;          // n[0] * n[1]
@@ -103,6 +103,7 @@ struct DevState {
     int n_first, n_last; // particles in the first / last owned plane (what the slab neighbours hold as ghosts)
     int exact_passes;    // list-build passes repeated with the FP64 predicate (a candidate inside the guard band)
     int max_candidates;  // largest 27-cell neighbourhood seen in the last list build
+    int unstaged_tiles;  // sweep tiles (all three sweeps) whose neighbourhood exceeded the shared-memory stage
 
 };
 
@@ -131,6 +132,7 @@ struct StepParams {
     float min_cell_len09; // 0.9 * min cell length (big-move rule, sph_equations3.cpp:330-335)
     float pseudo_factor;  // clamp(dt * pseudoViscosity, 0, 1)
     float thr_lo, thr_hi; // thr2 -+ band: below thr_lo certainly accepted, above thr_hi certainly rejected
+    float xacc, xband;    // the same on x = 1 - d^2 / h^2 (list build): accepted when x > xacc, inside the band when x < xband
     int par;              // parity of the current grid epoch; integrate writes rebuild_flag[par ^ 1]
 };
 

@@ -78,6 +78,7 @@ struct bbx_engine {
 #define BBX_PAD 64 // spare slots at the end of the particle arrays
 static int push_cull(bbx_engine *e);
 #define LAUNCH(e, kernel, grid, block, ...) do{ kernel<<<(grid), (block), 0, (e)->stream>>>(__VA_ARGS__); (e)->launches++; }while(0)
+#define LAUNCH_S(e, kernel, grid, block, smem, ...) do{ kernel<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__); (e)->launches++; }while(0)
 static inline int div_up(long long a, int b){ return (int)((a + b - 1) / b); }
 
 const char *bbx_last_error(void){ return g_last_error.c_str(); }
@@ -137,11 +138,13 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->list_ctas_per_sm, k_cell_lists_density<0>, BBX_LT, 0));
     if(e->list_ctas_per_sm < 1) e->list_ctas_per_sm = 1;
+    // the staged sweeps carry their tile's neighbourhood in dynamic shared memory (> 48 KB: opt in)
+    CU(cudaFuncSetAttribute(k_pressure, cudaFuncAttributeMaxDynamicSharedMemorySize, BBX_STAGE_BYTES(3)));
     // grid
     DevGrid &g = e->grid;
     for(int k = 0; k < 3; k++){
         g.min[k] = cfg->grid.min[k]; g.max[k] = cfg->grid.max[k]; g.len[k] = cfg->grid.cell_len[k];
-        g.minf[k] = (float)g.min[k]; g.maxf[k] = (float)g.max[k]; g.n[k] = cfg->grid.n[k];
+        g.minf[k] = (float)g.min[k]; g.maxf[k] = (float)g.max[k]; g.lenf[k] = (float)g.len[k]; g.n[k] = cfg->grid.n[k];
     }
     g.plane = g.n[0] * g.n[1];
     if((long long)g.n[0] * g.n[1] * g.n[2] != cfg->grid.total) { delete e; return set_error(BBX_ERR_INVALID, "grid.total != nx*ny*nz"); }
@@ -345,6 +348,24 @@ int bbx_overwrite_state(bbx_engine *e, const void *pos, const void *vel, int dty
     return BBX_OK;
 }
 
+static int exchange2(bbx_engine *e, float4 *a, float4 *b);
+int bbx_overwrite_owned(bbx_engine *e, const void *pos, const void *vel, int dtype){
+    CHECK_ENGINE(e);
+    if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "dtype must be BBX_F32 or BBX_F64");
+    if(e->n > 0){
+        if(!pos || !vel) return set_error(BBX_ERR_INVALID, "null");
+        size_t esz = dtype == BBX_F64 ? 8 : 4; size_t bytes = esz * 3 * (size_t)e->n;
+        int rc = ensure_stage(e, 2 * bytes); if(rc) return rc;
+        char *sp = (char *)e->stage, *sv = sp + bytes;
+        CU(cudaMemcpyAsync(sp, pos, bytes, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(sv, vel, bytes, cudaMemcpyHostToDevice, e->stream));
+        LAUNCH(e, k_overwrite, div_up(e->n, 256), 256, e->n, (const int *)nullptr, sp, sv, dtype == BBX_F64, e->pos[e->cur], e->vel[e->cur]);
+        CU(cudaGetLastError());
+    }
+    // the neighbours run their next grid update on their ghost copies of my boundary planes (old order)
+    return exchange2(e, e->pos[e->cur], e->vel[e->cur]);
+}
+
 // ------------------------------------------------------------------------------------ colliders
 static int fill_collider(bbx_engine *e, DevCollider &d, const bbx_collider &c){
     if(c.type < BBX_COLLIDER_BOX || c.type > BBX_COLLIDER_SDF) return set_error(BBX_ERR_INVALID, "unknown collider type %d", c.type);
@@ -494,6 +515,8 @@ static void make_params(bbx_engine *e, double dt, StepParams &P){
     P.thr2 = (float)(h * h - 1e-8);
     P.band = (float)(h * h * 1.0e-6 + 4e-8); // >> FP32 rounding of d^2 (~1e-7 relative) and of thr2
     P.thr_lo = P.thr2 - P.band; P.thr_hi = P.thr2 + P.band;
+    // list build: x = 1 - d^2 / h^2 evaluated in the cell frame (absolute error of a few 1e-7, bbx_lists.cuh)
+    { double bx = 4.0e-6 + 4e-8 / (h * h); P.xacc = (float)(1e-8 / (h * h) - bx); P.xband = (float)(1e-8 / (h * h) + bx); }
     P.par = (e->epoch + 1) & 1; // parity of the grid epoch this sub-step runs under (set right after its grid update)
     P.mass = (float)e->mass; P.mass2 = (float)(e->mass * e->mass); P.inv_mass = (float)(1.0 / e->mass);
     P.rho0 = (float)c.target_density;
@@ -613,6 +636,8 @@ static int phase_density(bbx_engine *e, const StepParams &P, int sph){
 }
 // grid of a list sweep: one thread per particle
 static int sweep_grid(bbx_engine *e){ return div_up(e->n, BBX_BS); }
+// grid of a staged sweep: one CTA per tile of BBX_TS consecutive slots
+static int tile_grid(bbx_engine *e){ return div_up(e->n, BBX_TS); }
 static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
     int cur = e->cur;
     if(e->n > 0){
@@ -626,7 +651,7 @@ static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
 static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
     int cur = e->cur;
     if(e->n > 0){
-        LAUNCH(e, k_pressure, sweep_grid(e), BBX_BS, P, e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
+        LAUNCH_S(e, k_pressure, tile_grid(e), BBX_TS, BBX_STAGE_BYTES(3), P, e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
                e->nbr, e->nbr_cnt, e->pressure, e->rho_pred, e->rho_err, e->posq);
         CU(cudaGetLastError());
     }
@@ -829,7 +854,7 @@ int bbx_stats(bbx_engine *e, bbx_step_stats *out){
     out->lost_particles = s.lost[done]; out->clamped = s.clamped; out->nan_count = s.nan_count;
     memcpy(&out->max_force, &s.max_force_bits, 4); memcpy(&out->max_density_error, &s.max_err_bits, 4);
     out->ms_grid = e->last_ms_grid; out->ms_step = e->last_ms_step;
-    out->exact_passes = s.exact_passes; out->max_candidates = s.max_candidates; out->occupied_cells = s.n_occ;
+    out->exact_passes = s.exact_passes; out->max_candidates = s.max_candidates; out->occupied_cells = s.n_occ; out->unstaged_tiles = s.unstaged_tiles;
     if(s.error) return set_error(s.error, "device-side error %d (%s)", s.error,
                                  s.error == BBX_ERR_OUT_OF_DOMAIN ? "particle outside the grid bounds" : "a cell run holds more than 4096 particles");
     return BBX_OK;

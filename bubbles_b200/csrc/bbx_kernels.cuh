@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) k_hash_count(int n_all, int n_lo, int n_o
         st->rebuild_flag[par ^ 1] = 0; st->jump_flag[par ^ 1] = 0; st->lost[par ^ 1] = 0;
         st->overflow = 0; st->clamped = 0; st->nan_count = 0; st->max_force_bits = 0; st->max_err_bits = 0;
         st->qn[0] = 0; st->qn[1] = 0; st->scan_ticket = 0; st->n_occ = 0;
-        st->exact_passes = 0; st->max_candidates = 0;
+        st->exact_passes = 0; st->max_candidates = 0; st->unstaged_tiles = 0;
     }
     if(idx < scan_tiles) scan_status[idx] = 0ull;
     if(idx >= n_all) return;
@@ -355,8 +355,8 @@ __device__ __forceinline__ uint4 *bbx_chunk_ptr(unsigned short *__restrict__ nbr
     const uint4 *lp = reinterpret_cast<const uint4 *>(nbr) + ((size_t)(i >> 5) * BBX_NBR_CHUNKS) * 32 + (i & 31);
 
 // Full 8-entry chunks run without per-entry guards (the next chunk is requested before the current one is
-// consumed); only the last, partial chunk tests k < cnt.
-template<typename F>
+// consumed); only the last, partial chunk tests k < cnt.  STRIDE = threads per CTA (column stride of sbase).
+template<int STRIDE, typename F>
 __device__ __forceinline__ void bbx_for_each_neighbor(const uint4 *__restrict__ lp, int cnt, const int *sbase_col, F &&body){
     const int full = cnt >> 3;
     uint4 ch = make_uint4(0u, 0u, 0u, 0u);
@@ -368,7 +368,7 @@ __device__ __forceinline__ void bbx_for_each_neighbor(const uint4 *__restrict__ 
 #pragma unroll
         for(int t = 0; t < 8; t++){
             const unsigned e = (t & 1) ? (wv[t >> 1] >> 16) : (wv[t >> 1] & 0xffffu);
-            const int j = sbase_col[(e >> BBX_RUN_SHIFT) * BBX_BS] + (int)(e & BBX_RUN_MASK);
+            const int j = sbase_col[(e >> BBX_RUN_SHIFT) * STRIDE] + (int)(e & BBX_RUN_MASK);
             body(j);
         }
     }
@@ -379,13 +379,110 @@ __device__ __forceinline__ void bbx_for_each_neighbor(const uint4 *__restrict__ 
         for(int t = 0; t < 7; t++){
             if(t < rest){
                 const unsigned e = (t & 1) ? (wv[t >> 1] >> 16) : (wv[t >> 1] & 0xffffu);
-                const int j = sbase_col[(e >> BBX_RUN_SHIFT) * BBX_BS] + (int)(e & BBX_RUN_MASK);
+                const int j = sbase_col[(e >> BBX_RUN_SHIFT) * STRIDE] + (int)(e & BBX_RUN_MASK);
                 body(j);
             }
         }
     }
 }
-#define BBX_LIST_FOREACH(J, ...) bbx_for_each_neighbor(lp, cnt, sbase + threadIdx.x, [&](int J) __VA_ARGS__ );
+#define BBX_LIST_FOREACH(J, ...) bbx_for_each_neighbor<BBX_BS>(lp, cnt, sbase + threadIdx.x, [&](int J) __VA_ARGS__ );
+
+// ------------------------------------------------------ shared-memory staging of a tile's neighbourhood
+// The three hot sweeps (viscosity + predict, predicted pressure, pressure force) run one CTA per TILE of
+// BBX_TS consecutive slots.  Slots are sorted by cell id, so the tile covers the cell range [c_lo, c_hi] and,
+// for each of the 9 (dy, dz) offsets, everything any of its particles can reference lies in the contiguous
+// slot range of the cells [c_lo - 1 + off, c_hi + 1 + off] (off = dy nx + dz nx ny).  The CTA copies the
+// gathered field of those 9 ranges into shared memory with coalesced 16-byte loads -- ~10 records per
+// particle instead of ~49 scattered gathers through L1 -- TRANSPOSED to one array per component: the list
+// walk then reads word j of each component with LDS.32, whose bank is j mod 32, and the 32 lanes of a warp
+// (consecutive particles of 2-3 cells) reference slots of one narrow window, so the loads are nearly
+// conflict free (float4 records read with LDS.128 were measured at 2.3 wavefronts per quarter warp: ncu,
+// profiles/).  A tile whose neighbourhood does not fit (CAP slots: sparse spray next to a dense bulk) walks
+// its lists against global memory instead.
+#define BBX_TS 256            // threads = particles per CTA of the staged sweeps
+#define BBX_STAGE_CAP 3200    // staged slots per tile (a dense tile needs ~9 x (256 + 2 x 12) = 2520)
+#define BBX_STAGE_HDR 128     // bytes: tile run table
+#define BBX_STAGE_BYTES(NC) (BBX_STAGE_HDR + 9 * BBX_TS * 4 + BBX_STAGE_CAP * (NC) * 4)
+
+// Stage NC components of `src` (REC float4 per slot; component k = float k of the slot's record) for the tile
+// of this CTA.  Every thread of the CTA calls this (no early exit before it).  Returns the column of
+// per-thread run bases for the list walk (stride BBX_TS): an index into the component arrays
+// stage[k * BBX_STAGE_CAP + j] if *staged (CTA-uniform), else a global slot index.
+template<int REC, int NC>
+__device__ __forceinline__ const int *bbx_stage_tile(const DevGrid &g, int n, const int *__restrict__ cell, const int *__restrict__ cell_start,
+        const float4 *__restrict__ src, unsigned char *smem, DevState *st_, bool *staged, const float **stage_out)
+{
+    int *ttab = reinterpret_cast<int *>(smem);             // [0..9] staged offset of each run (exclusive prefix, [9] = total), [10..18] first slot
+    int *sbase = reinterpret_cast<int *>(smem + BBX_STAGE_HDR);
+    float *stage = reinterpret_cast<float *>(smem + BBX_STAGE_HDR + 9 * BBX_TS * 4);
+    const int tid = threadIdx.x, i0 = blockIdx.x * BBX_TS, i = i0 + tid;
+    if(tid < 32){
+        const int lane = tid;
+        const int c_lo = cell[i0], c_hi = cell[min(i0 + BBX_TS, n) - 1];
+        int b = 0, len = 0;
+        if(lane < 9){
+            const int off = (lane / 3 - 1) * g.n[0] + (lane % 3 - 1) * g.plane;
+            const int ca = max(c_lo - 1 + off, 0), cb = min(c_hi + 1 + off, g.total - 1);
+            if(cb >= ca){ b = cell_start[ca]; len = cell_start[cb + 1] - b; }
+        }
+        int inc = len;
+#pragma unroll
+        for(int o = 1; o < 16; o <<= 1){ int y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
+        if(lane < 10) ttab[lane] = inc - len;   // lane 9: len = 0 -> total
+        if(lane < 9) ttab[10 + lane] = b;
+        if(lane == 9 && inc > BBX_STAGE_CAP) atomicAdd(&st_->unstaged_tiles, 1);
+    }
+    int base[9], end[9];
+    if(i < n) bbx_runs(g, cell_start, cell[i], base, end);
+    __syncthreads();
+    const bool st = ttab[9] <= BBX_STAGE_CAP;
+    if(st){
+        // first BBX_TS slots of every run: all loads in flight before the first store
+        float4 v[9][REC];
+#pragma unroll
+        for(int r = 0; r < 9; r++){
+            const int len = ttab[r + 1] - ttab[r];
+            if(tid < len){
+                const float4 *q = src + (ptrdiff_t)(ttab[10 + r] + tid) * REC;
+#pragma unroll
+                for(int h = 0; h < REC; h++) v[r][h] = q[h];
+            }
+        }
+#pragma unroll
+        for(int r = 0; r < 9; r++){
+            const int o = ttab[r], len = ttab[r + 1] - o;
+            if(tid < len){
+#pragma unroll
+                for(int k = 0; k < NC; k++){
+                    const float4 w = v[r][k >> 2];
+                    stage[k * BBX_STAGE_CAP + o + tid] = (k & 3) == 0 ? w.x : ((k & 3) == 1 ? w.y : ((k & 3) == 2 ? w.z : w.w));
+                }
+            }
+        }
+        // the rest of long runs
+        for(int r = 0; r < 9; r++){
+            const int o = ttab[r], len = ttab[r + 1] - o, b = ttab[10 + r];
+            for(int t = tid + BBX_TS; t < len; t += BBX_TS){
+                const float4 *q = src + (ptrdiff_t)(b + t) * REC;
+#pragma unroll
+                for(int h = 0; h < REC; h++){
+                    const float4 w = q[h];
+                    if(4 * h + 0 < NC) stage[(4 * h + 0) * BBX_STAGE_CAP + o + t] = w.x;
+                    if(4 * h + 1 < NC) stage[(4 * h + 1) * BBX_STAGE_CAP + o + t] = w.y;
+                    if(4 * h + 2 < NC) stage[(4 * h + 2) * BBX_STAGE_CAP + o + t] = w.z;
+                    if(4 * h + 3 < NC) stage[(4 * h + 3) * BBX_STAGE_CAP + o + t] = w.w;
+                }
+            }
+        }
+    }
+    if(i < n){
+#pragma unroll
+        for(int r = 0; r < 9; r++) sbase[r * BBX_TS + tid] = st ? base[r] - ttab[10 + r] + ttab[r] : base[r];
+    }
+    __syncthreads();
+    *staged = st; *stage_out = stage;
+    return sbase + tid;
+}
 
 // max over the sub-step of a non-negative float (its bits order like unsigned): warp max first, then one
 // atomic per warp; a partially active warp falls back to one atomic per thread
@@ -407,6 +504,9 @@ __device__ __forceinline__ float bbx_rsqrt_safe(float d2){ return bbx_rsqrt_appr
 // sph_equations3.cpp:80-110), then x* = x + dt (v + dt/m f), collide (restitution 0)
 // (PredictVelocityAndPositionFor with is_first, pcisph_equations3.cpp:3-28).  A particle the FP32
 // pre-check cannot clear of every collider is queued for k_collide_predict.
+// (One thread per particle, neighbours gathered straight from global memory: the shared-memory staging that
+// k_pressure uses was measured SLOWER here -- 7 words per neighbour cost ~19 bank-conflicted wavefronts from
+// shared memory against one LDG.E.256 through L1; profiles/r01_v6_notes.md.)
 __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGrid g, DevState *st, const DevCullSet *__restrict__ cull,
         const float4 *__restrict__ pos, const float4 *__restrict__ vel, const float4 *__restrict__ rec, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
@@ -481,22 +581,29 @@ __global__ void __launch_bounds__(256) k_predict_again(StepParams P, const DevCo
 // rho*_i = m sum_j W_std(|x*_i - x*_j|) over the same list; p += delta (rho* - rho0), negative increments
 // scaled by negativePressureScale (PredictPressureFor, pcisph_equations3.cpp:60-90).
 // Writes posq = (x_i, p_i / rho*_i^2) for the pressure-force sweep.
-__global__ void __launch_bounds__(BBX_BS) k_pressure(StepParams P, DevGrid g, DevState *st, int first,
+extern __shared__ __align__(128) unsigned char bbx_dyn_smem[];
+
+__global__ void __launch_bounds__(BBX_TS) k_pressure(StepParams P, DevGrid g, DevState *st, int first,
         const float4 *__restrict__ pos, const float4 *__restrict__ pred, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
         float *__restrict__ pressure, float *__restrict__ rho_pred, float *__restrict__ rho_err, float4 *__restrict__ posq)
 {
-    BBX_LIST_PROLOGUE();
-    if(!live) return;
-    float4 pi = pred[i];
+    bool staged; const float *S;
+    const int *scol = bbx_stage_tile<1, 3>(g, P.n, cell, cell_start, pred, bbx_dyn_smem, st, &staged, &S);
+    const int i = blockIdx.x * BBX_TS + threadIdx.x;
+    if(i >= P.n) return;
+    const int cnt = nbr_cnt[i];
+    const uint4 *lp = reinterpret_cast<const uint4 *>(nbr) + ((size_t)(i >> 5) * BBX_NBR_CHUNKS) * 32 + (i & 31);
+    const float4 pi = pred[i];
     float sum = 0.f;
-    BBX_LIST_FOREACH(j, {
-        float4 pj = pred[j];
+    auto pair = [&](const float4 pj){
         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
         float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
         float x = fmaxf(0.f, fmaf(-d2, P.inv_h2, 1.f));
         sum = fmaf(x * x, x, sum);
-    })
+    };
+    if(staged) bbx_for_each_neighbor<BBX_TS>(lp, cnt, scol, [&](int j){ const float *q = S + j; pair(make_float4(q[0], q[BBX_STAGE_CAP], q[2 * BBX_STAGE_CAP], 0.f)); });
+    else bbx_for_each_neighbor<BBX_TS>(lp, cnt, scol, [&](int j){ pair(pred[j]); });
     float rho = P.mass * P.w_std_c * sum;
     float err = rho - P.rho0;
     float dp = P.delta * err;
@@ -733,7 +840,7 @@ __global__ void __launch_bounds__(256) k_overwrite(int n, const int *__restrict_
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
-    size_t id = (size_t)pid[i];
+    size_t id = pid ? (size_t)pid[i] : (size_t)i; // pid = null: rows in slot order (bbx_overwrite_owned)
     float p[3], v[3];
     for(int k = 0; k < 3; k++){
         if(is_f64){ p[k] = (float)((const double *)pos)[3 * id + k]; v[k] = (float)((const double *)vel)[3 * id + k]; }

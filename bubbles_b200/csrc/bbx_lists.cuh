@@ -1,26 +1,29 @@
-// bbx list build (phase B, engine v4): per-particle neighbour lists + density, ONE WARP PER OCCUPIED CELL,
-// "transposed": the 32 lanes hold 32 consecutive CANDIDATES of the cell's 27-cell neighbourhood, the loop
-// runs over the cell's own particles (broadcast from shared memory).
+// bbx list build (phase B, engine v6): per-particle neighbour lists + density, ONE WARP PER OCCUPIED CELL,
+// "transposed": the 32 lanes hold 32 consecutive CANDIDATES of the cell's 27-cell neighbourhood, the own
+// particles of the cell are held in REGISTERS, 8 at a time.
 //
-// Why (ncu, profiles/r01_v2_*): with one thread per particle the candidate walk diverges (19 of 32 lanes
-// active) and each lane turns its accept bits into list entries one by one.  Here
-//   * every pair test of a round is one warp-wide instruction stream without divergence,
+// History (ncu, profiles/): one thread per particle diverges on the candidate walk (v2); v4/v5 made the lanes
+// candidates and looped over 16 own particles broadcast from shared memory -- every pair test then started
+// with an LDS.128 whose latency the 4-5 resident warps per scheduler could not hide (issue slots 62 % busy,
+// the rest waiting on the load).  Here
+//   * the cell's candidates are staged ONCE in shared memory in the cell frame: (u_j, list entry) with
+//     u = (x - cell centre) / h -- one coalesced global load and ~40 instructions per candidate per cell;
+//   * a group of 8 own particles lives in registers as (2 u_i, 1 - |u_i|^2); the round loop reads one
+//     candidate per lane (conflict-free LDS.128, fetched one round ahead) and runs 8 pair tests on registers;
+//   * the pair test is x = 1 - d^2 / h^2 = (1 - |u_i|^2) - |u_j|^2 + 2 u_j . u_i : 3 FFMA + 1 FADD; accepted when
+//     x > xacc, and the same x is the density weight (W_std ~ x^3);
 //   * the accept decisions of (round, particle) are ONE ballot; an accepted lane's list position is the
-//     particle's running count + popc(ballot & lanes below) -- no atomics, deterministic flat order,
-//   * candidates are read straight from global memory (coalesced inside a run), one round ahead of use;
-//     the only shared-memory traffic is the broadcast of the own particle and the 2-byte list stores.
-// The pair loop is ~23 instructions per (round, particle): LDS of the particle, 6 FP32 for d^2, compare,
-// ballot, guard-band flag, 7 for the list position / store / count, 4 FP32 for the clamped W_std.
-// (An "expand the ballots afterwards, one lane per particle" variant was measured and is 3x slower in the
-// expansion than these 7 instructions: 12 of 32 lanes active, ~17 instructions per set bit.)
+//     particle's running count + popc(ballot & lanes below) -- no atomics, deterministic flat order.
+// ~17 instructions per (round, particle).
 //
-// Candidates are visited in the flat order run-major / slot order, the same order v2 produced, and lists
-// keep v2's format: entry = (run << 12) | offset-in-run, chunk-transposed per 32 particles (the sweeps'
-// coalesced 512 B loads).  Any neighbourhood size works (no tile to overflow).
+// Candidates are visited in the flat order run-major / slot order and lists keep the format of v2:
+// entry = (run << 12) | offset-in-run, chunk-transposed per 32 particles (the sweeps' coalesced 512 B loads).
+// Neighbourhoods larger than BBX_CMAX candidates are staged in several chunks per group.
 //
-// Exactness: a candidate is accepted when d2 < thr_hi (FP32).  If any accepted candidate of a pass lay
-// inside the guard band [thr_lo, thr_hi] around h^2 - 1e-8, the pass is repeated with the FP64 predicate of
-// the reference (IsWithinStd, kernel.cpp:229-234) deciding the band members -- ~2 % of the passes.
+// Exactness: in the cell frame |u| <= ~2.6, so x carries an absolute error of a few 1e-7.  A candidate is
+// accepted when x > xacc (d^2 certainly below h^2 - 1e-8 + band).  If any accepted candidate of a group lay
+// inside the guard band (x < xband), the group is redone with the FP64 predicate of the reference
+// (IsWithinStd, kernel.cpp:229-234) deciding the band members -- ~1 % of the groups.
 // Reference: Grid::DistributeParticleBucket grid.h:422-447, Bucket::Insert particle.h:44-50 (cap 100),
 // ComputeDensityFor + ComputePressureValue sph_equations3.cpp:7-58.
 #pragma once
@@ -28,9 +31,16 @@
 
 #define BBX_LW 4                  // warps per CTA
 #define BBX_LT (BBX_LW * 32)
-#define BBX_BP 16                 // own particles per pass (density accumulators live in registers)
+#ifndef BBX_G
+#define BBX_G 4                   // own particles per group (registers): 4 or 8
+#endif
+#define BBX_G_SHIFT (BBX_G == 8 ? 2 : 3) // lane >> shift = particle whose density total the lane holds after the butterfly
+#define BBX_CMAX 512              // staged candidates per chunk (multiple of 32)
 #define BBX_ROW 104               // u16 entries per list row in shared memory (13 chunks of 8)
 #define BBX_FULL 0xffffffffu
+#ifndef BBX_LIST_MINB
+#define BBX_LIST_MINB 5           // resident CTAs per SM the list kernel is compiled for
+#endif
 
 // Slow path of one particle whose list would exceed 100 entries: re-walk the 27 cells in the reference's
 // order (y outer, x middle, z inner; chain order inside a cell) and keep the first 100 exactly like
@@ -67,102 +77,137 @@ __device__ __noinline__ void bbx_list_overflow_row(const StepParams &P, const De
 }
 
 struct ListWarp {
-    float4 *spi;             // [BBX_BP] own particles of the pass (unused slots: far away)
-    unsigned short *rows;    // [BBX_BP][BBX_ROW] lists being built
+    float4 *cand;            // [BBX_CMAX + 32] staged candidates (u_j.x, u_j.y, u_j.z, bits of the list entry)
+    float4 *spi;             // [BBX_G] own particles of the group, raw positions (FP64 re-check, cap-100 slow path)
+    unsigned short *rows;    // [BBX_G][BBX_ROW] lists being built
     int *tab;                // [0..9] exclusive prefix of the 9 run lengths (tab[9] = T), [10..18] first slot of each run
-    int *cnt;                // [BBX_BP]
+    int *cnt;                // [BBX_G]
 };
 
-// One pass: all candidates of the cell against up to 16 own particles.  Returns (warp-uniform) whether a
-// provisionally accepted candidate lay inside the guard band.
-template<bool EXACT>
-__device__ __forceinline__ bool bbx_list_pass(const StepParams &P, DevState *st, const ListWarp &W, int T, int mp, int lane,
-        const float4 *__restrict__ pos, float *acc)
+// Stage candidates of the cell's neighbourhood in flat order (run-major, slot order), starting at the cursor
+// (r0, k0), until the 9 runs are consumed (r0 = 9 on return) or BBX_CMAX candidates are staged; returns the
+// number staged (the array is padded to a multiple of 32 with candidates that are never accepted).
+// A candidate farther than h from the cell's box cannot be a neighbour of any particle of the cell and is
+// dropped here (ballot compaction keeps the flat order): ~24 % of the 27-cell neighbourhood.
+// (x - centre) is exact in FP32: both are multiples of the finer ulp and the difference is small.
+__device__ __forceinline__ int bbx_list_stage(const StepParams &P, DevState *st, const ListWarp &W, int lane, int &r0, int &k0,
+        float cx, float cy, float cz, float hx, float hy, float hz, const float4 *__restrict__ pos)
 {
-    bool band = false;
-    const unsigned lt = (1u << lane) - 1u;
-    int cnt[BBX_BP];
-#pragma unroll
-    for(int ii = 0; ii < BBX_BP; ii++){ acc[ii] = 0.f; cnt[ii] = 0; }
-    // candidate of (round 0, this lane), fetched one round ahead of its use
-    int f = lane;
-    float4 pj_next; unsigned short e_next;
-    {
-        const int fc = min(f, T - 1);
-        int r = 0;
-#pragma unroll
-        for(int k = 1; k < 9; k++) r += (fc >= W.tab[k]) ? 1 : 0;
-        const int off = fc - W.tab[r];
-        pj_next = pos[W.tab[10 + r] + off];
-        e_next = (unsigned short)((r << BBX_RUN_SHIFT) | min(off, BBX_MAX_RUN_LEN - 1));
-        if(off >= BBX_MAX_RUN_LEN) st->error = BBX_ERR_CAPACITY;
-        if(f >= T) pj_next.x = 1.0e15f;
-    }
-    {
+    __syncwarp();
+    const unsigned lt = lanemask_lt();
+    int n = 0;
+    int r = r0, k = k0;
 #pragma unroll 1
-        for(int f0 = 0; f0 < T; f0 += 32){
-            const float4 pj = pj_next;
-            const unsigned short entry = e_next;
-            // prefetch the next round's candidate
-            f += 32;
-            if(f - lane < T){
-                const int fc = min(f, T - 1);
-                int r = 0;
+    for(; r < 9; r++, k = 0){
+        const int base = W.tab[10 + r], len = W.tab[r + 1] - W.tab[r];
+        if(len > BBX_MAX_RUN_LEN) st->error = BBX_ERR_CAPACITY;
+        bool full = false;
+#pragma unroll 1
+        for(; k < len; k += 32){
+            if(n >= BBX_CMAX){ full = true; break; }
+            const int kk = k + lane;
+            const float4 raw = pos[base + min(kk, len - 1)];
+            const float ux = (raw.x - cx) * P.inv_h, uy = (raw.y - cy) * P.inv_h, uz = (raw.z - cz) * P.inv_h;
+            const float gx = fmaxf(fabsf(ux) - hx, 0.f), gy = fmaxf(fabsf(uy) - hy, 0.f), gz = fmaxf(fabsf(uz) - hz, 0.f);
+            const bool keep = (kk < len) && (fmaf(gx, gx, fmaf(gy, gy, gz * gz)) < 1.001f);
+            const unsigned msk = __ballot_sync(BBX_FULL, keep);
+            if(keep) W.cand[n + __popc(msk & lt)] = make_float4(ux, uy, uz, __uint_as_float(((unsigned)r << BBX_RUN_SHIFT) | (unsigned)min(kk, BBX_MAX_RUN_LEN - 1)));
+            n += __popc(msk);
+        }
+        if(full) break;
+    }
+    r0 = r; k0 = k;
+    if(n + lane < ((n + 31) & ~31)) W.cand[n + lane] = make_float4(1.0e15f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    return n;
+}
+
+// All staged candidates against the group's (up to 8) own particles in registers.  Accumulates cnt / acc over
+// chunks; xmin = smallest x among this lane's accepted pairs.
+template<bool EXACT>
+__device__ __forceinline__ void bbx_list_rounds(const StepParams &P, const ListWarp &W, int nc, int mg, int lane,
+        const float4 (&q)[BBX_G], const float4 *__restrict__ pos, int (&cnt)[BBX_G], float (&acc)[BBX_G], float &xmin)
+{
+    const unsigned lt = lanemask_lt();
+    // shared-memory byte address of this warp's list rows, pinned in a register (the compiler otherwise
+    // rebuilds it from special registers in front of every store)
+    unsigned rows_addr;
+    asm volatile("mov.u32 %0, %1;" : "=r"(rows_addr) : "r"((unsigned)__cvta_generic_to_shared(W.rows)));
+    float4 cn = W.cand[lane]; // (nc = 0: never used)
+#pragma unroll 1
+    for(int f0 = 0; f0 < nc; f0 += 32){
+        const float4 cj = cn;
+        if(f0 + 32 < nc) cn = W.cand[f0 + 32 + lane];
+        const float a = fmaf(cj.x, cj.x, fmaf(cj.y, cj.y, cj.z * cj.z));
+        const unsigned short entry = (unsigned short)__float_as_uint(cj.w);
 #pragma unroll
-                for(int k = 1; k < 9; k++) r += (fc >= W.tab[k]) ? 1 : 0;
-                const int off = fc - W.tab[r];
-                pj_next = pos[W.tab[10 + r] + off];
-                e_next = (unsigned short)((r << BBX_RUN_SHIFT) | min(off, BBX_MAX_RUN_LEN - 1));
-                if(off >= BBX_MAX_RUN_LEN) st->error = BBX_ERR_CAPACITY;
-                if(f >= T) pj_next.x = 1.0e15f;
-            }
+        for(int h = 0; h < BBX_G / 4; h++){
+            if(h * 4 < mg){
 #pragma unroll
-            for(int g4 = 0; g4 < BBX_BP / 4; g4++){
-                if(g4 * 4 < mp){
-#pragma unroll
-                    for(int q = 0; q < 4; q++){
-                        const int ii = g4 * 4 + q;
-                        const float4 pi = W.spi[ii];
-                        const float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-                        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                        bool in = d2 < P.thr_hi;
-                        if(EXACT){
-                            if(in && d2 >= P.thr_lo) in = bbx_within_std_exact(pi, pj, P.h2_d);
-                        }else{
-                            band |= in && (d2 >= P.thr_lo);
+                for(int t = 0; t < 4; t++){
+                    const int ii = h * 4 + t;
+                    const float x = fmaf(cj.x, q[ii].x, fmaf(cj.y, q[ii].y, fmaf(cj.z, q[ii].z, q[ii].w))) - a;
+                    bool in = x > P.xacc;
+                    if(EXACT){
+                        if(in && x < P.xband){
+                            const unsigned e = entry;
+                            in = bbx_within_std_exact(W.spi[ii], pos[W.tab[10 + (e >> BBX_RUN_SHIFT)] + (int)(e & BBX_RUN_MASK)], P.h2_d);
                         }
-                        const unsigned msk = __ballot_sync(BBX_FULL, in);
-                        // list position = entries so far + accepted lanes below this one (flat order); rows have
-                        // 104 slots, the count keeps running so that the cap-100 slow path can be detected
-                        const int k = min(cnt[ii] + __popc(msk & lt), BBX_ROW - 1);
-                        if(in) W.rows[ii * BBX_ROW + k] = entry;
-                        cnt[ii] += __popc(msk);
-                        const float x = fmaxf(0.f, fmaf(-d2, P.inv_h2, 1.f));
-                        acc[ii] = fmaf(x * x, x, acc[ii]);
+                    }else{
+                        xmin = in ? fminf(xmin, x) : xmin;
                     }
+                    const unsigned msk = __ballot_sync(BBX_FULL, in);
+                    // list position = entries so far + accepted lanes below this one (flat order); rows have
+                    // 104 slots, the count keeps running so that the cap-100 slow path can be detected
+                    const int k = min(cnt[ii] + __popc(msk & lt), BBX_ROW - 1);
+                    if(in) asm volatile("st.shared.u16 [%0], %1;" :: "r"(rows_addr + (unsigned)(ii * BBX_ROW * 2) + 2u * (unsigned)k), "h"(entry) : "memory");
+                    cnt[ii] += __popc(msk);
+                    const float x2 = x * x;
+                    acc[ii] = in ? fmaf(x2, x, acc[ii]) : acc[ii];
                 }
             }
         }
     }
+}
+
+// One group: every chunk of the neighbourhood against the group's particles (nc >= 0: the whole neighbourhood
+// is staged already, nc candidates).  Returns (warp-uniform) whether a provisionally accepted candidate lay
+// inside the guard band.
+template<bool EXACT>
+__device__ __forceinline__ bool bbx_list_group(const StepParams &P, DevState *st, const ListWarp &W, int nc, int mg, int lane,
+        float cx, float cy, float cz, float hx, float hy, float hz, const float4 (&q)[BBX_G], const float4 *__restrict__ pos,
+        int (&cnt)[BBX_G], float (&acc)[BBX_G])
+{
 #pragma unroll
-    for(int ii = 0; ii < BBX_BP; ii++) if(lane == ii) W.cnt[ii] = cnt[ii];
-    __syncwarp();
-    return __any_sync(BBX_FULL, band);
+    for(int ii = 0; ii < BBX_G; ii++){ acc[ii] = 0.f; cnt[ii] = 0; }
+    float xmin = 1.0e30f;
+    if(nc >= 0){
+        bbx_list_rounds<EXACT>(P, W, nc, mg, lane, q, pos, cnt, acc, xmin);
+    }else{
+        int r0 = 0, k0 = 0;
+#pragma unroll 1
+        while(r0 < 9){
+            const int n = bbx_list_stage(P, st, W, lane, r0, k0, cx, cy, cz, hx, hy, hz, pos);
+            bbx_list_rounds<EXACT>(P, W, n, mg, lane, q, pos, cnt, acc, xmin);
+        }
+    }
+    return __any_sync(BBX_FULL, xmin < P.xband);
 }
 
 template<int SPH_EOS>
-__global__ void __launch_bounds__(BBX_LT) k_cell_lists_density(StepParams P, DevGrid g, DevState *st, const int *__restrict__ occ_cells,
+__global__ void __launch_bounds__(BBX_LT, BBX_LIST_MINB) k_cell_lists_density(StepParams P, DevGrid g, DevState *st, const int *__restrict__ occ_cells,
         const float4 *__restrict__ pos, float4 *__restrict__ vel, const int *__restrict__ cell_start,
         unsigned short *__restrict__ nbr, int *__restrict__ nbr_cnt, float *__restrict__ pressure, float4 *__restrict__ posq,
         float4 *__restrict__ rec)
 {
-    __shared__ float4 s_pi[BBX_LW][BBX_BP];
-    __shared__ __align__(16) unsigned short s_rows[BBX_LW][BBX_BP * BBX_ROW];
+    __shared__ float4 s_cand[BBX_LW][BBX_CMAX + 32];
+    __shared__ float4 s_pi[BBX_LW][BBX_G];
+    __shared__ __align__(16) unsigned short s_rows[BBX_LW][BBX_G * BBX_ROW];
     __shared__ int s_tab[BBX_LW][20];
-    __shared__ int s_cnt[BBX_LW][BBX_BP];
-    __shared__ float s_ovs[BBX_LW][BBX_BP];
+    __shared__ int s_cnt[BBX_LW][BBX_G];
+    __shared__ float s_ovs[BBX_LW][BBX_G];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    ListWarp W; W.spi = s_pi[warp]; W.rows = s_rows[warp]; W.tab = s_tab[warp]; W.cnt = s_cnt[warp];
+    ListWarp W; W.cand = s_cand[warp]; W.spi = s_pi[warp]; W.rows = s_rows[warp]; W.tab = s_tab[warp]; W.cnt = s_cnt[warp];
     float *sovs = s_ovs[warp];
     const int n_occ = st->n_occ;
     const int nwarps = gridDim.x * BBX_LW;
@@ -171,9 +216,12 @@ __global__ void __launch_bounds__(BBX_LT) k_cell_lists_density(StepParams P, Dev
         const int c = occ_cells[w];
         // run table: run r = (dy + 1) * 3 + (dz + 1) covers cells (cx-1..cx+1, cy+dy, cz+dz), contiguous slots
         int T;
+        float ccx, ccy, ccz; // cell centre: origin of the cell frame of the pair test
         {
             int cz = c / g.plane; int rem = c - cz * g.plane; int cy = rem / g.n[0]; int cx = rem - cy * g.n[0];
             int xlo = max(cx - 1, 0), xhi = min(cx + 1, g.n[0] - 1);
+            ccx = g.minf[0] + ((float)cx + 0.5f) * g.lenf[0]; ccy = g.minf[1] + ((float)cy + 0.5f) * g.lenf[1];
+            ccz = g.minf[2] + ((float)(cz + g.zoff) + 0.5f) * g.lenf[2];
             int b = 0, len = 0;
             if(lane < 9){
                 int y = cy + lane / 3 - 1, z = cz + lane % 3 - 1;
@@ -194,19 +242,41 @@ __global__ void __launch_bounds__(BBX_LT) k_cell_lists_density(StepParams P, Dev
         }
         const int s0 = cell_start[c], m = cell_start[c + 1] - s0;
         if(lane == 0 && T > st->max_candidates) atomicMax(&st->max_candidates, T);
+        // half extents of the cell in the cell frame (culling of the staged candidates)
+        const float hx = 0.5f * g.lenf[0] * P.inv_h, hy = 0.5f * g.lenf[1] * P.inv_h, hz = 0.5f * g.lenf[2] * P.inv_h;
+        int nc = -1; // >= 0: the whole neighbourhood fits one stage, done once per cell
+        if(T <= BBX_CMAX){ int r0 = 0, k0 = 0; nc = bbx_list_stage(P, st, W, lane, r0, k0, ccx, ccy, ccz, hx, hy, hz, pos); }
 #pragma unroll 1
-        for(int p0 = 0; p0 < m; p0 += BBX_BP){
-            const int mp = min(BBX_BP, m - p0);
-            __syncwarp();
-            if(lane < BBX_BP) W.spi[lane] = lane < mp ? pos[s0 + p0 + lane] : make_float4(-1.0e15f, -1.0e15f, -1.0e15f, 0.f);
-            __syncwarp();
-            float acc[BBX_BP];
-            if(bbx_list_pass<false>(P, st, W, T, mp, lane, pos, acc)){
-                if(lane == 0) atomicAdd(&st->exact_passes, 1);
-                bbx_list_pass<true>(P, st, W, T, mp, lane, pos, acc);
+        for(int p0 = 0; p0 < m; p0 += BBX_G){
+            const int mg = min(BBX_G, m - p0);
+            // the group's particles: raw positions to shared memory (slow paths), cell-frame form to registers
+            float4 q[BBX_G];
+            {
+                float4 pr = make_float4(0.f, 0.f, 0.f, 0.f), pq = make_float4(0.f, 0.f, 0.f, -1.0e30f); // unused slots accept nothing
+                if(lane < mg){
+                    pr = pos[s0 + p0 + lane];
+                    const float ux = (pr.x - ccx) * P.inv_h, uy = (pr.y - ccy) * P.inv_h, uz = (pr.z - ccz) * P.inv_h;
+                    pq = make_float4(2.f * ux, 2.f * uy, 2.f * uz, 1.f - fmaf(ux, ux, fmaf(uy, uy, uz * uz)));
+                }
+                __syncwarp();
+                if(lane < BBX_G) W.spi[lane] = pr;
+#pragma unroll
+                for(int ii = 0; ii < BBX_G; ii++){
+                    q[ii].x = __shfl_sync(BBX_FULL, pq.x, ii); q[ii].y = __shfl_sync(BBX_FULL, pq.y, ii);
+                    q[ii].z = __shfl_sync(BBX_FULL, pq.z, ii); q[ii].w = __shfl_sync(BBX_FULL, pq.w, ii);
+                }
+                __syncwarp();
             }
+            int cnt[BBX_G]; float acc[BBX_G];
+            if(bbx_list_group<false>(P, st, W, nc, mg, lane, ccx, ccy, ccz, hx, hy, hz, q, pos, cnt, acc)){
+                if(lane == 0) atomicAdd(&st->exact_passes, 1);
+                bbx_list_group<true>(P, st, W, nc, mg, lane, ccx, ccy, ccz, hx, hy, hz, q, pos, cnt, acc);
+            }
+#pragma unroll
+            for(int ii = 0; ii < BBX_G; ii++) if(lane == ii) W.cnt[ii] = cnt[ii];
+            __syncwarp();
             // cap-100 slow path: lane ii redoes particle ii in the reference's order
-            if(lane < mp){
+            if(lane < mg){
                 int cn = W.cnt[lane]; float sm = 0.f;
                 if(cn > BBX_MAX_NEIGHBORS){
                     bbx_list_overflow_row(P, g, st, pos, cell_start, W.rows + lane * BBX_ROW, c, W.spi[lane], &cn, &sm);
@@ -214,35 +284,26 @@ __global__ void __launch_bounds__(BBX_LT) k_cell_lists_density(StepParams P, Dev
                 }
                 W.cnt[lane] = cn; sovs[lane] = sm;
             }
-            // sum the 16 accumulators over the 32 lanes (butterfly that halves the live values per step):
-            // afterwards lane l holds the total of particle (l >> 1) & 15
-#pragma unroll
-            for(int k = 0; k < 8; k++){
-                const bool up = lane & 16;
-                const float send = up ? acc[k] : acc[k + 8], keep = up ? acc[k + 8] : acc[k];
-                acc[k] = keep + __shfl_xor_sync(BBX_FULL, send, 16);
-            }
-#pragma unroll
-            for(int k = 0; k < 4; k++){
-                const bool up = lane & 8;
-                const float send = up ? acc[k] : acc[k + 4], keep = up ? acc[k + 4] : acc[k];
-                acc[k] = keep + __shfl_xor_sync(BBX_FULL, send, 8);
-            }
-#pragma unroll
-            for(int k = 0; k < 2; k++){
-                const bool up = lane & 4;
-                const float send = up ? acc[k] : acc[k + 2], keep = up ? acc[k + 2] : acc[k];
-                acc[k] = keep + __shfl_xor_sync(BBX_FULL, send, 4);
-            }
+            // sum the BBX_G accumulators over the 32 lanes (butterfly that halves the live values per step):
+            // afterwards lane l holds the total of particle (l >> BBX_G_SHIFT) & (BBX_G - 1)
             {
-                const bool up = lane & 2;
-                const float send = up ? acc[0] : acc[1], keep = up ? acc[1] : acc[0];
-                acc[0] = keep + __shfl_xor_sync(BBX_FULL, send, 2);
+                int bit = 16;
+#pragma unroll
+                for(int half = BBX_G / 2; half >= 1; half >>= 1){
+                    const bool up = lane & bit;
+#pragma unroll
+                    for(int k = 0; k < half; k++){
+                        const float send = up ? acc[k] : acc[k + half], keep = up ? acc[k + half] : acc[k];
+                        acc[k] = keep + __shfl_xor_sync(BBX_FULL, send, bit);
+                    }
+                    bit >>= 1;
+                }
+#pragma unroll
+                for(; bit >= 1; bit >>= 1) acc[0] += __shfl_xor_sync(BBX_FULL, acc[0], bit);
             }
-            acc[0] += __shfl_xor_sync(BBX_FULL, acc[0], 1);
             __syncwarp();
-            const int idx = (lane >> 1) & 15;
-            if(!(lane & 1) && idx < mp){
+            const int idx = (lane >> BBX_G_SHIFT) & (BBX_G - 1);
+            if(!(lane & ((1 << BBX_G_SHIFT) - 1)) && idx < mg){
                 const int i = s0 + p0 + idx;
                 int cn = W.cnt[idx]; float sum = acc[0];
                 if(cn < 0){ cn = -cn; sum = sovs[idx]; }
@@ -261,12 +322,12 @@ __global__ void __launch_bounds__(BBX_LT) k_cell_lists_density(StepParams P, Dev
                     posq[i] = make_float4(pi.x, pi.y, pi.z, p / (rho * rho));
                 }
             }
-            // lists of the pass: shared rows -> global, chunk-transposed (chunk ch of particle i is the uint4
+            // lists of the group: shared rows -> global, chunk-transposed (chunk ch of particle i is the uint4
             // ((i >> 5) * 13 + ch) * 32 + (i & 31)): consecutive lanes = consecutive particles of one chunk
             const uint4 *sl = reinterpret_cast<const uint4 *>(W.rows);
             uint4 *gl = reinterpret_cast<uint4 *>(nbr);
-            for(int t = lane; t < mp * BBX_NBR_CHUNKS; t += 32){
-                const int ch = t / mp, ii = t - ch * mp;
+            for(int t = lane; t < mg * BBX_NBR_CHUNKS; t += 32){
+                const int ch = t / mg, ii = t - ch * mg;
                 if(ch * 8 < abs(W.cnt[ii])){
                     const int i = s0 + p0 + ii;
                     gl[((size_t)(i >> 5) * BBX_NBR_CHUNKS + ch) * 32 + (i & 31)] = sl[ii * BBX_NBR_CHUNKS + ch];

@@ -215,6 +215,12 @@ class Engine:
         vel = np.ascontiguousarray(vel, dtype=pos.dtype)
         _check(self.lib.bbx_overwrite_state(self.h, pos.ctypes.data, vel.ctypes.data, dt))
 
+    def overwrite_owned(self, pos, vel):
+        """Overwrite the owned particles, rows in the order of the last download_owned (collective on slabs)."""
+        pos, dt = self._arr(pos)
+        vel = np.ascontiguousarray(vel, dtype=pos.dtype)
+        _check(self.lib.bbx_overwrite_owned(self.h, pos.ctypes.data, vel.ctypes.data, dt))
+
     @property
     def n(self):
         n = C.c_int()

@@ -152,7 +152,7 @@ typedef struct bbx_step_stats {
     int exact_passes;         /* list-build passes redone with the FP64 IsWithinStd predicate  */
     int max_candidates;       /* largest 27-cell neighbourhood of the last list build          */
     int occupied_cells;       /* occupied (owned) cells of the last grid update                */
-    int reserved;
+    int unstaged_tiles;       /* sweep tiles of the last sub-step whose neighbourhood did not fit in shared memory */
 } bbx_step_stats;
 
 typedef struct bbx_engine bbx_engine;
@@ -188,6 +188,10 @@ int bbx_append_particles(bbx_engine *e, int n, const void *pos, const void *vel,
 int bbx_particle_count(bbx_engine *e, int *n);
 /* overwrite positions+velocities of the existing particles (id order) without touching chains */
 int bbx_overwrite_state(bbx_engine *e, const void *pos, const void *vel, int dtype);
+/* slab engines (works on any engine): the same for the OWNED particles, rows in the order of the last
+ * bbx_download_owned (the engine's cell order); the neighbours' ghost copies of the boundary planes are
+ * refreshed, so the call is collective over the slab group.                                            */
+int bbx_overwrite_owned(bbx_engine *e, const void *pos, const void *vel, int dtype);
 
 /* -- colliders --------------------------------------------------------------------------------- */
 int bbx_set_colliders(bbx_engine *e, int n, const bbx_collider *colliders);

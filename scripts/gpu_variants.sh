@@ -1,0 +1,14 @@
+#!/usr/bin/env bash
+# A/B on the GPU box: one short bench per variant library in bubbles_b200/lib/variants (phase times only)
+set -uo pipefail
+mkdir -p gpurun_out
+for so in "$@"; do
+  BBX_LIB=$PWD/bubbles_b200/lib/variants/libbbx_${so}.so timeout 300 python bench.py --steps 30 --warmup 10 --no-cpu-baseline --e2e-steps 2 2>&1 | tail -1 > gpurun_out/var_${so}.json
+  python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/var_${so}.json")); print("${so}", round(d["ms_per_step"],4), {k: round(v,4) for k,v in d["roofline"]["phases_ms_per_step"].items()}, d["stats"]["exact_passes"], d["stats"].get("unstaged_tiles"))
+except Exception as ex:
+    print("${so} FAILED", ex, open("gpurun_out/var_${so}.json").read()[-500:])
+PY
+done

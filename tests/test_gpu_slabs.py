@@ -171,3 +171,43 @@ def test_slab_with_empty_rank_and_collider_in_ghost_zone():
     assert np.array_equal(grp.download(bb.POSITION, np.float32), one.download(bb.POSITION, np.float32))
     assert np.array_equal(grp.download(bb.VELOCITY, np.float32), one.download(bb.VELOCITY, np.float32))
     grp.close()
+
+
+def test_slab_overwrite_owned_round_trip():
+    """Host run loop on slabs (bench.py's e2e leg): download the owned particles, hand the same rows back with
+    bbx_overwrite_owned, step -- must stay bit-identical to the uninterrupted single-domain run; and a change
+    made on the host must reach the neighbour's ghost plane."""
+    sc = _moving_scene()
+    one = _single(sc)
+    grp, zb = _group(sc, 3)
+    grp.set_particles(sc["pos"], sc["vel"])
+    dt = sc["dt"]
+    for step in range(12):
+        one.step_pcisph(dt)
+
+        def io(e, r):
+            ids, p = e.download_owned(bb.POSITION, np.float32)
+            _, v = e.download_owned(bb.VELOCITY, np.float32)
+            if len(ids) == 0:
+                p = np.zeros((0, 3), np.float32); v = np.zeros((0, 3), np.float32)
+            e.overwrite_owned(p, v)
+            e.step_pcisph(dt)
+        grp.each(io)
+    assert np.array_equal(grp.download(bb.POSITION, np.float32), one.download(bb.POSITION, np.float32))
+    assert np.array_equal(grp.download(bb.VELOCITY, np.float32), one.download(bb.VELOCITY, np.float32))
+    # a host-side edit (every velocity zeroed) must act on both sides of the cuts: same as the single domain
+    p1 = one.download(bb.POSITION, np.float32)
+    one.overwrite_state(p1, np.zeros_like(p1))
+
+    def zero(e, r):
+        ids, p = e.download_owned(bb.POSITION, np.float32)
+        if len(ids) == 0:
+            p = np.zeros((0, 3), np.float32)
+        e.overwrite_owned(p, np.zeros_like(p))
+    grp.each(zero)
+    for _ in range(5):
+        one.step_pcisph(dt)
+        grp.step_pcisph(dt)
+    assert np.array_equal(grp.download(bb.POSITION, np.float32), one.download(bb.POSITION, np.float32))
+    assert np.array_equal(grp.download(bb.VELOCITY, np.float32), one.download(bb.VELOCITY, np.float32))
+    grp.close()
