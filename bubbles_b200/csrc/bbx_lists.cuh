@@ -35,7 +35,9 @@
 #define BBX_G 4                   // own particles per group (registers): 4 or 8
 #endif
 #define BBX_G_SHIFT (BBX_G == 8 ? 2 : 3) // lane >> shift = particle whose density total the lane holds after the butterfly
+#ifndef BBX_CMAX
 #define BBX_CMAX 512              // staged candidates per chunk (multiple of 32)
+#endif
 #define BBX_ROW 104               // u16 entries per list row in shared memory (13 chunks of 8)
 #define BBX_FULL 0xffffffffu
 #ifndef BBX_LIST_MINB
@@ -84,39 +86,50 @@ struct ListWarp {
     int *cnt;                // [BBX_G]
 };
 
-// Stage candidates of the cell's neighbourhood in flat order (run-major, slot order), starting at the cursor
-// (r0, k0), until the 9 runs are consumed (r0 = 9 on return) or BBX_CMAX candidates are staged; returns the
-// number staged (the array is padded to a multiple of 32 with candidates that are never accepted).
+// Candidate of flat index f (clamped to T - 1) of the cell's neighbourhood: raw position and list entry.
+struct ListFetch { float4 raw; unsigned entry; };
+__device__ __forceinline__ ListFetch bbx_list_fetch(DevState *st, const ListWarp &W, int T, int f, const float4 *__restrict__ pos){
+    ListFetch c;
+    const int fc = min(f, T - 1);
+    int r = 0;
+#pragma unroll
+    for(int q = 1; q < 9; q++) r += (fc >= W.tab[q]) ? 1 : 0;
+    const int off = fc - W.tab[r];
+    c.raw = pos[W.tab[10 + r] + off];
+    c.entry = ((unsigned)r << BBX_RUN_SHIFT) | (unsigned)min(off, BBX_MAX_RUN_LEN - 1);
+    if(off >= BBX_MAX_RUN_LEN) st->error = BBX_ERR_CAPACITY;
+    return c;
+}
+
+// Stage candidates of the cell's neighbourhood in flat order (run-major, slot order), starting at flat index
+// f0, until all T are consumed (f0 = T on return) or BBX_CMAX candidates are staged; returns the number staged
+// (the array is padded to a multiple of 32 with candidates that are never accepted).  Loads run two rounds
+// ahead of their use.
 // A candidate farther than h from the cell's box cannot be a neighbour of any particle of the cell and is
 // dropped here (ballot compaction keeps the flat order): ~24 % of the 27-cell neighbourhood.
 // (x - centre) is exact in FP32: both are multiples of the finer ulp and the difference is small.
-__device__ __forceinline__ int bbx_list_stage(const StepParams &P, DevState *st, const ListWarp &W, int lane, int &r0, int &k0,
+__device__ __forceinline__ int bbx_list_stage(const StepParams &P, DevState *st, const ListWarp &W, int T, int lane, int &f0,
         float cx, float cy, float cz, float hx, float hy, float hz, const float4 *__restrict__ pos)
 {
     __syncwarp();
     const unsigned lt = lanemask_lt();
     int n = 0;
-    int r = r0, k = k0;
+    int f = f0;
+    ListFetch a = bbx_list_fetch(st, W, T, f + lane, pos), b = a;
+    if(f + 32 < T) b = bbx_list_fetch(st, W, T, f + 32 + lane, pos);
 #pragma unroll 1
-    for(; r < 9; r++, k = 0){
-        const int base = W.tab[10 + r], len = W.tab[r + 1] - W.tab[r];
-        if(len > BBX_MAX_RUN_LEN) st->error = BBX_ERR_CAPACITY;
-        bool full = false;
-#pragma unroll 1
-        for(; k < len; k += 32){
-            if(n >= BBX_CMAX){ full = true; break; }
-            const int kk = k + lane;
-            const float4 raw = pos[base + min(kk, len - 1)];
-            const float ux = (raw.x - cx) * P.inv_h, uy = (raw.y - cy) * P.inv_h, uz = (raw.z - cz) * P.inv_h;
-            const float gx = fmaxf(fabsf(ux) - hx, 0.f), gy = fmaxf(fabsf(uy) - hy, 0.f), gz = fmaxf(fabsf(uz) - hz, 0.f);
-            const bool keep = (kk < len) && (fmaf(gx, gx, fmaf(gy, gy, gz * gz)) < 1.001f);
-            const unsigned msk = __ballot_sync(BBX_FULL, keep);
-            if(keep) W.cand[n + __popc(msk & lt)] = make_float4(ux, uy, uz, __uint_as_float(((unsigned)r << BBX_RUN_SHIFT) | (unsigned)min(kk, BBX_MAX_RUN_LEN - 1)));
-            n += __popc(msk);
-        }
-        if(full) break;
+    for(; f < T && n < BBX_CMAX; f += 32){
+        const ListFetch c = a;
+        a = b;
+        if(f + 64 < T) b = bbx_list_fetch(st, W, T, f + 64 + lane, pos);
+        const float ux = (c.raw.x - cx) * P.inv_h, uy = (c.raw.y - cy) * P.inv_h, uz = (c.raw.z - cz) * P.inv_h;
+        const float gx = fmaxf(fabsf(ux) - hx, 0.f), gy = fmaxf(fabsf(uy) - hy, 0.f), gz = fmaxf(fabsf(uz) - hz, 0.f);
+        const bool keep = (f + lane < T) && (fmaf(gx, gx, fmaf(gy, gy, gz * gz)) < 1.001f);
+        const unsigned msk = __ballot_sync(BBX_FULL, keep);
+        if(keep) W.cand[n + __popc(msk & lt)] = make_float4(ux, uy, uz, __uint_as_float(c.entry));
+        n += __popc(msk);
     }
-    r0 = r; k0 = k;
+    f0 = min(f, T);
     if(n + lane < ((n + 31) & ~31)) W.cand[n + lane] = make_float4(1.0e15f, 0.f, 0.f, 0.f);
     __syncwarp();
     return n;
@@ -174,7 +187,7 @@ __device__ __forceinline__ void bbx_list_rounds(const StepParams &P, const ListW
 // is staged already, nc candidates).  Returns (warp-uniform) whether a provisionally accepted candidate lay
 // inside the guard band.
 template<bool EXACT>
-__device__ __forceinline__ bool bbx_list_group(const StepParams &P, DevState *st, const ListWarp &W, int nc, int mg, int lane,
+__device__ __forceinline__ bool bbx_list_group(const StepParams &P, DevState *st, const ListWarp &W, int T, int nc, int mg, int lane,
         float cx, float cy, float cz, float hx, float hy, float hz, const float4 (&q)[BBX_G], const float4 *__restrict__ pos,
         int (&cnt)[BBX_G], float (&acc)[BBX_G])
 {
@@ -184,10 +197,10 @@ __device__ __forceinline__ bool bbx_list_group(const StepParams &P, DevState *st
     if(nc >= 0){
         bbx_list_rounds<EXACT>(P, W, nc, mg, lane, q, pos, cnt, acc, xmin);
     }else{
-        int r0 = 0, k0 = 0;
+        int f0 = 0;
 #pragma unroll 1
-        while(r0 < 9){
-            const int n = bbx_list_stage(P, st, W, lane, r0, k0, cx, cy, cz, hx, hy, hz, pos);
+        while(f0 < T){
+            const int n = bbx_list_stage(P, st, W, T, lane, f0, cx, cy, cz, hx, hy, hz, pos);
             bbx_list_rounds<EXACT>(P, W, n, mg, lane, q, pos, cnt, acc, xmin);
         }
     }
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(BBX_LT, BBX_LIST_MINB) k_cell_lists_density(St
         // half extents of the cell in the cell frame (culling of the staged candidates)
         const float hx = 0.5f * g.lenf[0] * P.inv_h, hy = 0.5f * g.lenf[1] * P.inv_h, hz = 0.5f * g.lenf[2] * P.inv_h;
         int nc = -1; // >= 0: the whole neighbourhood fits one stage, done once per cell
-        if(T <= BBX_CMAX){ int r0 = 0, k0 = 0; nc = bbx_list_stage(P, st, W, lane, r0, k0, ccx, ccy, ccz, hx, hy, hz, pos); }
+        if(T <= BBX_CMAX){ int f0 = 0; nc = bbx_list_stage(P, st, W, T, lane, f0, ccx, ccy, ccz, hx, hy, hz, pos); }
 #pragma unroll 1
         for(int p0 = 0; p0 < m; p0 += BBX_G){
             const int mg = min(BBX_G, m - p0);
@@ -268,9 +281,9 @@ __global__ void __launch_bounds__(BBX_LT, BBX_LIST_MINB) k_cell_lists_density(St
                 __syncwarp();
             }
             int cnt[BBX_G]; float acc[BBX_G];
-            if(bbx_list_group<false>(P, st, W, nc, mg, lane, ccx, ccy, ccz, hx, hy, hz, q, pos, cnt, acc)){
+            if(bbx_list_group<false>(P, st, W, T, nc, mg, lane, ccx, ccy, ccz, hx, hy, hz, q, pos, cnt, acc)){
                 if(lane == 0) atomicAdd(&st->exact_passes, 1);
-                bbx_list_group<true>(P, st, W, nc, mg, lane, ccx, ccy, ccz, hx, hy, hz, q, pos, cnt, acc);
+                bbx_list_group<true>(P, st, W, T, nc, mg, lane, ccx, ccy, ccz, hx, hy, hz, q, pos, cnt, acc);
             }
 #pragma unroll
             for(int ii = 0; ii < BBX_G; ii++) if(lane == ii) W.cnt[ii] = cnt[ii];
@@ -326,11 +339,12 @@ __global__ void __launch_bounds__(BBX_LT, BBX_LIST_MINB) k_cell_lists_density(St
             // ((i >> 5) * 13 + ch) * 32 + (i & 31)): consecutive lanes = consecutive particles of one chunk
             const uint4 *sl = reinterpret_cast<const uint4 *>(W.rows);
             uint4 *gl = reinterpret_cast<uint4 *>(nbr);
-            for(int t = lane; t < mg * BBX_NBR_CHUNKS; t += 32){
-                const int ch = t / mg, ii = t - ch * mg;
-                if(ch * 8 < abs(W.cnt[ii])){
-                    const int i = s0 + p0 + ii;
-                    gl[((size_t)(i >> 5) * BBX_NBR_CHUNKS + ch) * 32 + (i & 31)] = sl[ii * BBX_NBR_CHUNKS + ch];
+            {
+                const int ii = lane & (BBX_G - 1);
+                if(ii < mg){
+                    const int i = s0 + p0 + ii, full = abs(W.cnt[ii]);
+                    uint4 *dst = gl + ((size_t)(i >> 5) * BBX_NBR_CHUNKS) * 32 + (i & 31);
+                    for(int ch = lane / BBX_G; ch * 8 < full; ch += 32 / BBX_G) dst[(size_t)ch * 32] = sl[ii * BBX_NBR_CHUNKS + ch];
                 }
             }
         }
