@@ -374,6 +374,8 @@ def main():
                                    + (f", {world} z-slabs with NCCL ghost-plane exchange and migration" if world > 1 else ""),
                        "particles_per_gpu": n, "particles": n_global, "cells": cells, "dt": dt,
                        "parallelism": f"slab{world}" if world > 1 else "single",
+                       "halo": ("stores into the neighbours' ghost slots from inside the sweeps (CUDA IPC peer memory over NVLink) + NCCL for the grid phase"
+                                if eng.p2p else "NCCL send/recv per phase") if world > 1 else None,
                        "l2_policy": f"working set {state_bytes / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
                        "timing": "CUDA events on the engine stream between kernels, summed over phases, max over ranks",
                        "wall_ms_per_step": wall_ms},

@@ -4,7 +4,11 @@
 // NCCL/MPI); this layer is new.  A slab engine talks to rank-1 ("lo", smaller z) and rank+1 ("hi"):
 //   exchange()          contiguous device ranges to / from the two neighbours (ghost planes, migrants)
 //   allreduce_max_u32() global flags / maxima (big-move rule, CFL force maximum, density error)
-//   neighbor_counts()   two host integers to / from each neighbour (sizes of the next exchange)
+//   neighbor_counts()   host integers to / from each neighbour (sizes of the next exchange, owned counts)
+//   share_arrays()      once, after the communicator is up: the neighbours' device pointers to the arrays
+//                       that carry ghost slots (CUDA IPC between processes, plain pointers in-process), so
+//                       that the sweeps can store boundary-plane results straight into the neighbour's ghost
+//                       slots over NVLink instead of a send / recv pair per phase
 // Two implementations:
 //   NcclComm   one process per GPU, ncclSend/ncclRecv groups over NVLink (libnccl is dlopen'ed so that
 //              the single-GPU library has no link-time dependency on it)
@@ -26,6 +30,10 @@
 struct BbxSeg { void *ptr; size_t bytes; };
 #define BBX_MAX_SEGS 8
 #define BBX_LOCAL_MAX_RANKS 64
+#define BBX_PEER_NPTR 11  // pos[2], vel[2], rec, pred, posq, halo flags + mailbox, pid[2], ghost cell-table slices
+#define BBX_NCOUNTS 2     // integers per neighbour in neighbor_counts: boundary-plane particles, owned particles
+// allocation bases of the arrays a neighbour may write into, and the ghost slots in front of slot 0
+struct BbxPeerArrays { void *p[BBX_PEER_NPTR]; long long gc; };
 
 struct BbxComm {
     int rank = 0, nranks = 1;
@@ -37,8 +45,11 @@ struct BbxComm {
     virtual int exchange(cudaStream_t s, const BbxSeg *send_lo, const BbxSeg *recv_lo, int n_lo,
                          const BbxSeg *send_hi, const BbxSeg *recv_hi, int n_hi) = 0;
     virtual int allreduce_max_u32(cudaStream_t s, unsigned *dev, int count) = 0;
-    // returns with the host values filled in (synchronises the stream)
-    virtual int neighbor_counts(cudaStream_t s, int to_lo, int to_hi, int *from_lo, int *from_hi) = 0;
+    // returns with the host values filled in (synchronises the stream); BBX_NCOUNTS integers each
+    virtual int neighbor_counts(cudaStream_t s, const int *to_lo, const int *to_hi, int *from_lo, int *from_hi) = 0;
+    // *ok = 1: lo / hi hold pointers valid on THIS device / in THIS process for the neighbours' arrays
+    // (a missing neighbour's entry is zeroed); *ok = 0 on every rank if any rank cannot map its neighbours
+    virtual int share_arrays(cudaStream_t s, const BbxPeerArrays &mine, int want, BbxPeerArrays *lo, BbxPeerArrays *hi, int *ok) = 0;
     virtual int barrier() = 0;
 };
 
@@ -83,18 +94,20 @@ static NcclApi g_nccl;
 
 struct NcclComm : BbxComm {
     ncclComm_t comm = nullptr;
-    int *xdev = nullptr;   // [0..1] to lo / hi, [2..3] from lo / hi
+    int *xdev = nullptr;   // [0..K) to lo, [K..2K) to hi, [2K..3K) from lo, [3K..4K) from hi  (K = BBX_NCOUNTS)
     int *xhost = nullptr;  // pinned
+    void *opened[2 * BBX_PEER_NPTR]; int n_opened = 0; // IPC mappings of the neighbours' arrays
     int init(int rank_, int nranks_, const unsigned char *id){
         rank = rank_; nranks = nranks_;
         if(!g_nccl.load()){ err = g_nccl.load_error; return 1; }
         ncclUniqueId uid; memcpy(&uid, id, sizeof(uid));
         BBX_NCCL(g_nccl.CommInitRank(&comm, nranks, uid, rank));
-        BBX_CUC(cudaMalloc((void **)&xdev, 4 * sizeof(int)));
-        BBX_CUC(cudaMallocHost((void **)&xhost, 4 * sizeof(int)));
+        BBX_CUC(cudaMalloc((void **)&xdev, 4 * BBX_NCOUNTS * sizeof(int)));
+        BBX_CUC(cudaMallocHost((void **)&xhost, 4 * BBX_NCOUNTS * sizeof(int)));
         return 0;
     }
     ~NcclComm() override {
+        for(int k = 0; k < n_opened; k++) cudaIpcCloseMemHandle(opened[k]);
         if(comm) g_nccl.CommDestroy(comm);
         if(xdev) cudaFree(xdev);
         if(xhost) cudaFreeHost(xhost);
@@ -117,23 +130,69 @@ struct NcclComm : BbxComm {
         BBX_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclUint32, ncclMax, comm, s));
         return 0;
     }
-    int neighbor_counts(cudaStream_t s, int to_lo, int to_hi, int *from_lo, int *from_hi) override {
-        xhost[0] = to_lo; xhost[1] = to_hi; xhost[2] = 0; xhost[3] = 0;
-        BBX_CUC(cudaMemcpyAsync(xdev, xhost, 4 * sizeof(int), cudaMemcpyHostToDevice, s));
+    int neighbor_counts(cudaStream_t s, const int *to_lo, const int *to_hi, int *from_lo, int *from_hi) override {
+        const int K = BBX_NCOUNTS;
+        for(int k = 0; k < K; k++){ xhost[k] = to_lo[k]; xhost[K + k] = to_hi[k]; xhost[2 * K + k] = 0; xhost[3 * K + k] = 0; }
+        BBX_CUC(cudaMemcpyAsync(xdev, xhost, 4 * K * sizeof(int), cudaMemcpyHostToDevice, s));
         BBX_NCCL(g_nccl.GroupStart());
         if(has_lo()){
-            BBX_NCCL(g_nccl.Send(xdev + 0, sizeof(int), ncclChar, rank - 1, comm, s));
-            BBX_NCCL(g_nccl.Recv(xdev + 2, sizeof(int), ncclChar, rank - 1, comm, s));
+            BBX_NCCL(g_nccl.Send(xdev + 0, K * sizeof(int), ncclChar, rank - 1, comm, s));
+            BBX_NCCL(g_nccl.Recv(xdev + 2 * K, K * sizeof(int), ncclChar, rank - 1, comm, s));
         }
         if(has_hi()){
-            BBX_NCCL(g_nccl.Send(xdev + 1, sizeof(int), ncclChar, rank + 1, comm, s));
-            BBX_NCCL(g_nccl.Recv(xdev + 3, sizeof(int), ncclChar, rank + 1, comm, s));
+            BBX_NCCL(g_nccl.Send(xdev + K, K * sizeof(int), ncclChar, rank + 1, comm, s));
+            BBX_NCCL(g_nccl.Recv(xdev + 3 * K, K * sizeof(int), ncclChar, rank + 1, comm, s));
         }
         BBX_NCCL(g_nccl.GroupEnd());
-        BBX_CUC(cudaMemcpyAsync(xhost + 2, xdev + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        BBX_CUC(cudaMemcpyAsync(xhost + 2 * K, xdev + 2 * K, 2 * K * sizeof(int), cudaMemcpyDeviceToHost, s));
         BBX_CUC(cudaStreamSynchronize(s));
-        *from_lo = has_lo() ? xhost[2] : 0;
-        *from_hi = has_hi() ? xhost[3] : 0;
+        for(int k = 0; k < K; k++){ from_lo[k] = has_lo() ? xhost[2 * K + k] : 0; from_hi[k] = has_hi() ? xhost[3 * K + k] : 0; }
+        return 0;
+    }
+    // CUDA IPC: every rank exports its allocations, the handles travel to the two neighbours over NCCL, and
+    // each rank maps its neighbours' allocations (NVLink peer access).  Agreement: a global max over a
+    // "failed" flag, so either every rank stores into its neighbours' ghost slots or none does.
+    int share_arrays(cudaStream_t s, const BbxPeerArrays &mine, int want, BbxPeerArrays *lo, BbxPeerArrays *hi, int *ok) override {
+        struct Msg { cudaIpcMemHandle_t h[BBX_PEER_NPTR]; long long gc; int good; int pad; };
+        memset(lo, 0, sizeof(*lo)); memset(hi, 0, sizeof(*hi));
+        Msg *hm = nullptr, *dm = nullptr; // [0] mine, [1] from lo, [2] from hi
+        BBX_CUC(cudaMallocHost((void **)&hm, 3 * sizeof(Msg)));
+        BBX_CUC(cudaMalloc((void **)&dm, 3 * sizeof(Msg)));
+        memset(hm, 0, 3 * sizeof(Msg));
+        unsigned failed = want ? 0u : 1u;
+        for(int k = 0; k < BBX_PEER_NPTR && !failed; k++) if(cudaIpcGetMemHandle(&hm[0].h[k], mine.p[k]) != cudaSuccess){ cudaGetLastError(); failed = 1u; }
+        hm[0].gc = mine.gc; hm[0].good = failed ? 0 : 1;
+        BBX_CUC(cudaMemcpyAsync(dm, hm, 3 * sizeof(Msg), cudaMemcpyHostToDevice, s));
+        BBX_NCCL(g_nccl.GroupStart());
+        if(has_lo()){
+            BBX_NCCL(g_nccl.Send(dm + 0, sizeof(Msg), ncclChar, rank - 1, comm, s));
+            BBX_NCCL(g_nccl.Recv(dm + 1, sizeof(Msg), ncclChar, rank - 1, comm, s));
+        }
+        if(has_hi()){
+            BBX_NCCL(g_nccl.Send(dm + 0, sizeof(Msg), ncclChar, rank + 1, comm, s));
+            BBX_NCCL(g_nccl.Recv(dm + 2, sizeof(Msg), ncclChar, rank + 1, comm, s));
+        }
+        BBX_NCCL(g_nccl.GroupEnd());
+        BBX_CUC(cudaMemcpyAsync(hm, dm, 3 * sizeof(Msg), cudaMemcpyDeviceToHost, s));
+        BBX_CUC(cudaStreamSynchronize(s));
+        for(int side = 0; side < 2 && !failed; side++){
+            if(side == 0 ? !has_lo() : !has_hi()) continue;
+            const Msg &m = hm[1 + side]; BbxPeerArrays *dst = side == 0 ? lo : hi;
+            if(!m.good){ failed = 1u; break; }
+            dst->gc = m.gc;
+            for(int k = 0; k < BBX_PEER_NPTR; k++){
+                void *q = nullptr;
+                if(cudaIpcOpenMemHandle(&q, m.h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess){ cudaGetLastError(); failed = 1u; break; }
+                dst->p[k] = q; opened[n_opened++] = q;
+            }
+        }
+        unsigned *dflag = (unsigned *)dm;
+        BBX_CUC(cudaMemcpyAsync(dflag, &failed, sizeof(unsigned), cudaMemcpyHostToDevice, s));
+        BBX_NCCL(g_nccl.AllReduce(dflag, dflag, 1, ncclUint32, ncclMax, comm, s));
+        BBX_CUC(cudaMemcpyAsync(&failed, dflag, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+        BBX_CUC(cudaStreamSynchronize(s));
+        cudaFree(dm); cudaFreeHost(hm);
+        *ok = failed ? 0 : 1;
         return 0;
     }
     int barrier() override { return 0; } // every collective above already orders the ranks
@@ -149,8 +208,9 @@ struct LocalShared {
         BbxSeg send_lo[BBX_MAX_SEGS], send_hi[BBX_MAX_SEGS];
         int n_lo = 0, n_hi = 0;
         cudaEvent_t ready = nullptr, done = nullptr;
-        int to_lo = 0, to_hi = 0;
+        int to_lo[BBX_NCOUNTS] = {0}, to_hi[BBX_NCOUNTS] = {0};
         unsigned red[16];
+        BbxPeerArrays arrays; int want = 0;
     } slot[BBX_LOCAL_MAX_RANKS];
     // false on timeout / failure of a peer: the group is then poisoned (every later barrier fails)
     bool barrier(){
@@ -244,13 +304,29 @@ struct LocalComm : BbxComm {
         BBX_CUC(cudaStreamSynchronize(s)); // redhost is reused by the next call
         return 0;
     }
-    int neighbor_counts(cudaStream_t s, int to_lo, int to_hi, int *from_lo, int *from_hi) override {
+    int neighbor_counts(cudaStream_t s, const int *to_lo, const int *to_hi, int *from_lo, int *from_hi) override {
         (void)s;
-        sh->slot[rank].to_lo = to_lo; sh->slot[rank].to_hi = to_hi;
+        for(int k = 0; k < BBX_NCOUNTS; k++){ sh->slot[rank].to_lo[k] = to_lo[k]; sh->slot[rank].to_hi[k] = to_hi[k]; }
         if(!sh->barrier()) return fail("local slab group: counts");
-        *from_lo = has_lo() ? sh->slot[rank - 1].to_hi : 0;
-        *from_hi = has_hi() ? sh->slot[rank + 1].to_lo : 0;
+        for(int k = 0; k < BBX_NCOUNTS; k++){
+            from_lo[k] = has_lo() ? sh->slot[rank - 1].to_hi[k] : 0;
+            from_hi[k] = has_hi() ? sh->slot[rank + 1].to_lo[k] : 0;
+        }
         if(!sh->barrier()) return fail("local slab group: counts");
+        return 0;
+    }
+    // one process, one device: the neighbours' pointers are usable as they are
+    int share_arrays(cudaStream_t s, const BbxPeerArrays &mine, int want, BbxPeerArrays *lo, BbxPeerArrays *hi, int *ok) override {
+        (void)s;
+        memset(lo, 0, sizeof(*lo)); memset(hi, 0, sizeof(*hi));
+        sh->slot[rank].arrays = mine; sh->slot[rank].want = want;
+        if(!sh->barrier()) return fail("local slab group: share_arrays");
+        int all = 1;
+        for(int r = 0; r < nranks; r++) all &= sh->slot[r].want ? 1 : 0;
+        if(has_lo()) *lo = sh->slot[rank - 1].arrays;
+        if(has_hi()) *hi = sh->slot[rank + 1].arrays;
+        if(!sh->barrier()) return fail("local slab group: share_arrays");
+        *ok = all;
         return 0;
     }
     int barrier() override { return sh->barrier() ? 0 : fail("local slab group: barrier"); }

@@ -473,5 +473,49 @@ __device__ __forceinline__ bool bbx_inside_domain_certain(const DevCullSet &cs, 
     return px > cs.dom_lo[0] && px < cs.dom_hi[0] && py > cs.dom_lo[1] && py < cs.dom_hi[1] && pz > cs.dom_lo[2] && pz < cs.dom_hi[2];
 }
 
+// ------------------------------------------------------------------------------ halo push (slab engines)
+// Where the boundary-plane results of a sweep ALSO go: straight into the two neighbours' ghost slots
+// (peer device memory: CUDA IPC mappings over NVLink, or plain pointers for slabs sharing a device).
+// My first owned plane, slots [0, n_first), is the lower neighbour's upper ghost plane, its slots
+// [lo_base, lo_base + n_first) with lo_base = that neighbour's owned count; my last owned plane, slots
+// [hi_begin, n), is the upper neighbour's lower ghost plane, its slots [hi_begin - n, 0).
+// Up to two arrays per kernel (x and v of the integration).  Inactive: n_first = 0, hi_begin = INT_MAX.
+struct HaloDst {
+    float4 *lo[2], *hi[2];
+    int n_first, lo_base, hi_begin, n;
+};
+// float4 k of the `rec`-float4 record of slot i, array `which`
+__device__ __forceinline__ void bbx_halo_store(const HaloDst &h, int which, int rec, int i, int k, float4 v){
+    if(i < h.n_first) h.lo[which][(size_t)(h.lo_base + i) * rec + k] = v;
+    if(i >= h.hi_begin) h.hi[which][(ptrdiff_t)(i - h.n) * rec + k] = v;
+}
+#define BBX_HALO_PHASES 6   // density, predict, pressure, integrate, grid: counts, grid: boundary planes
+#define BBX_HALO_MAIL 4     // mailbox integers per side behind the flags: boundary-plane particles, owned particles, -, -
+// After the kernels of a phase: tell both neighbours that my stores into their ghost slots are complete
+// (stream order puts this after the producing kernels; the fence orders it after their stores system-wide).
+__global__ void k_halo_signal(unsigned *lo_flag, unsigned *hi_flag, unsigned seq){
+    if(threadIdx.x == 0){
+        __threadfence_system();
+        if(lo_flag) *(volatile unsigned *)lo_flag = seq;
+        if(hi_flag) *(volatile unsigned *)hi_flag = seq;
+    }
+}
+// Before the next phase reads ghost slots: wait until both neighbours have signalled this phase (bounded:
+// ~3 s of polling, then the sticky device error BBX_ERR_COMM instead of a hang).
+__global__ void k_halo_wait(const unsigned *from_lo, const unsigned *from_hi, unsigned seq, int *error){
+    if(threadIdx.x == 0){
+        const long long t0 = clock64();
+        for(int side = 0; side < 2; side++){
+            const volatile unsigned *f = side == 0 ? from_lo : from_hi;
+            if(!f) continue;
+            while((int)(*f - seq) < 0){
+                if(clock64() - t0 > 6000000000ll){ *error = BBX_ERR_COMM; break; }
+                __nanosleep(200);
+            }
+        }
+        __threadfence_system();
+    }
+}
+
 // warp helpers
 __device__ __forceinline__ unsigned lanemask_lt(){ unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }

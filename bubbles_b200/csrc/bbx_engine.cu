@@ -30,6 +30,7 @@ struct bbx_engine {
     bbx_config cfg;
     int device;
     cudaStream_t stream;
+    cudaStream_t side; cudaEvent_t ev_fork, ev_join; // slab engines: the global flag reduction runs beside the scan and the fill
     int n, cap;      // owned particles / capacity
     // slab engines: ghost capacity per side and the current ghost / boundary-plane counts (host copies).
     // Every slot-indexed array that neighbours are read from (pos, vel, pid, cell, newcell, pred, posq) is
@@ -38,6 +39,16 @@ struct bbx_engine {
     int gcap, n_glo, n_ghi, n_first, n_last;
     int has_lo, has_hi; // a slab neighbour exists below / above
     BbxComm *comm;
+    // halo push: the neighbours' arrays as seen from this device (slot-0 pointers), their owned counts, and the
+    // flags the neighbours raise in MY memory when their stores into my ghost slots are complete
+    struct PeerSide { float4 *pos[2], *vel[2], *rec, *pred, *posq; int *pid[2], *gtab; unsigned *flags; int n; } peer[2]; // [0] lower, [1] upper neighbour
+    int peers_ready;    // share_arrays done (lazily, at the first collective grid update)
+    int p2p;            // boundary-plane results are stored straight into the neighbours' ghost slots (else: send / recv per phase)
+    unsigned *halo_flags;            // device, [2 sides][BBX_HALO_PHASES]: [0][p] raised by the lower neighbour, [1][p] by the upper one;
+                                     // then [2 sides][BBX_HALO_MAIL] mailbox integers written by the neighbours
+    int *mail_host;                  // pinned copy of the mailbox
+    unsigned halo_seq[BBX_HALO_PHASES];
+    void *raw_shared[BBX_PEER_NPTR]; // allocation bases of pos[2], vel[2], rec, pred, posq, halo_flags, pid[2], gtab
     int *gtab;          // received cell-table slices of the two ghost planes, 2 x (plane + 1)
     std::vector<void *> raw; // allocation bases (for cudaFree)
     DevGrid grid;
@@ -136,6 +147,8 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     e->last_ms_grid = e->last_ms_step = 0.f;
     memset(e->phase_ms, 0, sizeof(e->phase_ms)); memset(e->phase_launches, 0, sizeof(e->phase_launches));
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->list_ctas_per_sm, k_cell_lists_density<0>, BBX_LT, 0));
     if(e->list_ctas_per_sm < 1) e->list_ctas_per_sm = 1;
     // the staged sweeps carry their tile's neighbourhood in dynamic shared memory (> 48 KB: opt in)
@@ -163,6 +176,8 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     if((long long)g.plane * g.n[2] > 0x7fffffffLL){ delete e; return set_error(BBX_ERR_INVALID, "more than 2^31 local cells"); }
     g.total = g.plane * g.n[2];
     e->gcap = 0; e->n_glo = e->n_ghi = e->n_first = e->n_last = 0; e->comm = nullptr; e->gtab = nullptr;
+    e->p2p = 0; e->peers_ready = 0; e->halo_flags = nullptr; e->mail_host = nullptr; memset(e->peer, 0, sizeof(e->peer)); memset(e->halo_seq, 0, sizeof(e->halo_seq));
+    memset(e->raw_shared, 0, sizeof(e->raw_shared));
     if(e->has_lo || e->has_hi){
         e->gcap = cfg->ghost_capacity > 0 ? cfg->ghost_capacity : std::max(4096, cfg->max_particles / 4);
     }
@@ -195,6 +210,17 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
         rc |= dev_alloc(&raw, 2 * capg);
         if(rc == BBX_OK){ e->raw.push_back((void *)raw); CU(cudaMemset(raw, 0, sizeof(float4) * 2 * capg)); e->rec = raw + 2 * gc; }
     }
+    if(rc == BBX_OK){
+        e->raw_shared[0] = e->pos[0] - gc; e->raw_shared[1] = e->pos[1] - gc; e->raw_shared[2] = e->vel[0] - gc; e->raw_shared[3] = e->vel[1] - gc;
+        e->raw_shared[4] = e->rec - 2 * gc; e->raw_shared[5] = e->pred - gc; e->raw_shared[6] = e->posq - gc;
+        e->raw_shared[8] = e->pid[0] - gc; e->raw_shared[9] = e->pid[1] - gc;
+    }
+    if(e->gcap){
+        const size_t words = (size_t)2 * (BBX_HALO_PHASES + BBX_HALO_MAIL);
+        rc |= dev_alloc(&e->halo_flags, words);
+        if(rc == BBX_OK){ CU(cudaMemset(e->halo_flags, 0, sizeof(unsigned) * words)); e->raw_shared[7] = e->halo_flags; }
+        CU(cudaMallocHost((void **)&e->mail_host, sizeof(int) * 2 * BBX_HALO_MAIL));
+    }
     rc |= dev_alloc(&e->count, (size_t)g.total + 8); rc |= dev_alloc(&e->perm, cap);
     rc |= dev_alloc(&e->occ_cells, (size_t)g.total); rc |= dev_alloc(&e->queue, cap);
     e->scan_tiles = div_up(g.c_own1 - g.c_own0, SCAN_TILE);
@@ -204,7 +230,7 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     rc |= dev_alloc(&e->smoothed, cap);
     rc |= dev_alloc(&e->pressure, cap); rc |= dev_alloc(&e->rho_pred, cap); rc |= dev_alloc(&e->rho_err, cap);
     rc |= dev_alloc(&e->st, 1); rc |= dev_alloc(&e->colliders, 1); rc |= dev_alloc(&e->cull, 1);
-    if(e->gcap) rc |= dev_alloc(&e->gtab, 2 * ((size_t)g.plane + 1));
+    if(e->gcap){ rc |= dev_alloc(&e->gtab, 2 * ((size_t)g.plane + 1)); e->raw_shared[10] = e->gtab; }
     if(rc != BBX_OK){ return rc; }
     CU(cudaMemset(e->count, 0, sizeof(int) * ((size_t)g.total + 8)));
     CU(cudaMallocHost((void **)&e->st_host, sizeof(DevState)));
@@ -232,11 +258,14 @@ int bbx_destroy(bbx_engine *e){
     cudaFree(e->nbr); cudaFree(e->nbr_cnt); cudaFree(e->force); cudaFree(e->force_p);
     cudaFree(e->smoothed); cudaFree(e->pressure); cudaFree(e->rho_pred); cudaFree(e->rho_err);
     if(e->gtab) cudaFree(e->gtab);
+    if(e->halo_flags) cudaFree(e->halo_flags);
+    if(e->mail_host) cudaFreeHost(e->mail_host);
     cudaFree(e->st); cudaFree(e->colliders); cudaFree(e->cull); cudaFreeHost(e->st_host);
     for(double *f : e->sdf_fields) cudaFree(f);
     for(float *f : e->sdf_fields32) cudaFree(f);
     if(e->stage) cudaFree(e->stage);
     for(cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
+    cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaStreamDestroy(e->side);
     cudaStreamDestroy(e->stream);
     delete e;
     return BBX_OK;
@@ -558,11 +587,65 @@ static int exchange_planes(bbx_engine *e, void *const *arr, const size_t *esz, i
 static int exchange1(bbx_engine *e, float4 *a){ void *arr[1] = {a}; size_t z[1] = {sizeof(float4)}; return exchange_planes(e, arr, z, 1); }
 static int exchange2(bbx_engine *e, float4 *a, float4 *b){ void *arr[2] = {a, b}; size_t z[2] = {sizeof(float4), sizeof(float4)}; return exchange_planes(e, arr, z, 2); }
 
+// ---- halo push: where the boundary planes of array(s) `which` go in the neighbours' memory
+enum { HALO_DENSITY = 0, HALO_PREDICT, HALO_PRESSURE, HALO_INTEGRATE, HALO_COUNTS, HALO_PLANES };
+static HaloDst halo_none(){ HaloDst h; memset(&h, 0, sizeof(h)); h.hi_begin = 0x7fffffff; return h; }
+static HaloDst halo_dst(bbx_engine *e, float4 *lo0, float4 *hi0, float4 *lo1 = nullptr, float4 *hi1 = nullptr){
+    HaloDst h = halo_none();
+    if(!e->p2p) return h;
+    h.lo[0] = lo0; h.hi[0] = hi0; h.lo[1] = lo1; h.hi[1] = hi1;
+    h.n = e->n;
+    h.n_first = e->has_lo ? e->n_first : 0; h.lo_base = e->peer[0].n;
+    h.hi_begin = e->has_hi ? e->n - e->n_last : 0x7fffffff;
+    return h;
+}
+// end of a phase whose kernels pushed their boundary planes: raise my flag at both neighbours, wait for theirs
+static unsigned *halo_flag_at(bbx_engine *e, int side, int phase){ // the flag I raise at neighbour `side` (I am its opposite side)
+    if(side == 0 ? !e->has_lo : !e->has_hi) return nullptr;
+    return e->peer[side].flags + (side == 0 ? 1 : 0) * BBX_HALO_PHASES + phase;
+}
+static int halo_wait(bbx_engine *e, int phase, unsigned seq){
+    LAUNCH(e, k_halo_wait, 1, 32, e->has_lo ? e->halo_flags + 0 * BBX_HALO_PHASES + phase : (const unsigned *)nullptr,
+           e->has_hi ? e->halo_flags + 1 * BBX_HALO_PHASES + phase : (const unsigned *)nullptr, seq, &e->st->error);
+    CU(cudaGetLastError());
+    return BBX_OK;
+}
+static int halo_sync(bbx_engine *e, int phase){
+    const unsigned seq = ++e->halo_seq[phase];
+    LAUNCH(e, k_halo_signal, 1, 32, halo_flag_at(e, 0, phase), halo_flag_at(e, 1, phase), seq);
+    return halo_wait(e, phase, seq);
+}
+// once the communicator is up: map the neighbours' arrays (BBX_P2P=0 keeps the send / recv path)
+static int setup_peers(bbx_engine *e){
+    e->p2p = 0; e->peers_ready = 1;
+    if(!IS_SLAB(e) || !e->comm) return BBX_OK;
+    const char *env = getenv("BBX_P2P");
+    const int want = (env && env[0] == '0') ? 0 : 1;
+    BbxPeerArrays mine, lo, hi; int ok = 0;
+    for(int k = 0; k < BBX_PEER_NPTR; k++) mine.p[k] = e->raw_shared[k];
+    mine.gc = e->gcap;
+    COMM(e->comm->share_arrays(e->stream, mine, want, &lo, &hi, &ok));
+    if(!ok) return BBX_OK;
+    const BbxPeerArrays *src[2] = {&lo, &hi};
+    for(int sd = 0; sd < 2; sd++){
+        if(sd == 0 ? !e->has_lo : !e->has_hi) continue;
+        const BbxPeerArrays &a = *src[sd]; const size_t gc = (size_t)a.gc;
+        bbx_engine::PeerSide &p = e->peer[sd];
+        p.pos[0] = (float4 *)a.p[0] + gc; p.pos[1] = (float4 *)a.p[1] + gc; p.vel[0] = (float4 *)a.p[2] + gc; p.vel[1] = (float4 *)a.p[3] + gc;
+        p.rec = (float4 *)a.p[4] + 2 * gc; p.pred = (float4 *)a.p[5] + gc; p.posq = (float4 *)a.p[6] + gc;
+        p.flags = (unsigned *)a.p[7];
+        p.pid[0] = (int *)a.p[8] + gc; p.pid[1] = (int *)a.p[9] + gc; p.gtab = (int *)a.p[10];
+    }
+    e->p2p = 1;
+    return BBX_OK;
+}
+
 // UpdateGridDistributionGPU minus the bucket fill (sph_equations3.cpp:511-539)
 #define BBX_SMALL_GRID (148 * 4)
 static int grid_update(bbx_engine *e){
     const bool slab = IS_SLAB(e);
     if(e->n == 0 && !slab) return BBX_OK;
+    if(slab && !e->peers_ready){ int rc = setup_peers(e); if(rc) return rc; }
     DevGrid &g = e->grid;
     int n_all = e->n_glo + e->n + e->n_ghi, cur = e->cur, nxt = cur ^ 1;
     int force = (e->force_full || !e->have_chains) ? 1 : 0;
@@ -570,16 +653,23 @@ static int grid_update(bbx_engine *e){
     const int own_cells = g.c_own1 - g.c_own0;
     LAUNCH(e, k_hash_count, div_up(std::max(std::max(n_all, e->scan_tiles), 1), 256), 256, n_all, e->n_glo, e->n, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st,
            force ? 0 : 1, par, e->scan_status, e->scan_tiles);
-    // the big-move rule and the jump detection are global decisions (the reference rebuilds ALL chains)
-    if(slab) COMM(e->comm->allreduce_max_u32(e->stream, (unsigned *)e->st, 4)); // rebuild_flag[2], jump_flag[2]
+    // the big-move rule and the jump detection are global decisions (the reference rebuilds ALL chains): the
+    // flags are reduced over the ranks on a side stream while the scan and the (speculative) fill run
+    if(slab){
+        CU(cudaEventRecord(e->ev_fork, e->stream));
+        CU(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+        COMM(e->comm->allreduce_max_u32(e->side, (unsigned *)e->st, 4)); // rebuild_flag[2], jump_flag[2]
+        CU(cudaEventRecord(e->ev_join, e->side));
+    }
     LAUNCH(e, k_scan_cells, e->scan_tiles, 256, e->count + g.c_own0, own_cells, g.c_own0, e->scan_status, e->st, e->cell_start[nxt] + g.c_own0, e->occ_cells);
     if(!force){
         // persistent grid: 8 lanes per occupied cell, grid-stride over the compact list of occupied cells
         int groups = std::max(1, std::min(n_all, own_cells));
         int blocks = std::min(div_up((long long)groups * 8, 256), 148 * 8);
-        LAUNCH(e, k_fill_incremental, blocks, 256, g, e->st, par, e->occ_cells, e->cell_start[cur], e->cell_start[nxt], e->newcell,
+        LAUNCH(e, k_fill_incremental, blocks, 256, g, e->st, par, slab ? 1 : 0, e->occ_cells, e->cell_start[cur], e->cell_start[nxt], e->newcell,
                e->pos[cur], e->vel[cur], e->pid[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec);
     }
+    if(slab) CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
     // full path (forced, or selected on the device by the big-move / jump flags); small grids when it is
     // only a flag check
     int fb_n = force ? div_up(std::max(n_all, 1), 256) : std::min(div_up(std::max(n_all, 1), 256), BBX_SMALL_GRID);
@@ -593,19 +683,62 @@ static int grid_update(bbx_engine *e){
         // migration happened implicitly: particles that crossed into my planes were found in my ghost
         // planes' old chains (in the reference's order), particles that left simply were not placed.
         // Now the ghost planes are replaced by the neighbours' freshly ordered boundary planes.
-        LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi);
-        int rc = read_state(e); if(rc) return rc;
-        const int n_new = e->st_host->n_own, nf = e->st_host->n_first, nl = e->st_host->n_last;
-        if(n_new > e->cap) return set_error(BBX_ERR_CAPACITY, "slab now owns %d particles, max_particles is %d", n_new, e->cap);
-        int glo = 0, ghi = 0;
-        COMM(e->comm->neighbor_counts(e->stream, nf, nl, &glo, &ghi));
-        if(glo > e->gcap || ghi > e->gcap) return set_error(BBX_ERR_CAPACITY, "ghost plane of %d particles exceeds ghost_capacity %d", std::max(glo, ghi), e->gcap);
         const size_t tb = sizeof(int) * ((size_t)g.plane + 1);
-        BbxSeg slo[4] = {{e->cell_start[nxt] + g.c_own0, tb}, {e->pos[nxt], sizeof(float4) * (size_t)nf}, {e->vel[nxt], sizeof(float4) * (size_t)nf}, {e->pid[nxt], sizeof(int) * (size_t)nf}};
-        BbxSeg rlo[4] = {{e->gtab, tb}, {e->pos[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->vel[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->pid[nxt] - glo, sizeof(int) * (size_t)glo}};
-        BbxSeg shi[4] = {{e->cell_start[nxt] + g.c_own1 - g.plane, tb}, {e->pos[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->vel[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->pid[nxt] + (n_new - nl), sizeof(int) * (size_t)nl}};
-        BbxSeg rhi[4] = {{e->gtab + g.plane + 1, tb}, {e->pos[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->vel[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->pid[nxt] + n_new, sizeof(int) * (size_t)ghi}};
-        COMM(e->comm->exchange(e->stream, slo, rlo, 4, shi, rhi, 4));
+        int n_new, nf, nl, glo = 0, ghi = 0;
+        if(e->p2p){
+            // sizes travel through the neighbours' mailboxes (peer memory), one host round trip in total
+            int *mail = (int *)(e->halo_flags + 2 * BBX_HALO_PHASES);
+            int *mlo = e->has_lo ? (int *)(e->peer[0].flags + 2 * BBX_HALO_PHASES) + 1 * BBX_HALO_MAIL : nullptr; // I am its UPPER side
+            int *mhi = e->has_hi ? (int *)(e->peer[1].flags + 2 * BBX_HALO_PHASES) + 0 * BBX_HALO_MAIL : nullptr;
+            const unsigned seq = ++e->halo_seq[HALO_COUNTS];
+            LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, mlo, mhi, halo_flag_at(e, 0, HALO_COUNTS), halo_flag_at(e, 1, HALO_COUNTS), seq);
+            int rc = halo_wait(e, HALO_COUNTS, seq); if(rc) return rc;
+            CU(cudaMemcpyAsync(e->mail_host, mail, sizeof(int) * 2 * BBX_HALO_MAIL, cudaMemcpyDeviceToHost, e->stream));
+            rc = read_state(e); if(rc) return rc;
+            n_new = e->st_host->n_own; nf = e->st_host->n_first; nl = e->st_host->n_last;
+            if(e->st_host->error == BBX_ERR_COMM) return set_error(BBX_ERR_COMM, "a slab neighbour never signalled its boundary-plane counts");
+            if(e->has_lo){ glo = e->mail_host[0]; e->peer[0].n = e->mail_host[1]; }
+            if(e->has_hi){ ghi = e->mail_host[BBX_HALO_MAIL]; e->peer[1].n = e->mail_host[BBX_HALO_MAIL + 1]; }
+        }else{
+            LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, (int *)nullptr, (int *)nullptr, (unsigned *)nullptr, (unsigned *)nullptr, 0u);
+            int rc = read_state(e); if(rc) return rc;
+            n_new = e->st_host->n_own; nf = e->st_host->n_first; nl = e->st_host->n_last;
+            // boundary-plane sizes (the next exchange) and owned counts
+            const int to_lo[BBX_NCOUNTS] = {nf, n_new}, to_hi[BBX_NCOUNTS] = {nl, n_new};
+            int from_lo[BBX_NCOUNTS], from_hi[BBX_NCOUNTS];
+            COMM(e->comm->neighbor_counts(e->stream, to_lo, to_hi, from_lo, from_hi));
+            glo = from_lo[0]; ghi = from_hi[0]; e->peer[0].n = from_lo[1]; e->peer[1].n = from_hi[1];
+        }
+        if(n_new > e->cap) return set_error(BBX_ERR_CAPACITY, "slab now owns %d particles, max_particles is %d", n_new, e->cap);
+        if(glo > e->gcap || ghi > e->gcap) return set_error(BBX_ERR_CAPACITY, "ghost plane of %d particles exceeds ghost_capacity %d", std::max(glo, ghi), e->gcap);
+        if(e->p2p){
+            // my freshly ordered boundary planes -> the neighbours' ghost slots (their table slices: lower ghost
+            // plane at gtab, upper one at gtab + plane + 1), then the planes flag
+            PushSegs S; memset(&S, 0, sizeof(S));
+            auto add = [&](const void *src, void *dst, size_t bytes){ if(bytes){ S.src[S.n] = src; S.dst[S.n] = dst; S.bytes[S.n] = (long long)bytes; S.n++; } };
+            if(e->has_lo){
+                const bbx_engine::PeerSide &p = e->peer[0];
+                add(e->cell_start[nxt] + g.c_own0, p.gtab + g.plane + 1, tb);
+                add(e->pos[nxt], p.pos[nxt] + p.n, sizeof(float4) * (size_t)nf);
+                add(e->vel[nxt], p.vel[nxt] + p.n, sizeof(float4) * (size_t)nf);
+                add(e->pid[nxt], p.pid[nxt] + p.n, sizeof(int) * (size_t)nf);
+            }
+            if(e->has_hi){
+                const bbx_engine::PeerSide &p = e->peer[1];
+                add(e->cell_start[nxt] + g.c_own1 - g.plane, p.gtab, tb);
+                add(e->pos[nxt] + (n_new - nl), p.pos[nxt] - nl, sizeof(float4) * (size_t)nl);
+                add(e->vel[nxt] + (n_new - nl), p.vel[nxt] - nl, sizeof(float4) * (size_t)nl);
+                add(e->pid[nxt] + (n_new - nl), p.pid[nxt] - nl, sizeof(int) * (size_t)nl);
+            }
+            LAUNCH(e, k_push_planes, 148, 256, S);
+            int rc = halo_sync(e, HALO_PLANES); if(rc) return rc;
+        }else{
+            BbxSeg slo[4] = {{e->cell_start[nxt] + g.c_own0, tb}, {e->pos[nxt], sizeof(float4) * (size_t)nf}, {e->vel[nxt], sizeof(float4) * (size_t)nf}, {e->pid[nxt], sizeof(int) * (size_t)nf}};
+            BbxSeg rlo[4] = {{e->gtab, tb}, {e->pos[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->vel[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->pid[nxt] - glo, sizeof(int) * (size_t)glo}};
+            BbxSeg shi[4] = {{e->cell_start[nxt] + g.c_own1 - g.plane, tb}, {e->pos[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->vel[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->pid[nxt] + (n_new - nl), sizeof(int) * (size_t)nl}};
+            BbxSeg rhi[4] = {{e->gtab + g.plane + 1, tb}, {e->pos[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->vel[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->pid[nxt] + n_new, sizeof(int) * (size_t)ghi}};
+            COMM(e->comm->exchange(e->stream, slo, rlo, 4, shi, rhi, 4));
+        }
         LAUNCH(e, k_ghost_table, div_up(g.plane, 256), 256, g, n_new, e->has_lo, e->has_hi, e->gtab, e->gtab + g.plane + 1, e->cell_start[nxt], e->cell[nxt], e->count);
         CU(cudaGetLastError());
         e->n = n_new; e->n_first = nf; e->n_last = nl; e->n_glo = glo; e->n_ghi = ghi;
@@ -625,10 +758,12 @@ static int list_blocks(bbx_engine *e){
 static int phase_density(bbx_engine *e, const StepParams &P, int sph){
     int cur = e->cur;
     if(e->n > 0){
-        if(sph) LAUNCH(e, k_cell_lists_density<1>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec);
-        else LAUNCH(e, k_cell_lists_density<0>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec);
+        if(sph) LAUNCH(e, k_cell_lists_density<1>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec, halo_none());
+        else LAUNCH(e, k_cell_lists_density<0>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
+                    halo_dst(e, e->peer[0].rec, e->peer[1].rec));
         CU(cudaGetLastError());
     }
+    if(!sph && e->p2p) return halo_sync(e, HALO_DENSITY);
     // ghost rho: the PCISPH viscosity sweep reads the 32-byte records (x, rho | v); the SPH step reads rho from
     // vel.w and also needs the ghosts' p / rho^2 (posq.w)
     if(sph) return exchange2(e, e->vel[cur], e->posq);
@@ -642,32 +777,38 @@ static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
     int cur = e->cur;
     if(e->n > 0){
         LAUNCH(e, k_force_np_predict, sweep_grid(e), BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->rec, e->cell[cur], e->cell_start[cur],
-               e->nbr, e->nbr_cnt, e->force, e->pred, e->queue);
-        LAUNCH(e, k_collide_predict, BBX_SMALL_GRID, 128, P, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force, e->pred);
+               e->nbr, e->nbr_cnt, e->force, e->pred, e->queue, halo_dst(e, e->peer[0].pred, e->peer[1].pred));
+        LAUNCH(e, k_collide_predict, BBX_SMALL_GRID, 128, P, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force, e->pred,
+               halo_dst(e, e->peer[0].pred, e->peer[1].pred));
         CU(cudaGetLastError());
     }
+    if(e->p2p) return halo_sync(e, HALO_PREDICT);
     return exchange1(e, e->pred); // ghost x*
 }
 static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
     int cur = e->cur;
     if(e->n > 0){
         LAUNCH_S(e, k_pressure, tile_grid(e), BBX_TS, BBX_STAGE_BYTES(3), P, e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
-               e->nbr, e->nbr_cnt, e->pressure, e->rho_pred, e->rho_err, e->posq);
+               e->nbr, e->nbr_cnt, e->pressure, e->rho_pred, e->rho_err, e->posq, halo_dst(e, e->peer[0].posq, e->peer[1].posq));
         CU(cudaGetLastError());
     }
+    if(e->p2p) return halo_sync(e, HALO_PRESSURE);
     return exchange1(e, e->posq); // ghost (x, p / rho*^2)
 }
 static int phase_pressure_force(bbx_engine *e, const StepParams &P, int integrate){
     int cur = e->cur; int nb = sweep_grid(e);
     if(e->n > 0){
         if(integrate){
-            LAUNCH(e, k_pressure_force<1>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue);
-            LAUNCH(e, k_collide_integrate, BBX_SMALL_GRID, 128, P, e->grid, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force);
+            LAUNCH(e, k_pressure_force<1>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue,
+                   halo_dst(e, e->peer[0].pos[cur], e->peer[1].pos[cur], e->peer[0].vel[cur], e->peer[1].vel[cur]));
+            LAUNCH(e, k_collide_integrate, BBX_SMALL_GRID, 128, P, e->grid, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force,
+                   halo_dst(e, e->peer[0].pos[cur], e->peer[1].pos[cur], e->peer[0].vel[cur], e->peer[1].vel[cur]));
         }else{
-            LAUNCH(e, k_pressure_force<0>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue);
+            LAUNCH(e, k_pressure_force<0>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue, halo_none());
         }
         CU(cudaGetLastError());
     }
+    if(integrate && e->p2p) return halo_sync(e, HALO_INTEGRATE);
     // after the integration the neighbours need the new x, v of my boundary planes (in the old order) to
     // run their own grid update: that is where migrating particles change owner
     if(integrate) return exchange2(e, e->pos[cur], e->vel[cur]);
@@ -856,7 +997,8 @@ int bbx_stats(bbx_engine *e, bbx_step_stats *out){
     out->ms_grid = e->last_ms_grid; out->ms_step = e->last_ms_step;
     out->exact_passes = s.exact_passes; out->max_candidates = s.max_candidates; out->occupied_cells = s.n_occ; out->unstaged_tiles = s.unstaged_tiles;
     if(s.error) return set_error(s.error, "device-side error %d (%s)", s.error,
-                                 s.error == BBX_ERR_OUT_OF_DOMAIN ? "particle outside the grid bounds" : "a cell run holds more than 4096 particles");
+                                 s.error == BBX_ERR_OUT_OF_DOMAIN ? "particle outside the grid bounds" :
+                                 (s.error == BBX_ERR_COMM ? "a slab neighbour never signalled its halo stores" : "a cell run holds more than 4096 particles"));
     return BBX_OK;
 }
 
@@ -1017,9 +1159,10 @@ int bbx_comm_init(bbx_engine *e, int rank, int nranks, const unsigned char id[BB
                          e->cfg.slab_z_begin, e->cfg.slab_z_end, e->grid.gnz);
     NcclComm *c = new NcclComm();
     if(c->init(rank, nranks, id)){ std::string m = c->err; delete c; return set_error(BBX_ERR_COMM, "%s", m.c_str()); }
-    e->comm = c;
+    e->comm = c; e->peers_ready = 0; // the neighbours' arrays are mapped at the first collective call (grid update)
     return BBX_OK;
 }
+int bbx_halo_mode(bbx_engine *e, int *p2p){ if(!e || !p2p) return set_error(BBX_ERR_INVALID, "null"); *p2p = e->p2p; return BBX_OK; }
 int bbx_comm_init_local(bbx_engine *e, int rank, int nranks, const char *group){
     CHECK_ENGINE(e);
     if(e->comm) return set_error(BBX_ERR_INVALID, "engine already has a communicator");
@@ -1028,7 +1171,7 @@ int bbx_comm_init_local(bbx_engine *e, int rank, int nranks, const char *group){
                          e->cfg.slab_z_begin, e->cfg.slab_z_end, e->grid.gnz);
     LocalComm *c = new LocalComm();
     if(c->init(group, rank, nranks)){ std::string m = c->err; delete c; return set_error(BBX_ERR_COMM, "%s", m.c_str()); }
-    e->comm = c;
+    e->comm = c; e->peers_ready = 0; // the neighbours' arrays are mapped at the first collective call (grid update)
     return BBX_OK;
 }
 // ParticleSet3 has no notion of slabs: this is the planner a multi-GPU host uses.  plane_counts[z] =

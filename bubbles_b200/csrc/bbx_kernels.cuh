@@ -164,14 +164,16 @@ __global__ void __launch_bounds__(256) k_scan_cells(int *__restrict__ count, int
 // old chain order, the particles whose new cell is c (Grid::DistributeToCellOpt, grid.h:449-494) --
 // ballot/popc compaction, no atomics, so the order is deterministic and equal to the reference's.
 // The matching lanes move the particle payload straight into the new sorted arrays.
-__global__ void __launch_bounds__(256) k_fill_incremental(DevGrid g, const DevState *st, int par,
+__global__ void __launch_bounds__(256) k_fill_incremental(DevGrid g, const DevState *st, int par, int ignore_flags,
         const int *__restrict__ occ_cells,
         const int *__restrict__ start_old, const int *__restrict__ start_new, const int *__restrict__ newcell,
         const float4 *__restrict__ pos_old, const float4 *__restrict__ vel_old, const int *__restrict__ pid_old,
         float4 *__restrict__ pos_new, float4 *__restrict__ vel_new, int *__restrict__ pid_new, int *__restrict__ cell_new,
         float4 *__restrict__ rec)
 {
-    if(st->rebuild_flag[par] | st->jump_flag[par]) return; // full rebuild path takes over
+    // full rebuild path takes over.  (Slab engines run the fill regardless: their flags are still being reduced
+    // over the ranks on a side stream; a full rebuild, if it comes, overwrites everything written here.)
+    if(!ignore_flags && (st->rebuild_flag[par] | st->jump_flag[par])) return;
     const int n_occ = st->n_occ;
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
     const unsigned gshift = grp * 8;
@@ -285,10 +287,36 @@ __global__ void __launch_bounds__(256) k_full_gather(const DevState *st, int par
 }
 
 // ---- slab engines: sizes of the boundary planes after the scan, and the ghost planes' part of the cell table
-__global__ void k_slab_counts(DevGrid g, DevState *st, const int *__restrict__ start_new, int has_lo, int has_hi){
+// With the halo push: the counts also go into the neighbours' mailboxes (my first plane's size + my owned count
+// to the lower neighbour's UPPER-side mailbox, my last plane's to the upper neighbour's LOWER-side one) and
+// the grid-counts flag is raised there -- no send / recv, no host round trip for the exchange of sizes.
+__global__ void k_slab_counts(DevGrid g, DevState *st, const int *__restrict__ start_new, int has_lo, int has_hi,
+        int *mail_lo, int *mail_hi, unsigned *flag_lo, unsigned *flag_hi, unsigned seq){
     const int n = st->n_own;
-    st->n_first = has_lo ? start_new[g.c_own0 + g.plane] : 0;
-    st->n_last = has_hi ? n - start_new[g.c_own1 - g.plane] : 0;
+    const int nf = has_lo ? start_new[g.c_own0 + g.plane] : 0;
+    const int nl = has_hi ? n - start_new[g.c_own1 - g.plane] : 0;
+    st->n_first = nf; st->n_last = nl;
+    if(mail_lo){ mail_lo[0] = nf; mail_lo[1] = n; }
+    if(mail_hi){ mail_hi[0] = nl; mail_hi[1] = n; }
+    __threadfence_system();
+    if(flag_lo) *(volatile unsigned *)flag_lo = seq;
+    if(flag_hi) *(volatile unsigned *)flag_hi = seq;
+}
+// Boundary planes of the freshly ordered arrays (cell-table slice, x, v, id) -> the neighbours' ghost slots:
+// up to 8 contiguous ranges, 16-byte words where the alignment allows, else 4-byte words.
+struct PushSegs { const void *src[8]; void *dst[8]; long long bytes[8]; int n; };
+__global__ void __launch_bounds__(256) k_push_planes(PushSegs S){
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for(int k = 0; k < S.n; k++){
+        const char *s = (const char *)S.src[k]; char *d = (char *)S.dst[k]; const long long b = S.bytes[k];
+        if(((((size_t)s) | ((size_t)d) | (size_t)b) & 15) == 0){
+            const uint4 *s4 = (const uint4 *)s; uint4 *d4 = (uint4 *)d;
+            for(long long i = tid; i < (b >> 4); i += nth) d4[i] = s4[i];
+        }else{
+            const int *s1 = (const int *)s; int *d1 = (int *)d;
+            for(long long i = tid; i < (b >> 2); i += nth) d1[i] = s1[i];
+        }
+    }
 }
 // recv_lo / recv_hi: the neighbour's slice of ITS cell table over the plane it sent (plane + 1 entries each).
 // Lower ghost cells end at slot 0 (negative starts), upper ghost cells begin at n_own.
@@ -510,7 +538,7 @@ __device__ __forceinline__ float bbx_rsqrt_safe(float d2){ return bbx_rsqrt_appr
 __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGrid g, DevState *st, const DevCullSet *__restrict__ cull,
         const float4 *__restrict__ pos, const float4 *__restrict__ vel, const float4 *__restrict__ rec, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
-        float4 *__restrict__ force, float4 *__restrict__ pred, int *__restrict__ queue)
+        float4 *__restrict__ force, float4 *__restrict__ pred, int *__restrict__ queue, HaloDst H)
 {
     BBX_LIST_PROLOGUE();
     if(!live) return;
@@ -537,7 +565,8 @@ __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGr
     float tvx = vi.x + k * fx, tvy = vi.y + k * fy, tvz = vi.z + k * fz;
     float tpx = pi.x + P.dt * tvx, tpy = pi.y + P.dt * tvy, tpz = pi.z + P.dt * tvz;
     pred[i] = make_float4(tpx, tpy, tpz, 0.f);
-    if(!bbx_cull(*cull, tpx, tpy, tpz, P.radius)) queue[atomicAdd(&st->qn[0], 1)] = i;
+    if(!bbx_cull(*cull, tpx, tpy, tpz, P.radius)) queue[atomicAdd(&st->qn[0], 1)] = i; // (k_collide_predict pushes its halo copy)
+    else bbx_halo_store(H, 0, 1, i, 0, make_float4(tpx, tpy, tpz, 0.f));
 }
 
 // x* of one particle from its forces + the exact collider response (restitution 0)
@@ -551,13 +580,15 @@ __device__ __forceinline__ float4 bbx_predict_exact(const StepParams &P, const D
 // queued particles of k_force_np_predict: redo the prediction with the exact FP64 response
 __global__ void __launch_bounds__(128) k_collide_predict(StepParams P, const DevState *st, const DevColliderSet *__restrict__ cs,
         const int *__restrict__ queue, const float4 *__restrict__ pos, const float4 *__restrict__ vel,
-        const float4 *__restrict__ force, float4 *__restrict__ pred)
+        const float4 *__restrict__ force, float4 *__restrict__ pred, HaloDst H)
 {
     const int qn = st->qn[0];
     for(int q = blockIdx.x * blockDim.x + threadIdx.x; q < qn; q += gridDim.x * blockDim.x){
         int i = queue[q];
         float4 f = force[i];
-        pred[i] = bbx_predict_exact(P, *cs, pos[i], vel[i], f.x, f.y, f.z);
+        const float4 x = bbx_predict_exact(P, *cs, pos[i], vel[i], f.x, f.y, f.z);
+        pred[i] = x;
+        bbx_halo_store(H, 0, 1, i, 0, x);
     }
 }
 
@@ -586,7 +617,7 @@ extern __shared__ __align__(128) unsigned char bbx_dyn_smem[];
 __global__ void __launch_bounds__(BBX_TS) k_pressure(StepParams P, DevGrid g, DevState *st, int first,
         const float4 *__restrict__ pos, const float4 *__restrict__ pred, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
-        float *__restrict__ pressure, float *__restrict__ rho_pred, float *__restrict__ rho_err, float4 *__restrict__ posq)
+        float *__restrict__ pressure, float *__restrict__ rho_pred, float *__restrict__ rho_err, float4 *__restrict__ posq, HaloDst H)
 {
     bool staged; const float *S;
     const int *scol = bbx_stage_tile<1, 3>(g, P.n, cell, cell_start, pred, bbx_dyn_smem, st, &staged, &S);
@@ -615,7 +646,9 @@ __global__ void __launch_bounds__(BBX_TS) k_pressure(StepParams P, DevGrid g, De
     float4 x0 = pos[i];
     float rho2 = rho * rho;
     // the reference skips a neighbour whose rho*^2 is ~0 (pcisph_equations3.cpp:137): NaN marks it
-    posq[i] = make_float4(x0.x, x0.y, x0.z, (rho2 < 1e-8f) ? __int_as_float(0x7fc00000) : p / rho2);
+    const float4 xq = make_float4(x0.x, x0.y, x0.z, (rho2 < 1e-8f) ? __int_as_float(0x7fc00000) : p / rho2);
+    posq[i] = xq;
+    bbx_halo_store(H, 0, 1, i, 0, xq);
     bbx_atomic_max_warp(&st->max_err_bits, fabsf(err));
 }
 
@@ -664,7 +697,7 @@ template<int INTEGRATE>
 __global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid g, DevState *st, const DevCullSet *__restrict__ cull,
         float4 *__restrict__ pos, float4 *__restrict__ vel, const float4 *__restrict__ posq, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
-        float4 *__restrict__ force, float4 *__restrict__ force_p, int *__restrict__ queue)
+        float4 *__restrict__ force, float4 *__restrict__ force_p, int *__restrict__ queue, HaloDst H)
 {
     BBX_LIST_PROLOGUE();
     if(!live) return;
@@ -695,6 +728,7 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid
         if(bbx_cull(*cull, po.x, po.y, po.z, P.radius) && bbx_inside_domain_certain(*cull, po.x, po.y, po.z)){
             bbx_integrate_flags(P, st, pi, po);
             pos[i] = po; vel[i] = vo;
+            bbx_halo_store(H, 0, 1, i, 0, po); bbx_halo_store(H, 1, 1, i, 0, vo);
         }else{
             queue[atomicAdd(&st->qn[1], 1)] = i; // pos / vel stay untouched: the exact kernel redoes the update
         }
@@ -702,7 +736,7 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid
 }
 // queued particles of k_pressure_force<1>: the exact FP64 collider response + domain clamp
 __global__ void __launch_bounds__(128) k_collide_integrate(StepParams P, DevGrid g, DevState *st, const DevColliderSet *__restrict__ cs,
-        const int *__restrict__ queue, float4 *__restrict__ pos, float4 *__restrict__ vel, const float4 *__restrict__ force)
+        const int *__restrict__ queue, float4 *__restrict__ pos, float4 *__restrict__ vel, const float4 *__restrict__ force, HaloDst H)
 {
     const int qn = st->qn[1];
     for(int q = blockIdx.x * blockDim.x + threadIdx.x; q < qn; q += gridDim.x * blockDim.x){
@@ -713,6 +747,7 @@ __global__ void __launch_bounds__(128) k_collide_integrate(StepParams P, DevGrid
         bbx_integrate_one<1>(P, g, st, cs, pi, vel[i], f.x, f.y, f.z, &po, &vo);
         bbx_integrate_flags(P, st, pi, po);
         pos[i] = po; vel[i] = vo;
+        bbx_halo_store(H, 0, 1, i, 0, po); bbx_halo_store(H, 1, 1, i, 0, vo);
     }
 }
 

@@ -211,7 +211,7 @@ template<int SPH_EOS>
 __global__ void __launch_bounds__(BBX_LT, BBX_LIST_MINB) k_cell_lists_density(StepParams P, DevGrid g, DevState *st, const int *__restrict__ occ_cells,
         const float4 *__restrict__ pos, float4 *__restrict__ vel, const int *__restrict__ cell_start,
         unsigned short *__restrict__ nbr, int *__restrict__ nbr_cnt, float *__restrict__ pressure, float4 *__restrict__ posq,
-        float4 *__restrict__ rec)
+        float4 *__restrict__ rec, HaloDst H)
 {
     __shared__ float4 s_cand[BBX_LW][BBX_CMAX + 32];
     __shared__ float4 s_pi[BBX_LW][BBX_G];
@@ -326,6 +326,12 @@ __global__ void __launch_bounds__(BBX_LT, BBX_LIST_MINB) k_cell_lists_density(St
                 // sweep; the grid fill wrote the record's x and v
                 reinterpret_cast<float *>(vel)[4 * (size_t)i + 3] = rho;
                 reinterpret_cast<float *>(rec)[8 * (size_t)i + 3] = rho;
+                if(i < H.n_first || i >= H.hi_begin){
+                    // boundary plane of a slab: the complete record goes to the neighbour's ghost slot as well
+                    const float4 pr = W.spi[idx], vv = vel[i];
+                    bbx_halo_store(H, 0, 2, i, 0, make_float4(pr.x, pr.y, pr.z, rho));
+                    bbx_halo_store(H, 0, 2, i, 1, make_float4(vv.x, vv.y, vv.z, 0.f));
+                }
                 if(SPH_EOS){
                     // Tait EOS, ComputePressureValue (sph_equations3.cpp:7-18)
                     float p = P.eos_scale * (powf(rho / P.rho0, P.eos_exponent) - 1.f);

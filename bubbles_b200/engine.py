@@ -215,6 +215,13 @@ class Engine:
         vel = np.ascontiguousarray(vel, dtype=pos.dtype)
         _check(self.lib.bbx_overwrite_state(self.h, pos.ctypes.data, vel.ctypes.data, dt))
 
+    @property
+    def p2p(self):
+        """True when halo results are stored straight into the neighbours' ghost slots (peer memory)."""
+        v = C.c_int()
+        _check(self.lib.bbx_halo_mode(self.h, C.byref(v)))
+        return bool(v.value)
+
     def overwrite_owned(self, pos, vel):
         """Overwrite the owned particles, rows in the order of the last download_owned (collective on slabs)."""
         pos, dt = self._arr(pos)

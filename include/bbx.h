@@ -247,6 +247,9 @@ int bbx_comm_unique_id(unsigned char id[BBX_NCCL_ID_BYTES]);
 int bbx_comm_init(bbx_engine *e, int rank, int nranks, const unsigned char id[BBX_NCCL_ID_BYTES]);
 /* several slab engines of one process on one device, each driven by its own host thread (same code path,
  * copies instead of NCCL): lets the slab logic be verified against the single-domain engine on one GPU */
+/* 1 when the sweeps store their boundary-plane results straight into the neighbours' ghost slots (peer
+ * memory over NVLink, CUDA IPC), 0 when every phase ends with a send / recv pair (BBX_P2P=0, or no peer access) */
+int bbx_halo_mode(bbx_engine *e, int *p2p);
 int bbx_comm_init_local(bbx_engine *e, int rank, int nranks, const char *group);
 /* plane_counts[nplanes] -> z_bounds[nranks + 1]: slabs of whole planes balanced by particle count */
 int bbx_slab_plan(int nplanes, const long long *plane_counts, int nranks, int *z_bounds);

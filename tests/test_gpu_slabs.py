@@ -211,3 +211,24 @@ def test_slab_overwrite_owned_round_trip():
     assert np.array_equal(grp.download(bb.POSITION, np.float32), one.download(bb.POSITION, np.float32))
     assert np.array_equal(grp.download(bb.VELOCITY, np.float32), one.download(bb.VELOCITY, np.float32))
     grp.close()
+
+
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_slab_halo_transports_agree(p2p, monkeypatch):
+    """The two halo transports -- stores into the neighbours' ghost slots from inside the sweeps (default) and a
+    send / recv pair per phase (BBX_P2P=0) -- must both reproduce the single domain bit for bit."""
+    monkeypatch.setenv("BBX_P2P", p2p)
+    sc = _moving_scene()
+    one = _single(sc)
+    grp, zb = _group(sc, 3)
+    grp.set_particles(sc["pos"], sc["vel"])
+    assert all(e.p2p == (p2p == "1") for e in grp.engines)  # (the neighbours' arrays are mapped at the first collective call)
+    for _ in range(40):
+        one.step_pcisph(sc["dt"])
+        grp.step_pcisph(sc["dt"])
+    for f in (bb.POSITION, bb.VELOCITY, bb.DENSITY, bb.PRESSURE):
+        assert np.array_equal(grp.download(f, np.float32), one.download(f, np.float32)), f"field {f}"
+    cc, co = grp.export_cells()
+    c1, o1 = one.export_cells()
+    assert np.array_equal(cc, c1) and np.array_equal(co, o1)
+    grp.close()
