@@ -189,6 +189,8 @@ def test_neighbor_cap_100_is_mirrored():
     assert np.array_equal(ids, tr["nbr_ids"])
     assert np.abs(eng.download(bb.DENSITY) - tr["density"]).max() / tr["density"].max() < TOL_RHO
     assert eng.stats().neighbor_overflow == tr["overflow"]
+    # (such neighbourhoods exceed the 512-candidate stage of the list build: the chunked path is what ran)
+    assert eng.stats().max_candidates > 512
 
 
 @pytest.mark.parametrize("kind", ["sphere_container", "sphere_obstacle", "box_obstacle", "sdf_torus"])
