@@ -9,7 +9,7 @@ if [ "${SKIP_CHECK:-0}" != "1" ]; then
   timeout 240 $TR scripts/slab_nccl_check.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -1 | tee gpurun_out/${TAG}_check_${N}gpu.json
 fi
 for P in ${MODES:-1 0}; do
-  BBX_P2P=$P timeout 600 $TR bench.py --gpus $N --steps ${STEPS:-50} --warmup 10 "$@" 2>&1 | grep "^{" | tail -1 > gpurun_out/${TAG}_bench_${N}gpu_p2p$P.json
+  BBX_P2P=$P timeout 600 $TR bench.py --gpus $N --steps ${STEPS:-50} --warmup ${WARMUP:-10} "$@" 2>&1 | grep "^{" | tail -1 > gpurun_out/${TAG}_bench_${N}gpu_p2p$P.json
   python - <<PY
 import json
 try:
