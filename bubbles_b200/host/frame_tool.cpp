@@ -1,0 +1,32 @@
+// frame_tool: writes one bbtool-readable text frame with the facade's SerializerSaveSphDataSet3 from a raw state
+// file -- host only (no engine), used by tests/test_frame_writer.py to compare the writer byte for byte with the
+// reference's own (src/third/serializer.cpp:812-921) and to feed the reference's reader.
+//   frame_tool <state.bin> <out.txt> <flags>
+//   state.bin: int64 n, double spacing, double mass, double pos[3n], double vel[3n], double rho[n]
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "bubbles_api.h"
+
+int main(int argc, char **argv){
+    if(argc < 4){ std::fprintf(stderr, "usage: frame_tool state.bin out.txt flags\n"); return 2; }
+    FILE *fp = std::fopen(argv[1], "rb");
+    if(!fp){ std::fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
+    int64_t n = 0; double spacing = 0, mass = 0;
+    size_t r = std::fread(&n, sizeof(n), 1, fp) + std::fread(&spacing, 8, 1, fp) + std::fread(&mass, 8, 1, fp);
+    std::vector<double> pos(3 * (size_t)n), vel(3 * (size_t)n), rho((size_t)n);
+    r += std::fread(pos.data(), 8, pos.size(), fp) + std::fread(vel.data(), 8, vel.size(), fp) + std::fread(rho.data(), 8, rho.size(), fp);
+    std::fclose(fp);
+    if(r != 3 + 7 * (size_t)n){ std::fprintf(stderr, "short state file\n"); return 2; }
+    bbx::ParticleSetBuilder3 b;
+    for(int64_t i = 0; i < n; i++) b.AddParticle(bbx::vec3f(pos[3*i], pos[3*i+1], pos[3*i+2]), bbx::vec3f(vel[3*i], vel[3*i+1], vel[3*i+2]));
+    auto set = bbx::SphParticleSet3FromBuilder(&b);
+    set->SetTargetSpacing(spacing);
+    set->set.mass = mass;
+    for(int64_t i = 0; i < n; i++) set->set.densities[(size_t)i] = rho[(size_t)i];
+    auto data = bbx::DefaultSphSolverData3(true);
+    data->sphpSet = set;
+    bbx::SerializerSaveSphDataSet3(data.get(), argv[2], std::atoi(argv[3]));
+    return 0;
+}

@@ -20,6 +20,7 @@
 #include <sstream>
 #include <iostream>
 #include <chrono>
+#include <serializer.h>
 
 #include <pcisph_solver.h>
 #include <sph_solver.h>
@@ -406,6 +407,28 @@ int main(int argc, char **argv){
             WriteNpy<double>(prefix + "pos.npy", pos.data(), n, 3);
             WriteNpy<double>(prefix + "vel.npy", vel.data(), n, 3);
             WriteNpy<int32_t>(prefix + "hit.npy", hit.data(), n, 0);
+        }
+        else if(cmd == "save_frame"){
+            // the reference's own frame writer (SerializerSaveSphDataSet3, src/third/serializer.cpp:884-921) on the current state
+            std::string file; int flags; in >> file >> flags;
+            SerializerSaveSphDataSet3(H.data, file.c_str(), flags);
+        }
+        else if(cmd == "load_frame"){
+            // the reference's own frame reader (what bbtool uses: SerializerLoadParticles3, serializer.cpp:444-559)
+            std::string file, prefix; in >> file >> prefix;
+            std::vector<SerializedParticle> ps; int flags = 0;
+            int n = SerializerLoadParticles3(&ps, file.c_str(), flags);
+            std::vector<double> pos(3 * (size_t)std::max(n, 0)), vel(3 * (size_t)std::max(n, 0)), rho((size_t)std::max(n, 0)), mass((size_t)std::max(n, 0));
+            for(int i = 0; i < n; i++){
+                pos[3*i] = ps[i].position.x; pos[3*i+1] = ps[i].position.y; pos[3*i+2] = ps[i].position.z;
+                vel[3*i] = ps[i].velocity.x; vel[3*i+1] = ps[i].velocity.y; vel[3*i+2] = ps[i].velocity.z;
+                rho[i] = ps[i].density; mass[i] = (flags & SERIALIZER_MASS) ? ps[i].mass : 0.0;
+            }
+            WriteNpy<double>(prefix + "pos.npy", pos.data(), n, 3);
+            WriteNpy<double>(prefix + "vel.npy", vel.data(), n, 3);
+            WriteNpy<double>(prefix + "rho.npy", rho.data(), n, 0);
+            WriteNpy<double>(prefix + "mass.npy", mass.data(), n, 0);
+            printf("[bbref] load_frame count=%d flags=%d\n", n, flags);
         }
         else if(cmd == "sdf_nodes"){
             // report the node layout of SDF collider idx so the test can sample its analytic SDF there

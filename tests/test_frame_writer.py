@@ -1,0 +1,77 @@
+"""SURVEY.md 8(f) row 1 -- frame files: the facade's SerializerSaveSphDataSet3 (bubbles_b200/host/bubbles_api.h)
+against the reference's OWN serializer (src/third/serializer.cpp), through the unmodified-reference harness:
+  * writer: the same particle state written by the reference (SaveSphParticleSet, :884-921) and by the facade
+    must give byte-identical files, for every field combination the facade supports (p, pv, pvd, pvdm);
+  * reader: the file the facade wrote is loaded by the reference's reader (SerializerLoadParticles3, :444-559 --
+    what `bbtool view / pbr / surface` call) and must give the count, the format and the "%g" values back.
+CPU only (the facade's particle set is a host mirror; no engine is involved)."""
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as G
+from oracle import oracle as O
+import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOOL = os.path.join(ROOT, "bubbles_b200", "lib", "frame_tool")
+P, V, D, M = 0x01, 0x02, 0x04, 0x20
+
+pytestmark = pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/bbref not built (reference sources absent)")
+
+
+def _tool():
+    if not os.path.exists(TOOL):
+        G.build()
+    return TOOL
+
+
+def _reference_state(tmp_path):
+    """Probe scene advanced 3 sub-steps by the reference; returns the harness job prefix + dumped arrays."""
+    sc = scenes.probe_scene()
+    O.write_particles(str(tmp_path / "p.bin"), sc["pos"], sc["vel"])
+    half = sc["domain_max"]
+    I = O.mat_str(np.eye(4))
+    job = ["threads 2", f"spacing {sc['spacing']}", f"scale {sc['scale']}",
+           f"collider box {I} {float(2 * half[0])!r} {float(2 * half[1])!r} {float(2 * half[2])!r} 1 0", "domain_from_collider 0",
+           f"particles {tmp_path}/p.bin", "setup", f"step {sc['dt']} 3", f"dump {tmp_path}/s_"]
+    return sc, job
+
+
+@pytest.mark.parametrize("flags", [P, P | V, P | V | D, P | V | D | M])
+def test_writer_is_byte_identical_to_the_reference_and_its_reader_loads_it(tmp_path, flags):
+    sc, job = _reference_state(tmp_path)
+    ref_txt, our_txt = tmp_path / "ref.txt", tmp_path / "bbx.txt"
+    out, _ = O.run_ref(job + [f"save_frame {ref_txt} {flags}"], str(tmp_path))
+    pos, vel, rho = (np.load(tmp_path / f"s_{k}.npy") for k in ("pos", "vel", "density"))
+    n = len(pos)
+    # the mass the reference wrote (ParticleSet3::GetMass) is a Setup scalar: take it from the engine-independent
+    # host arithmetic the facade uses (bbx_get_mass needs an engine; the oracle restates ComputeMass)
+    orc = scenes.make_oracle(sc)
+    mass = float(orc.P.mass)
+    with open(tmp_path / "state.bin", "wb") as f:
+        f.write(struct.pack("<qdd", n, float(sc["spacing"]), mass))
+        f.write(np.ascontiguousarray(pos, np.float64).tobytes())
+        f.write(np.ascontiguousarray(vel, np.float64).tobytes())
+        f.write(np.ascontiguousarray(rho, np.float64).tobytes())
+    r = subprocess.run([_tool(), str(tmp_path / "state.bin"), str(our_txt), str(flags)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(our_txt, "rb").read() == open(ref_txt, "rb").read()
+    # the reference's reader on OUR file
+    out, _ = O.run_ref([f"load_frame {our_txt} {tmp_path}/l_"], str(tmp_path))
+    m = re.search(r"load_frame count=(\d+) flags=(\d+)", out)
+    assert m and int(m.group(1)) == n and int(m.group(2)) == flags
+    g = lambda a: np.array([float("%g" % x) for x in np.ravel(a)]).reshape(np.shape(a))  # what "%g" keeps
+    # (the reference parses decimals with its own digit loop, ParseFloat: equal to strtod up to the last bits)
+    same = lambda a, b: np.allclose(a, b, rtol=1e-14, atol=0.0)
+    assert same(np.load(tmp_path / "l_pos.npy"), g(pos))
+    if flags & V:
+        assert same(np.load(tmp_path / "l_vel.npy"), g(vel))
+    if flags & D:
+        assert same(np.load(tmp_path / "l_rho.npy"), g(rho))
+    if flags & M:
+        assert same(np.load(tmp_path / "l_mass.npy"), np.full(n, float("%g" % mass)))
