@@ -80,56 +80,61 @@ __device__ __noinline__ void bbx_list_overflow_row(const StepParams &P, const De
 
 struct ListWarp {
     float4 *cand;            // [BBX_CMAX + 32] staged candidates (u_j.x, u_j.y, u_j.z, bits of the list entry)
+    unsigned short *ent;     // [BBX_CMAX] list entries of the raw candidates (first pass of the staging)
     float4 *spi;             // [BBX_G] own particles of the group, raw positions (FP64 re-check, cap-100 slow path)
     unsigned short *rows;    // [BBX_G][BBX_ROW] lists being built
     int *tab;                // [0..9] exclusive prefix of the 9 run lengths (tab[9] = T), [10..18] first slot of each run
     int *cnt;                // [BBX_G]
 };
 
-// Candidate of flat index f (clamped to T - 1) of the cell's neighbourhood: raw position and list entry.
-struct ListFetch { float4 raw; unsigned entry; };
-__device__ __forceinline__ ListFetch bbx_list_fetch(DevState *st, const ListWarp &W, int T, int f, const float4 *__restrict__ pos){
-    ListFetch c;
-    const int fc = min(f, T - 1);
-    int r = 0;
-#pragma unroll
-    for(int q = 1; q < 9; q++) r += (fc >= W.tab[q]) ? 1 : 0;
-    const int off = fc - W.tab[r];
-    c.raw = pos[W.tab[10 + r] + off];
-    c.entry = ((unsigned)r << BBX_RUN_SHIFT) | (unsigned)min(off, BBX_MAX_RUN_LEN - 1);
-    if(off >= BBX_MAX_RUN_LEN) st->error = BBX_ERR_CAPACITY;
-    return c;
-}
-
 // Stage candidates of the cell's neighbourhood in flat order (run-major, slot order), starting at flat index
-// f0, until all T are consumed (f0 = T on return) or BBX_CMAX candidates are staged; returns the number staged
-// (the array is padded to a multiple of 32 with candidates that are never accepted).  Loads run two rounds
-// ahead of their use.
-// A candidate farther than h from the cell's box cannot be a neighbour of any particle of the cell and is
-// dropped here (ballot compaction keeps the flat order): ~24 % of the 27-cell neighbourhood.
-// (x - centre) is exact in FP32: both are multiples of the finer ulp and the difference is small.
+// f0: up to BBX_CMAX of them per call (f0 advances; f0 = T when all are consumed); returns the number staged
+// (the array is padded to a multiple of 32 with candidates that are never accepted).
+//   pass 1: the raw positions go global -> shared with cp.async (LDGSTS, 16 B per candidate, every copy of the
+//           chunk in flight at once -- nothing waits on a load), the list entry (run, offset) beside them;
+//   pass 2: in place, round by round: cell frame u = (x - centre) / h (exact subtraction in FP32: both are
+//           multiples of the finer ulp and the difference is small), and a candidate farther than h from the
+//           cell's box -- it cannot be a neighbour of any particle of the cell -- is dropped (ballot compaction
+//           keeps the flat order): ~24 % of the 27-cell neighbourhood.
 __device__ __forceinline__ int bbx_list_stage(const StepParams &P, DevState *st, const ListWarp &W, int T, int lane, int &f0,
         float cx, float cy, float cz, float hx, float hy, float hz, const float4 *__restrict__ pos)
 {
     __syncwarp();
     const unsigned lt = lanemask_lt();
+    const int c0 = f0, nc = min(BBX_CMAX, T - c0);
+    {
+        int r = 0;
+        const unsigned cand_addr = (unsigned)__cvta_generic_to_shared(W.cand);
+#pragma unroll 2
+        for(int k = lane; k < nc; k += 32){
+            const int f = c0 + k;
+            while(f >= W.tab[r + 1]) r++;           // runs only move forward (tab[9] = T > f)
+            const int off = f - W.tab[r];
+            const float4 *src = pos + W.tab[10 + r] + off;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(cand_addr + 16u * (unsigned)k), "l"(src) : "memory");
+            W.ent[k] = (unsigned short)(((unsigned)r << BBX_RUN_SHIFT) | (unsigned)min(off, BBX_MAX_RUN_LEN - 1));
+            if(off >= BBX_MAX_RUN_LEN) st->error = BBX_ERR_CAPACITY;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
     int n = 0;
-    int f = f0;
-    ListFetch a = bbx_list_fetch(st, W, T, f + lane, pos), b = a;
-    if(f + 32 < T) b = bbx_list_fetch(st, W, T, f + 32 + lane, pos);
 #pragma unroll 1
-    for(; f < T && n < BBX_CMAX; f += 32){
-        const ListFetch c = a;
-        a = b;
-        if(f + 64 < T) b = bbx_list_fetch(st, W, T, f + 64 + lane, pos);
-        const float ux = (c.raw.x - cx) * P.inv_h, uy = (c.raw.y - cy) * P.inv_h, uz = (c.raw.z - cz) * P.inv_h;
+    for(int k0 = 0; k0 < nc; k0 += 32){
+        const int k = k0 + lane;
+        const float4 raw = W.cand[min(k, nc - 1)];
+        const unsigned entry = W.ent[min(k, nc - 1)];
+        __syncwarp(); // every lane has read its candidate before the compacted ones overwrite this range
+        const float ux = (raw.x - cx) * P.inv_h, uy = (raw.y - cy) * P.inv_h, uz = (raw.z - cz) * P.inv_h;
         const float gx = fmaxf(fabsf(ux) - hx, 0.f), gy = fmaxf(fabsf(uy) - hy, 0.f), gz = fmaxf(fabsf(uz) - hz, 0.f);
-        const bool keep = (f + lane < T) && (fmaf(gx, gx, fmaf(gy, gy, gz * gz)) < 1.001f);
+        const bool keep = (k < nc) && (fmaf(gx, gx, fmaf(gy, gy, gz * gz)) < 1.001f);
         const unsigned msk = __ballot_sync(BBX_FULL, keep);
-        if(keep) W.cand[n + __popc(msk & lt)] = make_float4(ux, uy, uz, __uint_as_float(c.entry));
+        if(keep) W.cand[n + __popc(msk & lt)] = make_float4(ux, uy, uz, __uint_as_float(entry));
         n += __popc(msk);
     }
-    f0 = min(f, T);
+    f0 = c0 + nc;
+    __syncwarp();
     if(n + lane < ((n + 31) & ~31)) W.cand[n + lane] = make_float4(1.0e15f, 0.f, 0.f, 0.f);
     __syncwarp();
     return n;
@@ -214,13 +219,14 @@ __global__ void __launch_bounds__(BBX_LT, BBX_LIST_MINB) k_cell_lists_density(St
         float4 *__restrict__ rec, HaloDst H)
 {
     __shared__ float4 s_cand[BBX_LW][BBX_CMAX + 32];
+    __shared__ unsigned short s_ent[BBX_LW][BBX_CMAX];
     __shared__ float4 s_pi[BBX_LW][BBX_G];
     __shared__ __align__(16) unsigned short s_rows[BBX_LW][BBX_G * BBX_ROW];
     __shared__ int s_tab[BBX_LW][20];
     __shared__ int s_cnt[BBX_LW][BBX_G];
     __shared__ float s_ovs[BBX_LW][BBX_G];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    ListWarp W; W.cand = s_cand[warp]; W.spi = s_pi[warp]; W.rows = s_rows[warp]; W.tab = s_tab[warp]; W.cnt = s_cnt[warp];
+    ListWarp W; W.cand = s_cand[warp]; W.ent = s_ent[warp]; W.spi = s_pi[warp]; W.rows = s_rows[warp]; W.tab = s_tab[warp]; W.cnt = s_cnt[warp];
     float *sovs = s_ovs[warp];
     const int n_occ = st->n_occ;
     const int nwarps = gridDim.x * BBX_LW;
