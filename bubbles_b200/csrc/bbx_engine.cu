@@ -341,6 +341,23 @@ int bbx_set_particles_ids(bbx_engine *e, int n, const void *pos, const void *vel
     return set_particles(e, n, pos, vel, ids, dtype);
 }
 
+// Re-sort after an append: old particles keep their recorded cell and their order inside it, the appended ones
+// follow in id order.  Counting sort by cell with the full-rebuild kernels, ordered by OLD SLOT (old slots are in
+// chain order, the appended particles sit behind them in id order).  Not a grid epoch: flags and parity stay.
+static int append_update(bbx_engine *e, int n_old, int k){
+    DevGrid &g = e->grid;
+    const int cur = e->cur, nxt = cur ^ 1, n_all = n_old + k, par = e->epoch & 1;
+    LAUNCH(e, k_append_hash, div_up(std::max(n_all, e->scan_tiles), 256), 256, n_old, k, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st, e->scan_status, e->scan_tiles);
+    LAUNCH(e, k_scan_cells, e->scan_tiles, 256, e->count, g.total, 0, e->scan_status, e->st, e->cell_start[nxt], e->occ_cells);
+    LAUNCH(e, k_full_scatter, div_up(n_all, 256), 256, n_all, 0, g, e->st, par, 1, e->newcell, e->cell_start[nxt], e->count, e->perm);
+    LAUNCH(e, k_full_sort_cells, div_up(g.total, 256), 256, g, e->st, par, 1, e->cell_start[nxt], (const int *)nullptr, e->perm, e->count);
+    LAUNCH(e, k_full_gather, div_up(n_all, 256), 256, e->st, par, 1, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
+           e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec);
+    CU(cudaGetLastError());
+    e->cur = nxt; e->n = n_all; e->have_chains = 1;
+    return BBX_OK;
+}
+
 int bbx_append_particles(bbx_engine *e, int n, const void *pos, const void *vel, int dtype){
     CHECK_ENGINE(e);
     if(n <= 0) return BBX_OK;
@@ -357,7 +374,11 @@ int bbx_append_particles(bbx_engine *e, int n, const void *pos, const void *vel,
         e->force_full = 0;
         return BBX_OK;
     }
-    return set_error(BBX_ERR_INVALID, "bbx_append_particles after stepping is not implemented yet");
+    // after stepping: ContinuousParticleSetBuilder3::Commit (grid.h:1424-1441) -- the chains of the existing
+    // particles stay as they are, the new ids go to the tail of the chain of the cell they hash to
+    const int n_old = e->n;
+    int rc = upload_particles(e, n_old, n, pos, vel, nullptr, dtype); if(rc) return rc;
+    return append_update(e, n_old, n);
 }
 
 int bbx_particle_count(bbx_engine *e, int *n){ if(!e || !n) return set_error(BBX_ERR_INVALID, "null"); *n = e->n; return BBX_OK; }

@@ -252,6 +252,8 @@ __global__ void __launch_bounds__(256) k_full_scatter(int n_all, int n_lo, DevGr
         perm[start_new[c] + k] = i;
     }
 }
+// pid_old = null: order by the OLD SLOT instead of the particle id (bbx_append_particles: old chains first, in
+// their order, then the appended particles in id order -- DistributeByParticleList, grid.h:358-387)
 __global__ void __launch_bounds__(256) k_full_sort_cells(DevGrid g, const DevState *st, int par, int force, const int *__restrict__ start_new,
         const int *__restrict__ pid_old, int *__restrict__ perm, int *__restrict__ cursor)
 {
@@ -260,12 +262,37 @@ __global__ void __launch_bounds__(256) k_full_sort_cells(DevGrid g, const DevSta
         cursor[c] = 0; // back to an all-zero histogram for the next sub-step
         int s = start_new[c], e = start_new[c + 1];
         for(int a = s + 1; a < e; a++){ // insertion sort by original id (segments are a dozen long)
-            int pa = perm[a]; int ka = pid_old[pa];
+            int pa = perm[a]; int ka = pid_old ? pid_old[pa] : pa;
             int b = a - 1;
-            while(b >= s && pid_old[perm[b]] > ka){ perm[b + 1] = perm[b]; b--; }
+            while(b >= s && (pid_old ? pid_old[perm[b]] : perm[b]) > ka){ perm[b + 1] = perm[b]; b--; }
             perm[b + 1] = pa;
         }
     }
+}
+// bbx_append_particles after stepping: cells of the old particles are the RECORDED ones (chains are not
+// re-hashed by an append), the new particles [n_old, n_old + k) hash their positions; histogram for the scan.
+__global__ void __launch_bounds__(256) k_append_hash(int n_old, int k, const float4 *__restrict__ pos, const int *__restrict__ oldcell,
+        int *__restrict__ newcell, int *__restrict__ count, DevGrid g, DevState *st,
+        unsigned long long *__restrict__ scan_status, int scan_tiles)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i == 0){ st->scan_ticket = 0; st->n_occ = 0; }
+    if(i < scan_tiles) scan_status[i] = 0ull;
+    if(i >= n_old + k) return;
+    int c;
+    if(i < n_old) c = oldcell[i];
+    else{
+        float4 p = pos[i];
+        int ux, uy, uz;
+        c = bbx_hash(g, p.x, p.y, p.z, &ux, &uy, &uz);
+        if(c < 0){ // outside the domain (the reference would index out of bounds): clamp + sticky error
+            ux = min(max(ux, 0), g.n[0] - 1); uy = min(max(uy, 0), g.n[1] - 1); uz = min(max(uz, 0), g.n[2] - 1);
+            c = ux + uy * g.n[0] + uz * g.plane;
+            st->error = BBX_ERR_OUT_OF_DOMAIN;
+        }
+    }
+    newcell[i] = c;
+    atomicAdd(&count[c], 1);
 }
 __global__ void __launch_bounds__(256) k_full_gather(const DevState *st, int par, int force, const int *__restrict__ perm,
         const int *__restrict__ newcell,

@@ -230,6 +230,8 @@ struct ParticleSet3 {
 struct SphParticleSet3 {
     ParticleSet3 set;
     Float targetSpacing = 0.1, kernelRadiusOverSpacing = 2.0, targetDensity = WaterDensity;
+    int reservedSize = 0;          // ContinuousParticleSetBuilder3: room for particles emitted during the run
+    bbx_engine *engine = nullptr;  // set by the solver's Setup: appended particles go to the device as well
     ParticleSet3 *GetParticleSet(){ return &set; }
     void SetRelativeKernelRadius(Float r){ kernelRadiusOverSpacing = r; }
     void SetTargetSpacing(Float s){ targetSpacing = s; }
@@ -241,6 +243,34 @@ inline std::shared_ptr<SphParticleSet3> SphParticleSet3FromBuilder(ParticleSetBu
     s->set.positions = b->positions; s->set.velocities = b->velocities; s->set.densities.assign(b->positions.size(), 0.0);
     return s;
 }
+
+// ContinuousParticleSetBuilder3 (src/core/grid.h:1246-1450): a particle set with reserved room; AddParticle queues,
+// Commit appends (ids continue from the current count) -- on the device the new particles join the tail of their
+// cells' chains exactly like DistributeByParticleList (bbx_append_particles).  MapGridEmit (the host-side
+// re-emission policy over the cell chains) is not provided: emit with an emitter, or AddParticle + Commit.
+struct ContinuousParticleSetBuilder3 {
+    std::vector<vec3f> positions, velocities;
+    std::shared_ptr<SphParticleSet3> particleSet = std::make_shared<SphParticleSet3>();
+    int maxNumOfParticles;
+    explicit ContinuousParticleSetBuilder3(int maxParticles = 2500000) : maxNumOfParticles(maxParticles > 1 ? maxParticles : 1) { particleSet->reservedSize = maxNumOfParticles; }
+    void SetKernelRadius(Float){}
+    template<typename G> void MapGrid(const G &){} // the engine owns the grid; nothing to map on the host
+    int AddParticle(const vec3f &pos, const vec3f &vel = vec3f(0)){
+        if(particleSet->set.GetParticleCount() + (int)positions.size() + 1 > maxNumOfParticles) return 0;
+        positions.push_back(pos); velocities.push_back(vel); return 1;
+    }
+    void Commit(){
+        if(positions.empty()) return;
+        ParticleSet3 &ps = particleSet->set;
+        if(particleSet->engine) Check(bbx_append_particles(particleSet->engine, (int)positions.size(), positions.data(), velocities.data(), BBX_F64));
+        ps.positions.insert(ps.positions.end(), positions.begin(), positions.end());
+        ps.velocities.insert(ps.velocities.end(), velocities.begin(), velocities.end());
+        ps.densities.resize(ps.positions.size(), 0.0);
+        positions.clear(); velocities.clear();
+    }
+    int GetParticleCount() const { return particleSet->set.GetParticleCount(); }
+};
+inline std::shared_ptr<SphParticleSet3> SphParticleSet3FromContinuousBuilder(ContinuousParticleSetBuilder3 *b){ b->Commit(); return b->particleSet; }
 
 // ----------------------------------------------------------------------------------------- emitters
 // BccLatticePointGenerator::ForEach (src/generator/bcclattice.cpp:5-36)
@@ -266,7 +296,7 @@ struct VolumeParticleEmitter3 {
     VolumeParticleEmitter3(const ShapePtr &s, const Bounds3f &b, Float sp, const vec3f &v = vec3f(0)) : shape(s), bound(b), spacing(sp), initVel(v) {}
     void SetJitter(Float j){ jitter = j < 0 ? 0 : (j > 1 ? 1 : j); }
     void SetValidator(std::function<bool(const vec3f &)> f){ validator = std::move(f); }
-    void Emit(ParticleSetBuilder3 *builder){
+    template<typename Builder> void Emit(Builder *builder){ // ParticleSetBuilder3 or ContinuousParticleSetBuilder3
         const Float maxJitter = 0.5 * jitter * spacing;
         BccLatticeForEach(bound, spacing, [&](const vec3f &point) -> bool {
             if(validator && !validator(point)) return true;
@@ -285,7 +315,7 @@ struct VolumeParticleEmitterSet3 {
     std::vector<VolumeParticleEmitter3 *> emitters;
     void AddEmitter(VolumeParticleEmitter3 *e){ emitters.push_back(e); }
     void SetJitter(Float j){ for(auto *e : emitters) e->SetJitter(j); }
-    void Emit(ParticleSetBuilder3 *b){ for(auto *e : emitters) e->Emit(b); }
+    template<typename Builder> void Emit(Builder *b){ for(auto *e : emitters) e->Emit(b); b->Commit(); }
 };
 
 // --------------------------------------------------------------------------------------------- grid
@@ -330,7 +360,7 @@ class SolverBase3 {
   public:
     SolverBase3(const SolverBase3 &) = delete;
     SolverBase3 &operator=(const SolverBase3 &) = delete;
-    ~SolverBase3(){ if(engine) bbx_destroy(engine); }
+    ~SolverBase3(){ if(engine){ if(data && data->sphpSet) data->sphpSet->engine = nullptr; bbx_destroy(engine); } }
     void Initialize(const std::shared_ptr<SphSolverData3> &d){ data = d; }
     void Setup(Float targetDensity, Float targetSpacing, Float relativeRadius, const std::shared_ptr<Grid3> &domain,
                const std::shared_ptr<SphParticleSet3> &pSet, int maxParticles = 0){
@@ -341,10 +371,12 @@ class SolverBase3 {
         c.spacing = targetSpacing; c.kernel_scale = relativeRadius; c.target_density = targetDensity; c.grid = domain->desc;
         const int n = pSet->set.GetParticleCount();
         c.max_particles = maxParticles > n ? maxParticles : (n > 0 ? n : 1);
+        if(pSet->reservedSize > c.max_particles) c.max_particles = pSet->reservedSize;
         if(engine){ bbx_destroy(engine); engine = nullptr; }
         Check(bbx_create(&c, &engine));
         Check(bbx_get_mass(engine, &pSet->set.mass));
         if(n > 0) Check(bbx_set_particles(engine, n, pSet->set.positions.data(), pSet->set.velocities.data(), BBX_F64));
+        pSet->engine = engine;
         if(data->collider) SetColliders(data->collider);
     }
     void SetColliders(const std::shared_ptr<ColliderSet3> &colliders){

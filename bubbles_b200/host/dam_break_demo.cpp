@@ -3,11 +3,13 @@
 // (MakeBox / VolumeParticleEmitter3 / UtilBuildGridForDomain / ColliderSetBuilder3 / PciSphSolver3 /
 // SerializerSaveSphDataSet3 / PciSphRunSimulation3), host code only -- every kernel runs inside libbbx.so.
 //
-//   dam_break_demo [--scaling S] [--frames N] [--steps N --dt X] [--jitter J] [--out DIR] [--dump FILE] [--sph]
+//   dam_break_demo [--scaling S] [--frames N] [--steps N --dt X] [--jitter J] [--out DIR] [--dump FILE] [--sph] [--emit K]
 //     --scaling  domainScaling of the reference scene (2.5 there: ~0.9 M particles; default 0.6: ~12 k)
 //     --frames   frames of 1/240 s through Advance() (CFL sub-stepping), default 2
 //     --steps    instead of frames: N fixed-dt sub-steps (AdvanceTimeStep)
 //     --out      directory for the text frames bbtool reads (out_<frame>.txt), off by default
+//     --emit     continuous emission (ContinuousParticleSetBuilder3): after every frame K more particles enter above the
+//                fluid (AddParticle + Commit), as the reference's MapGridEmit scenes do
 //     --dump     raw little-endian doubles: n, then n x 3 positions, n x 3 velocities (for the parity test)
 #include <cstdio>
 #include <cstdlib>
@@ -20,7 +22,7 @@ using namespace bbx;
 
 int main(int argc, char **argv){
     Float domainScaling = 0.6f, jitter = 0.001, dt = 0;
-    int frames = 2, steps = 0; bool sph = false;
+    int frames = 2, steps = 0, emit = 0; bool sph = false;
     std::string out, dump;
     for(int i = 1; i < argc; i++){
         std::string a = argv[i];
@@ -33,6 +35,7 @@ int main(int argc, char **argv){
         else if(a == "--out") out = next();
         else if(a == "--dump") dump = next();
         else if(a == "--sph") sph = true;
+        else if(a == "--emit") emit = std::atoi(next().c_str());
         else{ std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try{
@@ -50,7 +53,7 @@ int main(int argc, char **argv){
         ShapePtr container = MakeBox(Transform(), containerSize, true);
         ShapePtr boxp = MakeBox(Translate(xof, -yof, zof), boxSize);
 
-        ParticleSetBuilder3 pBuilder;
+        ContinuousParticleSetBuilder3 pBuilder(2500000);   // (room for --emit; otherwise the same as ParticleSetBuilder3)
         VolumeParticleEmitterSet3 emitterSet;
         VolumeParticleEmitter3 emitterp(boxp, boxp->GetBounds(), spacing, vec3f(0, -6, 0));
         emitterSet.AddEmitter(&emitterp);
@@ -62,7 +65,8 @@ int main(int argc, char **argv){
         cBuilder.AddCollider3(container);
         auto colliders = cBuilder.GetColliderSet();
 
-        auto sphSet = SphParticleSet3FromBuilder(&pBuilder);
+        auto sphSet = SphParticleSet3FromContinuousBuilder(&pBuilder);
+        if(!emit) sphSet->reservedSize = 0;              // no emission: size the engine for the block alone
         sphSet->SetRelativeKernelRadius(spacingScale);
         std::printf("particles %d, cells %d (%d x %d x %d)\n", pBuilder.GetParticleCount(), domainGrid->desc.total,
                     domainGrid->desc.n[0], domainGrid->desc.n[1], domainGrid->desc.n[2]);
@@ -90,6 +94,13 @@ int main(int argc, char **argv){
                     if(step == 0){ save(0); return 1; }
                     std::printf("Step (%d) : %g ms - Particles %d\n", step - 1, solver.GetAdvanceTime(), solver.GetParticleCount());
                     save(step);
+                    if(emit && step < frames){
+                        // a sheet of K particles one spacing apart, dropped from above the block
+                        int side = 1; while(side * side < emit) side++;
+                        for(int q = 0; q < emit; q++)
+                            pBuilder.AddParticle(vec3f(xof - 0.5 * boxFluidLen + spacing * (q % side + 1), 0.5 * boxYLen - 3 * spacing, zof - 0.5 * boxFluidLen + spacing * (q / side + 1)), vec3f(0, -3, 0));
+                        pBuilder.Commit();
+                    }
                     return step >= frames ? 0 : 1;
                 });
             }

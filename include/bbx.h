@@ -182,8 +182,10 @@ int bbx_set_particles(bbx_engine *e, int n, const void *pos, const void *vel, in
  * keeps the particles whose cell plane it owns and ignores the rest, so every rank may pass the whole
  * scene or just its share.  Collective over the slab group (ends with the first ghost exchange).        */
 int bbx_set_particles_ids(bbx_engine *e, int n, const void *pos, const void *vel, const int *ids, int dtype);
-/* ContinuousParticleSetBuilder3-style append: new ids continue from the current count, new
- * particles go to the tail of their cell's chain (DistributeByParticleList, grid.h:358-387) */
+/* ContinuousParticleSetBuilder3::AddParticle + Commit (grid.h:1409-1441): new ids continue from the current
+ * count, the new particles go to the tail of their cell's chain (DistributeByParticleList, grid.h:358-387), the
+ * chains of the existing particles are left as they are.  Works before and between steps (neighbour lists are
+ * refreshed by the next sub-step); not available on slab engines. */
 int bbx_append_particles(bbx_engine *e, int n, const void *pos, const void *vel, int dtype);
 int bbx_particle_count(bbx_engine *e, int *n);
 /* overwrite positions+velocities of the existing particles (id order) without touching chains */

@@ -193,6 +193,33 @@ class Oracle:
         # PciSphSolver3::Setup: initial serial DistributeByParticle (pcisph_solver3.cpp:140-143)
         self.L.orc_full_rebuild(C.byref(self.P.grid), n, _p(a["pos"]), _p(a["cell_count"]), _p(a["cell_order"]))
 
+    def append_particles(self, pos, vel):
+        """ContinuousParticleSetBuilder3::AddParticle + Commit (src/core/grid.h:1409-1441): ids continue from n, the
+        new particles join the tail of their cells' chains; everything else of the old state is kept."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        vel = np.ascontiguousarray(vel, dtype=np.float64).reshape(-1, 3)
+        k, n = len(pos), self.S.n
+        if k == 0:
+            return
+        old = {name: self.arr(name) for name in self.a}   # current roles (the chain buffers may be swapped)
+        a = {}
+        for name in ("pos", "vel", "force", "pos_pred", "vel_pred", "force_p"):
+            a[name] = np.zeros((n + k, 3)); a[name][:n] = old[name]
+        a["pos"][n:] = pos; a["vel"][n:] = vel
+        for name in ("density", "pressure", "density_pred"):
+            a[name] = np.zeros(n + k); a[name][:n] = old[name]
+        total = self.P.grid.total
+        a["cell_count"] = np.zeros(total, dtype=np.int32); a["cell_count2"] = np.zeros(total, dtype=np.int32)
+        a["cell_order"] = np.zeros(n + k, dtype=np.int32); a["cell_order2"] = np.zeros(n + k, dtype=np.int32)
+        self.L.orc_append_chains(C.byref(self.P.grid), n, k, _p(pos), _p(old["cell_count"]), _p(old["cell_order"]),
+                                 _p(a["cell_count"]), _p(a["cell_order"]))
+        a["nbr_count"] = np.zeros(n + k, dtype=np.int32); a["nbr_count"][:n] = old["nbr_count"]
+        a["nbr_ids"] = np.full((n + k, MAX_BUCKET), -1, dtype=np.int32); a["nbr_ids"][:n] = old["nbr_ids"]
+        self.a = a
+        self.S.n = n + k
+        for name, v in a.items():
+            setattr(self.S, name, v.ctypes.data)
+
     def arr(self, name):
         """numpy view of a state array (follows the chain double-buffer swap)."""
         ptr = getattr(self.S, name)

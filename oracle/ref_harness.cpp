@@ -94,6 +94,7 @@ struct Harness{
     std::vector<Shape *> shapes;
     std::vector<Float> frictions;
     ParticleSetBuilder3 builder;
+    ContinuousParticleSetBuilder3 *cbuilder = nullptr; // `continuous <max>`: reserve room so that `append` can add particles between steps
     Grid3 *grid = nullptr;
     PciSphSolver3 pci;
     SphSolver3 sph;
@@ -171,7 +172,8 @@ static void Setup(Harness &H){
     ColliderSetBuilder3 cBuilder;
     for(size_t i = 0; i < H.shapes.size(); i++) cBuilder.AddCollider3(H.shapes[i], H.frictions[i]);
     H.colliders = cBuilder.GetColliderSet();
-    H.sphSet = SphParticleSet3FromBuilder(&H.builder);
+    if(H.cbuilder){ H.cbuilder->Commit(); H.sphSet = SphParticleSet3FromContinuousBuilder(H.cbuilder); }
+    else H.sphSet = SphParticleSet3FromBuilder(&H.builder);
     H.sphSet->SetRelativeKernelRadius(H.scale);
     H.data = DefaultSphSolverData3(H.gravity != 0);
     if(H.solverKind == 0){
@@ -186,6 +188,7 @@ static void Setup(Harness &H){
         if(H.viscosity >= 0) H.sph.SetViscosityCoefficient(H.viscosity);
     }
     if(H.drag >= 0) H.data->dragCoefficient = H.drag;
+    if(H.cbuilder){ H.cbuilder->SetKernelRadius(H.spacing * H.scale); H.cbuilder->MapGrid(H.grid); }
     ParticleSet3 *pSet = H.sphSet->GetParticleSet();
     vec3ui res = H.grid->GetIndexCount();
     printf("[bbref] N=%d cells=%u (%u x %u x %u) mass=%.17g h=%.17g\n", pSet->GetParticleCount(),
@@ -334,9 +337,29 @@ int main(int argc, char **argv){
             if(fread(pos.data(), sizeof(double), 3 * n, fp) != (size_t)(3 * n)) return 2;
             if(fread(vel.data(), sizeof(double), 3 * n, fp) != (size_t)(3 * n)) return 2;
             fclose(fp);
+            for(int64_t i = 0; i < n; i++){
+                vec3f p(pos[3*i], pos[3*i+1], pos[3*i+2]), v(vel[3*i], vel[3*i+1], vel[3*i+2]);
+                if(H.cbuilder) H.cbuilder->AddParticle(p, v); else H.builder.AddParticle(p, v);
+            }
+        }
+        else if(cmd == "continuous"){ int maxp; in >> maxp; H.cbuilder = new ContinuousParticleSetBuilder3(maxp); }
+        else if(cmd == "append"){
+            // ContinuousParticleSetBuilder3::AddParticle + Commit (src/core/grid.h:1409-1441): AppendData, then
+            // DistributeByParticleList puts the new ids at the tail of their cells' chains
+            std::string file; in >> file;
+            if(!H.cbuilder){ fprintf(stderr, "append needs `continuous <max>` before the particles\n"); return 2; }
+            FILE *fp = fopen(file.c_str(), "rb");
+            if(!fp){ fprintf(stderr, "cannot open %s\n", file.c_str()); return 2; }
+            int64_t n = 0;
+            if(fread(&n, sizeof(n), 1, fp) != 1) return 2;
+            std::vector<double> pos(3 * n), vel(3 * n);
+            if(fread(pos.data(), sizeof(double), 3 * n, fp) != (size_t)(3 * n)) return 2;
+            if(fread(vel.data(), sizeof(double), 3 * n, fp) != (size_t)(3 * n)) return 2;
+            fclose(fp);
             for(int64_t i = 0; i < n; i++)
-                H.builder.AddParticle(vec3f(pos[3*i], pos[3*i+1], pos[3*i+2]),
-                                      vec3f(vel[3*i], vel[3*i+1], vel[3*i+2]));
+                if(!H.cbuilder->AddParticle(vec3f(pos[3*i], pos[3*i+1], pos[3*i+2]), vec3f(vel[3*i], vel[3*i+1], vel[3*i+2]))){ fprintf(stderr, "append: builder full\n"); return 2; }
+            H.cbuilder->Commit();
+            printf("[bbref] append n=%lld total=%d\n", (long long)n, H.sphSet->GetParticleSet()->GetParticleCount());
         }
         else if(cmd == "setup"){ Setup(H); }
         else if(cmd == "set_chains"){

@@ -116,6 +116,38 @@ def obstacle_run():
     print("obstacle_run", len(data["s0_pos"]), "particles")
 
 
+def append_block():
+    """The particles appended in append_run: a small jitter-free BCC block above the probe scene's fluid, moving down."""
+    pts = O.bcc_points((-0.2, 0.12, -0.2), (-0.08, 0.2, -0.06), 0.02)
+    return pts, np.tile(np.array([0.5, -2.0, 0.25]), (len(pts), 1))
+
+
+def append_run():
+    """Continuous emission (ContinuousParticleSetBuilder3::AddParticle + Commit, src/core/grid.h:1409-1441): probe scene,
+    20 sub-steps, append a block, chains right after the append, one traced sub-step, 30 more sub-steps, a second
+    append (the same block again, shifted), 20 more sub-steps."""
+    sc = scenes.probe_scene()
+    wd = tempfile.mkdtemp(prefix="bbref_")
+    O.write_particles(os.path.join(wd, "p.bin"), sc["pos"], sc["vel"])
+    add_pos, add_vel = append_block()
+    O.write_particles(os.path.join(wd, "a1.bin"), add_pos, add_vel)
+    O.write_particles(os.path.join(wd, "a2.bin"), add_pos + np.array([0.3, 0.0, 0.2]), add_vel)
+    job = ["threads 4", "spacing 0.02", "scale 1.8", f"collider box {I} 0.6 0.6 0.6 1 0", "domain_from_collider 0",
+           "continuous 6000", f"particles {wd}/p.bin", "setup", "step 7e-4 20", "dump {wd}/s20_", "dump_grid {wd}/s20_",
+           f"append {wd}/a1.bin", "dump_grid {wd}/a1_", "trace 7e-4 {wd}/t_", "step 7e-4 30",
+           f"append {wd}/a2.bin", "dump_grid {wd}/a2_", "step 7e-4 20", "dump {wd}/end_", "dump_grid {wd}/end_"]
+    out, _ = O.run_ref(job, wd)
+    data = dict(p_pos=sc["pos"].astype(np.float64), p_vel=sc["vel"].astype(np.float64), add_pos=add_pos, add_vel=add_vel)
+    for pre, names in (("s20_", ["pos", "vel", "cell_count", "cell_order"]), ("a1_", ["cell_count", "cell_order"]),
+                       ("a2_", ["cell_count", "cell_order"]), ("end_", ["pos", "vel", "density", "cell_count", "cell_order"])):
+        for k, v in load_all(wd, pre, names).items():
+            data[pre + k] = v
+    for k, v in load_all(wd, "t_", TRACE).items():
+        data["t_" + k] = v
+    np.savez_compressed(os.path.join(HERE, "append_run.npz"), **data)
+    print("append_run", len(sc["pos"]), "+", len(add_pos), "+", len(add_pos), "particles")
+
+
 def grid_facts():
     """UtilBuildGridForDomain results printed by the reference for several domains / spacings."""
     rows = []
@@ -139,4 +171,5 @@ if __name__ == "__main__":
     probe_trace()
     collider_vectors()
     obstacle_run()
+    append_run()
     grid_facts()

@@ -85,3 +85,14 @@ def test_demo_advance_frames_and_sph():
     assert "non-finite 0" in r.stdout
     r = subprocess.run([_demo(), "--sph", "--steps", "10"], capture_output=True, text=True)
     assert r.returncode == 0 and "===== OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_demo_continuous_emission():
+    """ContinuousParticleSetBuilder3 of the facade: particles appended between frames (bbx_append_particles after
+    stepping) -- the particle count grows by K per frame and the run stays finite."""
+    r = subprocess.run([_demo(), "--frames", "3", "--emit", "100"], capture_output=True, text=True)
+    assert r.returncode == 0 and "===== OK" in r.stdout, r.stdout + r.stderr
+    counts = [int(x) for x in __import__("re").findall(r"Particles (\d+)", r.stdout)]
+    assert len(counts) == 3 and counts[1] == counts[0] + 100 and counts[2] == counts[0] + 200, r.stdout
+    assert "non-finite 0" in r.stdout

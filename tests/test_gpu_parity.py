@@ -330,3 +330,58 @@ def test_domain_corner_and_face_particles_hash_like_reference():
     eng, orc = _pair(sc2)
     cc, co = eng.export_cells()
     assert np.array_equal(cc, orc.arr("cell_count")) and np.array_equal(co, orc.arr("cell_order"))
+
+
+def test_append_particles_between_steps_matches_reference_chains():
+    """bbx_append_particles after stepping = ContinuousParticleSetBuilder3::AddParticle + Commit (grid.h:1409-1441):
+    the new ids join the tail of their cells' chains, the old chains stay.  The oracle side of this is pinned against
+    the unmodified reference (tests/golden/append_run.npz); here the engine follows the oracle through two appends
+    with the state resynced every step (identical inputs), chains and lists bit-exact."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "append_run.npz"))
+    sc = scenes.probe_scene()
+    eng = scenes.make_engine(sc, max_particles=6000)
+    orc = scenes.make_oracle(sc)
+    eng.set_particles(sc["pos"], sc["vel"])
+    orc.set_particles(sc["pos"], sc["vel"])
+    dt = sc["dt"]
+
+    def run(steps):
+        for step in range(steps):
+            orc.substep_pcisph(dt)
+            eng.step_pcisph(dt)
+            cc, co = eng.export_cells()
+            assert np.array_equal(cc, orc.arr("cell_count")) and np.array_equal(co, orc.arr("cell_order")), f"step {step}"
+            cnt, ids = eng.export_neighbors()
+            assert np.array_equal(cnt, orc.a["nbr_count"]) and np.array_equal(ids, orc.a["nbr_ids"]), f"step {step}"
+            pos, vel = scenes.f32(orc.a["pos"]), scenes.f32(orc.a["vel"])
+            orc.a["pos"][:] = pos
+            orc.a["vel"][:] = vel
+            eng.overwrite_state(pos, vel)
+
+    run(12)
+    add_pos, add_vel = scenes.f32(g["add_pos"]), scenes.f32(g["add_vel"])
+    for shift in (np.zeros(3), np.array([0.3, 0.0, 0.2])):
+        p = scenes.f32(add_pos + shift)
+        n0 = eng.n
+        eng.append_particles(p, add_vel)
+        orc.append_particles(p, add_vel)
+        assert eng.n == n0 + len(p) == orc.S.n
+        cc, co = eng.export_cells()                     # chains right after the append
+        assert np.array_equal(cc, orc.arr("cell_count")) and np.array_equal(co, orc.arr("cell_order"))
+        assert np.array_equal(eng.download(bb.POSITION, np.float32)[n0:], p)   # ids are append order
+        tr = orc.trace_pcisph(dt)                       # the sub-step right after it
+        eng.step_pcisph(dt)
+        cc, co = eng.export_cells()
+        assert np.array_equal(cc, tr["cell_count"]) and np.array_equal(co, tr["cell_order"])
+        cnt, ids = eng.export_neighbors()
+        assert np.array_equal(cnt, tr["nbr_count"]) and np.array_equal(ids, tr["nbr_ids"])
+        assert np.abs(eng.download(bb.DENSITY) - tr["density"]).max() / 1000.0 < TOL_RHO
+        ext = float(np.max(sc["domain_max"] - sc["domain_min"]))
+        assert np.abs(eng.download(bb.POSITION) - tr["pos_out"]).max() / ext < TOL_POS
+        pos, vel = scenes.f32(orc.a["pos"]), scenes.f32(orc.a["vel"])
+        orc.a["pos"][:] = pos
+        orc.a["vel"][:] = vel
+        eng.overwrite_state(pos, vel)
+        run(10)
+    assert eng.stats().nan_count == 0
