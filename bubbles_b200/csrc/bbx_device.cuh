@@ -501,7 +501,8 @@ __global__ void k_halo_signal(unsigned *lo_flag, unsigned *hi_flag, unsigned seq
     }
 }
 // Before the next phase reads ghost slots: wait until both neighbours have signalled this phase (bounded:
-// ~3 s of polling, then the sticky device error BBX_ERR_COMM instead of a hang).
+// ~30 s of polling -- a neighbour's host may be busy between two calls -- then the sticky device error
+// BBX_ERR_COMM instead of a hang).
 __global__ void k_halo_wait(const unsigned *from_lo, const unsigned *from_hi, unsigned seq, int *error){
     if(threadIdx.x == 0){
         const long long t0 = clock64();
@@ -509,7 +510,7 @@ __global__ void k_halo_wait(const unsigned *from_lo, const unsigned *from_hi, un
             const volatile unsigned *f = side == 0 ? from_lo : from_hi;
             if(!f) continue;
             while((int)(*f - seq) < 0){
-                if(clock64() - t0 > 6000000000ll){ *error = BBX_ERR_COMM; break; }
+                if(clock64() - t0 > 60000000000ll){ *error = BBX_ERR_COMM; break; }
                 __nanosleep(200);
             }
         }
