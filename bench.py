@@ -195,6 +195,32 @@ def cpu_baseline(n_gpu_particles):
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": f"failed: {ex}"}
 
 
+def reference_gpu(n_particles):
+    """The unmodified reference's GPU path (its native mode: managed memory, FP64, 16-thread blocks as shipped) on the
+    bench workload itself (capped at 2 M particles), on this box's GPU -- reported beside the CPU path, never the
+    optimisation target."""
+    import numpy as np
+    from oracle import oracle as O
+    if not O.ref_gpu_available():
+        return {"value": None, "unit": UNIT, "sample": "oracle/_ref/bbref_gpu not built"}
+    sc = make_scene(min(n_particles, 2_000_000))
+    n = len(sc["pos"])
+    try:
+        wd = tempfile.mkdtemp(prefix="bbref_gpu_")
+        O.write_particles(os.path.join(wd, "p.bin"), sc["pos"], sc["vel"])
+        half = sc["domain_max"]
+        I = O.mat_str(np.eye(4))
+        job = [f"spacing {sc['spacing']}", f"scale {sc['scale']}",
+               f"collider box {I} {float(2 * half[0])!r} {float(2 * half[1])!r} {float(2 * half[2])!r} 1 0", "domain_from_collider 0",
+               f"particles {wd}/p.bin", "setup", f"step {sc['dt']} 2", f"step {sc['dt']} 10"]
+        out, _ = O.run_ref(job, wd, timeout=600, gpu=True)
+        m = re.findall(r"particle_updates_per_s=(\S+)", out)
+        return {"value": float(m[-1]), "unit": UNIT, "kind": "reference GPU path (unmodified sources, sm_100 build, block size 16 as shipped, FP64, managed memory)",
+                "sample": f"{n}-particle dam break, 10 sub-steps after 2 warm-up, on this box's GPU"}
+    except Exception as ex:
+        return {"value": None, "unit": UNIT, "sample": f"failed: {str(ex)[-300:]}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,11 +422,14 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(n)
+            eng.close(); eng = None  # free the device before the reference's own GPU build takes it
+            line["reference_gpu"] = reference_gpu(n)
         else:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                                     "sample": "only measured at N = 1"}
         print(json.dumps(line), flush=True)
-    eng.close()
+    if eng is not None:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
 

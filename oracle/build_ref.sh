@@ -34,3 +34,9 @@ echo "$SRCS" | xargs -P "$JOBS" -I{} bash -c 'compile_one {}'
 $NVCC $FLAGS -c "$HERE/ref_harness.cpp" -o "$OBJ/_harness.o"
 $NVCC --gpu-architecture=sm_100 -o "$OUT/bbref" "$OBJ"/*.o -ldl -lpthread
 echo "[build_ref] built $OUT/bbref"
+# the reference's GPU path (its native mode) with the same driver: its own managed-memory arena instead of the shim
+mkdir -p "$OUT/obj_gpu"
+$NVCC $FLAGS -c "$REF/src/cuda/memory.cpp" -o "$OUT/obj_gpu/cuda_memory.o"
+$NVCC $FLAGS -DBBREF_GPU -c "$HERE/ref_harness.cpp" -o "$OUT/obj_gpu/_harness_gpu.o"
+$NVCC --gpu-architecture=sm_100 -o "$OUT/bbref_gpu" $(ls "$OBJ"/*.o | grep -v "/_harness.o") "$OUT/obj_gpu/cuda_memory.o" "$OUT/obj_gpu/_harness_gpu.o" -ldl -lpthread
+echo "[build_ref] built $OUT/bbref_gpu"

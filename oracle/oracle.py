@@ -317,6 +317,14 @@ def ref_available():
     return os.path.exists(REF_BIN)
 
 
+REF_GPU_BIN = os.path.join(os.path.dirname(REF_BIN), "bbref_gpu")
+
+
+def ref_gpu_available():
+    """The same driver linked for the reference's GPU path (its native mode); needs a GPU at run time."""
+    return os.path.exists(REF_GPU_BIN)
+
+
 def mat_str(m):
     return " ".join(repr(float(x)) for x in np.asarray(m, dtype=np.float64).ravel())
 
@@ -330,11 +338,12 @@ def write_particles(path, pos, vel):
         f.write(vel.tobytes())
 
 
-def run_ref(job_lines, workdir=None, timeout=3600):
-    """Run bbref on a job; returns (stdout, workdir). Job lines may use {wd} for the work directory."""
+def run_ref(job_lines, workdir=None, timeout=3600, gpu=False):
+    """Run bbref (gpu=True: bbref_gpu, the reference's GPU path) on a job; returns (stdout, workdir). Job lines may
+    use {wd} for the work directory."""
     wd = workdir or tempfile.mkdtemp(prefix="bbref_")
     job = os.path.join(wd, "job.txt")
     with open(job, "w") as f:
         f.write("\n".join(l.format(wd=wd) for l in job_lines) + "\n")
-    out = subprocess.run([REF_BIN, job], check=True, capture_output=True, text=True, timeout=timeout).stdout
+    out = subprocess.run([REF_GPU_BIN if gpu else REF_BIN, job], check=True, capture_output=True, text=True, timeout=timeout).stdout
     return out, wd

@@ -31,6 +31,11 @@
 #include <util.h>
 #include <memory.h>
 
+// BBREF_GPU: the same driver for the reference's GPU path (its native mode): the reference's own managed-memory
+// arena (src/cuda/memory.cpp) is linked instead of the shim, the system stays in GPU mode and every kernel of the
+// reference runs on the device with the launch strategy it ships with (16-thread blocks).  Only meaningful on a
+// box with a GPU: bench.py times it beside the CPU path ("reference_gpu").
+#ifndef BBREF_GPU
 // ---- shim for src/cuda/memory.cpp (signatures: src/cuda/cutil.h:134-136, src/cuda/memory.h:17-32)
 void *_cudaAllocate(size_t bytes, int, const char *, bool){ return calloc(1, bytes ? bytes : 1); }
 void *_cudaAllocateUnregister(size_t bytes, int, const char *, bool){ return calloc(1, bytes ? bytes : 1); }
@@ -39,6 +44,7 @@ void CudaMemoryManagerStart(const char *){}
 std::string CudaGetCurrentKey(){ return std::string("oracle"); }
 void CudaMemoryManagerClearCurrent(){}
 void CudaMemoryManagerClearAll(){}
+#endif
 // lives in the (excluded) 2D solver: src/solvers/pcisph_solver2.cpp:7
 extern const Float kDefaultTimeStepLimitScale = 5.0;
 
@@ -168,7 +174,9 @@ static void DumpState(Harness &H, const std::string &prefix){
 static void Setup(Harness &H){
     if(!H.hasDomain){ fprintf(stderr, "no domain\n"); exit(2); }
     H.grid = UtilBuildGridForDomain(H.domain, H.spacing, H.scale);
+#ifndef BBREF_GPU
     HostBuildNeighborLists(H.grid);
+#endif
     ColliderSetBuilder3 cBuilder;
     for(size_t i = 0; i < H.shapes.size(); i++) cBuilder.AddCollider3(H.shapes[i], H.frictions[i]);
     H.colliders = cBuilder.GetColliderSet();
@@ -240,8 +248,12 @@ static void TraceStep(Harness &H, Float dt, const std::string &prefix){
 int main(int argc, char **argv){
     if(argc < 2){ fprintf(stderr, "usage: bbref job.txt\n"); return 2; }
     cudaSetLaunchStrategy(CudaLaunchStrategy::CustomizedBlockSize, 16);
+#ifndef BBREF_GPU
     SetSystemUseCPU();
     SetCPUThreads(1);
+#else
+    { int nd = 0; if(cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0){ fprintf(stderr, "bbref_gpu: no CUDA device\n"); return 3; } }
+#endif
     Harness H;
     std::ifstream job(argv[1]);
     if(!job){ fprintf(stderr, "cannot open job %s\n", argv[1]); return 2; }
@@ -397,6 +409,9 @@ int main(int argc, char **argv){
                 if(H.solverKind == 0) AdvanceTimeStep(&H.pci, dt, 1);
                 else AdvanceTimeStep(&H.sph, dt, 1);
             }
+#ifdef BBREF_GPU
+            cudaDeviceSynchronize();
+#endif
             double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             int np = H.sphSet->GetParticleSet()->GetParticleCount();
             printf("[bbref] steps=%d dt=%g seconds=%.6f particle_updates_per_s=%.6e\n", n, (double)dt, sec,
