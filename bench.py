@@ -31,6 +31,10 @@ UNIT = "particle-updates/s"
 PHASE_BYTES = {"grid": 96, "density": 20, "force_np+predict": 116, "pressure": 24, "pressure_force+integrate": 136}
 PHASE_IDS = {"grid": 0, "density": 1, "force_np+predict": 2, "pressure": 4, "pressure_force+integrate": 5}
 BYTES_PER_UPDATE = 392  # K = 1 predict-correct iteration (the reference's effective behaviour)
+# --solver sph (BASELINE configs[0], SphSolver3): grid 96 + density/EOS 24 + all forces and integrate 72 = 192 B per update
+SPH_PHASE_BYTES = {"grid": 96, "density": 24, "forces": 40, "integrate": 32}
+SPH_PHASE_IDS = {"grid": 0, "density": 1, "forces": 2, "integrate": 6}
+SPH_BYTES_PER_UPDATE = 192
 
 
 def peaks():
@@ -230,6 +234,8 @@ def main():
     ap.add_argument("--particles", type=float, default=1.0e6, help="particles per GPU (weak scaling)")
     ap.add_argument("--workload", default="dam", choices=["dam", "sdf"],
                     help="dam: PCISPH dam break in a box (configs 2, 4, 5); sdf: same plus a baked-SDF torus collider (config 3)")
+    ap.add_argument("--solver", default="pcisph", choices=["pcisph", "sph"],
+                    help="sph: the SphSolver3 step (BASELINE configs[0]; fixed dt 1.44e-4 = 0.4 h / c_s), single GPU line for the record")
     ap.add_argument("--ref-particles", type=float, default=2.5e5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
@@ -273,6 +279,9 @@ def main():
         eng.set_particles(pos32, vel32)
     n = n_global // world  # nominal particles per GPU (the slabs hold about this many each)
     dt = sc["dt"]
+    phase_ids, phase_bytes, bytes_per_update, solver = PHASE_IDS, PHASE_BYTES, BYTES_PER_UPDATE, bb.SOLVER_PCISPH
+    if args.solver == "sph":
+        phase_ids, phase_bytes, bytes_per_update, solver, dt = SPH_PHASE_IDS, SPH_PHASE_BYTES, SPH_BYTES_PER_UPDATE, bb.SOLVER_SPH, 1.44e-4
     state_bytes = n * (16 * 8 + 4 * 8 + 208)  # float4 arrays, scalars/indices, neighbour list
 
     def barrier():
@@ -281,7 +290,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -------------------------------------------------------------
-    eng.step_many(dt, args.warmup)
+    eng.step_many(dt, args.warmup, solver)
     eng.synchronize()
     eng.set_timing(True)
     eng.reset_kernel_time()
@@ -292,13 +301,13 @@ def main():
     t0 = time.perf_counter()
     # CUDA events bracket the K sub-steps on the engine's own stream (bbx_advance-style timing is done
     # inside the library: per-phase events are recorded between the kernels, no sync until the end)
-    eng.step_many(dt, args.steps)
+    eng.step_many(dt, args.steps, solver)
     eng.synchronize()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = eng.launches - l0
     phase = {}
-    for name, pid in PHASE_IDS.items():
+    for name, pid in phase_ids.items():
         ms, k = eng.kernel_time(pid)
         phase[name] = (ms, k)
     gap_ms, _ = eng.kernel_time(7)  # device idle time between sub-steps (launch gaps), part of the step time
@@ -332,7 +341,7 @@ def main():
     def e2e_step():
         if world == 1:
             rc = lib.bbx_overwrite_state(eng.h, buf["ip"].data_ptr(), buf["iv"].data_ptr(), bb.F32)
-            rc |= lib.bbx_step_pcisph(eng.h, dt)
+            rc |= (lib.bbx_step_sph if args.solver == "sph" else lib.bbx_step_pcisph)(eng.h, dt)
             rc |= lib.bbx_download(eng.h, bb.POSITION, buf["op"].data_ptr(), bb.F32)
             rc |= lib.bbx_download(eng.h, bb.VELOCITY, buf["ov"].data_ptr(), bb.F32)
             m = len(pos32)
@@ -381,7 +390,7 @@ def main():
         dom = max(phase, key=lambda k: phase[k][0])
         dom_ms = phase[dom][0] / max(1, phase[dom][1])
         cells = eng.grid.total // world
-        dom_bytes = PHASE_BYTES[dom] * n + (8 * cells if dom == "grid" else 0)
+        dom_bytes = phase_bytes[dom] * n + (8 * cells if dom == "grid" else 0)
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -389,14 +398,16 @@ def main():
             tj = json.load(open(tpath))
             if tj.get("particles") and dom in tj.get("dram_bytes_per_launch", {}):
                 traffic = tj["dram_bytes_per_launch"][dom] * (n / tj["particles"])
-        step_gbs = (BYTES_PER_UPDATE * n + 8 * cells) / (ms_per_step * 1e-3) / 1e9
+        step_gbs = (bytes_per_update * n + 8 * cells) / (ms_per_step * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if args.solver == "pcisph" else "particle-updates/s (3D SPH sub-step, dam break)",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": ("PCISPH 3D dam break + baked-SDF torus collider (BASELINE configs[2] stand-in), " if args.workload == "sdf" else "") +
-                                   f"PCISPH 3D dam break, {n_global} particles = {n} per GPU (BASELINE configs[1] per GPU), spacing 0.02, h = 1.8 s, "
-                                   f"{cells} cells, fixed dt 7.2e-4, reference-compat (1 predict-correct iteration)"
+                                   f"{'PCISPH' if args.solver == 'pcisph' else 'SPH'} 3D dam break, {n_global} particles = {n} per GPU (BASELINE configs[{'1' if args.solver == 'pcisph' else '0'}] per GPU), spacing 0.02, h = 1.8 s, " +
+                                   (f"{cells} cells, fixed dt 7.2e-4, reference-compat (1 predict-correct iteration)" if args.solver == "pcisph" else
+                                    f"{cells} cells, SphSolver3 step (BASELINE configs[0]), fixed dt 1.44e-4")
                                    + (f", {world} z-slabs with NCCL ghost-plane exchange and migration" if world > 1 else ""),
                        "particles_per_gpu": n, "particles": n_global, "cells": cells, "dt": dt,
                        "parallelism": f"slab{world}" if world > 1 else "single",
@@ -413,8 +424,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_particle": PHASE_BYTES[dom],
-                         "whole_step": {"bytes_per_update": BYTES_PER_UPDATE, "achieved": step_gbs, "frac": step_gbs / peak},
+                         "algorithmic_bytes_per_particle": phase_bytes[dom],
+                         "whole_step": {"bytes_per_update": bytes_per_update, "achieved": step_gbs, "frac": step_gbs / peak},
                          "phases_ms_per_step": {k: v[0] / args.steps for k, v in phase.items()},
                          "gap_ms_per_step": gap_ms / args.steps},
             "stats": {"neighbor_overflow": st.neighbor_overflow, "clamped": st.clamped, "rebuild_flag": st.rebuild_flag,

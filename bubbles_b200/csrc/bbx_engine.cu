@@ -785,9 +785,7 @@ static int phase_density(bbx_engine *e, const StepParams &P, int sph){
         CU(cudaGetLastError());
     }
     if(!sph && e->p2p) return halo_sync(e, HALO_DENSITY);
-    // ghost rho: the PCISPH viscosity sweep reads the 32-byte records (x, rho | v); the SPH step reads rho from
-    // vel.w and also needs the ghosts' p / rho^2 (posq.w)
-    if(sph) return exchange2(e, e->vel[cur], e->posq);
+    // ghost rho (and, for the SPH step, p / rho^2): both force sweeps read the 32-byte records (x, rho | v, p / rho^2)
     { void *arr[1] = {e->rec}; size_t z[1] = {2 * sizeof(float4)}; return exchange_planes(e, arr, z, 1); }
 }
 // grid of a list sweep: one thread per particle
@@ -846,6 +844,7 @@ static int phase_integrate(bbx_engine *e, const StepParams &P, int with_fp){
 static int phase_pseudo_viscosity(bbx_engine *e, const StepParams &P, double dt){
     if(!(e->cfg.pseudo_viscosity * dt > 0.1)) return BBX_OK; // sph_equations3.cpp:655-657
     int cur = e->cur;
+    // (the ghosts' rho for the aggregation weights rides in vel.w: it came with the post-integration halo)
     if(e->n > 0){
         LAUNCH(e, k_pseudo_aggregate, sweep_grid(e), BBX_BS, P, e->grid, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->smoothed);
         LAUNCH(e, k_pseudo_interpolate, div_up(e->n, 256), 256, P, e->vel[cur], e->smoothed);
@@ -921,7 +920,7 @@ static int step_sph(bbx_engine *e, double dt){
     if((rc = phase_density(e, P, 1))) return rc;
     tick(e, T_FORCE_NP);
     if(e->n > 0){
-        LAUNCH(e, k_sph_forces, sweep_grid(e), BBX_BS, P, e->grid, e->posq, e->vel[e->cur], e->cell[e->cur], e->cell_start[e->cur], e->nbr, e->nbr_cnt, e->force);
+        LAUNCH(e, k_sph_forces, sweep_grid(e), BBX_BS, P, e->grid, e->posq, e->vel[e->cur], e->rec, e->cell[e->cur], e->cell_start[e->cur], e->nbr, e->nbr_cnt, e->force);
         CU(cudaGetLastError());
     }
     tick(e, T_INTEGRATE);

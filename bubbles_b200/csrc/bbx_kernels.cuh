@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(256) k_integrate(StepParams P, DevGrid g, DevS
 // ComputeAllForcesFor (sph_equations3.cpp:184-272) with Jacobi semantics: gravity + drag + viscosity
 // (only inside the spiky support and j != i) + pressure force from rho, p of this sub-step.
 __global__ void __launch_bounds__(BBX_BS) k_sph_forces(StepParams P, DevGrid g,
-        const float4 *__restrict__ posq, const float4 *__restrict__ vel, const int *__restrict__ cell,
+        const float4 *__restrict__ posq, const float4 *__restrict__ vel, const float4 *__restrict__ rec, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
         float4 *__restrict__ force)
 {
@@ -810,14 +810,17 @@ __global__ void __launch_bounds__(BBX_BS) k_sph_forces(StepParams P, DevGrid g,
     float tx = 0.f, ty = 0.f, tz = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
     float qi = pi.w;
     BBX_LIST_FOREACH(j, {
-        float4 pj = posq[j]; float4 vj = vel[j];
+        // x_j, rho_j, v_j, p_j / rho_j^2 in ONE 256-bit gather from the records the list build completed
+        float4 pj, vj;
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(pj.x), "=f"(pj.y), "=f"(pj.z), "=f"(pj.w), "=f"(vj.x), "=f"(vj.y), "=f"(vj.z), "=f"(vj.w) : "l"(rec + 2 * (ptrdiff_t)j));
         float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
         float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
         float inv_d = (d2 > 1.0e-16f) ? bbx_rsqrt_approx(d2) : 0.f;
         float x = (j != i) ? fmaxf(0.f, fmaf(-d2 * inv_d, P.inv_h, 1.f)) : 0.f;
-        float w = (qi + pj.w) * (x * x) * inv_d;
+        float w = (qi + vj.w) * (x * x) * inv_d;
         tx = fmaf(dx, w, tx); ty = fmaf(dy, w, ty); tz = fmaf(dz, w, tz);
-        float wv = x * bbx_rcp_approx(vj.w);
+        float wv = x * bbx_rcp_approx(pj.w);
         ax = fmaf(vj.x - vi.x, wv, ax); ay = fmaf(vj.y - vi.y, wv, ay); az = fmaf(vj.z - vi.z, wv, az);
     })
     float sp = -P.mass2 * P.dw_spiky_c;

@@ -344,7 +344,9 @@ __global__ void __launch_bounds__(BBX_LT, BBX_LIST_MINB) k_cell_lists_density(St
                     if(p < 0.f) p *= P.neg_pressure_scale;
                     pressure[i] = p;
                     const float4 pi = W.spi[idx];
-                    posq[i] = make_float4(pi.x, pi.y, pi.z, p / (rho * rho));
+                    const float q = p / (rho * rho);
+                    posq[i] = make_float4(pi.x, pi.y, pi.z, q);
+                    reinterpret_cast<float *>(rec)[8 * (size_t)i + 7] = q; // the SPH force sweep gathers (x, rho | v, p / rho^2)
                 }
             }
             // lists of the group: shared rows -> global, chunk-transposed (chunk ch of particle i is the uint4
