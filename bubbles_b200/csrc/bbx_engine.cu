@@ -60,6 +60,7 @@ struct bbx_engine {
     int cur;
     int have_chains; // cell_start[cur] / cell[cur] valid
     int *newcell, *count, *perm, *occ_cells, *queue;
+    unsigned *movemask; // per old cell: directions its leaving particles took (k_hash_count -> k_fill_incremental)
     unsigned long long *scan_status;
     int scan_tiles;
     int epoch;       // grid updates done so far; flags are double-buffered by its parity (DevState)
@@ -223,6 +224,7 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     }
     rc |= dev_alloc(&e->count, (size_t)g.total + 8); rc |= dev_alloc(&e->perm, cap);
     rc |= dev_alloc(&e->occ_cells, (size_t)g.total); rc |= dev_alloc(&e->queue, cap);
+    rc |= dev_alloc(&e->movemask, (size_t)g.total);
     e->scan_tiles = div_up(g.c_own1 - g.c_own0, SCAN_TILE);
     rc |= dev_alloc(&e->scan_status, (size_t)e->scan_tiles);
     rc |= dev_alloc(&e->nbr, capw * BBX_NBR_CHUNKS * 8); rc |= dev_alloc(&e->nbr_cnt, cap);
@@ -254,7 +256,7 @@ int bbx_destroy(bbx_engine *e){
     if(e->comm){ delete e->comm; e->comm = nullptr; }
     for(void *p : e->raw) cudaFree(p);
     for(int b = 0; b < 2; b++) cudaFree(e->cell_start[b]);
-    cudaFree(e->count); cudaFree(e->perm); cudaFree(e->occ_cells); cudaFree(e->queue); cudaFree(e->scan_status);
+    cudaFree(e->movemask); cudaFree(e->count); cudaFree(e->perm); cudaFree(e->occ_cells); cudaFree(e->queue); cudaFree(e->scan_status);
     cudaFree(e->nbr); cudaFree(e->nbr_cnt); cudaFree(e->force); cudaFree(e->force_p);
     cudaFree(e->smoothed); cudaFree(e->pressure); cudaFree(e->rho_pred); cudaFree(e->rho_err);
     if(e->gtab) cudaFree(e->gtab);
@@ -672,8 +674,9 @@ static int grid_update(bbx_engine *e){
     int force = (e->force_full || !e->have_chains) ? 1 : 0;
     int par = e->epoch & 1;
     const int own_cells = g.c_own1 - g.c_own0;
+    if(!force) CU(cudaMemsetAsync(e->movemask, 0, sizeof(unsigned) * (size_t)g.total, e->stream));
     LAUNCH(e, k_hash_count, div_up(std::max(std::max(n_all, e->scan_tiles), 1), 256), 256, n_all, e->n_glo, e->n, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st,
-           force ? 0 : 1, par, e->scan_status, e->scan_tiles);
+           force ? 0 : 1, par, e->scan_status, e->scan_tiles, e->movemask);
     // the big-move rule and the jump detection are global decisions (the reference rebuilds ALL chains): the
     // flags are reduced over the ranks on a side stream while the scan and the (speculative) fill run
     if(slab){
@@ -688,7 +691,7 @@ static int grid_update(bbx_engine *e){
         int groups = std::max(1, std::min(n_all, own_cells));
         int blocks = std::min(div_up((long long)groups * 8, 256), 148 * 8);
         LAUNCH(e, k_fill_incremental, blocks, 256, g, e->st, par, slab ? 1 : 0, e->occ_cells, e->cell_start[cur], e->cell_start[nxt], e->newcell,
-               e->pos[cur], e->vel[cur], e->pid[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec);
+               e->pos[cur], e->vel[cur], e->pid[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec, e->movemask);
     }
     if(slab) CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
     // full path (forced, or selected on the device by the big-move / jump flags); small grids when it is

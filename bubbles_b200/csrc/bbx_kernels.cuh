@@ -25,10 +25,13 @@
 
 // A1: cell hash per particle + histogram + jump detection.  Thread 0 also resets the per-sub-step
 // statistics and the flag slots of the *next* epoch (see DevState).
+// movemask[o] collects, for the particles that LEAVE old cell o, the directions they leave in (bit = 9 (dy + 1) +
+// 3 (dx + 1) + (dz + 1) of new - old cell, i.e. the position of the new cell in o's neighbour list): the fill then
+// walks only the old segments that really send something to a cell instead of all 27.
 __global__ void __launch_bounds__(256) k_hash_count(int n_all, int n_lo, int n_own, const float4 *__restrict__ pos, const int *__restrict__ oldcell,
                                                     int *__restrict__ newcell, int *__restrict__ count,
                                                     DevGrid g, DevState *st, int have_old, int par,
-                                                    unsigned long long *__restrict__ scan_status, int scan_tiles)
+                                                    unsigned long long *__restrict__ scan_status, int scan_tiles, unsigned *__restrict__ movemask)
 {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if(idx == 0){
@@ -65,10 +68,14 @@ __global__ void __launch_bounds__(256) k_hash_count(int n_all, int n_lo, int n_o
     }
     newcell[i] = c;
     atomicAdd(&count[c], 1);
-    if(have_old && owned){
+    if(have_old){
         int oc = oldcell[i];
-        int oz = oc / g.plane; int rem = oc - oz * g.plane; int oy = rem / g.n[0]; int ox = rem - oy * g.n[0];
-        if(abs(ox - ux) > 1 || abs(oy - uy) > 1 || abs(oz - uz) > 1){ st->jump_flag[par] = 1; atomicAdd(&st->lost[par], 1); }
+        if(oc != c){
+            int oz = oc / g.plane; int rem = oc - oz * g.plane; int oy = rem / g.n[0]; int ox = rem - oy * g.n[0];
+            const int dx = ux - ox, dy = uy - oy, dz = uz - oz;
+            if(abs(dx) > 1 || abs(dy) > 1 || abs(dz) > 1){ if(owned){ st->jump_flag[par] = 1; atomicAdd(&st->lost[par], 1); } }
+            else atomicOr(&movemask[oc], 1u << (9 * (dy + 1) + 3 * (dx + 1) + (dz + 1)));
+        }
     }
 }
 
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(256) k_fill_incremental(DevGrid g, const DevSt
         const int *__restrict__ start_old, const int *__restrict__ start_new, const int *__restrict__ newcell,
         const float4 *__restrict__ pos_old, const float4 *__restrict__ vel_old, const int *__restrict__ pid_old,
         float4 *__restrict__ pos_new, float4 *__restrict__ vel_new, int *__restrict__ pid_new, int *__restrict__ cell_new,
-        float4 *__restrict__ rec)
+        float4 *__restrict__ rec, const unsigned *__restrict__ movemask)
 {
     // full rebuild path takes over.  (Slab engines run the fill regardless: their flags are still being reduced
     // over the ranks on a side stream; a full rebuild, if it comes, overwrites everything written here.)
@@ -197,8 +204,12 @@ __global__ void __launch_bounds__(256) k_fill_incremental(DevGrid g, const DevSt
                 int x = cx + dx, y = cy + dy, z = cz + dz;
                 if(x >= 0 && x < g.n[0] && y >= 0 && y < g.n[1] && z >= 0 && z < g.n[2]){
                     int nb = x + y * g.n[0] + z * g.plane;
-                    seg_s[q] = start_old[nb];
-                    seg_len[q] = start_old[nb + 1] - seg_s[q];
+                    // neighbour k sends particles here only if some of its particles left in direction c - nb,
+                    // which is entry 26 - k of ITS neighbour list (k = 13: the cell itself, the stayers)
+                    if(k == 13 || ((movemask[nb] >> (26 - k)) & 1u)){
+                        seg_s[q] = start_old[nb];
+                        seg_len[q] = start_old[nb + 1] - seg_s[q];
+                    }
                 }
             }
         }
