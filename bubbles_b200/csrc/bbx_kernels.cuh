@@ -213,35 +213,43 @@ __global__ void __launch_bounds__(256) k_fill_incremental(DevGrid g, const DevSt
                 }
             }
         }
-        int found = 0;
+        // neighbours with something to walk, as a bit set over the reference order: per lane, OR over the group's 8
+        // lanes, and the union over the warp's 4 groups drives the (warp-uniform) loop in ascending order
+        unsigned act = 0;
 #pragma unroll
-        for(int q = 0; q < 4; q++){
+        for(int q = 0; q < 4; q++) if(seg_len[q] > 0) act |= 1u << (sub + 8 * q);
+        act |= __shfl_xor_sync(0xffffffffu, act, 1); act |= __shfl_xor_sync(0xffffffffu, act, 2); act |= __shfl_xor_sync(0xffffffffu, act, 4);
+        unsigned wact = act | __shfl_xor_sync(0xffffffffu, act, 8);
+        wact |= __shfl_xor_sync(0xffffffffu, wact, 16);
+        int found = 0;
 #pragma unroll 1
-            for(int kk = 0; kk < 8; kk++){
-                if(q * 8 + kk >= 27) break;
-                int s = __shfl_sync(0xffffffffu, seg_s[q], kk, 8);
-                int len = __shfl_sync(0xffffffffu, seg_len[q], kk, 8);
-                if(found >= want) len = 0;
-                // trip count = longest segment among the 4 groups
-                int maxlen = len;
-                maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 8));
-                maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 16));
+        while(wact){
+            const int k = __ffs(wact) - 1; wact &= wact - 1;
+            const int q = k >> 3, kk = k & 7;
+            const int sq = q == 0 ? seg_s[0] : (q == 1 ? seg_s[1] : (q == 2 ? seg_s[2] : seg_s[3]));
+            const int lq = q == 0 ? seg_len[0] : (q == 1 ? seg_len[1] : (q == 2 ? seg_len[2] : seg_len[3]));
+            const int s = __shfl_sync(0xffffffffu, sq, kk, 8);
+            int len = __shfl_sync(0xffffffffu, lq, kk, 8);
+            if(found >= want) len = 0;
+            // trip count = longest segment among the 4 groups
+            int maxlen = len;
+            maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 8));
+            maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 16));
 #pragma unroll 1
-                for(int b = 0; b < maxlen; b += 8){
-                    int j = s + b + sub;
-                    bool m = (b + sub < len) && (newcell[j] == c);
-                    unsigned bal = (__ballot_sync(0xffffffffu, m) >> gshift) & 0xffu;
-                    if(m){
-                        int d = dst + found + __popc(bal & ((1u << sub) - 1u));
-                        const float4 pp = pos_old[j], vv = vel_old[j];
-                        pos_new[d] = pp;
-                        vel_new[d] = vv;
-                        rec[2 * (size_t)d] = pp; rec[2 * (size_t)d + 1] = vv; // gather record (rho follows in the list build)
-                        pid_new[d] = pid_old[j];
-                        cell_new[d] = c;
-                    }
-                    found += __popc(bal);
+            for(int b = 0; b < maxlen; b += 8){
+                int j = s + b + sub;
+                bool m = (b + sub < len) && (newcell[j] == c);
+                unsigned bal = (__ballot_sync(0xffffffffu, m) >> gshift) & 0xffu;
+                if(m){
+                    int d = dst + found + __popc(bal & ((1u << sub) - 1u));
+                    const float4 pp = pos_old[j], vv = vel_old[j];
+                    pos_new[d] = pp;
+                    vel_new[d] = vv;
+                    rec[2 * (size_t)d] = pp; rec[2 * (size_t)d + 1] = vv; // gather record (rho follows in the list build)
+                    pid_new[d] = pid_old[j];
+                    cell_new[d] = c;
                 }
+                found += __popc(bal);
             }
         }
     }
