@@ -580,7 +580,7 @@ __device__ __forceinline__ float bbx_rsqrt_safe(float d2){ return bbx_rsqrt_appr
 // pre-check cannot clear of every collider is queued for k_collide_predict.
 // (One thread per particle, neighbours gathered straight from global memory: the shared-memory staging that
 // k_pressure uses was measured SLOWER here -- 7 words per neighbour cost ~19 bank-conflicted wavefronts from
-// shared memory against one LDG.E.256 through L1; profiles/r01_v6_notes.md.)
+// shared memory against one LDG.E.256 through L1; profiles/r01_notes.md.)
 __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGrid g, DevState *st, const DevCullSet *__restrict__ cull,
         const float4 *__restrict__ pos, const float4 *__restrict__ vel, const float4 *__restrict__ rec, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
