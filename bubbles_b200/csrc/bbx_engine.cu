@@ -665,6 +665,7 @@ static int setup_peers(bbx_engine *e){
 
 // UpdateGridDistributionGPU minus the bucket fill (sph_equations3.cpp:511-539)
 #define BBX_SMALL_GRID (148 * 4)
+#define BBX_CHECK_GRID 148 // grid of the full-rebuild kernels when they are only a flag check (they stride over the data if it fires)
 static int grid_update(bbx_engine *e){
     const bool slab = IS_SLAB(e);
     if(e->n == 0 && !slab) return BBX_OK;
@@ -696,8 +697,8 @@ static int grid_update(bbx_engine *e){
     if(slab) CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
     // full path (forced, or selected on the device by the big-move / jump flags); small grids when it is
     // only a flag check
-    int fb_n = force ? div_up(std::max(n_all, 1), 256) : std::min(div_up(std::max(n_all, 1), 256), BBX_SMALL_GRID);
-    int fb_c = force ? div_up(own_cells, 256) : std::min(div_up(own_cells, 256), BBX_SMALL_GRID);
+    int fb_n = force ? div_up(std::max(n_all, 1), 256) : std::min(div_up(std::max(n_all, 1), 256), BBX_CHECK_GRID);
+    int fb_c = force ? div_up(own_cells, 256) : std::min(div_up(own_cells, 256), BBX_CHECK_GRID);
     LAUNCH(e, k_full_scatter, fb_n, 256, n_all, e->n_glo, g, e->st, par, force, e->newcell, e->cell_start[nxt], e->count, e->perm);
     LAUNCH(e, k_full_sort_cells, fb_c, 256, g, e->st, par, force, e->cell_start[nxt], e->pid[cur], e->perm, e->count);
     LAUNCH(e, k_full_gather, fb_n, 256, e->st, par, force, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
