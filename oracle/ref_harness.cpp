@@ -354,6 +354,11 @@ int main(int argc, char **argv){
                 if(H.cbuilder) H.cbuilder->AddParticle(p, v); else H.builder.AddParticle(p, v);
             }
         }
+        else if(cmd == "pseudo"){
+            // pseudo-viscosity coefficient (SphSolverData3::pseudoViscosity, default 10: the smoothing only runs when
+            // coefficient * dt > 0.1, sph_equations3.cpp:469-483); after `setup`
+            Float c; in >> c; if(!H.data){ fprintf(stderr, "pseudo: after setup\n"); return 2; } H.data->pseudoViscosity = c;
+        }
         else if(cmd == "continuous"){ int maxp; in >> maxp; H.cbuilder = new ContinuousParticleSetBuilder3(maxp); }
         else if(cmd == "append"){
             // ContinuousParticleSetBuilder3::AddParticle + Commit (src/core/grid.h:1409-1441): AppendData, then

@@ -148,6 +148,23 @@ def append_run():
     print("append_run", len(sc["pos"]), "+", len(add_pos), "+", len(add_pos), "particles")
 
 
+def pseudo_run():
+    """Pseudo-viscosity smoothing switched on (coefficient 200: 200 * 7e-4 > 0.1; ComputePseudoViscosity*KernelFor,
+    src/equations/sph_equations3.cpp:341-382, 469-483): probe scene, 25 sub-steps."""
+    sc = scenes.probe_scene()
+    wd = tempfile.mkdtemp(prefix="bbref_")
+    O.write_particles(os.path.join(wd, "p.bin"), sc["pos"], sc["vel"])
+    job = ["threads 4", "spacing 0.02", "scale 1.8", f"collider box {I} 0.6 0.6 0.6 1 0", "domain_from_collider 0",
+           f"particles {wd}/p.bin", "setup", "pseudo 200", "step 7e-4 1", "dump {wd}/s1_", "step 7e-4 24", "dump {wd}/s25_"]
+    O.run_ref(job, wd)
+    data = dict(p_pos=sc["pos"].astype(np.float64), p_vel=sc["vel"].astype(np.float64))
+    for pre in ("s1_", "s25_"):
+        for k, v in load_all(wd, pre, ["pos", "vel", "density"]).items():
+            data[pre + k] = v
+    np.savez_compressed(os.path.join(HERE, "pseudo_run.npz"), **data)
+    print("pseudo_run", len(sc["pos"]), "particles")
+
+
 def grid_facts():
     """UtilBuildGridForDomain results printed by the reference for several domains / spacings."""
     rows = []
@@ -172,4 +189,5 @@ if __name__ == "__main__":
     collider_vectors()
     obstacle_run()
     append_run()
+    pseudo_run()
     grid_facts()

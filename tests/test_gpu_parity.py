@@ -385,3 +385,32 @@ def test_append_particles_between_steps_matches_reference_chains():
         eng.overwrite_state(pos, vel)
         run(10)
     assert eng.stats().nan_count == 0
+
+
+def test_pseudo_viscosity_smoothing_matches_oracle():
+    """The cold branch at the end of every sub-step (pseudoViscosity * dt > 0.1; sph_equations3.cpp:341-382, 469-483;
+    k_pseudo_aggregate / k_pseudo_interpolate), oracle side pinned bit-exactly against the reference
+    (tests/golden/pseudo_run.npz): 10 sub-steps with the state resynced after each, velocities within tolerance."""
+    sc = scenes.probe_scene()
+    eng = scenes.make_engine(sc, pseudo_viscosity=200.0)
+    orc = scenes.make_oracle(sc)
+    orc.P.pseudo_viscosity = 200.0
+    eng.set_particles(sc["pos"], sc["vel"])
+    orc.set_particles(sc["pos"], sc["vel"])
+    plain = scenes.make_engine(sc)
+    plain.set_particles(sc["pos"], sc["vel"])
+    dt = sc["dt"]
+    ext = float(np.max(sc["domain_max"] - sc["domain_min"]))
+    for step in range(10):
+        orc.substep_pcisph(dt)
+        eng.step_pcisph(dt)
+        v, vo = eng.download(bb.VELOCITY), orc.a["vel"]
+        assert np.abs(v - vo).max() / np.abs(vo).max() < 10 * TOL_VEL, f"step {step}"
+        assert np.abs(eng.download(bb.POSITION) - orc.a["pos"]).max() / ext < TOL_POS, f"step {step}"
+        if step == 0:
+            plain.step_pcisph(dt)  # the smoothing really ran: without it the velocities differ far beyond the tolerance
+            assert np.abs(plain.download(bb.VELOCITY) - vo).max() / np.abs(vo).max() > 100 * TOL_VEL
+        pos, vel = scenes.f32(orc.a["pos"]), scenes.f32(orc.a["vel"])
+        orc.a["pos"][:] = pos
+        orc.a["vel"][:] = vel
+        eng.overwrite_state(pos, vel)
