@@ -29,6 +29,7 @@
 #include <functional>
 #include <memory>
 #include <stdexcept>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -449,6 +450,45 @@ inline void SerializerSaveSphDataSet3(SphSolverData3 *data, const char *filename
     }
     std::fprintf(fp, "\tDataEnd\nFluidEnd\n");
     std::fclose(fp);
+}
+
+// Shape::BoxSerialize / SphereSerialize (src/shapes/box.cpp:37-57, sphere.cpp:11-31): the "ShapeBegin ... ShapeEnd"
+// block bbtool reads (stream formatting of the reference: 6 significant digits); other shape kinds have no text form.
+inline std::string ShapeSerialize(const Shape &s){
+    if(s.type != ShapeBox && s.type != ShapeSphere) return std::string();
+    std::stringstream ss;
+    ss << "ShapeBegin\n";
+    if(s.type == ShapeBox){
+        ss << "\t\"Type\" box" << std::endl;
+        ss << "\t\"Length\" " << s.sizex << " " << s.sizey << " " << s.sizez << std::endl;
+    }else{
+        ss << "\t\"Type\" sphere" << std::endl;
+        ss << "\t\"Radius\" " << s.radius << std::endl;
+    }
+    ss << "\t\"Transform\" ";
+    for(int i = 0; i < 4; i++) for(int j = 0; j < 4; j++){
+        if(i == 3 && j == 3) ss << s.ObjectToWorld.m[i][j]; else ss << s.ObjectToWorld.m[i][j] << " ";
+    }
+    ss << std::endl;
+    ss << "ShapeEnd";
+    return ss.str();
+}
+// UtilSaveSimulation3 (src/core/util.h:296-328): the file is rewritten with the shape blocks of the active obstacle
+// colliders -- every collider but the LAST, which the reference takes to be the domain -- followed by the particle
+// block.  (The boundary column needs the boundary classification, which is out of scope: flags p, v, d, m.)
+inline void UtilSaveSimulation3(ColliderSet3 *colliders, SphSolverData3 *data, const char *filename, int flags){
+    std::remove(filename);
+    FILE *fp = std::fopen(filename, "a+");
+    if(!fp){ std::printf("Failed to open file %s\n", filename); return; }
+    std::stringstream ss;
+    if(colliders) for(int i = 0; i < colliders->nColiders() - 1; i++) if(colliders->active[i]) ss << ShapeSerialize(*colliders->shapes[i]) << std::endl;
+    std::fprintf(fp, "%s", ss.str().c_str());
+    std::fclose(fp);
+    SerializerSaveSphDataSet3(data, filename, flags);
+}
+template<typename Solver, typename ParticleAccessor>
+inline void UtilSaveSimulation3(Solver *solver, ParticleAccessor *, const char *filename, int flags){
+    UtilSaveSimulation3(solver->GetColliders().get(), solver->GetSphSolverData(), filename, flags);
 }
 
 // PciSphRunSimulation3 / UtilRunSimulation3 (src/core/util.h:539-599) without the viewer: callback(step) before the

@@ -1,11 +1,13 @@
 // frame_tool: writes one bbtool-readable text frame with the facade's SerializerSaveSphDataSet3 from a raw state
 // file -- host only (no engine), used by tests/test_frame_writer.py to compare the writer byte for byte with the
 // reference's own (src/third/serializer.cpp:812-921) and to feed the reference's reader.
-//   frame_tool <state.bin> <out.txt> <flags>
+//   frame_tool <state.bin> <out.txt> <flags> [--box tx ty tz sx sy sz | --sphere tx ty tz r] ...
+//     with shapes: UtilSaveSimulation3 (shape blocks of every collider but the last + the particle block)
 //   state.bin: int64 n, double spacing, double mass, double pos[3n], double vel[3n], double rho[n]
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 #include "bubbles_api.h"
 
@@ -27,6 +29,17 @@ int main(int argc, char **argv){
     for(int64_t i = 0; i < n; i++) set->set.densities[(size_t)i] = rho[(size_t)i];
     auto data = bbx::DefaultSphSolverData3(true);
     data->sphpSet = set;
-    bbx::SerializerSaveSphDataSet3(data.get(), argv[2], std::atoi(argv[3]));
+    bbx::ColliderSetBuilder3 cb; int shapes = 0;
+    for(int a = 4; a < argc; ){
+        std::string k = argv[a];
+        if(k == "--box" && a + 6 < argc){
+            cb.AddCollider3(bbx::MakeBox(bbx::Translate(std::atof(argv[a+1]), std::atof(argv[a+2]), std::atof(argv[a+3])),
+                                         bbx::vec3f(std::atof(argv[a+4]), std::atof(argv[a+5]), std::atof(argv[a+6])))); a += 7; shapes++;
+        }else if(k == "--sphere" && a + 4 < argc){
+            cb.AddCollider3(bbx::MakeSphere(bbx::Translate(std::atof(argv[a+1]), std::atof(argv[a+2]), std::atof(argv[a+3])), std::atof(argv[a+4]))); a += 5; shapes++;
+        }else{ std::fprintf(stderr, "bad shape argument %s\n", argv[a]); return 2; }
+    }
+    if(shapes) bbx::UtilSaveSimulation3(cb.GetColliderSet().get(), data.get(), argv[2], std::atoi(argv[3]));
+    else bbx::SerializerSaveSphDataSet3(data.get(), argv[2], std::atoi(argv[3]));
     return 0;
 }

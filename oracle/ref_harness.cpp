@@ -456,6 +456,12 @@ int main(int argc, char **argv){
             std::string file; int flags; in >> file >> flags;
             SerializerSaveSphDataSet3(H.data, file.c_str(), flags);
         }
+        else if(cmd == "save_sim"){
+            // UtilSaveSimulation3 (src/core/util.h:296-328): shape blocks of every collider but the last + the particle block
+            std::string file; int flags; in >> file >> flags;
+            if(H.solverKind == 0) UtilSaveSimulation3<PciSphSolver3, ParticleSet3>(&H.pci, H.sphSet->GetParticleSet(), file.c_str(), flags);
+            else UtilSaveSimulation3<SphSolver3, ParticleSet3>(&H.sph, H.sphSet->GetParticleSet(), file.c_str(), flags);
+        }
         else if(cmd == "load_frame"){
             // the reference's own frame reader (what bbtool uses: SerializerLoadParticles3, serializer.cpp:444-559)
             std::string file, prefix; in >> file >> prefix;

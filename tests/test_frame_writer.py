@@ -75,3 +75,33 @@ def test_writer_is_byte_identical_to_the_reference_and_its_reader_loads_it(tmp_p
         assert same(np.load(tmp_path / "l_rho.npy"), g(rho))
     if flags & M:
         assert same(np.load(tmp_path / "l_mass.npy"), np.full(n, float("%g" % mass)))
+
+
+def test_simulation_file_with_shape_blocks_is_byte_identical(tmp_path):
+    """UtilSaveSimulation3 (src/core/util.h:296-328): shape blocks (Shape::BoxSerialize / SphereSerialize,
+    box.cpp:37-57, sphere.cpp:11-31) of every collider but the last -- the domain -- then the particle block."""
+    sc = scenes.probe_scene()
+    O.write_particles(str(tmp_path / "p.bin"), sc["pos"], sc["vel"])
+    I = O.mat_str(np.eye(4))
+    box_t, sph_t = (-0.15, -0.25, -0.1), (0.1, -0.27, 0.1)
+    job = ["threads 2", f"spacing {sc['spacing']}", f"scale {sc['scale']}",
+           f"collider box {O.mat_str(O.translate(*box_t))} 0.1 0.125 0.15 0 0.1",
+           f"collider sphere {O.mat_str(O.translate(*sph_t))} 0.08 0 0.2",
+           f"collider box {I} 0.6 0.6 0.6 1 0", "domain_from_collider 2",
+           f"particles {tmp_path}/p.bin", "setup", f"step {sc['dt']} 2", f"dump {tmp_path}/s_",
+           f"save_sim {tmp_path}/ref.txt {P | V}"]
+    O.run_ref(job, str(tmp_path))
+    pos, vel, rho = (np.load(tmp_path / f"s_{k}.npy") for k in ("pos", "vel", "density"))
+    with open(tmp_path / "state.bin", "wb") as f:
+        f.write(struct.pack("<qdd", len(pos), float(sc["spacing"]), 0.0))
+        for a in (pos, vel, rho):
+            f.write(np.ascontiguousarray(a, np.float64).tobytes())
+    args = [_tool(), str(tmp_path / "state.bin"), str(tmp_path / "bbx.txt"), str(P | V),
+            "--box", *[repr(float(x)) for x in box_t], "0.1", "0.125", "0.15",
+            "--sphere", *[repr(float(x)) for x in sph_t], "0.08",
+            "--box", "0", "0", "0", "0.6", "0.6", "0.6"]
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref, ours = open(tmp_path / "ref.txt", "rb").read(), open(tmp_path / "bbx.txt", "rb").read()
+    assert ref.startswith(b"ShapeBegin\n\t\"Type\" box") and ref.count(b"ShapeBegin") == 2  # the container is not written
+    assert ours == ref
