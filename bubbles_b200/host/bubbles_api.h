@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -450,6 +451,126 @@ inline void SerializerSaveSphDataSet3(SphSolverData3 *data, const char *filename
     }
     std::fprintf(fp, "\tDataEnd\nFluidEnd\n");
     std::fclose(fp);
+}
+
+// ---- frame reader: SerializerLoadParticles3 / SerializerLoadSphDataSet3 / SerializerLoadPoints3
+// (src/third/serializer.cpp:84-261, 444-577).  Numbers are parsed the way the reference parses them (ParseFloat,
+// src/third/obj_loader.cpp:270-278 = tinyobjloader's tryParseDouble: decimal digits accumulated in a double, the
+// fraction digit by digit times 10^-k, a power-of-ten exponent applied as ldexp(m * 5^e, e)), NOT with strtod: the
+// values loaded here are bit-identical to what bbtool and the reference's loaders see.
+inline bool ParseDecimal(const char *s, const char *end, double *out){
+    static const double frac_lut[8] = {1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001};
+    if(s >= end) return false;
+    double m = 0.0; int e10 = 0; bool neg = false;
+    const char *c = s;
+    if(*c == '+' || *c == '-'){ neg = (*c == '-'); c++; }
+    else if(!(*c >= '0' && *c <= '9')) return false;
+    int digits = 0;
+    while(c != end && *c >= '0' && *c <= '9'){ m = m * 10 + (int)(*c - '0'); c++; digits++; }
+    if(digits == 0) return false;
+    bool has_exp = false;
+    if(c != end){
+        if(*c == '.'){
+            c++;
+            int k = 1;
+            while(c != end && *c >= '0' && *c <= '9'){ m += (int)(*c - '0') * (k < 8 ? frac_lut[k] : std::pow(10.0, -k)); k++; c++; }
+            has_exp = (c != end) && (*c == 'e' || *c == 'E');
+        }else has_exp = (*c == 'e' || *c == 'E');
+    }
+    if(has_exp){
+        c++;
+        bool eneg = false;
+        if(c != end && (*c == '+' || *c == '-')){ eneg = (*c == '-'); c++; }
+        else if(!(c != end && *c >= '0' && *c <= '9')) return false;   // an empty exponent is not a number
+        int ed = 0;
+        while(c != end && *c >= '0' && *c <= '9'){ e10 = e10 * 10 + (int)(*c - '0'); c++; ed++; }
+        if(ed == 0) return false;
+        if(eneg) e10 = -e10;
+    }
+    *out = (neg ? -1 : 1) * (e10 ? std::ldexp(m * std::pow(5.0, e10), e10) : m);
+    return true;
+}
+inline Float ParseFloat(const char **token){
+    *token += std::strspn(*token, " \t");
+    const char *end = *token + std::strcspn(*token, " \t\r");
+    double v = 0; ParseDecimal(*token, end, &v);
+    *token = end;
+    return v;
+}
+inline vec3f ParseV3(const char **token){ Float a = ParseFloat(token), b = ParseFloat(token), c = ParseFloat(token); return vec3f(a, b, c); }
+enum { SERIALIZER_LAYERS = 0x40, SERIALIZER_RULE_BOUNDARY_EXCLUSIVE = 0x80, SERIALIZER_XYZ = 0x100 };
+inline int SerializerFlagsFromString(const char *spec){
+    int flags = 0;
+    for(const char *p = spec; *p; p++){
+        switch(*p | 0x20){
+            case 'p': flags |= SERIALIZER_POSITION; break; case 'v': flags |= SERIALIZER_VELOCITY; break;
+            case 'd': flags |= SERIALIZER_DENSITY; break;  case 'm': flags |= SERIALIZER_MASS; break;
+            case 'b': flags |= SERIALIZER_BOUNDARY; break; case 'n': flags |= SERIALIZER_NORMAL; break;
+            case 'l': flags |= SERIALIZER_LAYERS; break;   case 'o': flags |= SERIALIZER_RULE_BOUNDARY_EXCLUSIVE; break;
+            case 'z': flags |= SERIALIZER_XYZ; break;
+            default: std::printf("Unknown flag argument %c\n", *p); return -1;
+        }
+    }
+    return flags;
+}
+struct SerializedParticle { vec3f position, velocity, normal; Float density = 0, mass = 0; int boundary = 0; };
+// header of the first fluid section: "Count", "Format"; leaves the stream behind its "DataBegin" line
+inline int SerializerFindFluidSection(std::istream &is, std::string &format){
+    std::string line; int count = 0; bool in_region = false;
+    while(std::getline(is, line)){
+        if(!line.empty() && line.back() == '\r') line.pop_back();
+        std::istringstream ls(line); std::string tok;
+        while(ls >> tok){
+            if(!in_region){ if(tok == "FluidBegin") in_region = true; continue; }
+            if(tok == "\"Count\""){ std::string v; if(ls >> v){ const char *t = v.c_str(); count = (int)ParseFloat(&t); } }
+            else if(tok == "\"Format\""){ ls >> format; }
+            else if(tok == "DataBegin") return count;
+            else if(tok == "FluidEnd") in_region = false;
+        }
+    }
+    return count;
+}
+inline int SerializerLoadParticles3(std::vector<SerializedParticle> *pSet, const char *filename, int &flags){
+    std::ifstream ifs(filename);
+    if(!ifs){ std::printf("Could not open file %s\n", filename); return -1; }
+    std::string format;
+    const int expected = SerializerFindFluidSection(ifs, format);
+    if(!format.empty()) flags = SerializerFlagsFromString(format.c_str());
+    pSet->clear(); pSet->reserve(expected > 0 ? expected : 0);
+    std::string line; bool found_end = false;
+    while(std::getline(ifs, line)){
+        if(!line.empty() && line.back() == '\r') line.pop_back();
+        const char *token = line.c_str();
+        token += std::strspn(token, " \t");
+        if(token[0] == '\0' || token[0] == '#') continue;
+        if(std::strstr(token, "DataEnd")){ found_end = true; break; }
+        SerializedParticle q;
+        auto skip = [&](){ while(*token == ' ' || *token == '\t' || *token == '\r') token++; };
+        if(flags & SERIALIZER_POSITION){ q.position = ParseV3(&token); skip(); }
+        if(flags & SERIALIZER_VELOCITY){ q.velocity = ParseV3(&token); skip(); }
+        if(flags & SERIALIZER_DENSITY){ q.density = ParseFloat(&token); skip(); }
+        if(flags & SERIALIZER_MASS){ q.mass = ParseFloat(&token); skip(); }
+        if(flags & SERIALIZER_BOUNDARY){
+            q.boundary = (int)ParseFloat(&token); skip();
+            if((flags & SERIALIZER_RULE_BOUNDARY_EXCLUSIVE) && !q.boundary) continue;
+        }
+        if(flags & SERIALIZER_NORMAL){ q.normal = ParseV3(&token); skip(); }
+        pSet->push_back(q);
+    }
+    if(!found_end) throw Error(BBX_ERR_INVALID, "Unterminated fluid description, missing 'DataEnd'");
+    return (int)pSet->size();
+}
+inline int SerializerLoadSphDataSet3(ParticleSetBuilder3 *builder, const char *filename, int &flags, std::vector<int> *boundary = nullptr){
+    std::vector<SerializedParticle> ps;
+    const int n = SerializerLoadParticles3(&ps, filename, flags);
+    for(int i = 0; i < n; i++){ builder->AddParticle(ps[i].position, ps[i].velocity); if(boundary) boundary->push_back(ps[i].boundary); }
+    return n;
+}
+inline void SerializerLoadPoints3(std::vector<vec3f> *points, const char *filename, int &flags){
+    std::vector<SerializedParticle> ps;
+    const int n = SerializerLoadParticles3(&ps, filename, flags);
+    points->clear();
+    for(int i = 0; i < n; i++) points->push_back(ps[i].position);
 }
 
 // Shape::BoxSerialize / SphereSerialize (src/shapes/box.cpp:37-57, sphere.cpp:11-31): the "ShapeBegin ... ShapeEnd"

@@ -11,7 +11,29 @@
 #include <vector>
 #include "bubbles_api.h"
 
+// frame_tool --load <frame.txt> <out.bin>: the facade's reader (SerializerLoadParticles3) on a frame file;
+//   out.bin: int64 n, int64 flags, double pos[3n], vel[3n], rho[n], mass[n]
+static int load_mode(const char *in, const char *out){
+    std::vector<bbx::SerializedParticle> ps; int flags = 0;
+    const int n = bbx::SerializerLoadParticles3(&ps, in, flags);
+    if(n < 0) return 1;
+    FILE *fp = std::fopen(out, "wb");
+    if(!fp) return 1;
+    int64_t hdr[2] = {n, flags};
+    std::fwrite(hdr, sizeof(int64_t), 2, fp);
+    for(int pass = 0; pass < 4; pass++) for(int i = 0; i < n; i++){
+        const bbx::SerializedParticle &q = ps[(size_t)i];
+        if(pass == 0){ double v[3] = {q.position.x, q.position.y, q.position.z}; std::fwrite(v, 8, 3, fp); }
+        else if(pass == 1){ double v[3] = {q.velocity.x, q.velocity.y, q.velocity.z}; std::fwrite(v, 8, 3, fp); }
+        else if(pass == 2){ double v = q.density; std::fwrite(&v, 8, 1, fp); }
+        else{ double v = (flags & bbx::SERIALIZER_MASS) ? q.mass : 0.0; std::fwrite(&v, 8, 1, fp); }
+    }
+    std::fclose(fp);
+    return 0;
+}
+
 int main(int argc, char **argv){
+    if(argc == 4 && std::string(argv[1]) == "--load") return load_mode(argv[2], argv[3]);
     if(argc < 4){ std::fprintf(stderr, "usage: frame_tool state.bin out.txt flags\n"); return 2; }
     FILE *fp = std::fopen(argv[1], "rb");
     if(!fp){ std::fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }

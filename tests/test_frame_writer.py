@@ -105,3 +105,35 @@ def test_simulation_file_with_shape_blocks_is_byte_identical(tmp_path):
     ref, ours = open(tmp_path / "ref.txt", "rb").read(), open(tmp_path / "bbx.txt", "rb").read()
     assert ref.startswith(b"ShapeBegin\n\t\"Type\" box") and ref.count(b"ShapeBegin") == 2  # the container is not written
     assert ours == ref
+
+
+def _load_with_facade(path, tmp_path, tag):
+    out = tmp_path / f"{tag}.bin"
+    r = subprocess.run([_tool(), "--load", str(path), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = open(out, "rb").read()
+    n, flags = struct.unpack("<qq", raw[:16])
+    a = np.frombuffer(raw[16:], dtype=np.float64)
+    return n, flags, a[:3 * n].reshape(n, 3), a[3 * n:6 * n].reshape(n, 3), a[6 * n:7 * n], a[7 * n:8 * n]
+
+
+@pytest.mark.parametrize("flags", [P, P | V | D, P | V | D | M])
+def test_reader_loads_reference_frames_bit_identically_to_the_reference_reader(tmp_path, flags):
+    """The facade's frame reader (SerializerLoadParticles3 / LoadSphDataSet3 / LoadPoints3, serializer.cpp:84-261,
+    444-577, numbers parsed like ParseFloat, obj_loader.cpp:270-278) on files the REFERENCE wrote -- plain frames and a
+    simulation file with shape blocks in front -- against the reference's own reader on the same files: count, format
+    and every value bit for bit."""
+    sc, job = _reference_state(tmp_path)
+    box = f"collider box {O.mat_str(O.translate(-0.15, -0.25, -0.1))} 0.1 0.1 0.1 0 0.1"
+    job = job[:3] + [box] + job[3:]            # an obstacle in front of the container (written by save_sim)
+    job[job.index("domain_from_collider 0")] = "domain_from_collider 1"
+    ref_txt, sim_txt = tmp_path / "ref.txt", tmp_path / "sim.txt"
+    O.run_ref(job + [f"save_frame {ref_txt} {flags}", f"save_sim {sim_txt} {flags}",
+                     f"load_frame {ref_txt} {tmp_path}/a_", f"load_frame {sim_txt} {tmp_path}/b_"], str(tmp_path))
+    for path, pre in ((ref_txt, "a_"), (sim_txt, "b_")):
+        n, fl, pos, vel, rho, mass = _load_with_facade(path, tmp_path, pre)
+        assert fl == flags and n == len(np.load(tmp_path / f"{pre}pos.npy"))
+        assert np.array_equal(pos, np.load(tmp_path / f"{pre}pos.npy"))
+        assert np.array_equal(vel, np.load(tmp_path / f"{pre}vel.npy"))
+        assert np.array_equal(rho, np.load(tmp_path / f"{pre}rho.npy"))
+        assert np.array_equal(mass, np.load(tmp_path / f"{pre}mass.npy"))
