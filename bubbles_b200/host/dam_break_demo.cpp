@@ -3,13 +3,15 @@
 // (MakeBox / VolumeParticleEmitter3 / UtilBuildGridForDomain / ColliderSetBuilder3 / PciSphSolver3 /
 // SerializerSaveSphDataSet3 / PciSphRunSimulation3), host code only -- every kernel runs inside libbbx.so.
 //
-//   dam_break_demo [--scaling S] [--frames N] [--steps N --dt X] [--jitter J] [--out DIR] [--dump FILE] [--sph] [--emit K]
+//   dam_break_demo [--scaling S] [--frames N] [--steps N --dt X] [--jitter J] [--out DIR] [--dump FILE] [--sph] [--emit K] [--load FRAME]
 //     --scaling  domainScaling of the reference scene (2.5 there: ~0.9 M particles; default 0.6: ~12 k)
 //     --frames   frames of 1/240 s through Advance() (CFL sub-stepping), default 2
 //     --steps    instead of frames: N fixed-dt sub-steps (AdvanceTimeStep)
 //     --out      directory for the text frames bbtool reads (out_<frame>.txt), off by default
 //     --emit     continuous emission (ContinuousParticleSetBuilder3): after every frame K more particles enter above the
 //                fluid (AddParticle + Commit), as the reference's MapGridEmit scenes do
+//     --load     start from a frame file (positions and, when present, velocities: SerializerLoadSphDataSet3) instead of
+//                emitting the block, e.g. the reference's resources/dam_break_50
 //     --dump     raw little-endian doubles: n, then n x 3 positions, n x 3 velocities (for the parity test)
 #include <cstdio>
 #include <cstdlib>
@@ -23,7 +25,7 @@ using namespace bbx;
 int main(int argc, char **argv){
     Float domainScaling = 0.6f, jitter = 0.001, dt = 0;
     int frames = 2, steps = 0, emit = 0; bool sph = false;
-    std::string out, dump;
+    std::string out, dump, load;
     for(int i = 1; i < argc; i++){
         std::string a = argv[i];
         auto next = [&](){ if(i + 1 >= argc){ std::fprintf(stderr, "missing value for %s\n", a.c_str()); std::exit(2); } return std::string(argv[++i]); };
@@ -36,6 +38,7 @@ int main(int argc, char **argv){
         else if(a == "--dump") dump = next();
         else if(a == "--sph") sph = true;
         else if(a == "--emit") emit = std::atoi(next().c_str());
+        else if(a == "--load") load = next();
         else{ std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try{
@@ -58,7 +61,15 @@ int main(int argc, char **argv){
         VolumeParticleEmitter3 emitterp(boxp, boxp->GetBounds(), spacing, vec3f(0, -6, 0));
         emitterSet.AddEmitter(&emitterp);
         emitterSet.SetJitter(jitter);
-        emitterSet.Emit(&pBuilder);
+        if(load.empty()) emitterSet.Emit(&pBuilder);
+        else{
+            ParticleSetBuilder3 fromFile; int flags = SERIALIZER_POSITION;
+            const int n = SerializerLoadSphDataSet3(&fromFile, load.c_str(), flags);
+            if(n <= 0){ std::fprintf(stderr, "no particles in %s\n", load.c_str()); return 1; }
+            for(int i = 0; i < n; i++) pBuilder.AddParticle(fromFile.positions[i], (flags & SERIALIZER_VELOCITY) ? fromFile.velocities[i] : vec3f(0, -6, 0));
+            pBuilder.Commit();
+            std::printf("loaded %d particles (format %s) from %s\n", n, SerializerStringFromFlags(flags).c_str(), load.c_str());
+        }
 
         auto domainGrid = UtilBuildGridForDomain(container->GetBounds(), spacing, spacingScale);
         ColliderSetBuilder3 cBuilder;
