@@ -3,6 +3,7 @@ test_pcisph3_dam_break, src/tests/test_pcisph_extra.cpp:1102-1169): builds with 
 loudly without a GPU, and on a GPU produces exactly what the ctypes path produces for the same scene, plus a
 text frame in the format bbtool reads (src/third/serializer.cpp:884-921)."""
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -96,3 +97,14 @@ def test_demo_continuous_emission():
     counts = [int(x) for x in __import__("re").findall(r"Particles (\d+)", r.stdout)]
     assert len(counts) == 3 and counts[1] == counts[0] + 100 and counts[2] == counts[0] + 200, r.stdout
     assert "non-finite 0" in r.stdout
+
+
+@pytest.mark.gpu
+def test_demo_restarts_from_a_frame_file(tmp_path):
+    """--load: a frame written by the facade (positions only, "%g") is read back by the facade's reader and stepped."""
+    r = subprocess.run([_demo(), "--jitter", "0", "--steps", "5", "--out", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    n = int(re.search(r"particles (\d+),", r.stdout).group(1))
+    r = subprocess.run([_demo(), "--load", str(tmp_path / "out_1.txt"), "--steps", "5"], capture_output=True, text=True)
+    assert r.returncode == 0 and "===== OK" in r.stdout, r.stdout + r.stderr
+    assert f"loaded {n} particles (format p)" in r.stdout and "non-finite 0" in r.stdout
