@@ -119,15 +119,32 @@ struct Shape {
         }
         return b;
     }
-    // Shape::SignedDistance for the analytic shapes (emitter acceptance test, src/core/shape.cpp:284-288)
+    // Shape::SignedDistance (src/core/shape.cpp:275-288) = -|d| inside, |d| outside, d = ClosestDistance.  Box:
+    // BoxClosestDistance (src/shapes/box.cpp:74-109) with the reference's Inside(point, bounds)
+    // (src/core/geometry.h:1773-1783): a point outside the box still counts as inside when it lies within 1e-6 of ANY
+    // face plane -- the emitter keeps such lattice points, so the rule is mirrored here.
     Float SignedDistance(const vec3f &p) const {
         vec3f q = ObjectToWorld.InversePoint(p);
         Float d;
         if(type == ShapeSphere) d = q.Length() - radius;
         else if(type == ShapeBox){
-            vec3f a(std::fabs(q.x) - sizex / 2, std::fabs(q.y) - sizey / 2, std::fabs(q.z) - sizez / 2);
-            vec3f o(std::fmax(a.x, 0.0), std::fmax(a.y, 0.0), std::fmax(a.z, 0.0));
-            d = o.Length() + std::fmin(std::fmax(a.x, std::fmax(a.y, a.z)), 0.0);
+            const vec3f hi(sizex / 2.0, sizey / 2.0, sizez / 2.0), lo(-hi.x, -hi.y, -hi.z);
+            bool in = q.x >= lo.x && q.x <= hi.x && q.y >= lo.y && q.y <= hi.y && q.z >= lo.z && q.z <= hi.z;
+            if(!in){
+                const Float ox = std::fmin(std::fabs(lo.x - q.x), std::fabs(hi.x - q.x));
+                const Float oy = std::fmin(std::fabs(lo.y - q.y), std::fabs(hi.y - q.y));
+                const Float oz = std::fmin(std::fabs(lo.z - q.z), std::fabs(hi.z - q.z));
+                in = ox < 1e-6 || oy < 1e-6 || oz < 1e-6;
+            }
+            if(in){ // distance to the nearest of the six face planes, negative
+                Float best = std::fabs(q.x - hi.x);
+                const Float c[5] = {std::fabs(q.y - hi.y), std::fabs(q.z - hi.z), std::fabs(q.x - lo.x), std::fabs(q.y - lo.y), std::fabs(q.z - lo.z)};
+                for(Float v : c) if(v < best) best = v;
+                d = -best;
+            }else{
+                const vec3f cl(std::fmin(std::fmax(q.x, lo.x), hi.x), std::fmin(std::fmax(q.y, lo.y), hi.y), std::fmin(std::fmax(q.z, lo.z), hi.z));
+                d = (q - cl).Length();
+            }
         }else d = SampleSDF(p);
         return reverseOrientation ? -d : d;
     }
@@ -302,7 +319,9 @@ struct VolumeParticleEmitter3 {
         const Float maxJitter = 0.5 * jitter * spacing;
         BccLatticeForEach(bound, spacing, [&](const vec3f &point) -> bool {
             if(validator && !validator(point)) return true;
-            const float u0 = rand() / (RAND_MAX + 1.f), u1 = rand() / (RAND_MAX + 1.f);
+            // vec2f u(rand_float(), rand_float()) (emitter.cpp:272): g++ evaluates the arguments right to left, so the FIRST
+            // draw is u[1]; kept that way so that an emission reproduces the reference's particles
+            const float u1 = rand() / (RAND_MAX + 1.f), u0 = rand() / (RAND_MAX + 1.f);
             const Float usqrt = 2 * std::sqrt((Float)u1 * (1 - (Float)u1)), utheta = 2 * Pi * (Float)u0;
             const vec3f target = point + maxJitter * vec3f(std::cos(utheta) * usqrt, std::sin(utheta) * usqrt, 1 - 2 * (Float)u1);
             if(shape->SignedDistance(target) <= 0){

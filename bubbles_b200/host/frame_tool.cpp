@@ -32,8 +32,29 @@ static int load_mode(const char *in, const char *out){
     return 0;
 }
 
+// frame_tool --emit <out.bin> tx ty tz sx sy sz spacing vx vy vz jitter seed: the facade's VolumeParticleEmitter3 over a
+//   box (libc rand() seeded like the reference scene scripts do); out.bin: int64 n, double pos[3n], vel[3n]
+static int emit_mode(int argc, char **argv){
+    if(argc != 15) return 2;
+    double a[12]; for(int k = 0; k < 12; k++) a[k] = std::atof(argv[3 + k]);
+    std::srand((unsigned)a[11]);
+    auto box = bbx::MakeBox(bbx::Translate(a[0], a[1], a[2]), bbx::vec3f(a[3], a[4], a[5]));
+    bbx::VolumeParticleEmitter3 em(box, box->GetBounds(), a[6], bbx::vec3f(a[7], a[8], a[9]));
+    bbx::VolumeParticleEmitterSet3 set; set.AddEmitter(&em); set.SetJitter(a[10]);
+    bbx::ParticleSetBuilder3 b; set.Emit(&b);
+    FILE *fp = std::fopen(argv[2], "wb");
+    if(!fp) return 1;
+    int64_t n = b.GetParticleCount();
+    std::fwrite(&n, sizeof(n), 1, fp);
+    std::fwrite(b.positions.data(), sizeof(bbx::vec3f), b.positions.size(), fp);
+    std::fwrite(b.velocities.data(), sizeof(bbx::vec3f), b.velocities.size(), fp);
+    std::fclose(fp);
+    return 0;
+}
+
 int main(int argc, char **argv){
     if(argc == 4 && std::string(argv[1]) == "--load") return load_mode(argv[2], argv[3]);
+    if(argc >= 2 && std::string(argv[1]) == "--emit") return emit_mode(argc, argv);
     if(argc < 4){ std::fprintf(stderr, "usage: frame_tool state.bin out.txt flags\n"); return 2; }
     FILE *fp = std::fopen(argv[1], "rb");
     if(!fp){ std::fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }

@@ -108,3 +108,22 @@ def test_demo_restarts_from_a_frame_file(tmp_path):
     r = subprocess.run([_demo(), "--load", str(tmp_path / "out_1.txt"), "--steps", "5"], capture_output=True, text=True)
     assert r.returncode == 0 and "===== OK" in r.stdout, r.stdout + r.stderr
     assert f"loaded {n} particles (format p)" in r.stdout and "non-finite 0" in r.stdout
+
+
+def test_facade_emitter_reproduces_the_reference_emitter_bit_for_bit(tmp_path):
+    """VolumeParticleEmitter3 of the facade (BCC lattice, jitter from libc rand(), shape test) against the particles the
+    REFERENCE's emitter produced for the same box (tests/golden/probe_trace.npz, s0_*: emit_box at (0.1, -0.1, 0.1),
+    0.2 x 0.3 x 0.2, spacing 0.02, v = (0, -1, 0), jitter 0.001, srand(1)).  CPU only."""
+    G.build()
+    tool = os.path.join(ROOT, "bubbles_b200", "lib", "frame_tool")
+    out = tmp_path / "emit.bin"
+    r = subprocess.run([tool, "--emit", str(out), "0.1", "-0.1", "0.1", "0.2", "0.3", "0.2", "0.02", "0", "-1", "0", "0.001", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = open(out, "rb").read()
+    n = int(np.frombuffer(raw[:8], dtype=np.int64)[0])
+    a = np.frombuffer(raw[8:], dtype=np.float64)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "probe_trace.npz"))
+    assert n == len(g["s0_pos"])
+    assert np.array_equal(a[:3 * n].reshape(n, 3), g["s0_pos"])
+    assert np.array_equal(a[3 * n:].reshape(n, 3), g["s0_vel"])
