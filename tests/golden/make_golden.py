@@ -165,6 +165,32 @@ def pseudo_run():
     print("pseudo_run", len(sc["pos"]), "particles")
 
 
+def sdf_run():
+    """Block dropped on a baked-SDF torus (MakeSDFShape-style vertex grid, Shape::ClosestPointBySDF in the response),
+    150 sub-steps: the SDF collider inside a whole trajectory."""
+    import bubbles_b200 as bb
+    torus = scenes.sdf_torus((0.05, -0.1, 0.0), 0.12, 0.04)
+    bmin, bmax = (-0.15, -0.16, -0.2), (0.25, -0.04, 0.2)
+    nodes, dx, origin = bb.sdf_grid_layout(bmin, bmax, 0.01, 0.1)
+    ix, iy, iz = np.meshgrid(np.arange(nodes[0]), np.arange(nodes[1]), np.arange(nodes[2]), indexing="ij")
+    pts = np.stack([origin[0] + dx * ix, origin[1] + dx * iy, origin[2] + dx * iz], axis=-1)
+    field = np.ascontiguousarray(torus(pts.reshape(-1, 3)).reshape(nodes).transpose(2, 1, 0))
+    wd = tempfile.mkdtemp(prefix="bbref_")
+    field.tofile(os.path.join(wd, "sdf.bin"))
+    job = ["threads 4", "spacing 0.02", "scale 1.8", f"collider box {I} 0.7 0.7 0.7 1 0",
+           f"collider sdf {bmin[0]} {bmin[1]} {bmin[2]} {bmax[0]} {bmax[1]} {bmax[2]} 0.01 0.1 0.1 {wd}/sdf.bin",
+           "domain_from_collider 0", f"emit_box {T(0.05, 0.12, 0.0)} 0.2 0.2 0.2 0 -2.5 0 0.001 3", "setup",
+           "dump {wd}/s0_", "step 7e-4 150", "dump {wd}/s150_", "dump_grid {wd}/s150_"]
+    O.run_ref(job, wd)
+    data = {}
+    for pre, names in (("s0_", ["pos", "vel"]), ("s150_", ["pos", "vel", "density", "cell_count", "cell_order"])):
+        for k, v in load_all(wd, pre, names).items():
+            data[pre + k] = v
+    np.savez_compressed(os.path.join(HERE, "sdf_run.npz"), **data)
+    print("sdf_run", len(data["s0_pos"]), "particles; moved by the torus:",
+          int((np.abs(data["s150_vel"][:, 0]) > 1e-3).sum()))
+
+
 def grid_facts():
     """UtilBuildGridForDomain results printed by the reference for several domains / spacings."""
     rows = []
@@ -190,4 +216,5 @@ if __name__ == "__main__":
     obstacle_run()
     append_run()
     pseudo_run()
+    sdf_run()
     grid_facts()
