@@ -257,6 +257,7 @@ class Oracle:
         L.orc_density(C.byref(P), n, _p(a["pos"]), _p(a["nbr_count"]), _p(a["nbr_ids"]), _p(a["density"]),
                       _p(a["pressure"]))
         out["density"] = a["density"].copy()
+        out["eos_pressure"] = a["pressure"].copy()
         L.orc_force_np(C.byref(P), n, _p(a["pos"]), _p(a["vel"]), _p(a["density"]), _p(a["nbr_count"]),
                        _p(a["nbr_ids"]), _p(a["force"]))
         out["force_np"] = a["force"].copy()

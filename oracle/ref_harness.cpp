@@ -221,6 +221,7 @@ static void TraceStep(Harness &H, Float dt, const std::string &prefix){
     ComputeParticleInteractionCPU(data);
     ComputeDensityCPU(data);
     DumpScalar(prefix + "density.npy", pSet->densities.data, n);
+    DumpScalar(prefix + "eos_pressure.npy", pSet->pressures.data, n); // ComputePressureValue (Tait EOS) of ComputeDensityFor
     ComputeNonPressureForceCPU(data);
     DumpVec3(prefix + "force_np.npy", pSet->forces.data, n);
     Float delta = H.pci.ComputeDelta(dt);

@@ -27,7 +27,7 @@ def load_all(wd, prefix, names):
     return {n: np.load(os.path.join(wd, prefix + n + ".npy")) for n in names}
 
 
-TRACE = ["rebuild_flag", "cell_count", "cell_order", "nbr_count", "nbr_ids", "density", "force_np", "delta", "pos_pred",
+TRACE = ["rebuild_flag", "cell_count", "cell_order", "nbr_count", "nbr_ids", "density", "eos_pressure", "force_np", "delta", "pos_pred",
          "density_pred", "pressure", "force_p", "max_density_error", "pos_out", "vel_out", "force_out", "rebuild_flag_out"]
 
 
@@ -105,9 +105,11 @@ def obstacle_run():
            f"collider sphere {T(0.1, -0.27, 0.1)} 0.08 0 0.2", f"collider box {T(-0.15, -0.25, -0.1)} 0.1 0.1 0.1 0 0.1",
            "domain_from_collider 0", f"emit_box {T(0.05, -0.1, 0.05)} 0.24 0.3 0.24 0 -2 0 0.001 7", "setup",
            "dump {wd}/s0_", "step 7e-4 240", "dump {wd}/s240_", "dump_grid {wd}/s240_",
-           "advance 0.004166666666666667", "advance 0.004166666666666667", "dump {wd}/adv_"]
+           "advance 0.004166666666666667", "advance 0.004166666666666667", "dump {wd}/adv_", "trace 7e-4 {wd}/t_"]
     out, wd = O.run_ref(job)
     data = {}
+    for k, v in load_all(wd, "t_", ["density", "eos_pressure", "nbr_count", "pos_out"]).items():  # a compressed state: Tait EOS > 0
+        data["t_" + k] = v
     for pre, names in (("s0_", ["pos", "vel"]), ("s240_", ["pos", "vel", "density", "cell_count", "cell_order", "nbr_count"]),
                        ("adv_", ["pos", "vel"])):
         for k, v in load_all(wd, pre, names).items():
