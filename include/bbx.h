@@ -35,7 +35,7 @@ enum bbx_status {
     BBX_ERR_NO_DEVICE = 3,    /* no usable GPU: the engine has no CPU path                   */
     BBX_ERR_CAPACITY = 4,     /* more particles than max_particles                           */
     BBX_ERR_OUT_OF_DOMAIN = 5,/* a particle position is outside the grid bounds              */
-    BBX_ERR_COMM = 6          /* NCCL error                                                  */
+    BBX_ERR_COMM = 6          /* NCCL error, or a slab neighbour that never signalled its halo */
 };
 
 enum bbx_solver { BBX_SOLVER_PCISPH = 0, BBX_SOLVER_SPH = 1 };
