@@ -22,12 +22,14 @@
 // host copies of positions / velocities / densities (what the reference's callbacks read through managed
 // memory).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <sstream>
@@ -226,6 +228,16 @@ struct ColliderSetBuilder3 {
     std::shared_ptr<ColliderSet3> GetColliderSet(){ return set; }
 };
 
+// --------------------------------------------------------------------------------------------- grid
+struct Grid3 { bbx_grid_desc desc; Bounds3f GetBounds() const { return Bounds3f(vec3f(desc.min[0], desc.min[1], desc.min[2]), vec3f(desc.max[0], desc.max[1], desc.max[2])); }
+               int GetCellCount() const { return desc.total; } };
+inline std::shared_ptr<Grid3> UtilBuildGridForDomain(const Bounds3f &domain, Float spacing, Float spacingScale){
+    auto g = std::make_shared<Grid3>();
+    double lo[3] = {domain.pMin.x, domain.pMin.y, domain.pMin.z}, hi[3] = {domain.pMax.x, domain.pMax.y, domain.pMax.z};
+    Check(bbx_grid_for_domain(lo, hi, spacing, spacingScale, &g->desc));
+    return g;
+}
+
 // ---------------------------------------------------------------------------------------- particles
 struct ParticleSetBuilder3 {
     std::vector<vec3f> positions, velocities;
@@ -263,17 +275,46 @@ inline std::shared_ptr<SphParticleSet3> SphParticleSet3FromBuilder(ParticleSetBu
     return s;
 }
 
+// The re-emission rule of ContinuousParticleSetBuilder3::MapGridEmit (src/core/grid.h:1367-1407) as a pure function:
+// for every mapped cell (ascending id) whose CURRENT chain has room (< 100 = MaximumParticlesPerBucket), its first
+// min(100 - size, template size) template positions are re-emitted unless a particle of the current chain lies
+// within d.  cell_count / cell_order = the chains (bbx_export_cells), positions = current positions by id.
+inline std::vector<vec3f> MapGridEmitCandidates(const std::map<unsigned, std::vector<vec3f>> &mapped, int total_cells,
+        const int *cell_count, const int *cell_order, const vec3f *positions, Float d){
+    std::vector<int> start((size_t)total_cells + 1, 0);
+    for(int c = 0; c < total_cells; c++) start[(size_t)c + 1] = start[(size_t)c] + cell_count[c];
+    std::vector<vec3f> out;
+    for(const auto &kv : mapped){
+        const unsigned h = kv.first; const std::vector<vec3f> &tmpl = kv.second;
+        if((int)h >= total_cells) continue;
+        const int size = cell_count[h];
+        if(size >= BBX_MAX_NEIGHBORS) continue;
+        const int toInsert = std::min(BBX_MAX_NEIGHBORS - size, (int)tmpl.size());
+        for(int i = 0; i < toInsert; i++){
+            bool can_add = true;
+            for(int j = 0; j < size && can_add; j++) if((positions[cell_order[start[h] + j]] - tmpl[(size_t)i]).Length() < d) can_add = false;
+            if(can_add) out.push_back(tmpl[(size_t)i]);
+        }
+    }
+    return out;
+}
+
 // ContinuousParticleSetBuilder3 (src/core/grid.h:1246-1450): a particle set with reserved room; AddParticle queues,
 // Commit appends (ids continue from the current count) -- on the device the new particles join the tail of their
-// cells' chains exactly like DistributeByParticleList (bbx_append_particles).  MapGridEmit (the host-side
-// re-emission policy over the cell chains) is not provided: emit with an emitter, or AddParticle + Commit.
+// cells' chains exactly like DistributeByParticleList (bbx_append_particles).  MapGrid (after the solver's Setup)
+// remembers the chains' positions as the emission template; MapGridEmit re-emits them between frames where there is
+// room (the chains come from the engine: bbx_export_cells; the positions are the solver's host mirror, so call it
+// after Advance).
 struct ContinuousParticleSetBuilder3 {
     std::vector<vec3f> positions, velocities;
     std::shared_ptr<SphParticleSet3> particleSet = std::make_shared<SphParticleSet3>();
     int maxNumOfParticles;
-    explicit ContinuousParticleSetBuilder3(int maxParticles = 2500000) : maxNumOfParticles(maxParticles > 1 ? maxParticles : 1) { particleSet->reservedSize = maxNumOfParticles; }
+    int reemitions = 0; bool reemitOnce = false;
+    std::map<unsigned, std::vector<vec3f>> mappedPositions;
+    int mappedCells = 0;
+    explicit ContinuousParticleSetBuilder3(int maxParticles = 2500000, bool _reemitOnce = false)
+        : maxNumOfParticles(maxParticles > 1 ? maxParticles : 1), reemitOnce(_reemitOnce) { particleSet->reservedSize = maxNumOfParticles; }
     void SetKernelRadius(Float){}
-    template<typename G> void MapGrid(const G &){} // the engine owns the grid; nothing to map on the host
     int AddParticle(const vec3f &pos, const vec3f &vel = vec3f(0)){
         if(particleSet->set.GetParticleCount() + (int)positions.size() + 1 > maxNumOfParticles) return 0;
         positions.push_back(pos); velocities.push_back(vel); return 1;
@@ -288,6 +329,41 @@ struct ContinuousParticleSetBuilder3 {
         positions.clear(); velocities.clear();
     }
     int GetParticleCount() const { return particleSet->set.GetParticleCount(); }
+    // chains of the engine: counts per cell + concatenated ids
+    void Chains(const Grid3 &grid, std::vector<int> *count, std::vector<int> *order) const {
+        if(!particleSet->engine) throw Error(BBX_ERR_INVALID, "MapGrid / MapGridEmit need the solver's Setup() first");
+        count->assign((size_t)grid.desc.total, 0); order->assign((size_t)std::max(1, GetParticleCount()), 0);
+        Check(bbx_export_cells(particleSet->engine, count->data(), order->data()));
+    }
+    template<typename G> void MapGrid(const G &grid){ // G: Grid3 or a smart pointer to it
+        const Grid3 &gr = DerefGrid(grid);
+        std::vector<int> count, order; Chains(gr, &count, &order);
+        mappedPositions.clear(); mappedCells = gr.desc.total;
+        size_t at = 0;
+        for(int c = 0; c < gr.desc.total; c++){
+            if(count[(size_t)c] > 0){
+                std::vector<vec3f> &v = mappedPositions[(unsigned)c];
+                for(int j = 0; j < count[(size_t)c]; j++) v.push_back(particleSet->set.positions[(size_t)order[at + (size_t)j]]);
+            }
+            at += (size_t)count[(size_t)c];
+        }
+        mapped = &gr;
+    }
+    int MapGridEmit(const std::function<vec3f(const vec3f &)> &velocity, Float d = 0.02){
+        if((reemitions > 0 && reemitOnce) || !mapped) return 0;
+        std::vector<int> count, order; Chains(*mapped, &count, &order);
+        std::vector<vec3f> add = MapGridEmitCandidates(mappedPositions, mapped->desc.total, count.data(), order.data(), particleSet->set.positions.data(), d);
+        int added = 0;
+        for(const vec3f &p : add){ if(!AddParticle(p, velocity(p))) break; added++; }
+        if(added > 0) Commit();
+        reemitions++;
+        return added;
+    }
+  private:
+    const Grid3 *mapped = nullptr;
+    static const Grid3 &DerefGrid(const Grid3 &g){ return g; }
+    static const Grid3 &DerefGrid(const Grid3 *g){ return *g; }
+    static const Grid3 &DerefGrid(const std::shared_ptr<Grid3> &g){ return *g; }
 };
 inline std::shared_ptr<SphParticleSet3> SphParticleSet3FromContinuousBuilder(ContinuousParticleSetBuilder3 *b){ b->Commit(); return b->particleSet; }
 
@@ -338,16 +414,6 @@ struct VolumeParticleEmitterSet3 {
     void SetJitter(Float j){ for(auto *e : emitters) e->SetJitter(j); }
     template<typename Builder> void Emit(Builder *b){ for(auto *e : emitters) e->Emit(b); b->Commit(); }
 };
-
-// --------------------------------------------------------------------------------------------- grid
-struct Grid3 { bbx_grid_desc desc; Bounds3f GetBounds() const { return Bounds3f(vec3f(desc.min[0], desc.min[1], desc.min[2]), vec3f(desc.max[0], desc.max[1], desc.max[2])); }
-               int GetCellCount() const { return desc.total; } };
-inline std::shared_ptr<Grid3> UtilBuildGridForDomain(const Bounds3f &domain, Float spacing, Float spacingScale){
-    auto g = std::make_shared<Grid3>();
-    double lo[3] = {domain.pMin.x, domain.pMin.y, domain.pMin.z}, hi[3] = {domain.pMax.x, domain.pMax.y, domain.pMax.z};
-    Check(bbx_grid_for_domain(lo, hi, spacing, spacingScale, &g->desc));
-    return g;
-}
 
 // ------------------------------------------------------------------------------------------ solvers
 // SphSolverData3 constants (src/core/sph_solver.h:31-50); the arrays live in the engine

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <string>
 #include <vector>
 #include "bubbles_api.h"
@@ -52,8 +53,37 @@ static int emit_mode(int argc, char **argv){
     return 0;
 }
 
+// frame_tool --mapemit <in.bin> <out.bin>: the facade's MapGridEmit rule (MapGridEmitCandidates) as a pure function.
+//   in.bin: double d; int64 n, total, m; double pos[3n]; int32 cell_count[total]; int32 cell_order[n];
+//           then m mapped cells: int64 cell, int64 k, double tmpl[3k]
+//   out.bin: int64 count, double new_pos[3 count]
+static int mapemit_mode(const char *in, const char *out){
+    FILE *fp = std::fopen(in, "rb");
+    if(!fp) return 1;
+    double d = 0; int64_t n = 0, total = 0, m = 0;
+    size_t r = std::fread(&d, 8, 1, fp) + std::fread(&n, 8, 1, fp) + std::fread(&total, 8, 1, fp) + std::fread(&m, 8, 1, fp);
+    std::vector<bbx::vec3f> pos((size_t)n); std::vector<int> count((size_t)total), order((size_t)n);
+    r += std::fread(pos.data(), sizeof(bbx::vec3f), pos.size(), fp) + std::fread(count.data(), 4, count.size(), fp) + std::fread(order.data(), 4, order.size(), fp);
+    std::map<unsigned, std::vector<bbx::vec3f>> mapped;
+    for(int64_t c = 0; c < m; c++){
+        int64_t cell = 0, k = 0; r += std::fread(&cell, 8, 1, fp) + std::fread(&k, 8, 1, fp);
+        std::vector<bbx::vec3f> &v = mapped[(unsigned)cell]; v.resize((size_t)k);
+        r += std::fread(v.data(), sizeof(bbx::vec3f), v.size(), fp);
+    }
+    std::fclose(fp);
+    (void)r;
+    std::vector<bbx::vec3f> add = bbx::MapGridEmitCandidates(mapped, (int)total, count.data(), order.data(), pos.data(), d);
+    fp = std::fopen(out, "wb");
+    if(!fp) return 1;
+    int64_t cnt = (int64_t)add.size();
+    std::fwrite(&cnt, 8, 1, fp); std::fwrite(add.data(), sizeof(bbx::vec3f), add.size(), fp);
+    std::fclose(fp);
+    return 0;
+}
+
 int main(int argc, char **argv){
     if(argc == 4 && std::string(argv[1]) == "--load") return load_mode(argv[2], argv[3]);
+    if(argc == 4 && std::string(argv[1]) == "--mapemit") return mapemit_mode(argv[2], argv[3]);
     if(argc >= 2 && std::string(argv[1]) == "--emit") return emit_mode(argc, argv);
     if(argc < 4){ std::fprintf(stderr, "usage: frame_tool state.bin out.txt flags\n"); return 2; }
     FILE *fp = std::fopen(argv[1], "rb");

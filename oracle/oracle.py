@@ -220,6 +220,42 @@ class Oracle:
         for name, v in a.items():
             setattr(self.S, name, v.ctypes.data)
 
+    def map_grid(self):
+        """ContinuousParticleSetBuilder3::MapGrid (src/core/grid.h:1288-1321): remember, for every occupied cell, the
+        positions of its chain (in chain order) -- the emission template of map_grid_emit."""
+        cc, co = self.arr("cell_count"), self.arr("cell_order")
+        start = np.concatenate([[0], np.cumsum(cc)])
+        self.mapped = {int(c): self.a["pos"][co[start[c]:start[c + 1]]].copy() for c in np.nonzero(cc)[0]}
+
+    def map_grid_emit(self, velocity, d=0.02):
+        """ContinuousParticleSetBuilder3::MapGridEmit (src/core/grid.h:1367-1407): for every mapped cell (ascending id)
+        whose CURRENT chain has room (< 100), re-emit its first min(100 - size, len) template positions that have no
+        particle of the current chain within d; one Commit at the end.  Returns the number of particles added."""
+        cc, co = self.arr("cell_count"), self.arr("cell_order")
+        start = np.concatenate([[0], np.cumsum(cc)])
+        pos = self.a["pos"]
+        new = []
+        for c in sorted(self.mapped):
+            size = int(cc[c])
+            if size >= MAX_BUCKET:
+                continue
+            tmpl = self.mapped[c]
+            members = pos[co[start[c]:start[c + 1]]]
+            for i in range(min(MAX_BUCKET - size, len(tmpl))):
+                pi = tmpl[i]
+                ok = True
+                for pj in members:
+                    dx = pj - pi          # Distance(pj, pi) = sqrt(|pj - pi|^2) (geometry.h:632-633, 797-800)
+                    if np.sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]) < d:
+                        ok = False
+                        break
+                if ok:
+                    new.append(pi)
+        if new:
+            new = np.array(new)
+            self.append_particles(new, np.tile(np.asarray(velocity, dtype=np.float64), (len(new), 1)))
+        return len(new)
+
     def arr(self, name):
         """numpy view of a state array (follows the chain double-buffer swap)."""
         ptr = getattr(self.S, name)

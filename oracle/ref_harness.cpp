@@ -361,6 +361,16 @@ int main(int argc, char **argv){
             Float c; in >> c; if(!H.data){ fprintf(stderr, "pseudo: after setup\n"); return 2; } H.data->pseudoViscosity = c;
         }
         else if(cmd == "continuous"){ int maxp; in >> maxp; H.cbuilder = new ContinuousParticleSetBuilder3(maxp); }
+        else if(cmd == "map_emit"){
+            // ContinuousParticleSetBuilder3::MapGridEmit (src/core/grid.h:1367-1407): re-emit the particles of the cells
+            // mapped at setup wherever the cell has room and no particle closer than d; constant emission velocity
+            Float vx, vy, vz, d; in >> vx >> vy >> vz >> d;
+            if(!H.cbuilder){ fprintf(stderr, "map_emit needs `continuous <max>` before the particles\n"); return 2; }
+            int before = H.sphSet->GetParticleSet()->GetParticleCount();
+            H.cbuilder->MapGridEmit([&](const vec3f &) -> vec3f { return vec3f(vx, vy, vz); }, d);
+            printf("[bbref] map_emit added=%d total=%d\n", H.sphSet->GetParticleSet()->GetParticleCount() - before,
+                   H.sphSet->GetParticleSet()->GetParticleCount());
+        }
         else if(cmd == "append"){
             // ContinuousParticleSetBuilder3::AddParticle + Commit (src/core/grid.h:1409-1441): AppendData, then
             // DistributeByParticleList puts the new ids at the tail of their cells' chains

@@ -150,6 +150,28 @@ def append_run():
     print("append_run", len(sc["pos"]), "+", len(add_pos), "+", len(add_pos), "particles")
 
 
+def emit_run():
+    """Continuous re-emission (ContinuousParticleSetBuilder3::MapGrid at setup + MapGridEmit between steps,
+    src/core/grid.h:1288-1407): the probe block falls out of its initial cells, the mapped cells re-emit twice."""
+    sc = scenes.probe_scene()
+    wd = tempfile.mkdtemp(prefix="bbref_")
+    O.write_particles(os.path.join(wd, "p.bin"), sc["pos"], sc["vel"])
+    job = ["threads 4", "spacing 0.02", "scale 1.8", f"collider box {I} 0.6 0.6 0.6 1 0", "domain_from_collider 0",
+           "continuous 12000", f"particles {wd}/p.bin", "setup", "dump_grid {wd}/s0_", "step 7e-4 40", "dump {wd}/s40_", "dump_grid {wd}/s40_",
+           "map_emit 0 -1 0 0.02", "dump {wd}/e1_", "dump_grid {wd}/e1_", "step 7e-4 30", "map_emit 0 -1 0 0.02",
+           "dump {wd}/e2_", "dump_grid {wd}/e2_", "step 7e-4 10", "dump {wd}/end_", "dump_grid {wd}/end_"]
+    out, _ = O.run_ref(job, wd)
+    added = [int(x) for x in re.findall(r"map_emit added=(\d+)", out)]
+    data = dict(p_pos=sc["pos"].astype(np.float64), p_vel=sc["vel"].astype(np.float64), added=np.array(added))
+    for pre, names in (("s0_", ["cell_count", "cell_order"]), ("s40_", ["pos", "vel", "cell_count", "cell_order"]),
+                       ("e1_", ["pos", "vel", "cell_count", "cell_order"]), ("e2_", ["pos", "vel", "cell_count", "cell_order"]),
+                       ("end_", ["pos", "vel", "cell_order"])):
+        for k, v in load_all(wd, pre, names).items():
+            data[pre + k] = v
+    np.savez_compressed(os.path.join(HERE, "emit_run.npz"), **data)
+    print("emit_run", len(sc["pos"]), "particles, added", added)
+
+
 def pseudo_run():
     """Pseudo-viscosity smoothing switched on (coefficient 200: 200 * 7e-4 > 0.1; ComputePseudoViscosity*KernelFor,
     src/equations/sph_equations3.cpp:341-382, 469-483): probe scene, 25 sub-steps."""
@@ -217,6 +239,7 @@ if __name__ == "__main__":
     collider_vectors()
     obstacle_run()
     append_run()
+    emit_run()
     pseudo_run()
     sdf_run()
     grid_facts()

@@ -127,3 +127,44 @@ def test_facade_emitter_reproduces_the_reference_emitter_bit_for_bit(tmp_path):
     assert n == len(g["s0_pos"])
     assert np.array_equal(a[:3 * n].reshape(n, 3), g["s0_pos"])
     assert np.array_equal(a[3 * n:].reshape(n, 3), g["s0_vel"])
+
+
+def test_facade_map_grid_emit_rule_matches_the_reference(tmp_path):
+    """ContinuousParticleSetBuilder3::MapGridEmit of the facade (MapGridEmitCandidates: which template positions are
+    re-emitted) on the states the REFERENCE went through (tests/golden/emit_run.npz: chains and positions before each
+    of its two emissions) must pick exactly the particles the reference added, in its order.  CPU only."""
+    G.build()
+    tool = os.path.join(ROOT, "bubbles_b200", "lib", "frame_tool")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "emit_run.npz"))
+    n0 = len(g["p_pos"])
+    cc0, co0 = g["s0_cell_count"], g["s0_cell_order"]
+    start0 = np.concatenate([[0], np.cumsum(cc0)])
+    mapped = {int(c): g["p_pos"][co0[start0[c]:start0[c + 1]]] for c in np.nonzero(cc0)[0]}   # MapGrid right after setup
+
+    def run(pos, cc, co):
+        with open(tmp_path / "in.bin", "wb") as f:
+            f.write(np.float64(0.02).tobytes())
+            f.write(np.array([len(pos), len(cc), len(mapped)], dtype=np.int64).tobytes())
+            f.write(np.ascontiguousarray(pos, np.float64).tobytes())
+            f.write(np.ascontiguousarray(cc, np.int32).tobytes())
+            f.write(np.ascontiguousarray(co, np.int32).tobytes())
+            for c in sorted(mapped):
+                f.write(np.array([c, len(mapped[c])], dtype=np.int64).tobytes())
+                f.write(np.ascontiguousarray(mapped[c], np.float64).tobytes())
+        r = subprocess.run([tool, "--mapemit", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        raw = open(tmp_path / "out.bin", "rb").read()
+        k = int(np.frombuffer(raw[:8], dtype=np.int64)[0])
+        return np.frombuffer(raw[8:], dtype=np.float64).reshape(k, 3)
+
+    add1 = run(g["s40_pos"], g["s40_cell_count"], g["s40_cell_order"])
+    assert len(add1) == int(g["added"][0]) and np.array_equal(add1, g["e1_pos"][n0:])
+    # second emission: the state right before it is not in the golden, but the oracle (pinned on this very run) is
+    from oracle import oracle as O
+    orc = O.Oracle(0.02, 1.8, (-0.3, -0.3, -0.3), (0.3, 0.3, 0.3), [O.make_collider("box", size=(0.6, 0.6, 0.6), reverse=True)])
+    orc.set_particles(g["e1_pos"], g["e1_vel"])
+    orc.set_chains(g["e1_cell_count"], g["e1_cell_order"])
+    for _ in range(30):
+        orc.substep_pcisph(7e-4)
+    add2 = run(orc.a["pos"], orc.arr("cell_count"), orc.arr("cell_order"))
+    assert len(add2) == int(g["added"][1]) and np.array_equal(add2, g["e2_pos"][len(g["e1_pos"]):])
