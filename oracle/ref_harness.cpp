@@ -490,6 +490,16 @@ int main(int argc, char **argv){
             WriteNpy<double>(prefix + "mass.npy", mass.data(), n, 0);
             printf("[bbref] load_frame count=%d flags=%d\n", n, flags);
         }
+        else if(cmd == "collider_velocity"){
+            // Shape::SetVelocities (src/core/shape.cpp:290-298): rigid motion of collider idx (only the sphere's closest-point
+            // query carries VelocityAt into the response)
+            int idx; vec3f v, w; in >> idx >> v.x >> v.y >> v.z >> w.x >> w.y >> w.z;
+            H.shapes[idx]->SetVelocities(v, w);
+        }
+        else if(cmd == "collider_active"){
+            // ColliderSet3::SetActive (src/core/collider.cpp:232-236), after setup
+            int idx, on; in >> idx >> on; H.colliders->SetActive(idx, on != 0);
+        }
         else if(cmd == "sdf_nodes"){
             // report the node layout of SDF collider idx so the test can sample its analytic SDF there
             int idx; in >> idx; FieldGrid3f *g = H.shapes[idx]->grid;

@@ -96,6 +96,19 @@ def collider_vectors():
             for k in ("pos", "vel", "hit"):
                 data[f"{name}_{tag}_{k}"] = np.load(os.path.join(wd, f"{name}_{tag}_{k}.npy"))
         print(name, "hits", int(data[f"{name}_a_hit"].sum()), int(data[f"{name}_b_hit"].sum()))
+    # a moving, spinning sphere obstacle (Shape::SetVelocities -> VelocityAt in the response) and a collider switched off
+    wd = tempfile.mkdtemp(prefix="bbref_")
+    O.write_particles(os.path.join(wd, "q.bin"), pos, vel)
+    job = ["threads 1", "spacing 0.02", "scale 1.8", f"collider box {I} 0.7 0.7 0.7 1 0",
+           f"collider sphere {T(-0.1, 0.1, 0.1)} 0.12 0 0.5", f"collider box {T(0.1, -0.2, 0.0)} 0.2 0.1 0.3 0 0.25",
+           "domain -0.4 -0.4 -0.4 0.4 0.4 0.4", f"particles {wd}/q.bin", "setup",
+           "collider_velocity 1 0.5 -0.25 1.5 0 3 -2", f"collide {wd}/q.bin 0.02 0.6 {wd}/mv_",
+           "collider_active 2 0", f"collide {wd}/q.bin 0.02 0.6 {wd}/off_"]
+    O.run_ref(job, wd)
+    for tag in ("mv", "off"):
+        for k in ("pos", "vel", "hit"):
+            data[f"moving_{tag}_{k}"] = np.load(os.path.join(wd, f"{tag}_{k}.npy"))
+    print("moving sphere hits", int(data["moving_mv_hit"].sum()), "with the box off", int(data["moving_off_hit"].sum()))
     np.savez_compressed(os.path.join(HERE, "collider_vectors.npz"), **data)
 
 
