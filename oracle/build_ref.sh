@@ -30,6 +30,12 @@ compile_one() {
 }
 export -f compile_one; export REF OBJ NVCC FLAGS
 echo "$SRCS" | xargs -P "$JOBS" -I{} bash -c 'compile_one {}'
+# nothing to do when both binaries are newer than the harness source and every reference object
+NEWEST_OBJ=$(ls -t "$OBJ"/*.o 2>/dev/null | grep -v "/_harness.o" | head -1 || true)
+if [ -x "$OUT/bbref" ] && [ -x "$OUT/bbref_gpu" ] && [ "$OUT/bbref" -nt "$HERE/ref_harness.cpp" ] && [ "$OUT/bbref_gpu" -nt "$HERE/ref_harness.cpp" ] \
+   && [ -n "$NEWEST_OBJ" ] && [ "$OUT/bbref" -nt "$NEWEST_OBJ" ] && [ "$OUT/bbref_gpu" -nt "$NEWEST_OBJ" ] && [ "$OUT/bbref" -nt "$HERE/build_ref.sh" ]; then
+  echo "[build_ref] up to date: $OUT/bbref, $OUT/bbref_gpu"; exit 0
+fi
 # harness (ours) + malloc shim for the managed-memory arena
 $NVCC $FLAGS -c "$HERE/ref_harness.cpp" -o "$OBJ/_harness.o"
 $NVCC --gpu-architecture=sm_100 -o "$OUT/bbref" "$OBJ"/*.o -ldl -lpthread
