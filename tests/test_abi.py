@@ -67,3 +67,18 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+
+
+def test_python_emitter_glibc_mode_reproduces_the_reference_emitter():
+    """bubbles_b200.emitter.VolumeParticleEmitter3(rng="glibc") against the particles the reference's emitter produced
+    (tests/golden/probe_trace.npz: emit_box at (0.1, -0.1, 0.1), 0.2 x 0.3 x 0.2, jitter 0.001, srand(1))."""
+    import numpy as np
+    from bubbles_b200 import emitter
+    g = np.load(os.path.join(ROOT, "tests", "golden", "probe_trace.npz"))
+    c, size = np.array([0.1, -0.1, 0.1]), np.array([0.2, 0.3, 0.2])
+    b = emitter.ParticleSetBuilder3()
+    em = emitter.VolumeParticleEmitter3(emitter.box_inside_reference(c, size), c - size / 2, c + size / 2, 0.02, (0, -1, 0),
+                                        jitter=0.001, seed=1, rng="glibc")
+    em.Emit(b)
+    assert b.GetParticleCount() == len(g["s0_pos"])
+    assert np.array_equal(b.positions, g["s0_pos"]) and np.array_equal(b.velocities, g["s0_vel"])
