@@ -131,6 +131,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+def workload_label(solver, workload, n_global, n, cells, world):
+    """config["workload"]: one string for the bbx arm and the reference arm (same scene -> same label)."""
+    return (("PCISPH 3D dam break + baked-SDF torus collider (BASELINE configs[2] stand-in), " if workload == "sdf" else "") +
+            f"{'PCISPH' if solver == 'pcisph' else 'SPH'} 3D dam break, {n_global} particles = {n} per GPU (BASELINE configs[{'1' if solver == 'pcisph' else '0'}] per GPU), spacing 0.02, h = 1.8 s, " +
+            (f"{cells} cells, fixed dt 7.2e-4, reference-compat (1 predict-correct iteration)" if solver == "pcisph" else
+             f"{cells} cells, SphSolver3 step (BASELINE configs[0]), fixed dt 1.44e-4") +
+            (f", {world} z-slabs with ghost-plane exchange and migration over NVLink" if world > 1 else ""))
+
+
 def make_scene(n_target):
     import scenes
     return scenes.dam_break_scene(n_target=n_target, jitter=0.0)
@@ -164,7 +173,7 @@ def run_reference(args, rank):
     n = len(sc["pos"])
     steps, warm = max(1, args.steps), max(0, args.warmup)
     # keep the whole run within a few minutes whatever K the driver asks for
-    est = n / 2.0e4 / max(1, min(cores, 8))  # s per sub-step, conservative
+    est = n / 1.0e5 / max(1, min(cores, 16))  # s per sub-step, conservative (measured: 3.2e6 updates/s on 16 cores)
     if est * (steps + warm) > 240:
         steps = max(1, int(240 / est) - warm)
     half = sc["domain_max"]
@@ -193,11 +202,15 @@ def run_reference(args, rank):
             orc.substep_pcisph(sc["dt"])
         sec = time.perf_counter() - t0
         value = n * steps / sec
-    sample = f"{n}-particle dam break (same constants as the GPU workload), {steps} sub-steps after {warm} warm-up, FP64"
+    sample = f"{n}-particle dam break (the bench workload's scene and constants), {steps} sub-steps after {warm} warm-up, FP64, {cores} host threads"
+    cells = int(__import__("scenes").make_oracle(sc).grid["total"])
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"PCISPH 3D dam break, bounded CPU sample of {n} particles, dt 7.2e-4, reference CPU path"},
+            # N = 1: the very scene the bbx arm steps (same label); N > 1: the 1-GPU scene as the bounded sample of the N-GPU workload
+            "config": {"workload": workload_label("pcisph", "dam", n, n, cells, 1), "particles_per_gpu": n, "particles": n, "cells": cells, "dt": sc["dt"],
+                       "parallelism": "single",
+                       "arm": "unmodified reference, CPU path (AdvanceTimeStep(PciSphSolver3*, dt, use_cpu = 1)), all host threads; the GPU is only touched by the reference's own setup code"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -263,19 +276,279 @@ def reference_gpu(n_particles):
         return {"value": None, "unit": UNIT, "sample": f"failed: {str(ex)[-300:]}"}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU cores next to its GPU BEFORE the pinned host buffers are allocated (first touch puts
+    them on that NUMA node): with 8 ranks on one box the host copies otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = [x for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip().isdigit()]
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(vis[index]) if index < len(vis) else index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False
+
+
+class Job:
+    """One engine (single domain or one z-slab of an NCCL group) on this rank's GPU, holding a synthetic scene."""
+
+    def __init__(self, particles_total, workload, rank, world, local_rank):
+        import bubbles_b200 as bb
+        import scenes
+        self.bb, self.rank, self.world = bb, rank, world
+        # weak scaling: ONE dam-break scene of (particles per GPU) x N particles, cut into N z-slabs of whole cell planes
+        # balanced by particle count; ghost planes / migration / per-phase halos travel over NVLink.  Every rank
+        # generates only its own share of the (deterministic) BCC block.
+        sc = scenes.dam_break_scene_slab(particles_total, rank, world, obstacle=scenes.torus_obstacle if workload == "sdf" else None)
+        self.sc, self.n_global, self.dt = sc, sc["n_global"], sc["dt"]
+        if world > 1:
+            cap, gcap = bb.slab_capacity(sc["hist"], sc["z_bounds"], rank, slack=2.0)
+            self.slab = bb.NcclSlab(sc["grid"], sc["spacing"], sc["scale"], sc["z_bounds"], rank, world, broadcast_bytes, cap, gcap, device=local_rank)
+            self.eng = self.slab.engine
+            self.eng.set_colliders(scenes.engine_colliders(sc))
+            self.eng.set_particles_ids(sc["pos"], sc["vel"], sc["ids"])
+        else:
+            self.eng = scenes.make_engine(sc, device=local_rank)
+            self.eng.set_particles(sc["pos"], sc["vel"])
+        self.n = self.n_global // world  # nominal particles per GPU (the slabs hold about this many each)
+        self.cells = sc["grid"].total // world
+
+    def reset(self):
+        if self.world > 1:
+            self.eng.set_particles_ids(self.sc["pos"], self.sc["vel"], self.sc["ids"])
+        else:
+            self.eng.set_particles(self.sc["pos"], self.sc["vel"])
+
+    def close(self):
+        if self.eng is not None:
+            self.eng.close()
+            self.eng = None
+
+
+def rank_max(values, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(values, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed_blocks(job, solver, dt, steps, repeats, local_rank):
+    """`repeats` back-to-back blocks of exactly `steps` sub-steps, each bracketed by two CUDA events on the engine's stream
+    (bbx_step_many_timed) and a barrier + synchronize on both sides; per block the max over ranks.  Returns the per-block
+    ms per sub-step, the wall-clock ms per sub-step of the median block, the launches per block and the clock record
+    sampled DURING the blocks."""
+    eng, world = job.eng, job.world
+    sampler = ClockSampler(local_rank)
+    barrier(world)
+    sampler.start()
+    blocks, walls = [], []
+    l0 = eng.launches
+    for _ in range(repeats):
+        barrier(world)
+        t0 = time.perf_counter()
+        ms = eng.step_many_timed(dt, steps, solver)
+        barrier(world)
+        wall = (time.perf_counter() - t0) * 1e3
+        ms, wall = rank_max([ms, wall], world)
+        blocks.append(ms / steps)
+        walls.append(wall / steps)
+    clocks = sampler.stop()
+    launches = (eng.launches - l0) // repeats
+    order = sorted(range(repeats), key=lambda k: blocks[k])
+    med = order[repeats // 2]
+    return blocks, blocks[med], walls[med], launches, clocks
+
+
+def phase_breakdown(job, solver, dt, steps, phase_ids):
+    """Per-phase device time of `steps` further sub-steps (events between the kernels on the engine's stream)."""
+    eng = job.eng
+    eng.set_timing(True)
+    eng.reset_kernel_time()
+    eng.step_many(dt, steps, solver)
+    eng.synchronize()
+    phase = {name: eng.kernel_time(pid) for name, pid in phase_ids.items()}
+    gap_ms, _ = eng.kernel_time(7)  # device idle time between sub-steps (launch gaps)
+    eng.set_timing(False)
+    return phase, gap_ms
+
+
+def parity_leg(job, dt):
+    """The parity gate on the state the timed region left behind (tests/parity_gate.py: the oracle as CHECKER, after the
+    clock has stopped): one traced sub-step from identical inputs, cell order and neighbour lists bit-exact, fields
+    within the FP32-vs-FP64 tolerances.  N > 1: every rank ships its owned rows (ids, FP32 state, cell order, one 64-bit
+    checksum per neighbour-list row) to rank 0, which runs the oracle on the whole scene."""
+    import numpy as np
+    import torch.distributed as dist
+    import parity_gate as pg
+    import scenes
+    bb, eng, world, rank, sc = job.bb, job.eng, job.world, job.rank, job.sc
+    t0 = time.perf_counter()
+    ext = float(np.max(np.asarray(sc["domain_max"]) - np.asarray(sc["domain_min"])))
+    if world == 1:
+        orc = scenes.make_oracle(sc)
+        orc.set_particles(sc["pos"].astype(np.float64), sc["vel"].astype(np.float64))
+        substep = eng.stats().substeps
+        pg.sync_oracle_from_engine(eng, orc)
+        r, _ = pg.gate_substep(eng, orc, dt, ext)
+        r.update(substep=int(substep), particles=int(eng.n), oracle="oracle/bbx_oracle.c (FP64, pinned bit-exact to the unmodified reference)",
+                 seconds=time.perf_counter() - t0, tolerances=pg.TOL)
+        return r
+    # ---- slabs: gather the inputs, trace on rank 0, compare what every rank computed
+    ids, pos = eng.download_owned(bb.POSITION, np.float32)
+    _, vel = eng.download_owned(bb.VELOCITY, np.float32)
+    cc, co = eng.export_cells()
+    st = eng.stats()
+    inputs = [None] * world
+    dist.gather_object((ids, pos, vel, np.nonzero(cc)[0].astype(np.int32), cc[cc > 0], co, int(st.rebuild_flag), int(st.substeps)), inputs if rank == 0 else None, dst=0)
+    eng.run_phase(bb.PHASE_GRID, dt)
+    eng.run_phase(bb.PHASE_DENSITY, dt)
+    ids2, rho = eng.download_owned(bb.DENSITY, np.float32)
+    cnt, rows = eng.export_neighbors_owned()
+    sums = pg.row_checksums(rows)
+    del rows
+    cc2, co2 = eng.export_cells()
+    outputs = [None] * world
+    dist.gather_object((ids2, rho, cnt, sums, np.nonzero(cc2)[0].astype(np.int32), cc2[cc2 > 0], co2, int(eng.stats().exact_passes)), outputs if rank == 0 else None, dst=0)
+    if rank != 0:
+        return None
+    n, total = job.n_global, sc["grid"].total
+    p64, v64 = np.zeros((n, 3)), np.zeros((n, 3))
+    cell_count, order, flag = np.zeros(total, dtype=np.int32), [], 0
+    for i_, p_, v_, ci, cv, o_, f_, sub in inputs:
+        p64[i_] = p_; v64[i_] = v_
+        cell_count[ci] = cv; order.append(o_); flag |= f_
+    orc = scenes.make_oracle(sc)
+    orc.set_particles(p64, v64)
+    orc.set_chains(cell_count, np.concatenate(order))  # slabs own ascending, disjoint cell ranges: global order = concatenation
+    orc.S.rebuild_flag = flag
+    tr = orc.trace_pcisph(dt)
+    rho_e, cnt_e, sum_e = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.uint64)
+    cc_e, order_e, exact = np.zeros(total, dtype=np.int32), [], 0
+    owned = np.zeros(n, dtype=np.int32)
+    for i_, r_, c_, s_, ci, cv, o_, x_ in outputs:
+        rho_e[i_] = r_; cnt_e[i_] = c_; sum_e[i_] = s_; owned[i_] += 1
+        cc_e[ci] = cv; order_e.append(o_); exact += x_
+    r = {"substep": int(inputs[0][7]), "particles": int(n), "ranks": world,
+         "every_particle_owned_once": bool((owned == 1).all()),
+         "cell_counts_bit_exact": bool(np.array_equal(cc_e, tr["cell_count"])),
+         "cell_order_bit_exact": bool(np.array_equal(np.concatenate(order_e), tr["cell_order"])),
+         "neighbor_counts_bit_exact": bool(np.array_equal(cnt_e, tr["nbr_count"])),
+         "neighbor_lists_bit_exact": bool(np.array_equal(sum_e, pg.row_checksums(tr["nbr_ids"]))),
+         "neighbor_lists_compared_as": "64-bit order-sensitive checksum per list row (rows gathered from the ranks)",
+         "err_density": float(np.abs(rho_e.astype(np.float64) - tr["density"]).max() / pg.RHO0), "exact_passes": int(exact),
+         "oracle": "oracle/bbx_oracle.c on the whole scene, rank 0", "seconds": time.perf_counter() - t0, "tolerances": {"rho": pg.TOL["rho"]}}
+    r["lists_bit_exact"] = bool(r["every_particle_owned_once"] and r["cell_counts_bit_exact"] and r["cell_order_bit_exact"]
+                                and r["neighbor_counts_bit_exact"] and r["neighbor_lists_bit_exact"])
+    r["fields_within_tolerance"] = bool(r["err_density"] < pg.TOL["rho"])
+    r["ok"] = bool(r["lists_bit_exact"] and r["fields_within_tolerance"])
+    return r
+
+
+def e2e_leg(job, solver, dt, steps, sph):
+    """The same sub-step through the C ABI with HOST buffers: every step uploads positions + velocities from pinned host
+    memory, steps, and reads positions + velocities (+ ids on slabs) back into pinned host memory."""
+    import torch
+    bb, eng, world, sc = job.bb, job.eng, job.world, job.sc
+    lib = eng.lib
+    pos32, vel32 = sc["pos"], sc["vel"]
+    hcap = max(len(pos32), int(eng.cfg.max_particles))  # slabs gain particles through migration
+    buf = {k: torch.zeros((hcap, 3), dtype=torch.float32).pin_memory() for k in ("ip", "iv", "op", "ov")}
+    hid = torch.zeros(hcap, dtype=torch.int32).pin_memory()
+    cnt = C.c_int()
+    h2d, d2h = [0], [0]
+    job.reset()  # restart from the initial block so that the e2e run simulates the same thing
+    if world == 1:
+        buf["ip"][:len(pos32)] = torch.from_numpy(pos32); buf["iv"][:len(vel32)] = torch.from_numpy(vel32)
+        cnt.value = len(pos32)
+    else:
+        rc = lib.bbx_download_state(eng.h, buf["ip"].data_ptr(), buf["iv"].data_ptr(), hid.data_ptr(), bb.F32, 1, C.byref(cnt))
+        if rc:
+            raise SystemExit("bbx error: " + lib.bbx_last_error().decode())
+
+    def step():
+        m = cnt.value
+        if world == 1:
+            rc = lib.bbx_overwrite_state(eng.h, buf["ip"].data_ptr(), buf["iv"].data_ptr(), bb.F32)
+            rc = rc or (lib.bbx_step_sph if sph else lib.bbx_step_pcisph)(eng.h, dt)
+            rc = rc or lib.bbx_download_state(eng.h, buf["op"].data_ptr(), buf["ov"].data_ptr(), None, bb.F32, 0, C.byref(cnt))
+            h2d[0] = 24 * m; d2h[0] = 24 * m
+        else:
+            # slab engines: every rank hands over the particles it holds (rows in the engine's cell order, the order of the
+            # previous download), steps, and reads its owned particles back with their global ids
+            rc = lib.bbx_overwrite_owned(eng.h, buf["ip"].data_ptr(), buf["iv"].data_ptr(), bb.F32)
+            rc = rc or lib.bbx_step_pcisph(eng.h, dt)
+            rc = rc or lib.bbx_download_state(eng.h, buf["op"].data_ptr(), buf["ov"].data_ptr(), hid.data_ptr(), bb.F32, 1, C.byref(cnt))
+            h2d[0] = 24 * m; d2h[0] = 28 * cnt.value
+        if rc:
+            raise SystemExit("bbx error: " + lib.bbx_last_error().decode())
+        buf["ip"], buf["op"] = buf["op"], buf["ip"]  # next step's input is this step's output
+        buf["iv"], buf["ov"] = buf["ov"], buf["iv"]
+
+    for _ in range(3):
+        step()
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    barrier(world)
+    sec = rank_max([(time.perf_counter() - t0) / steps], world)[0]
+    tot = rank_max([float(h2d[0]), float(d2h[0])], 1)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor(tot, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tot = [float(x) for x in t]
+    return {"value": job.n_global / sec, "unit": UNIT, "h2d_bytes_per_step": int(tot[0]), "d2h_bytes_per_step": int(tot[1]),
+            "ms_per_step": sec * 1e3,
+            "api": ("bbx_overwrite_state + bbx_step_pcisph + bbx_download_state(positions, velocities), pinned host buffers" if world == 1 else
+                    "per rank: bbx_overwrite_owned(host) + bbx_step_pcisph + bbx_download_state(positions, velocities, ids), pinned host buffers"),
+            "steps": steps}
+
+
+def extra_config(name, particles_total, workload, rank, world, local_rank, steps, warmup, peak):
+    """One more BASELINE config on the same GPUs: ms per sub-step, updates/s, whole-step roofline fraction, clocks."""
+    job = Job(particles_total, workload, rank, world, local_rank)
+    try:
+        job.eng.step_many(job.dt, warmup, job.bb.SOLVER_PCISPH)
+        job.eng.synchronize()
+        blocks, ms, wall, launches, clocks = timed_blocks(job, job.bb.SOLVER_PCISPH, job.dt, steps, 3, local_rank)
+        st = job.eng.stats()
+        gbs = (BYTES_PER_UPDATE * job.n + 8 * job.cells) / (ms * 1e-3) / 1e9
+        return {"workload": name, "particles": job.n_global, "n_gpus": world, "ms_per_step": ms, "ms_per_step_blocks": blocks, "steps": steps, "warmup": warmup,
+                "value": job.n_global / (ms * 1e-3), "unit": UNIT, "whole_step_frac": gbs / peak, "whole_step_gbs_per_gpu": gbs,
+                "wall_ms_per_step": wall, "clocks": clocks, "nan_count": int(st.nan_count), "halo_p2p": bool(job.eng.p2p) if world > 1 else None}
+    finally:
+        job.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--repeats", type=int, default=5, help="timed blocks of --steps sub-steps; the median block is reported (BASELINE.md 3)")
     ap.add_argument("--impl", default="bbx", choices=["bbx", "reference"])
     ap.add_argument("--particles", type=float, default=1.0e6, help="particles per GPU (weak scaling)")
     ap.add_argument("--workload", default="dam", choices=["dam", "sdf"],
                     help="dam: PCISPH dam break in a box (configs 2, 4, 5); sdf: same plus a baked-SDF torus collider (config 3)")
     ap.add_argument("--solver", default="pcisph", choices=["pcisph", "sph"],
                     help="sph: the SphSolver3 step (BASELINE configs[0]; fixed dt 1.44e-4 = 0.4 h / c_s), single GPU line for the record")
-    ap.add_argument("--ref-particles", type=float, default=2.5e5)
+    ap.add_argument("--ref-particles", type=float, default=1.0e6, help="reference arm: particles of its dam-break scene (default: the bench workload itself)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the additional BASELINE configs (8 M SDF at N = 1, 32 M at N = 2 / 4, 100 M at N = 8)")
+    ap.add_argument("--developed-substeps", type=int, default=400, help="second timing after this many sub-steps (splash developed); 0 = skip")
     ap.add_argument("--e2e-steps", type=int, default=10)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -286,199 +559,129 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     import bubbles_b200 as bb
-    import scenes
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: bubbles_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # weak scaling: ONE dam-break scene of (particles per GPU) x N particles, cut into N z-slabs of whole cell
-    # planes balanced by particle count; ghost planes / migration / per-phase halos travel over NCCL.  Every rank
-    # generates only its own share of the (deterministic) BCC block.
-    sc = scenes.dam_break_scene_slab(args.particles * world, rank, world,
-                                     obstacle=scenes.torus_obstacle if args.workload == "sdf" else None)
-    n_global = sc["n_global"]
-    pos32, vel32 = sc["pos"], sc["vel"]
-    if world > 1:
-        grid, zb, hist = sc["grid"], sc["z_bounds"], sc["hist"]
-        cap, gcap = bb.slab_capacity(hist, zb, rank, slack=2.0)
-        slab = bb.NcclSlab(grid, sc["spacing"], sc["scale"], zb, rank, world, broadcast_bytes, cap, gcap, device=local_rank)
-        eng = slab.engine
-        eng.set_colliders(scenes.engine_colliders(sc))
-        eng.set_particles_ids(pos32, vel32, sc["ids"])
-    else:
-        eng = scenes.make_engine(sc, device=local_rank)
-        eng.set_particles(pos32, vel32)
-    n = n_global // world  # nominal particles per GPU (the slabs hold about this many each)
-    dt = sc["dt"]
+    job = Job(args.particles * world, args.workload, rank, world, local_rank)
+    eng, n, n_global, cells = job.eng, job.n, job.n_global, job.cells
+    dt = job.dt
     phase_ids, phase_bytes, bytes_per_update, solver = PHASE_IDS, PHASE_BYTES, BYTES_PER_UPDATE, bb.SOLVER_PCISPH
     if args.solver == "sph":
         phase_ids, phase_bytes, bytes_per_update, solver, dt = SPH_PHASE_IDS, SPH_PHASE_BYTES, SPH_BYTES_PER_UPDATE, bb.SOLVER_SPH, 1.44e-4
     state_bytes = n * (16 * 8 + 4 * 8 + 208)  # float4 arrays, scalars/indices, neighbour list
+    peak, peak_src = peaks()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident throughput -------------------------------------------------------------
+    # ---- device-resident throughput: W warm-up sub-steps, then `repeats` blocks of exactly K sub-steps -------------
     eng.step_many(dt, args.warmup, solver)
     eng.synchronize()
-    eng.set_timing(True)
-    eng.reset_kernel_time()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    l0 = eng.launches
-    t0 = time.perf_counter()
-    # CUDA events bracket the K sub-steps on the engine's own stream (bbx_advance-style timing is done
-    # inside the library: per-phase events are recorded between the kernels, no sync until the end)
-    eng.step_many(dt, args.steps, solver)
-    eng.synchronize()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
-    launches = eng.launches - l0
-    phase = {}
-    for name, pid in phase_ids.items():
-        ms, k = eng.kernel_time(pid)
-        phase[name] = (ms, k)
-    gap_ms, _ = eng.kernel_time(7)  # device idle time between sub-steps (launch gaps), part of the step time
-    ms_total = sum(v[0] for v in phase.values()) + gap_ms
-    ms_per_step = ms_total / args.steps
-    eng.set_timing(False)
+    blocks, ms_per_step, wall_ms, launches, clocks = timed_blocks(job, solver, dt, args.steps, args.repeats, local_rank)
+    value = n_global / (ms_per_step * 1e-3)
+    phase, gap_ms = phase_breakdown(job, solver, dt, args.steps, phase_ids)
     st = eng.stats()
     if st.nan_count:
         raise SystemExit("non-finite positions during the timed region")
-    t = torch.tensor([ms_per_step, wall * 1e3 / args.steps], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step, wall_ms = float(t[0]), float(t[1])
-    value = n_global / (ms_per_step * 1e-3)
+    stats = {"neighbor_overflow": st.neighbor_overflow, "clamped": st.clamped, "rebuild_flag": st.rebuild_flag, "occupied_cells": st.occupied_cells,
+             "max_candidates": st.max_candidates, "exact_passes": st.exact_passes, "unstaged_tiles": st.unstaged_tiles, "substeps": st.substeps}
 
-    # ---- end to end through the C ABI with host buffers ------------------------------------------
-    hcap0 = max(len(pos32), int(eng.cfg.max_particles))
-    hp = torch.zeros((hcap0, 3), dtype=torch.float32).pin_memory(); hp[:len(pos32)] = torch.from_numpy(pos32)
-    hv = torch.zeros((hcap0, 3), dtype=torch.float32).pin_memory(); hv[:len(vel32)] = torch.from_numpy(vel32)
-    op = torch.empty_like(hp).pin_memory()
-    ov = torch.empty_like(hv).pin_memory()
-    buf = {"ip": hp, "iv": hv, "op": op, "ov": ov}  # pinned input / output buffers, swapped after every step
-    lib = eng.lib
+    # ---- parity gate on the benched state (after the clock has stopped) ---------------------------------------------
+    parity = None
+    if not args.no_parity and args.solver == "pcisph":
+        parity = parity_leg(job, dt)
 
-    hcap = max(len(pos32), int(eng.cfg.max_particles))  # slabs gain particles through migration
-    hid = torch.zeros(hcap, dtype=torch.int32).pin_memory()
-    cnt = C.c_int()
-    h2d = [0]
-    d2h = [0]
+    # ---- the same measurement on a developed flow (splash, spray, compressed cells) ---------------------------------
+    developed = None
+    if args.developed_substeps > 0 and args.solver == "pcisph":
+        todo = args.developed_substeps - eng.stats().substeps
+        if todo > 0:
+            eng.step_many(dt, todo, solver)
+            eng.synchronize()
+        dblocks, dms, dwall, _, dclocks = timed_blocks(job, solver, dt, args.steps, 3, local_rank)
+        dphase, dgap = phase_breakdown(job, solver, dt, args.steps, phase_ids)
+        dst = eng.stats()
+        developed = {"after_substeps": int(args.developed_substeps), "ms_per_step": dms, "ms_per_step_blocks": dblocks, "value": n_global / (dms * 1e-3),
+                     "phases_ms_per_step": {k: v[0] / args.steps for k, v in dphase.items()}, "clocks": dclocks,
+                     "stats": {"exact_passes": dst.exact_passes, "unstaged_tiles": dst.unstaged_tiles, "max_candidates": dst.max_candidates,
+                               "occupied_cells": dst.occupied_cells, "clamped": dst.clamped, "nan_count": dst.nan_count}}
+        if not args.no_parity:
+            developed["parity"] = parity_leg(job, dt)
 
-    def e2e_step():
-        if world == 1:
-            rc = lib.bbx_overwrite_state(eng.h, buf["ip"].data_ptr(), buf["iv"].data_ptr(), bb.F32)
-            rc |= (lib.bbx_step_sph if args.solver == "sph" else lib.bbx_step_pcisph)(eng.h, dt)
-            rc |= lib.bbx_download(eng.h, bb.POSITION, buf["op"].data_ptr(), bb.F32)
-            rc |= lib.bbx_download(eng.h, bb.VELOCITY, buf["ov"].data_ptr(), bb.F32)
-            m = len(pos32)
-            h2d[0] = 24 * m; d2h[0] = 24 * m
-        else:
-            # slab engines: every rank hands over the particles it holds (host buffers, global ids), steps, and
-            # reads its owned particles back with their ids -- the per-rank share of what a host run loop does
-            # (rows travel in the engine's cell order, the order of the previous download)
-            m = cnt.value
-            rc = lib.bbx_overwrite_owned(eng.h, buf["ip"].data_ptr(), buf["iv"].data_ptr(), bb.F32)
-            rc |= lib.bbx_step_pcisph(eng.h, dt)
-            rc |= lib.bbx_download_owned(eng.h, bb.POSITION, buf["op"].data_ptr(), bb.F32, hid.data_ptr(), C.byref(cnt))
-            rc |= lib.bbx_download_owned(eng.h, bb.VELOCITY, buf["ov"].data_ptr(), bb.F32, None, None)
-            h2d[0] = 24 * m; d2h[0] = 28 * m  # ids come back with the positions
-        if rc:
-            raise SystemExit("bbx error: " + lib.bbx_last_error().decode())
-        # next step's input is this step's output: swap the pinned host buffers
-        buf["ip"], buf["op"] = buf["op"], buf["ip"]
-        buf["iv"], buf["ov"] = buf["ov"], buf["iv"]
+    # ---- end to end through the C ABI with host buffers ------------------------------------------------------------
+    e2e = e2e_leg(job, solver, dt, args.e2e_steps, args.solver == "sph")
+    p2p = bool(eng.p2p) if world > 1 else None
+    job.close()
 
-    # restart from the initial block so that the e2e run simulates the same thing
-    if world == 1:
-        hp[:len(pos32)] = torch.from_numpy(pos32); hv[:len(vel32)] = torch.from_numpy(vel32)
-        eng.set_particles(pos32, vel32)
-    else:
-        eng.set_particles_ids(pos32, vel32, sc["ids"])
-        rc = lib.bbx_download_owned(eng.h, bb.POSITION, hp.data_ptr(), bb.F32, hid.data_ptr(), C.byref(cnt))
-        rc |= lib.bbx_download_owned(eng.h, bb.VELOCITY, hv.data_ptr(), bb.F32, None, None)
-        if rc:
-            raise SystemExit("bbx error: " + lib.bbx_last_error().decode())
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n_global / float(t[0])
+    # ---- the other BASELINE configs this GPU count can hold ----------------------------------------------------------
+    configs = {}
+    if not args.no_extra_configs and args.solver == "pcisph" and args.workload == "dam" and args.particles == 1.0e6:
+        extra = {1: [("sdf8m", 8.0e6, "sdf")], 2: [("dam32m", 32.0e6, "dam")], 4: [("dam32m", 32.0e6, "dam")], 8: [("dam100m", 100.0e6, "dam")]}.get(world, [])
+        for name, total, wl in extra:
+            try:
+                configs[name] = extra_config(name, total, wl, rank, world, local_rank, min(args.steps, 30), 10, peak)
+            except SystemExit:
+                raise
+            except Exception as ex:  # an extra config must never cost the headline line
+                configs[name] = {"workload": name, "failed": str(ex)[-300:]}
+                break
 
     if rank == 0:
-        peak, peak_src = peaks()
         dom = max(phase, key=lambda k: phase[k][0])
         dom_ms = phase[dom][0] / max(1, phase[dom][1])
-        cells = eng.grid.total // world
         dom_bytes = phase_bytes[dom] * n + (8 * cells if dom == "grid" else 0)
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, limiter = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if tj.get("particles") and dom in tj.get("dram_bytes_per_launch", {}):
                 traffic = tj["dram_bytes_per_launch"][dom] * (n / tj["particles"])
+            limiter = tj.get("limiters", {}).get(dom)
         step_gbs = (bytes_per_update * n + 8 * cells) / (ms_per_step * 1e-3) / 1e9
         line = {
             "metric": METRIC if args.solver == "pcisph" else "particle-updates/s (3D SPH sub-step, dam break)",
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("PCISPH 3D dam break + baked-SDF torus collider (BASELINE configs[2] stand-in), " if args.workload == "sdf" else "") +
-                                   f"{'PCISPH' if args.solver == 'pcisph' else 'SPH'} 3D dam break, {n_global} particles = {n} per GPU (BASELINE configs[{'1' if args.solver == 'pcisph' else '0'}] per GPU), spacing 0.02, h = 1.8 s, " +
-                                   (f"{cells} cells, fixed dt 7.2e-4, reference-compat (1 predict-correct iteration)" if args.solver == "pcisph" else
-                                    f"{cells} cells, SphSolver3 step (BASELINE configs[0]), fixed dt 1.44e-4")
-                                   + (f", {world} z-slabs with NCCL ghost-plane exchange and migration" if world > 1 else ""),
+            "config": {"workload": workload_label(args.solver, args.workload, n_global, n, cells, world),
                        "particles_per_gpu": n, "particles": n_global, "cells": cells, "dt": dt,
                        "parallelism": f"slab{world}" if world > 1 else "single",
-                       "halo": ("stores into the neighbours' ghost slots from inside the sweeps (CUDA IPC peer memory over NVLink) + NCCL for the grid phase"
-                                if eng.p2p else "NCCL send/recv per phase") if world > 1 else None,
+                       "halo": ("stores into the neighbours' ghost slots from inside the sweeps (CUDA IPC peer memory over NVLink) + NCCL for the global flags"
+                                if p2p else "NCCL send/recv per phase") if world > 1 else None,
                        "l2_policy": f"working set {state_bytes / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
-                       "timing": "CUDA events on the engine stream between kernels, summed over phases, max over ranks",
-                       "wall_ms_per_step": wall_ms},
+                       "timing": f"{args.repeats} blocks of {args.steps} sub-steps after {args.warmup} warm-up, each block bracketed by two CUDA events on the engine's stream "
+                                 "(launch gaps included), max over ranks per block; ms_per_step = the MEDIAN block",
+                       "ms_per_step_blocks": blocks, "wall_ms_per_step": wall_ms, "host_numa_binding": numa},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d[0] * world, "d2h_bytes_per_step": d2h[0] * world,
-                    "api": ("bbx_overwrite_state + bbx_step_pcisph + bbx_download(POSITION, VELOCITY), pinned host buffers" if world == 1 else
-                            "per rank: bbx_overwrite_owned(host) + bbx_step_pcisph + bbx_download_owned(POSITION, VELOCITY, ids), pinned host buffers"),
-                    "steps": args.e2e_steps},
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_particle": phase_bytes[dom],
                          "whole_step": {"bytes_per_update": bytes_per_update, "achieved": step_gbs, "frac": step_gbs / peak},
                          "phases_ms_per_step": {k: v[0] / args.steps for k, v in phase.items()},
-                         "gap_ms_per_step": gap_ms / args.steps},
-            "stats": {"neighbor_overflow": st.neighbor_overflow, "clamped": st.clamped, "rebuild_flag": st.rebuild_flag,
-                      "occupied_cells": st.occupied_cells, "max_candidates": st.max_candidates, "exact_passes": st.exact_passes, "unstaged_tiles": st.unstaged_tiles},
+                         "gap_ms_per_step": gap_ms / args.steps,
+                         "limiter": limiter},
+            "stats": stats,
+            "parity": parity,
+            "developed": developed,
+            "configs": configs,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(n)
-            eng.close(); eng = None  # free the device before the reference's own GPU build takes it
             line["reference_gpu"] = reference_gpu(n)
+            line["reference_gpu"]["note"] = ("extra key, not the reference arm: the unmodified reference in its native GPU mode on this box; the "
+                                             "`--impl reference` arm steps the CPU path (use_cpu = 1) and only touches the GPU while the reference's own setup code runs")
         else:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                                     "sample": "only measured at N = 1"}
         print(json.dumps(line), flush=True)
-    if eng is not None:
-        eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -20,6 +20,8 @@ F32, F64, I32 = 0, 1, 2
 (PHASE_GRID, PHASE_DENSITY, PHASE_FORCE_NP, PHASE_PREDICT, PHASE_PRESSURE, PHASE_PRESSURE_FORCE,
  PHASE_INTEGRATE) = range(7)
 COLLIDER_BOX, COLLIDER_SPHERE, COLLIDER_SDF = 0, 1, 2
+(PARAM_VISCOSITY, PARAM_PSEUDO_VISCOSITY, PARAM_DRAG, PARAM_RESTITUTION, PARAM_NEGATIVE_PRESSURE_SCALE, PARAM_REFERENCE_COMPAT,
+ PARAM_MAX_ITERATIONS, PARAM_MAX_DENSITY_ERROR_RATIO, PARAM_TIME_STEP_LIMIT_SCALE, PARAM_GRAVITY_X, PARAM_GRAVITY_Y, PARAM_GRAVITY_Z) = range(12)
 
 
 class GridDesc(C.Structure):
@@ -70,6 +72,7 @@ SYMBOLS = {
     "bbx_grid_build": (C.c_int, [C.c_int * 3, C.c_double * 3, C.c_double * 3, C.POINTER(GridDesc)]),
     "bbx_create": (C.c_int, [C.POINTER(Config), C.POINTER(_E)]),
     "bbx_destroy": (C.c_int, [_E]),
+    "bbx_set_param": (C.c_int, [_E, C.c_int, C.c_double]),
     "bbx_get_mass": (C.c_int, [_E, C.POINTER(C.c_double)]),
     "bbx_get_delta": (C.c_int, [_E, C.c_double, C.POINTER(C.c_double)]),
     "bbx_set_particles": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
@@ -85,12 +88,14 @@ SYMBOLS = {
     "bbx_step_sph": (C.c_int, [_E, C.c_double]),
     "bbx_advance": (C.c_int, [_E, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "bbx_step_many": (C.c_int, [_E, C.c_double, C.c_int, C.c_int]),
+    "bbx_step_many_timed": (C.c_int, [_E, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "bbx_run_phase": (C.c_int, [_E, C.c_int, C.c_double]),
     "bbx_synchronize": (C.c_int, [_E]),
     "bbx_set_timing": (C.c_int, [_E, C.c_int]),
     "bbx_stats": (C.c_int, [_E, C.POINTER(StepStats)]),
     "bbx_download": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_int]),
     "bbx_download_owned": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "bbx_download_state": (C.c_int, [_E, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "bbx_export_cells": (C.c_int, [_E, C.c_void_p, C.c_void_p]),
     "bbx_export_neighbors": (C.c_int, [_E, C.c_void_p, C.c_void_p]),
     "bbx_export_neighbors_owned": (C.c_int, [_E, C.c_void_p, C.c_void_p]),

@@ -104,7 +104,7 @@ struct DevState {
     int exact_passes;    // list-build passes repeated with the FP64 predicate (a candidate inside the guard band)
     int max_candidates;  // largest 27-cell neighbourhood seen in the last list build
     int unstaged_tiles;  // sweep tiles (all three sweeps) whose neighbourhood exceeded the shared-memory stage
-
+    int cap;             // particle capacity of the engine (owned slots): the fill / scatter kernels refuse to write past it
 };
 
 // Scalars of one sub-step, passed by value to every kernel.

@@ -41,7 +41,7 @@ struct bbx_engine {
     BbxComm *comm;
     // halo push: the neighbours' arrays as seen from this device (slot-0 pointers), their owned counts, and the
     // flags the neighbours raise in MY memory when their stores into my ghost slots are complete
-    struct PeerSide { float4 *pos[2], *vel[2], *rec, *pred, *posq; int *pid[2], *gtab; unsigned *flags; int n; } peer[2]; // [0] lower, [1] upper neighbour
+    struct PeerSide { float4 *pos[2], *vel[2], *rec, *pred, *posq; int *pid[2], *gtab; unsigned *flags; int n; long long gc; } peer[2]; // [0] lower, [1] upper neighbour (gc = ITS ghost capacity per side)
     int peers_ready;    // share_arrays done (lazily, at the first collective grid update)
     int p2p;            // boundary-plane results are stored straight into the neighbours' ghost slots (else: send / recv per phase)
     unsigned *halo_flags;            // device, [2 sides][BBX_HALO_PHASES]: [0][p] raised by the lower neighbour, [1][p] by the upper one;
@@ -71,6 +71,8 @@ struct bbx_engine {
     float4 *rec;     // 32-byte gather records (x, y, z, rho | vx, vy, vz, -), 2 float4 per slot, written by the list build
     float *pressure, *rho_pred, *rho_err;
     DevState *st; DevState *st_host; // st_host pinned
+    int *err_probe;  // pinned: copy of st->error enqueued behind every sub-step (no sync); checked by the next API call
+    int sm_count;    // multiprocessors of the device (persistent grids are sized from it)
     DevColliderSet *colliders; DevColliderSet colliders_host;
     DevCullSet *cull; DevCullSet cull_host;
     std::vector<double *> sdf_fields;
@@ -92,6 +94,24 @@ static int push_cull(bbx_engine *e);
 #define LAUNCH(e, kernel, grid, block, ...) do{ kernel<<<(grid), (block), 0, (e)->stream>>>(__VA_ARGS__); (e)->launches++; }while(0)
 #define LAUNCH_S(e, kernel, grid, block, smem, ...) do{ kernel<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__); (e)->launches++; }while(0)
 static inline int div_up(long long a, int b){ return (int)((a + b - 1) / b); }
+
+static const char *device_error_text(int code){
+    return code == BBX_ERR_OUT_OF_DOMAIN ? "particle outside the grid bounds" :
+           (code == BBX_ERR_COMM ? "a slab neighbour never signalled its halo stores" :
+           (code == BBX_ERR_CAPACITY ? "more particles than slots (max_particles / ghost_capacity), or a cell run longer than 4096 particles" : "device-side error"));
+}
+// Device-side errors are sticky in DevState::error.  Every sub-step ends with an asynchronous copy of that word into
+// pinned host memory (no synchronisation); the stepping calls look at it on entry, the synchronising calls after
+// their sync -- so a failure surfaces at the latest one call after the sub-step that hit it, and
+// bbx_set_particles clears it.
+static int sticky_error(bbx_engine *e){
+    const int code = e->err_probe ? *(volatile int *)e->err_probe : 0;
+    if(code) return set_error(code, "device-side error %d (%s)", code, device_error_text(code));
+    return BBX_OK;
+}
+static void probe_error(bbx_engine *e){
+    if(e->err_probe) cudaMemcpyAsync(e->err_probe, &e->st->error, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+}
 
 const char *bbx_last_error(void){ return g_last_error.c_str(); }
 int bbx_version(void){ return BBX_VERSION; }
@@ -129,6 +149,7 @@ template<typename T> static int dev_alloc(T **p, size_t count){
     return BBX_OK;
 }
 
+static int create_engine(const bbx_config *cfg, bbx_engine **slot);
 int bbx_create(const bbx_config *cfg, bbx_engine **out){
     if(!cfg || !out) return set_error(BBX_ERR_INVALID, "null argument");
     if(cfg->struct_size != (int)sizeof(bbx_config)) return set_error(BBX_ERR_INVALID, "bbx_config size mismatch (%d vs %d)", cfg->struct_size, (int)sizeof(bbx_config));
@@ -139,7 +160,22 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
         return set_error(BBX_ERR_NO_DEVICE, "no CUDA device: bbx has no CPU fallback");
     if(cfg->device < 0 || cfg->device >= ndev) return set_error(BBX_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
     CU(cudaSetDevice(cfg->device));
+    bbx_engine *e = nullptr;
+    int rc = create_engine(cfg, &e);
+    if(rc != BBX_OK){ std::string keep = g_last_error; bbx_destroy(e); g_last_error = keep; return rc; } // one cleanup path; first error kept
+    *out = e;
+    return BBX_OK;
+}
+
+static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     bbx_engine *e = new bbx_engine();
+    *slot = e; // from here on the caller destroys it on failure
+    e->stream = nullptr; e->side = nullptr; e->ev_fork = nullptr; e->ev_join = nullptr; e->comm = nullptr;
+    for(int b = 0; b < 2; b++){ e->pos[b] = e->vel[b] = nullptr; e->pid[b] = e->cell[b] = e->cell_start[b] = nullptr; }
+    e->newcell = e->count = e->perm = e->occ_cells = e->queue = nullptr; e->movemask = nullptr; e->scan_status = nullptr;
+    e->nbr = nullptr; e->nbr_cnt = nullptr; e->force = e->force_p = e->pred = e->posq = e->smoothed = e->rec = nullptr;
+    e->pressure = e->rho_pred = e->rho_err = nullptr; e->st = nullptr; e->st_host = nullptr; e->err_probe = nullptr;
+    e->colliders = nullptr; e->cull = nullptr; e->gtab = nullptr; e->halo_flags = nullptr; e->mail_host = nullptr; e->stage = nullptr;
     memset(&e->cfg, 0, sizeof(e->cfg));
     e->cfg = *cfg;
     e->device = cfg->device;
@@ -150,6 +186,8 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));
+    if(e->sm_count < 1) e->sm_count = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->list_ctas_per_sm, k_cell_lists_density<0>, BBX_LT, 0));
     if(e->list_ctas_per_sm < 1) e->list_ctas_per_sm = 1;
     // the staged sweeps carry their tile's neighbourhood in dynamic shared memory (> 48 KB: opt in)
@@ -161,20 +199,20 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
         g.minf[k] = (float)g.min[k]; g.maxf[k] = (float)g.max[k]; g.lenf[k] = (float)g.len[k]; g.n[k] = cfg->grid.n[k];
     }
     g.plane = g.n[0] * g.n[1];
-    if((long long)g.n[0] * g.n[1] * g.n[2] != cfg->grid.total) { delete e; return set_error(BBX_ERR_INVALID, "grid.total != nx*ny*nz"); }
+    if((long long)g.n[0] * g.n[1] * g.n[2] != cfg->grid.total) return set_error(BBX_ERR_INVALID, "grid.total != nx*ny*nz");
     // z-slab: owned global planes [zb, ze); one ghost plane towards each existing neighbour
     g.gnz = g.n[2];
     int zb = 0, ze = g.gnz;
     if(cfg->slab_z_end > cfg->slab_z_begin){
         zb = cfg->slab_z_begin; ze = cfg->slab_z_end;
-        if(zb < 0 || ze > g.gnz){ delete e; return set_error(BBX_ERR_INVALID, "slab [%d, %d) outside the grid's %d planes", zb, ze, g.gnz); }
+        if(zb < 0 || ze > g.gnz) return set_error(BBX_ERR_INVALID, "slab [%d, %d) outside the grid's %d planes", zb, ze, g.gnz);
     }
     e->has_lo = zb > 0; e->has_hi = ze < g.gnz;
     g.zoff = zb - (e->has_lo ? 1 : 0);
     g.n[2] = (ze - zb) + (e->has_lo ? 1 : 0) + (e->has_hi ? 1 : 0);
     g.own_z0 = e->has_lo ? 1 : 0; g.own_z1 = g.own_z0 + (ze - zb);
     g.c_own0 = g.own_z0 * g.plane; g.c_own1 = g.own_z1 * g.plane;
-    if((long long)g.plane * g.n[2] > 0x7fffffffLL){ delete e; return set_error(BBX_ERR_INVALID, "more than 2^31 local cells"); }
+    if((long long)g.plane * g.n[2] > 0x7fffffffLL) return set_error(BBX_ERR_INVALID, "more than 2^31 local cells");
     g.total = g.plane * g.n[2];
     e->gcap = 0; e->n_glo = e->n_ghi = e->n_first = e->n_last = 0; e->comm = nullptr; e->gtab = nullptr;
     e->p2p = 0; e->peers_ready = 0; e->halo_flags = nullptr; e->mail_host = nullptr; memset(e->peer, 0, sizeof(e->peer)); memset(e->halo_seq, 0, sizeof(e->halo_seq));
@@ -198,17 +236,18 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     const size_t gc = (size_t)e->gcap;
     size_t cap = (size_t)e->cap + BBX_PAD, capw = ((cap + 31) / 32) * 32, capg = cap + 2 * gc;
     int rc = BBX_OK;
-#define BBX_ALLOC_G(ptr) do{ rc |= dev_alloc(&(ptr), capg); if(rc == BBX_OK){ e->raw.push_back((void *)(ptr)); CU(cudaMemset((ptr), 0, sizeof(*(ptr)) * capg)); (ptr) += gc; } }while(0)
+#define BBX_TRY(call) do{ if(rc == BBX_OK) rc = (call); }while(0) /* keeps the FIRST error */
+#define BBX_ALLOC_G(ptr) do{ BBX_TRY(dev_alloc(&(ptr), capg)); if(rc == BBX_OK){ e->raw.push_back((void *)(ptr)); CU(cudaMemset((ptr), 0, sizeof(*(ptr)) * capg)); (ptr) += gc; }else (ptr) = nullptr; }while(0)
     for(int b = 0; b < 2 && rc == BBX_OK; b++){
         BBX_ALLOC_G(e->pos[b]); BBX_ALLOC_G(e->vel[b]); BBX_ALLOC_G(e->pid[b]); BBX_ALLOC_G(e->cell[b]);
-        rc |= dev_alloc(&e->cell_start[b], (size_t)g.total + 1);
+        BBX_TRY(dev_alloc(&e->cell_start[b], (size_t)g.total + 1));
         if(rc == BBX_OK) CU(cudaMemset(e->cell_start[b], 0, sizeof(int) * ((size_t)g.total + 1)));
     }
     BBX_ALLOC_G(e->newcell); BBX_ALLOC_G(e->pred); BBX_ALLOC_G(e->posq);
 #undef BBX_ALLOC_G
     {   // records: 2 float4 per slot, ghost slots in front like the other slot-indexed arrays (32-byte aligned)
         float4 *raw = nullptr;
-        rc |= dev_alloc(&raw, 2 * capg);
+        BBX_TRY(dev_alloc(&raw, 2 * capg));
         if(rc == BBX_OK){ e->raw.push_back((void *)raw); CU(cudaMemset(raw, 0, sizeof(float4) * 2 * capg)); e->rec = raw + 2 * gc; }
     }
     if(rc == BBX_OK){
@@ -218,26 +257,29 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     }
     if(e->gcap){
         const size_t words = (size_t)2 * (BBX_HALO_PHASES + BBX_HALO_MAIL);
-        rc |= dev_alloc(&e->halo_flags, words);
+        BBX_TRY(dev_alloc(&e->halo_flags, words));
         if(rc == BBX_OK){ CU(cudaMemset(e->halo_flags, 0, sizeof(unsigned) * words)); e->raw_shared[7] = e->halo_flags; }
         CU(cudaMallocHost((void **)&e->mail_host, sizeof(int) * 2 * BBX_HALO_MAIL));
     }
-    rc |= dev_alloc(&e->count, (size_t)g.total + 8); rc |= dev_alloc(&e->perm, cap);
-    rc |= dev_alloc(&e->occ_cells, (size_t)g.total); rc |= dev_alloc(&e->queue, cap);
-    rc |= dev_alloc(&e->movemask, (size_t)g.total);
+    BBX_TRY(dev_alloc(&e->count, (size_t)g.total + 8)); BBX_TRY(dev_alloc(&e->perm, cap));
+    BBX_TRY(dev_alloc(&e->occ_cells, (size_t)g.total)); BBX_TRY(dev_alloc(&e->queue, cap));
+    BBX_TRY(dev_alloc(&e->movemask, (size_t)g.total));
     e->scan_tiles = div_up(g.c_own1 - g.c_own0, SCAN_TILE);
-    rc |= dev_alloc(&e->scan_status, (size_t)e->scan_tiles);
-    rc |= dev_alloc(&e->nbr, capw * BBX_NBR_CHUNKS * 8); rc |= dev_alloc(&e->nbr_cnt, cap);
-    rc |= dev_alloc(&e->force, cap); rc |= dev_alloc(&e->force_p, cap);
-    rc |= dev_alloc(&e->smoothed, cap);
-    rc |= dev_alloc(&e->pressure, cap); rc |= dev_alloc(&e->rho_pred, cap); rc |= dev_alloc(&e->rho_err, cap);
-    rc |= dev_alloc(&e->st, 1); rc |= dev_alloc(&e->colliders, 1); rc |= dev_alloc(&e->cull, 1);
-    if(e->gcap){ rc |= dev_alloc(&e->gtab, 2 * ((size_t)g.plane + 1)); e->raw_shared[10] = e->gtab; }
+    BBX_TRY(dev_alloc(&e->scan_status, (size_t)e->scan_tiles));
+    BBX_TRY(dev_alloc(&e->nbr, capw * BBX_NBR_CHUNKS * 8)); BBX_TRY(dev_alloc(&e->nbr_cnt, cap));
+    BBX_TRY(dev_alloc(&e->force, cap)); BBX_TRY(dev_alloc(&e->force_p, cap));
+    BBX_TRY(dev_alloc(&e->smoothed, cap));
+    BBX_TRY(dev_alloc(&e->pressure, cap)); BBX_TRY(dev_alloc(&e->rho_pred, cap)); BBX_TRY(dev_alloc(&e->rho_err, cap));
+    BBX_TRY(dev_alloc(&e->st, 1)); BBX_TRY(dev_alloc(&e->colliders, 1)); BBX_TRY(dev_alloc(&e->cull, 1));
+    if(e->gcap){ BBX_TRY(dev_alloc(&e->gtab, 2 * ((size_t)g.plane + 1))); e->raw_shared[10] = e->gtab; }
     if(rc != BBX_OK){ return rc; }
     CU(cudaMemset(e->count, 0, sizeof(int) * ((size_t)g.total + 8)));
     CU(cudaMallocHost((void **)&e->st_host, sizeof(DevState)));
-    CU(cudaMemset(e->st, 0, sizeof(DevState)));
+    CU(cudaMallocHost((void **)&e->err_probe, sizeof(int)));
+    *e->err_probe = 0;
     memset(e->st_host, 0, sizeof(DevState));
+    e->st_host->cap = e->cap;
+    CU(cudaMemcpy(e->st, e->st_host, sizeof(DevState), cudaMemcpyHostToDevice));
     memset(&e->colliders_host, 0, sizeof(DevColliderSet));
     CU(cudaMemset(e->colliders, 0, sizeof(DevColliderSet)));
     { int rc2 = push_cull(e); if(rc2) return rc2; }
@@ -245,14 +287,13 @@ int bbx_create(const bbx_config *cfg, bbx_engine **out){
     CU(cudaMemset(e->pressure, 0, sizeof(float) * cap)); CU(cudaMemset(e->rho_pred, 0, sizeof(float) * cap));
     CU(cudaMemset(e->rho_err, 0, sizeof(float) * cap));
     CU(cudaMemset(e->nbr_cnt, 0, sizeof(int) * cap));
-    *out = e;
     return BBX_OK;
 }
 
 int bbx_destroy(bbx_engine *e){
     if(!e) return BBX_OK;
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
+    if(e->stream) cudaStreamSynchronize(e->stream);
     if(e->comm){ delete e->comm; e->comm = nullptr; }
     for(void *p : e->raw) cudaFree(p);
     for(int b = 0; b < 2; b++) cudaFree(e->cell_start[b]);
@@ -262,13 +303,16 @@ int bbx_destroy(bbx_engine *e){
     if(e->gtab) cudaFree(e->gtab);
     if(e->halo_flags) cudaFree(e->halo_flags);
     if(e->mail_host) cudaFreeHost(e->mail_host);
-    cudaFree(e->st); cudaFree(e->colliders); cudaFree(e->cull); cudaFreeHost(e->st_host);
+    cudaFree(e->st); cudaFree(e->colliders); cudaFree(e->cull); if(e->st_host) cudaFreeHost(e->st_host);
+    if(e->err_probe) cudaFreeHost(e->err_probe);
     for(double *f : e->sdf_fields) cudaFree(f);
     for(float *f : e->sdf_fields32) cudaFree(f);
     if(e->stage) cudaFree(e->stage);
     for(cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
-    cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaStreamDestroy(e->side);
-    cudaStreamDestroy(e->stream);
+    if(e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if(e->ev_join) cudaEventDestroy(e->ev_join);
+    if(e->side) cudaStreamDestroy(e->side);
+    if(e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return BBX_OK;
 }
@@ -277,6 +321,28 @@ int bbx_get_mass(bbx_engine *e, double *mass){ if(!e || !mass) return set_error(
 int bbx_get_delta(bbx_engine *e, double dt, double *delta){
     if(!e || !delta) return set_error(BBX_ERR_INVALID, "null");
     *delta = bbxh_delta(e->mass_over_rho0_sq, e->delta_denom, dt);
+    return BBX_OK;
+}
+
+int bbx_set_param(bbx_engine *e, int param, double value){
+    if(!e) return set_error(BBX_ERR_INVALID, "null engine");
+    if(!(value == value)) return set_error(BBX_ERR_INVALID, "NaN parameter");
+    bbx_config &c = e->cfg; // make_params reads it at the start of every sub-step
+    switch(param){
+        case BBX_PARAM_VISCOSITY: c.viscosity = value > 0 ? value : 0; break; // SetViscosityCoefficient clamps at 0
+        case BBX_PARAM_PSEUDO_VISCOSITY: c.pseudo_viscosity = value; break;
+        case BBX_PARAM_DRAG: c.drag = value; break;
+        case BBX_PARAM_RESTITUTION: c.restitution = value; break;
+        case BBX_PARAM_NEGATIVE_PRESSURE_SCALE: c.negative_pressure_scale = value; break;
+        case BBX_PARAM_REFERENCE_COMPAT: c.pcisph_reference_compat = value != 0 ? 1 : 0; break;
+        case BBX_PARAM_MAX_ITERATIONS: if(value < 1) return set_error(BBX_ERR_INVALID, "at least one iteration"); c.pcisph_max_iterations = (int)value; break;
+        case BBX_PARAM_MAX_DENSITY_ERROR_RATIO: c.pcisph_max_density_error_ratio = value; break;
+        case BBX_PARAM_TIME_STEP_LIMIT_SCALE: if(!(value > 0)) return set_error(BBX_ERR_INVALID, "scale must be positive"); c.time_step_limit_scale = value; break;
+        case BBX_PARAM_GRAVITY_X: c.gravity[0] = value; break;
+        case BBX_PARAM_GRAVITY_Y: c.gravity[1] = value; break;
+        case BBX_PARAM_GRAVITY_Z: c.gravity[2] = value; break;
+        default: return set_error(BBX_ERR_INVALID, "unknown parameter %d", param);
+    }
     return BBX_OK;
 }
 
@@ -324,6 +390,10 @@ static int set_particles(bbx_engine *e, int n, const void *pos, const void *vel,
     e->n = IS_SLAB(e) ? 0 : n;
     e->n_glo = e->n_ghi = e->n_first = e->n_last = 0;
     e->have_chains = 0; e->force_full = 1;
+    // a fresh particle set starts with a clean slate: the sticky device error of an earlier set is dropped
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemsetAsync(&e->st->error, 0, sizeof(int), e->stream));
+    *e->err_probe = 0; e->st_host->error = 0;
     if(n == 0 && !IS_SLAB(e)) return BBX_OK;
     int rc;
     if(n > 0){ rc = upload_particles(e, 0, n, pos, vel, ids, dtype); if(rc) return rc; }
@@ -390,6 +460,7 @@ int bbx_overwrite_state(bbx_engine *e, const void *pos, const void *vel, int dty
     if(IS_SLAB(e)) return set_error(BBX_ERR_INVALID, "bbx_overwrite_state is not available on slab engines");
     if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "dtype must be BBX_F32 or BBX_F64");
     if(e->n == 0) return BBX_OK;
+    if(!pos || !vel) return set_error(BBX_ERR_INVALID, "null positions / velocities (bbx_particle_count rows of 3 values each are read)");
     size_t esz = dtype == BBX_F64 ? 8 : 4; size_t bytes = esz * 3 * (size_t)e->n;
     int rc = ensure_stage(e, 2 * bytes); if(rc) return rc;
     char *sp = (char *)e->stage, *sv = sp + bytes;
@@ -658,14 +729,15 @@ static int setup_peers(bbx_engine *e){
         p.rec = (float4 *)a.p[4] + 2 * gc; p.pred = (float4 *)a.p[5] + gc; p.posq = (float4 *)a.p[6] + gc;
         p.flags = (unsigned *)a.p[7];
         p.pid[0] = (int *)a.p[8] + gc; p.pid[1] = (int *)a.p[9] + gc; p.gtab = (int *)a.p[10];
+        p.gc = a.gc;
     }
     e->p2p = 1;
     return BBX_OK;
 }
 
 // UpdateGridDistributionGPU minus the bucket fill (sph_equations3.cpp:511-539)
-#define BBX_SMALL_GRID (148 * 4)
-#define BBX_CHECK_GRID 148 // grid of the full-rebuild kernels when they are only a flag check (they stride over the data if it fires)
+#define BBX_SMALL_GRID (e->sm_count * 4)
+#define BBX_CHECK_GRID (e->sm_count) // grid of the full-rebuild kernels when they are only a flag check (they stride over the data if it fires)
 static int grid_update(bbx_engine *e){
     const bool slab = IS_SLAB(e);
     if(e->n == 0 && !slab) return BBX_OK;
@@ -690,7 +762,7 @@ static int grid_update(bbx_engine *e){
     if(!force){
         // persistent grid: 8 lanes per occupied cell, grid-stride over the compact list of occupied cells
         int groups = std::max(1, std::min(n_all, own_cells));
-        int blocks = std::min(div_up((long long)groups * 8, 256), 148 * 8);
+        int blocks = std::min(div_up((long long)groups * 8, 256), e->sm_count * 8);
         LAUNCH(e, k_fill_incremental, blocks, 256, g, e->st, par, slab ? 1 : 0, e->occ_cells, e->cell_start[cur], e->cell_start[nxt], e->newcell,
                e->pos[cur], e->vel[cur], e->pid[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec, e->movemask);
     }
@@ -736,6 +808,13 @@ static int grid_update(bbx_engine *e){
         }
         if(n_new > e->cap) return set_error(BBX_ERR_CAPACITY, "slab now owns %d particles, max_particles is %d", n_new, e->cap);
         if(glo > e->gcap || ghi > e->gcap) return set_error(BBX_ERR_CAPACITY, "ghost plane of %d particles exceeds ghost_capacity %d", std::max(glo, ghi), e->gcap);
+        // sender side of the same rule: my boundary planes must fit the NEIGHBOURS' ghost slots (their capacity came with
+        // share_arrays).  Both ends of a cut see the same numbers, so both refuse here and nothing is written past an allocation.
+        if(e->p2p && ((e->has_lo && nf > e->peer[0].gc) || (e->has_hi && nl > e->peer[1].gc)))
+            return set_error(BBX_ERR_CAPACITY, "boundary plane of %d particles exceeds the neighbour's ghost_capacity %lld",
+                             (e->has_lo && nf > e->peer[0].gc) ? nf : nl, (e->has_lo && nf > e->peer[0].gc) ? e->peer[0].gc : e->peer[1].gc);
+        // any other device-side failure of an earlier sub-step (out of domain, halo time-out, run overflow) stops the run here
+        if(e->st_host->error) return set_error(e->st_host->error, "device-side error %d (%s)", e->st_host->error, device_error_text(e->st_host->error));
         if(e->p2p){
             // my freshly ordered boundary planes -> the neighbours' ghost slots (their table slices: lower ghost
             // plane at gtab, upper one at gtab + plane + 1), then the planes flag
@@ -755,7 +834,7 @@ static int grid_update(bbx_engine *e){
                 add(e->vel[nxt] + (n_new - nl), p.vel[nxt] - nl, sizeof(float4) * (size_t)nl);
                 add(e->pid[nxt] + (n_new - nl), p.pid[nxt] - nl, sizeof(int) * (size_t)nl);
             }
-            LAUNCH(e, k_push_planes, 148, 256, S);
+            LAUNCH(e, k_push_planes, e->sm_count, 256, S);
             int rc = halo_sync(e, HALO_PLANES); if(rc) return rc;
         }else{
             BbxSeg slo[4] = {{e->cell_start[nxt] + g.c_own0, tb}, {e->pos[nxt], sizeof(float4) * (size_t)nf}, {e->vel[nxt], sizeof(float4) * (size_t)nf}, {e->pid[nxt], sizeof(int) * (size_t)nf}};
@@ -778,7 +857,7 @@ static int grid_update(bbx_engine *e){
 // persistent grid of the list build: one warp per occupied cell, grid-stride over the occupied-cell list
 static int list_blocks(bbx_engine *e){
     long long cells = std::min<long long>(e->n, e->grid.c_own1 - e->grid.c_own0);
-    return (int)std::max<long long>(1, std::min<long long>((cells + BBX_LW - 1) / BBX_LW, (long long)148 * e->list_ctas_per_sm));
+    return (int)std::max<long long>(1, std::min<long long>((cells + BBX_LW - 1) / BBX_LW, (long long)e->sm_count * e->list_ctas_per_sm));
 }
 static int phase_density(bbx_engine *e, const StepParams &P, int sph){
     int cur = e->cur;
@@ -867,6 +946,7 @@ static int step_pcisph(bbx_engine *e, double dt){
     if(!(dt > 0)) return set_error(BBX_ERR_INVALID, "dt must be positive");
     StepParams P;
     int rc;
+    if((rc = sticky_error(e))) return rc;
     tick(e, T_GRID);
     if((rc = grid_update(e))) return rc;
     make_params(e, dt, P);
@@ -908,6 +988,7 @@ static int step_pcisph(bbx_engine *e, double dt){
     }
     if((rc = phase_pseudo_viscosity(e, P, dt))) return rc;
     tick(e, T_COUNT);
+    probe_error(e);
     e->substeps++;
     return BBX_OK;
 }
@@ -917,6 +998,7 @@ static int step_sph(bbx_engine *e, double dt){
     if(!(dt > 0)) return set_error(BBX_ERR_INVALID, "dt must be positive");
     StepParams P;
     int rc;
+    if((rc = sticky_error(e))) return rc;
     tick(e, T_GRID);
     if((rc = grid_update(e))) return rc;
     make_params(e, dt, P);
@@ -931,6 +1013,7 @@ static int step_sph(bbx_engine *e, double dt){
     if((rc = phase_integrate(e, P, 0))) return rc;
     if((rc = phase_pseudo_viscosity(e, P, dt))) return rc;
     tick(e, T_COUNT);
+    probe_error(e);
     e->substeps++;
     return BBX_OK;
 }
@@ -947,6 +1030,21 @@ int bbx_step_many(bbx_engine *e, double dt, int solver, int n){
     }
     if(e->timing) harvest(e);
     return BBX_OK;
+}
+// n sub-steps bracketed by two events on the engine's stream: *ms = device time of the whole region (launch gaps
+// included), the figure bench.py reports; returns after the last sub-step has finished
+int bbx_step_many_timed(bbx_engine *e, double dt, int solver, int n, float *ms){
+    CHECK_ENGINE(e);
+    if(!ms) return set_error(BBX_ERR_INVALID, "null");
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); if(cudaEventCreate(&e1) != cudaSuccess){ cudaEventDestroy(e0); return set_error(BBX_ERR_CUDA, "cudaEventCreate failed"); }
+    int rc = BBX_OK;
+    if(cudaEventRecord(e0, e->stream) != cudaSuccess) rc = set_error(BBX_ERR_CUDA, "cudaEventRecord failed");
+    for(int s = 0; s < n && rc == BBX_OK; s++) rc = solver == BBX_SOLVER_SPH ? step_sph(e, dt) : step_pcisph(e, dt);
+    if(rc == BBX_OK && (cudaEventRecord(e1, e->stream) != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess)) rc = set_error(BBX_ERR_CUDA, "event synchronisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if(rc == BBX_OK){ *ms = 0.f; cudaEventElapsedTime(ms, e0, e1); rc = sticky_error(e); }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if(e->timing) harvest(e);
+    return rc;
 }
 
 int bbx_run_phase(bbx_engine *e, int phase, double dt){
@@ -977,31 +1075,35 @@ static unsigned number_of_time_steps(bbx_engine *e, double remaining, double max
 
 int bbx_advance(bbx_engine *e, double seconds, int solver, int *substeps, float *ms){
     CHECK_ENGINE(e);
-    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, e->stream));
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); if(cudaEventCreate(&e1) != cudaSuccess){ cudaEventDestroy(e0); return set_error(BBX_ERR_CUDA, "cudaEventCreate failed"); }
+    int rc = BBX_OK;
+    if(cudaEventRecord(e0, e->stream) != cudaSuccess) rc = set_error(BBX_ERR_CUDA, "cudaEventRecord failed");
     double remaining = seconds; int count = 0;
     double scale = solver == BBX_SOLVER_SPH ? 1.0 : e->cfg.time_step_limit_scale;
-    while(remaining > (double)0.0001f){ // `while(remainingTime > Epsilon)`, pcisph_solver3.cpp:76
-        if(IS_SLAB(e)) COMM(e->comm->allreduce_max_u32(e->stream, &e->st->max_force_bits, 1)); // same dt on every slab
-        int rc = read_state(e); if(rc) return rc;
+    while(rc == BBX_OK && remaining > (double)0.0001f){ // `while(remainingTime > Epsilon)`, pcisph_solver3.cpp:76
+        if(IS_SLAB(e) && e->comm->allreduce_max_u32(e->stream, &e->st->max_force_bits, 1)){ rc = set_error(BBX_ERR_COMM, "%s", e->comm->err.c_str()); break; } // same dt on every slab
+        if((rc = read_state(e))) break;
+        // the CFL scan synchronises anyway: a device-side failure of the previous sub-step ends the frame here
+        if(e->st_host->error){ rc = set_error(e->st_host->error, "device-side error %d (%s)", e->st_host->error, device_error_text(e->st_host->error)); break; }
         float mf; memcpy(&mf, &e->st_host->max_force_bits, 4);
         unsigned nsteps = number_of_time_steps(e, remaining, (double)mf, scale);
         double dt = remaining / (double)nsteps;
         rc = solver == BBX_SOLVER_SPH ? step_sph(e, dt) : step_pcisph(e, dt);
-        if(rc) return rc;
+        if(rc) break;
         remaining -= dt; count++;
     }
-    CU(cudaEventRecord(e1, e->stream));
-    CU(cudaEventSynchronize(e1));
-    float t = 0.f; cudaEventElapsedTime(&t, e0, e1);
+    if(rc == BBX_OK && (cudaEventRecord(e1, e->stream) != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess)) rc = set_error(BBX_ERR_CUDA, "event synchronisation failed");
+    float t = 0.f; if(rc == BBX_OK) cudaEventElapsedTime(&t, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if(rc == BBX_OK) rc = sticky_error(e);
+    if(rc) return rc;
     if(e->timing) harvest(e);
     if(substeps) *substeps = count;
     if(ms) *ms = t;
     return BBX_OK;
 }
 
-int bbx_synchronize(bbx_engine *e){ CHECK_ENGINE(e); CU(cudaStreamSynchronize(e->stream)); return BBX_OK; }
+int bbx_synchronize(bbx_engine *e){ CHECK_ENGINE(e); CU(cudaStreamSynchronize(e->stream)); return sticky_error(e); }
 int bbx_set_timing(bbx_engine *e, int enabled){ CHECK_ENGINE(e); if(e->timing) harvest(e); e->timing = enabled ? 1 : 0; e->ev_used = 0; return BBX_OK; }
 
 int bbx_stats(bbx_engine *e, bbx_step_stats *out){
@@ -1020,9 +1122,7 @@ int bbx_stats(bbx_engine *e, bbx_step_stats *out){
     memcpy(&out->max_force, &s.max_force_bits, 4); memcpy(&out->max_density_error, &s.max_err_bits, 4);
     out->ms_grid = e->last_ms_grid; out->ms_step = e->last_ms_step;
     out->exact_passes = s.exact_passes; out->max_candidates = s.max_candidates; out->occupied_cells = s.n_occ; out->unstaged_tiles = s.unstaged_tiles;
-    if(s.error) return set_error(s.error, "device-side error %d (%s)", s.error,
-                                 s.error == BBX_ERR_OUT_OF_DOMAIN ? "particle outside the grid bounds" :
-                                 (s.error == BBX_ERR_COMM ? "a slab neighbour never signalled its halo stores" : "a cell run holds more than 4096 particles"));
+    if(s.error) return set_error(s.error, "device-side error %d (%s)", s.error, device_error_text(s.error));
     return BBX_OK;
 }
 
@@ -1070,6 +1170,28 @@ int bbx_download_owned(bbx_engine *e, int field, void *dst, int dtype, int *ids,
     }
     if(!dst) return BBX_OK;
     return download(e, field, dst, dtype, 1);
+}
+
+// positions + velocities (+ ids) of one frame with ONE kernel, back-to-back copies and ONE synchronisation: what a host
+// run loop reads after Advance (UtilRunSimulation3, src/core/util.h:583-590)
+int bbx_download_state(bbx_engine *e, void *pos, void *vel, int *ids, int dtype, int owned_order, int *count){
+    CHECK_ENGINE(e);
+    if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "dtype must be BBX_F32 or BBX_F64");
+    if(IS_SLAB(e) && !owned_order) return set_error(BBX_ERR_INVALID, "a slab engine returns its owned particles in cell order: pass owned_order = 1");
+    if(count) *count = e->n;
+    if(e->n == 0) return BBX_OK;
+    if(!pos || !vel) return set_error(BBX_ERR_INVALID, "null destination");
+    const int n = e->n, cur = e->cur;
+    const size_t bytes = (dtype == BBX_F64 ? 8 : 4) * 3 * (size_t)n;
+    int rc = ensure_stage(e, 2 * bytes); if(rc) return rc;
+    char *sp = (char *)e->stage, *sv = sp + bytes;
+    LAUNCH(e, k_download_state, div_up(n, 256), 256, n, owned_order ? (const int *)nullptr : e->pid[cur], e->pos[cur], e->vel[cur], dtype == BBX_F64, sp, sv);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pos, sp, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(vel, sv, bytes, cudaMemcpyDeviceToHost, e->stream));
+    if(ids) CU(cudaMemcpyAsync(ids, e->pid[cur], sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return sticky_error(e);
 }
 
 int bbx_export_cells(bbx_engine *e, int *cell_count, int *cell_order){

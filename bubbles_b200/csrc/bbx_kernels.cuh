@@ -163,6 +163,9 @@ __global__ void __launch_bounds__(256) k_scan_cells(int *__restrict__ count, int
         start[total] = (int)(run & 0x7fffffffull);
         st->n_own = (int)(run & 0x7fffffffull);
         st->n_occ = (int)(run >> 31);
+        // more particles than slots (a slab that gained too many by migration): the fill / scatter / gather kernels
+        // below write nothing and the host turns the sticky flag into BBX_ERR_CAPACITY
+        if((int)(run & 0x7fffffffull) > st->cap) st->error = BBX_ERR_CAPACITY;
     }
 }
 
@@ -181,6 +184,7 @@ __global__ void __launch_bounds__(256) k_fill_incremental(DevGrid g, const DevSt
     // full rebuild path takes over.  (Slab engines run the fill regardless: their flags are still being reduced
     // over the ranks on a side stream; a full rebuild, if it comes, overwrites everything written here.)
     if(!ignore_flags && (st->rebuild_flag[par] | st->jump_flag[par])) return;
+    if(st->n_own > st->cap) return;
     const int n_occ = st->n_occ;
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
     const unsigned gshift = grp * 8;
@@ -263,6 +267,7 @@ __global__ void __launch_bounds__(256) k_full_scatter(int n_all, int n_lo, DevGr
         const int *__restrict__ start_new, int *__restrict__ cursor, int *__restrict__ perm)
 {
     if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
+    if(st->n_own > st->cap) return;
     for(int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_all; idx += gridDim.x * blockDim.x){
         int i = idx - n_lo;
         int c = newcell[i];
@@ -277,8 +282,10 @@ __global__ void __launch_bounds__(256) k_full_sort_cells(DevGrid g, const DevSta
         const int *__restrict__ pid_old, int *__restrict__ perm, int *__restrict__ cursor)
 {
     if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
+    const bool over = st->n_own > st->cap;
     for(int c = g.c_own0 + blockIdx.x * blockDim.x + threadIdx.x; c < g.c_own1; c += gridDim.x * blockDim.x){
         cursor[c] = 0; // back to an all-zero histogram for the next sub-step
+        if(over) continue;
         int s = start_new[c], e = start_new[c + 1];
         for(int a = s + 1; a < e; a++){ // insertion sort by original id (segments are a dozen long)
             int pa = perm[a]; int ka = pid_old ? pid_old[pa] : pa;
@@ -321,6 +328,7 @@ __global__ void __launch_bounds__(256) k_full_gather(const DevState *st, int par
 {
     if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
     const int n = st->n_own;
+    if(n > st->cap) return;
     for(int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x){
         int j = perm[d];
         const float4 pp = pos_old[j], vv = vel_old[j];
@@ -950,6 +958,22 @@ __global__ void __launch_bounds__(256) k_download(int n, const int *__restrict__
     }else{
         float v = src4 ? src4[i].w : src1[i];
         if(is_f64) ((double *)dst)[id] = v; else ((float *)dst)[id] = v;
+    }
+}
+// positions AND velocities in one pass (bbx_download_state): row = particle id, or the slot when pid = null
+__global__ void __launch_bounds__(256) k_download_state(int n, const int *__restrict__ pid, const float4 *__restrict__ pos, const float4 *__restrict__ vel,
+                                                        int is_f64, void *__restrict__ dpos, void *__restrict__ dvel)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    size_t id = pid ? (size_t)pid[i] : (size_t)i;
+    const float4 p = pos[i], v = vel[i];
+    if(is_f64){
+        double *a = (double *)dpos + 3 * id, *b = (double *)dvel + 3 * id;
+        a[0] = p.x; a[1] = p.y; a[2] = p.z; b[0] = v.x; b[1] = v.y; b[2] = v.z;
+    }else{
+        float *a = (float *)dpos + 3 * id, *b = (float *)dvel + 3 * id;
+        a[0] = p.x; a[1] = p.y; a[2] = p.z; b[0] = v.x; b[1] = v.y; b[2] = v.z;
     }
 }
 __global__ void __launch_bounds__(256) k_export_cells(int total, const int *__restrict__ cell_start, int *__restrict__ cell_count){

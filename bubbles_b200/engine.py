@@ -184,17 +184,30 @@ class Engine:
             return np.ascontiguousarray(a), L.F32
         return np.ascontiguousarray(a, dtype=np.float64), L.F64
 
-    def set_particles(self, pos, vel):
-        pos, dt = self._arr(pos)
+    @staticmethod
+    def _pair(pos, vel, rows=None):
+        """contiguous (pos, vel, dtype code) of equal shape [n, 3] (and exactly `rows` rows when given): the C ABI
+        reads n x 3 values from each pointer, a short array would be read past its end"""
+        pos, dt = Engine._arr(pos)
         vel = np.ascontiguousarray(vel, dtype=pos.dtype)
+        pos, vel = pos.reshape(-1, 3), vel.reshape(-1, 3)
+        if pos.shape != vel.shape:
+            raise ValueError(f"positions {pos.shape} and velocities {vel.shape} differ in shape")
+        if rows is not None and len(pos) != rows:
+            raise ValueError(f"{len(pos)} rows given, the engine holds {rows} particles")
+        return pos, vel, dt
+
+    def set_particles(self, pos, vel):
+        pos, vel, dt = self._pair(pos, vel)
         _check(self.lib.bbx_set_particles(self.h, len(pos), pos.ctypes.data, vel.ctypes.data, dt))
 
     def set_particles_ids(self, pos, vel, ids=None):
         """Slab engines: keeps the particles of the owned planes; collective over the slab group."""
-        pos, dt = self._arr(pos)
-        vel = np.ascontiguousarray(vel, dtype=pos.dtype)
+        pos, vel, dt = self._pair(pos, vel)
         if ids is not None:
             ids = np.ascontiguousarray(ids, dtype=np.int32)
+            if len(ids) != len(pos):
+                raise ValueError(f"{len(ids)} ids for {len(pos)} particles")
         _check(self.lib.bbx_set_particles_ids(self.h, len(pos), pos.ctypes.data, vel.ctypes.data,
                                               None if ids is None else ids.ctypes.data, dt))
 
@@ -206,13 +219,11 @@ class Engine:
         _check(self.lib.bbx_comm_init(self.h, rank, nranks, buf))
 
     def append_particles(self, pos, vel):
-        pos, dt = self._arr(pos)
-        vel = np.ascontiguousarray(vel, dtype=pos.dtype)
+        pos, vel, dt = self._pair(pos, vel)
         _check(self.lib.bbx_append_particles(self.h, len(pos), pos.ctypes.data, vel.ctypes.data, dt))
 
     def overwrite_state(self, pos, vel):
-        pos, dt = self._arr(pos)
-        vel = np.ascontiguousarray(vel, dtype=pos.dtype)
+        pos, vel, dt = self._pair(pos, vel, rows=self.n)
         _check(self.lib.bbx_overwrite_state(self.h, pos.ctypes.data, vel.ctypes.data, dt))
 
     @property
@@ -224,8 +235,7 @@ class Engine:
 
     def overwrite_owned(self, pos, vel):
         """Overwrite the owned particles, rows in the order of the last download_owned (collective on slabs)."""
-        pos, dt = self._arr(pos)
-        vel = np.ascontiguousarray(vel, dtype=pos.dtype)
+        pos, vel, dt = self._pair(pos, vel, rows=self.n)
         _check(self.lib.bbx_overwrite_owned(self.h, pos.ctypes.data, vel.ctypes.data, dt))
 
     @property
@@ -245,6 +255,10 @@ class Engine:
     def update_collider(self, index, collider):
         _check(self.lib.bbx_update_collider(self.h, index, C.byref(collider)))
 
+    def set_param(self, param, value):
+        """a solver constant the reference reads live (viscosity, pseudo-viscosity, compat flag ...): next sub-step on"""
+        _check(self.lib.bbx_set_param(self.h, int(param), float(value)))
+
     # -- stepping
     def step_pcisph(self, dt):
         _check(self.lib.bbx_step_pcisph(self.h, dt))
@@ -254,6 +268,12 @@ class Engine:
 
     def step_many(self, dt, n, solver=L.SOLVER_PCISPH):
         _check(self.lib.bbx_step_many(self.h, dt, solver, n))
+
+    def step_many_timed(self, dt, n, solver=L.SOLVER_PCISPH):
+        """n sub-steps; returns the device time (ms) of the whole region, events on the engine's stream."""
+        ms = C.c_float()
+        _check(self.lib.bbx_step_many_timed(self.h, dt, solver, n, C.byref(ms)))
+        return ms.value
 
     def advance(self, seconds, solver=L.SOLVER_PCISPH):
         sub, ms = C.c_int(), C.c_float()

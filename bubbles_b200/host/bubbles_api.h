@@ -402,10 +402,12 @@ struct VolumeParticleEmitter3 {
             const vec3f target = point + maxJitter * vec3f(std::cos(utheta) * usqrt, std::sin(utheta) * usqrt, 1 - 2 * (Float)u1);
             if(shape->SignedDistance(target) <= 0){
                 if(emittedParticles >= maxParticles) return false;
-                builder->AddParticle(target, initVel); emittedParticles++;
+                if(!builder->AddParticle(target, initVel)) return false; // builder full: the emission stops (emitter.cpp:283-289)
+                emittedParticles++;
             }
             return true;
         });
+        builder->Commit(); // the reference's _Emit commits per emitter (emitter.cpp:300-303)
     }
 };
 struct VolumeParticleEmitterSet3 {
@@ -473,7 +475,9 @@ class SolverBase3 {
         Check(bbx_set_colliders(engine, (int)abi.size(), abi.data()));
     }
     std::shared_ptr<ColliderSet3> GetColliders(){ return data->collider; }
-    void SetViscosityCoefficient(Float v){ data->cfg.viscosity = v > 0 ? v : 0; }
+    // the reference reads SphSolverData3 live every sub-step: setters called after Setup() reach the engine too
+    void SetParam(int param, double value){ if(engine) Check(bbx_set_param(engine, param, value)); }
+    void SetViscosityCoefficient(Float v){ data->cfg.viscosity = v > 0 ? v : 0; SetParam(BBX_PARAM_VISCOSITY, data->cfg.viscosity); }
     SphSolverData3 *GetSphSolverData(){ return data.get(); }
     SphParticleSet3 *GetSphParticleSet(){ return data->sphpSet.get(); }
     Float GetKernelRadius(){ return data->sphpSet->GetKernelRadius(); }
@@ -497,12 +501,12 @@ class PciSphSolver3 : public SolverBase3 {
     PciSphSolver3() : SolverBase3(BBX_SOLVER_PCISPH) {}
     Float ComputeDelta(Float timeIntervalInSeconds){ double d = 0; Check(bbx_get_delta(engine, timeIntervalInSeconds, &d)); return d; }
     // 1: the reference's effective behaviour (one predict-correct iteration); 0: iterate to tolerance
-    void SetReferenceCompat(bool on){ data->cfg.pcisph_reference_compat = on ? 1 : 0; }
+    void SetReferenceCompat(bool on){ data->cfg.pcisph_reference_compat = on ? 1 : 0; SetParam(BBX_PARAM_REFERENCE_COMPAT, on ? 1 : 0); }
 };
 class SphSolver3 : public SolverBase3 {
   public:
     SphSolver3() : SolverBase3(BBX_SOLVER_SPH) {}
-    void SetPseudoViscosityCoefficient(Float v){ data->cfg.pseudo_viscosity = v; }
+    void SetPseudoViscosityCoefficient(Float v){ data->cfg.pseudo_viscosity = v; SetParam(BBX_PARAM_PSEUDO_VISCOSITY, v); }
 };
 
 // --------------------------------------------------------------------------------------- serializer

@@ -170,6 +170,16 @@ int bbx_grid_build(const int resolution[3], const double p0[3], const double p1[
 /* PciSphSolver3::Setup / SphSolver3::Setup: allocates device state, computes mass and delta denom */
 int bbx_create(const bbx_config *cfg, bbx_engine **out);
 int bbx_destroy(bbx_engine *e);
+/* Solver constants that the reference reads live from SphSolverData3 / PciSphSolver3 every sub-step
+ * (SphSolver3::SetViscosityCoefficient, SetPseudoViscosityCoefficient, src/solvers/sph_solver3.cpp:22-33): change
+ * one after bbx_create; takes effect with the next sub-step. */
+enum bbx_param {
+    BBX_PARAM_VISCOSITY = 0, BBX_PARAM_PSEUDO_VISCOSITY = 1, BBX_PARAM_DRAG = 2, BBX_PARAM_RESTITUTION = 3,
+    BBX_PARAM_NEGATIVE_PRESSURE_SCALE = 4, BBX_PARAM_REFERENCE_COMPAT = 5, BBX_PARAM_MAX_ITERATIONS = 6,
+    BBX_PARAM_MAX_DENSITY_ERROR_RATIO = 7, BBX_PARAM_TIME_STEP_LIMIT_SCALE = 8,
+    BBX_PARAM_GRAVITY_X = 9, BBX_PARAM_GRAVITY_Y = 10, BBX_PARAM_GRAVITY_Z = 11
+};
+int bbx_set_param(bbx_engine *e, int param, double value);
 /* scalars computed at setup: ParticleSet3::GetMass, PciSphSolver3::deltaDenom, ::ComputeDelta(dt) */
 int bbx_get_mass(bbx_engine *e, double *mass);
 int bbx_get_delta(bbx_engine *e, double dt, double *delta);
@@ -209,8 +219,15 @@ int bbx_step_sph(bbx_engine *e, double dt);
 int bbx_advance(bbx_engine *e, double seconds, int solver, int *substeps, float *ms);
 /* n fixed-dt sub-steps enqueued back to back without host synchronisation */
 int bbx_step_many(bbx_engine *e, double dt, int solver, int n);
+/* the same, bracketed by two events on the engine's stream: *ms = device time of the n sub-steps, launch gaps
+ * included (what bench.py reports); returns once the last sub-step has finished */
+int bbx_step_many_timed(bbx_engine *e, double dt, int solver, int n, float *ms);
 int bbx_run_phase(bbx_engine *e, int phase, double dt);
 int bbx_synchronize(bbx_engine *e);
+/* Device-side failures (a particle outside the grid, a slab neighbour that never signalled, more particles than
+ * slots) are sticky: the sub-step that hits one keeps running on what it has, the NEXT stepping call -- or any
+ * synchronising call (bbx_synchronize, bbx_step_many_timed, bbx_advance, bbx_stats) -- returns the code, and
+ * bbx_set_particles clears it.  The reference aborts the process in these situations (AssertA / exit). */
 /* device-event timing of every sub-step phase (off by default; costs a sync per sub-step) */
 int bbx_set_timing(bbx_engine *e, int enabled);
 int bbx_stats(bbx_engine *e, bbx_step_stats *out);
@@ -220,6 +237,11 @@ int bbx_download(bbx_engine *e, int field, void *dst, int dtype);
 /* slab engines (works on any engine): the owned particles in the engine's cell order; ids[k] = global id
  * of row k of dst, *count = owned particles.  dst or ids may be NULL.                                   */
 int bbx_download_owned(bbx_engine *e, int field, void *dst, int dtype, int *ids, int *count);
+/* positions and velocities of one frame in a single call (one kernel, one synchronisation): rows in particle-id
+ * order (owned_order = 0, single-domain engines) or in the engine's cell order with ids[k] = global id of row k
+ * (owned_order = 1, any engine; ids may be NULL).  *count = rows written.  What UtilRunSimulation3 reads after every
+ * Advance (src/core/util.h:583-590). */
+int bbx_download_state(bbx_engine *e, void *pos, void *vel, int *ids, int dtype, int owned_order, int *count);
 /* active chains: cell_count[total], cell_order[n] (concatenated chains, original ids) */
 int bbx_export_cells(bbx_engine *e, int *cell_count, int *cell_order);
 /* stored neighbour lists in the reference's bucket order: counts[n], ids[n*100] (unused = -1) */
