@@ -73,6 +73,8 @@ struct bbx_engine {
     DevState *st; DevState *st_host; // st_host pinned
     int *err_probe;  // pinned: copy of st->error enqueued behind every sub-step (no sync); checked by the next API call
     int sm_count;    // multiprocessors of the device (persistent grids are sized from it)
+    int deferred_error; // slab engines: a device-side error seen in the middle of a collective sub-step; the sub-step is
+                        // finished (so that the neighbours are not left waiting for this rank's halo signals), then returned
     DevColliderSet *colliders; DevColliderSet colliders_host;
     DevCullSet *cull; DevCullSet cull_host;
     std::vector<double *> sdf_fields;
@@ -180,7 +182,7 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     e->cfg = *cfg;
     e->device = cfg->device;
     e->n = 0; e->cap = cfg->max_particles; e->cur = 0; e->have_chains = 0; e->launches = 0; e->substeps = 0; e->epoch = 0;
-    e->timing = 0; e->ev_used = 0; e->force_full = 1; e->stage = nullptr; e->stage_bytes = 0;
+    e->timing = 0; e->ev_used = 0; e->force_full = 1; e->stage = nullptr; e->stage_bytes = 0; e->deferred_error = 0;
     e->last_ms_grid = e->last_ms_step = 0.f;
     memset(e->phase_ms, 0, sizeof(e->phase_ms)); memset(e->phase_launches, 0, sizeof(e->phase_launches));
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -393,7 +395,7 @@ static int set_particles(bbx_engine *e, int n, const void *pos, const void *vel,
     // a fresh particle set starts with a clean slate: the sticky device error of an earlier set is dropped
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaMemsetAsync(&e->st->error, 0, sizeof(int), e->stream));
-    *e->err_probe = 0; e->st_host->error = 0;
+    *e->err_probe = 0; e->st_host->error = 0; e->deferred_error = 0;
     if(n == 0 && !IS_SLAB(e)) return BBX_OK;
     int rc;
     if(n > 0){ rc = upload_particles(e, 0, n, pos, vel, ids, dtype); if(rc) return rc; }
@@ -813,8 +815,11 @@ static int grid_update(bbx_engine *e){
         if(e->p2p && ((e->has_lo && nf > e->peer[0].gc) || (e->has_hi && nl > e->peer[1].gc)))
             return set_error(BBX_ERR_CAPACITY, "boundary plane of %d particles exceeds the neighbour's ghost_capacity %lld",
                              (e->has_lo && nf > e->peer[0].gc) ? nf : nl, (e->has_lo && nf > e->peer[0].gc) ? e->peer[0].gc : e->peer[1].gc);
-        // any other device-side failure of an earlier sub-step (out of domain, halo time-out, run overflow) stops the run here
-        if(e->st_host->error) return set_error(e->st_host->error, "device-side error %d (%s)", e->st_host->error, device_error_text(e->st_host->error));
+        // any other device-side failure (halo time-out, run overflow) stops the run here; a particle that left the slab's halo
+        // (dropped by the hash kernel) lets the collective sub-step finish first -- every signal the neighbours wait for is
+        // still sent -- and is reported by the stepping call on its way out
+        if(e->st_host->error == BBX_ERR_OUT_OF_DOMAIN) e->deferred_error = BBX_ERR_OUT_OF_DOMAIN;
+        else if(e->st_host->error) return set_error(e->st_host->error, "device-side error %d (%s)", e->st_host->error, device_error_text(e->st_host->error));
         if(e->p2p){
             // my freshly ordered boundary planes -> the neighbours' ghost slots (their table slices: lower ghost
             // plane at gtab, upper one at gtab + plane + 1), then the planes flag
@@ -990,6 +995,7 @@ static int step_pcisph(bbx_engine *e, double dt){
     tick(e, T_COUNT);
     probe_error(e);
     e->substeps++;
+    if(e->deferred_error) return set_error(e->deferred_error, "device-side error %d (%s)", e->deferred_error, device_error_text(e->deferred_error));
     return BBX_OK;
 }
 
@@ -1015,6 +1021,7 @@ static int step_sph(bbx_engine *e, double dt){
     tick(e, T_COUNT);
     probe_error(e);
     e->substeps++;
+    if(e->deferred_error) return set_error(e->deferred_error, "device-side error %d (%s)", e->deferred_error, device_error_text(e->deferred_error));
     return BBX_OK;
 }
 

@@ -438,14 +438,24 @@ __device__ __forceinline__ uint4 *bbx_chunk_ptr(unsigned short *__restrict__ nbr
 
 // Full 8-entry chunks run without per-entry guards (the next chunk is requested before the current one is
 // consumed); only the last, partial chunk tests k < cnt.  STRIDE = threads per CTA (column stride of sbase).
+// a list chunk is read exactly once per sweep: keep it out of L1, whose lines the scattered gathers want
+__device__ __forceinline__ uint4 bbx_load_chunk(const uint4 *p){
+#ifdef BBX_LIST_NOALLOC
+    uint4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
 template<int STRIDE, typename F>
 __device__ __forceinline__ void bbx_for_each_neighbor(const uint4 *__restrict__ lp, int cnt, const int *sbase_col, F &&body){
     const int full = cnt >> 3;
     uint4 ch = make_uint4(0u, 0u, 0u, 0u);
-    if(cnt > 0) ch = lp[0];
+    if(cnt > 0) ch = bbx_load_chunk(lp);
     for(int c = 0; c < full; c++){
         const uint4 cur = ch;
-        if((c + 1) * 8 < cnt) ch = lp[(size_t)(c + 1) * 32];
+        if((c + 1) * 8 < cnt) ch = bbx_load_chunk(lp + (size_t)(c + 1) * 32);
         const unsigned wv[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
         for(int t = 0; t < 8; t++){

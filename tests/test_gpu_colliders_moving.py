@@ -44,11 +44,11 @@ def _set_oracle_collider(orc, index, c):
     C.memmove(C.byref(orc._colliders[index]), C.byref(c), C.sizeof(O.Collider))
 
 
-def _path(k):
+def _path(k, z0=0.1):
     """scripted motion: the sphere sweeps in +z / -x while spinning (a keyframed TransformSequence sampled per sub-step)"""
     t = 7e-4 * k
     lin = (-0.8, 0.1 * np.cos(40 * t), 2.0)
-    center = (0.1 + lin[0] * t, -0.25 + 0.0025 * np.sin(40 * t), 0.1 + lin[2] * t)
+    center = (0.1 + lin[0] * t, -0.25 + 0.0025 * np.sin(40 * t), z0 + lin[2] * t)
     return tuple(float(np.float64(c)) for c in center), tuple(float(v) for v in lin), (0.0, 25.0, -10.0)
 
 
@@ -110,8 +110,13 @@ def test_update_collider_rejects_type_change_and_bad_index():
 
 
 def test_collider_moving_across_a_slab_cut_matches_single_domain_bit_for_bit():
-    """Every slab engine gets the same update; the sphere travels in +z through the cuts of a 3-slab group."""
+    """Every slab engine gets the same update; the sphere travels in +z through the cuts of a 3-slab group.
+    (It starts just outside the block: a particle deep inside a collider at t = 0 is ejected by up to the sphere's
+    radius = 2 cell planes in one sub-step, more than the one-plane halo of a slab engine can follow -- that case is
+    BBX_ERR_OUT_OF_DOMAIN by design, checked in the last test of this file.)"""
+    Z0 = -0.075
     sc = _scene()
+    sc["colliders"][1]["translate"] = (0.1, -0.25, Z0)
     grid = bb.UtilBuildGridForDomain(sc["domain_min"], sc["domain_max"], sc["spacing"], sc["scale"])
     hist = bb.plane_histogram(grid, sc["pos"])
     zb = bb.plan_slabs(hist, 3)
@@ -126,7 +131,7 @@ def test_collider_moving_across_a_slab_cut_matches_single_domain_bit_for_bit():
     crossed = False
     z_prev = None
     for k in range(90):
-        c, lin, ang = _path(k)
+        c, lin, ang = _path(k, Z0)
         ec, _ = _sphere_at(c, lin, ang)
         one.update_collider(1, ec)
         for e in grp.engines:
@@ -140,7 +145,7 @@ def test_collider_moving_across_a_slab_cut_matches_single_domain_bit_for_bit():
         if z_prev is not None and (z_prev - RADIUS < lo) != (c[2] + RADIUS < lo):
             crossed = True
         z_prev = c[2]
-    assert crossed or (0.1 - RADIUS < lo < _path(89)[0][2] + RADIUS), "the sphere never reached a slab cut"
+    assert crossed or (Z0 - RADIUS < lo < _path(89, Z0)[0][2] + RADIUS), "the sphere never reached a slab cut"
     for f in (bb.POSITION, bb.VELOCITY, bb.DENSITY):
         assert np.array_equal(grp.download(f, np.float32), one.download(f, np.float32)), f"field {f}"
     cc, co = grp.export_cells()
@@ -148,3 +153,28 @@ def test_collider_moving_across_a_slab_cut_matches_single_domain_bit_for_bit():
     assert np.array_equal(cc, c1) and np.array_equal(co, o1)
     grp.close()
     one.close()
+
+
+def test_two_plane_jump_on_a_slab_engine_is_reported_not_silently_dropped():
+    """A particle that moves two cell planes in one sub-step (here: ejected from deep inside a collider) cannot be
+    followed by the one-plane halo of a slab engine.  The single-domain engine takes the reference's route (jump
+    detection -> full rebuild); the slab engine must return BBX_ERR_OUT_OF_DOMAIN from the stepping API instead of
+    stepping on without the particle (device-side errors never reached the caller)."""
+    sc = _scene()                                   # the block starts overlapping the sphere obstacle
+    grid = bb.UtilBuildGridForDomain(sc["domain_min"], sc["domain_max"], sc["spacing"], sc["scale"])
+    zb = bb.plan_slabs(bb.plane_histogram(grid, sc["pos"]), 3)
+    n = len(sc["pos"])
+    grp = bb.LocalSlabGroup(grid, sc["spacing"], sc["scale"], zb, n, ghost_capacity=n)
+    grp.set_colliders(scenes.engine_colliders(sc))
+    grp.set_particles(sc["pos"], sc["vel"])
+    with pytest.raises(bb.BbxError) as ei:
+        for _ in range(4):
+            grp.step_pcisph(sc["dt"])
+    assert ei.value.code == bb.ERR_OUT_OF_DOMAIN
+    # a fresh particle set clears the sticky error
+    calm = scenes.block_scene((0.6, 0.6, 0.6), (0.2, 0.3, 0.2), (0.0, 0.1, 0.0), (0, -1, 0))
+    grp.set_particles(calm["pos"], calm["vel"])
+    for _ in range(3):
+        grp.step_pcisph(sc["dt"])
+    assert all(s.nan_count == 0 for s in grp.stats())
+    grp.close()
