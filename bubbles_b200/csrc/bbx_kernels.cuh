@@ -440,7 +440,7 @@ __device__ __forceinline__ uint4 *bbx_chunk_ptr(unsigned short *__restrict__ nbr
 // consumed); only the last, partial chunk tests k < cnt.  STRIDE = threads per CTA (column stride of sbase).
 // a list chunk is read exactly once per sweep: keep it out of L1, whose lines the scattered gathers want
 __device__ __forceinline__ uint4 bbx_load_chunk(const uint4 *p){
-#ifdef BBX_LIST_NOALLOC
+#ifndef BBX_LIST_L1ALLOC  // (measured: -2..3 % on each of the three sweeps, profiles/r02_notes.md)
     uint4 v;
     asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;

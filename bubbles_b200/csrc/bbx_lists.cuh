@@ -45,7 +45,7 @@
 #define BBX_LW 4                  // warps per CTA = cells per sub-chunk
 #define BBX_LT (BBX_LW * 32)
 #ifndef BBX_G
-#define BBX_G 4                   // own particles per group (registers): 4 or 8
+#define BBX_G 4                   // own particles per group (registers)
 #endif
 #define BBX_G_SHIFT (BBX_G == 8 ? 2 : 3) // lane >> shift = particle whose density total the lane holds after the butterfly
 #ifndef BBX_CMAX
@@ -149,7 +149,11 @@ __device__ __forceinline__ int bbx_list_compact_pool(const StepParams &P, DevSta
 #pragma unroll 1
     for(int k0 = 0; k0 < T; k0 += 32){
         const int f = min(k0 + lane, T - 1);
-        while(f >= W.tab[r + 1]) r++;               // windows only move forward (tab[9] = T > f)
+        // windows only move forward (tab[9] = T > f): 32 candidates further on a lane is at most two non-empty windows on
+        // in a dense neighbourhood -- two predicated steps, then the general loop for what is left (sparse cells)
+        r += (r < 8 && f >= W.tab[r + 1]) ? 1 : 0;
+        r += (r < 8 && f >= W.tab[r + 1]) ? 1 : 0;
+        while(f >= W.tab[r + 1]) r++;
         const int off = f - W.tab[r];
         const float4 raw = pool[W.tab[19 + r] + off];
         float ux, uy, uz;
@@ -163,7 +167,7 @@ __device__ __forceinline__ int bbx_list_compact_pool(const StepParams &P, DevSta
     }
     if(n > BBX_CMAX) return -1;
     bbx_list_pad(W, n, lane);
-    return n;
+    return (n + 31) & ~31; // whole rounds (the padding is never accepted)
 }
 
 // Rare path (neighbourhood too large for the pool / the warp's array): candidates [f0, ...) of the flat order straight
@@ -193,51 +197,63 @@ __device__ __noinline__ int bbx_list_stage_global(const StepParams &P, DevState 
     return n;
 }
 
-// All staged candidates against the group's own particles in registers.  Accumulates cnt / acc over
-// pieces; xmin = smallest x among this lane's accepted pairs.
-template<bool EXACT>
-__device__ __forceinline__ void bbx_list_rounds(const StepParams &P, const ListWarp &W, int nc, int mg, int lane,
+// All staged candidates against NG (2 or 4) own particles of the group in registers.  Accumulates cnt / acc over
+// pieces; xmin = smallest x among this lane's accepted pairs.  The candidate of the NEXT round is in flight while the
+// current one is tested (two register sets, the loop body is written out twice: no copies, no address rebuild).
+__device__ __forceinline__ float4 bbx_lds128(unsigned addr){
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+template<bool EXACT, int NG>
+__device__ __forceinline__ void bbx_list_rounds(const StepParams &P, const ListWarp &W, int nc, int lane,
         const float4 (&q)[BBX_G], const float4 *__restrict__ pos, int (&cnt)[BBX_G], float (&acc)[BBX_G], float &xmin)
 {
+    if(nc <= 0) return;
     const unsigned lt = lanemask_lt();
-    // shared-memory byte address of this warp's list rows, pinned in a register (the compiler otherwise
-    // rebuilds it from special registers in front of every store)
-    unsigned rows_addr;
-    asm volatile("mov.u32 %0, %1;" : "=r"(rows_addr) : "r"((unsigned)__cvta_generic_to_shared(W.rows)));
-    float4 cn = W.cand[lane]; // (nc = 0: never used)
-#pragma unroll 1
-    for(int f0 = 0; f0 < nc; f0 += 32){
-        const float4 cj = cn;
-        if(f0 + 32 < nc) cn = W.cand[f0 + 32 + lane];
+    // shared-memory byte addresses pinned in registers (the compiler otherwise rebuilds them from special registers
+    // in front of every access)
+    unsigned rows_addr, ca;
+    asm volatile("mov.u32 %0, %1;" : "=r"(rows_addr) : "r"(bbx_smem_u32(W.rows)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(ca) : "r"(bbx_smem_u32(W.cand) + 16u * (unsigned)lane));
+    const unsigned ca_end = ca + 16u * (unsigned)nc; // nc is a multiple of 32 (padded)
+    float xacc;
+    asm volatile("mov.f32 %0, %1;" : "=f"(xacc) : "f"(P.xacc));
+    auto round = [&](const float4 cj){
         const float a = fmaf(cj.x, cj.x, fmaf(cj.y, cj.y, cj.z * cj.z));
         const unsigned short entry = (unsigned short)__float_as_uint(cj.w);
 #pragma unroll
-        for(int h = 0; h < BBX_G / 4; h++){
-            if(h * 4 < mg){
-#pragma unroll
-                for(int t = 0; t < 4; t++){
-                    const int ii = h * 4 + t;
-                    const float x = fmaf(cj.x, q[ii].x, fmaf(cj.y, q[ii].y, fmaf(cj.z, q[ii].z, q[ii].w))) - a;
-                    bool in = x > P.xacc;
-                    if(EXACT){
-                        if(in && x < P.xband){
-                            const unsigned e = entry;
-                            in = bbx_within_std_exact(W.spi[ii], pos[W.tab[10 + (e >> BBX_RUN_SHIFT)] + (int)(e & BBX_RUN_MASK)], P.h2_d);
-                        }
-                    }else{
-                        xmin = in ? fminf(xmin, x) : xmin;
-                    }
-                    const unsigned msk = __ballot_sync(BBX_FULL, in);
-                    // list position = entries so far + accepted lanes below this one (flat order); rows have
-                    // 104 slots, the count keeps running so that the cap-100 slow path can be detected
-                    const int k = min(cnt[ii] + __popc(msk & lt), BBX_ROW - 1);
-                    if(in) asm volatile("st.shared.u16 [%0], %1;" :: "r"(rows_addr + (unsigned)(ii * BBX_ROW * 2) + 2u * (unsigned)k), "h"(entry) : "memory");
-                    cnt[ii] += __popc(msk);
-                    const float x2 = x * x;
-                    acc[ii] = in ? fmaf(x2, x, acc[ii]) : acc[ii];
+        for(int ii = 0; ii < NG; ii++){
+            const float x = fmaf(cj.x, q[ii].x, fmaf(cj.y, q[ii].y, fmaf(cj.z, q[ii].z, q[ii].w))) - a;
+            bool in = x > xacc;
+            if(EXACT){
+                if(in && x < P.xband){
+                    const unsigned e = entry;
+                    in = bbx_within_std_exact(W.spi[ii], pos[W.tab[10 + (e >> BBX_RUN_SHIFT)] + (int)(e & BBX_RUN_MASK)], P.h2_d);
                 }
+            }else{
+                if(in) xmin = fminf(xmin, x);
             }
+            const unsigned msk = __ballot_sync(BBX_FULL, in);
+            // list position = entries so far + accepted lanes below this one (flat order); rows have
+            // 104 slots, the count keeps running so that the cap-100 slow path can be detected
+            const int k = min(cnt[ii] + __popc(msk & lt), BBX_ROW - 1);
+            if(in) asm volatile("st.shared.u16 [%0], %1;" :: "r"(rows_addr + (unsigned)(ii * BBX_ROW * 2) + 2u * (unsigned)k), "h"(entry) : "memory");
+            cnt[ii] += __popc(msk);
+            const float x2 = x * x;
+            acc[ii] = in ? fmaf(x2, x, acc[ii]) : acc[ii];
         }
+    };
+    float4 c0 = bbx_lds128(ca), c1 = c0;
+#pragma unroll 1
+    for(;;){
+        if(ca + 512u < ca_end) c1 = bbx_lds128(ca + 512u);
+        round(c0);
+        if(ca + 512u >= ca_end) break;
+        if(ca + 1024u < ca_end) c0 = bbx_lds128(ca + 1024u);
+        round(c1);
+        ca += 1024u;
+        if(ca >= ca_end) break;
     }
 }
 
@@ -252,13 +268,15 @@ __device__ __forceinline__ bool bbx_list_group(const StepParams &P, DevState *st
     for(int ii = 0; ii < BBX_G; ii++){ acc[ii] = 0.f; cnt[ii] = 0; }
     float xmin = 1.0e30f;
     if(nc >= 0){
-        bbx_list_rounds<EXACT>(P, W, nc, mg, lane, q, pos, cnt, acc, xmin);
+        // a tail group of 1 or 2 particles tests 2 slots instead of 4
+        if(mg > 2) bbx_list_rounds<EXACT, BBX_G>(P, W, nc, lane, q, pos, cnt, acc, xmin);
+        else bbx_list_rounds<EXACT, 2>(P, W, nc, lane, q, pos, cnt, acc, xmin);
     }else{
         int f0 = 0;
 #pragma unroll 1
         while(f0 < T){
             const int n = bbx_list_stage_global(P, st, W, T, lane, &f0, F, pos);
-            bbx_list_rounds<EXACT>(P, W, n, mg, lane, q, pos, cnt, acc, xmin);
+            bbx_list_rounds<EXACT, BBX_G>(P, W, (n + 31) & ~31, lane, q, pos, cnt, acc, xmin);
         }
     }
     return __any_sync(BBX_FULL, xmin < P.xband);

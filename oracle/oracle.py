@@ -83,6 +83,7 @@ def lib():
         L.orc_pcisph_substep.argtypes = [C.POINTER(Params), C.POINTER(State), C.c_double, C.c_int, C.c_int,
                                          C.c_double]
         L.orc_sph_substep.argtypes = [C.POINTER(Params), C.POINTER(State), C.c_double]
+        L.orc_sph_substep_gs.argtypes = [C.POINTER(Params), C.POINTER(State), C.c_double]
         _lib = L
     return _lib
 
@@ -276,7 +277,13 @@ class Oracle:
         return self.L.orc_pcisph_substep(C.byref(self.P), C.byref(self.S), dt, int(compat), max_it, max_err_ratio)
 
     def substep_sph(self, dt):
+        """AdvanceTimeStep(SphSolver3*) in the race-free Jacobi form the engine implements"""
         self.L.orc_sph_substep(C.byref(self.P), C.byref(self.S), dt)
+
+    def substep_sph_gs(self, dt):
+        """the same sub-step exactly as the reference's CPU path runs it on ONE thread: particles in ascending id, each
+        integrated inside its force evaluation (Gauss-Seidel) -- pinned bit-exactly against bbref (sph_run.npz)"""
+        self.L.orc_sph_substep_gs(C.byref(self.P), C.byref(self.S), dt)
 
     def trace_pcisph(self, dt):
         """One compat sub-step phase by phase; returns dict of per-phase arrays (copies)."""

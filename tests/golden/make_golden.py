@@ -228,6 +228,28 @@ def sdf_run():
           int((np.abs(data["s150_vel"][:, 0]) > 1e-3).sum()))
 
 
+def sph_run():
+    """SphSolver3 (BASELINE configs[0]'s solver, src/solvers/sph_solver3.cpp:48-67) on ONE thread -- the only deterministic
+    mode of its CPU path: ComputeAllForcesFor integrates every particle inside its own force evaluation
+    (src/equations/sph_equations3.cpp:184-278), so with one thread particle i sees the moved neighbours j < i
+    (Gauss-Seidel).  Probe scene with a sphere obstacle on the floor, fixed dt = 0.4 h / c_s = 1.44e-4: state after 1,
+    20 and 120 sub-steps (the block reaches the floor and the sphere), chains and lists of sub-step 1."""
+    job = ["solver sph", "threads 1", "spacing 0.02", "scale 1.8", f"collider box {I} 0.6 0.6 0.6 1 0",
+           f"collider sphere {T(0.1, -0.27, 0.1)} 0.08 0 0.2", "domain_from_collider 0",
+           f"emit_box {T(0.1, -0.02, 0.1)} 0.2 0.3 0.2 0 -6 0 0.001 1", "setup", "dump {wd}/s0_",
+           "step 1.44e-4 1", "dump {wd}/s1_", "dump_grid {wd}/s1_", "step 1.44e-4 19", "dump {wd}/s20_",
+           "step 1.44e-4 100", "dump {wd}/s120_", "dump_grid {wd}/s120_"]
+    out, wd = O.run_ref(job)
+    data = {}
+    for pre, names in (("s0_", ["pos", "vel"]), ("s1_", ["pos", "vel", "force", "density", "pressure", "cell_count", "cell_order", "nbr_count"]),
+                       ("s20_", ["pos", "vel", "force", "density", "pressure"]),
+                       ("s120_", ["pos", "vel", "force", "density", "pressure", "cell_count", "cell_order", "nbr_count"])):
+        for k, v in load_all(wd, pre, names).items():
+            data[pre + k] = v
+    np.savez_compressed(os.path.join(HERE, "sph_run.npz"), **data)
+    print("sph_run", len(data["s0_pos"]), "particles")
+
+
 def grid_facts():
     """UtilBuildGridForDomain results printed by the reference for several domains / spacings."""
     rows = []
@@ -249,6 +271,7 @@ def grid_facts():
 if __name__ == "__main__":
     assert O.ref_available(), "run oracle/build_ref.sh first"
     probe_trace()
+    sph_run()
     collider_vectors()
     obstacle_run()
     append_run()

@@ -254,6 +254,40 @@ def test_sph_step_matches_jacobi_oracle():
     assert np.abs(eng.download(bb.DENSITY) - orc.a["density"]).max() / 1000.0 < 10 * TOL_RHO
 
 
+def test_sph_step_against_the_reference_run_golden():
+    """a20 pinned: tests/golden/sph_run.npz is the UNMODIFIED reference's SphSolver3 on one thread (Gauss-Seidel, the only
+    deterministic mode of its CPU path; the oracle's restatement of it is bit-exact, test_oracle_vs_reference.py).  The
+    engine runs the race-free Jacobi form: density and EOS pressure of the first sub-step within the FP32 tolerance of the
+    reference's own values, trajectories within the stated Jacobi-vs-Gauss-Seidel bound, Chamfer distance
+    as in the reference's resources/chamfer.py."""
+    import os
+    from scipy.spatial import KDTree
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sph_run.npz"))
+    sc = scenes.probe_scene()
+    sc["colliders"] = sc["colliders"] + [dict(kind="sphere", radius=0.08, translate=(0.1, -0.27, 0.1), friction=0.2)]
+    sc["pos"], sc["vel"] = scenes.f32(g["s0_pos"]), scenes.f32(g["s0_vel"])
+    eng = scenes.make_engine(sc)
+    eng.set_particles(sc["pos"], sc["vel"])
+    dt, s = 1.44e-4, sc["spacing"]
+    eng.step_sph(dt)
+    # (the positions were rounded to FP32 on the way in: 6e-8 relative, amplified by the stiff Tait EOS in the pressure)
+    assert np.abs(eng.download(bb.DENSITY) - g["s1_density"]).max() / 1000.0 < 10 * TOL_RHO
+    pmax = np.abs(g["s1_pressure"]).max()
+    assert np.abs(eng.download(bb.PRESSURE) - g["s1_pressure"]).max() / pmax < 5e-3
+    assert np.array_equal(eng.download(bb.NEIGHBOR_COUNT), g["s1_nbr_count"])
+    eng.step_many(dt, 19, bb.SOLVER_SPH)
+    d = np.linalg.norm(eng.download(bb.POSITION) - g["s20_pos"], axis=1)
+    assert d.max() <= 0.03 * s, d.max() / s
+    eng.step_many(dt, 100, bb.SOLVER_SPH)
+    p = eng.download(bb.POSITION)
+    d = np.linalg.norm(p - g["s120_pos"], axis=1)
+    assert d.max() <= 0.25 * s, d.max() / s
+    ch = KDTree(p).query(g["s120_pos"])[0].mean() + KDTree(g["s120_pos"]).query(p)[0].mean()
+    assert ch <= 0.1 * s, ch / s
+    assert eng.stats().nan_count == 0
+    eng.close()
+
+
 def test_advance_cfl_substep_count_matches_oracle():
     sc = scenes.probe_scene()
     eng, orc = _pair(sc)
