@@ -105,12 +105,19 @@ struct DevState {
     int max_candidates;  // largest 27-cell neighbourhood seen in the last list build
     int unstaged_tiles;  // sweep tiles (all three sweeps) whose neighbourhood exceeded the shared-memory stage
     int cap;             // particle capacity of the engine (owned slots): the fill / scatter kernels refuse to write past it
+    // slab engines: what the kernels need to know about the ghost planes, kept ON THE DEVICE so that no sub-step waits for
+    // the host (k_slab_plan writes them from the neighbours' mailboxes; the host reads them back lazily)
+    int n_glo, n_ghi;    // particles in the lower / upper ghost plane
+    int peer_n[2];       // owned particles of the lower / upper neighbour (where my boundary planes start in ITS slot space)
+    int gcap;            // ghost slots per side of this engine
+    int n_own_prev;      // owned particles BEFORE the running grid update (the scan overwrites n_own; the full rebuild walks the old slots)
 };
 
 // Scalars of one sub-step, passed by value to every kernel.
 struct StepParams {
-    int n;              // particles on this device (owned + ghosts)
+    int n;              // launch bound of the per-particle kernels (>= owned particles; the kernels read the count from dyn)
     int n_owned;
+    const DevState *dyn; // the engine's DevState: dyn->n_own = owned particles after the last grid update
     float h, h2, inv_h, inv_h2;
     float thr2;         // h^2 - 1e-8: acceptance threshold of IsWithinStd on d^2
     float band;         // guard band around thr2 inside which the predicate is re-evaluated in FP64
@@ -483,7 +490,17 @@ __device__ __forceinline__ bool bbx_inside_domain_certain(const DevCullSet &cs, 
 struct HaloDst {
     float4 *lo[2], *hi[2];
     int n_first, lo_base, hi_begin, n;
+    int has_lo, has_hi; // a neighbour exists on that side and takes pushed results
 };
+// the counts live in DevState (no host round trip in the slab grid update): every kernel that pushes resolves them once
+__device__ __forceinline__ HaloDst bbx_halo_resolve(HaloDst h, const DevState *st){
+    if(h.has_lo | h.has_hi){
+        h.n = st->n_own;
+        h.n_first = h.has_lo ? st->n_first : 0; h.lo_base = st->peer_n[0];
+        h.hi_begin = h.has_hi ? st->n_own - st->n_last : 0x7fffffff;
+    }
+    return h;
+}
 // float4 k of the `rec`-float4 record of slot i, array `which`
 __device__ __forceinline__ void bbx_halo_store(const HaloDst &h, int which, int rec, int i, int k, float4 v){
     if(i < h.n_first) h.lo[which][(size_t)(h.lo_base + i) * rec + k] = v;

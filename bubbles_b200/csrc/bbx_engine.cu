@@ -73,6 +73,8 @@ struct bbx_engine {
     DevState *st; DevState *st_host; // st_host pinned
     int *err_probe;  // pinned: copy of st->error enqueued behind every sub-step (no sync); checked by the next API call
     int sm_count;    // multiprocessors of the device (persistent grids are sized from it)
+    int counts_stale;   // slab engines with the halo push: n / n_first / n_last / ghost counts live in DevState; the host copies
+                        // (e->n ...) are refreshed by sync_counts() when an API call needs them
     int deferred_error; // slab engines: a device-side error seen in the middle of a collective sub-step; the sub-step is
                         // finished (so that the neighbours are not left waiting for this rank's halo signals), then returned
     DevColliderSet *colliders; DevColliderSet colliders_host;
@@ -110,6 +112,14 @@ static int sticky_error(bbx_engine *e){
     const int code = e->err_probe ? *(volatile int *)e->err_probe : 0;
     if(code) return set_error(code, "device-side error %d (%s)", code, device_error_text(code));
     return BBX_OK;
+}
+// entry of a sub-step.  On a slab engine a particle that left the halo (BBX_ERR_OUT_OF_DOMAIN: dropped by the hash kernel,
+// the state stays consistent) must not make this rank skip a collective sub-step its neighbours are about to wait in:
+// the sub-step runs and the code is returned on the way out (deferred_error).
+static int entry_error(bbx_engine *e){
+    const int code = e->err_probe ? *(volatile int *)e->err_probe : 0;
+    if(code == BBX_ERR_OUT_OF_DOMAIN && (e->has_lo || e->has_hi)){ e->deferred_error = code; return BBX_OK; }
+    return sticky_error(e);
 }
 static void probe_error(bbx_engine *e){
     if(e->err_probe) cudaMemcpyAsync(e->err_probe, &e->st->error, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
@@ -182,7 +192,7 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     e->cfg = *cfg;
     e->device = cfg->device;
     e->n = 0; e->cap = cfg->max_particles; e->cur = 0; e->have_chains = 0; e->launches = 0; e->substeps = 0; e->epoch = 0;
-    e->timing = 0; e->ev_used = 0; e->force_full = 1; e->stage = nullptr; e->stage_bytes = 0; e->deferred_error = 0;
+    e->timing = 0; e->ev_used = 0; e->force_full = 1; e->stage = nullptr; e->stage_bytes = 0; e->deferred_error = 0; e->counts_stale = 0;
     e->last_ms_grid = e->last_ms_step = 0.f;
     memset(e->phase_ms, 0, sizeof(e->phase_ms)); memset(e->phase_launches, 0, sizeof(e->phase_launches));
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -280,7 +290,7 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     CU(cudaMallocHost((void **)&e->err_probe, sizeof(int)));
     *e->err_probe = 0;
     memset(e->st_host, 0, sizeof(DevState));
-    e->st_host->cap = e->cap;
+    e->st_host->cap = e->cap; e->st_host->gcap = e->gcap;
     CU(cudaMemcpy(e->st, e->st_host, sizeof(DevState), cudaMemcpyHostToDevice));
     memset(&e->colliders_host, 0, sizeof(DevColliderSet));
     CU(cudaMemset(e->colliders, 0, sizeof(DevColliderSet)));
@@ -361,6 +371,21 @@ static int grid_update(bbx_engine *e);
 #define IS_SLAB(e) ((e)->has_lo || (e)->has_hi)
 #define COMM(call) do{ if((call)) return set_error(BBX_ERR_COMM, "%s", e->comm->err.c_str()); }while(0)
 
+// Slab engines keep their particle counts on the device (DevState) and launch the per-particle kernels over the capacity;
+// the host copies are brought up to date only when an API call needs exact numbers (downloads, exports, the send / recv
+// transport of the cold paths).
+static inline int launch_n(const bbx_engine *e){ return IS_SLAB(e) ? e->cap : e->n; }
+static int sync_counts(bbx_engine *e){
+    if(!e->counts_stale) return BBX_OK;
+    int rc = read_state(e); if(rc) return rc;
+    const DevState &s = *e->st_host;
+    e->n = s.n_own; e->n_first = s.n_first; e->n_last = s.n_last; e->n_glo = s.n_glo; e->n_ghi = s.n_ghi;
+    e->peer[0].n = s.peer_n[0]; e->peer[1].n = s.peer_n[1];
+    e->counts_stale = 0;
+    if(s.error == BBX_ERR_CAPACITY) return set_error(BBX_ERR_CAPACITY, "slab capacity exceeded: %d owned (max_particles %d), ghost planes %d / %d (ghost_capacity %d)", s.n_own, e->cap, s.n_glo, s.n_ghi, e->gcap);
+    return BBX_OK;
+}
+
 static int upload_particles(bbx_engine *e, int first, int n, const void *pos, const void *vel, const int *ids, int dtype){
     if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "dtype must be BBX_F32 or BBX_F64");
     size_t esz = dtype == BBX_F64 ? 8 : 4;
@@ -395,7 +420,8 @@ static int set_particles(bbx_engine *e, int n, const void *pos, const void *vel,
     // a fresh particle set starts with a clean slate: the sticky device error of an earlier set is dropped
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaMemsetAsync(&e->st->error, 0, sizeof(int), e->stream));
-    *e->err_probe = 0; e->st_host->error = 0; e->deferred_error = 0;
+    CU(cudaMemsetAsync(&e->st->n_glo, 0, 4 * sizeof(int), e->stream)); // n_glo, n_ghi, peer_n[2]: no ghosts yet
+    *e->err_probe = 0; e->st_host->error = 0; e->deferred_error = 0; e->counts_stale = 0;
     if(n == 0 && !IS_SLAB(e)) return BBX_OK;
     int rc;
     if(n > 0){ rc = upload_particles(e, 0, n, pos, vel, ids, dtype); if(rc) return rc; }
@@ -455,7 +481,11 @@ int bbx_append_particles(bbx_engine *e, int n, const void *pos, const void *vel,
     return append_update(e, n_old, n);
 }
 
-int bbx_particle_count(bbx_engine *e, int *n){ if(!e || !n) return set_error(BBX_ERR_INVALID, "null"); *n = e->n; return BBX_OK; }
+int bbx_particle_count(bbx_engine *e, int *n){
+    if(!e || !n) return set_error(BBX_ERR_INVALID, "null");
+    if(e->counts_stale){ CU(cudaSetDevice(e->device)); int rc = sync_counts(e); if(rc) return rc; }
+    *n = e->n; return BBX_OK;
+}
 
 int bbx_overwrite_state(bbx_engine *e, const void *pos, const void *vel, int dtype){
     CHECK_ENGINE(e);
@@ -476,6 +506,7 @@ int bbx_overwrite_state(bbx_engine *e, const void *pos, const void *vel, int dty
 static int exchange2(bbx_engine *e, float4 *a, float4 *b);
 int bbx_overwrite_owned(bbx_engine *e, const void *pos, const void *vel, int dtype){
     CHECK_ENGINE(e);
+    { int rc_ = sync_counts(e); if(rc_) return rc_; }
     if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "dtype must be BBX_F32 or BBX_F64");
     if(e->n > 0){
         if(!pos || !vel) return set_error(BBX_ERR_INVALID, "null");
@@ -634,7 +665,7 @@ static void harvest(bbx_engine *e){
 static void make_params(bbx_engine *e, double dt, StepParams &P){
     const bbx_config &c = e->cfg;
     double h = e->h, pi = 3.14159265358979323846;
-    P.n = e->n; P.n_owned = e->n;
+    P.n = launch_n(e); P.n_owned = P.n; P.dyn = e->st;
     P.h = (float)h; P.h2 = (float)(h * h); P.inv_h = (float)(1.0 / h); P.inv_h2 = (float)(1.0 / (h * h));
     P.h_d = h; P.h2_d = h * h;
     P.thr2 = (float)(h * h - 1e-8);
@@ -669,6 +700,7 @@ static void make_params(bbx_engine *e, double dt, StepParams &P){
 // are contiguous because slots are sorted by cell id and z is the slowest cell index -- no pack kernels.
 static int exchange_planes(bbx_engine *e, void *const *arr, const size_t *esz, int narr){
     if(!IS_SLAB(e)) return BBX_OK;
+    { int rc = sync_counts(e); if(rc) return rc; } // (send / recv sizes are host values)
     BbxSeg slo[BBX_MAX_SEGS], rlo[BBX_MAX_SEGS], shi[BBX_MAX_SEGS], rhi[BBX_MAX_SEGS];
     for(int k = 0; k < narr; k++){
         char *base = (char *)arr[k]; size_t z = esz[k];
@@ -690,9 +722,7 @@ static HaloDst halo_dst(bbx_engine *e, float4 *lo0, float4 *hi0, float4 *lo1 = n
     HaloDst h = halo_none();
     if(!e->p2p) return h;
     h.lo[0] = lo0; h.hi[0] = hi0; h.lo[1] = lo1; h.hi[1] = hi1;
-    h.n = e->n;
-    h.n_first = e->has_lo ? e->n_first : 0; h.lo_base = e->peer[0].n;
-    h.hi_begin = e->has_hi ? e->n - e->n_last : 0x7fffffff;
+    h.has_lo = e->has_lo; h.has_hi = e->has_hi; // the plane sizes are resolved on the device (bbx_halo_resolve)
     return h;
 }
 // end of a phase whose kernels pushed their boundary planes: raise my flag at both neighbours, wait for theirs
@@ -745,12 +775,16 @@ static int grid_update(bbx_engine *e){
     if(e->n == 0 && !slab) return BBX_OK;
     if(slab && !e->peers_ready){ int rc = setup_peers(e); if(rc) return rc; }
     DevGrid &g = e->grid;
-    int n_all = e->n_glo + e->n + e->n_ghi, cur = e->cur, nxt = cur ^ 1;
+    const int cur = e->cur, nxt = cur ^ 1;
+    // single domain: the host knows the counts.  Slab engines: they live in DevState (n_all = -1 tells the kernels to read
+    // them there) and the launches cover the capacity -- nothing below waits for the host when the halo push is on.
+    const int n_all = slab ? -1 : e->n, n_lo = slab ? 0 : 0, n_own = slab ? 0 : e->n;
+    const int n_bound = slab ? e->cap + 2 * e->gcap : e->n;
     int force = (e->force_full || !e->have_chains) ? 1 : 0;
     int par = e->epoch & 1;
     const int own_cells = g.c_own1 - g.c_own0;
     if(!force) CU(cudaMemsetAsync(e->movemask, 0, sizeof(unsigned) * (size_t)g.total, e->stream));
-    LAUNCH(e, k_hash_count, div_up(std::max(std::max(n_all, e->scan_tiles), 1), 256), 256, n_all, e->n_glo, e->n, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st,
+    LAUNCH(e, k_hash_count, div_up(std::max(std::max(n_bound, e->scan_tiles), 1), 256), 256, n_all, n_lo, n_own, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st,
            force ? 0 : 1, par, e->scan_status, e->scan_tiles, e->movemask);
     // the big-move rule and the jump detection are global decisions (the reference rebuilds ALL chains): the
     // flags are reduced over the ranks on a side stream while the scan and the (speculative) fill run
@@ -763,7 +797,7 @@ static int grid_update(bbx_engine *e){
     LAUNCH(e, k_scan_cells, e->scan_tiles, 256, e->count + g.c_own0, own_cells, g.c_own0, e->scan_status, e->st, e->cell_start[nxt] + g.c_own0, e->occ_cells);
     if(!force){
         // persistent grid: 8 lanes per occupied cell, grid-stride over the compact list of occupied cells
-        int groups = std::max(1, std::min(n_all, own_cells));
+        int groups = std::max(1, std::min(n_bound, own_cells));
         int blocks = std::min(div_up((long long)groups * 8, 256), e->sm_count * 8);
         LAUNCH(e, k_fill_incremental, blocks, 256, g, e->st, par, slab ? 1 : 0, e->occ_cells, e->cell_start[cur], e->cell_start[nxt], e->newcell,
                e->pos[cur], e->vel[cur], e->pid[cur], e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec, e->movemask);
@@ -771,9 +805,9 @@ static int grid_update(bbx_engine *e){
     if(slab) CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
     // full path (forced, or selected on the device by the big-move / jump flags); small grids when it is
     // only a flag check
-    int fb_n = force ? div_up(std::max(n_all, 1), 256) : std::min(div_up(std::max(n_all, 1), 256), BBX_CHECK_GRID);
+    int fb_n = force ? div_up(std::max(n_bound, 1), 256) : std::min(div_up(std::max(n_bound, 1), 256), BBX_CHECK_GRID);
     int fb_c = force ? div_up(own_cells, 256) : std::min(div_up(own_cells, 256), BBX_CHECK_GRID);
-    LAUNCH(e, k_full_scatter, fb_n, 256, n_all, e->n_glo, g, e->st, par, force, e->newcell, e->cell_start[nxt], e->count, e->perm);
+    LAUNCH(e, k_full_scatter, fb_n, 256, n_all, n_lo, g, e->st, par, force, e->newcell, e->cell_start[nxt], e->count, e->perm);
     LAUNCH(e, k_full_sort_cells, fb_c, 256, g, e->st, par, force, e->cell_start[nxt], e->pid[cur], e->perm, e->count);
     LAUNCH(e, k_full_gather, fb_n, 256, e->st, par, force, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
            e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec);
@@ -783,74 +817,52 @@ static int grid_update(bbx_engine *e){
         // planes' old chains (in the reference's order), particles that left simply were not placed.
         // Now the ghost planes are replaced by the neighbours' freshly ordered boundary planes.
         const size_t tb = sizeof(int) * ((size_t)g.plane + 1);
-        int n_new, nf, nl, glo = 0, ghi = 0;
         if(e->p2p){
-            // sizes travel through the neighbours' mailboxes (peer memory), one host round trip in total
+            // sizes travel through the neighbours' mailboxes (peer memory) and stay on the device: k_slab_counts posts mine,
+            // k_slab_plan reads theirs into DevState, k_push_planes takes its ranges from there -- no host round trip
             int *mail = (int *)(e->halo_flags + 2 * BBX_HALO_PHASES);
             int *mlo = e->has_lo ? (int *)(e->peer[0].flags + 2 * BBX_HALO_PHASES) + 1 * BBX_HALO_MAIL : nullptr; // I am its UPPER side
             int *mhi = e->has_hi ? (int *)(e->peer[1].flags + 2 * BBX_HALO_PHASES) + 0 * BBX_HALO_MAIL : nullptr;
             const unsigned seq = ++e->halo_seq[HALO_COUNTS];
             LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, mlo, mhi, halo_flag_at(e, 0, HALO_COUNTS), halo_flag_at(e, 1, HALO_COUNTS), seq);
             int rc = halo_wait(e, HALO_COUNTS, seq); if(rc) return rc;
-            CU(cudaMemcpyAsync(e->mail_host, mail, sizeof(int) * 2 * BBX_HALO_MAIL, cudaMemcpyDeviceToHost, e->stream));
-            rc = read_state(e); if(rc) return rc;
-            n_new = e->st_host->n_own; nf = e->st_host->n_first; nl = e->st_host->n_last;
-            if(e->st_host->error == BBX_ERR_COMM) return set_error(BBX_ERR_COMM, "a slab neighbour never signalled its boundary-plane counts");
-            if(e->has_lo){ glo = e->mail_host[0]; e->peer[0].n = e->mail_host[1]; }
-            if(e->has_hi){ ghi = e->mail_host[BBX_HALO_MAIL]; e->peer[1].n = e->mail_host[BBX_HALO_MAIL + 1]; }
+            LAUNCH(e, k_slab_plan, 1, 1, e->st, mail, e->has_lo, e->has_hi, (int)std::min<long long>(e->peer[0].gc, 0x7fffffff), (int)std::min<long long>(e->peer[1].gc, 0x7fffffff));
+            // my freshly ordered boundary planes -> the neighbours' ghost slots (their table slices: lower ghost
+            // plane at gtab, upper one at gtab + plane + 1), then the planes flag
+            PushPtrs Q; memset(&Q, 0, sizeof(Q));
+            Q.has_lo = e->has_lo; Q.has_hi = e->has_hi; Q.plane = g.plane;
+            Q.tab_first = e->cell_start[nxt] + g.c_own0; Q.tab_last = e->cell_start[nxt] + g.c_own1 - g.plane;
+            Q.pos = e->pos[nxt]; Q.vel = e->vel[nxt]; Q.pid = e->pid[nxt];
+            if(e->has_lo){ const bbx_engine::PeerSide &p = e->peer[0]; Q.gtab_lo = p.gtab + g.plane + 1; Q.pos_lo = p.pos[nxt]; Q.vel_lo = p.vel[nxt]; Q.pid_lo = p.pid[nxt]; }
+            if(e->has_hi){ const bbx_engine::PeerSide &p = e->peer[1]; Q.gtab_hi = p.gtab; Q.pos_hi = p.pos[nxt]; Q.vel_hi = p.vel[nxt]; Q.pid_hi = p.pid[nxt]; }
+            LAUNCH(e, k_push_planes, e->sm_count, 256, Q, e->st);
+            rc = halo_sync(e, HALO_PLANES); if(rc) return rc;
+            e->counts_stale = 1;
         }else{
             LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, (int *)nullptr, (int *)nullptr, (unsigned *)nullptr, (unsigned *)nullptr, 0u);
             int rc = read_state(e); if(rc) return rc;
-            n_new = e->st_host->n_own; nf = e->st_host->n_first; nl = e->st_host->n_last;
+            const int n_new = e->st_host->n_own, nf = e->st_host->n_first, nl = e->st_host->n_last;
             // boundary-plane sizes (the next exchange) and owned counts
             const int to_lo[BBX_NCOUNTS] = {nf, n_new}, to_hi[BBX_NCOUNTS] = {nl, n_new};
             int from_lo[BBX_NCOUNTS], from_hi[BBX_NCOUNTS];
             COMM(e->comm->neighbor_counts(e->stream, to_lo, to_hi, from_lo, from_hi));
-            glo = from_lo[0]; ghi = from_hi[0]; e->peer[0].n = from_lo[1]; e->peer[1].n = from_hi[1];
-        }
-        if(n_new > e->cap) return set_error(BBX_ERR_CAPACITY, "slab now owns %d particles, max_particles is %d", n_new, e->cap);
-        if(glo > e->gcap || ghi > e->gcap) return set_error(BBX_ERR_CAPACITY, "ghost plane of %d particles exceeds ghost_capacity %d", std::max(glo, ghi), e->gcap);
-        // sender side of the same rule: my boundary planes must fit the NEIGHBOURS' ghost slots (their capacity came with
-        // share_arrays).  Both ends of a cut see the same numbers, so both refuse here and nothing is written past an allocation.
-        if(e->p2p && ((e->has_lo && nf > e->peer[0].gc) || (e->has_hi && nl > e->peer[1].gc)))
-            return set_error(BBX_ERR_CAPACITY, "boundary plane of %d particles exceeds the neighbour's ghost_capacity %lld",
-                             (e->has_lo && nf > e->peer[0].gc) ? nf : nl, (e->has_lo && nf > e->peer[0].gc) ? e->peer[0].gc : e->peer[1].gc);
-        // any other device-side failure (halo time-out, run overflow) stops the run here; a particle that left the slab's halo
-        // (dropped by the hash kernel) lets the collective sub-step finish first -- every signal the neighbours wait for is
-        // still sent -- and is reported by the stepping call on its way out
-        if(e->st_host->error == BBX_ERR_OUT_OF_DOMAIN) e->deferred_error = BBX_ERR_OUT_OF_DOMAIN;
-        else if(e->st_host->error) return set_error(e->st_host->error, "device-side error %d (%s)", e->st_host->error, device_error_text(e->st_host->error));
-        if(e->p2p){
-            // my freshly ordered boundary planes -> the neighbours' ghost slots (their table slices: lower ghost
-            // plane at gtab, upper one at gtab + plane + 1), then the planes flag
-            PushSegs S; memset(&S, 0, sizeof(S));
-            auto add = [&](const void *src, void *dst, size_t bytes){ if(bytes){ S.src[S.n] = src; S.dst[S.n] = dst; S.bytes[S.n] = (long long)bytes; S.n++; } };
-            if(e->has_lo){
-                const bbx_engine::PeerSide &p = e->peer[0];
-                add(e->cell_start[nxt] + g.c_own0, p.gtab + g.plane + 1, tb);
-                add(e->pos[nxt], p.pos[nxt] + p.n, sizeof(float4) * (size_t)nf);
-                add(e->vel[nxt], p.vel[nxt] + p.n, sizeof(float4) * (size_t)nf);
-                add(e->pid[nxt], p.pid[nxt] + p.n, sizeof(int) * (size_t)nf);
-            }
-            if(e->has_hi){
-                const bbx_engine::PeerSide &p = e->peer[1];
-                add(e->cell_start[nxt] + g.c_own1 - g.plane, p.gtab, tb);
-                add(e->pos[nxt] + (n_new - nl), p.pos[nxt] - nl, sizeof(float4) * (size_t)nl);
-                add(e->vel[nxt] + (n_new - nl), p.vel[nxt] - nl, sizeof(float4) * (size_t)nl);
-                add(e->pid[nxt] + (n_new - nl), p.pid[nxt] - nl, sizeof(int) * (size_t)nl);
-            }
-            LAUNCH(e, k_push_planes, e->sm_count, 256, S);
-            int rc = halo_sync(e, HALO_PLANES); if(rc) return rc;
-        }else{
+            const int glo = from_lo[0], ghi = from_hi[0]; e->peer[0].n = from_lo[1]; e->peer[1].n = from_hi[1];
+            if(n_new > e->cap) return set_error(BBX_ERR_CAPACITY, "slab now owns %d particles, max_particles is %d", n_new, e->cap);
+            if(glo > e->gcap || ghi > e->gcap) return set_error(BBX_ERR_CAPACITY, "ghost plane of %d particles exceeds ghost_capacity %d", std::max(glo, ghi), e->gcap);
+            LAUNCH(e, k_slab_plan_host, 1, 1, e->st, glo, ghi, e->peer[0].n, e->peer[1].n);
             BbxSeg slo[4] = {{e->cell_start[nxt] + g.c_own0, tb}, {e->pos[nxt], sizeof(float4) * (size_t)nf}, {e->vel[nxt], sizeof(float4) * (size_t)nf}, {e->pid[nxt], sizeof(int) * (size_t)nf}};
             BbxSeg rlo[4] = {{e->gtab, tb}, {e->pos[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->vel[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->pid[nxt] - glo, sizeof(int) * (size_t)glo}};
             BbxSeg shi[4] = {{e->cell_start[nxt] + g.c_own1 - g.plane, tb}, {e->pos[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->vel[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->pid[nxt] + (n_new - nl), sizeof(int) * (size_t)nl}};
             BbxSeg rhi[4] = {{e->gtab + g.plane + 1, tb}, {e->pos[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->vel[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->pid[nxt] + n_new, sizeof(int) * (size_t)ghi}};
             COMM(e->comm->exchange(e->stream, slo, rlo, 4, shi, rhi, 4));
+            e->n = n_new; e->n_first = nf; e->n_last = nl; e->n_glo = glo; e->n_ghi = ghi;
+            // a particle that left the slab's halo (dropped by the hash kernel) lets the collective sub-step finish first -- every
+            // exchange the neighbours wait for still happens -- and is reported by the stepping call on its way out
+            if(e->st_host->error == BBX_ERR_OUT_OF_DOMAIN) e->deferred_error = BBX_ERR_OUT_OF_DOMAIN;
+            else if(e->st_host->error) return set_error(e->st_host->error, "device-side error %d (%s)", e->st_host->error, device_error_text(e->st_host->error));
         }
-        LAUNCH(e, k_ghost_table, div_up(g.plane, 256), 256, g, n_new, e->has_lo, e->has_hi, e->gtab, e->gtab + g.plane + 1, e->cell_start[nxt], e->cell[nxt], e->count);
+        LAUNCH(e, k_ghost_table, div_up(g.plane, 256), 256, g, e->st, e->has_lo, e->has_hi, e->gtab, e->gtab + g.plane + 1, e->cell_start[nxt], e->cell[nxt], e->count);
         CU(cudaGetLastError());
-        e->n = n_new; e->n_first = nf; e->n_last = nl; e->n_glo = glo; e->n_ghi = ghi;
     }
     e->cur = nxt;
     e->have_chains = 1;
@@ -861,12 +873,12 @@ static int grid_update(bbx_engine *e){
 
 // persistent grid of the list build: one warp per occupied cell, grid-stride over the occupied-cell list
 static int list_blocks(bbx_engine *e){
-    long long cells = std::min<long long>(e->n, e->grid.c_own1 - e->grid.c_own0);
+    long long cells = std::min<long long>(launch_n(e), e->grid.c_own1 - e->grid.c_own0);
     return (int)std::max<long long>(1, std::min<long long>((cells + BBX_LW - 1) / BBX_LW, (long long)e->sm_count * e->list_ctas_per_sm));
 }
 static int phase_density(bbx_engine *e, const StepParams &P, int sph){
     int cur = e->cur;
-    if(e->n > 0){
+    if(launch_n(e) > 0){
         if(sph) LAUNCH(e, k_cell_lists_density<1>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec, halo_none());
         else LAUNCH(e, k_cell_lists_density<0>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
                     halo_dst(e, e->peer[0].rec, e->peer[1].rec));
@@ -877,12 +889,12 @@ static int phase_density(bbx_engine *e, const StepParams &P, int sph){
     { void *arr[1] = {e->rec}; size_t z[1] = {2 * sizeof(float4)}; return exchange_planes(e, arr, z, 1); }
 }
 // grid of a list sweep: one thread per particle
-static int sweep_grid(bbx_engine *e){ return div_up(e->n, BBX_BS); }
+static int sweep_grid(bbx_engine *e){ return div_up(launch_n(e), BBX_BS); }
 // grid of a staged sweep: one CTA per tile of BBX_TS consecutive slots
-static int tile_grid(bbx_engine *e){ return div_up(e->n, BBX_TS); }
+static int tile_grid(bbx_engine *e){ return div_up(launch_n(e), BBX_TS); }
 static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
     int cur = e->cur;
-    if(e->n > 0){
+    if(launch_n(e) > 0){
         LAUNCH(e, k_force_np_predict, sweep_grid(e), BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->rec, e->cell[cur], e->cell_start[cur],
                e->nbr, e->nbr_cnt, e->force, e->pred, e->queue, halo_dst(e, e->peer[0].pred, e->peer[1].pred));
         LAUNCH(e, k_collide_predict, BBX_SMALL_GRID, 128, P, e->st, e->colliders, e->queue, e->pos[cur], e->vel[cur], e->force, e->pred,
@@ -894,7 +906,7 @@ static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
 }
 static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
     int cur = e->cur;
-    if(e->n > 0){
+    if(launch_n(e) > 0){
         LAUNCH_S(e, k_pressure, tile_grid(e), BBX_TS, BBX_STAGE_BYTES(3), P, e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
                e->nbr, e->nbr_cnt, e->pressure, e->rho_pred, e->rho_err, e->posq, halo_dst(e, e->peer[0].posq, e->peer[1].posq));
         CU(cudaGetLastError());
@@ -904,7 +916,7 @@ static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
 }
 static int phase_pressure_force(bbx_engine *e, const StepParams &P, int integrate){
     int cur = e->cur; int nb = sweep_grid(e);
-    if(e->n > 0){
+    if(launch_n(e) > 0){
         if(integrate){
             LAUNCH(e, k_pressure_force<1>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue,
                    halo_dst(e, e->peer[0].pos[cur], e->peer[1].pos[cur], e->peer[0].vel[cur], e->peer[1].vel[cur]));
@@ -923,8 +935,8 @@ static int phase_pressure_force(bbx_engine *e, const StepParams &P, int integrat
 }
 static int phase_integrate(bbx_engine *e, const StepParams &P, int with_fp){
     int cur = e->cur;
-    if(e->n > 0){
-        LAUNCH(e, k_integrate, div_up(e->n, 256), 256, P, e->grid, e->st, e->colliders, e->cull, e->pos[cur], e->vel[cur], e->force, with_fp ? e->force_p : (const float4 *)nullptr);
+    if(launch_n(e) > 0){
+        LAUNCH(e, k_integrate, div_up(launch_n(e), 256), 256, P, e->grid, e->st, e->colliders, e->cull, e->pos[cur], e->vel[cur], e->force, with_fp ? e->force_p : (const float4 *)nullptr);
         CU(cudaGetLastError());
     }
     return exchange2(e, e->pos[cur], e->vel[cur]);
@@ -933,9 +945,9 @@ static int phase_pseudo_viscosity(bbx_engine *e, const StepParams &P, double dt)
     if(!(e->cfg.pseudo_viscosity * dt > 0.1)) return BBX_OK; // sph_equations3.cpp:655-657
     int cur = e->cur;
     // (the ghosts' rho for the aggregation weights rides in vel.w: it came with the post-integration halo)
-    if(e->n > 0){
+    if(launch_n(e) > 0){
         LAUNCH(e, k_pseudo_aggregate, sweep_grid(e), BBX_BS, P, e->grid, e->pos[cur], e->vel[cur], e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->smoothed);
-        LAUNCH(e, k_pseudo_interpolate, div_up(e->n, 256), 256, P, e->vel[cur], e->smoothed);
+        LAUNCH(e, k_pseudo_interpolate, div_up(launch_n(e), 256), 256, P, e->vel[cur], e->smoothed);
         CU(cudaGetLastError());
     }
     return exchange1(e, e->vel[cur]);
@@ -951,7 +963,7 @@ static int step_pcisph(bbx_engine *e, double dt){
     if(!(dt > 0)) return set_error(BBX_ERR_INVALID, "dt must be positive");
     StepParams P;
     int rc;
-    if((rc = sticky_error(e))) return rc;
+    if((rc = entry_error(e))) return rc;
     tick(e, T_GRID);
     if((rc = grid_update(e))) return rc;
     make_params(e, dt, P);
@@ -971,7 +983,7 @@ static int step_pcisph(bbx_engine *e, double dt){
         for(int k = 0; k < e->cfg.pcisph_max_iterations; k++){
             if(k > 0){
                 tick(e, T_PREDICT);
-                if(e->n > 0) LAUNCH(e, k_predict_again, div_up(e->n, 256), 256, P, e->colliders, e->cull, e->pos[e->cur], e->vel[e->cur], e->force, e->force_p, e->pred);
+                if(launch_n(e) > 0) LAUNCH(e, k_predict_again, div_up(launch_n(e), 256), 256, P, e->colliders, e->cull, e->pos[e->cur], e->vel[e->cur], e->force, e->force_p, e->pred);
                 if((rc = exchange1(e, e->pred))) return rc;
             }
             tick(e, T_PRESSURE);
@@ -1004,14 +1016,14 @@ static int step_sph(bbx_engine *e, double dt){
     if(!(dt > 0)) return set_error(BBX_ERR_INVALID, "dt must be positive");
     StepParams P;
     int rc;
-    if((rc = sticky_error(e))) return rc;
+    if((rc = entry_error(e))) return rc;
     tick(e, T_GRID);
     if((rc = grid_update(e))) return rc;
     make_params(e, dt, P);
     tick(e, T_DENSITY);
     if((rc = phase_density(e, P, 1))) return rc;
     tick(e, T_FORCE_NP);
-    if(e->n > 0){
+    if(launch_n(e) > 0){
         LAUNCH(e, k_sph_forces, sweep_grid(e), BBX_BS, P, e->grid, e->posq, e->vel[e->cur], e->rec, e->cell[e->cur], e->cell_start[e->cur], e->nbr, e->nbr_cnt, e->force);
         CU(cudaGetLastError());
     }
@@ -1119,6 +1131,7 @@ int bbx_stats(bbx_engine *e, bbx_step_stats *out){
     int it = e->st_host->iterations;
     int rc = read_state(e); if(rc) return rc;
     e->st_host->iterations = it;
+    if(e->counts_stale){ e->counts_stale = 1; rc = sync_counts(e); if(rc) return rc; e->st_host->iterations = it; }
     const DevState &s = *e->st_host;
     memset(out, 0, sizeof(*out));
     out->particles = e->n; out->ghosts = e->n_glo + e->n_ghi; out->substeps = e->substeps; out->pcisph_iterations = it;
@@ -1136,6 +1149,7 @@ int bbx_stats(bbx_engine *e, bbx_step_stats *out){
 // ---------------------------------------------------------------------------------------- results
 static int download(bbx_engine *e, int field, void *dst, int dtype, int compact){
     if(!dst) return set_error(BBX_ERR_INVALID, "null destination");
+    { int rc_ = sync_counts(e); if(rc_) return rc_; }
     if(e->n == 0) return BBX_OK;
     int cur = e->cur; int n = e->n;
     const float4 *s4 = nullptr; const float *s1 = nullptr; const int *si = nullptr; int comps = 3;
@@ -1169,6 +1183,7 @@ int bbx_download(bbx_engine *e, int field, void *dst, int dtype){
 }
 int bbx_download_owned(bbx_engine *e, int field, void *dst, int dtype, int *ids, int *count){
     CHECK_ENGINE(e);
+    { int rc_ = sync_counts(e); if(rc_) return rc_; }
     if(count) *count = e->n;
     if(e->n == 0) return BBX_OK;
     if(ids){
@@ -1185,6 +1200,7 @@ int bbx_download_state(bbx_engine *e, void *pos, void *vel, int *ids, int dtype,
     CHECK_ENGINE(e);
     if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "dtype must be BBX_F32 or BBX_F64");
     if(IS_SLAB(e) && !owned_order) return set_error(BBX_ERR_INVALID, "a slab engine returns its owned particles in cell order: pass owned_order = 1");
+    { int rc_ = sync_counts(e); if(rc_) return rc_; }
     if(count) *count = e->n;
     if(e->n == 0) return BBX_OK;
     if(!pos || !vel) return set_error(BBX_ERR_INVALID, "null destination");
@@ -1203,6 +1219,7 @@ int bbx_download_state(bbx_engine *e, void *pos, void *vel, int *ids, int dtype,
 
 int bbx_export_cells(bbx_engine *e, int *cell_count, int *cell_order){
     CHECK_ENGINE(e);
+    { int rc_ = sync_counts(e); if(rc_) return rc_; }
     if(!cell_count || !cell_order) return set_error(BBX_ERR_INVALID, "null");
     // cell_count covers the GLOBAL grid; a slab engine fills the cells it owns (others 0) and cell_order holds
     // its owned particles: the single-domain order is the concatenation of the slabs' orders
@@ -1222,6 +1239,7 @@ int bbx_export_cells(bbx_engine *e, int *cell_count, int *cell_order){
 
 static int export_neighbors(bbx_engine *e, int *counts, int *ids, int compact){
     if(!counts || !ids) return set_error(BBX_ERR_INVALID, "null");
+    { int rc_ = sync_counts(e); if(rc_) return rc_; }
     if(e->n == 0) return BBX_OK;
     int n = e->n; size_t bytes = sizeof(int) * (size_t)n * (BBX_MAX_NEIGHBORS + 1);
     int rc = ensure_stage(e, bytes); if(rc) return rc;

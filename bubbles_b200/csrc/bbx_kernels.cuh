@@ -34,7 +34,10 @@ __global__ void __launch_bounds__(256) k_hash_count(int n_all, int n_lo, int n_o
                                                     unsigned long long *__restrict__ scan_status, int scan_tiles, unsigned *__restrict__ movemask)
 {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    // slab engines: the counts of the LAST grid update are on the device (n_all < 0), the launch covers the capacity
+    if(n_all < 0){ n_lo = st->n_glo; n_own = st->n_own; n_all = n_lo + n_own + st->n_ghi; }
     if(idx == 0){
+        st->n_own_prev = n_own;
         st->rebuild_flag[par ^ 1] = 0; st->jump_flag[par ^ 1] = 0; st->lost[par ^ 1] = 0;
         st->overflow = 0; st->clamped = 0; st->nan_count = 0; st->max_force_bits = 0; st->max_err_bits = 0;
         st->qn[0] = 0; st->qn[1] = 0; st->scan_ticket = 0; st->n_occ = 0;
@@ -268,6 +271,7 @@ __global__ void __launch_bounds__(256) k_full_scatter(int n_all, int n_lo, DevGr
 {
     if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
     if(st->n_own > st->cap) return;
+    if(n_all < 0){ n_lo = st->n_glo; n_all = n_lo + st->n_own_prev + st->n_ghi; } // (n_own is already the NEW count: the scan has run)
     for(int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_all; idx += gridDim.x * blockDim.x){
         int i = idx - n_lo;
         int c = newcell[i];
@@ -356,30 +360,69 @@ __global__ void k_slab_counts(DevGrid g, DevState *st, const int *__restrict__ s
     if(flag_lo) *(volatile unsigned *)flag_lo = seq;
     if(flag_hi) *(volatile unsigned *)flag_hi = seq;
 }
-// Boundary planes of the freshly ordered arrays (cell-table slice, x, v, id) -> the neighbours' ghost slots:
-// up to 8 contiguous ranges, 16-byte words where the alignment allows, else 4-byte words.
-struct PushSegs { const void *src[8]; void *dst[8]; long long bytes[8]; int n; };
-__global__ void __launch_bounds__(256) k_push_planes(PushSegs S){
+// After the neighbours' counts have arrived (k_halo_wait on the counts flag): ghost-plane sizes and the neighbours' owned
+// counts from MY mailbox into DevState, where every later kernel reads them -- the host is not involved.  A ghost plane
+// that would not fit (mine, or mine in the neighbour's memory) raises the sticky capacity error; the push kernel then
+// writes nothing, so no allocation is overrun.
+__global__ void k_slab_plan(DevState *st, const int *__restrict__ mail, int has_lo, int has_hi, int peer_gc_lo, int peer_gc_hi){
+    const int glo = has_lo ? mail[0] : 0, ghi = has_hi ? mail[BBX_HALO_MAIL] : 0;
+    st->n_glo = glo; st->n_ghi = ghi;
+    st->peer_n[0] = has_lo ? mail[1] : 0; st->peer_n[1] = has_hi ? mail[BBX_HALO_MAIL + 1] : 0;
+    if(glo > st->gcap || ghi > st->gcap || (has_lo && st->n_first > peer_gc_lo) || (has_hi && st->n_last > peer_gc_hi) || st->n_own > st->cap)
+        st->error = BBX_ERR_CAPACITY;
+}
+// host path (send / recv transport): the same fields from host values
+__global__ void k_slab_plan_host(DevState *st, int glo, int ghi, int peer_lo, int peer_hi){
+    st->n_glo = glo; st->n_ghi = ghi; st->peer_n[0] = peer_lo; st->peer_n[1] = peer_hi;
+}
+// Boundary planes of the freshly ordered arrays (cell-table slice, x, v, id) -> the neighbours' ghost slots: up to 8
+// contiguous ranges whose sizes are read from DevState (k_slab_plan), 16-byte words where the alignment allows, else 4-byte.
+struct PushPtrs {
+    const int *tab_first, *tab_last;        // my cell-table slices over the first / last owned plane (plane + 1 entries)
+    const float4 *pos, *vel; const int *pid; // my freshly ordered arrays (slot 0)
+    int *gtab_lo, *gtab_hi;                  // where the slices go: lower neighbour's UPPER ghost table, upper neighbour's LOWER one
+    float4 *pos_lo, *vel_lo, *pos_hi, *vel_hi; int *pid_lo, *pid_hi; // the neighbours' arrays (their slot 0)
+    int has_lo, has_hi, plane;
+};
+__device__ __forceinline__ void bbx_push_range(const void *src, void *dst, long long b, int tid, int nth){
+    const char *s = (const char *)src; char *d = (char *)dst;
+    if(b <= 0) return;
+    if(((((size_t)s) | ((size_t)d) | (size_t)b) & 15) == 0){
+        const uint4 *s4 = (const uint4 *)s; uint4 *d4 = (uint4 *)d;
+        for(long long i = tid; i < (b >> 4); i += nth) d4[i] = s4[i];
+    }else{
+        const int *s1 = (const int *)s; int *d1 = (int *)d;
+        for(long long i = tid; i < (b >> 2); i += nth) d1[i] = s1[i];
+    }
+}
+__global__ void __launch_bounds__(256) k_push_planes(PushPtrs Q, const DevState *st){
+    if(st->error == BBX_ERR_CAPACITY) return;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for(int k = 0; k < S.n; k++){
-        const char *s = (const char *)S.src[k]; char *d = (char *)S.dst[k]; const long long b = S.bytes[k];
-        if(((((size_t)s) | ((size_t)d) | (size_t)b) & 15) == 0){
-            const uint4 *s4 = (const uint4 *)s; uint4 *d4 = (uint4 *)d;
-            for(long long i = tid; i < (b >> 4); i += nth) d4[i] = s4[i];
-        }else{
-            const int *s1 = (const int *)s; int *d1 = (int *)d;
-            for(long long i = tid; i < (b >> 2); i += nth) d1[i] = s1[i];
-        }
+    const int n = st->n_own, nf = st->n_first, nl = st->n_last;
+    const long long tb = 4ll * (Q.plane + 1);
+    if(Q.has_lo){
+        const int at = st->peer_n[0]; // my first plane follows the lower neighbour's owned slots
+        bbx_push_range(Q.tab_first, Q.gtab_lo, tb, tid, nth);
+        bbx_push_range(Q.pos, Q.pos_lo + at, 16ll * nf, tid, nth);
+        bbx_push_range(Q.vel, Q.vel_lo + at, 16ll * nf, tid, nth);
+        bbx_push_range(Q.pid, Q.pid_lo + at, 4ll * nf, tid, nth);
+    }
+    if(Q.has_hi){
+        bbx_push_range(Q.tab_last, Q.gtab_hi, tb, tid, nth);
+        bbx_push_range(Q.pos + (n - nl), Q.pos_hi - nl, 16ll * nl, tid, nth);
+        bbx_push_range(Q.vel + (n - nl), Q.vel_hi - nl, 16ll * nl, tid, nth);
+        bbx_push_range(Q.pid + (n - nl), Q.pid_hi - nl, 4ll * nl, tid, nth);
     }
 }
 // recv_lo / recv_hi: the neighbour's slice of ITS cell table over the plane it sent (plane + 1 entries each).
 // Lower ghost cells end at slot 0 (negative starts), upper ghost cells begin at n_own.
-__global__ void __launch_bounds__(256) k_ghost_table(DevGrid g, int n_own, int has_lo, int has_hi,
+__global__ void __launch_bounds__(256) k_ghost_table(DevGrid g, const DevState *st, int has_lo, int has_hi,
         const int *__restrict__ recv_lo, const int *__restrict__ recv_hi,
         int *__restrict__ start_new, int *__restrict__ cell_new, int *__restrict__ count)
 {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if(c >= g.plane) return;
+    const int n_own = st->n_own;
     if(has_lo){
         int s = recv_lo[c] - recv_lo[g.plane], e = recv_lo[c + 1] - recv_lo[g.plane];
         start_new[c] = s;
@@ -426,7 +469,7 @@ __device__ __forceinline__ uint4 *bbx_chunk_ptr(unsigned short *__restrict__ nbr
 #define BBX_LIST_PROLOGUE()                                                                        \
     __shared__ int sbase[9 * BBX_BS];                                                              \
     int i = blockIdx.x * BBX_BS + threadIdx.x;                                                     \
-    bool live = i < P.n;                                                                           \
+    bool live = i < P.dyn->n_own;                                                                  \
     int cnt = 0;                                                                                   \
     if(live){                                                                                      \
         int base[9], end[9];                                                                       \
@@ -606,6 +649,7 @@ __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGr
 {
     BBX_LIST_PROLOGUE();
     if(!live) return;
+    H = bbx_halo_resolve(H, st);
     float4 pi = pos[i]; float4 vi = vel[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
     BBX_LIST_FOREACH(j, {
@@ -647,6 +691,7 @@ __global__ void __launch_bounds__(128) k_collide_predict(StepParams P, const Dev
         const float4 *__restrict__ force, float4 *__restrict__ pred, HaloDst H)
 {
     const int qn = st->qn[0];
+    H = bbx_halo_resolve(H, st);
     for(int q = blockIdx.x * blockDim.x + threadIdx.x; q < qn; q += gridDim.x * blockDim.x){
         int i = queue[q];
         float4 f = force[i];
@@ -662,7 +707,7 @@ __global__ void __launch_bounds__(256) k_predict_again(StepParams P, const DevCo
         const float4 *__restrict__ force_p, float4 *__restrict__ pred)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= P.n) return;
+    if(i >= P.dyn->n_own) return;
     float4 pi = pos[i], vi = vel[i], f = force[i], fp = force_p[i];
     float fx = f.x + fp.x, fy = f.y + fp.y, fz = f.z + fp.z;
     float k = P.dt * P.inv_mass;
@@ -684,9 +729,12 @@ __global__ void __launch_bounds__(BBX_TS) k_pressure(StepParams P, DevGrid g, De
         float *__restrict__ pressure, float *__restrict__ rho_pred, float *__restrict__ rho_err, float4 *__restrict__ posq, HaloDst H)
 {
     bool staged; const float *S;
-    const int *scol = bbx_stage_tile<1, 3>(g, P.n, cell, cell_start, pred, bbx_dyn_smem, st, &staged, &S);
+    const int n = st->n_own;
+    if((int)blockIdx.x * BBX_TS >= n) return; // (the launch covers the capacity of a slab engine)
+    H = bbx_halo_resolve(H, st);
+    const int *scol = bbx_stage_tile<1, 3>(g, n, cell, cell_start, pred, bbx_dyn_smem, st, &staged, &S);
     const int i = blockIdx.x * BBX_TS + threadIdx.x;
-    if(i >= P.n) return;
+    if(i >= n) return;
     const int cnt = nbr_cnt[i];
     const uint4 *lp = reinterpret_cast<const uint4 *>(nbr) + ((size_t)(i >> 5) * BBX_NBR_CHUNKS) * 32 + (i & 31);
     const float4 pi = pred[i];
@@ -765,6 +813,7 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid
 {
     BBX_LIST_PROLOGUE();
     if(!live) return;
+    H = bbx_halo_resolve(H, st);
     float4 pi = posq[i];
     float tx = 0.f, ty = 0.f, tz = 0.f;
     float qi = pi.w;
@@ -803,6 +852,7 @@ __global__ void __launch_bounds__(128) k_collide_integrate(StepParams P, DevGrid
         const int *__restrict__ queue, float4 *__restrict__ pos, float4 *__restrict__ vel, const float4 *__restrict__ force, HaloDst H)
 {
     const int qn = st->qn[1];
+    H = bbx_halo_resolve(H, st);
     for(int q = blockIdx.x * blockDim.x + threadIdx.x; q < qn; q += gridDim.x * blockDim.x){
         int i = queue[q];
         float4 f = force[i];
@@ -820,7 +870,7 @@ __global__ void __launch_bounds__(256) k_integrate(StepParams P, DevGrid g, DevS
         float4 *__restrict__ pos, float4 *__restrict__ vel, float4 *__restrict__ force, const float4 *__restrict__ force_p)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= P.n) return;
+    if(i >= st->n_own) return;
     float4 pi = pos[i], v = vel[i], f = force[i];
     float fx = f.x, fy = f.y, fz = f.z;
     if(force_p){ float4 fp = force_p[i]; fx += fp.x; fy += fp.y; fz += fp.z; force[i] = make_float4(fx, fy, fz, 0.f); }
@@ -892,7 +942,7 @@ __global__ void __launch_bounds__(BBX_BS) k_pseudo_aggregate(StepParams P, DevGr
 }
 __global__ void __launch_bounds__(256) k_pseudo_interpolate(StepParams P, float4 *__restrict__ vel, const float4 *__restrict__ smoothed){
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= P.n) return;
+    if(i >= P.dyn->n_own) return;
     float4 v = vel[i], s = smoothed[i];
     float t = P.pseudo_factor;
     vel[i] = make_float4((1.f - t) * v.x + t * s.x, (1.f - t) * v.y + t * s.y, (1.f - t) * v.z + t * s.z, v.w);
