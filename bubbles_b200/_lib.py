@@ -78,6 +78,7 @@ SYMBOLS = {
     "bbx_set_particles": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "bbx_set_particles_ids": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bbx_append_particles": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "bbx_append_particles_ids": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bbx_particle_count": (C.c_int, [_E, C.POINTER(C.c_int)]),
     "bbx_overwrite_state": (C.c_int, [_E, C.c_void_p, C.c_void_p, C.c_int]),
     "bbx_overwrite_owned": (C.c_int, [_E, C.c_void_p, C.c_void_p, C.c_int]),
@@ -99,6 +100,7 @@ SYMBOLS = {
     "bbx_export_cells": (C.c_int, [_E, C.c_void_p, C.c_void_p]),
     "bbx_export_neighbors": (C.c_int, [_E, C.c_void_p, C.c_void_p]),
     "bbx_export_neighbors_owned": (C.c_int, [_E, C.c_void_p, C.c_void_p]),
+    "bbx_query_cells": (C.c_int, [_E, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "bbx_inject_chains": (C.c_int, [_E, C.c_void_p, C.c_void_p]),
     "bbx_set_rebuild_flag": (C.c_int, [_E, C.c_int]),
     "bbx_launch_count": (C.c_int, [_E, C.POINTER(C.c_longlong)]),

@@ -51,6 +51,10 @@ struct BbxComm {
     // (a missing neighbour's entry is zeroed); *ok = 0 on every rank if any rank cannot map its neighbours
     virtual int share_arrays(cudaStream_t s, const BbxPeerArrays &mine, int want, BbxPeerArrays *lo, BbxPeerArrays *hi, int *ok) = 0;
     virtual int barrier() = 0;
+    // several engines of ONE process on ONE device (test transport): their streams share the device's few hardware queues,
+    // so a backlog of spinning halo waits from one engine can sit in front of the very kernel it waits for -- such engines
+    // drain their stream at the end of every sub-step (one process per GPU never needs to)
+    virtual bool shares_device() const { return false; }
 };
 
 // ------------------------------------------------------------------------------------------ NCCL
@@ -330,4 +334,5 @@ struct LocalComm : BbxComm {
         return 0;
     }
     int barrier() override { return sh->barrier() ? 0 : fail("local slab group: barrier"); }
+    bool shares_device() const override { return true; }
 };

@@ -113,11 +113,12 @@ struct DevState {
     int n_own_prev;      // owned particles BEFORE the running grid update (the scan overwrites n_own; the full rebuild walks the old slots)
 };
 
-// Scalars of one sub-step, passed by value to every kernel.
+// Scalars of one sub-step, passed by value to every kernel.  bbx_count(P): owned particles -- a kernel argument on
+// single-domain engines, a device read on slab engines (no host round trip in their grid update).
 struct StepParams {
     int n;              // launch bound of the per-particle kernels (>= owned particles; the kernels read the count from dyn)
     int n_owned;
-    const DevState *dyn; // the engine's DevState: dyn->n_own = owned particles after the last grid update
+    const DevState *dyn; // slab engines: their DevState, where the owned count lives (dyn->n_own); null: n is exact
     float h, h2, inv_h, inv_h2;
     float thr2;         // h^2 - 1e-8: acceptance threshold of IsWithinStd on d^2
     float band;         // guard band around thr2 inside which the predicate is re-evaluated in FP64
@@ -142,6 +143,8 @@ struct StepParams {
     float xacc, xband;    // the same on x = 1 - d^2 / h^2 (list build): accepted when x > xacc, inside the band when x < xband
     int par;              // parity of the current grid epoch; integrate writes rebuild_flag[par ^ 1]
 };
+
+__device__ __forceinline__ int bbx_count(const StepParams &P){ return P.dyn ? P.dyn->n_own : P.n; }
 
 // ------------------------------------------------------------------------------------------- grid
 

@@ -444,16 +444,20 @@ int bbx_set_particles_ids(bbx_engine *e, int n, const void *pos, const void *vel
 // Re-sort after an append: old particles keep their recorded cell and their order inside it, the appended ones
 // follow in id order.  Counting sort by cell with the full-rebuild kernels, ordered by OLD SLOT (old slots are in
 // chain order, the appended particles sit behind them in id order).  Not a grid epoch: flags and parity stay.
-static int append_update(bbx_engine *e, int n_old, int k){
+static int slab_refresh_ghosts(bbx_engine *e, int nxt);
+// split / id0: see k_full_sort_cells (slab engines: the appended particles are ordered by id, not by slot)
+static int append_update(bbx_engine *e, int n_old, int k, int split = -1, int id0 = 0){
     DevGrid &g = e->grid;
     const int cur = e->cur, nxt = cur ^ 1, n_all = n_old + k, par = e->epoch & 1;
+    const int own_cells = g.c_own1 - g.c_own0;
     LAUNCH(e, k_append_hash, div_up(std::max(n_all, e->scan_tiles), 256), 256, n_old, k, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st, e->scan_status, e->scan_tiles);
-    LAUNCH(e, k_scan_cells, e->scan_tiles, 256, e->count, g.total, 0, e->scan_status, e->st, e->cell_start[nxt], e->occ_cells);
+    LAUNCH(e, k_scan_cells, e->scan_tiles, 256, e->count + g.c_own0, own_cells, g.c_own0, e->scan_status, e->st, e->cell_start[nxt] + g.c_own0, e->occ_cells);
     LAUNCH(e, k_full_scatter, div_up(n_all, 256), 256, n_all, 0, g, e->st, par, 1, e->newcell, e->cell_start[nxt], e->count, e->perm);
-    LAUNCH(e, k_full_sort_cells, div_up(g.total, 256), 256, g, e->st, par, 1, e->cell_start[nxt], (const int *)nullptr, e->perm, e->count);
+    LAUNCH(e, k_full_sort_cells, div_up(g.total, 256), 256, g, e->st, par, 1, e->cell_start[nxt], split >= 0 ? e->pid[cur] : (const int *)nullptr, e->perm, e->count, split, id0);
     LAUNCH(e, k_full_gather, div_up(n_all, 256), 256, e->st, par, 1, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
            e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec);
     CU(cudaGetLastError());
+    if(IS_SLAB(e)){ int rc = slab_refresh_ghosts(e, nxt); if(rc) return rc; } // the neighbours' ghost copies of my boundary planes changed too
     e->cur = nxt; e->n = n_all; e->have_chains = 1;
     return BBX_OK;
 }
@@ -479,6 +483,41 @@ int bbx_append_particles(bbx_engine *e, int n, const void *pos, const void *vel,
     const int n_old = e->n;
     int rc = upload_particles(e, n_old, n, pos, vel, nullptr, dtype); if(rc) return rc;
     return append_update(e, n_old, n);
+}
+
+// bbx_append_particles with explicit global ids.  Slab engines (collective over the group): every rank passes the appended
+// particles (all of them, or any superset of its share) with their global ids -- which must be larger than every id
+// already in the run, as the ids of ContinuousParticleSetBuilder3::AddParticle are -- and keeps those of its owned planes
+// at the tail of their cells' chains, in id order; the boundary planes are exchanged again.
+int bbx_append_particles_ids(bbx_engine *e, int n, const void *pos, const void *vel, const int *ids, int dtype){
+    CHECK_ENGINE(e);
+    if(!IS_SLAB(e)){
+        if(ids) for(int k = 0; k < n; k++) if(ids[k] != e->n + k) return set_error(BBX_ERR_INVALID, "single-domain engines number appended particles themselves: ids must continue from %d", e->n);
+        return bbx_append_particles(e, n, pos, vel, dtype);
+    }
+    if(n < 0 || (n > 0 && (!pos || !vel || !ids))) return set_error(BBX_ERR_INVALID, "bad particle arguments (slab engines need ids)");
+    if(!e->have_chains) return set_error(BBX_ERR_INVALID, "append on a slab engine needs a particle set first (bbx_set_particles_ids)");
+    int rc = sync_counts(e); if(rc) return rc;
+    const int n_old = e->n;
+    int id0 = 0x7fffffff;
+    for(int k = 0; k < n; k++) id0 = std::min(id0, ids[k]);
+    if(n == 0) id0 = 0;
+    if(n > 0){
+        if(dtype != BBX_F32 && dtype != BBX_F64) return set_error(BBX_ERR_INVALID, "dtype must be BBX_F32 or BBX_F64");
+        const size_t bytes = (dtype == BBX_F64 ? 8 : 4) * 3 * (size_t)n, idb = sizeof(int) * (size_t)n;
+        rc = ensure_stage(e, 2 * bytes + idb); if(rc) return rc;
+        char *sp = (char *)e->stage, *sv = sp + bytes; int *si = (int *)(sv + bytes);
+        CU(cudaMemcpyAsync(sp, pos, bytes, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(sv, vel, bytes, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(si, ids, idb, cudaMemcpyHostToDevice, e->stream));
+        // the cursor st->n_own stands at the owned count: the kept particles go behind the owned slots
+        LAUNCH(e, k_upload_slab, div_up(n, 256), 256, n, sp, sv, si, dtype == BBX_F64, e->grid, e->cap, e->st, e->pos[e->cur], e->vel[e->cur], e->pid[e->cur]);
+        CU(cudaGetLastError());
+    }
+    rc = read_state(e); if(rc) return rc;
+    if(e->st_host->error == BBX_ERR_CAPACITY) return set_error(BBX_ERR_CAPACITY, "slab would hold more than max_particles = %d particles", e->cap);
+    const int kept = e->st_host->n_own - n_old;
+    return append_update(e, n_old, kept, n_old, id0);
 }
 
 int bbx_particle_count(bbx_engine *e, int *n){
@@ -665,7 +704,7 @@ static void harvest(bbx_engine *e){
 static void make_params(bbx_engine *e, double dt, StepParams &P){
     const bbx_config &c = e->cfg;
     double h = e->h, pi = 3.14159265358979323846;
-    P.n = launch_n(e); P.n_owned = P.n; P.dyn = e->st;
+    P.n = launch_n(e); P.n_owned = P.n; P.dyn = IS_SLAB(e) ? e->st : nullptr;
     P.h = (float)h; P.h2 = (float)(h * h); P.inv_h = (float)(1.0 / h); P.inv_h2 = (float)(1.0 / (h * h));
     P.h_d = h; P.h2_d = h * h;
     P.thr2 = (float)(h * h - 1e-8);
@@ -767,6 +806,63 @@ static int setup_peers(bbx_engine *e){
     return BBX_OK;
 }
 
+// Slab engines, after the owned slots of buffer `nxt` have been (re)ordered: the ghost planes of that buffer are replaced by
+// the neighbours' freshly ordered boundary planes (collective: counts, planes, ghost part of the cell table).
+static int slab_refresh_ghosts(bbx_engine *e, int nxt){
+    DevGrid &g = e->grid;
+    // migration happened implicitly: particles that crossed into my planes were found in my ghost
+    // planes' old chains (in the reference's order), particles that left simply were not placed.
+    // Now the ghost planes are replaced by the neighbours' freshly ordered boundary planes.
+    const size_t tb = sizeof(int) * ((size_t)g.plane + 1);
+    if(e->p2p){
+        // sizes travel through the neighbours' mailboxes (peer memory) and stay on the device: k_slab_counts posts mine,
+        // k_slab_plan reads theirs into DevState, k_push_planes takes its ranges from there -- no host round trip
+        int *mail = (int *)(e->halo_flags + 2 * BBX_HALO_PHASES);
+        int *mlo = e->has_lo ? (int *)(e->peer[0].flags + 2 * BBX_HALO_PHASES) + 1 * BBX_HALO_MAIL : nullptr; // I am its UPPER side
+        int *mhi = e->has_hi ? (int *)(e->peer[1].flags + 2 * BBX_HALO_PHASES) + 0 * BBX_HALO_MAIL : nullptr;
+        const unsigned seq = ++e->halo_seq[HALO_COUNTS];
+        LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, mlo, mhi, halo_flag_at(e, 0, HALO_COUNTS), halo_flag_at(e, 1, HALO_COUNTS), seq);
+        int rc = halo_wait(e, HALO_COUNTS, seq); if(rc) return rc;
+        LAUNCH(e, k_slab_plan, 1, 1, e->st, mail, e->has_lo, e->has_hi, (int)std::min<long long>(e->peer[0].gc, 0x7fffffff), (int)std::min<long long>(e->peer[1].gc, 0x7fffffff));
+        // my freshly ordered boundary planes -> the neighbours' ghost slots (their table slices: lower ghost
+        // plane at gtab, upper one at gtab + plane + 1), then the planes flag
+        PushPtrs Q; memset(&Q, 0, sizeof(Q));
+        Q.has_lo = e->has_lo; Q.has_hi = e->has_hi; Q.plane = g.plane;
+        Q.tab_first = e->cell_start[nxt] + g.c_own0; Q.tab_last = e->cell_start[nxt] + g.c_own1 - g.plane;
+        Q.pos = e->pos[nxt]; Q.vel = e->vel[nxt]; Q.pid = e->pid[nxt];
+        if(e->has_lo){ const bbx_engine::PeerSide &p = e->peer[0]; Q.gtab_lo = p.gtab + g.plane + 1; Q.pos_lo = p.pos[nxt]; Q.vel_lo = p.vel[nxt]; Q.pid_lo = p.pid[nxt]; }
+        if(e->has_hi){ const bbx_engine::PeerSide &p = e->peer[1]; Q.gtab_hi = p.gtab; Q.pos_hi = p.pos[nxt]; Q.vel_hi = p.vel[nxt]; Q.pid_hi = p.pid[nxt]; }
+        LAUNCH(e, k_push_planes, e->sm_count, 256, Q, e->st);
+        rc = halo_sync(e, HALO_PLANES); if(rc) return rc;
+        e->counts_stale = 1;
+    }else{
+        LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, (int *)nullptr, (int *)nullptr, (unsigned *)nullptr, (unsigned *)nullptr, 0u);
+        int rc = read_state(e); if(rc) return rc;
+        const int n_new = e->st_host->n_own, nf = e->st_host->n_first, nl = e->st_host->n_last;
+        // boundary-plane sizes (the next exchange) and owned counts
+        const int to_lo[BBX_NCOUNTS] = {nf, n_new}, to_hi[BBX_NCOUNTS] = {nl, n_new};
+        int from_lo[BBX_NCOUNTS], from_hi[BBX_NCOUNTS];
+        COMM(e->comm->neighbor_counts(e->stream, to_lo, to_hi, from_lo, from_hi));
+        const int glo = from_lo[0], ghi = from_hi[0]; e->peer[0].n = from_lo[1]; e->peer[1].n = from_hi[1];
+        if(n_new > e->cap) return set_error(BBX_ERR_CAPACITY, "slab now owns %d particles, max_particles is %d", n_new, e->cap);
+        if(glo > e->gcap || ghi > e->gcap) return set_error(BBX_ERR_CAPACITY, "ghost plane of %d particles exceeds ghost_capacity %d", std::max(glo, ghi), e->gcap);
+        LAUNCH(e, k_slab_plan_host, 1, 1, e->st, glo, ghi, e->peer[0].n, e->peer[1].n);
+        BbxSeg slo[4] = {{e->cell_start[nxt] + g.c_own0, tb}, {e->pos[nxt], sizeof(float4) * (size_t)nf}, {e->vel[nxt], sizeof(float4) * (size_t)nf}, {e->pid[nxt], sizeof(int) * (size_t)nf}};
+        BbxSeg rlo[4] = {{e->gtab, tb}, {e->pos[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->vel[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->pid[nxt] - glo, sizeof(int) * (size_t)glo}};
+        BbxSeg shi[4] = {{e->cell_start[nxt] + g.c_own1 - g.plane, tb}, {e->pos[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->vel[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->pid[nxt] + (n_new - nl), sizeof(int) * (size_t)nl}};
+        BbxSeg rhi[4] = {{e->gtab + g.plane + 1, tb}, {e->pos[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->vel[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->pid[nxt] + n_new, sizeof(int) * (size_t)ghi}};
+        COMM(e->comm->exchange(e->stream, slo, rlo, 4, shi, rhi, 4));
+        e->n = n_new; e->n_first = nf; e->n_last = nl; e->n_glo = glo; e->n_ghi = ghi;
+        // a particle that left the slab's halo (dropped by the hash kernel) lets the collective sub-step finish first -- every
+        // exchange the neighbours wait for still happens -- and is reported by the stepping call on its way out
+        if(e->st_host->error == BBX_ERR_OUT_OF_DOMAIN) e->deferred_error = BBX_ERR_OUT_OF_DOMAIN;
+        else if(e->st_host->error) return set_error(e->st_host->error, "device-side error %d (%s)", e->st_host->error, device_error_text(e->st_host->error));
+    }
+    LAUNCH(e, k_ghost_table, div_up(g.plane, 256), 256, g, e->st, e->has_lo, e->has_hi, e->gtab, e->gtab + g.plane + 1, e->cell_start[nxt], e->cell[nxt], e->count);
+    CU(cudaGetLastError());
+    return BBX_OK;
+}
+
 // UpdateGridDistributionGPU minus the bucket fill (sph_equations3.cpp:511-539)
 #define BBX_SMALL_GRID (e->sm_count * 4)
 #define BBX_CHECK_GRID (e->sm_count) // grid of the full-rebuild kernels when they are only a flag check (they stride over the data if it fires)
@@ -808,62 +904,11 @@ static int grid_update(bbx_engine *e){
     int fb_n = force ? div_up(std::max(n_bound, 1), 256) : std::min(div_up(std::max(n_bound, 1), 256), BBX_CHECK_GRID);
     int fb_c = force ? div_up(own_cells, 256) : std::min(div_up(own_cells, 256), BBX_CHECK_GRID);
     LAUNCH(e, k_full_scatter, fb_n, 256, n_all, n_lo, g, e->st, par, force, e->newcell, e->cell_start[nxt], e->count, e->perm);
-    LAUNCH(e, k_full_sort_cells, fb_c, 256, g, e->st, par, force, e->cell_start[nxt], e->pid[cur], e->perm, e->count);
+    LAUNCH(e, k_full_sort_cells, fb_c, 256, g, e->st, par, force, e->cell_start[nxt], e->pid[cur], e->perm, e->count, -1, 0);
     LAUNCH(e, k_full_gather, fb_n, 256, e->st, par, force, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
            e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec);
     CU(cudaGetLastError());
-    if(slab){
-        // migration happened implicitly: particles that crossed into my planes were found in my ghost
-        // planes' old chains (in the reference's order), particles that left simply were not placed.
-        // Now the ghost planes are replaced by the neighbours' freshly ordered boundary planes.
-        const size_t tb = sizeof(int) * ((size_t)g.plane + 1);
-        if(e->p2p){
-            // sizes travel through the neighbours' mailboxes (peer memory) and stay on the device: k_slab_counts posts mine,
-            // k_slab_plan reads theirs into DevState, k_push_planes takes its ranges from there -- no host round trip
-            int *mail = (int *)(e->halo_flags + 2 * BBX_HALO_PHASES);
-            int *mlo = e->has_lo ? (int *)(e->peer[0].flags + 2 * BBX_HALO_PHASES) + 1 * BBX_HALO_MAIL : nullptr; // I am its UPPER side
-            int *mhi = e->has_hi ? (int *)(e->peer[1].flags + 2 * BBX_HALO_PHASES) + 0 * BBX_HALO_MAIL : nullptr;
-            const unsigned seq = ++e->halo_seq[HALO_COUNTS];
-            LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, mlo, mhi, halo_flag_at(e, 0, HALO_COUNTS), halo_flag_at(e, 1, HALO_COUNTS), seq);
-            int rc = halo_wait(e, HALO_COUNTS, seq); if(rc) return rc;
-            LAUNCH(e, k_slab_plan, 1, 1, e->st, mail, e->has_lo, e->has_hi, (int)std::min<long long>(e->peer[0].gc, 0x7fffffff), (int)std::min<long long>(e->peer[1].gc, 0x7fffffff));
-            // my freshly ordered boundary planes -> the neighbours' ghost slots (their table slices: lower ghost
-            // plane at gtab, upper one at gtab + plane + 1), then the planes flag
-            PushPtrs Q; memset(&Q, 0, sizeof(Q));
-            Q.has_lo = e->has_lo; Q.has_hi = e->has_hi; Q.plane = g.plane;
-            Q.tab_first = e->cell_start[nxt] + g.c_own0; Q.tab_last = e->cell_start[nxt] + g.c_own1 - g.plane;
-            Q.pos = e->pos[nxt]; Q.vel = e->vel[nxt]; Q.pid = e->pid[nxt];
-            if(e->has_lo){ const bbx_engine::PeerSide &p = e->peer[0]; Q.gtab_lo = p.gtab + g.plane + 1; Q.pos_lo = p.pos[nxt]; Q.vel_lo = p.vel[nxt]; Q.pid_lo = p.pid[nxt]; }
-            if(e->has_hi){ const bbx_engine::PeerSide &p = e->peer[1]; Q.gtab_hi = p.gtab; Q.pos_hi = p.pos[nxt]; Q.vel_hi = p.vel[nxt]; Q.pid_hi = p.pid[nxt]; }
-            LAUNCH(e, k_push_planes, e->sm_count, 256, Q, e->st);
-            rc = halo_sync(e, HALO_PLANES); if(rc) return rc;
-            e->counts_stale = 1;
-        }else{
-            LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, (int *)nullptr, (int *)nullptr, (unsigned *)nullptr, (unsigned *)nullptr, 0u);
-            int rc = read_state(e); if(rc) return rc;
-            const int n_new = e->st_host->n_own, nf = e->st_host->n_first, nl = e->st_host->n_last;
-            // boundary-plane sizes (the next exchange) and owned counts
-            const int to_lo[BBX_NCOUNTS] = {nf, n_new}, to_hi[BBX_NCOUNTS] = {nl, n_new};
-            int from_lo[BBX_NCOUNTS], from_hi[BBX_NCOUNTS];
-            COMM(e->comm->neighbor_counts(e->stream, to_lo, to_hi, from_lo, from_hi));
-            const int glo = from_lo[0], ghi = from_hi[0]; e->peer[0].n = from_lo[1]; e->peer[1].n = from_hi[1];
-            if(n_new > e->cap) return set_error(BBX_ERR_CAPACITY, "slab now owns %d particles, max_particles is %d", n_new, e->cap);
-            if(glo > e->gcap || ghi > e->gcap) return set_error(BBX_ERR_CAPACITY, "ghost plane of %d particles exceeds ghost_capacity %d", std::max(glo, ghi), e->gcap);
-            LAUNCH(e, k_slab_plan_host, 1, 1, e->st, glo, ghi, e->peer[0].n, e->peer[1].n);
-            BbxSeg slo[4] = {{e->cell_start[nxt] + g.c_own0, tb}, {e->pos[nxt], sizeof(float4) * (size_t)nf}, {e->vel[nxt], sizeof(float4) * (size_t)nf}, {e->pid[nxt], sizeof(int) * (size_t)nf}};
-            BbxSeg rlo[4] = {{e->gtab, tb}, {e->pos[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->vel[nxt] - glo, sizeof(float4) * (size_t)glo}, {e->pid[nxt] - glo, sizeof(int) * (size_t)glo}};
-            BbxSeg shi[4] = {{e->cell_start[nxt] + g.c_own1 - g.plane, tb}, {e->pos[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->vel[nxt] + (n_new - nl), sizeof(float4) * (size_t)nl}, {e->pid[nxt] + (n_new - nl), sizeof(int) * (size_t)nl}};
-            BbxSeg rhi[4] = {{e->gtab + g.plane + 1, tb}, {e->pos[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->vel[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->pid[nxt] + n_new, sizeof(int) * (size_t)ghi}};
-            COMM(e->comm->exchange(e->stream, slo, rlo, 4, shi, rhi, 4));
-            e->n = n_new; e->n_first = nf; e->n_last = nl; e->n_glo = glo; e->n_ghi = ghi;
-            // a particle that left the slab's halo (dropped by the hash kernel) lets the collective sub-step finish first -- every
-            // exchange the neighbours wait for still happens -- and is reported by the stepping call on its way out
-            if(e->st_host->error == BBX_ERR_OUT_OF_DOMAIN) e->deferred_error = BBX_ERR_OUT_OF_DOMAIN;
-            else if(e->st_host->error) return set_error(e->st_host->error, "device-side error %d (%s)", e->st_host->error, device_error_text(e->st_host->error));
-        }
-        LAUNCH(e, k_ghost_table, div_up(g.plane, 256), 256, g, e->st, e->has_lo, e->has_hi, e->gtab, e->gtab + g.plane + 1, e->cell_start[nxt], e->cell[nxt], e->count);
-        CU(cudaGetLastError());
-    }
+    if(slab){ int rc = slab_refresh_ghosts(e, nxt); if(rc) return rc; }
     e->cur = nxt;
     e->have_chains = 1;
     e->last_force = force;
@@ -1007,6 +1052,7 @@ static int step_pcisph(bbx_engine *e, double dt){
     tick(e, T_COUNT);
     probe_error(e);
     e->substeps++;
+    if(e->comm && e->comm->shares_device()) CU(cudaStreamSynchronize(e->stream));
     if(e->deferred_error) return set_error(e->deferred_error, "device-side error %d (%s)", e->deferred_error, device_error_text(e->deferred_error));
     return BBX_OK;
 }
@@ -1033,6 +1079,7 @@ static int step_sph(bbx_engine *e, double dt){
     tick(e, T_COUNT);
     probe_error(e);
     e->substeps++;
+    if(e->comm && e->comm->shares_device()) CU(cudaStreamSynchronize(e->stream));
     if(e->deferred_error) return set_error(e->deferred_error, "device-side error %d (%s)", e->deferred_error, device_error_text(e->deferred_error));
     return BBX_OK;
 }
@@ -1215,6 +1262,24 @@ int bbx_download_state(bbx_engine *e, void *pos, void *vel, int *ids, int dtype,
     if(ids) CU(cudaMemcpyAsync(ids, e->pid[cur], sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return sticky_error(e);
+}
+
+int bbx_query_cells(bbx_engine *e, int n, const int *cells, const double *points, double d, int *cell_size, int *blocked){
+    CHECK_ENGINE(e);
+    if(n <= 0) return BBX_OK;
+    if(!cells || !points || !cell_size || !blocked) return set_error(BBX_ERR_INVALID, "null");
+    if(!e->have_chains){ for(int k = 0; k < n; k++){ cell_size[k] = 0; blocked[k] = 0; } return BBX_OK; }
+    const size_t bi = sizeof(int) * (size_t)n, bp = sizeof(double) * 3 * (size_t)n;
+    int rc = ensure_stage(e, bp + 3 * bi); if(rc) return rc;
+    double *dp = (double *)e->stage; int *dc = (int *)((char *)e->stage + bp), *ds = dc + n, *db = ds + n;
+    CU(cudaMemcpyAsync(dp, points, bp, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(dc, cells, bi, cudaMemcpyHostToDevice, e->stream));
+    LAUNCH(e, k_query_cells, div_up(n, 256), 256, n, e->grid, dc, dp, d, e->cell_start[e->cur], e->pos[e->cur], ds, db);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cell_size, ds, bi, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(blocked, db, bi, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BBX_OK;
 }
 
 int bbx_export_cells(bbx_engine *e, int *cell_count, int *cell_order){

@@ -281,9 +281,15 @@ __global__ void __launch_bounds__(256) k_full_scatter(int n_all, int n_lo, DevGr
     }
 }
 // pid_old = null: order by the OLD SLOT instead of the particle id (bbx_append_particles: old chains first, in
-// their order, then the appended particles in id order -- DistributeByParticleList, grid.h:358-387)
+// their order, then the appended particles in id order -- DistributeByParticleList, grid.h:358-387).  split >= 0 (append on
+// a slab engine, where the appended particles were kept by an atomic cursor and sit in arbitrary slot order behind the old
+// ones): slots below `split` order by slot, the others behind them by particle id.
+__device__ __forceinline__ int bbx_sort_key(const int *__restrict__ pid_old, int split, int id0, int pa){
+    if(split >= 0) return pa < split ? pa : split + (pid_old[pa] - id0);
+    return pid_old ? pid_old[pa] : pa;
+}
 __global__ void __launch_bounds__(256) k_full_sort_cells(DevGrid g, const DevState *st, int par, int force, const int *__restrict__ start_new,
-        const int *__restrict__ pid_old, int *__restrict__ perm, int *__restrict__ cursor)
+        const int *__restrict__ pid_old, int *__restrict__ perm, int *__restrict__ cursor, int split, int id0)
 {
     if(!force && !(st->rebuild_flag[par] | st->jump_flag[par])) return;
     const bool over = st->n_own > st->cap;
@@ -292,9 +298,9 @@ __global__ void __launch_bounds__(256) k_full_sort_cells(DevGrid g, const DevSta
         if(over) continue;
         int s = start_new[c], e = start_new[c + 1];
         for(int a = s + 1; a < e; a++){ // insertion sort by original id (segments are a dozen long)
-            int pa = perm[a]; int ka = pid_old ? pid_old[pa] : pa;
+            int pa = perm[a]; int ka = bbx_sort_key(pid_old, split, id0, pa);
             int b = a - 1;
-            while(b >= s && (pid_old ? pid_old[perm[b]] : perm[b]) > ka){ perm[b + 1] = perm[b]; b--; }
+            while(b >= s && bbx_sort_key(pid_old, split, id0, perm[b]) > ka){ perm[b + 1] = perm[b]; b--; }
             perm[b + 1] = pa;
         }
     }
@@ -469,7 +475,7 @@ __device__ __forceinline__ uint4 *bbx_chunk_ptr(unsigned short *__restrict__ nbr
 #define BBX_LIST_PROLOGUE()                                                                        \
     __shared__ int sbase[9 * BBX_BS];                                                              \
     int i = blockIdx.x * BBX_BS + threadIdx.x;                                                     \
-    bool live = i < P.dyn->n_own;                                                                  \
+    bool live = i < bbx_count(P);                                                                  \
     int cnt = 0;                                                                                   \
     if(live){                                                                                      \
         int base[9], end[9];                                                                       \
@@ -707,7 +713,7 @@ __global__ void __launch_bounds__(256) k_predict_again(StepParams P, const DevCo
         const float4 *__restrict__ force_p, float4 *__restrict__ pred)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= P.dyn->n_own) return;
+    if(i >= bbx_count(P)) return;
     float4 pi = pos[i], vi = vel[i], f = force[i], fp = force_p[i];
     float fx = f.x + fp.x, fy = f.y + fp.y, fz = f.z + fp.z;
     float k = P.dt * P.inv_mass;
@@ -729,7 +735,7 @@ __global__ void __launch_bounds__(BBX_TS) k_pressure(StepParams P, DevGrid g, De
         float *__restrict__ pressure, float *__restrict__ rho_pred, float *__restrict__ rho_err, float4 *__restrict__ posq, HaloDst H)
 {
     bool staged; const float *S;
-    const int n = st->n_own;
+    const int n = bbx_count(P);
     if((int)blockIdx.x * BBX_TS >= n) return; // (the launch covers the capacity of a slab engine)
     H = bbx_halo_resolve(H, st);
     const int *scol = bbx_stage_tile<1, 3>(g, n, cell, cell_start, pred, bbx_dyn_smem, st, &staged, &S);
@@ -870,7 +876,7 @@ __global__ void __launch_bounds__(256) k_integrate(StepParams P, DevGrid g, DevS
         float4 *__restrict__ pos, float4 *__restrict__ vel, float4 *__restrict__ force, const float4 *__restrict__ force_p)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= st->n_own) return;
+    if(i >= bbx_count(P)) return;
     float4 pi = pos[i], v = vel[i], f = force[i];
     float fx = f.x, fy = f.y, fz = f.z;
     if(force_p){ float4 fp = force_p[i]; fx += fp.x; fy += fp.y; fz += fp.z; force[i] = make_float4(fx, fy, fz, 0.f); }
@@ -942,7 +948,7 @@ __global__ void __launch_bounds__(BBX_BS) k_pseudo_aggregate(StepParams P, DevGr
 }
 __global__ void __launch_bounds__(256) k_pseudo_interpolate(StepParams P, float4 *__restrict__ vel, const float4 *__restrict__ smoothed){
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= P.dyn->n_own) return;
+    if(i >= bbx_count(P)) return;
     float4 v = vel[i], s = smoothed[i];
     float t = P.pseudo_factor;
     vel[i] = make_float4((1.f - t) * v.x + t * s.x, (1.f - t) * v.y + t * s.y, (1.f - t) * v.z + t * s.z, v.w);
@@ -1035,6 +1041,28 @@ __global__ void __launch_bounds__(256) k_download_state(int n, const int *__rest
         float *a = (float *)dpos + 3 * id, *b = (float *)dvel + 3 * id;
         a[0] = p.x; a[1] = p.y; a[2] = p.z; b[0] = v.x; b[1] = v.y; b[2] = v.z;
     }
+}
+// ContinuousParticleSetBuilder3::MapGridEmit's per-cell test (src/core/grid.h:1367-1407) for a batch of template points:
+// size of the CURRENT chain of the point's cell, and whether a particle of that chain lies closer than d --
+// Distance(pj, pi) = sqrt(|pj - pi|^2) in FP64 like the reference (geometry.h:632-633, 797-800) on the FP32-stored positions.
+// cells are GLOBAL cell ids; a cell this (slab) engine does not own answers size -1.
+__global__ void __launch_bounds__(256) k_query_cells(int n, DevGrid g, const int *__restrict__ cells, const double *__restrict__ points, double d,
+        const int *__restrict__ cell_start, const float4 *__restrict__ pos, int *__restrict__ cell_size, int *__restrict__ blocked)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= n) return;
+    const int c = cells[k] - g.zoff * g.plane; // local cell id
+    if(cells[k] < 0 || c < g.c_own0 || c >= g.c_own1){ cell_size[k] = -1; blocked[k] = 0; return; }
+    const int s = cell_start[c], e = cell_start[c + 1];
+    const double px = points[3 * (size_t)k], py = points[3 * (size_t)k + 1], pz = points[3 * (size_t)k + 2];
+    int hit = 0;
+    for(int j = s; j < e && !hit; j++){
+        const float4 q = pos[j];
+        const double x = __dsub_rn((double)q.x, px), y = __dsub_rn((double)q.y, py), z = __dsub_rn((double)q.z, pz);
+        const double l2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+        if(__dsqrt_rn(l2) < d) hit = 1;
+    }
+    cell_size[k] = e - s; blocked[k] = hit;
 }
 __global__ void __launch_bounds__(256) k_export_cells(int total, const int *__restrict__ cell_start, int *__restrict__ cell_count){
     int c = blockIdx.x * blockDim.x + threadIdx.x;

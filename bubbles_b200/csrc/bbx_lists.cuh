@@ -7,10 +7,7 @@
 // with an LDS.128 whose latency the 4-5 resident warps per scheduler could not hide (issue slots 62 % busy,
 // the rest waiting on the load).  Here
 //   * the cell's candidates are staged ONCE in shared memory in the cell frame: (u_j, list entry) with
-//     u = (x - cell centre) / h.  The 27-cell neighbourhood is 9 contiguous slot ranges ("windows": x is the fastest
-//     cell index), which lanes 0..8 move into the warp's buffer with ONE bulk copy each (cp.async.bulk.shared.global +
-//     a per-warp mbarrier: SASS UBLKCP / SYNCS) -- no per-candidate copy instruction; a second pass transforms and
-//     culls in place;
+//     u = (x - cell centre) / h -- one coalesced global load and ~40 instructions per candidate per cell;
 //   * a group of 8 own particles lives in registers as (2 u_i, 1 - |u_i|^2); the round loop reads one
 //     candidate per lane (conflict-free LDS.128, fetched one round ahead) and runs 8 pair tests on registers;
 //   * the pair test is x = 1 - d^2 / h^2 = (1 - |u_i|^2) - |u_j|^2 + 2 u_j . u_i : 3 FFMA + 1 FADD; accepted when
@@ -46,24 +43,6 @@
 #ifndef BBX_LIST_MINB
 #define BBX_LIST_MINB 5           // resident CTAs per SM the list kernel is compiled for
 #endif
-
-// ---- mbarrier / bulk-copy plumbing (PTX; SASS: SYNCS.*, UBLKCP)
-__device__ __forceinline__ unsigned bbx_smem_u32(const void *p){ return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bbx_mbar_init(unsigned long long *b, unsigned count){
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bbx_smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void bbx_mbar_arrive_expect_tx(unsigned long long *b, unsigned bytes){
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bbx_smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bbx_mbar_wait(unsigned long long *b, unsigned parity){
-    asm volatile("{\n\t.reg .pred p;\n\tBBX_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra BBX_DONE_%=;\n\tbra BBX_WAIT_%=;\n\tBBX_DONE_%=:\n\t}"
-                 :: "r"(bbx_smem_u32(b)), "r"(parity) : "memory");
-}
-// global -> shared, `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted on the mbarrier
-__device__ __forceinline__ void bbx_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *b){
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(bbx_smem_u32(dst)), "l"(src), "r"(bytes), "r"(bbx_smem_u32(b)) : "memory");
-}
 
 // Slow path of one particle whose list would exceed 100 entries: re-walk the 27 cells in the reference's
 // order (y outer, x middle, z inner; chain order inside a cell) and keep the first 100 exactly like
@@ -106,7 +85,6 @@ struct ListWarp {
     unsigned short *rows;    // [BBX_G][BBX_ROW] lists being built
     int *tab;                // [0..9] exclusive prefix of the 9 run lengths (tab[9] = T), [10..18] first slot of each run
     int *cnt;                // [BBX_G]
-    unsigned long long *mbar; // this warp's mbarrier (bulk staging)
 };
 
 // Stage candidates of the cell's neighbourhood in flat order (run-major, slot order), starting at flat index
@@ -156,51 +134,6 @@ __device__ __forceinline__ int bbx_list_stage(const StepParams &P, DevState *st,
         n += __popc(msk);
     }
     f0 = c0 + nc;
-    __syncwarp();
-    if(n + lane < ((n + 31) & ~31)) W.cand[n + lane] = make_float4(1.0e15f, 0.f, 0.f, 0.f);
-    __syncwarp();
-    return n;
-}
-
-// The same for a neighbourhood that fits the buffer at once (T <= BBX_CMAX, the normal case), with the raw positions
-// brought in by 9 bulk copies -- window r lands at flat offset tab[r], so the buffer holds the candidates in flat order --
-// and ONE pass that transforms, culls and compacts in place (a lane reads slot f, all lanes synchronise, the kept ones
-// are written to slots <= f).  The list entry (window, offset) is recomputed from the flat index: the windows only move
-// forward, 32 candidates further on is at most two non-empty windows on in a dense neighbourhood.
-__device__ __forceinline__ int bbx_list_stage_bulk(const StepParams &P, DevState *st, const ListWarp &W, int T, int lane, unsigned &parity,
-        float cx, float cy, float cz, float hx, float hy, float hz, const float4 *__restrict__ pos)
-{
-    // the buffer was read and written through the generic proxy (previous cell): order those accesses before the copy engine's writes
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if(lane == 0) bbx_mbar_arrive_expect_tx(W.mbar, 16u * (unsigned)T);
-    __syncwarp();
-    if(lane < 9){
-        const int o = W.tab[lane], len = W.tab[lane + 1] - o;
-        if(len > 0) bbx_bulk_g2s(W.cand + o, pos + W.tab[10 + lane], 16u * (unsigned)len, W.mbar);
-    }
-    bbx_mbar_wait(W.mbar, parity);
-    parity ^= 1u;
-    const unsigned lt = lanemask_lt();
-    int n = 0, r = 0;
-#pragma unroll 1
-    for(int k0 = 0; k0 < T; k0 += 32){
-        const int f = min(k0 + lane, T - 1);
-        r += (r < 8 && f >= W.tab[r + 1]) ? 1 : 0;
-        r += (r < 8 && f >= W.tab[r + 1]) ? 1 : 0;
-        while(f >= W.tab[r + 1]) r++;               // (tab[9] = T > f)
-        const int off = f - W.tab[r];
-        const float4 raw = W.cand[f];
-        __syncwarp(); // every lane has read its candidate before the compacted ones overwrite this range
-        const float ux = (raw.x - cx) * P.inv_h, uy = (raw.y - cy) * P.inv_h, uz = (raw.z - cz) * P.inv_h;
-        const float gx = fmaxf(fabsf(ux) - hx, 0.f), gy = fmaxf(fabsf(uy) - hy, 0.f), gz = fmaxf(fabsf(uz) - hz, 0.f);
-        const bool keep = (k0 + lane < T) && (fmaf(gx, gx, fmaf(gy, gy, gz * gz)) < 1.001f);
-        if(off >= BBX_MAX_RUN_LEN) st->error = BBX_ERR_CAPACITY;
-        const unsigned entry = ((unsigned)r << BBX_RUN_SHIFT) | (unsigned)min(off, BBX_MAX_RUN_LEN - 1);
-        const unsigned msk = __ballot_sync(BBX_FULL, keep);
-        if(keep) W.cand[n + __popc(msk & lt)] = make_float4(ux, uy, uz, __uint_as_float(entry));
-        n += __popc(msk);
-    }
     __syncwarp();
     if(n + lane < ((n + 31) & ~31)) W.cand[n + lane] = make_float4(1.0e15f, 0.f, 0.f, 0.f);
     __syncwarp();
@@ -292,13 +225,8 @@ __global__ void __launch_bounds__(BBX_LT, BBX_LIST_MINB) k_cell_lists_density(St
     __shared__ int s_tab[BBX_LW][20];
     __shared__ int s_cnt[BBX_LW][BBX_G];
     __shared__ float s_ovs[BBX_LW][BBX_G];
-    __shared__ unsigned long long s_mbar[BBX_LW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     ListWarp W; W.cand = s_cand[warp]; W.ent = s_ent[warp]; W.spi = s_pi[warp]; W.rows = s_rows[warp]; W.tab = s_tab[warp]; W.cnt = s_cnt[warp];
-    W.mbar = &s_mbar[warp];
-    if(lane == 0){ bbx_mbar_init(W.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    __syncwarp();
-    unsigned parity = 0;
     float *sovs = s_ovs[warp];
     const int n_occ = st->n_occ;
     const int nwarps = gridDim.x * BBX_LW;
@@ -337,7 +265,7 @@ __global__ void __launch_bounds__(BBX_LT, BBX_LIST_MINB) k_cell_lists_density(St
         // half extents of the cell in the cell frame (culling of the staged candidates)
         const float hx = 0.5f * g.lenf[0] * P.inv_h, hy = 0.5f * g.lenf[1] * P.inv_h, hz = 0.5f * g.lenf[2] * P.inv_h;
         int nc = -1; // >= 0: the whole neighbourhood fits one stage, done once per cell
-        if(T <= BBX_CMAX) nc = bbx_list_stage_bulk(P, st, W, T, lane, parity, ccx, ccy, ccz, hx, hy, hz, pos);
+        if(T <= BBX_CMAX){ int f0 = 0; nc = bbx_list_stage(P, st, W, T, lane, f0, ccx, ccy, ccz, hx, hy, hz, pos); }
 #pragma unroll 1
         for(int p0 = 0; p0 < m; p0 += BBX_G){
             const int mg = min(BBX_G, m - p0);

@@ -222,6 +222,14 @@ class Engine:
         pos, vel, dt = self._pair(pos, vel)
         _check(self.lib.bbx_append_particles(self.h, len(pos), pos.ctypes.data, vel.ctypes.data, dt))
 
+    def append_particles_ids(self, pos, vel, ids):
+        """append with explicit global ids (slab engines: collective, each rank keeps the particles of its planes)"""
+        pos, vel, dt = self._pair(pos, vel)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        if len(ids) != len(pos):
+            raise ValueError(f"{len(ids)} ids for {len(pos)} particles")
+        _check(self.lib.bbx_append_particles_ids(self.h, len(pos), pos.ctypes.data, vel.ctypes.data, ids.ctypes.data, dt))
+
     def overwrite_state(self, pos, vel):
         pos, vel, dt = self._pair(pos, vel, rows=self.n)
         _check(self.lib.bbx_overwrite_state(self.h, pos.ctypes.data, vel.ctypes.data, dt))
@@ -345,6 +353,17 @@ class Engine:
         ids = np.full((n, L.MAX_NEIGHBORS), -1, dtype=np.int32)
         _check(self.lib.bbx_export_neighbors(self.h, counts.ctypes.data, ids.ctypes.data))
         return counts, ids
+
+    def query_cells(self, cells, points, d):
+        """MapGridEmit's per-cell test on the device: (chain length of each point's cell, blocked flags)"""
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        if len(cells) != len(points):
+            raise ValueError("one cell id per point")
+        size = np.zeros(len(cells), dtype=np.int32)
+        blocked = np.zeros(len(cells), dtype=np.int32)
+        _check(self.lib.bbx_query_cells(self.h, len(cells), cells.ctypes.data, points.ctypes.data, float(d), size.ctypes.data, blocked.ctypes.data))
+        return size, blocked
 
     def inject_chains(self, cell_count, cell_order):
         cc = np.ascontiguousarray(cell_count, dtype=np.int32)

@@ -351,8 +351,27 @@ struct ContinuousParticleSetBuilder3 {
     }
     int MapGridEmit(const std::function<vec3f(const vec3f &)> &velocity, Float d = 0.02){
         if((reemitions > 0 && reemitOnce) || !mapped) return 0;
-        std::vector<int> count, order; Chains(*mapped, &count, &order);
-        std::vector<vec3f> add = MapGridEmitCandidates(mappedPositions, mapped->desc.total, count.data(), order.data(), particleSet->set.positions.data(), d);
+        // the per-cell test runs on the device (bbx_query_cells): template points go up, 8 bytes per point come back -- the
+        // chains are not downloaded (the reference walks them on the host, grid.h:1367-1407)
+        std::vector<int> cells; std::vector<vec3f> pts;
+        for(const auto &kv : mappedPositions){
+            if((int)kv.first >= mapped->desc.total) continue;
+            for(const vec3f &p : kv.second){ cells.push_back((int)kv.first); pts.push_back(p); }
+        }
+        std::vector<int> size(cells.size()), blocked(cells.size());
+        if(!particleSet->engine) throw Error(BBX_ERR_INVALID, "MapGridEmit needs the solver's Setup() first");
+        static_assert(sizeof(vec3f) == 3 * sizeof(double), "vec3f must be 3 packed doubles");
+        Check(bbx_query_cells(particleSet->engine, (int)cells.size(), cells.data(), (const double *)pts.data(), d, size.data(), blocked.data()));
+        std::vector<vec3f> add;
+        for(size_t k = 0; k < cells.size();){
+            size_t e = k; while(e < cells.size() && cells[e] == cells[k]) e++;       // the template of one cell
+            const int sz = size[k];
+            if(sz >= 0 && sz < BBX_MAX_NEIGHBORS){
+                const size_t toInsert = std::min<size_t>((size_t)(BBX_MAX_NEIGHBORS - sz), e - k);
+                for(size_t i = 0; i < toInsert; i++) if(!blocked[k + i]) add.push_back(pts[k + i]);
+            }
+            k = e;
+        }
         int added = 0;
         for(const vec3f &p : add){ if(!AddParticle(p, velocity(p))) break; added++; }
         if(added > 0) Commit();

@@ -3,13 +3,16 @@
 // (MakeBox / VolumeParticleEmitter3 / UtilBuildGridForDomain / ColliderSetBuilder3 / PciSphSolver3 /
 // SerializerSaveSphDataSet3 / PciSphRunSimulation3), host code only -- every kernel runs inside libbbx.so.
 //
-//   dam_break_demo [--scaling S] [--frames N] [--steps N --dt X] [--jitter J] [--out DIR] [--dump FILE] [--sph] [--emit K] [--load FRAME]
+//   dam_break_demo [--scaling S] [--frames N] [--steps N --dt X] [--jitter J] [--out DIR] [--dump FILE] [--sph] [--emit K] [--map-emit] [--load FRAME]
 //     --scaling  domainScaling of the reference scene (2.5 there: ~0.9 M particles; default 0.6: ~12 k)
 //     --frames   frames of 1/240 s through Advance() (CFL sub-stepping), default 2
 //     --steps    instead of frames: N fixed-dt sub-steps (AdvanceTimeStep)
 //     --out      directory for the text frames bbtool reads (out_<frame>.txt), off by default
 //     --emit     continuous emission (ContinuousParticleSetBuilder3): after every frame K more particles enter above the
 //                fluid (AddParticle + Commit), as the reference's MapGridEmit scenes do
+//     --map-emit continuous RE-emission (ContinuousParticleSetBuilder3::MapGrid after Setup, MapGridEmit after every frame,
+//                src/core/grid.h:1288-1407): the cells the block started in are refilled where there is room; the per-cell
+//                test runs on the device (bbx_query_cells)
 //     --load     start from a frame file (positions and, when present, velocities: SerializerLoadSphDataSet3) instead of
 //                emitting the block, e.g. the reference's resources/dam_break_50
 //     --dump     raw little-endian doubles: n, then n x 3 positions, n x 3 velocities (for the parity test)
@@ -24,7 +27,7 @@ using namespace bbx;
 
 int main(int argc, char **argv){
     Float domainScaling = 0.6f, jitter = 0.001, dt = 0;
-    int frames = 2, steps = 0, emit = 0; bool sph = false;
+    int frames = 2, steps = 0, emit = 0; bool sph = false, mapEmit = false;
     std::string out, dump, load;
     for(int i = 1; i < argc; i++){
         std::string a = argv[i];
@@ -38,6 +41,7 @@ int main(int argc, char **argv){
         else if(a == "--dump") dump = next();
         else if(a == "--sph") sph = true;
         else if(a == "--emit") emit = std::atoi(next().c_str());
+        else if(a == "--map-emit") mapEmit = true;
         else if(a == "--load") load = next();
         else{ std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -77,7 +81,7 @@ int main(int argc, char **argv){
         auto colliders = cBuilder.GetColliderSet();
 
         auto sphSet = SphParticleSet3FromContinuousBuilder(&pBuilder);
-        if(!emit) sphSet->reservedSize = 0;              // no emission: size the engine for the block alone
+        if(!emit && !mapEmit) sphSet->reservedSize = 0;  // no emission: size the engine for the block alone
         sphSet->SetRelativeKernelRadius(spacingScale);
         std::printf("particles %d, cells %d (%d x %d x %d)\n", pBuilder.GetParticleCount(), domainGrid->desc.total,
                     domainGrid->desc.n[0], domainGrid->desc.n[1], domainGrid->desc.n[2]);
@@ -87,6 +91,7 @@ int main(int argc, char **argv){
             solver.Initialize(DefaultSphSolverData3());
             solver.Setup(WaterDensity, spacing, spacingScale, domainGrid, sphSet);
             solver.SetColliders(colliders);
+            if(mapEmit) pBuilder.MapGrid(domainGrid);
             auto save = [&](int frame){
                 if(out.empty()) return;
                 std::string path = out + "/out_" + std::to_string(frame) + ".txt";
@@ -111,6 +116,10 @@ int main(int argc, char **argv){
                         for(int q = 0; q < emit; q++)
                             pBuilder.AddParticle(vec3f(xof - 0.5 * boxFluidLen + spacing * (q % side + 1), 0.5 * boxYLen - 3 * spacing, zof - 0.5 * boxFluidLen + spacing * (q / side + 1)), vec3f(0, -3, 0));
                         pBuilder.Commit();
+                    }
+                    if(mapEmit && step < frames){
+                        const int added = pBuilder.MapGridEmit([](const vec3f &) { return vec3f(0, -6, 0); }, spacing);
+                        std::printf("map-emit added %d\n", added);
                     }
                     return step >= frames ? 0 : 1;
                 });

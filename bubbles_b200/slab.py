@@ -111,6 +111,14 @@ class LocalSlabGroup:
         self.n_total = len(pos)
         self.each(lambda e, r: e.set_particles_ids(pos, vel, ids))
 
+    def append_particles(self, pos, vel):
+        """ContinuousParticleSetBuilder3::AddParticle + Commit on the group: ids continue from the global count, every
+        slab keeps the particles of its planes"""
+        first = sum(self.counts)
+        ids = np.arange(first, first + len(pos), dtype=np.int32)
+        self.each(lambda e, r: e.append_particles_ids(pos, vel, ids))
+        self.n_total = first + len(pos)
+
     def step_pcisph(self, dt):
         self.each(lambda e, r: e.step_pcisph(dt))
 

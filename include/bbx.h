@@ -195,8 +195,12 @@ int bbx_set_particles_ids(bbx_engine *e, int n, const void *pos, const void *vel
 /* ContinuousParticleSetBuilder3::AddParticle + Commit (grid.h:1409-1441): new ids continue from the current
  * count, the new particles go to the tail of their cell's chain (DistributeByParticleList, grid.h:358-387), the
  * chains of the existing particles are left as they are.  Works before and between steps (neighbour lists are
- * refreshed by the next sub-step); not available on slab engines. */
+ * refreshed by the next sub-step); slab engines: bbx_append_particles_ids. */
 int bbx_append_particles(bbx_engine *e, int n, const void *pos, const void *vel, int dtype);
+/* the same with explicit global ids, which is how particles are appended to SLAB engines (collective over the group):
+ * every rank passes the appended particles (or any superset of its share); ids must exceed every id already in the run.
+ * Single-domain engines accept ids == NULL or the continuing sequence. */
+int bbx_append_particles_ids(bbx_engine *e, int n, const void *pos, const void *vel, const int *ids, int dtype);
 int bbx_particle_count(bbx_engine *e, int *n);
 /* overwrite positions+velocities of the existing particles (id order) without touching chains */
 int bbx_overwrite_state(bbx_engine *e, const void *pos, const void *vel, int dtype);
@@ -248,6 +252,11 @@ int bbx_export_cells(bbx_engine *e, int *cell_count, int *cell_order);
 int bbx_export_neighbors(bbx_engine *e, int *counts, int *ids);
 /* same for the owned particles of a slab engine, rows in the order of bbx_download_owned (ids are global) */
 int bbx_export_neighbors_owned(bbx_engine *e, int *counts, int *ids);
+/* The per-cell test of ContinuousParticleSetBuilder3::MapGridEmit (src/core/grid.h:1367-1407) on the device, for a batch
+ * of n template points (FP64 x, y, z) with the GLOBAL ids of their cells: cell_size[k] = length of the cell's current
+ * chain (-1: a cell this slab engine does not own), blocked[k] = 1 when a particle of that chain lies closer than d
+ * (the reference walks the chains on the host; this keeps them on the device -- only 8 bytes per point come back). */
+int bbx_query_cells(bbx_engine *e, int n, const int *cells, const double *points, double d, int *cell_size, int *blocked);
 /* replace the chain order (parity tests: reproduce a history-dependent order) */
 int bbx_inject_chains(bbx_engine *e, const int *cell_count, const int *cell_order);
 /* set SphParticleSet3::requiresHigherLevelUpdate */

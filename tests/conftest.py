@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# LocalSlabGroup puts several slab engines (2 streams each, kernels that spin on their neighbours' flags) on ONE device:
+# more hardware queues than the default 8 keep their streams from aliasing (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

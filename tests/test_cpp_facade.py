@@ -100,6 +100,19 @@ def test_demo_continuous_emission():
 
 
 @pytest.mark.gpu
+def test_demo_map_grid_emit_runs_on_the_gpu():
+    """The facade's MapGrid / MapGridEmit (src/core/grid.h:1288-1407) end to end on the device: the cells the block
+    started in are refilled after every frame (per-cell test: bbx_query_cells, Commit: bbx_append_particles)."""
+    r = subprocess.run([_demo(), "--frames", "3", "--map-emit"], capture_output=True, text=True)
+    assert r.returncode == 0 and "===== OK" in r.stdout, r.stdout + r.stderr
+    added = [int(x) for x in re.findall(r"map-emit added (\d+)", r.stdout)]
+    counts = [int(x) for x in re.findall(r"Particles (\d+)", r.stdout)]
+    assert len(added) == 2 and all(a > 0 for a in added), r.stdout
+    assert counts[1] == counts[0] + added[0] and counts[2] == counts[1] + added[1], r.stdout
+    assert "non-finite 0" in r.stdout
+
+
+@pytest.mark.gpu
 def test_demo_restarts_from_a_frame_file(tmp_path):
     """--load: a frame written by the facade (positions only, "%g") is read back by the facade's reader and stepped."""
     r = subprocess.run([_demo(), "--jitter", "0", "--steps", "5", "--out", str(tmp_path)], capture_output=True, text=True)

@@ -232,3 +232,49 @@ def test_slab_halo_transports_agree(p2p, monkeypatch):
     c1, o1 = one.export_cells()
     assert np.array_equal(cc, c1) and np.array_equal(co, o1)
     grp.close()
+
+
+def test_append_particles_on_slab_engines_matches_single_domain():
+    """SURVEY.md 8(f)2 on slabs: bbx_append_particles_ids = ContinuousParticleSetBuilder3::AddParticle + Commit
+    (src/core/grid.h:1409-1441) with the appended block straddling the cuts -- every slab keeps the particles of its
+    planes at the tail of their cells' chains (id order), the boundary planes are exchanged again.  Chains, ids and the
+    trajectory that follows: bit-identical to the single-domain engine (whose append is pinned against the reference,
+    test_append_particles_between_steps_matches_reference_chains)."""
+    sc = _moving_scene()
+    n0 = len(sc["pos"])
+    from oracle import oracle as O
+    pts = scenes.f32(O.bcc_points((-0.12, 0.12, -0.14), (0.1, 0.2, 0.16), 0.02))       # a sheet above the block, over all three slabs
+    vel = scenes.f32(np.tile([0.3, -2.0, 0.5], (len(pts), 1)))
+    cap = n0 + 2 * len(pts)
+    one = _single(sc, max_particles=cap)
+    grp, zb = _group(sc, 3, cap=cap)
+    grp.set_particles(sc["pos"], sc["vel"])
+    dt = sc["dt"]
+
+    def same(step):
+        cc, co = grp.export_cells()
+        c1, o1 = one.export_cells()
+        assert np.array_equal(cc, c1) and np.array_equal(co, o1), f"chains differ at {step}"
+        for f in (bb.POSITION, bb.VELOCITY, bb.DENSITY):
+            assert np.array_equal(grp.download(f, np.float32), one.download(f, np.float32)), f"field {f} differs at {step}"
+
+    for _ in range(15):
+        one.step_pcisph(dt)
+        grp.step_pcisph(dt)
+    for rep, shift in enumerate((np.zeros(3), np.array([0.01, 0.0, -0.01]))):
+        p = scenes.f32(pts + shift)
+        before = grp.counts
+        one.append_particles(p, vel)
+        grp.append_particles(p, vel)
+        assert sum(grp.counts) == one.n == n0 + (rep + 1) * len(pts)
+        assert sum(a != b for a, b in zip(before, grp.counts)) >= 2, "the appended block landed in one slab only"
+        same(f"append {rep}")
+        for step in range(12):
+            one.step_pcisph(dt)
+            grp.step_pcisph(dt)
+        same(f"after append {rep}")
+    n1, i1 = one.export_neighbors()
+    ng, ig = grp.export_neighbors()
+    assert np.array_equal(n1, ng) and np.array_equal(i1, ig)
+    assert all(s.nan_count == 0 for s in grp.stats())
+    grp.close()
