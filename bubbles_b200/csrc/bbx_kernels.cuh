@@ -655,7 +655,6 @@ __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGr
 {
     BBX_LIST_PROLOGUE();
     if(!live) return;
-    H = bbx_halo_resolve(H, st);
     float4 pi = pos[i]; float4 vi = vel[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
     BBX_LIST_FOREACH(j, {
@@ -680,7 +679,7 @@ __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGr
     float tpx = pi.x + P.dt * tvx, tpy = pi.y + P.dt * tvy, tpz = pi.z + P.dt * tvz;
     pred[i] = make_float4(tpx, tpy, tpz, 0.f);
     if(!bbx_cull(*cull, tpx, tpy, tpz, P.radius)) queue[atomicAdd(&st->qn[0], 1)] = i; // (k_collide_predict pushes its halo copy)
-    else bbx_halo_store(H, 0, 1, i, 0, make_float4(tpx, tpy, tpz, 0.f));
+    else{ H = bbx_halo_resolve(H, st); bbx_halo_store(H, 0, 1, i, 0, make_float4(tpx, tpy, tpz, 0.f)); }
 }
 
 // x* of one particle from its forces + the exact collider response (restitution 0)
@@ -729,7 +728,7 @@ __global__ void __launch_bounds__(256) k_predict_again(StepParams P, const DevCo
 // Writes posq = (x_i, p_i / rho*_i^2) for the pressure-force sweep.
 extern __shared__ __align__(128) unsigned char bbx_dyn_smem[];
 
-__global__ void __launch_bounds__(BBX_TS) k_pressure(StepParams P, DevGrid g, DevState *st, int first,
+__global__ void __launch_bounds__(BBX_TS, 4) k_pressure(StepParams P, DevGrid g, DevState *st, int first,
         const float4 *__restrict__ pos, const float4 *__restrict__ pred, const int *__restrict__ cell,
         const int *__restrict__ cell_start, const unsigned short *__restrict__ nbr, const int *__restrict__ nbr_cnt,
         float *__restrict__ pressure, float *__restrict__ rho_pred, float *__restrict__ rho_err, float4 *__restrict__ posq, HaloDst H)
@@ -737,7 +736,6 @@ __global__ void __launch_bounds__(BBX_TS) k_pressure(StepParams P, DevGrid g, De
     bool staged; const float *S;
     const int n = bbx_count(P);
     if((int)blockIdx.x * BBX_TS >= n) return; // (the launch covers the capacity of a slab engine)
-    H = bbx_halo_resolve(H, st);
     const int *scol = bbx_stage_tile<1, 3>(g, n, cell, cell_start, pred, bbx_dyn_smem, st, &staged, &S);
     const int i = blockIdx.x * BBX_TS + threadIdx.x;
     if(i >= n) return;
@@ -766,6 +764,7 @@ __global__ void __launch_bounds__(BBX_TS) k_pressure(StepParams P, DevGrid g, De
     // the reference skips a neighbour whose rho*^2 is ~0 (pcisph_equations3.cpp:137): NaN marks it
     const float4 xq = make_float4(x0.x, x0.y, x0.z, (rho2 < 1e-8f) ? __int_as_float(0x7fc00000) : p / rho2);
     posq[i] = xq;
+    H = bbx_halo_resolve(H, st); // (late: the plane sizes are only needed here, not across the neighbour loop)
     bbx_halo_store(H, 0, 1, i, 0, xq);
     bbx_atomic_max_warp(&st->max_err_bits, fabsf(err));
 }
@@ -819,7 +818,6 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid
 {
     BBX_LIST_PROLOGUE();
     if(!live) return;
-    H = bbx_halo_resolve(H, st);
     float4 pi = posq[i];
     float tx = 0.f, ty = 0.f, tz = 0.f;
     float qi = pi.w;
@@ -847,6 +845,7 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid
         if(bbx_cull(*cull, po.x, po.y, po.z, P.radius) && bbx_inside_domain_certain(*cull, po.x, po.y, po.z)){
             bbx_integrate_flags(P, st, pi, po);
             pos[i] = po; vel[i] = vo;
+            H = bbx_halo_resolve(H, st);
             bbx_halo_store(H, 0, 1, i, 0, po); bbx_halo_store(H, 1, 1, i, 0, vo);
         }else{
             queue[atomicAdd(&st->qn[1], 1)] = i; // pos / vel stay untouched: the exact kernel redoes the update
