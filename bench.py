@@ -586,6 +586,12 @@ def main():
     value = n_global / (ms_per_step * 1e-3)
     phase, gap_ms = phase_breakdown(job, solver, dt, args.steps, phase_ids)
     st = eng.stats()
+    per_rank = None
+    if world > 1:  # where the time of each rank goes (a phase ends with the wait for the neighbours' halo: skew shows up there)
+        mine = {"rank": rank, "owned": int(st.particles), "ghosts": int(st.ghosts), "occupied_cells": int(st.occupied_cells),
+                "phases_ms_per_step": {k: v[0] / args.steps for k, v in phase.items()}}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     if st.nan_count:
         raise SystemExit("non-finite positions during the timed region")
     stats = {"neighbor_overflow": st.neighbor_overflow, "clamped": st.clamped, "rebuild_flag": st.rebuild_flag, "occupied_cells": st.occupied_cells,
@@ -669,6 +675,7 @@ def main():
                          "gap_ms_per_step": gap_ms / args.steps,
                          "limiter": limiter},
             "stats": stats,
+            "ranks": per_rank,
             "parity": parity,
             "developed": developed,
             "configs": configs,

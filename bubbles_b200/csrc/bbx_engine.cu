@@ -73,6 +73,10 @@ struct bbx_engine {
     DevState *st; DevState *st_host; // st_host pinned
     int *err_probe;  // pinned: copy of st->error enqueued behind every sub-step (no sync); checked by the next API call
     int sm_count;    // multiprocessors of the device (persistent grids are sized from it)
+    // slab engines with the halo push launch their per-particle kernels over a BOUND of the owned count: the last count the
+    // host has seen (an asynchronous copy of DevState behind every grid update, polled -- never waited for) plus a margin;
+    // k_slab_plan checks the real count against the bound on the device (sticky capacity error if it was ever too small)
+    DevState *st_hint; cudaEvent_t ev_hint; int hint_pending; int n_hint; int n_launch;
     int counts_stale;   // slab engines with the halo push: n / n_first / n_last / ghost counts live in DevState; the host copies
                         // (e->n ...) are refreshed by sync_counts() when an API call needs them
     int deferred_error; // slab engines: a device-side error seen in the middle of a collective sub-step; the sub-step is
@@ -188,6 +192,7 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     e->nbr = nullptr; e->nbr_cnt = nullptr; e->force = e->force_p = e->pred = e->posq = e->smoothed = e->rec = nullptr;
     e->pressure = e->rho_pred = e->rho_err = nullptr; e->st = nullptr; e->st_host = nullptr; e->err_probe = nullptr;
     e->colliders = nullptr; e->cull = nullptr; e->gtab = nullptr; e->halo_flags = nullptr; e->mail_host = nullptr; e->stage = nullptr;
+    e->st_hint = nullptr; e->ev_hint = nullptr; e->hint_pending = 0; e->n_hint = 0; e->n_launch = 0;
     memset(&e->cfg, 0, sizeof(e->cfg));
     e->cfg = *cfg;
     e->device = cfg->device;
@@ -288,6 +293,9 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     CU(cudaMemset(e->count, 0, sizeof(int) * ((size_t)g.total + 8)));
     CU(cudaMallocHost((void **)&e->st_host, sizeof(DevState)));
     CU(cudaMallocHost((void **)&e->err_probe, sizeof(int)));
+    CU(cudaMallocHost((void **)&e->st_hint, sizeof(DevState)));
+    memset(e->st_hint, 0, sizeof(DevState));
+    CU(cudaEventCreateWithFlags(&e->ev_hint, cudaEventDisableTiming));
     *e->err_probe = 0;
     memset(e->st_host, 0, sizeof(DevState));
     e->st_host->cap = e->cap; e->st_host->gcap = e->gcap;
@@ -317,6 +325,8 @@ int bbx_destroy(bbx_engine *e){
     if(e->mail_host) cudaFreeHost(e->mail_host);
     cudaFree(e->st); cudaFree(e->colliders); cudaFree(e->cull); if(e->st_host) cudaFreeHost(e->st_host);
     if(e->err_probe) cudaFreeHost(e->err_probe);
+    if(e->st_hint) cudaFreeHost(e->st_hint);
+    if(e->ev_hint) cudaEventDestroy(e->ev_hint);
     for(double *f : e->sdf_fields) cudaFree(f);
     for(float *f : e->sdf_fields32) cudaFree(f);
     if(e->stage) cudaFree(e->stage);
@@ -374,12 +384,18 @@ static int grid_update(bbx_engine *e);
 // Slab engines keep their particle counts on the device (DevState) and launch the per-particle kernels over the capacity;
 // the host copies are brought up to date only when an API call needs exact numbers (downloads, exports, the send / recv
 // transport of the cold paths).
-static inline int launch_n(const bbx_engine *e){ return IS_SLAB(e) ? e->cap : e->n; }
+static inline int launch_n(const bbx_engine *e){ return IS_SLAB(e) ? e->n_launch : e->n; }
+static inline int bound_of(const bbx_engine *e, int n){ return (int)std::min<long long>(e->cap, (long long)n + n / 16 + 4096); }
+// the newest owned count that has reached the host, without waiting for anything
+static void poll_hint(bbx_engine *e){
+    if(e->hint_pending && cudaEventQuery(e->ev_hint) == cudaSuccess){ e->n_hint = e->st_hint->n_own; e->hint_pending = 0; }
+}
 static int sync_counts(bbx_engine *e){
     if(!e->counts_stale) return BBX_OK;
     int rc = read_state(e); if(rc) return rc;
     const DevState &s = *e->st_host;
     e->n = s.n_own; e->n_first = s.n_first; e->n_last = s.n_last; e->n_glo = s.n_glo; e->n_ghi = s.n_ghi;
+    e->n_hint = s.n_own;
     e->peer[0].n = s.peer_n[0]; e->peer[1].n = s.peer_n[1];
     e->counts_stale = 0;
     if(s.error == BBX_ERR_CAPACITY) return set_error(BBX_ERR_CAPACITY, "slab capacity exceeded: %d owned (max_particles %d), ghost planes %d / %d (ghost_capacity %d)", s.n_own, e->cap, s.n_glo, s.n_ghi, e->gcap);
@@ -402,7 +418,7 @@ static int upload_particles(bbx_engine *e, int first, int n, const void *pos, co
         CU(cudaGetLastError());
         rc = read_state(e); if(rc) return rc;
         if(e->st_host->error == BBX_ERR_CAPACITY) return set_error(BBX_ERR_CAPACITY, "slab holds more than max_particles = %d particles", e->cap);
-        e->n = e->st_host->n_own;
+        e->n = e->st_host->n_own; e->n_hint = e->n; e->hint_pending = 0; e->n_launch = bound_of(e, e->n);
         return BBX_OK;
     }
     LAUNCH(e, k_upload, div_up(n, 256), 256, n, first, sp, sv, dtype == BBX_F64, e->pos[e->cur] + first, e->vel[e->cur] + first, e->pid[e->cur] + first);
@@ -517,6 +533,7 @@ int bbx_append_particles_ids(bbx_engine *e, int n, const void *pos, const void *
     rc = read_state(e); if(rc) return rc;
     if(e->st_host->error == BBX_ERR_CAPACITY) return set_error(BBX_ERR_CAPACITY, "slab would hold more than max_particles = %d particles", e->cap);
     const int kept = e->st_host->n_own - n_old;
+    e->n_hint = n_old + kept; e->n_launch = std::max(e->n_launch, bound_of(e, n_old + kept)); // (k_slab_plan checks the count against it)
     return append_update(e, n_old, kept, n_old, id0);
 }
 
@@ -823,7 +840,12 @@ static int slab_refresh_ghosts(bbx_engine *e, int nxt){
         const unsigned seq = ++e->halo_seq[HALO_COUNTS];
         LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, mlo, mhi, halo_flag_at(e, 0, HALO_COUNTS), halo_flag_at(e, 1, HALO_COUNTS), seq);
         int rc = halo_wait(e, HALO_COUNTS, seq); if(rc) return rc;
-        LAUNCH(e, k_slab_plan, 1, 1, e->st, mail, e->has_lo, e->has_hi, (int)std::min<long long>(e->peer[0].gc, 0x7fffffff), (int)std::min<long long>(e->peer[1].gc, 0x7fffffff));
+        LAUNCH(e, k_slab_plan, 1, 1, e->st, mail, e->has_lo, e->has_hi, (int)std::min<long long>(e->peer[0].gc, 0x7fffffff), (int)std::min<long long>(e->peer[1].gc, 0x7fffffff), e->n_launch);
+        if(!e->hint_pending){ // the counts of this update on their way to the host (polled at the next update, never waited for)
+            CU(cudaMemcpyAsync(e->st_hint, e->st, sizeof(DevState), cudaMemcpyDeviceToHost, e->stream));
+            CU(cudaEventRecord(e->ev_hint, e->stream));
+            e->hint_pending = 1;
+        }
         // my freshly ordered boundary planes -> the neighbours' ghost slots (their table slices: lower ghost
         // plane at gtab, upper one at gtab + plane + 1), then the planes flag
         PushPtrs Q; memset(&Q, 0, sizeof(Q));
@@ -853,6 +875,7 @@ static int slab_refresh_ghosts(bbx_engine *e, int nxt){
         BbxSeg rhi[4] = {{e->gtab + g.plane + 1, tb}, {e->pos[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->vel[nxt] + n_new, sizeof(float4) * (size_t)ghi}, {e->pid[nxt] + n_new, sizeof(int) * (size_t)ghi}};
         COMM(e->comm->exchange(e->stream, slo, rlo, 4, shi, rhi, 4));
         e->n = n_new; e->n_first = nf; e->n_last = nl; e->n_glo = glo; e->n_ghi = ghi;
+        e->n_hint = n_new; e->n_launch = std::max(e->n_launch, bound_of(e, n_new));
         // a particle that left the slab's halo (dropped by the hash kernel) lets the collective sub-step finish first -- every
         // exchange the neighbours wait for still happens -- and is reported by the stepping call on its way out
         if(e->st_host->error == BBX_ERR_OUT_OF_DOMAIN) e->deferred_error = BBX_ERR_OUT_OF_DOMAIN;
@@ -875,7 +898,15 @@ static int grid_update(bbx_engine *e){
     // single domain: the host knows the counts.  Slab engines: they live in DevState (n_all = -1 tells the kernels to read
     // them there) and the launches cover the capacity -- nothing below waits for the host when the halo push is on.
     const int n_all = slab ? -1 : e->n, n_lo = slab ? 0 : 0, n_own = slab ? 0 : e->n;
-    const int n_bound = slab ? e->cap + 2 * e->gcap : e->n;
+    int n_bound = e->n;
+    if(slab){
+        // the slots to hash are those of the LAST update (covered by the bound it was checked against); the kernels behind
+        // the scan work on the new count, covered by the bound chosen now from the newest count the host has seen
+        poll_hint(e);
+        const int prev = e->n_launch;
+        e->n_launch = e->p2p ? bound_of(e, std::max(e->n_hint, 1)) : bound_of(e, e->n);
+        n_bound = std::max(prev, e->n_launch) + 2 * e->gcap;
+    }
     int force = (e->force_full || !e->have_chains) ? 1 : 0;
     int par = e->epoch & 1;
     const int own_cells = g.c_own1 - g.c_own0;

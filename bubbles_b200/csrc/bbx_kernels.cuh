@@ -370,11 +370,14 @@ __global__ void k_slab_counts(DevGrid g, DevState *st, const int *__restrict__ s
 // counts from MY mailbox into DevState, where every later kernel reads them -- the host is not involved.  A ghost plane
 // that would not fit (mine, or mine in the neighbour's memory) raises the sticky capacity error; the push kernel then
 // writes nothing, so no allocation is overrun.
-__global__ void k_slab_plan(DevState *st, const int *__restrict__ mail, int has_lo, int has_hi, int peer_gc_lo, int peer_gc_hi){
+__global__ void k_slab_plan(DevState *st, const int *__restrict__ mail, int has_lo, int has_hi, int peer_gc_lo, int peer_gc_hi, int launch_bound){
     const int glo = has_lo ? mail[0] : 0, ghi = has_hi ? mail[BBX_HALO_MAIL] : 0;
     st->n_glo = glo; st->n_ghi = ghi;
     st->peer_n[0] = has_lo ? mail[1] : 0; st->peer_n[1] = has_hi ? mail[BBX_HALO_MAIL + 1] : 0;
-    if(glo > st->gcap || ghi > st->gcap || (has_lo && st->n_first > peer_gc_lo) || (has_hi && st->n_last > peer_gc_hi) || st->n_own > st->cap)
+    // (launch_bound: the per-particle kernels of this sub-step are launched over that many slots -- the host chose it from an
+    // older count plus a margin; should the slab have grown past it, the sub-step is incomplete and must not go unnoticed)
+    if(glo > st->gcap || ghi > st->gcap || (has_lo && st->n_first > peer_gc_lo) || (has_hi && st->n_last > peer_gc_hi) || st->n_own > st->cap
+       || st->n_own > launch_bound)
         st->error = BBX_ERR_CAPACITY;
 }
 // host path (send / recv transport): the same fields from host values
