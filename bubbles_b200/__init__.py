@@ -6,6 +6,6 @@ an Engine does (there is no CPU fallback).
 """
 from . import _lib  # noqa: F401
 from ._lib import *  # noqa: F401,F403  (enum values)
-from .engine import (BbxError, ColliderSetBuilder3, Engine, MakeBox, MakeGrid, MakeSDFShape, MakeSphere,  # noqa: F401
+from .engine import (BbxError, ColliderSetBuilder3, Engine, MakeBox, MakeGrid, MakeMesh, MakeSDFShape, MakeSphere,  # noqa: F401
                      Translate, UtilBuildGridForDomain, identity, sdf_grid_layout)
 from .slab import LocalSlabGroup, NcclSlab, plan_slabs, plane_histogram, slab_capacity  # noqa: F401,E402

@@ -19,7 +19,7 @@ SOLVER_PCISPH, SOLVER_SPH = 0, 1
 F32, F64, I32 = 0, 1, 2
 (PHASE_GRID, PHASE_DENSITY, PHASE_FORCE_NP, PHASE_PREDICT, PHASE_PRESSURE, PHASE_PRESSURE_FORCE,
  PHASE_INTEGRATE) = range(7)
-COLLIDER_BOX, COLLIDER_SPHERE, COLLIDER_SDF = 0, 1, 2
+COLLIDER_BOX, COLLIDER_SPHERE, COLLIDER_SDF, COLLIDER_MESH = 0, 1, 2, 3
 (PARAM_VISCOSITY, PARAM_PSEUDO_VISCOSITY, PARAM_DRAG, PARAM_RESTITUTION, PARAM_NEGATIVE_PRESSURE_SCALE, PARAM_REFERENCE_COMPAT,
  PARAM_MAX_ITERATIONS, PARAM_MAX_DENSITY_ERROR_RATIO, PARAM_TIME_STEP_LIMIT_SCALE, PARAM_GRAVITY_X, PARAM_GRAVITY_Y, PARAM_GRAVITY_Z) = range(12)
 
@@ -36,7 +36,8 @@ class Collider(C.Structure):
                 ("linear_velocity", C.c_double * 3), ("angular_velocity", C.c_double * 3),
                 ("sdf_resolution", C.c_int * 3), ("reserved2", C.c_int),
                 ("sdf_spacing", C.c_double * 3), ("sdf_origin", C.c_double * 3),
-                ("sdf_field", C.c_void_p)]
+                ("sdf_field", C.c_void_p),
+                ("mesh_vertices", C.c_int), ("mesh_triangles", C.c_int), ("mesh_points", C.c_void_p), ("mesh_indices", C.c_void_p)]
 
 
 class Config(C.Structure):

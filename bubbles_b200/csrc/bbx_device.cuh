@@ -36,6 +36,10 @@ struct DevGrid {
     int c_own0, c_own1; // owned local cells [own_z0 * plane, own_z1 * plane)
 };
 
+// one node of the BVH over a mesh collider's triangles (built on the host, bbx_set_colliders): a leaf holds `count` > 0
+// triangles starting at `first` of the reordered triangle list, an inner node its two children
+struct DevBvhNode { double lo[3], hi[3]; int left, right, first, count; };
+
 struct DevCollider {
     int type, reverse, active, pad;
     double o2w[16];
@@ -52,6 +56,10 @@ struct DevCollider {
     const double *sdf_field; // device pointer
     const float *sdf_field32; // FP32 shadow of the field (pre-check only)
     double lipschitz;         // upper bound of |grad| of the trilinear field
+    // triangle mesh (BBX_COLLIDER_MESH): vertices, triangles in BVH leaf order, the BVH, bounds of the triangles
+    const double *mesh_points; const int *mesh_tris; const DevBvhNode *bvh;
+    int n_tris, n_nodes;
+    double mesh_lo[3], mesh_hi[3];
 };
 
 struct DevColliderSet {
@@ -317,7 +325,57 @@ __device__ __forceinline__ Vec3d sdf_gradient(const DevCollider &c, Vec3d p){
     return v3(gx, gy, gz);
 }
 
+// DistanceTriangle (src/shapes/bvh.cpp:212-242): the edge projections are clamped to [0.0001, 1] as there
+__device__ __forceinline__ Vec3d cross3(Vec3d a, Vec3d b){ return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ double edge_dist2(Vec3d e, Vec3d q){
+    const double t = clampd(dot3(e, q) / dot3(e, e), 0.0001, 1.0);
+    const Vec3d v = t * e - q;
+    return dot3(v, v);
+}
+__device__ __forceinline__ double distance_triangle(const DevCollider &c, Vec3d p, int t){
+    const int *ix = c.mesh_tris + 3 * (size_t)t;
+    const double *pa_ = c.mesh_points + 3 * (size_t)ix[0], *pb_ = c.mesh_points + 3 * (size_t)ix[1], *pc_ = c.mesh_points + 3 * (size_t)ix[2];
+    const Vec3d a = v3(pa_[0], pa_[1], pa_[2]), b = v3(pb_[0], pb_[1], pb_[2]), cc = v3(pc_[0], pc_[1], pc_[2]);
+    const Vec3d ba = b - a, pa = p - a, cb = cc - b, pb = p - b, ac = a - cc, pc = p - cc;
+    const Vec3d nor = cross3(ba, ac);
+    auto sgn = [](double x){ return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); };
+    const double s = sgn(dot3(cross3(ba, nor), pa)) + sgn(dot3(cross3(cb, nor), pb)) + sgn(dot3(cross3(ac, nor), pc));
+    const double v = s < 2.0 ? fmin(fmin(edge_dist2(ba, pa), edge_dist2(cb, pb)), edge_dist2(ac, pc))
+                             : dot3(nor, pa) * dot3(nor, pa) / dot3(nor, nor);
+    return sqrt(v);
+}
+// Shape::MeshClosestDistance (BVHMeshClosestDistance, src/shapes/bvh.cpp:500-557): nearest triangle through the BVH; a
+// subtree is entered only while its box is closer than the best distance so far, nearer child first
+__device__ __noinline__ double mesh_closest_distance(const DevCollider &c, Vec3d p){
+    double best = 3.1622776601683794E+18; // SqrtInfinity
+    int stack[64]; int sp = 0; int node = 0;
+    auto box_d2 = [&](const DevBvhNode &n){
+        const double x = p.x - clampd(p.x, n.lo[0], n.hi[0]), y = p.y - clampd(p.y, n.lo[1], n.hi[1]), z = p.z - clampd(p.z, n.lo[2], n.hi[2]);
+        return x * x + y * y + z * z;
+    };
+    while(node >= 0){
+        const DevBvhNode &n = c.bvh[node];
+        if(n.count > 0){
+            for(int k = 0; k < n.count; k++){ const double d = distance_triangle(c, p, n.first + k); if(d < best) best = d; }
+            node = sp > 0 ? stack[--sp] : -1;
+        }else{
+            const double b2 = best * best;
+            const double dl = box_d2(c.bvh[n.left]), dr = box_d2(c.bvh[n.right]);
+            const bool vl = dl < b2, vr = dr < b2;
+            if(vl && vr){
+                const int first = dl < dr ? n.left : n.right, second = dl < dr ? n.right : n.left;
+                if(sp < 64) stack[sp++] = second;
+                node = first;
+            }else if(vl) node = n.left;
+            else if(vr) node = n.right;
+            else node = sp > 0 ? stack[--sp] : -1;
+        }
+    }
+    return best;
+}
+
 __device__ __forceinline__ double closest_distance(const DevCollider &c, Vec3d p){
+    if(c.type == BBX_COLLIDER_MESH) return mesh_closest_distance(c, p);
     if(c.type == BBX_COLLIDER_SPHERE){
         Vec3d pl = xf_point(c.w2o, p);
         return len3(pl) - c.radius;
@@ -334,7 +392,9 @@ __device__ __noinline__ bool bbx_resolve_collision(const DevColliderSet &cs, dou
     Vec3d pos = v3(*px, *py, *pz);
     int target = -1; double minDistance = 3.4028234663852886e38; // Infinity == FLT_MAX
     for(int i = 0; i < cs.count; i++){
-        if(cs.c[i].active){
+        // (a mesh only counts for points inside its bounds: Collider3::OptmizedClosestPointCheck, collider.cpp:113-121)
+        if(cs.c[i].active && !(cs.c[i].type == BBX_COLLIDER_MESH && !inside_bounds(pos, v3(cs.c[i].mesh_lo[0], cs.c[i].mesh_lo[1], cs.c[i].mesh_lo[2]),
+                                                                              v3(cs.c[i].mesh_hi[0], cs.c[i].mesh_hi[1], cs.c[i].mesh_hi[2])))){
             double d = fabs(closest_distance(cs.c[i], pos));
             if(d < minDistance){ target = i; minDistance = d; }
         }
@@ -342,7 +402,7 @@ __device__ __noinline__ bool bbx_resolve_collision(const DevColliderSet &cs, dou
     if(target < 0) return false;
     const DevCollider &c = cs.c[target];
     Vec3d cp, nrm, cv = v3(0, 0, 0); double sd; bool inside;
-    if(c.type == BBX_COLLIDER_SDF){ // Shape::ClosestPointBySDF
+    if(c.type == BBX_COLLIDER_SDF || c.type == BBX_COLLIDER_MESH){ // any shape with a grid: Shape::ClosestPointBySDF
         Vec3d tn = v3(0, 1, 0);
         Vec3d point = xf_point(c.w2o, pos);
         Vec3d tp = point;
@@ -387,6 +447,8 @@ __device__ __noinline__ bool bbx_resolve_collision(const DevColliderSet &cs, dou
         sd = box_query(c, pos, true, &cp, &nrm);
         inside = (c.reverse != 0) == !(sd < 0);
     }
+    // Collider3::IsPenetrating (collider.cpp:123-133)
+    if(c.type == BBX_COLLIDER_MESH && !inside_bounds(pos, v3(c.mesh_lo[0], c.mesh_lo[1], c.mesh_lo[2]), v3(c.mesh_hi[0], c.mesh_hi[1], c.mesh_hi[2]))) return false;
     if(!(inside || fabs(sd) < radius)) return false;
     Vec3d tp = cp + radius * nrm;
     Vec3d vel = v3(*vx, *vy, *vz);

@@ -24,6 +24,8 @@ static int set_error(int code, const char *fmt, ...){
 #define CU(call) do{ cudaError_t _e = (call); if(_e != cudaSuccess) return set_error(BBX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); }while(0)
 #define CHECK_ENGINE(e) do{ if(!(e)) return set_error(BBX_ERR_INVALID, "null engine"); CU(cudaSetDevice((e)->device)); }while(0)
 
+#define BBX_HINT_RING 4
+#define BBX_HINT_LAG 2
 enum { T_GRID = 0, T_DENSITY, T_FORCE_NP, T_PREDICT, T_PRESSURE, T_PRESSURE_FORCE, T_INTEGRATE, T_COUNT };
 
 struct bbx_engine {
@@ -73,10 +75,11 @@ struct bbx_engine {
     DevState *st; DevState *st_host; // st_host pinned
     int *err_probe;  // pinned: copy of st->error enqueued behind every sub-step (no sync); checked by the next API call
     int sm_count;    // multiprocessors of the device (persistent grids are sized from it)
-    // slab engines with the halo push launch their per-particle kernels over a BOUND of the owned count: the last count the
-    // host has seen (an asynchronous copy of DevState behind every grid update, polled -- never waited for) plus a margin;
-    // k_slab_plan checks the real count against the bound on the device (sticky capacity error if it was ever too small)
-    DevState *st_hint; cudaEvent_t ev_hint; int hint_pending; int n_hint; int n_launch;
+    // slab engines with the halo push launch their per-particle kernels over a BOUND of the owned count: the count of the grid
+    // update BBX_HINT_LAG sub-steps back (an asynchronous copy of DevState behind every update, in a small ring; the host
+    // waits for THAT old copy only, which also keeps it from running more than a few sub-steps ahead of the device) plus a
+    // margin; k_slab_plan checks the real count against the bound on the device (sticky capacity error if ever too small)
+    DevState *st_hint; cudaEvent_t ev_hint[BBX_HINT_RING]; long long hint_count; int n_hint; int n_launch;
     int counts_stale;   // slab engines with the halo push: n / n_first / n_last / ghost counts live in DevState; the host copies
                         // (e->n ...) are refreshed by sync_counts() when an API call needs them
     int deferred_error; // slab engines: a device-side error seen in the middle of a collective sub-step; the sub-step is
@@ -85,6 +88,7 @@ struct bbx_engine {
     DevCullSet *cull; DevCullSet cull_host;
     std::vector<double *> sdf_fields;
     std::vector<float *> sdf_fields32;
+    std::vector<void *> mesh_allocs; // device copies of mesh colliders: vertices, triangles in BVH leaf order, BVH nodes
     void *stage; size_t stage_bytes; // device staging for upload / download
     long long launches;
     int substeps;
@@ -192,7 +196,7 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     e->nbr = nullptr; e->nbr_cnt = nullptr; e->force = e->force_p = e->pred = e->posq = e->smoothed = e->rec = nullptr;
     e->pressure = e->rho_pred = e->rho_err = nullptr; e->st = nullptr; e->st_host = nullptr; e->err_probe = nullptr;
     e->colliders = nullptr; e->cull = nullptr; e->gtab = nullptr; e->halo_flags = nullptr; e->mail_host = nullptr; e->stage = nullptr;
-    e->st_hint = nullptr; e->ev_hint = nullptr; e->hint_pending = 0; e->n_hint = 0; e->n_launch = 0;
+    e->st_hint = nullptr; for(int k = 0; k < BBX_HINT_RING; k++) e->ev_hint[k] = nullptr; e->hint_count = 0; e->n_hint = 0; e->n_launch = 0;
     memset(&e->cfg, 0, sizeof(e->cfg));
     e->cfg = *cfg;
     e->device = cfg->device;
@@ -293,9 +297,9 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     CU(cudaMemset(e->count, 0, sizeof(int) * ((size_t)g.total + 8)));
     CU(cudaMallocHost((void **)&e->st_host, sizeof(DevState)));
     CU(cudaMallocHost((void **)&e->err_probe, sizeof(int)));
-    CU(cudaMallocHost((void **)&e->st_hint, sizeof(DevState)));
-    memset(e->st_hint, 0, sizeof(DevState));
-    CU(cudaEventCreateWithFlags(&e->ev_hint, cudaEventDisableTiming));
+    CU(cudaMallocHost((void **)&e->st_hint, BBX_HINT_RING * sizeof(DevState)));
+    memset(e->st_hint, 0, BBX_HINT_RING * sizeof(DevState));
+    for(int k = 0; k < BBX_HINT_RING; k++) CU(cudaEventCreateWithFlags(&e->ev_hint[k], cudaEventDisableTiming));
     *e->err_probe = 0;
     memset(e->st_host, 0, sizeof(DevState));
     e->st_host->cap = e->cap; e->st_host->gcap = e->gcap;
@@ -326,9 +330,10 @@ int bbx_destroy(bbx_engine *e){
     cudaFree(e->st); cudaFree(e->colliders); cudaFree(e->cull); if(e->st_host) cudaFreeHost(e->st_host);
     if(e->err_probe) cudaFreeHost(e->err_probe);
     if(e->st_hint) cudaFreeHost(e->st_hint);
-    if(e->ev_hint) cudaEventDestroy(e->ev_hint);
+    for(int k = 0; k < BBX_HINT_RING; k++) if(e->ev_hint[k]) cudaEventDestroy(e->ev_hint[k]);
     for(double *f : e->sdf_fields) cudaFree(f);
     for(float *f : e->sdf_fields32) cudaFree(f);
+    for(void *m : e->mesh_allocs) cudaFree(m);
     if(e->stage) cudaFree(e->stage);
     for(cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
     if(e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -386,16 +391,22 @@ static int grid_update(bbx_engine *e);
 // transport of the cold paths).
 static inline int launch_n(const bbx_engine *e){ return IS_SLAB(e) ? e->n_launch : e->n; }
 static inline int bound_of(const bbx_engine *e, int n){ return (int)std::min<long long>(e->cap, (long long)n + n / 16 + 4096); }
-// the newest owned count that has reached the host, without waiting for anything
-static void poll_hint(bbx_engine *e){
-    if(e->hint_pending && cudaEventQuery(e->ev_hint) == cudaSuccess){ e->n_hint = e->st_hint->n_own; e->hint_pending = 0; }
+// the owned count of the grid update BBX_HINT_LAG sub-steps back (by now that copy has long landed unless the host is
+// running ahead -- then this is where it waits, a couple of sub-steps of device work still queued behind it)
+static int poll_hint(bbx_engine *e){
+    if(e->hint_count >= BBX_HINT_LAG){
+        const int slot = (int)((e->hint_count - BBX_HINT_LAG) % BBX_HINT_RING);
+        CU(cudaEventSynchronize(e->ev_hint[slot]));
+        e->n_hint = e->st_hint[slot].n_own;
+    }
+    return BBX_OK;
 }
 static int sync_counts(bbx_engine *e){
     if(!e->counts_stale) return BBX_OK;
     int rc = read_state(e); if(rc) return rc;
     const DevState &s = *e->st_host;
     e->n = s.n_own; e->n_first = s.n_first; e->n_last = s.n_last; e->n_glo = s.n_glo; e->n_ghi = s.n_ghi;
-    e->n_hint = s.n_own;
+    e->n_hint = s.n_own; e->hint_count = 0;
     e->peer[0].n = s.peer_n[0]; e->peer[1].n = s.peer_n[1];
     e->counts_stale = 0;
     if(s.error == BBX_ERR_CAPACITY) return set_error(BBX_ERR_CAPACITY, "slab capacity exceeded: %d owned (max_particles %d), ghost planes %d / %d (ghost_capacity %d)", s.n_own, e->cap, s.n_glo, s.n_ghi, e->gcap);
@@ -418,7 +429,7 @@ static int upload_particles(bbx_engine *e, int first, int n, const void *pos, co
         CU(cudaGetLastError());
         rc = read_state(e); if(rc) return rc;
         if(e->st_host->error == BBX_ERR_CAPACITY) return set_error(BBX_ERR_CAPACITY, "slab holds more than max_particles = %d particles", e->cap);
-        e->n = e->st_host->n_own; e->n_hint = e->n; e->hint_pending = 0; e->n_launch = bound_of(e, e->n);
+        e->n = e->st_host->n_own; e->n_hint = e->n; e->hint_count = 0; e->n_launch = bound_of(e, e->n);
         return BBX_OK;
     }
     LAUNCH(e, k_upload, div_up(n, 256), 256, n, first, sp, sv, dtype == BBX_F64, e->pos[e->cur] + first, e->vel[e->cur] + first, e->pid[e->cur] + first);
@@ -533,7 +544,7 @@ int bbx_append_particles_ids(bbx_engine *e, int n, const void *pos, const void *
     rc = read_state(e); if(rc) return rc;
     if(e->st_host->error == BBX_ERR_CAPACITY) return set_error(BBX_ERR_CAPACITY, "slab would hold more than max_particles = %d particles", e->cap);
     const int kept = e->st_host->n_own - n_old;
-    e->n_hint = n_old + kept; e->n_launch = std::max(e->n_launch, bound_of(e, n_old + kept)); // (k_slab_plan checks the count against it)
+    e->n_hint = n_old + kept; e->hint_count = 0; e->n_launch = std::max(e->n_launch, bound_of(e, n_old + kept)); // (k_slab_plan checks the count against it)
     return append_update(e, n_old, kept, n_old, id0);
 }
 
@@ -579,15 +590,69 @@ int bbx_overwrite_owned(bbx_engine *e, const void *pos, const void *vel, int dty
 }
 
 // ------------------------------------------------------------------------------------ colliders
+// BVH over the triangles of a mesh collider (host): median split of the centroids along the widest axis, leaves of <= 4
+// triangles.  Any BVH gives the same closest distance (the traversal only skips boxes that cannot beat the best so far).
+struct BvhTri { double lo[3], hi[3], ctr[3]; int id; };
+static int bvh_build(std::vector<DevBvhNode> &nodes, std::vector<BvhTri> &tris, int begin, int end){
+    const int me = (int)nodes.size();
+    nodes.push_back(DevBvhNode());
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+    for(int t = begin; t < end; t++) for(int k = 0; k < 3; k++){
+        lo[k] = std::min(lo[k], tris[t].lo[k]); hi[k] = std::max(hi[k], tris[t].hi[k]);
+        clo[k] = std::min(clo[k], tris[t].ctr[k]); chi[k] = std::max(chi[k], tris[t].ctr[k]);
+    }
+    DevBvhNode n; memset(&n, 0, sizeof(n));
+    for(int k = 0; k < 3; k++){ n.lo[k] = lo[k]; n.hi[k] = hi[k]; }
+    n.left = n.right = -1; n.first = begin; n.count = 0;
+    if(end - begin <= 4){ n.count = end - begin; nodes[me] = n; return me; }
+    int axis = 0; for(int k = 1; k < 3; k++) if(chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+    const int mid = (begin + end) / 2;
+    std::nth_element(tris.begin() + begin, tris.begin() + mid, tris.begin() + end, [axis](const BvhTri &a, const BvhTri &b){ return a.ctr[axis] < b.ctr[axis]; });
+    n.left = bvh_build(nodes, tris, begin, mid);
+    n.right = bvh_build(nodes, tris, mid, end);
+    nodes[me] = n;
+    return me;
+}
+static int fill_mesh(bbx_engine *e, DevCollider &d, const bbx_collider &c){
+    if(c.mesh_vertices <= 0 || c.mesh_triangles <= 0 || !c.mesh_points || !c.mesh_indices) return set_error(BBX_ERR_INVALID, "mesh collider without triangles");
+    const int nv = c.mesh_vertices, nt = c.mesh_triangles;
+    std::vector<BvhTri> tris((size_t)nt);
+    for(int t = 0; t < nt; t++){
+        BvhTri &b = tris[t]; b.id = t;
+        for(int k = 0; k < 3; k++){ b.lo[k] = 1e300; b.hi[k] = -1e300; b.ctr[k] = 0; }
+        for(int v = 0; v < 3; v++){
+            const int ix = c.mesh_indices[3 * (size_t)t + v];
+            if(ix < 0 || ix >= nv) return set_error(BBX_ERR_INVALID, "mesh index %d out of range (%d vertices)", ix, nv);
+            for(int k = 0; k < 3; k++){ const double x = c.mesh_points[3 * (size_t)ix + k]; b.lo[k] = std::min(b.lo[k], x); b.hi[k] = std::max(b.hi[k], x); b.ctr[k] += x / 3.0; }
+        }
+    }
+    std::vector<DevBvhNode> nodes; nodes.reserve((size_t)nt);
+    bvh_build(nodes, tris, 0, nt);
+    std::vector<int> order(3 * (size_t)nt);
+    for(int t = 0; t < nt; t++) for(int v = 0; v < 3; v++) order[3 * (size_t)t + v] = c.mesh_indices[3 * (size_t)tris[t].id + v];
+    double *dp = nullptr; int *di = nullptr; DevBvhNode *dn = nullptr;
+    CU(cudaMalloc((void **)&dp, sizeof(double) * 3 * (size_t)nv)); e->mesh_allocs.push_back(dp);
+    CU(cudaMalloc((void **)&di, sizeof(int) * 3 * (size_t)nt)); e->mesh_allocs.push_back(di);
+    CU(cudaMalloc((void **)&dn, sizeof(DevBvhNode) * nodes.size())); e->mesh_allocs.push_back(dn);
+    CU(cudaMemcpy(dp, c.mesh_points, sizeof(double) * 3 * (size_t)nv, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(di, order.data(), sizeof(int) * 3 * (size_t)nt, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dn, nodes.data(), sizeof(DevBvhNode) * nodes.size(), cudaMemcpyHostToDevice));
+    d.mesh_points = dp; d.mesh_tris = di; d.bvh = dn; d.n_tris = nt; d.n_nodes = (int)nodes.size();
+    for(int k = 0; k < 3; k++){ d.mesh_lo[k] = nodes[0].lo[k]; d.mesh_hi[k] = nodes[0].hi[k]; } // MeshGetBounds = the BVH root
+    return BBX_OK;
+}
+
 static int fill_collider(bbx_engine *e, DevCollider &d, const bbx_collider &c){
-    if(c.type < BBX_COLLIDER_BOX || c.type > BBX_COLLIDER_SDF) return set_error(BBX_ERR_INVALID, "unknown collider type %d", c.type);
+    if(c.type < BBX_COLLIDER_BOX || c.type > BBX_COLLIDER_MESH) return set_error(BBX_ERR_INVALID, "unknown collider type %d", c.type);
     d.type = c.type; d.reverse = c.reverse_orientation ? 1 : 0; d.active = c.active ? 1 : 0;
     memcpy(d.o2w, c.object_to_world, sizeof(d.o2w)); memcpy(d.w2o, c.world_to_object, sizeof(d.w2o));
     memcpy(d.size, c.size, sizeof(d.size)); d.radius = c.radius; d.friction = c.friction;
     memcpy(d.linvel, c.linear_velocity, sizeof(d.linvel)); memcpy(d.angvel, c.angular_velocity, sizeof(d.angvel));
     d.sdf_field = nullptr; d.sdf_field32 = nullptr; d.lipschitz = 0.0;
-    if(c.type == BBX_COLLIDER_SDF){
-        if(!c.sdf_field) return set_error(BBX_ERR_INVALID, "SDF collider without field");
+    d.mesh_points = nullptr; d.mesh_tris = nullptr; d.bvh = nullptr; d.n_tris = d.n_nodes = 0;
+    if(c.type == BBX_COLLIDER_MESH){ int rc = fill_mesh(e, d, c); if(rc) return rc; }
+    if(c.type == BBX_COLLIDER_SDF || c.type == BBX_COLLIDER_MESH){
+        if(!c.sdf_field) return set_error(BBX_ERR_INVALID, c.type == BBX_COLLIDER_MESH ? "mesh collider without its SDF grid" : "SDF collider without field");
         size_t total = (size_t)c.sdf_resolution[0] * c.sdf_resolution[1] * c.sdf_resolution[2];
         if(total == 0) return set_error(BBX_ERR_INVALID, "SDF collider with empty grid");
         double *dev = nullptr;
@@ -669,6 +734,8 @@ int bbx_set_colliders(bbx_engine *e, int n, const bbx_collider *colliders){
     e->sdf_fields.clear();
     for(float *f : e->sdf_fields32) cudaFree(f);
     e->sdf_fields32.clear();
+    for(void *m : e->mesh_allocs) cudaFree(m);
+    e->mesh_allocs.clear();
     memset(&e->colliders_host, 0, sizeof(DevColliderSet));
     for(int i = 0; i < n; i++){ int rc = fill_collider(e, e->colliders_host.c[i], colliders[i]); if(rc) return rc; }
     e->colliders_host.count = n;
@@ -679,6 +746,8 @@ int bbx_update_collider(bbx_engine *e, int index, const bbx_collider *c){
     if(!c || index < 0 || index >= e->colliders_host.count) return set_error(BBX_ERR_INVALID, "collider index out of range");
     DevCollider &d = e->colliders_host.c[index];
     if(c->type != d.type) return set_error(BBX_ERR_INVALID, "bbx_update_collider cannot change the collider type");
+    if(d.type == BBX_COLLIDER_MESH && (memcmp(d.o2w, c->object_to_world, sizeof(d.o2w)) != 0))
+        return set_error(BBX_ERR_INVALID, "a mesh collider is stored in world space with its baked SDF: it cannot be moved, set the colliders again");
     const double *keep = d.sdf_field; // the baked field (and its FP32 shadow, Lipschitz bound) stay
     d.reverse = c->reverse_orientation ? 1 : 0; d.active = c->active ? 1 : 0;
     memcpy(d.o2w, c->object_to_world, sizeof(d.o2w)); memcpy(d.w2o, c->world_to_object, sizeof(d.w2o));
@@ -841,10 +910,11 @@ static int slab_refresh_ghosts(bbx_engine *e, int nxt){
         LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, mlo, mhi, halo_flag_at(e, 0, HALO_COUNTS), halo_flag_at(e, 1, HALO_COUNTS), seq);
         int rc = halo_wait(e, HALO_COUNTS, seq); if(rc) return rc;
         LAUNCH(e, k_slab_plan, 1, 1, e->st, mail, e->has_lo, e->has_hi, (int)std::min<long long>(e->peer[0].gc, 0x7fffffff), (int)std::min<long long>(e->peer[1].gc, 0x7fffffff), e->n_launch);
-        if(!e->hint_pending){ // the counts of this update on their way to the host (polled at the next update, never waited for)
-            CU(cudaMemcpyAsync(e->st_hint, e->st, sizeof(DevState), cudaMemcpyDeviceToHost, e->stream));
-            CU(cudaEventRecord(e->ev_hint, e->stream));
-            e->hint_pending = 1;
+        {   // the counts of this update on their way to the host (looked at BBX_HINT_LAG updates from now)
+            const int slot = (int)(e->hint_count % BBX_HINT_RING);
+            CU(cudaMemcpyAsync(&e->st_hint[slot], e->st, sizeof(DevState), cudaMemcpyDeviceToHost, e->stream));
+            CU(cudaEventRecord(e->ev_hint[slot], e->stream));
+            e->hint_count++;
         }
         // my freshly ordered boundary planes -> the neighbours' ghost slots (their table slices: lower ghost
         // plane at gtab, upper one at gtab + plane + 1), then the planes flag
@@ -902,7 +972,7 @@ static int grid_update(bbx_engine *e){
     if(slab){
         // the slots to hash are those of the LAST update (covered by the bound it was checked against); the kernels behind
         // the scan work on the new count, covered by the bound chosen now from the newest count the host has seen
-        poll_hint(e);
+        { int rc = poll_hint(e); if(rc) return rc; }
         const int prev = e->n_launch;
         e->n_launch = e->p2p ? bound_of(e, std::max(e->n_hint, 1)) : bound_of(e, e->n);
         n_bound = std::max(prev, e->n_launch) + 2 * e->gcap;

@@ -377,8 +377,12 @@ __global__ void k_slab_plan(DevState *st, const int *__restrict__ mail, int has_
     // (launch_bound: the per-particle kernels of this sub-step are launched over that many slots -- the host chose it from an
     // older count plus a margin; should the slab have grown past it, the sub-step is incomplete and must not go unnoticed)
     if(glo > st->gcap || ghi > st->gcap || (has_lo && st->n_first > peer_gc_lo) || (has_hi && st->n_last > peer_gc_hi) || st->n_own > st->cap
-       || st->n_own > launch_bound)
+       || st->n_own > launch_bound){
         st->error = BBX_ERR_CAPACITY;
+        // the run is flagged and stops at the next API call; until then every kernel of this engine becomes a no-op, so that
+        // nothing indexes past an allocation or past its launch
+        st->n_glo = 0; st->n_ghi = 0; st->n_own = 0; st->n_occ = 0; st->n_first = 0; st->n_last = 0;
+    }
 }
 // host path (send / recv transport): the same fields from host values
 __global__ void k_slab_plan_host(DevState *st, int glo, int ghi, int peer_lo, int peer_hi){

@@ -102,6 +102,20 @@ def MakeSDFShape(bounds_min, bounds_max, sdf, dx=0.01, margin=0.1):
     return c
 
 
+def MakeMesh(vertices, triangles, sdf, reverse_orientation=False):
+    """MakeMesh (shape.h:275) + the SDF grid the collider set generates for it (GenerateShapeSDF, shape.cpp:479-511):
+    vertices [n, 3], triangles [m, 3], sdf = dict(res=node counts, spacing=(dx, dy, dz), origin, field float64 x-fastest)."""
+    c = _shape(L.COLLIDER_MESH, None, reverse_orientation, sdf_resolution=tuple(int(r) for r in sdf["res"]),
+               sdf_spacing=tuple(float(x) for x in sdf["spacing"]), sdf_origin=tuple(float(x) for x in sdf["origin"]))
+    c._field = np.ascontiguousarray(sdf["field"], dtype=np.float64)
+    c._points = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+    c._indices = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
+    c.sdf_field = c._field.ctypes.data
+    c.mesh_vertices, c.mesh_triangles = len(c._points), len(c._indices)
+    c.mesh_points, c.mesh_indices = c._points.ctypes.data, c._indices.ctypes.data
+    return c
+
+
 def UtilBuildGridForDomain(domain_min, domain_max, spacing, spacing_scale):
     g = L.GridDesc()
     _check(L.load().bbx_grid_for_domain(_vec3(domain_min), _vec3(domain_max), spacing, spacing_scale, C.byref(g)))

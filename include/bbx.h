@@ -69,7 +69,11 @@ enum bbx_phase {
     BBX_PHASE_INTEGRATE = 6    /* AccumulateAndIntegrateGPU (:207-212) + pseudo-viscosity (cold)               */
 };
 
-enum bbx_collider_type { BBX_COLLIDER_BOX = 0, BBX_COLLIDER_SPHERE = 1, BBX_COLLIDER_SDF = 2 };
+/* BBX_COLLIDER_MESH = a Shape of type ShapeMesh (MakeMesh, src/shapes/bvh.cpp:51-56) with the SDF grid the collider set
+ * generates for it (ColliderSet3::GenerateSDFs -> GenerateShapeSDF, src/core/shape.cpp:479-511): the triangles decide which
+ * collider is nearest (Shape::MeshClosestDistance through a BVH, and only for points inside the mesh bounds:
+ * Collider3::OptmizedClosestPointCheck, collider.cpp:113-121), the grid gives closest point, normal and inside test. */
+enum bbx_collider_type { BBX_COLLIDER_BOX = 0, BBX_COLLIDER_SPHERE = 1, BBX_COLLIDER_SDF = 2, BBX_COLLIDER_MESH = 3 };
 
 /* One collider = Collider3 + Shape (src/core/collider.h:55-73, src/core/shape.h:140-170).
  * Matrices are row-major 4x4 (Transform::m / mInv, src/core/transform.h:399-416). */
@@ -92,6 +96,10 @@ typedef struct bbx_collider {
     double sdf_spacing[3];
     double sdf_origin[3];
     const double *sdf_field;  /* host pointer, copied by bbx_set_colliders                   */
+    /* triangle mesh (BBX_COLLIDER_MESH; world space, as Transform::Mesh leaves it): copied by bbx_set_colliders */
+    int mesh_vertices, mesh_triangles;
+    const double *mesh_points;   /* mesh_vertices x 3                                        */
+    const int *mesh_indices;     /* mesh_triangles x 3                                       */
 } bbx_collider;
 
 /* Grid geometry = result of UtilBuildGridForDomain / MakeGrid (src/core/util.cpp:269-287,

@@ -38,7 +38,9 @@ class Collider(C.Structure):
                 ("linvel", C.c_double * 3), ("angvel", C.c_double * 3),
                 ("sdf_res", C.c_int * 3), ("_pad2", C.c_int),
                 ("sdf_spacing", C.c_double * 3), ("sdf_origin", C.c_double * 3),
-                ("sdf_field", C.c_void_p)]
+                ("sdf_field", C.c_void_p),
+                ("n_vertices", C.c_int), ("n_triangles", C.c_int), ("vertices", C.c_void_p), ("indices", C.c_void_p),
+                ("mesh_min", C.c_double * 3), ("mesh_max", C.c_double * 3)]
 
 
 class Params(C.Structure):
@@ -102,10 +104,11 @@ def translate(x, y, z):
 
 
 def make_collider(kind, o2w=IDENTITY, size=(0, 0, 0), radius=0.0, reverse=False, friction=0.0,
-                  active=True, linvel=(0, 0, 0), angvel=(0, 0, 0), sdf=None, w2o=None):
-    """kind: 'box' | 'sphere' | 'sdf'. sdf = dict(res=(nx,ny,nz) nodes, spacing, origin, field float64)."""
+                  active=True, linvel=(0, 0, 0), angvel=(0, 0, 0), sdf=None, w2o=None, mesh=None):
+    """kind: 'box' | 'sphere' | 'sdf' | 'mesh'. sdf = dict(res=(nx,ny,nz) nodes, spacing, origin, field float64);
+    mesh = (vertices [n, 3] float64, triangles [m, 3] int32), together with the sdf generated for it."""
     c = Collider()
-    c.type = {"box": 0, "sphere": 1, "sdf": 2}[kind]
+    c.type = {"box": 0, "sphere": 1, "sdf": 2, "mesh": 3}[kind]
     c.reverse = int(reverse)
     c.active = int(active)
     o2w = np.asarray(o2w, dtype=np.float64)
@@ -130,6 +133,14 @@ def make_collider(kind, o2w=IDENTITY, size=(0, 0, 0), radius=0.0, reverse=False,
         c.sdf_origin[:] = sdf["origin"]
         c._field = np.ascontiguousarray(sdf["field"], dtype=np.float64)
         c.sdf_field = c._field.ctypes.data
+    if mesh is not None:
+        c._vertices = np.ascontiguousarray(mesh[0], dtype=np.float64)
+        c._indices = np.ascontiguousarray(mesh[1], dtype=np.int32)
+        c.n_vertices, c.n_triangles = len(c._vertices), len(c._indices)
+        c.vertices, c.indices = c._vertices.ctypes.data, c._indices.ctypes.data
+        used = c._vertices[np.unique(c._indices)]      # bounds of the BVH root = of the triangles (bvh.cpp, MeshGetBounds)
+        c.mesh_min[:] = used.min(axis=0)
+        c.mesh_max[:] = used.max(axis=0)
     return c
 
 
@@ -338,6 +349,13 @@ class Oracle:
         self.L.orc_resolve_collision_many(C.byref(self.P), C.c_double(radius), C.c_double(restitution),
                                           len(pos), _p(pos), _p(vel), _p(hit))
         return pos, vel, hit
+
+    def mesh_closest_distance(self, index, points):
+        """Shape::MeshClosestDistance of collider `index` at points [n, 3]"""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        self.L.orc_mesh_closest_distance.restype = C.c_double
+        self.L.orc_mesh_closest_distance.argtypes = [C.POINTER(Collider), C.c_void_p]
+        return np.array([self.L.orc_mesh_closest_distance(C.byref(self._colliders[index]), _p(pts[i])) for i in range(len(pts))])
 
     def number_of_time_steps(self, time_step, scale):
         return self.L.orc_number_of_time_steps(C.byref(self.P), self.S.n, _p(self.a["force"]), time_step, scale)

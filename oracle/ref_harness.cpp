@@ -46,6 +46,8 @@ void CudaMemoryManagerClearCurrent(){}
 void CudaMemoryManagerClearAll(){}
 #endif
 // lives in the (excluded) 2D solver: src/solvers/pcisph_solver2.cpp:7
+// (src/core/shape.cpp:411-431, not declared in a header)
+bb_cpu_gpu void SetNodeSDFKernel(FieldGrid3f *grid, Shape *shape, int i);
 extern const Float kDefaultTimeStepLimitScale = 5.0;
 
 // free functions defined (non-static) in the reference translation units
@@ -325,6 +327,43 @@ int main(int argc, char **argv){
                 }
                 shape->grid->MarkFilled();
                 H.shapes.push_back(shape); H.frictions.push_back(fr);
+            }else if(kind == "mesh"){
+                // triangle-mesh collider: MakeMesh (src/shapes/bvh.cpp:51-56: BVH over the triangles) + the SDF the collider set
+                // generates for it, GenerateShapeSDF (src/core/shape.cpp:479-511) -- whose kernel launch is replaced by a host
+                // loop over the same per-node function (SetNodeSDFKernel, shape.cpp:411-431: BVH closest distance, sign by
+                // ray parity), because there is no device here.  File: int64 nv, nt; nv x 3 doubles; nt x 3 int32.
+                std::string file; int rev; Float fr, dx, margin;
+                in >> file >> rev >> fr >> dx >> margin;
+                FILE *fp = fopen(file.c_str(), "rb");
+                if(!fp){ fprintf(stderr, "cannot open mesh %s\n", file.c_str()); return 2; }
+                int64_t nv = 0, nt = 0; size_t got = fread(&nv, 8, 1, fp) + fread(&nt, 8, 1, fp);
+                std::vector<double> vp(3 * nv); std::vector<int32_t> vi(3 * nt);
+                got += fread(vp.data(), 8, 3 * nv, fp) + fread(vi.data(), 4, 3 * nt, fp);
+                fclose(fp);
+                if(got != (size_t)(2 + 3 * nv + 3 * nt)){ fprintf(stderr, "short mesh file\n"); return 2; }
+                ParsedMesh *mesh = (ParsedMesh *)calloc(1, sizeof(ParsedMesh));
+                mesh->p = (Point3f *)calloc(nv, sizeof(Point3f));
+                mesh->indices = (Point3i *)calloc(3 * nt, sizeof(Point3i));
+                for(int64_t i = 0; i < nv; i++) mesh->p[i] = Point3f(vp[3 * i], vp[3 * i + 1], vp[3 * i + 2]);
+                for(int64_t i = 0; i < 3 * nt; i++) mesh->indices[i] = Point3i(vi[i], 0, 0);
+                mesh->nTriangles = (int)nt; mesh->nVertices = (int)nv;
+                snprintf(mesh->name, sizeof(mesh->name), "harness-mesh");
+                Shape *shape = MakeMesh(mesh, Transform(), rev != 0);
+                {   // GenerateShapeSDF(shape, dx, margin), host loop instead of GPULaunch(CreateShapeSDFGPU)
+                    Bounds3f bounds = shape->GetBounds();
+                    vec3f sc(bounds.ExtentOn(0), bounds.ExtentOn(1), bounds.ExtentOn(2));
+                    bounds.pMin -= margin * sc; bounds.pMax += margin * sc;
+                    Float width = bounds.ExtentOn(0), height = bounds.ExtentOn(1), depth = bounds.ExtentOn(2);
+                    int resolution = (int)std::ceil(width / dx);
+                    dx = width / (Float)resolution;
+                    int resolutionY = (int)std::ceil(resolution * height / width);
+                    int resolutionZ = (int)std::ceil(resolution * depth / width);
+                    shape->grid = (FieldGrid3f *)calloc(1, sizeof(FieldGrid3f));
+                    shape->grid->Build(vec3ui(resolution, resolutionY, resolutionZ), vec3f(dx), bounds.pMin, VertexCentered);
+                    for(unsigned int i = 0; i < shape->grid->total; i++) SetNodeSDFKernel(shape->grid, shape, (int)i);
+                    shape->grid->MarkFilled();
+                }
+                H.shapes.push_back(shape); H.frictions.push_back(fr);
             }else{ fprintf(stderr, "unknown collider %s\n", kind.c_str()); return 2; }
         }
         else if(cmd == "emit_box"){
@@ -461,6 +500,31 @@ int main(int argc, char **argv){
             WriteNpy<double>(prefix + "pos.npy", pos.data(), n, 3);
             WriteNpy<double>(prefix + "vel.npy", vel.data(), n, 3);
             WriteNpy<int32_t>(prefix + "hit.npy", hit.data(), n, 0);
+        }
+        else if(cmd == "dump_sdf"){
+            // the SDF grid attached to shape idx: node counts, spacing, origin (position of node 0), field (x fastest)
+            int idx; std::string prefix; in >> idx >> prefix;
+            FieldGrid3f *gr = H.shapes[idx]->grid;
+            if(!gr){ fprintf(stderr, "shape %d has no sdf grid\n", idx); return 2; }
+            int32_t res[3] = {(int32_t)gr->resolution.x, (int32_t)gr->resolution.y, (int32_t)gr->resolution.z};
+            vec3f p0 = gr->GetDataPosition(vec3ui(0, 0, 0));
+            double meta[6] = {(double)gr->spacing.x, (double)gr->spacing.y, (double)gr->spacing.z, (double)p0.x, (double)p0.y, (double)p0.z};
+            WriteNpy<int32_t>(prefix + "res.npy", res, 3, 0);
+            WriteNpy<double>(prefix + "meta.npy", meta, 6, 0);
+            WriteNpy<double>(prefix + "field.npy", gr->field, gr->total, 0);
+            Bounds3f b = H.shapes[idx]->GetBounds();
+            double bb[6] = {(double)b.pMin.x, (double)b.pMin.y, (double)b.pMin.z, (double)b.pMax.x, (double)b.pMax.y, (double)b.pMax.z};
+            WriteNpy<double>(prefix + "bounds.npy", bb, 6, 0);
+        }
+        else if(cmd == "closest_distance"){
+            // Shape::ClosestDistance of shape idx at a list of points (mesh: BVHMeshClosestDistance, bvh.cpp:500-557)
+            int idx; std::string file, prefix; in >> idx >> file >> prefix;
+            FILE *fp = fopen(file.c_str(), "rb");
+            int64_t n = 0; size_t r = fread(&n, sizeof(n), 1, fp);
+            std::vector<double> pos(3 * n), out(n);
+            r += fread(pos.data(), 8, 3 * n, fp); fclose(fp);
+            for(int64_t i = 0; i < n; i++) out[i] = H.shapes[idx]->ClosestDistance(vec3f(pos[3*i], pos[3*i+1], pos[3*i+2]));
+            WriteNpy<double>(prefix + "distance.npy", out.data(), n, 0);
         }
         else if(cmd == "save_frame"){
             // the reference's own frame writer (SerializerSaveSphDataSet3, src/third/serializer.cpp:884-921) on the current state
