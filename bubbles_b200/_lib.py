@@ -86,6 +86,7 @@ SYMBOLS = {
     "bbx_set_colliders": (C.c_int, [_E, C.c_int, C.POINTER(Collider)]),
     "bbx_update_collider": (C.c_int, [_E, C.c_int, C.POINTER(Collider)]),
     "bbx_set_collider_active": (C.c_int, [_E, C.c_int, C.c_int]),
+    "bbx_collider_distance": (C.c_int, [_E, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bbx_step_pcisph": (C.c_int, [_E, C.c_double]),
     "bbx_step_sph": (C.c_int, [_E, C.c_double]),
     "bbx_advance": (C.c_int, [_E, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]),

@@ -756,6 +756,21 @@ int bbx_update_collider(bbx_engine *e, int index, const bbx_collider *c){
     d.sdf_field = keep;
     return push_colliders(e);
 }
+int bbx_collider_distance(bbx_engine *e, int index, int n, const double *points, double *out){
+    CHECK_ENGINE(e);
+    if(index < 0 || index >= e->colliders_host.count) return set_error(BBX_ERR_INVALID, "collider index out of range");
+    if(n <= 0) return BBX_OK;
+    if(!points || !out) return set_error(BBX_ERR_INVALID, "null");
+    const size_t bp = sizeof(double) * 3 * (size_t)n, bo = sizeof(double) * (size_t)n;
+    int rc = ensure_stage(e, bp + bo); if(rc) return rc;
+    double *dp = (double *)e->stage, *dout = dp + 3 * (size_t)n;
+    CU(cudaMemcpyAsync(dp, points, bp, cudaMemcpyHostToDevice, e->stream));
+    LAUNCH(e, k_collider_distance, div_up(n, 128), 128, n, e->colliders, index, dp, dout);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout, bo, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BBX_OK;
+}
 int bbx_set_collider_active(bbx_engine *e, int index, int active){
     CHECK_ENGINE(e);
     if(index < 0 || index >= e->colliders_host.count) return set_error(BBX_ERR_INVALID, "collider index out of range");

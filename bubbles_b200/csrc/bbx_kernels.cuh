@@ -1070,6 +1070,12 @@ __global__ void __launch_bounds__(256) k_query_cells(int n, DevGrid g, const int
     }
     cell_size[k] = e - s; blocked[k] = hit;
 }
+// Shape::ClosestDistance of one collider at a batch of points (parity tests of the mesh BVH: bbx_collider_distance)
+__global__ void __launch_bounds__(128) k_collider_distance(int n, const DevColliderSet *__restrict__ cs, int index, const double *__restrict__ points, double *__restrict__ out){
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= n) return;
+    out[k] = closest_distance(cs->c[index], v3(points[3 * (size_t)k], points[3 * (size_t)k + 1], points[3 * (size_t)k + 2]));
+}
 __global__ void __launch_bounds__(256) k_export_cells(int total, const int *__restrict__ cell_start, int *__restrict__ cell_count){
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if(c < total) cell_count[c] = cell_start[c + 1] - cell_start[c];

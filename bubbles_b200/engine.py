@@ -274,6 +274,13 @@ class Engine:
     def set_collider_active(self, index, active):
         _check(self.lib.bbx_set_collider_active(self.h, index, int(active)))
 
+    def collider_distance(self, index, points):
+        """Shape::ClosestDistance of collider `index` at points [n, 3] (device evaluation)"""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(len(pts), dtype=np.float64)
+        _check(self.lib.bbx_collider_distance(self.h, int(index), len(pts), pts.ctypes.data, out.ctypes.data))
+        return out
+
     def update_collider(self, index, collider):
         _check(self.lib.bbx_update_collider(self.h, index, C.byref(collider)))
 

@@ -221,6 +221,9 @@ int bbx_overwrite_owned(bbx_engine *e, const void *pos, const void *vel, int dty
 int bbx_set_colliders(bbx_engine *e, int n, const bbx_collider *colliders);
 int bbx_update_collider(bbx_engine *e, int index, const bbx_collider *collider); /* Shape::Update/SetVelocities */
 int bbx_set_collider_active(bbx_engine *e, int index, int active);             /* ColliderSet3::SetActive   */
+/* Shape::ClosestDistance of collider `index` (src/core/shape.cpp:206-233) at n points (x, y, z FP64): box / sphere signed,
+ * SDF grid sample, mesh = distance to the nearest triangle through the device BVH (parity tests) */
+int bbx_collider_distance(bbx_engine *e, int index, int n, const double *points, double *out);
 
 /* -- stepping ---------------------------------------------------------------------------------- */
 /* AdvanceTimeStep(PciSphSolver3*, dt) (src/solvers/pcisph_solver3.cpp:42-65): one sub-step */

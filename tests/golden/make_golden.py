@@ -250,6 +250,39 @@ def sph_run():
     print("sph_run", len(data["s0_pos"]), "particles")
 
 
+def mesh_collider():
+    """Triangle-mesh collider (MakeMesh + the SDF grid GenerateShapeSDF builds for it: BVH closest distance, sign by ray
+    parity -- src/shapes/bvh.cpp:51-56, 500-557, src/core/shape.cpp:358-377, 411-431, 479-511), on a procedural closed torus
+    mesh: the grid the reference generates, Shape::ClosestDistance and the collider-set response at 4 000 random points, and
+    a 150-sub-step run of the probe block dropped on it."""
+    P, Tr = scenes.torus_mesh((0.1, -0.26, 0.1), 0.09, 0.03)
+    wd = tempfile.mkdtemp(prefix="bbref_")
+    with open(os.path.join(wd, "m.bin"), "wb") as f:
+        f.write(np.int64(len(P)).tobytes()); f.write(np.int64(len(Tr)).tobytes()); f.write(P.tobytes()); f.write(Tr.tobytes())
+    rng = np.random.default_rng(11)
+    q = rng.uniform([-0.05, -0.31, -0.05], [0.25, -0.2, 0.25], size=(4000, 3))
+    v = rng.normal(0, 1.5, size=(4000, 3))
+    O.write_particles(os.path.join(wd, "q.bin"), q, v)
+    sc = scenes.probe_scene()
+    O.write_particles(os.path.join(wd, "p.bin"), sc["pos"], sc["vel"])
+    job = ["threads 4", "spacing 0.02", "scale 1.8", f"collider box {I} 0.6 0.6 0.6 1 0", f"collider mesh {wd}/m.bin 0 0.1 0.01 0.1",
+           "domain_from_collider 0", f"particles {wd}/p.bin", "setup", f"dump_sdf 1 {wd}/sdf_", f"closest_distance 1 {wd}/q.bin {wd}/cd_",
+           f"collide {wd}/q.bin 0.02 0 {wd}/a_", f"collide {wd}/q.bin 0.02 0.6 {wd}/b_", "step 7e-4 150", "dump {wd}/s150_", "dump_grid {wd}/s150_"]
+    O.run_ref(job, wd)
+    data = dict(vertices=P, triangles=Tr, q_pos=q, q_vel=v, p_pos=sc["pos"].astype(np.float64), p_vel=sc["vel"].astype(np.float64))
+    for k in ("res", "meta", "field", "bounds"):
+        data["sdf_" + k] = np.load(os.path.join(wd, f"sdf_{k}.npy"))
+    data["distance"] = np.load(os.path.join(wd, "cd_distance.npy"))
+    for tag in ("a", "b"):
+        for k in ("pos", "vel", "hit"):
+            data[f"{tag}_{k}"] = np.load(os.path.join(wd, f"{tag}_{k}.npy"))
+    for k, val in load_all(wd, "s150_", ["pos", "vel", "cell_count", "cell_order"]).items():
+        data["s150_" + k] = val
+    np.savez_compressed(os.path.join(HERE, "mesh_collider.npz"), **data)
+    print("mesh_collider", len(Tr), "triangles, sdf", data["sdf_res"], "hits", int(data["a_hit"].sum()), int(data["b_hit"].sum()),
+          "inside nodes", int((data["sdf_field"] < 0).sum()))
+
+
 def grid_facts():
     """UtilBuildGridForDomain results printed by the reference for several domains / spacings."""
     rows = []
@@ -272,6 +305,7 @@ if __name__ == "__main__":
     assert O.ref_available(), "run oracle/build_ref.sh first"
     probe_trace()
     sph_run()
+    mesh_collider()
     collider_vectors()
     obstacle_run()
     append_run()

@@ -122,6 +122,8 @@ def engine_colliders(sc):
             s = bb.MakeBox(_xf(c), c["size"], c.get("reverse", False))
         elif c["kind"] == "sphere":
             s = bb.MakeSphere(_xf(c), c["radius"], c.get("reverse", False))
+        elif c["kind"] == "mesh":
+            s = bb.MakeMesh(c["vertices"], c["triangles"], c["sdf"], c.get("reverse", False))
         else:
             s = bb.MakeSDFShape(c["bounds_min"], c["bounds_max"], c["sdf"], c.get("dx", 0.01), c.get("margin", 0.1))
         s.friction = c.get("friction", 0.0)
@@ -146,6 +148,9 @@ def make_oracle(sc, **kw):
             cols.append(O.make_collider("box", m, size=c["size"], reverse=c.get("reverse", False), friction=c.get("friction", 0.0)))
         elif c["kind"] == "sphere":
             cols.append(O.make_collider("sphere", m, radius=c["radius"], reverse=c.get("reverse", False), friction=c.get("friction", 0.0)))
+        elif c["kind"] == "mesh":
+            cols.append(O.make_collider("mesh", friction=c.get("friction", 0.0), reverse=c.get("reverse", False),
+                                        mesh=(c["vertices"], c["triangles"]), sdf=c["sdf"]))
         else:
             nodes, dx, origin = bb.sdf_grid_layout(c["bounds_min"], c["bounds_max"], c.get("dx", 0.01), c.get("margin", 0.1))
             ix, iy, iz = np.meshgrid(np.arange(nodes[0]), np.arange(nodes[1]), np.arange(nodes[2]), indexing="ij")
@@ -154,6 +159,28 @@ def make_oracle(sc, **kw):
             cols.append(O.make_collider("sdf", friction=c.get("friction", 0.0),
                                         sdf=dict(res=nodes, spacing=(dx, dx, dx), origin=origin, field=field)))
     return O.Oracle(sc["spacing"], sc["scale"], sc["domain_min"], sc["domain_max"], cols, **kw)
+
+
+def torus_mesh(center, R, r, nu=32, nv=16):
+    """A closed, consistently oriented triangle mesh of a torus around the y axis (stand-in for the absent whale / dragon
+    .obj files): (vertices [nu * nv, 3] float64, triangles [2 * nu * nv, 3] int32)."""
+    u = np.arange(nu) * 2 * np.pi / nu
+    v = np.arange(nv) * 2 * np.pi / nv
+    U, V = np.meshgrid(u, v, indexing="ij")
+    P = np.stack([(R + r * np.cos(V)) * np.cos(U), r * np.sin(V), (R + r * np.cos(V)) * np.sin(U)], -1).reshape(-1, 3) + np.asarray(center, float)
+    idx = lambda i, j: (i % nu) * nv + (j % nv)
+    T = []
+    for i in range(nu):
+        for j in range(nv):
+            a, b, c, d = idx(i, j), idx(i + 1, j), idx(i + 1, j + 1), idx(i, j + 1)
+            T += [(a, b, c), (a, c, d)]
+    return np.ascontiguousarray(P, dtype=np.float64), np.array(T, dtype=np.int32)
+
+
+def mesh_collider_from_golden(g, friction=0.1):
+    """scene collider entry of a mesh collider whose SDF grid was generated by the REFERENCE (tests/golden/mesh_collider.npz)"""
+    return dict(kind="mesh", vertices=g["vertices"], triangles=g["triangles"], friction=friction,
+                sdf=dict(res=tuple(int(x) for x in g["sdf_res"]), spacing=tuple(g["sdf_meta"][:3]), origin=tuple(g["sdf_meta"][3:]), field=g["sdf_field"]))
 
 
 def torus_obstacle(container, fluid, center):

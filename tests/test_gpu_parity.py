@@ -193,9 +193,12 @@ def test_neighbor_cap_100_is_mirrored():
     assert eng.stats().max_candidates > 512
 
 
-@pytest.mark.parametrize("kind", ["sphere_container", "sphere_obstacle", "box_obstacle", "sdf_torus"])
+@pytest.mark.parametrize("kind", ["sphere_container", "sphere_obstacle", "box_obstacle", "sdf_torus", "mesh_torus"])
 def test_colliders_phase_by_phase(kind):
     extra, container = [], (0.6, 0.6, 0.6)
+    if kind == "mesh_torus":   # triangle mesh + the SDF grid the REFERENCE generated for it (tests/golden/mesh_collider.npz)
+        import os
+        extra = [scenes.mesh_collider_from_golden(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mesh_collider.npz")), friction=0.1)]
     if kind == "sphere_obstacle":
         extra = [dict(kind="sphere", radius=0.08, translate=(0.1, -0.27, 0.1), friction=0.2)]
     elif kind == "box_obstacle":
@@ -222,6 +225,27 @@ def test_colliders_phase_by_phase(kind):
         free = tr["pos_out"] - (pos + dt * tr["vel_out"])
         hits += int((np.abs(free).max(axis=1) > 1e-9).sum())
     assert hits > 0, "scene never touched the collider"
+
+
+def test_mesh_collider_distance_through_the_device_bvh():
+    """Shape::MeshClosestDistance on the device (BVH built by bbx_set_colliders, nearest-child-first traversal) against the
+    reference's values at 4 000 points (golden), and against the brute-force oracle at points far outside the mesh where
+    the traversal prunes hardest.  FP64 on both sides; the device may contract a * b + c into FMAs: 1e-12 relative."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mesh_collider.npz"))
+    sc = scenes.probe_scene()
+    sc["colliders"] = sc["colliders"] + [scenes.mesh_collider_from_golden(g)]
+    eng, orc = _pair(sc)
+    d = eng.collider_distance(1, g["q_pos"])
+    assert np.abs(d - g["distance"]).max() <= 1e-12 * max(1.0, np.abs(g["distance"]).max())
+    rng = np.random.default_rng(4)
+    far = rng.uniform(-0.29, 0.29, size=(2000, 3))
+    assert np.abs(eng.collider_distance(1, far) - orc.mesh_closest_distance(1, far)).max() <= 1e-12
+    # the other families through the same entry (signed distances)
+    assert np.abs(eng.collider_distance(0, far) + (0.3 - np.abs(far).max(axis=1))).max() < 1e-12   # reversed container box
+    with pytest.raises(bb.BbxError):
+        eng.collider_distance(5, far)
+    eng.close()
 
 
 def test_correct_mode_iterates_and_reduces_density_error():
