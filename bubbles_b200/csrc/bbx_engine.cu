@@ -209,7 +209,14 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));
     if(e->sm_count < 1) e->sm_count = 1;
+#ifndef BBX_LISTS_TP
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->list_ctas_per_sm, k_cell_lists_density<0>, BBX_LT, 0));
+#else
+    // the thread-per-particle list build stages its tiles' candidates in dynamic shared memory (> 48 KB: opt in)
+    CU(cudaFuncSetAttribute(k_lists_density_tp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BBX_TP_SMEM));
+    CU(cudaFuncSetAttribute(k_lists_density_tp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BBX_TP_SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->list_ctas_per_sm, k_lists_density_tp<0>, BBX_TP_WARPS * 32, BBX_TP_SMEM));
+#endif
     if(e->list_ctas_per_sm < 1) e->list_ctas_per_sm = 1;
     // the staged sweeps carry their tile's neighbourhood in dynamic shared memory (> 48 KB: opt in)
     CU(cudaFuncSetAttribute(k_pressure, cudaFuncAttributeMaxDynamicSharedMemorySize, BBX_STAGE_BYTES(3)));
@@ -1032,17 +1039,31 @@ static int grid_update(bbx_engine *e){
     return BBX_OK;
 }
 
+#ifndef BBX_LISTS_TP
 // persistent grid of the list build: one warp per occupied cell, grid-stride over the occupied-cell list
 static int list_blocks(bbx_engine *e){
     long long cells = std::min<long long>(launch_n(e), e->grid.c_own1 - e->grid.c_own0);
     return (int)std::max<long long>(1, std::min<long long>((cells + BBX_LW - 1) / BBX_LW, (long long)e->sm_count * e->list_ctas_per_sm));
 }
+#else
+// persistent grid of the list build: one warp per tile of 32 consecutive slots, grid-stride over the tiles
+static int list_blocks(bbx_engine *e){
+    long long tiles = ((long long)launch_n(e) + 31) / 32;
+    return (int)std::max<long long>(1, std::min<long long>((tiles + BBX_TP_WARPS - 1) / BBX_TP_WARPS, (long long)e->sm_count * e->list_ctas_per_sm));
+}
+#endif
 static int phase_density(bbx_engine *e, const StepParams &P, int sph){
     int cur = e->cur;
     if(launch_n(e) > 0){
+#ifdef BBX_LISTS_TP
+        if(sph) LAUNCH_S(e, k_lists_density_tp<1>, list_blocks(e), BBX_TP_WARPS * 32, BBX_TP_SMEM, P, e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec, halo_none());
+        else LAUNCH_S(e, k_lists_density_tp<0>, list_blocks(e), BBX_TP_WARPS * 32, BBX_TP_SMEM, P, e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
+                    halo_dst(e, e->peer[0].rec, e->peer[1].rec));
+#else
         if(sph) LAUNCH(e, k_cell_lists_density<1>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec, halo_none());
         else LAUNCH(e, k_cell_lists_density<0>, list_blocks(e), BBX_LT, P, e->grid, e->st, e->occ_cells, e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
                     halo_dst(e, e->peer[0].rec, e->peer[1].rec));
+#endif
         CU(cudaGetLastError());
     }
     if(!sph && e->p2p) return halo_sync(e, HALO_DENSITY);

@@ -18,6 +18,7 @@
 #pragma once
 #include "bbx_device.cuh"
 #include "bbx_lists.cuh"
+#include "bbx_lists_tp.cuh"
 
 #define BBX_BS 128  // threads per CTA of the particle kernels
 
