@@ -8,6 +8,7 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <mutex>
 
 #include "../../include/bbx.h"
 #include "bbx_kernels.cuh"
@@ -170,6 +171,31 @@ template<typename T> static int dev_alloc(T **p, size_t count){
 }
 
 static int create_engine(const bbx_config *cfg, bbx_engine **slot);
+// CUDA loads a kernel lazily at its first launch, and that load synchronises the context.  A first launch issued while a
+// neighbour's k_halo_wait is spinning on this very rank's signal (several slab engines of ONE process on ONE device: the
+// LocalComm test transport) would therefore wait for the spin, which waits for the launch: 30 s of stall, then BBX_ERR_COMM.
+// Every kernel is loaded here, once per process, before any engine steps.
+static int preload_kernels(){
+    static std::mutex m; static bool done = false;
+    std::lock_guard<std::mutex> lk(m);
+    if(done) return BBX_OK;
+    cudaFuncAttributes a;
+#define BBX_PRELOAD(k) CU(cudaFuncGetAttributes(&a, k))
+    BBX_PRELOAD(k_append_hash); BBX_PRELOAD(k_cell_lists_density<0>); BBX_PRELOAD(k_cell_lists_density<1>);
+    BBX_PRELOAD(k_lists_density_tp<0>); BBX_PRELOAD(k_lists_density_tp<1>);
+    BBX_PRELOAD(k_collide_integrate); BBX_PRELOAD(k_collide_predict); BBX_PRELOAD(k_collider_distance);
+    BBX_PRELOAD(k_download); BBX_PRELOAD(k_download_state); BBX_PRELOAD(k_export_cells); BBX_PRELOAD(k_export_neighbors);
+    BBX_PRELOAD(k_fill_incremental); BBX_PRELOAD(k_force_np_predict); BBX_PRELOAD(k_full_gather); BBX_PRELOAD(k_full_scatter);
+    BBX_PRELOAD(k_full_sort_cells); BBX_PRELOAD(k_ghost_table); BBX_PRELOAD(k_halo_signal); BBX_PRELOAD(k_halo_wait);
+    BBX_PRELOAD(k_hash_count); BBX_PRELOAD(k_inject_gather); BBX_PRELOAD(k_integrate); BBX_PRELOAD(k_overwrite);
+    BBX_PRELOAD(k_predict_again); BBX_PRELOAD(k_pressure); BBX_PRELOAD(k_pressure_force<0>); BBX_PRELOAD(k_pressure_force<1>);
+    BBX_PRELOAD(k_pseudo_aggregate); BBX_PRELOAD(k_pseudo_interpolate); BBX_PRELOAD(k_push_planes); BBX_PRELOAD(k_query_cells);
+    BBX_PRELOAD(k_scan_cells); BBX_PRELOAD(k_slab_counts); BBX_PRELOAD(k_slab_plan); BBX_PRELOAD(k_slab_plan_host);
+    BBX_PRELOAD(k_slot_of_id); BBX_PRELOAD(k_sph_forces); BBX_PRELOAD(k_upload); BBX_PRELOAD(k_upload_slab);
+#undef BBX_PRELOAD
+    done = true;
+    return BBX_OK;
+}
 int bbx_create(const bbx_config *cfg, bbx_engine **out){
     if(!cfg || !out) return set_error(BBX_ERR_INVALID, "null argument");
     if(cfg->struct_size != (int)sizeof(bbx_config)) return set_error(BBX_ERR_INVALID, "bbx_config size mismatch (%d vs %d)", cfg->struct_size, (int)sizeof(bbx_config));
@@ -209,7 +235,8 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));
     if(e->sm_count < 1) e->sm_count = 1;
-#ifndef BBX_LISTS_TP
+    { int rc_ = preload_kernels(); if(rc_) return rc_; }
+#ifdef BBX_LISTS_V7
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->list_ctas_per_sm, k_cell_lists_density<0>, BBX_LT, 0));
 #else
     // the thread-per-particle list build stages its tiles' candidates in dynamic shared memory (> 48 KB: opt in)
@@ -1039,7 +1066,7 @@ static int grid_update(bbx_engine *e){
     return BBX_OK;
 }
 
-#ifndef BBX_LISTS_TP
+#ifdef BBX_LISTS_V7
 // persistent grid of the list build: one warp per occupied cell, grid-stride over the occupied-cell list
 static int list_blocks(bbx_engine *e){
     long long cells = std::min<long long>(launch_n(e), e->grid.c_own1 - e->grid.c_own0);
@@ -1055,7 +1082,7 @@ static int list_blocks(bbx_engine *e){
 static int phase_density(bbx_engine *e, const StepParams &P, int sph){
     int cur = e->cur;
     if(launch_n(e) > 0){
-#ifdef BBX_LISTS_TP
+#ifndef BBX_LISTS_V7
         if(sph) LAUNCH_S(e, k_lists_density_tp<1>, list_blocks(e), BBX_TP_WARPS * 32, BBX_TP_SMEM, P, e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec, halo_none());
         else LAUNCH_S(e, k_lists_density_tp<0>, list_blocks(e), BBX_TP_WARPS * 32, BBX_TP_SMEM, P, e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
                     halo_dst(e, e->peer[0].rec, e->peer[1].rec));
