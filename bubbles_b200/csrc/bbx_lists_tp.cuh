@@ -225,19 +225,20 @@ __global__ void __launch_bounds__(BBX_TP_WARPS * 32, BBX_TP_MINB) k_lists_densit
                 const unsigned ent = (unsigned)r << BBX_RUN_SHIFT;
                 float dmx = 0.f;
                 int k0 = 0;
+                const float thr_m = member ? P.thr_hi : -1.f;
                 // A candidate up to thr_hi is appended provisionally; a lane that took one from inside the guard band redoes
                 // the run with the FP64 predicate.  Blocks inside every member's window run without the per-step window test.
-#define BBX_TP_STEP(VALID)                                                                                                   \
+// one pair test + predicated append, in PTX so that it stays four predicated instructions (the compiler otherwise turns
+// the append into a branch that ~every warp takes): THR is thr_hi for a lane inside its window and -1 outside
+#define BBX_TP_STEP(THR)                                                                                                     \
                     {                                                                                                        \
                         const float dx = pi.x - cj[u].x, dy = pi.y - cj[u].y, dz = pi.z - cj[u].z;                           \
                         const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));                                                \
-                        if((VALID) && d2 <= P.thr_hi){                                                                       \
-                            const float y = P.h2 - d2;                                                                       \
-                            asm volatile("st.shared.u16 [%0], %1;" :: "r"(wa), "h"((unsigned short)(ent + (unsigned)(k0 + u))) : "memory"); \
-                            wa += 2u;                                                                                        \
-                            acc = fmaf(y * y, y, acc);                                                                       \
-                            dmx = fmaxf(dmx, d2);                                                                            \
-                        }                                                                                                    \
+                        const float y = P.h2 - d2, y2 = y * y;                                                               \
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %3, %4;\n\t@p st.shared.u16 [%0], %5;\n\t@p add.u32 %0, %0, 2;\n\t" \
+                                     "@p fma.rn.f32 %1, %6, %7, %1;\n\t@p max.f32 %2, %2, %3;\n\t}"                      \
+                                     : "+r"(wa), "+f"(acc), "+f"(dmx)                                                        \
+                                     : "f"(d2), "f"(THR), "h"((unsigned short)(ent + (unsigned)(k0 + u))), "f"(y2), "f"(y) : "memory"); \
                     }
 #pragma unroll 1
                 for(; k0 < Lall; k0 += BBX_TP_UNROLL){
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(BBX_TP_WARPS * 32, BBX_TP_MINB) k_lists_densit
 #pragma unroll
                     for(int u = 0; u < BBX_TP_UNROLL; u++) cj[u] = cp[k0 + u];
 #pragma unroll
-                    for(int u = 0; u < BBX_TP_UNROLL; u++) BBX_TP_STEP(member)
+                    for(int u = 0; u < BBX_TP_UNROLL; u++) BBX_TP_STEP(thr_m)
                 }
 #pragma unroll 1
                 for(; k0 < L; k0 += BBX_TP_UNROLL){
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(BBX_TP_WARPS * 32, BBX_TP_MINB) k_lists_densit
 #pragma unroll
                     for(int u = 0; u < BBX_TP_UNROLL; u++) if(k0 + u < mylen) cj[u] = cp[k0 + u];
 #pragma unroll
-                    for(int u = 0; u < BBX_TP_UNROLL; u++) BBX_TP_STEP(k0 + u < mylen)
+                    for(int u = 0; u < BBX_TP_UNROLL; u++) BBX_TP_STEP(k0 + u < mylen ? P.thr_hi : -1.f)
                 }
 #undef BBX_TP_STEP
                 if(dmx >= P.thr_lo){
