@@ -8,4 +8,4 @@ from . import _lib  # noqa: F401
 from ._lib import *  # noqa: F401,F403  (enum values)
 from .engine import (BbxError, ColliderSetBuilder3, Engine, MakeBox, MakeGrid, MakeMesh, MakeSDFShape, MakeSphere,  # noqa: F401
                      Translate, UtilBuildGridForDomain, identity, sdf_grid_layout)
-from .slab import LocalSlabGroup, NcclSlab, plan_slabs, plane_histogram, slab_capacity  # noqa: F401,E402
+from .slab import LocalSlabGroup, NcclSlab, plan_slabs, plan_step, plane_histogram, slab_capacity  # noqa: F401,E402

@@ -113,6 +113,9 @@ SYMBOLS = {
     "bbx_comm_init_local": (C.c_int, [_E, C.c_int, C.c_int, C.c_char_p]),
     "bbx_halo_mode": (C.c_int, [_E, C.POINTER(C.c_int)]),
     "bbx_slab_plan": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_int)]),
+    "bbx_plane_counts": (C.c_int, [_E, C.POINTER(C.c_longlong)]),
+    "bbx_rebalance": (C.c_int, [_E, C.POINTER(C.c_int)]),
+    "bbx_slab_plan_step": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bbx_plane_histogram": (C.c_int, [C.POINTER(GridDesc), C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]),
 }
 

@@ -69,6 +69,7 @@ struct bbx_engine {
     int epoch;       // grid updates done so far; flags are double-buffered by its parity (DevState)
     int masked;      // cells smaller than h (informational; the cell-centric list build needs no window test)
     int list_ctas_per_sm;
+    long long cells_alloc; // entries of the cell-indexed arrays (slab engines: enough for any slab of the grid)
     unsigned short *nbr; int *nbr_cnt;
     float4 *force, *force_p, *pred, *posq, *smoothed;
     float4 *rec;     // 32-byte gather records (x, y, z, rho | vx, vy, vz, -), 2 float4 per slot, written by the list build
@@ -287,6 +288,9 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
         double minlen = std::min(g.len[0], std::min(g.len[1], g.len[2]));
         e->masked = (minlen * minlen >= e->h * e->h - 0.5e-8) ? 0 : 1;
     }
+    // cell-indexed arrays: a slab engine is sized for any slab of the grid (bbx_rebalance moves the cuts during a run)
+    e->cells_alloc = (e->has_lo || e->has_hi) ? (long long)g.plane * (g.gnz + 2) : (long long)g.total;
+    if(e->cells_alloc > 0x7fffffffLL) return set_error(BBX_ERR_INVALID, "more than 2^31 cells");
     // particle arrays carry BBX_PAD spare slots: the list build reads (and discards) up to 7 slots past a run
     const size_t gc = (size_t)e->gcap;
     size_t cap = (size_t)e->cap + BBX_PAD, capw = ((cap + 31) / 32) * 32, capg = cap + 2 * gc;
@@ -295,8 +299,8 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
 #define BBX_ALLOC_G(ptr) do{ BBX_TRY(dev_alloc(&(ptr), capg)); if(rc == BBX_OK){ e->raw.push_back((void *)(ptr)); CU(cudaMemset((ptr), 0, sizeof(*(ptr)) * capg)); (ptr) += gc; }else (ptr) = nullptr; }while(0)
     for(int b = 0; b < 2 && rc == BBX_OK; b++){
         BBX_ALLOC_G(e->pos[b]); BBX_ALLOC_G(e->vel[b]); BBX_ALLOC_G(e->pid[b]); BBX_ALLOC_G(e->cell[b]);
-        BBX_TRY(dev_alloc(&e->cell_start[b], (size_t)g.total + 1));
-        if(rc == BBX_OK) CU(cudaMemset(e->cell_start[b], 0, sizeof(int) * ((size_t)g.total + 1)));
+        BBX_TRY(dev_alloc(&e->cell_start[b], (size_t)e->cells_alloc + 1));
+        if(rc == BBX_OK) CU(cudaMemset(e->cell_start[b], 0, sizeof(int) * ((size_t)e->cells_alloc + 1)));
     }
     BBX_ALLOC_G(e->newcell); BBX_ALLOC_G(e->pred); BBX_ALLOC_G(e->posq);
 #undef BBX_ALLOC_G
@@ -316,11 +320,11 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
         if(rc == BBX_OK){ CU(cudaMemset(e->halo_flags, 0, sizeof(unsigned) * words)); e->raw_shared[7] = e->halo_flags; }
         CU(cudaMallocHost((void **)&e->mail_host, sizeof(int) * 2 * BBX_HALO_MAIL));
     }
-    BBX_TRY(dev_alloc(&e->count, (size_t)g.total + 8)); BBX_TRY(dev_alloc(&e->perm, cap));
-    BBX_TRY(dev_alloc(&e->occ_cells, (size_t)g.total)); BBX_TRY(dev_alloc(&e->queue, cap));
-    BBX_TRY(dev_alloc(&e->movemask, (size_t)g.total));
+    BBX_TRY(dev_alloc(&e->count, (size_t)e->cells_alloc + 8)); BBX_TRY(dev_alloc(&e->perm, cap));
+    BBX_TRY(dev_alloc(&e->occ_cells, (size_t)e->cells_alloc)); BBX_TRY(dev_alloc(&e->queue, cap));
+    BBX_TRY(dev_alloc(&e->movemask, (size_t)e->cells_alloc));
     e->scan_tiles = div_up(g.c_own1 - g.c_own0, SCAN_TILE);
-    BBX_TRY(dev_alloc(&e->scan_status, (size_t)e->scan_tiles));
+    BBX_TRY(dev_alloc(&e->scan_status, (size_t)div_up(e->cells_alloc, SCAN_TILE)));
     BBX_TRY(dev_alloc(&e->nbr, capw * BBX_NBR_CHUNKS * 8)); BBX_TRY(dev_alloc(&e->nbr_cnt, cap));
     BBX_TRY(dev_alloc(&e->force, cap)); BBX_TRY(dev_alloc(&e->force_p, cap));
     BBX_TRY(dev_alloc(&e->smoothed, cap));
@@ -328,7 +332,7 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     BBX_TRY(dev_alloc(&e->st, 1)); BBX_TRY(dev_alloc(&e->colliders, 1)); BBX_TRY(dev_alloc(&e->cull, 1));
     if(e->gcap){ BBX_TRY(dev_alloc(&e->gtab, 2 * ((size_t)g.plane + 1))); e->raw_shared[10] = e->gtab; }
     if(rc != BBX_OK){ return rc; }
-    CU(cudaMemset(e->count, 0, sizeof(int) * ((size_t)g.total + 8)));
+    CU(cudaMemset(e->count, 0, sizeof(int) * ((size_t)e->cells_alloc + 8)));
     CU(cudaMallocHost((void **)&e->st_host, sizeof(DevState)));
     CU(cudaMallocHost((void **)&e->err_probe, sizeof(int)));
     CU(cudaMallocHost((void **)&e->st_hint, BBX_HINT_RING * sizeof(DevState)));
@@ -513,9 +517,9 @@ static int append_update(bbx_engine *e, int n_old, int k, int split = -1, int id
     const int own_cells = g.c_own1 - g.c_own0;
     LAUNCH(e, k_append_hash, div_up(std::max(n_all, e->scan_tiles), 256), 256, n_old, k, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st, e->scan_status, e->scan_tiles);
     LAUNCH(e, k_scan_cells, e->scan_tiles, 256, e->count + g.c_own0, own_cells, g.c_own0, e->scan_status, e->st, e->cell_start[nxt] + g.c_own0, e->occ_cells);
-    LAUNCH(e, k_full_scatter, div_up(n_all, 256), 256, n_all, 0, g, e->st, par, 1, e->newcell, e->cell_start[nxt], e->count, e->perm);
+    LAUNCH(e, k_full_scatter, div_up(std::max(n_all, 1), 256), 256, n_all, 0, g, e->st, par, 1, e->newcell, e->cell_start[nxt], e->count, e->perm);
     LAUNCH(e, k_full_sort_cells, div_up(g.total, 256), 256, g, e->st, par, 1, e->cell_start[nxt], split >= 0 ? e->pid[cur] : (const int *)nullptr, e->perm, e->count, split, id0);
-    LAUNCH(e, k_full_gather, div_up(n_all, 256), 256, e->st, par, 1, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
+    LAUNCH(e, k_full_gather, div_up(std::max(n_all, 1), 256), 256, e->st, par, 1, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
            e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec);
     CU(cudaGetLastError());
     if(IS_SLAB(e)){ int rc = slab_refresh_ghosts(e, nxt); if(rc) return rc; } // the neighbours' ghost copies of my boundary planes changed too
@@ -1596,6 +1600,125 @@ int bbx_slab_plan(int nplanes, const long long *plane_counts, int nranks, int *z
     z_bounds[nranks] = nplanes;
     return BBX_OK;
 }
+// one step from the cuts `current` towards `target` that bbx_rebalance can follow: every cut stays strictly inside the two
+// slabs it separates (planes change hands between neighbours only, every rank keeps a plane); returns 1 in *done when the
+// step reaches the target
+int bbx_slab_plan_step(int nranks, const int *current, const int *target, int *step, int *done){
+    if(!current || !target || !step || nranks < 1) return set_error(BBX_ERR_INVALID, "bad arguments");
+    step[0] = current[0]; step[nranks] = current[nranks];
+    int reached = 1;
+    for(int r = 1; r < nranks; r++){
+        int lo = current[r - 1] + 1, hi = current[r + 1] - 1;
+        lo = std::max(lo, step[r - 1] + 1);                       // keep the step itself strictly increasing
+        int c = std::min(std::max(target[r], lo), hi);
+        step[r] = c;
+        if(c != target[r]) reached = 0;
+    }
+    if(done) *done = reached;
+    return BBX_OK;
+}
+// ---- re-balancing of the z cuts during a run (collective over the slab group, between two sub-steps)
+// owned particles per GLOBAL cell plane, by the cells recorded at the last grid update (zero outside my planes)
+int bbx_plane_counts(bbx_engine *e, long long *plane_counts){
+    CHECK_ENGINE(e);
+    if(!plane_counts) return set_error(BBX_ERR_INVALID, "null");
+    const DevGrid &g = e->grid;
+    for(int z = 0; z < g.gnz; z++) plane_counts[z] = 0;
+    { int rc = sync_counts(e); if(rc) return rc; }
+    if(e->n == 0 || !e->have_chains) return BBX_OK;
+    const int planes = g.own_z1 - g.own_z0;
+    std::vector<int> cs((size_t)planes + 1);
+    CU(cudaMemcpy2DAsync(cs.data(), sizeof(int), e->cell_start[e->cur] + g.c_own0, sizeof(int) * (size_t)g.plane, sizeof(int), (size_t)planes + 1, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    for(int k = 0; k < planes; k++) plane_counts[g.zoff + g.own_z0 + k] = (long long)cs[k + 1] - cs[k];
+    return BBX_OK;
+}
+// The slab group moves to the cuts z_bounds[0 .. nranks] (z_bounds[r] .. z_bounds[r + 1] = the planes of rank r; every rank
+// passes the same array).  Whole planes change hands between NEIGHBOURS only -- a cut may move at most to the far end of
+// the slab next to it, and every rank must keep at least one of its planes; call again to move further.  The particles of
+// a plane travel as contiguous slot ranges (x, v, id, recorded cell) in their chain order, the receiver files them under
+// the recorded cells with the re-sort of an append (old slots = chain order) and the boundary planes are exchanged again:
+// cell orders, neighbour lists and the trajectory stay bit-identical to the single-domain engine.
+int bbx_rebalance(bbx_engine *e, const int *z_bounds){
+    CHECK_ENGINE(e);
+    if(!IS_SLAB(e)) return BBX_OK;
+    if(!z_bounds) return set_error(BBX_ERR_INVALID, "null");
+    if(!e->comm) return set_error(BBX_ERR_INVALID, "slab engine without a communicator");
+    if(!e->have_chains) return set_error(BBX_ERR_INVALID, "bbx_rebalance needs a particle set (bbx_set_particles_ids) first");
+    int rc = sync_counts(e); if(rc) return rc;
+    DevGrid &g = e->grid;
+    const int rank = e->comm->rank, nranks = e->comm->nranks;
+    const int z0 = g.zoff + g.own_z0, z1 = g.zoff + g.own_z1, nz0 = z_bounds[rank], nz1 = z_bounds[rank + 1];
+    if(z_bounds[0] != 0 || z_bounds[nranks] != g.gnz) return set_error(BBX_ERR_INVALID, "z_bounds must run from 0 to the grid's %d planes", g.gnz);
+    for(int r = 0; r < nranks; r++) if(z_bounds[r + 1] <= z_bounds[r]) return set_error(BBX_ERR_INVALID, "every rank needs at least one plane");
+    const int k0 = std::max(z0, nz0), k1 = std::min(z1, nz1);      // the planes I keep
+    // a plan this rank cannot follow must stop EVERY rank before the first exchange: agree on it (global max of a flag)
+    const int cur = e->cur, nxt = cur ^ 1, n = e->n;
+    {
+        unsigned bad = (k1 <= k0) ? 1u : 0u;
+        CU(cudaMemcpyAsync(e->perm, &bad, sizeof(unsigned), cudaMemcpyHostToDevice, e->stream));
+        COMM(e->comm->allreduce_max_u32(e->stream, (unsigned *)e->perm, 1));
+        unsigned any = 0;
+        CU(cudaMemcpyAsync(&any, e->perm, sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        if(bad) return set_error(BBX_ERR_INVALID, "rank %d would keep none of its planes [%d, %d) in [%d, %d): move the cuts in smaller steps (bbx_slab_plan_step)", rank, z0, z1, nz0, nz1);
+        if(any) return set_error(BBX_ERR_INVALID, "another rank of the slab group cannot follow this plan (a cut moved past a neighbouring slab)");
+    }
+    // slot boundaries of the planes that leave (cell table of the current buffer, owned part)
+    int slot_k0 = 0, slot_k1 = n;
+    if(k0 > z0) CU(cudaMemcpyAsync(&slot_k0, e->cell_start[cur] + g.c_own0 + (size_t)(k0 - z0) * g.plane, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if(k1 < z1) CU(cudaMemcpyAsync(&slot_k1, e->cell_start[cur] + g.c_own0 + (size_t)(k1 - z0) * g.plane, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    const int s_lo = slot_k0, s_hi = n - slot_k1, n_keep = slot_k1 - slot_k0;
+    const int to_lo[BBX_NCOUNTS] = {s_lo, 0}, to_hi[BBX_NCOUNTS] = {s_hi, 0};
+    int from_lo[BBX_NCOUNTS] = {0, 0}, from_hi[BBX_NCOUNTS] = {0, 0};
+    COMM(e->comm->neighbor_counts(e->stream, to_lo, to_hi, from_lo, from_hi));
+    const int r_lo = e->has_lo ? from_lo[0] : 0, r_hi = e->has_hi ? from_hi[0] : 0;
+    if((nz0 >= z0 && r_lo > 0) || (nz1 <= z1 && r_hi > 0)) return set_error(BBX_ERR_INVALID, "the ranks of the slab group disagree about z_bounds");
+    const long long n_new = (long long)n_keep + r_lo + r_hi;
+    if(n_new > e->cap) return set_error(BBX_ERR_CAPACITY, "after re-balancing rank %d would own %lld particles, max_particles is %d", rank, n_new, e->cap);
+    // the new grid of this rank (one ghost plane per neighbour, as at creation)
+    const int zoff_new = nz0 - (e->has_lo ? 1 : 0);
+    const long long plane = g.plane;
+    // kept particles -> front of the other buffer, recorded cells re-based to the new local plane numbering
+    if(n_keep > 0){
+        CU(cudaMemcpyAsync(e->pos[nxt], e->pos[cur] + slot_k0, sizeof(float4) * (size_t)n_keep, cudaMemcpyDeviceToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->vel[nxt], e->vel[cur] + slot_k0, sizeof(float4) * (size_t)n_keep, cudaMemcpyDeviceToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->pid[nxt], e->pid[cur] + slot_k0, sizeof(int) * (size_t)n_keep, cudaMemcpyDeviceToDevice, e->stream));
+        LAUNCH(e, k_cells_shift, div_up(n_keep, 256), 256, n_keep, e->cell[cur] + slot_k0, e->cell[nxt], (int)((long long)(g.zoff - zoff_new) * plane));
+    }
+    // the planes that leave travel with GLOBAL cell ids (staged in perm: s_lo + s_hi <= n slots)
+    if(s_lo > 0) LAUNCH(e, k_cells_shift, div_up(s_lo, 256), 256, s_lo, e->cell[cur], e->perm, (int)((long long)g.zoff * plane));
+    if(s_hi > 0) LAUNCH(e, k_cells_shift, div_up(s_hi, 256), 256, s_hi, e->cell[cur] + slot_k1, e->perm + s_lo, (int)((long long)g.zoff * plane));
+    CU(cudaGetLastError());
+    {
+        const size_t f4 = sizeof(float4), i4 = sizeof(int);
+        BbxSeg slo[4] = {{e->pos[cur], f4 * (size_t)s_lo}, {e->vel[cur], f4 * (size_t)s_lo}, {e->pid[cur], i4 * (size_t)s_lo}, {e->perm, i4 * (size_t)s_lo}};
+        BbxSeg shi[4] = {{e->pos[cur] + slot_k1, f4 * (size_t)s_hi}, {e->vel[cur] + slot_k1, f4 * (size_t)s_hi}, {e->pid[cur] + slot_k1, i4 * (size_t)s_hi}, {e->perm + s_lo, i4 * (size_t)s_hi}};
+        const size_t a = (size_t)n_keep, b = (size_t)n_keep + (size_t)r_lo;
+        BbxSeg rlo[4] = {{e->pos[nxt] + a, f4 * (size_t)r_lo}, {e->vel[nxt] + a, f4 * (size_t)r_lo}, {e->pid[nxt] + a, i4 * (size_t)r_lo}, {e->cell[nxt] + a, i4 * (size_t)r_lo}};
+        BbxSeg rhi[4] = {{e->pos[nxt] + b, f4 * (size_t)r_hi}, {e->vel[nxt] + b, f4 * (size_t)r_hi}, {e->pid[nxt] + b, i4 * (size_t)r_hi}, {e->cell[nxt] + b, i4 * (size_t)r_hi}};
+        COMM(e->comm->exchange(e->stream, slo, rlo, 4, shi, rhi, 4));
+    }
+    if(r_lo + r_hi > 0) LAUNCH(e, k_cells_shift, div_up(r_lo + r_hi, 256), 256, r_lo + r_hi, e->cell[nxt] + n_keep, e->cell[nxt] + n_keep, (int)(-(long long)zoff_new * plane));
+    CU(cudaGetLastError());
+    // switch to the new slab
+    g.zoff = zoff_new;
+    g.n[2] = (nz1 - nz0) + (e->has_lo ? 1 : 0) + (e->has_hi ? 1 : 0);
+    g.own_z0 = e->has_lo ? 1 : 0; g.own_z1 = g.own_z0 + (nz1 - nz0);
+    g.c_own0 = g.own_z0 * g.plane; g.c_own1 = g.own_z1 * g.plane;
+    g.total = g.plane * g.n[2];
+    e->cfg.slab_z_begin = nz0; e->cfg.slab_z_end = nz1;
+    e->scan_tiles = div_up(g.c_own1 - g.c_own0, SCAN_TILE);
+    e->cur = nxt; e->n = (int)n_new;
+    const int n_dev = (int)n_new;
+    CU(cudaMemcpyAsync(&e->st->n_own, &n_dev, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream)); // (n_dev is a stack variable)
+    e->n_hint = e->n; e->hint_count = 0; e->n_launch = bound_of(e, e->n);
+    // file the particles under their recorded cells (stable by slot = chain order) and exchange the boundary planes again
+    return append_update(e, e->n, 0);
+}
+
 // global cell plane of each particle (the hash of Grid::GetHashedPosition, z component), host arithmetic
 int bbx_plane_histogram(const bbx_grid_desc *grid, int n, const void *pos, int dtype, long long *plane_counts){
     if(!grid || !plane_counts || (n > 0 && !pos) || (dtype != BBX_F32 && dtype != BBX_F64)) return set_error(BBX_ERR_INVALID, "bad arguments");

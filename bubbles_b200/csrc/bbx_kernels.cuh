@@ -1133,3 +1133,9 @@ __global__ void __launch_bounds__(256) k_inject_gather(int n, const int *__restr
     pos_new[d] = pp; vel_new[d] = vv; rec[2 * (size_t)d] = pp; rec[2 * (size_t)d + 1] = vv;
     pid_new[d] = id; cell_new[d] = cell_of_slot_new[d];
 }
+
+// bbx_rebalance: recorded cell ids moved to another local plane numbering (dst may be src)
+__global__ void __launch_bounds__(256) k_cells_shift(int n, const int *src, int *dst, int delta){
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) dst[i] = src[i] + delta;
+}

@@ -362,6 +362,17 @@ class Engine:
         _check(self.lib.bbx_export_neighbors_owned(self.h, counts.ctypes.data, ids.ctypes.data))
         return counts, ids
 
+    def plane_counts(self):
+        """owned particles per GLOBAL cell plane (bbx_plane_counts)"""
+        out = (C.c_longlong * self.grid.n[2])()
+        _check(self.lib.bbx_plane_counts(self.h, out))
+        return np.array(out[:], dtype=np.int64)
+
+    def rebalance(self, z_bounds):
+        """collective over the slab group: move to the cuts z_bounds (bbx_rebalance)"""
+        zb = (C.c_int * len(z_bounds))(*[int(z) for z in z_bounds])
+        _check(self.lib.bbx_rebalance(self.h, zb))
+
     def export_cells(self):
         count = np.zeros(self.grid.total, dtype=np.int32)
         order = np.zeros(self.n, dtype=np.int32)

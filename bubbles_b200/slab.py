@@ -37,6 +37,18 @@ def plan_slabs(plane_counts, nranks):
     return list(zb[:])
 
 
+def plan_step(current, target):
+    """(step, done): the part of the way from the cuts `current` to `target` that one bbx_rebalance can go
+    (bbx_slab_plan_step: every cut stays strictly inside the two slabs it separates)"""
+    nr = len(current) - 1
+    cur = (C.c_int * (nr + 1))(*[int(z) for z in current])
+    tgt = (C.c_int * (nr + 1))(*[int(z) for z in target])
+    step = (C.c_int * (nr + 1))()
+    done = C.c_int()
+    _check(L.load().bbx_slab_plan_step(nr, cur, tgt, step, C.byref(done)))
+    return list(step[:]), bool(done.value)
+
+
 def slab_capacity(plane_counts, z_bounds, rank, slack=1.5, floor=4096):
     """(max_particles, ghost_capacity) of one slab: its share of the particles with room for migration."""
     z0, z1 = z_bounds[rank], z_bounds[rank + 1]
@@ -118,6 +130,24 @@ class LocalSlabGroup:
         ids = np.arange(first, first + len(pos), dtype=np.int32)
         self.each(lambda e, r: e.append_particles_ids(pos, vel, ids))
         self.n_total = first + len(pos)
+
+    def rebalance(self, z_bounds=None, max_calls=8):
+        """Move the cuts to z_bounds (default: bbx_slab_plan over the current plane histogram), in as many neighbour-only
+        steps as it takes; returns the cuts reached."""
+        if self.nslabs < 2:
+            return self.z_bounds
+        if z_bounds is None:
+            hist = sum(e.plane_counts() for e in self.engines)
+            z_bounds = plan_slabs(hist, self.nslabs)
+        for _ in range(max_calls):
+            if list(z_bounds) == list(self.z_bounds):
+                break
+            step, done = plan_step(self.z_bounds, z_bounds)
+            if step == list(self.z_bounds):
+                break
+            self.each(lambda e, r: e.rebalance(step))
+            self.z_bounds = step
+        return self.z_bounds
 
     def step_pcisph(self, dt):
         self.each(lambda e, r: e.step_pcisph(dt))

@@ -297,6 +297,17 @@ int bbx_halo_mode(bbx_engine *e, int *p2p);
 int bbx_comm_init_local(bbx_engine *e, int rank, int nranks, const char *group);
 /* plane_counts[nplanes] -> z_bounds[nranks + 1]: slabs of whole planes balanced by particle count */
 int bbx_slab_plan(int nplanes, const long long *plane_counts, int nranks, int *z_bounds);
+/* Re-balancing during a run (the reference has no decomposition; the static plan of bbx_slab_plan drifts as the fluid
+ * moves).  bbx_plane_counts: owned particles per GLOBAL cell plane (grid n[2] entries, zero outside this engine's planes;
+ * sum them over the group and feed bbx_slab_plan).  bbx_rebalance: collective over the group, between two sub-steps;
+ * every rank passes the same z_bounds[nranks + 1].  Whole planes change hands between neighbouring ranks only (a rank
+ * must keep at least one of its planes: move far cuts in several calls), in their chain order: results stay
+ * bit-identical to the single-domain engine. */
+int bbx_plane_counts(bbx_engine *e, long long *plane_counts);
+int bbx_rebalance(bbx_engine *e, const int *z_bounds);
+/* current[nranks + 1], target[nranks + 1] -> step[nranks + 1]: the part of the way to `target` one bbx_rebalance can go
+ * (every cut stays strictly inside the two slabs it separates); *done = 1 when step == target */
+int bbx_slab_plan_step(int nranks, const int *current, const int *target, int *step, int *done);
 /* particles per global cell plane (host arithmetic, same hash as the engine) */
 int bbx_plane_histogram(const bbx_grid_desc *grid, int n, const void *pos, int dtype, long long *plane_counts);
 

@@ -278,3 +278,56 @@ def test_append_particles_on_slab_engines_matches_single_domain():
     assert np.array_equal(n1, ng) and np.array_equal(i1, ig)
     assert all(s.nan_count == 0 for s in grp.stats())
     grp.close()
+
+
+def test_rebalance_moves_the_cuts_and_stays_bit_identical_to_the_single_domain():
+    """bbx_rebalance (include/bbx.h, "re-balancing during a run"): the static plan drifts as the fluid sloshes; the group
+    re-plans from the per-plane histogram (bbx_plane_counts -> bbx_slab_plan -> bbx_slab_plan_step) and whole planes change
+    hands between neighbours in their chain order.  Also driven far off balance on purpose (cuts pushed several planes
+    both ways, more than one neighbour-only step).  Chains, lists and the trajectory: bit-identical to the single domain."""
+    sc = _moving_scene()
+    n = len(sc["pos"])
+    one = _single(sc)
+    grp, zb = _group(sc, 3, cap=n)
+    grp.set_particles(sc["pos"], sc["vel"])
+    dt = sc["dt"]
+
+    def same(tag):
+        cc, co = grp.export_cells()
+        c1, o1 = one.export_cells()
+        assert np.array_equal(cc, c1) and np.array_equal(co, o1), f"chains differ {tag}"
+        for f in (bb.POSITION, bb.VELOCITY, bb.DENSITY):
+            assert np.array_equal(grp.download(f, np.float32), one.download(f, np.float32)), f"field {f} differs {tag}"
+
+    for _ in range(10):
+        one.step_pcisph(dt); grp.step_pcisph(dt)
+    same("before")
+    counts0 = list(grp.counts)
+    # (a) far off balance: the first cut three planes down, the second two planes up -- planes travel both ways
+    target = [zb[0], zb[1] - 3, zb[2] + 2, zb[3]]
+    reached = grp.rebalance(target)
+    assert reached == target and sum(grp.counts) == n and list(grp.counts) != counts0
+    hist = sum(e.plane_counts() for e in grp.engines)
+    assert hist.sum() == n and [int(hist[reached[r]:reached[r + 1]].sum()) for r in range(3)] == list(grp.counts)
+    same("after the forced move")
+    for _ in range(12):
+        one.step_pcisph(dt); grp.step_pcisph(dt)
+    same("12 sub-steps after the forced move")
+    # (b) back to balance from the histogram
+    reached = grp.rebalance()
+    hist = sum(e.plane_counts() for e in grp.engines)
+    assert sum(grp.counts) == n and max(grp.counts) - min(grp.counts) <= hist.max()   # (whole planes: ~6 planes hold the block)
+    for _ in range(12):
+        one.step_pcisph(dt); grp.step_pcisph(dt)
+    same("12 sub-steps after re-balancing")
+    n1, i1 = one.export_neighbors()
+    ng, ig = grp.export_neighbors()
+    assert np.array_equal(n1, ng) and np.array_equal(i1, ig)
+    # (c) a plan a rank cannot follow stops every rank before anything moves (no hang, no change)
+    with pytest.raises(bb.BbxError):
+        grp.each(lambda e, r: e.rebalance([0, 1, 2, grp.grid.n[2]]) if reached[1] > 3 else e.rebalance([0, grp.grid.n[2] - 2, grp.grid.n[2] - 1, grp.grid.n[2]]))
+    one.step_pcisph(dt); grp.step_pcisph(dt)
+    same("after the refused plan")
+    assert all(s.nan_count == 0 for s in grp.stats())
+    grp.close()
+    one.close()
