@@ -313,9 +313,41 @@ class Job:
             self.eng.set_particles(sc["pos"], sc["vel"])
         self.n = self.n_global // world  # nominal particles per GPU (the slabs hold about this many each)
         self.cells = sc["grid"].total // world
+        self.z_bounds = list(sc["z_bounds"]) if world > 1 else None
+        self.rebalances = 0
+
+    def rebalance(self, target=None):
+        """Slab group: re-plan the z cuts from the current per-plane histogram (bbx_plane_counts summed over the ranks ->
+        bbx_slab_plan) and move there in neighbour-only steps (bbx_slab_plan_step, bbx_rebalance).  Host-synchronous;
+        returns the wall-clock ms it took on this rank (0 when the plan did not change)."""
+        if self.world < 2:
+            return 0.0
+        import torch
+        import torch.distributed as dist
+        bb = self.bb
+        t0 = time.perf_counter()
+        if target is None:
+            hist = torch.from_numpy(self.eng.plane_counts()).cuda()
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+            target = bb.plan_slabs(hist.cpu().numpy(), self.world)
+        moved = False
+        for _ in range(8):
+            if list(target) == self.z_bounds:
+                break
+            step, _ = bb.plan_step(self.z_bounds, target)
+            if step == self.z_bounds:
+                break
+            self.eng.rebalance(step)
+            self.z_bounds = step
+            moved = True
+        if moved:
+            self.eng.synchronize()
+            self.rebalances += 1
+        return (time.perf_counter() - t0) * 1e3
 
     def reset(self):
         if self.world > 1:
+            self.rebalance(list(self.sc["z_bounds"]))  # this rank's share of the initial block belongs to the initial slabs
             self.eng.set_particles_ids(self.sc["pos"], self.sc["vel"], self.sc["ids"])
         else:
             self.eng.set_particles(self.sc["pos"], self.sc["vel"])
@@ -343,7 +375,7 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
-def timed_blocks(job, solver, dt, steps, repeats, local_rank):
+def timed_blocks(job, solver, dt, steps, repeats, local_rank, rebalance=True):
     """`repeats` back-to-back blocks of exactly `steps` sub-steps, each bracketed by two CUDA events on the engine's stream
     (bbx_step_many_timed) and a barrier + synchronize on both sides; per block the max over ranks.  Returns the per-block
     ms per sub-step, the wall-clock ms per sub-step of the median block, the launches per block and the clock record
@@ -357,7 +389,10 @@ def timed_blocks(job, solver, dt, steps, repeats, local_rank):
     for _ in range(repeats):
         barrier(world)
         t0 = time.perf_counter()
-        ms = eng.step_many_timed(dt, steps, solver)
+        # slab groups re-plan their z cuts at the start of every block; that time (host wall clock, synchronous) is part of
+        # the block: it is work the run needs in order to keep stepping at this rate
+        reb = job.rebalance() if (world > 1 and rebalance) else 0.0
+        ms = eng.step_many_timed(dt, steps, solver) + reb
         barrier(world)
         wall = (time.perf_counter() - t0) * 1e3
         ms, wall = rank_max([ms, wall], world)
@@ -550,6 +585,7 @@ def main():
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the additional BASELINE configs (8 M SDF at N = 1, 32 M at N = 2 / 4, 100 M at N = 8)")
     ap.add_argument("--developed-substeps", type=int, default=400, help="second timing after this many sub-steps (splash developed); 0 = skip")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep the static slab plan of the initial distribution (default: re-plan the z cuts at the start of every timed block)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -582,7 +618,7 @@ def main():
     # ---- device-resident throughput: W warm-up sub-steps, then `repeats` blocks of exactly K sub-steps -------------
     eng.step_many(dt, args.warmup, solver)
     eng.synchronize()
-    blocks, ms_per_step, wall_ms, launches, clocks = timed_blocks(job, solver, dt, args.steps, args.repeats, local_rank)
+    blocks, ms_per_step, wall_ms, launches, clocks = timed_blocks(job, solver, dt, args.steps, args.repeats, local_rank, not args.no_rebalance)
     value = n_global / (ms_per_step * 1e-3)
     phase, gap_ms = phase_breakdown(job, solver, dt, args.steps, phase_ids)
     st = eng.stats()
@@ -606,10 +642,14 @@ def main():
     developed = None
     if args.developed_substeps > 0 and args.solver == "pcisph":
         todo = args.developed_substeps - eng.stats().substeps
-        if todo > 0:
-            eng.step_many(dt, todo, solver)
+        while todo > 0:
+            chunk = min(todo, 100)
+            if world > 1 and not args.no_rebalance:
+                job.rebalance()
+            eng.step_many(dt, chunk, solver)
             eng.synchronize()
-        dblocks, dms, dwall, _, dclocks = timed_blocks(job, solver, dt, args.steps, 3, local_rank)
+            todo -= chunk
+        dblocks, dms, dwall, _, dclocks = timed_blocks(job, solver, dt, args.steps, 3, local_rank, not args.no_rebalance)
         dphase, dgap = phase_breakdown(job, solver, dt, args.steps, phase_ids)
         dst = eng.stats()
         developed = {"after_substeps": int(args.developed_substeps), "ms_per_step": dms, "ms_per_step_blocks": dblocks, "value": n_global / (dms * 1e-3),
@@ -622,6 +662,7 @@ def main():
     # ---- end to end through the C ABI with host buffers ------------------------------------------------------------
     e2e = e2e_leg(job, solver, dt, args.e2e_steps, args.solver == "sph")
     p2p = bool(eng.p2p) if world > 1 else None
+    rebalances = job.rebalances
     job.close()
 
     # ---- the other BASELINE configs this GPU count can hold ----------------------------------------------------------
@@ -663,7 +704,9 @@ def main():
                        "l2_policy": f"working set {state_bytes / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
                        "timing": f"{args.repeats} blocks of {args.steps} sub-steps after {args.warmup} warm-up, each block bracketed by two CUDA events on the engine's stream "
                                  "(launch gaps included), max over ranks per block; ms_per_step = the MEDIAN block",
-                       "ms_per_step_blocks": blocks, "wall_ms_per_step": wall_ms, "host_numa_binding": numa},
+                       "ms_per_step_blocks": blocks, "wall_ms_per_step": wall_ms, "host_numa_binding": numa,
+                       "rebalance": (None if world == 1 else ("off (static plan)" if args.no_rebalance else
+                                     f"z cuts re-planned at the start of every timed block (bbx_rebalance; {rebalances} moves so far, their host time is inside the blocks)"))},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),

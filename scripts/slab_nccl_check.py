@@ -39,7 +39,25 @@ def main():
     eng.set_colliders(scenes.engine_colliders(sc))
     eng.set_particles_ids(sc["pos"], sc["vel"])
     n0 = eng.n
-    eng.step_many(sc["dt"], steps)
+    # two thirds of the way, then the z cuts are re-planned from the per-plane histogram (bbx_plane_counts summed over the
+    # ranks -> bbx_slab_plan -> bbx_slab_plan_step -> bbx_rebalance: planes change hands over NCCL), then the rest
+    first = (2 * steps) // 3
+    eng.step_many(sc["dt"], first)
+    hist_now = torch.from_numpy(eng.plane_counts()).cuda()
+    dist.all_reduce(hist_now, op=dist.ReduceOp.SUM)
+    target = bb.plan_slabs(hist_now.cpu().numpy(), world)
+    zb_now, moves = list(zb), 0
+    for _ in range(8):
+        if zb_now == list(target):
+            break
+        step, _ = bb.plan_step(zb_now, target)
+        if step == zb_now:
+            break
+        eng.rebalance(step)
+        zb_now = step
+        moves += 1
+    n_mid = eng.n
+    eng.step_many(sc["dt"], steps - first)
     parts = {}
     ids, parts["pos"] = eng.download_owned(bb.POSITION, np.float32)
     _, parts["vel"] = eng.download_owned(bb.VELOCITY, np.float32)
@@ -47,14 +65,15 @@ def main():
     cc, co = eng.export_cells()
     st = eng.stats()
     gathered = [None] * world
-    dist.gather_object((ids, parts, cc, co, n0, eng.n, st.nan_count, st.ghosts), gathered if rank == 0 else None, dst=0)
+    dist.gather_object((ids, parts, cc, co, n0, eng.n, st.nan_count, st.ghosts, n_mid), gathered if rank == 0 else None, dst=0)
     ok = True
     if rank == 0:
         one = scenes.make_engine(sc, device=local)
         one.set_particles(sc["pos"], sc["vel"])
         one.step_many(sc["dt"], steps)
         n = len(sc["pos"])
-        res = {"n_gpus": world, "particles": n, "steps": steps, "z_bounds": zb}
+        res = {"n_gpus": world, "particles": n, "steps": steps, "z_bounds": zb, "z_bounds_rebalanced": zb_now, "rebalance_calls": moves,
+               "owned_after_rebalance": [g[8] for g in gathered]}
         owned = np.zeros(n, dtype=np.int32)
         merged = {k: np.zeros((n, 3) if k != "rho" else n, dtype=np.float32) for k in parts}
         ccs = np.zeros(grid.total, dtype=np.int32)
