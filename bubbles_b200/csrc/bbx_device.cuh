@@ -104,7 +104,7 @@ struct DevState {
     unsigned max_force_bits; // float bits of max |f| (non-negative floats order like unsigned)
     unsigned max_err_bits;   // float bits of max |rho* - rho0|
     int n_occ;           // occupied cells found by the last scan
-    int qn[2];           // collider slow-path queue lengths: [0] predict, [1] integrate
+    int qn[4];           // collider slow-path queue lengths: [0] predict, [1] integrate; [2], [3]: the same for the boundary passes of a slab engine (their own queue)
     unsigned scan_ticket;
     int iterations;
     int n_own;           // owned particles after the last grid update / upload (slab engines)
@@ -150,9 +150,33 @@ struct StepParams {
     float thr_lo, thr_hi; // thr2 -+ band: below thr_lo certainly accepted, above thr_hi certainly rejected
     float xacc, xband;    // the same on x = 1 - d^2 / h^2 (list build): accepted when x > xacc, inside the band when x < xband
     int par;              // parity of the current grid epoch; integrate writes rebuild_flag[par ^ 1]
+    int part;             // slab engines with the halo push: 0 = every block, 1 = the BOUNDARY blocks only (those holding slots of
+                          // the first / last owned plane -- their results go to the neighbours and are wanted early), 2 = the rest
 };
 
 __device__ __forceinline__ int bbx_count(const StepParams &P){ return P.dyn ? P.dyn->n_own : P.n; }
+
+// Boundary / interior split of a sweep over n slots in blocks of T (slots are sorted by cell, z slowest: the first owned
+// plane is slots [0, n_first), the last one [n - n_last, n)).  bbx_part_blocks: how many blocks pass `part` has;
+// bbx_part_block: the real block behind its v-th one.  A block that holds any boundary-plane slot is a boundary block, so
+// an interior block never touches a ghost slot -- it needs nothing from the neighbours and can run while their halos travel.
+struct PartMap { int tb0, tb1, nb; };
+__device__ __forceinline__ PartMap bbx_part_map(const StepParams &P, int T, int n){
+    PartMap m; m.nb = (n + T - 1) / T; m.tb0 = 0; m.tb1 = m.nb;
+    if(P.part != 0){
+        const int b0 = min(P.dyn->n_first, n), b1 = max(n - P.dyn->n_last, b0);
+        m.tb0 = min((b0 + T - 1) / T, m.nb); m.tb1 = min(max(b1 / T, m.tb0), m.nb);
+    }
+    return m;
+}
+__device__ __forceinline__ int bbx_part_blocks(const StepParams &P, const PartMap &m){
+    return P.part == 0 ? m.nb : (P.part == 1 ? m.tb0 + (m.nb - m.tb1) : m.tb1 - m.tb0);
+}
+__device__ __forceinline__ int bbx_part_block(const StepParams &P, const PartMap &m, int v){   // -1: past the end of the pass
+    if(P.part == 0) return v < m.nb ? v : -1;
+    if(P.part == 1){ const int b = v < m.tb0 ? v : m.tb1 + (v - m.tb0); return b < m.nb ? b : -1; }
+    const int b = m.tb0 + v; return b < m.tb1 ? b : -1;
+}
 
 // ------------------------------------------------------------------------------------------- grid
 

@@ -70,6 +70,9 @@ struct bbx_engine {
     int masked;      // cells smaller than h (informational; the cell-centric list build needs no window test)
     int list_ctas_per_sm;
     long long cells_alloc; // entries of the cell-indexed arrays (slab engines: enough for any slab of the grid)
+    int *queue_b;          // collider slow-path queue of the boundary passes (slab engines with the halo push)
+    int overlap;           // halo push: boundary blocks first, their halo travels while the interior blocks run (BBX_OVERLAP=0: off)
+    unsigned halo_due[BBX_HALO_PHASES]; // sequence number of a halo this engine has signalled but not yet waited for (0: none)
     unsigned short *nbr; int *nbr_cnt;
     float4 *force, *force_p, *pred, *posq, *smoothed;
     float4 *rec;     // 32-byte gather records (x, y, z, rho | vx, vy, vz, -), 2 float4 per slot, written by the list build
@@ -219,7 +222,7 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     *slot = e; // from here on the caller destroys it on failure
     e->stream = nullptr; e->side = nullptr; e->ev_fork = nullptr; e->ev_join = nullptr; e->comm = nullptr;
     for(int b = 0; b < 2; b++){ e->pos[b] = e->vel[b] = nullptr; e->pid[b] = e->cell[b] = e->cell_start[b] = nullptr; }
-    e->newcell = e->count = e->perm = e->occ_cells = e->queue = nullptr; e->movemask = nullptr; e->scan_status = nullptr;
+    e->newcell = e->count = e->perm = e->occ_cells = e->queue = e->queue_b = nullptr; e->overlap = 0; memset(e->halo_due, 0, sizeof(e->halo_due)); e->movemask = nullptr; e->scan_status = nullptr;
     e->nbr = nullptr; e->nbr_cnt = nullptr; e->force = e->force_p = e->pred = e->posq = e->smoothed = e->rec = nullptr;
     e->pressure = e->rho_pred = e->rho_err = nullptr; e->st = nullptr; e->st_host = nullptr; e->err_probe = nullptr;
     e->colliders = nullptr; e->cull = nullptr; e->gtab = nullptr; e->halo_flags = nullptr; e->mail_host = nullptr; e->stage = nullptr;
@@ -322,6 +325,7 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     }
     BBX_TRY(dev_alloc(&e->count, (size_t)e->cells_alloc + 8)); BBX_TRY(dev_alloc(&e->perm, cap));
     BBX_TRY(dev_alloc(&e->occ_cells, (size_t)e->cells_alloc)); BBX_TRY(dev_alloc(&e->queue, cap));
+    if(e->has_lo || e->has_hi) BBX_TRY(dev_alloc(&e->queue_b, cap));
     BBX_TRY(dev_alloc(&e->movemask, (size_t)e->cells_alloc));
     e->scan_tiles = div_up(g.c_own1 - g.c_own0, SCAN_TILE);
     BBX_TRY(dev_alloc(&e->scan_status, (size_t)div_up(e->cells_alloc, SCAN_TILE)));
@@ -359,7 +363,7 @@ int bbx_destroy(bbx_engine *e){
     if(e->comm){ delete e->comm; e->comm = nullptr; }
     for(void *p : e->raw) cudaFree(p);
     for(int b = 0; b < 2; b++) cudaFree(e->cell_start[b]);
-    cudaFree(e->movemask); cudaFree(e->count); cudaFree(e->perm); cudaFree(e->occ_cells); cudaFree(e->queue); cudaFree(e->scan_status);
+    cudaFree(e->movemask); cudaFree(e->count); cudaFree(e->perm); cudaFree(e->occ_cells); cudaFree(e->queue); cudaFree(e->queue_b); cudaFree(e->scan_status);
     cudaFree(e->nbr); cudaFree(e->nbr_cnt); cudaFree(e->force); cudaFree(e->force_p);
     cudaFree(e->smoothed); cudaFree(e->pressure); cudaFree(e->rho_pred); cudaFree(e->rho_err);
     if(e->gtab) cudaFree(e->gtab);
@@ -509,10 +513,12 @@ int bbx_set_particles_ids(bbx_engine *e, int n, const void *pos, const void *vel
 // Re-sort after an append: old particles keep their recorded cell and their order inside it, the appended ones
 // follow in id order.  Counting sort by cell with the full-rebuild kernels, ordered by OLD SLOT (old slots are in
 // chain order, the appended particles sit behind them in id order).  Not a grid epoch: flags and parity stay.
-static int slab_refresh_ghosts(bbx_engine *e, int nxt);
+static int slab_refresh_ghosts(bbx_engine *e, int nxt, unsigned posted_seq = 0);
 // split / id0: see k_full_sort_cells (slab engines: the appended particles are ordered by id, not by slot)
+static int halo_settle_all(bbx_engine *e);
 static int append_update(bbx_engine *e, int n_old, int k, int split = -1, int id0 = 0){
     DevGrid &g = e->grid;
+    { int rc = halo_settle_all(e); if(rc) return rc; }
     const int cur = e->cur, nxt = cur ^ 1, n_all = n_old + k, par = e->epoch & 1;
     const int own_cells = g.c_own1 - g.c_own0;
     LAUNCH(e, k_append_hash, div_up(std::max(n_all, e->scan_tiles), 256), 256, n_old, k, e->pos[cur], e->cell[cur], e->newcell, e->count, g, e->st, e->scan_status, e->scan_tiles);
@@ -852,6 +858,7 @@ static void make_params(bbx_engine *e, double dt, StepParams &P){
     // list build: x = 1 - d^2 / h^2 evaluated in the cell frame (absolute error of a few 1e-7, bbx_lists.cuh)
     { double bx = 4.0e-6 + 4e-8 / (h * h); P.xacc = (float)(1e-8 / (h * h) - bx); P.xband = (float)(1e-8 / (h * h) + bx); }
     P.par = (e->epoch + 1) & 1; // parity of the grid epoch this sub-step runs under (set right after its grid update)
+    P.part = 0;
     P.mass = (float)e->mass; P.mass2 = (float)(e->mass * e->mass); P.inv_mass = (float)(1.0 / e->mass);
     P.rho0 = (float)c.target_density;
     P.w_std_c = (float)(315.0 / (64.0 * pi * h * h * h));
@@ -878,6 +885,7 @@ static void make_params(bbx_engine *e, double dt, StepParams &P){
 // are contiguous because slots are sorted by cell id and z is the slowest cell index -- no pack kernels.
 static int exchange_planes(bbx_engine *e, void *const *arr, const size_t *esz, int narr){
     if(!IS_SLAB(e)) return BBX_OK;
+    { int rc = halo_settle_all(e); if(rc) return rc; }
     { int rc = sync_counts(e); if(rc) return rc; } // (send / recv sizes are host values)
     BbxSeg slo[BBX_MAX_SEGS], rlo[BBX_MAX_SEGS], shi[BBX_MAX_SEGS], rhi[BBX_MAX_SEGS];
     for(int k = 0; k < narr; k++){
@@ -919,6 +927,34 @@ static int halo_sync(bbx_engine *e, int phase){
     LAUNCH(e, k_halo_signal, 1, 32, halo_flag_at(e, 0, phase), halo_flag_at(e, 1, phase), seq);
     return halo_wait(e, phase, seq);
 }
+// Overlapped form: the signal goes out as soon as the BOUNDARY blocks of the phase have stored their results into the
+// neighbours (the interior blocks are launched behind it), the matching wait is issued only where the neighbours' results
+// are read -- in front of the boundary blocks of the next phase.  The skew between the ranks then hides behind the interior
+// work instead of adding up phase by phase.
+static void halo_signal(bbx_engine *e, int phase){
+    const unsigned seq = ++e->halo_seq[phase];
+    LAUNCH(e, k_halo_signal, 1, 32, halo_flag_at(e, 0, phase), halo_flag_at(e, 1, phase), seq);
+    e->halo_due[phase] = seq;
+}
+static int halo_settle(bbx_engine *e, int phase){
+    if(!e->halo_due[phase]) return BBX_OK;
+    const unsigned seq = e->halo_due[phase];
+    e->halo_due[phase] = 0;
+    return halo_wait(e, phase, seq);
+}
+static int halo_settle_all(bbx_engine *e){
+    for(int ph = HALO_DENSITY; ph <= HALO_INTEGRATE; ph++){ int rc = halo_settle(e, ph); if(rc) return rc; }
+    return BBX_OK;
+}
+// blocks of T slots that can hold slots of the boundary planes (upper bound: a boundary plane fits the neighbour's ghost slots)
+static int boundary_blocks(bbx_engine *e, int T){
+    long long slots = 0;
+    if(e->has_lo) slots += std::min<long long>(e->cap, e->peer[0].gc);
+    if(e->has_hi) slots += std::min<long long>(e->cap, e->peer[1].gc);
+    slots = std::min<long long>(slots, launch_n(e));
+    return (int)(slots / T) + 4;
+}
+static inline StepParams with_part(const StepParams &P, int part){ StepParams Q = P; Q.part = part; return Q; }
 // once the communicator is up: map the neighbours' arrays (BBX_P2P=0 keeps the send / recv path)
 static int setup_peers(bbx_engine *e){
     e->p2p = 0; e->peers_ready = 1;
@@ -942,12 +978,31 @@ static int setup_peers(bbx_engine *e){
         p.gc = a.gc;
     }
     e->p2p = 1;
+    {
+        const char *ov = getenv("BBX_OVERLAP");
+#ifdef BBX_LISTS_V7
+        e->overlap = 0;
+#else
+        e->overlap = (ov && ov[0] == '0') ? 0 : 1;
+#endif
+    }
     return BBX_OK;
 }
 
 // Slab engines, after the owned slots of buffer `nxt` have been (re)ordered: the ghost planes of that buffer are replaced by
 // the neighbours' freshly ordered boundary planes (collective: counts, planes, ghost part of the cell table).
-static int slab_refresh_ghosts(bbx_engine *e, int nxt){
+// (halo push) my boundary-plane sizes and owned count into the neighbours' mailboxes + the counts flag: possible as soon as
+// the scan has produced the new cell table -- the grid update posts them BEFORE its fill, so that the neighbours' counts are
+// on their way while the fill runs (returns the sequence number slab_refresh_ghosts waits for)
+static unsigned post_counts(bbx_engine *e, int nxt){
+    DevGrid &g = e->grid;
+    int *mlo = e->has_lo ? (int *)(e->peer[0].flags + 2 * BBX_HALO_PHASES) + 1 * BBX_HALO_MAIL : nullptr; // I am its UPPER side
+    int *mhi = e->has_hi ? (int *)(e->peer[1].flags + 2 * BBX_HALO_PHASES) + 0 * BBX_HALO_MAIL : nullptr;
+    const unsigned seq = ++e->halo_seq[HALO_COUNTS];
+    LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, mlo, mhi, halo_flag_at(e, 0, HALO_COUNTS), halo_flag_at(e, 1, HALO_COUNTS), seq);
+    return seq;
+}
+static int slab_refresh_ghosts(bbx_engine *e, int nxt, unsigned posted_seq){
     DevGrid &g = e->grid;
     // migration happened implicitly: particles that crossed into my planes were found in my ghost
     // planes' old chains (in the reference's order), particles that left simply were not placed.
@@ -957,10 +1012,7 @@ static int slab_refresh_ghosts(bbx_engine *e, int nxt){
         // sizes travel through the neighbours' mailboxes (peer memory) and stay on the device: k_slab_counts posts mine,
         // k_slab_plan reads theirs into DevState, k_push_planes takes its ranges from there -- no host round trip
         int *mail = (int *)(e->halo_flags + 2 * BBX_HALO_PHASES);
-        int *mlo = e->has_lo ? (int *)(e->peer[0].flags + 2 * BBX_HALO_PHASES) + 1 * BBX_HALO_MAIL : nullptr; // I am its UPPER side
-        int *mhi = e->has_hi ? (int *)(e->peer[1].flags + 2 * BBX_HALO_PHASES) + 0 * BBX_HALO_MAIL : nullptr;
-        const unsigned seq = ++e->halo_seq[HALO_COUNTS];
-        LAUNCH(e, k_slab_counts, 1, 1, g, e->st, e->cell_start[nxt], e->has_lo, e->has_hi, mlo, mhi, halo_flag_at(e, 0, HALO_COUNTS), halo_flag_at(e, 1, HALO_COUNTS), seq);
+        const unsigned seq = posted_seq ? posted_seq : post_counts(e, nxt);
         int rc = halo_wait(e, HALO_COUNTS, seq); if(rc) return rc;
         LAUNCH(e, k_slab_plan, 1, 1, e->st, mail, e->has_lo, e->has_hi, (int)std::min<long long>(e->peer[0].gc, 0x7fffffff), (int)std::min<long long>(e->peer[1].gc, 0x7fffffff), e->n_launch);
         {   // the counts of this update on their way to the host (looked at BBX_HINT_LAG updates from now)
@@ -1018,6 +1070,7 @@ static int grid_update(bbx_engine *e){
     if(slab && !e->peers_ready){ int rc = setup_peers(e); if(rc) return rc; }
     DevGrid &g = e->grid;
     const int cur = e->cur, nxt = cur ^ 1;
+    if(slab){ int rc = halo_settle_all(e); if(rc) return rc; } // (the neighbours' x, v of the last integration: hashed below)
     // single domain: the host knows the counts.  Slab engines: they live in DevState (n_all = -1 tells the kernels to read
     // them there) and the launches cover the capacity -- nothing below waits for the host when the halo push is on.
     const int n_all = slab ? -1 : e->n, n_lo = slab ? 0 : 0, n_own = slab ? 0 : e->n;
@@ -1045,6 +1098,8 @@ static int grid_update(bbx_engine *e){
         CU(cudaEventRecord(e->ev_join, e->side));
     }
     LAUNCH(e, k_scan_cells, e->scan_tiles, 256, e->count + g.c_own0, own_cells, g.c_own0, e->scan_status, e->st, e->cell_start[nxt] + g.c_own0, e->occ_cells);
+    unsigned counts_seq = 0;
+    if(slab && e->p2p) counts_seq = post_counts(e, nxt);   // the new table is complete: the sizes can travel while the fill runs
     if(!force){
         // persistent grid: 8 lanes per occupied cell, grid-stride over the compact list of occupied cells
         int groups = std::max(1, std::min(n_bound, own_cells));
@@ -1062,7 +1117,7 @@ static int grid_update(bbx_engine *e){
     LAUNCH(e, k_full_gather, fb_n, 256, e->st, par, force, e->perm, e->newcell, e->pos[cur], e->vel[cur], e->pid[cur],
            e->pos[nxt], e->vel[nxt], e->pid[nxt], e->cell[nxt], e->rec);
     CU(cudaGetLastError());
-    if(slab){ int rc = slab_refresh_ghosts(e, nxt); if(rc) return rc; }
+    if(slab){ int rc = slab_refresh_ghosts(e, nxt, counts_seq); if(rc) return rc; }
     e->cur = nxt;
     e->have_chains = 1;
     e->last_force = force;
@@ -1088,6 +1143,17 @@ static int phase_density(bbx_engine *e, const StepParams &P, int sph){
     if(launch_n(e) > 0){
 #ifndef BBX_LISTS_V7
         if(sph) LAUNCH_S(e, k_lists_density_tp<1>, list_blocks(e), BBX_TP_WARPS * 32, BBX_TP_SMEM, P, e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec, halo_none());
+        else if(e->overlap){
+            // boundary tiles (their rho / records go to the neighbours), the density flag, then everything else
+            const int bb_ = std::min(div_up(boundary_blocks(e, 32), BBX_TP_WARPS), e->sm_count * e->list_ctas_per_sm);
+            LAUNCH_S(e, k_lists_density_tp<0>, bb_, BBX_TP_WARPS * 32, BBX_TP_SMEM, with_part(P, 1), e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
+                     halo_dst(e, e->peer[0].rec, e->peer[1].rec));
+            halo_signal(e, HALO_DENSITY);
+            LAUNCH_S(e, k_lists_density_tp<0>, list_blocks(e), BBX_TP_WARPS * 32, BBX_TP_SMEM, with_part(P, 2), e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
+                     halo_none());
+            CU(cudaGetLastError());
+            return BBX_OK;
+        }
         else LAUNCH_S(e, k_lists_density_tp<0>, list_blocks(e), BBX_TP_WARPS * 32, BBX_TP_SMEM, P, e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
                     halo_dst(e, e->peer[0].rec, e->peer[1].rec));
 #else
@@ -1097,6 +1163,7 @@ static int phase_density(bbx_engine *e, const StepParams &P, int sph){
 #endif
         CU(cudaGetLastError());
     }
+    if(!sph && e->overlap){ halo_signal(e, HALO_DENSITY); return BBX_OK; }   // (a slab without particles still signals)
     if(!sph && e->p2p) return halo_sync(e, HALO_DENSITY);
     // ghost rho (and, for the SPH step, p / rho^2): both force sweeps read the 32-byte records (x, rho | v, p / rho^2)
     { void *arr[1] = {e->rec}; size_t z[1] = {2 * sizeof(float4)}; return exchange_planes(e, arr, z, 1); }
@@ -1107,6 +1174,22 @@ static int sweep_grid(bbx_engine *e){ return div_up(launch_n(e), BBX_BS); }
 static int tile_grid(bbx_engine *e){ return div_up(launch_n(e), BBX_TS); }
 static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
     int cur = e->cur;
+    if(e->overlap){
+        int rc = halo_settle(e, HALO_DENSITY); if(rc) return rc;           // the boundary blocks read the neighbours' rho
+        for(int part = 1; part <= 2; part++){
+            if(launch_n(e) > 0){
+                const StepParams Q = with_part(P, part);
+                int *q = part == 1 ? e->queue_b : e->queue;
+                const HaloDst H = part == 1 ? halo_dst(e, e->peer[0].pred, e->peer[1].pred) : halo_none();
+                LAUNCH(e, k_force_np_predict, part == 1 ? boundary_blocks(e, BBX_BS) : sweep_grid(e), BBX_BS, Q, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->rec, e->cell[cur], e->cell_start[cur],
+                       e->nbr, e->nbr_cnt, e->force, e->pred, q, H);
+                LAUNCH(e, k_collide_predict, BBX_SMALL_GRID, 128, Q, e->st, e->colliders, q, e->pos[cur], e->vel[cur], e->force, e->pred, H);
+                CU(cudaGetLastError());
+            }
+            if(part == 1) halo_signal(e, HALO_PREDICT);
+        }
+        return BBX_OK;
+    }
     if(launch_n(e) > 0){
         LAUNCH(e, k_force_np_predict, sweep_grid(e), BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->rec, e->cell[cur], e->cell_start[cur],
                e->nbr, e->nbr_cnt, e->force, e->pred, e->queue, halo_dst(e, e->peer[0].pred, e->peer[1].pred));
@@ -1119,6 +1202,18 @@ static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
 }
 static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
     int cur = e->cur;
+    if(e->overlap){
+        int rc = halo_settle(e, HALO_PREDICT); if(rc) return rc;           // the boundary blocks read the neighbours' x*
+        for(int part = 1; part <= 2; part++){
+            if(launch_n(e) > 0){
+                LAUNCH_S(e, k_pressure, part == 1 ? boundary_blocks(e, BBX_TS) : tile_grid(e), BBX_TS, BBX_STAGE_BYTES(3), with_part(P, part), e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
+                         e->nbr, e->nbr_cnt, e->pressure, e->rho_pred, e->rho_err, e->posq, part == 1 ? halo_dst(e, e->peer[0].posq, e->peer[1].posq) : halo_none());
+                CU(cudaGetLastError());
+            }
+            if(part == 1) halo_signal(e, HALO_PRESSURE);
+        }
+        return BBX_OK;
+    }
     if(launch_n(e) > 0){
         LAUNCH_S(e, k_pressure, tile_grid(e), BBX_TS, BBX_STAGE_BYTES(3), P, e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
                e->nbr, e->nbr_cnt, e->pressure, e->rho_pred, e->rho_err, e->posq, halo_dst(e, e->peer[0].posq, e->peer[1].posq));
@@ -1129,6 +1224,21 @@ static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
 }
 static int phase_pressure_force(bbx_engine *e, const StepParams &P, int integrate){
     int cur = e->cur; int nb = sweep_grid(e);
+    if(e->overlap){ int rc = halo_settle(e, HALO_PRESSURE); if(rc) return rc; }   // the neighbours' (x, p / rho*^2)
+    if(e->overlap && integrate){
+        for(int part = 1; part <= 2; part++){
+            if(launch_n(e) > 0){
+                const StepParams Q = with_part(P, part);
+                int *q = part == 1 ? e->queue_b : e->queue;
+                const HaloDst H = part == 1 ? halo_dst(e, e->peer[0].pos[cur], e->peer[1].pos[cur], e->peer[0].vel[cur], e->peer[1].vel[cur]) : halo_none();
+                LAUNCH(e, k_pressure_force<1>, part == 1 ? boundary_blocks(e, BBX_BS) : nb, BBX_BS, Q, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, q, H);
+                LAUNCH(e, k_collide_integrate, BBX_SMALL_GRID, 128, Q, e->grid, e->st, e->colliders, q, e->pos[cur], e->vel[cur], e->force, H);
+                CU(cudaGetLastError());
+            }
+            if(part == 1) halo_signal(e, HALO_INTEGRATE);   // (waited for by the next grid update)
+        }
+        return BBX_OK;
+    }
     if(launch_n(e) > 0){
         if(integrate){
             LAUNCH(e, k_pressure_force<1>, nb, BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, e->queue,
@@ -1645,7 +1755,8 @@ int bbx_rebalance(bbx_engine *e, const int *z_bounds){
     if(!z_bounds) return set_error(BBX_ERR_INVALID, "null");
     if(!e->comm) return set_error(BBX_ERR_INVALID, "slab engine without a communicator");
     if(!e->have_chains) return set_error(BBX_ERR_INVALID, "bbx_rebalance needs a particle set (bbx_set_particles_ids) first");
-    int rc = sync_counts(e); if(rc) return rc;
+    int rc = halo_settle_all(e); if(rc) return rc;
+    rc = sync_counts(e); if(rc) return rc;
     DevGrid &g = e->grid;
     const int rank = e->comm->rank, nranks = e->comm->nranks;
     const int z0 = g.zoff + g.own_z0, z1 = g.zoff + g.own_z1, nz0 = z_bounds[rank], nz1 = z_bounds[rank + 1];

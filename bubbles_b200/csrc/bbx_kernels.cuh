@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) k_hash_count(int n_all, int n_lo, int n_o
         st->n_own_prev = n_own;
         st->rebuild_flag[par ^ 1] = 0; st->jump_flag[par ^ 1] = 0; st->lost[par ^ 1] = 0;
         st->overflow = 0; st->clamped = 0; st->nan_count = 0; st->max_force_bits = 0; st->max_err_bits = 0;
-        st->qn[0] = 0; st->qn[1] = 0; st->scan_ticket = 0; st->n_occ = 0;
+        st->qn[0] = 0; st->qn[1] = 0; st->qn[2] = 0; st->qn[3] = 0; st->scan_ticket = 0; st->n_occ = 0;
         st->exact_passes = 0; st->max_candidates = 0; st->unstaged_tiles = 0;
     }
     if(idx < scan_tiles) scan_status[idx] = 0ull;
@@ -482,8 +482,10 @@ __device__ __forceinline__ uint4 *bbx_chunk_ptr(unsigned short *__restrict__ nbr
 // Each thread keeps the 9 run bases of its cell in shared memory (dynamic index by run id).
 #define BBX_LIST_PROLOGUE()                                                                        \
     __shared__ int sbase[9 * BBX_BS];                                                              \
-    int i = blockIdx.x * BBX_BS + threadIdx.x;                                                     \
-    bool live = i < bbx_count(P);                                                                  \
+    const int n_ = bbx_count(P);                                                                   \
+    const int blk_ = bbx_part_block(P, bbx_part_map(P, BBX_BS, n_), blockIdx.x);                   \
+    int i = blk_ * BBX_BS + threadIdx.x;                                                           \
+    bool live = blk_ >= 0 && i < n_;                                                               \
     int cnt = 0;                                                                                   \
     if(live){                                                                                      \
         int base[9], end[9];                                                                       \
@@ -558,13 +560,13 @@ __device__ __forceinline__ void bbx_for_each_neighbor(const uint4 *__restrict__ 
 // per-thread run bases for the list walk (stride BBX_TS): an index into the component arrays
 // stage[k * BBX_STAGE_CAP + j] if *staged (CTA-uniform), else a global slot index.
 template<int REC, int NC>
-__device__ __forceinline__ const int *bbx_stage_tile(const DevGrid &g, int n, const int *__restrict__ cell, const int *__restrict__ cell_start,
+__device__ __forceinline__ const int *bbx_stage_tile(const DevGrid &g, int n, int blk, const int *__restrict__ cell, const int *__restrict__ cell_start,
         const float4 *__restrict__ src, unsigned char *smem, DevState *st_, bool *staged, const float **stage_out)
 {
     int *ttab = reinterpret_cast<int *>(smem);             // [0..9] staged offset of each run (exclusive prefix, [9] = total), [10..18] first slot
     int *sbase = reinterpret_cast<int *>(smem + BBX_STAGE_HDR);
     float *stage = reinterpret_cast<float *>(smem + BBX_STAGE_HDR + 9 * BBX_TS * 4);
-    const int tid = threadIdx.x, i0 = blockIdx.x * BBX_TS, i = i0 + tid;
+    const int tid = threadIdx.x, i0 = blk * BBX_TS, i = i0 + tid;
     if(tid < 32){
         const int lane = tid;
         const int c_lo = cell[i0], c_hi = cell[min(i0 + BBX_TS, n) - 1];
@@ -686,7 +688,7 @@ __global__ void __launch_bounds__(BBX_BS) k_force_np_predict(StepParams P, DevGr
     float tvx = vi.x + k * fx, tvy = vi.y + k * fy, tvz = vi.z + k * fz;
     float tpx = pi.x + P.dt * tvx, tpy = pi.y + P.dt * tvy, tpz = pi.z + P.dt * tvz;
     pred[i] = make_float4(tpx, tpy, tpz, 0.f);
-    if(!bbx_cull(*cull, tpx, tpy, tpz, P.radius)) queue[atomicAdd(&st->qn[0], 1)] = i; // (k_collide_predict pushes its halo copy)
+    if(!bbx_cull(*cull, tpx, tpy, tpz, P.radius)) queue[atomicAdd(&st->qn[P.part == 1 ? 2 : 0], 1)] = i; // (k_collide_predict pushes its halo copy)
     else{ H = bbx_halo_resolve(H, st); bbx_halo_store(H, 0, 1, i, 0, make_float4(tpx, tpy, tpz, 0.f)); }
 }
 
@@ -703,7 +705,7 @@ __global__ void __launch_bounds__(128) k_collide_predict(StepParams P, const Dev
         const int *__restrict__ queue, const float4 *__restrict__ pos, const float4 *__restrict__ vel,
         const float4 *__restrict__ force, float4 *__restrict__ pred, HaloDst H)
 {
-    const int qn = st->qn[0];
+    const int qn = st->qn[P.part == 1 ? 2 : 0];
     H = bbx_halo_resolve(H, st);
     for(int q = blockIdx.x * blockDim.x + threadIdx.x; q < qn; q += gridDim.x * blockDim.x){
         int i = queue[q];
@@ -743,9 +745,10 @@ __global__ void __launch_bounds__(BBX_TS, 4) k_pressure(StepParams P, DevGrid g,
 {
     bool staged; const float *S;
     const int n = bbx_count(P);
-    if((int)blockIdx.x * BBX_TS >= n) return; // (the launch covers the capacity of a slab engine)
-    const int *scol = bbx_stage_tile<1, 3>(g, n, cell, cell_start, pred, bbx_dyn_smem, st, &staged, &S);
-    const int i = blockIdx.x * BBX_TS + threadIdx.x;
+    const int blk = bbx_part_block(P, bbx_part_map(P, BBX_TS, n), blockIdx.x);
+    if(blk < 0) return; // (the launch covers the capacity of a slab engine / the largest boundary pass)
+    const int *scol = bbx_stage_tile<1, 3>(g, n, blk, cell, cell_start, pred, bbx_dyn_smem, st, &staged, &S);
+    const int i = blk * BBX_TS + threadIdx.x;
     if(i >= n) return;
     const int cnt = nbr_cnt[i];
     const uint4 *lp = reinterpret_cast<const uint4 *>(nbr) + ((size_t)(i >> 5) * BBX_NBR_CHUNKS) * 32 + (i & 31);
@@ -856,7 +859,7 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid
             H = bbx_halo_resolve(H, st);
             bbx_halo_store(H, 0, 1, i, 0, po); bbx_halo_store(H, 1, 1, i, 0, vo);
         }else{
-            queue[atomicAdd(&st->qn[1], 1)] = i; // pos / vel stay untouched: the exact kernel redoes the update
+            queue[atomicAdd(&st->qn[P.part == 1 ? 3 : 1], 1)] = i; // pos / vel stay untouched: the exact kernel redoes the update
         }
     }
 }
@@ -864,7 +867,7 @@ __global__ void __launch_bounds__(BBX_BS) k_pressure_force(StepParams P, DevGrid
 __global__ void __launch_bounds__(128) k_collide_integrate(StepParams P, DevGrid g, DevState *st, const DevColliderSet *__restrict__ cs,
         const int *__restrict__ queue, float4 *__restrict__ pos, float4 *__restrict__ vel, const float4 *__restrict__ force, HaloDst H)
 {
-    const int qn = st->qn[1];
+    const int qn = st->qn[P.part == 1 ? 3 : 1];
     H = bbx_halo_resolve(H, st);
     for(int q = blockIdx.x * blockDim.x + threadIdx.x; q < qn; q += gridDim.x * blockDim.x){
         int i = queue[q];

@@ -140,9 +140,11 @@ __global__ void __launch_bounds__(BBX_TP_WARPS * 32, BBX_TP_MINB) k_lists_densit
     unsigned par = 0;                  // bit b: phase parity the next wait on mbar[b] expects
     const int n = bbx_count(P);
     H = bbx_halo_resolve(H, st);
-    const int ntiles = (n + 31) >> 5, nwarps = gridDim.x * BBX_TP_WARPS;
+    const PartMap pm = bbx_part_map(P, 32, n);          // (slab engines: boundary tiles first, see bbx_part_map)
+    const int nvt = bbx_part_blocks(P, pm), nwarps = gridDim.x * BBX_TP_WARPS;
 #pragma unroll 1
-    for(int t = blockIdx.x * BBX_TP_WARPS + warp; t < ntiles; t += nwarps){
+    for(int vt = blockIdx.x * BBX_TP_WARPS + warp; vt < nvt; vt += nwarps){
+        const int t = bbx_part_block(P, pm, vt);
         const int i = t * 32 + lane;
         const bool live = i < n;
         int c = 0; float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
