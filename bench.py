@@ -315,6 +315,7 @@ class Job:
         self.cells = sc["grid"].total // world
         self.z_bounds = list(sc["z_bounds"]) if world > 1 else None
         self.rebalances = 0
+        self.rebalance_ms = []
 
     def rebalance(self, target=None):
         """Slab group: re-plan the z cuts from the current per-plane histogram (bbx_plane_counts summed over the ranks ->
@@ -343,7 +344,9 @@ class Job:
         if moved:
             self.eng.synchronize()
             self.rebalances += 1
-        return (time.perf_counter() - t0) * 1e3
+        ms = (time.perf_counter() - t0) * 1e3
+        self.rebalance_ms.append(round(ms, 3))
+        return ms
 
     def reset(self):
         if self.world > 1:
@@ -662,7 +665,7 @@ def main():
     # ---- end to end through the C ABI with host buffers ------------------------------------------------------------
     e2e = e2e_leg(job, solver, dt, args.e2e_steps, args.solver == "sph")
     p2p = bool(eng.p2p) if world > 1 else None
-    rebalances = job.rebalances
+    rebalances, rebalance_ms = job.rebalances, list(job.rebalance_ms)
     job.close()
 
     # ---- the other BASELINE configs this GPU count can hold ----------------------------------------------------------
@@ -706,7 +709,8 @@ def main():
                                  "(launch gaps included), max over ranks per block; ms_per_step = the MEDIAN block",
                        "ms_per_step_blocks": blocks, "wall_ms_per_step": wall_ms, "host_numa_binding": numa,
                        "rebalance": (None if world == 1 else ("off (static plan)" if args.no_rebalance else
-                                     f"z cuts re-planned at the start of every timed block (bbx_rebalance; {rebalances} moves so far, their host time is inside the blocks)"))},
+                                     f"z cuts re-planned at the start of every timed block (bbx_rebalance; {rebalances} moves so far, their host time is inside the blocks)")),
+                       "rebalance_ms_rank0": rebalance_ms},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),

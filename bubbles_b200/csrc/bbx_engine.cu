@@ -73,6 +73,8 @@ struct bbx_engine {
     int *queue_b;          // collider slow-path queue of the boundary passes (slab engines with the halo push)
     int overlap;           // halo push: boundary blocks first, their halo travels while the interior blocks run (BBX_OVERLAP=0: off)
     unsigned halo_due[BBX_HALO_PHASES]; // sequence number of a halo this engine has signalled but not yet waited for (0: none)
+    cudaStream_t bstream;  // the boundary blocks of a phase run here, beside the interior blocks on `stream`
+    cudaEvent_t ev_b[4], ev_i[4], ev_grid; // boundary / interior blocks of phase k are done; the grid update is done
     unsigned short *nbr; int *nbr_cnt;
     float4 *force, *force_p, *pred, *posq, *smoothed;
     float4 *rec;     // 32-byte gather records (x, y, z, rho | vx, vy, vz, -), 2 float4 per slot, written by the list build
@@ -110,6 +112,7 @@ struct bbx_engine {
 static int push_cull(bbx_engine *e);
 #define LAUNCH(e, kernel, grid, block, ...) do{ kernel<<<(grid), (block), 0, (e)->stream>>>(__VA_ARGS__); (e)->launches++; }while(0)
 #define LAUNCH_S(e, kernel, grid, block, smem, ...) do{ kernel<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__); (e)->launches++; }while(0)
+#define LAUNCH_ON(e, strm, kernel, grid, block, smem, ...) do{ kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__); (e)->launches++; }while(0)
 static inline int div_up(long long a, int b){ return (int)((a + b - 1) / b); }
 
 static const char *device_error_text(int code){
@@ -221,6 +224,7 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     bbx_engine *e = new bbx_engine();
     *slot = e; // from here on the caller destroys it on failure
     e->stream = nullptr; e->side = nullptr; e->ev_fork = nullptr; e->ev_join = nullptr; e->comm = nullptr;
+    e->bstream = nullptr; e->ev_grid = nullptr; for(int k = 0; k < 4; k++){ e->ev_b[k] = nullptr; e->ev_i[k] = nullptr; }
     for(int b = 0; b < 2; b++){ e->pos[b] = e->vel[b] = nullptr; e->pid[b] = e->cell[b] = e->cell_start[b] = nullptr; }
     e->newcell = e->count = e->perm = e->occ_cells = e->queue = e->queue_b = nullptr; e->overlap = 0; memset(e->halo_due, 0, sizeof(e->halo_due)); e->movemask = nullptr; e->scan_status = nullptr;
     e->nbr = nullptr; e->nbr_cnt = nullptr; e->force = e->force_p = e->pred = e->posq = e->smoothed = e->rec = nullptr;
@@ -236,6 +240,9 @@ static int create_engine(const bbx_config *cfg, bbx_engine **slot){
     memset(e->phase_ms, 0, sizeof(e->phase_ms)); memset(e->phase_launches, 0, sizeof(e->phase_launches));
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->bstream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->ev_grid, cudaEventDisableTiming));
+    for(int k = 0; k < 4; k++){ CU(cudaEventCreateWithFlags(&e->ev_b[k], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e->ev_i[k], cudaEventDisableTiming)); }
     CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));
     if(e->sm_count < 1) e->sm_count = 1;
@@ -380,6 +387,9 @@ int bbx_destroy(bbx_engine *e){
     for(cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
     if(e->ev_fork) cudaEventDestroy(e->ev_fork);
     if(e->ev_join) cudaEventDestroy(e->ev_join);
+    if(e->bstream){ cudaStreamSynchronize(e->bstream); cudaStreamDestroy(e->bstream); }
+    if(e->ev_grid) cudaEventDestroy(e->ev_grid);
+    for(int k = 0; k < 4; k++){ if(e->ev_b[k]) cudaEventDestroy(e->ev_b[k]); if(e->ev_i[k]) cudaEventDestroy(e->ev_i[k]); }
     if(e->side) cudaStreamDestroy(e->side);
     if(e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -916,8 +926,8 @@ static unsigned *halo_flag_at(bbx_engine *e, int side, int phase){ // the flag I
     if(side == 0 ? !e->has_lo : !e->has_hi) return nullptr;
     return e->peer[side].flags + (side == 0 ? 1 : 0) * BBX_HALO_PHASES + phase;
 }
-static int halo_wait(bbx_engine *e, int phase, unsigned seq){
-    LAUNCH(e, k_halo_wait, 1, 32, e->has_lo ? e->halo_flags + 0 * BBX_HALO_PHASES + phase : (const unsigned *)nullptr,
+static int halo_wait(bbx_engine *e, int phase, unsigned seq, cudaStream_t strm = nullptr){
+    LAUNCH_ON(e, strm ? strm : e->stream, k_halo_wait, 1, 32, 0, e->has_lo ? e->halo_flags + 0 * BBX_HALO_PHASES + phase : (const unsigned *)nullptr,
            e->has_hi ? e->halo_flags + 1 * BBX_HALO_PHASES + phase : (const unsigned *)nullptr, seq, &e->st->error);
     CU(cudaGetLastError());
     return BBX_OK;
@@ -927,23 +937,51 @@ static int halo_sync(bbx_engine *e, int phase){
     LAUNCH(e, k_halo_signal, 1, 32, halo_flag_at(e, 0, phase), halo_flag_at(e, 1, phase), seq);
     return halo_wait(e, phase, seq);
 }
-// Overlapped form: the signal goes out as soon as the BOUNDARY blocks of the phase have stored their results into the
-// neighbours (the interior blocks are launched behind it), the matching wait is issued only where the neighbours' results
-// are read -- in front of the boundary blocks of the next phase.  The skew between the ranks then hides behind the interior
-// work instead of adding up phase by phase.
-static void halo_signal(bbx_engine *e, int phase){
+// Overlapped form (slab engines with the halo push, reference-compat PCISPH step).  A phase runs as two launches: its
+// BOUNDARY blocks (every block holding a slot of the first / last owned plane) on `bstream`, its interior blocks on
+// `stream`, side by side.  The boundary blocks store their results straight into the neighbours and raise the phase flag;
+// the matching wait sits in front of the boundary blocks of the NEXT phase only -- interior blocks never touch a ghost
+// slot.  So a rank that runs ahead of its neighbour by less than an interior sweep never idles, instead of paying the
+// skew phase by phase.  Dependencies inside the rank: boundary(p) after interior(p-1) [event], interior(p) after
+// boundary(p-1) [event]; the two streams order the rest.
+static void halo_signal(bbx_engine *e, int phase, cudaStream_t strm){
     const unsigned seq = ++e->halo_seq[phase];
-    LAUNCH(e, k_halo_signal, 1, 32, halo_flag_at(e, 0, phase), halo_flag_at(e, 1, phase), seq);
+    LAUNCH_ON(e, strm, k_halo_signal, 1, 32, 0, halo_flag_at(e, 0, phase), halo_flag_at(e, 1, phase), seq);
     e->halo_due[phase] = seq;
 }
-static int halo_settle(bbx_engine *e, int phase){
+static int halo_settle(bbx_engine *e, int phase, cudaStream_t strm = nullptr){
     if(!e->halo_due[phase]) return BBX_OK;
     const unsigned seq = e->halo_due[phase];
     e->halo_due[phase] = 0;
-    return halo_wait(e, phase, seq);
+    return halo_wait(e, phase, seq, strm);
 }
 static int halo_settle_all(bbx_engine *e){
     for(int ph = HALO_DENSITY; ph <= HALO_INTEGRATE; ph++){ int rc = halo_settle(e, ph); if(rc) return rc; }
+    return BBX_OK;
+}
+// start of overlapped phase `ph` (HALO_DENSITY .. HALO_INTEGRATE): order the two streams against the previous phase and
+// put the wait for the neighbours' previous halo in front of the boundary blocks
+static int ov_begin(bbx_engine *e, int ph){
+    if(ph == HALO_DENSITY){
+        CU(cudaEventRecord(e->ev_grid, e->stream));                       // the grid update (ghost planes included) is on `stream`
+        CU(cudaStreamWaitEvent(e->bstream, e->ev_grid, 0));
+        return BBX_OK;
+    }
+    CU(cudaStreamWaitEvent(e->bstream, e->ev_i[ph - 1], 0));
+    CU(cudaStreamWaitEvent(e->stream, e->ev_b[ph - 1], 0));
+    return halo_settle(e, ph - 1, e->bstream);
+}
+static int ov_end(bbx_engine *e, int ph){
+    CU(cudaEventRecord(e->ev_b[ph], e->bstream));
+    CU(cudaEventRecord(e->ev_i[ph], e->stream));
+    if(ph == HALO_INTEGRATE) CU(cudaStreamWaitEvent(e->stream, e->ev_b[ph], 0));   // `stream` done = sub-step done
+    return BBX_OK;
+}
+// after a single phase run on its own (bbx_run_phase): whatever follows on `stream` sees the boundary blocks' results too
+static int ov_join(bbx_engine *e){
+    if(!e->overlap) return BBX_OK;
+    CU(cudaEventRecord(e->ev_grid, e->bstream));
+    CU(cudaStreamWaitEvent(e->stream, e->ev_grid, 0));
     return BBX_OK;
 }
 // blocks of T slots that can hold slots of the boundary planes (upper bound: a boundary plane fits the neighbour's ghost slots)
@@ -1144,15 +1182,16 @@ static int phase_density(bbx_engine *e, const StepParams &P, int sph){
 #ifndef BBX_LISTS_V7
         if(sph) LAUNCH_S(e, k_lists_density_tp<1>, list_blocks(e), BBX_TP_WARPS * 32, BBX_TP_SMEM, P, e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec, halo_none());
         else if(e->overlap){
-            // boundary tiles (their rho / records go to the neighbours), the density flag, then everything else
+            // boundary tiles (their rho / records go to the neighbours, then the density flag) beside all the others
+            int rc = ov_begin(e, HALO_DENSITY); if(rc) return rc;
             const int bb_ = std::min(div_up(boundary_blocks(e, 32), BBX_TP_WARPS), e->sm_count * e->list_ctas_per_sm);
-            LAUNCH_S(e, k_lists_density_tp<0>, bb_, BBX_TP_WARPS * 32, BBX_TP_SMEM, with_part(P, 1), e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
+            LAUNCH_ON(e, e->bstream, k_lists_density_tp<0>, bb_, BBX_TP_WARPS * 32, BBX_TP_SMEM, with_part(P, 1), e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
                      halo_dst(e, e->peer[0].rec, e->peer[1].rec));
-            halo_signal(e, HALO_DENSITY);
+            halo_signal(e, HALO_DENSITY, e->bstream);
             LAUNCH_S(e, k_lists_density_tp<0>, list_blocks(e), BBX_TP_WARPS * 32, BBX_TP_SMEM, with_part(P, 2), e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
                      halo_none());
             CU(cudaGetLastError());
-            return BBX_OK;
+            return ov_end(e, HALO_DENSITY);
         }
         else LAUNCH_S(e, k_lists_density_tp<0>, list_blocks(e), BBX_TP_WARPS * 32, BBX_TP_SMEM, P, e->grid, e->st, e->cell[cur], e->pos[cur], e->vel[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->pressure, e->posq, e->rec,
                     halo_dst(e, e->peer[0].rec, e->peer[1].rec));
@@ -1163,7 +1202,11 @@ static int phase_density(bbx_engine *e, const StepParams &P, int sph){
 #endif
         CU(cudaGetLastError());
     }
-    if(!sph && e->overlap){ halo_signal(e, HALO_DENSITY); return BBX_OK; }   // (a slab without particles still signals)
+    if(!sph && e->overlap){   // (a slab without particles still signals)
+        int rc = ov_begin(e, HALO_DENSITY); if(rc) return rc;
+        halo_signal(e, HALO_DENSITY, e->bstream);
+        return ov_end(e, HALO_DENSITY);
+    }
     if(!sph && e->p2p) return halo_sync(e, HALO_DENSITY);
     // ghost rho (and, for the SPH step, p / rho^2): both force sweeps read the 32-byte records (x, rho | v, p / rho^2)
     { void *arr[1] = {e->rec}; size_t z[1] = {2 * sizeof(float4)}; return exchange_planes(e, arr, z, 1); }
@@ -1175,20 +1218,21 @@ static int tile_grid(bbx_engine *e){ return div_up(launch_n(e), BBX_TS); }
 static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
     int cur = e->cur;
     if(e->overlap){
-        int rc = halo_settle(e, HALO_DENSITY); if(rc) return rc;           // the boundary blocks read the neighbours' rho
+        int rc = ov_begin(e, HALO_PREDICT); if(rc) return rc;              // (the boundary blocks read the neighbours' rho)
         for(int part = 1; part <= 2; part++){
+            cudaStream_t strm = part == 1 ? e->bstream : e->stream;
             if(launch_n(e) > 0){
                 const StepParams Q = with_part(P, part);
                 int *q = part == 1 ? e->queue_b : e->queue;
                 const HaloDst H = part == 1 ? halo_dst(e, e->peer[0].pred, e->peer[1].pred) : halo_none();
-                LAUNCH(e, k_force_np_predict, part == 1 ? boundary_blocks(e, BBX_BS) : sweep_grid(e), BBX_BS, Q, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->rec, e->cell[cur], e->cell_start[cur],
+                LAUNCH_ON(e, strm, k_force_np_predict, part == 1 ? boundary_blocks(e, BBX_BS) : sweep_grid(e), BBX_BS, 0, Q, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->rec, e->cell[cur], e->cell_start[cur],
                        e->nbr, e->nbr_cnt, e->force, e->pred, q, H);
-                LAUNCH(e, k_collide_predict, BBX_SMALL_GRID, 128, Q, e->st, e->colliders, q, e->pos[cur], e->vel[cur], e->force, e->pred, H);
+                LAUNCH_ON(e, strm, k_collide_predict, BBX_SMALL_GRID, 128, 0, Q, e->st, e->colliders, q, e->pos[cur], e->vel[cur], e->force, e->pred, H);
                 CU(cudaGetLastError());
             }
-            if(part == 1) halo_signal(e, HALO_PREDICT);
+            if(part == 1) halo_signal(e, HALO_PREDICT, e->bstream);
         }
-        return BBX_OK;
+        return ov_end(e, HALO_PREDICT);
     }
     if(launch_n(e) > 0){
         LAUNCH(e, k_force_np_predict, sweep_grid(e), BBX_BS, P, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->rec, e->cell[cur], e->cell_start[cur],
@@ -1203,16 +1247,16 @@ static int phase_force_np_predict(bbx_engine *e, const StepParams &P){
 static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
     int cur = e->cur;
     if(e->overlap){
-        int rc = halo_settle(e, HALO_PREDICT); if(rc) return rc;           // the boundary blocks read the neighbours' x*
+        int rc = ov_begin(e, HALO_PRESSURE); if(rc) return rc;             // (the boundary blocks read the neighbours' x*)
         for(int part = 1; part <= 2; part++){
             if(launch_n(e) > 0){
-                LAUNCH_S(e, k_pressure, part == 1 ? boundary_blocks(e, BBX_TS) : tile_grid(e), BBX_TS, BBX_STAGE_BYTES(3), with_part(P, part), e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
+                LAUNCH_ON(e, part == 1 ? e->bstream : e->stream, k_pressure, part == 1 ? boundary_blocks(e, BBX_TS) : tile_grid(e), BBX_TS, BBX_STAGE_BYTES(3), with_part(P, part), e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
                          e->nbr, e->nbr_cnt, e->pressure, e->rho_pred, e->rho_err, e->posq, part == 1 ? halo_dst(e, e->peer[0].posq, e->peer[1].posq) : halo_none());
                 CU(cudaGetLastError());
             }
-            if(part == 1) halo_signal(e, HALO_PRESSURE);
+            if(part == 1) halo_signal(e, HALO_PRESSURE, e->bstream);
         }
-        return BBX_OK;
+        return ov_end(e, HALO_PRESSURE);
     }
     if(launch_n(e) > 0){
         LAUNCH_S(e, k_pressure, tile_grid(e), BBX_TS, BBX_STAGE_BYTES(3), P, e->grid, e->st, first, e->pos[cur], e->pred, e->cell[cur], e->cell_start[cur],
@@ -1224,20 +1268,25 @@ static int phase_pressure(bbx_engine *e, const StepParams &P, int first){
 }
 static int phase_pressure_force(bbx_engine *e, const StepParams &P, int integrate){
     int cur = e->cur; int nb = sweep_grid(e);
-    if(e->overlap){ int rc = halo_settle(e, HALO_PRESSURE); if(rc) return rc; }   // the neighbours' (x, p / rho*^2)
+    if(e->overlap && !integrate){   // ("correct" mode: one launch, after everything the pressure sweep produced, the neighbours' part included)
+        CU(cudaStreamWaitEvent(e->stream, e->ev_b[HALO_PRESSURE], 0));
+        int rc = halo_settle(e, HALO_PRESSURE); if(rc) return rc;
+    }
     if(e->overlap && integrate){
+        int rc = ov_begin(e, HALO_INTEGRATE); if(rc) return rc;            // (the boundary blocks read the neighbours' (x, p / rho*^2))
         for(int part = 1; part <= 2; part++){
+            cudaStream_t strm = part == 1 ? e->bstream : e->stream;
             if(launch_n(e) > 0){
                 const StepParams Q = with_part(P, part);
                 int *q = part == 1 ? e->queue_b : e->queue;
                 const HaloDst H = part == 1 ? halo_dst(e, e->peer[0].pos[cur], e->peer[1].pos[cur], e->peer[0].vel[cur], e->peer[1].vel[cur]) : halo_none();
-                LAUNCH(e, k_pressure_force<1>, part == 1 ? boundary_blocks(e, BBX_BS) : nb, BBX_BS, Q, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, q, H);
-                LAUNCH(e, k_collide_integrate, BBX_SMALL_GRID, 128, Q, e->grid, e->st, e->colliders, q, e->pos[cur], e->vel[cur], e->force, H);
+                LAUNCH_ON(e, strm, k_pressure_force<1>, part == 1 ? boundary_blocks(e, BBX_BS) : nb, BBX_BS, 0, Q, e->grid, e->st, e->cull, e->pos[cur], e->vel[cur], e->posq, e->cell[cur], e->cell_start[cur], e->nbr, e->nbr_cnt, e->force, e->force_p, q, H);
+                LAUNCH_ON(e, strm, k_collide_integrate, BBX_SMALL_GRID, 128, 0, Q, e->grid, e->st, e->colliders, q, e->pos[cur], e->vel[cur], e->force, H);
                 CU(cudaGetLastError());
             }
-            if(part == 1) halo_signal(e, HALO_INTEGRATE);   // (waited for by the next grid update)
+            if(part == 1) halo_signal(e, HALO_INTEGRATE, e->bstream);   // (waited for by the next grid update)
         }
-        return BBX_OK;
+        return ov_end(e, HALO_INTEGRATE);
     }
     if(launch_n(e) > 0){
         if(integrate){
@@ -1397,10 +1446,10 @@ int bbx_run_phase(bbx_engine *e, int phase, double dt){
     StepParams P; make_params(e, dt, P);
     switch(phase){
         case BBX_PHASE_GRID: return grid_update(e);
-        case BBX_PHASE_DENSITY: return phase_density(e, P, 0);
-        case BBX_PHASE_FORCE_NP: return phase_force_np_predict(e, P);
+        case BBX_PHASE_DENSITY: { int rc = phase_density(e, P, 0); return rc ? rc : ov_join(e); }
+        case BBX_PHASE_FORCE_NP: { int rc = phase_force_np_predict(e, P); return rc ? rc : ov_join(e); }
         case BBX_PHASE_PREDICT: return BBX_OK; // fused into FORCE_NP on the first iteration
-        case BBX_PHASE_PRESSURE: return phase_pressure(e, P, 1);
+        case BBX_PHASE_PRESSURE: { int rc = phase_pressure(e, P, 1); return rc ? rc : ov_join(e); }
         case BBX_PHASE_PRESSURE_FORCE: return phase_pressure_force(e, P, 0);
         case BBX_PHASE_INTEGRATE: { int rc = phase_integrate(e, P, 1); if(rc) return rc; e->substeps++; return phase_pseudo_viscosity(e, P, dt); }
     }
