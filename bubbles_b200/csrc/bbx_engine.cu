@@ -1840,27 +1840,29 @@ int bbx_rebalance(bbx_engine *e, const int *z_bounds){
     // the new grid of this rank (one ghost plane per neighbour, as at creation)
     const int zoff_new = nz0 - (e->has_lo ? 1 : 0);
     const long long plane = g.plane;
-    // kept particles -> front of the other buffer, recorded cells re-based to the new local plane numbering
+    // the other buffer is laid out [planes from below | kept | planes from above]: plane order = cell order, chains intact.
+    // Kept particles: recorded cells re-based to the new local plane numbering
     if(n_keep > 0){
-        CU(cudaMemcpyAsync(e->pos[nxt], e->pos[cur] + slot_k0, sizeof(float4) * (size_t)n_keep, cudaMemcpyDeviceToDevice, e->stream));
-        CU(cudaMemcpyAsync(e->vel[nxt], e->vel[cur] + slot_k0, sizeof(float4) * (size_t)n_keep, cudaMemcpyDeviceToDevice, e->stream));
-        CU(cudaMemcpyAsync(e->pid[nxt], e->pid[cur] + slot_k0, sizeof(int) * (size_t)n_keep, cudaMemcpyDeviceToDevice, e->stream));
-        LAUNCH(e, k_cells_shift, div_up(n_keep, 256), 256, n_keep, e->cell[cur] + slot_k0, e->cell[nxt], (int)((long long)(g.zoff - zoff_new) * plane));
+        CU(cudaMemcpyAsync(e->pos[nxt] + r_lo, e->pos[cur] + slot_k0, sizeof(float4) * (size_t)n_keep, cudaMemcpyDeviceToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->vel[nxt] + r_lo, e->vel[cur] + slot_k0, sizeof(float4) * (size_t)n_keep, cudaMemcpyDeviceToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->pid[nxt] + r_lo, e->pid[cur] + slot_k0, sizeof(int) * (size_t)n_keep, cudaMemcpyDeviceToDevice, e->stream));
+        LAUNCH(e, k_cells_shift, div_up(n_keep, 256), 256, n_keep, e->cell[cur] + slot_k0, e->cell[nxt] + r_lo, (int)((long long)(g.zoff - zoff_new) * plane));
     }
     // the planes that leave travel with GLOBAL cell ids (staged in perm: s_lo + s_hi <= n slots)
     if(s_lo > 0) LAUNCH(e, k_cells_shift, div_up(s_lo, 256), 256, s_lo, e->cell[cur], e->perm, (int)((long long)g.zoff * plane));
     if(s_hi > 0) LAUNCH(e, k_cells_shift, div_up(s_hi, 256), 256, s_hi, e->cell[cur] + slot_k1, e->perm + s_lo, (int)((long long)g.zoff * plane));
     CU(cudaGetLastError());
+    const size_t at_hi = (size_t)r_lo + (size_t)n_keep;
     {
         const size_t f4 = sizeof(float4), i4 = sizeof(int);
         BbxSeg slo[4] = {{e->pos[cur], f4 * (size_t)s_lo}, {e->vel[cur], f4 * (size_t)s_lo}, {e->pid[cur], i4 * (size_t)s_lo}, {e->perm, i4 * (size_t)s_lo}};
         BbxSeg shi[4] = {{e->pos[cur] + slot_k1, f4 * (size_t)s_hi}, {e->vel[cur] + slot_k1, f4 * (size_t)s_hi}, {e->pid[cur] + slot_k1, i4 * (size_t)s_hi}, {e->perm + s_lo, i4 * (size_t)s_hi}};
-        const size_t a = (size_t)n_keep, b = (size_t)n_keep + (size_t)r_lo;
-        BbxSeg rlo[4] = {{e->pos[nxt] + a, f4 * (size_t)r_lo}, {e->vel[nxt] + a, f4 * (size_t)r_lo}, {e->pid[nxt] + a, i4 * (size_t)r_lo}, {e->cell[nxt] + a, i4 * (size_t)r_lo}};
-        BbxSeg rhi[4] = {{e->pos[nxt] + b, f4 * (size_t)r_hi}, {e->vel[nxt] + b, f4 * (size_t)r_hi}, {e->pid[nxt] + b, i4 * (size_t)r_hi}, {e->cell[nxt] + b, i4 * (size_t)r_hi}};
+        BbxSeg rlo[4] = {{e->pos[nxt], f4 * (size_t)r_lo}, {e->vel[nxt], f4 * (size_t)r_lo}, {e->pid[nxt], i4 * (size_t)r_lo}, {e->cell[nxt], i4 * (size_t)r_lo}};
+        BbxSeg rhi[4] = {{e->pos[nxt] + at_hi, f4 * (size_t)r_hi}, {e->vel[nxt] + at_hi, f4 * (size_t)r_hi}, {e->pid[nxt] + at_hi, i4 * (size_t)r_hi}, {e->cell[nxt] + at_hi, i4 * (size_t)r_hi}};
         COMM(e->comm->exchange(e->stream, slo, rlo, 4, shi, rhi, 4));
     }
-    if(r_lo + r_hi > 0) LAUNCH(e, k_cells_shift, div_up(r_lo + r_hi, 256), 256, r_lo + r_hi, e->cell[nxt] + n_keep, e->cell[nxt] + n_keep, (int)(-(long long)zoff_new * plane));
+    if(r_lo > 0) LAUNCH(e, k_cells_shift, div_up(r_lo, 256), 256, r_lo, e->cell[nxt], e->cell[nxt], (int)(-(long long)zoff_new * plane));
+    if(r_hi > 0) LAUNCH(e, k_cells_shift, div_up(r_hi, 256), 256, r_hi, e->cell[nxt] + at_hi, e->cell[nxt] + at_hi, (int)(-(long long)zoff_new * plane));
     CU(cudaGetLastError());
     // switch to the new slab
     g.zoff = zoff_new;
@@ -1870,13 +1872,17 @@ int bbx_rebalance(bbx_engine *e, const int *z_bounds){
     g.total = g.plane * g.n[2];
     e->cfg.slab_z_begin = nz0; e->cfg.slab_z_end = nz1;
     e->scan_tiles = div_up(g.c_own1 - g.c_own0, SCAN_TILE);
-    e->cur = nxt; e->n = (int)n_new;
+    e->n = (int)n_new;
     const int n_dev = (int)n_new;
     CU(cudaMemcpyAsync(&e->st->n_own, &n_dev, sizeof(int), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream)); // (n_dev is a stack variable)
     e->n_hint = e->n; e->hint_count = 0; e->n_launch = bound_of(e, e->n);
-    // file the particles under their recorded cells (stable by slot = chain order) and exchange the boundary planes again
-    return append_update(e, e->n, 0);
+    // the slots are in cell order: cell table + gather records from the recorded cells, then the boundary planes again
+    LAUNCH(e, k_table_from_sorted, div_up(std::max(e->n, 1), 256), 256, e->n, g, e->cell[nxt], e->cell_start[nxt], e->pos[nxt], e->vel[nxt], e->rec);
+    CU(cudaGetLastError());
+    rc = slab_refresh_ghosts(e, nxt); if(rc) return rc;
+    e->cur = nxt; e->have_chains = 1;
+    return BBX_OK;
 }
 
 // global cell plane of each particle (the hash of Grid::GetHashedPosition, z component), host arithmetic

@@ -1142,3 +1142,17 @@ __global__ void __launch_bounds__(256) k_cells_shift(int n, const int *src, int 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i < n) dst[i] = src[i] + delta;
 }
+
+// bbx_rebalance: the slots [0, n) are in cell order already (planes arrive in chain order and are laid out in plane order):
+// rebuild the owned part of the cell table from the recorded cells, and the gather records of the force sweeps
+__global__ void __launch_bounds__(256) k_table_from_sorted(int n, DevGrid g, const int *__restrict__ cell, int *__restrict__ start,
+        const float4 *__restrict__ pos, const float4 *__restrict__ vel, float4 *__restrict__ rec)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n == 0){ for(int c = g.c_own0 + i; c <= g.c_own1; c += gridDim.x * blockDim.x) start[c] = 0; return; }
+    if(i >= n) return;
+    const int c = cell[i], prev = i > 0 ? cell[i - 1] : g.c_own0 - 1;
+    for(int cc = prev + 1; cc <= c; cc++) start[cc] = i;
+    if(i == n - 1) for(int cc = c + 1; cc <= g.c_own1; cc++) start[cc] = n;
+    rec[2 * (size_t)i] = pos[i]; rec[2 * (size_t)i + 1] = vel[i];
+}
