@@ -316,28 +316,52 @@ class Job:
         self.z_bounds = list(sc["z_bounds"]) if world > 1 else None
         self.rebalances = 0
         self.rebalance_ms = []
+        # (sub-step, global plane histogram) of the last re-plan look; the initial plan IS a look at sub-step 0
+        self.last_look = (0, __import__("numpy").asarray(sc["hist"], dtype="float64")) if world > 1 else None
+        self.caps = [bb.slab_capacity(sc["hist"], sc["z_bounds"], r, slack=2.0)[0] for r in range(world)] if world > 1 else None
 
-    def rebalance(self, target=None):
-        """Slab group: re-plan the z cuts from the current per-plane histogram (bbx_plane_counts summed over the ranks ->
+    def rebalance(self, every=100, gain=0.02):
+        """Slab group: re-plan the z cuts from the per-plane histogram (bbx_plane_counts summed over the ranks ->
         bbx_slab_plan) and move there in neighbour-only steps (bbx_slab_plan_step, bbx_rebalance).  Host-synchronous;
-        returns the wall-clock ms it took on this rank (0 when the plan did not change)."""
+        returns the wall-clock ms it took on this rank.  Policy: look at most once per `every` sub-steps (a look costs
+        ~0.3 ms, a move ~2 ms: one to two sub-steps); plan on the histogram EXTRAPOLATED to the middle of the next
+        interval from the drift since the previous look (a dam break pushes ~10 % of the mass across a cut in 100
+        sub-steps); move only when the fullest slab of the new plan is at least `gain` x the mean lighter than the
+        fullest slab of the current one.  Every decision is a function of the GLOBAL histogram and of the capacities
+        every rank can compute, so all ranks take the same one (bbx_rebalance is collective); a step that would bring a
+        slab within 10 % of its max_particles is not taken."""
         if self.world < 2:
             return 0.0
+        import numpy as np
         import torch
         import torch.distributed as dist
         bb = self.bb
         t0 = time.perf_counter()
-        if target is None:
-            hist = torch.from_numpy(self.eng.plane_counts()).cuda()
-            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
-            target = bb.plan_slabs(hist.cpu().numpy(), self.world)
+        now = int(self.eng.stats().substeps)
+        if self.last_look is not None and now - self.last_look[0] < every:
+            return 0.0
+        hist = torch.from_numpy(self.eng.plane_counts()).cuda()
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        hist = hist.cpu().numpy().astype(np.float64)
+        plan_on = hist
+        if self.last_look is not None and now > self.last_look[0]:
+            drift = (hist - self.last_look[1]) / (now - self.last_look[0])   # particles per plane per sub-step
+            plan_on = np.maximum(hist + drift * (every / 2), 0.0)
+        self.last_look = (now, hist)
+        target = [int(z) for z in bb.plan_slabs(np.rint(plan_on).astype(np.int64), self.world)]
+        owned = lambda zb, h: [float(h[zb[r]:zb[r + 1]].sum()) for r in range(self.world)]
+        if max(owned(self.z_bounds, plan_on)) - max(owned(target, plan_on)) < gain * plan_on.sum() / self.world:
+            target = self.z_bounds
         moved = False
         for _ in range(8):
             if list(target) == self.z_bounds:
                 break
             step, _ = bb.plan_step(self.z_bounds, target)
+            step = [int(z) for z in step]
             if step == self.z_bounds:
                 break
+            if any(max(a, b) > 0.9 * c for a, b, c in zip(owned(step, hist), owned(step, plan_on), self.caps)):
+                break   # (same verdict on every rank)
             self.eng.rebalance(step)
             self.z_bounds = step
             moved = True
@@ -349,10 +373,10 @@ class Job:
         return ms
 
     def reset(self):
-        if self.world > 1:
-            self.rebalance(list(self.sc["z_bounds"]))  # this rank's share of the initial block belongs to the initial slabs
-            self.eng.set_particles_ids(self.sc["pos"], self.sc["vel"], self.sc["ids"])
-        else:
+        """Single domain: back to the initial block.  (Slab groups keep stepping from where they are: a rank only holds
+        its share of the initial block under the INITIAL cuts, and walking the cuts back there in neighbour-only steps can
+        overfill a slab on the way.)"""
+        if self.world == 1:
             self.eng.set_particles(self.sc["pos"], self.sc["vel"])
 
     def close(self):
@@ -505,7 +529,7 @@ def e2e_leg(job, solver, dt, steps, sph):
     hid = torch.zeros(hcap, dtype=torch.int32).pin_memory()
     cnt = C.c_int()
     h2d, d2h = [0], [0]
-    job.reset()  # restart from the initial block so that the e2e run simulates the same thing
+    job.reset()  # single domain: restart from the initial block; slab groups go on from the state they are in
     if world == 1:
         buf["ip"][:len(pos32)] = torch.from_numpy(pos32); buf["iv"][:len(vel32)] = torch.from_numpy(vel32)
         cnt.value = len(pos32)
@@ -570,6 +594,42 @@ def extra_config(name, particles_total, workload, rank, world, local_rank, steps
         job.close()
 
 
+class Deadline:
+    """Safety net of the bbx arm: the headline measurement is taken first and the legs behind it (parity gates, developed
+    flow, e2e, extra configs, CPU baseline) fill further keys of the SAME line.  If the run is still going `seconds` after it
+    started -- a leg slower than planned on this box, or one rank stuck in a collective another rank left with an error --
+    rank 0 prints the line as it stands (missing keys null, "truncated" says why) and every rank exits 0, instead of the
+    whole job dying at the driver's limit with nothing printed."""
+
+    def __init__(self, seconds, rank):
+        import threading
+        self.rank, self.line, self.lock, self.done = rank, None, threading.Lock(), False
+        self.t0 = time.perf_counter()
+        self.timer = threading.Timer(seconds, self._fire, args=(f"deadline of {seconds:.0f} s reached",))
+        self.timer.daemon = True
+        if seconds > 0:
+            self.timer.start()
+
+    def _fire(self, why):
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+            if self.rank == 0 and self.line is not None:
+                self.line["truncated"] = why
+                print(json.dumps(self.line), flush=True)
+        os._exit(0 if (self.rank != 0 or self.line is not None) else 3)
+
+    def fail(self, why):
+        """an error on this rank after the headline was measured: same exit as the deadline"""
+        self._fire(why)
+
+    def finish(self):
+        with self.lock:
+            self.done = True
+        self.timer.cancel()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -588,6 +648,7 @@ def main():
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the additional BASELINE configs (8 M SDF at N = 1, 32 M at N = 2 / 4, 100 M at N = 8)")
     ap.add_argument("--developed-substeps", type=int, default=400, help="second timing after this many sub-steps (splash developed); 0 = skip")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--deadline", type=float, default=780.0, help="seconds after which the line is printed as it stands and every rank exits 0 (0 = off)")
     ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep the static slab plan of the initial distribution (default: re-plan the z cuts at the start of every timed block)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -619,6 +680,7 @@ def main():
     peak, peak_src = peaks()
 
     # ---- device-resident throughput: W warm-up sub-steps, then `repeats` blocks of exactly K sub-steps -------------
+    guard = Deadline(args.deadline, rank)
     eng.step_many(dt, args.warmup, solver)
     eng.synchronize()
     blocks, ms_per_step, wall_ms, launches, clocks = timed_blocks(job, solver, dt, args.steps, args.repeats, local_rank, not args.no_rebalance)
@@ -635,52 +697,10 @@ def main():
         raise SystemExit("non-finite positions during the timed region")
     stats = {"neighbor_overflow": st.neighbor_overflow, "clamped": st.clamped, "rebuild_flag": st.rebuild_flag, "occupied_cells": st.occupied_cells,
              "max_candidates": st.max_candidates, "exact_passes": st.exact_passes, "unstaged_tiles": st.unstaged_tiles, "substeps": st.substeps}
-
-    # ---- parity gate on the benched state (after the clock has stopped) ---------------------------------------------
-    parity = None
-    if not args.no_parity and args.solver == "pcisph":
-        parity = parity_leg(job, dt)
-
-    # ---- the same measurement on a developed flow (splash, spray, compressed cells) ---------------------------------
-    developed = None
-    if args.developed_substeps > 0 and args.solver == "pcisph":
-        todo = args.developed_substeps - eng.stats().substeps
-        while todo > 0:
-            chunk = min(todo, 100)
-            if world > 1 and not args.no_rebalance:
-                job.rebalance()
-            eng.step_many(dt, chunk, solver)
-            eng.synchronize()
-            todo -= chunk
-        dblocks, dms, dwall, _, dclocks = timed_blocks(job, solver, dt, args.steps, 3, local_rank, not args.no_rebalance)
-        dphase, dgap = phase_breakdown(job, solver, dt, args.steps, phase_ids)
-        dst = eng.stats()
-        developed = {"after_substeps": int(args.developed_substeps), "ms_per_step": dms, "ms_per_step_blocks": dblocks, "value": n_global / (dms * 1e-3),
-                     "phases_ms_per_step": {k: v[0] / args.steps for k, v in dphase.items()}, "clocks": dclocks,
-                     "stats": {"exact_passes": dst.exact_passes, "unstaged_tiles": dst.unstaged_tiles, "max_candidates": dst.max_candidates,
-                               "occupied_cells": dst.occupied_cells, "clamped": dst.clamped, "nan_count": dst.nan_count}}
-        if not args.no_parity:
-            developed["parity"] = parity_leg(job, dt)
-
-    # ---- end to end through the C ABI with host buffers ------------------------------------------------------------
-    e2e = e2e_leg(job, solver, dt, args.e2e_steps, args.solver == "sph")
     p2p = bool(eng.p2p) if world > 1 else None
-    rebalances, rebalance_ms = job.rebalances, list(job.rebalance_ms)
-    job.close()
 
-    # ---- the other BASELINE configs this GPU count can hold ----------------------------------------------------------
-    configs = {}
-    if not args.no_extra_configs and args.solver == "pcisph" and args.workload == "dam" and args.particles == 1.0e6:
-        extra = {1: [("sdf8m", 8.0e6, "sdf")], 2: [("dam32m", 32.0e6, "dam")], 4: [("dam32m", 32.0e6, "dam")], 8: [("dam100m", 100.0e6, "dam")]}.get(world, [])
-        for name, total, wl in extra:
-            try:
-                configs[name] = extra_config(name, total, wl, rank, world, local_rank, min(args.steps, 30), 10, peak)
-            except SystemExit:
-                raise
-            except Exception as ex:  # an extra config must never cost the headline line
-                configs[name] = {"workload": name, "failed": str(ex)[-300:]}
-                break
-
+    # ---- the headline line (rank 0); the legs below fill its remaining keys --------------------------------------------
+    line = None
     if rank == 0:
         dom = max(phase, key=lambda k: phase[k][0])
         dom_ms = phase[dom][0] / max(1, phase[dom][1])
@@ -709,10 +729,11 @@ def main():
                                  "(launch gaps included), max over ranks per block; ms_per_step = the MEDIAN block",
                        "ms_per_step_blocks": blocks, "wall_ms_per_step": wall_ms, "host_numa_binding": numa,
                        "rebalance": (None if world == 1 else ("off (static plan)" if args.no_rebalance else
-                                     f"z cuts re-planned at the start of every timed block (bbx_rebalance; {rebalances} moves so far, their host time is inside the blocks)")),
-                       "rebalance_ms_rank0": rebalance_ms},
+                                     "z cuts re-planned at the start of a timed block when >= 100 sub-steps have passed since the last look, on the drift-extrapolated "
+                                     "plane histogram, moved when the fullest slab gets >= 2 % of the mean lighter (bbx_rebalance; host time inside the blocks)")),
+                       "rebalances": job.rebalances, "rebalance_ms_rank0": list(job.rebalance_ms)},
             "clocks": clocks,
-            "e2e": e2e,
+            "e2e": None,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -723,18 +744,76 @@ def main():
                          "limiter": limiter},
             "stats": stats,
             "ranks": per_rank,
-            "parity": parity,
-            "developed": developed,
-            "configs": configs,
+            "parity": None,
+            "developed": None,
+            "configs": {},
+            "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                             "sample": "only measured at N = 1" if world > 1 else "not measured"},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        guard.line = line
+
+    def put(key, val):
+        if line is not None:
+            line[key] = val
+
+    try:
+        # ---- end to end through the C ABI with host buffers (slab groups: from the state the timed region left) -------
+        if world > 1:
+            put("e2e", e2e_leg(job, solver, dt, args.e2e_steps, args.solver == "sph"))
+
+        # ---- parity gate on the benched state (after the clock has stopped) -----------------------------------------
+        if not args.no_parity and args.solver == "pcisph":
+            put("parity", parity_leg(job, dt))
+
+        # ---- the same measurement on a developed flow (splash, spray, compressed cells) -----------------------------
+        if args.developed_substeps > 0 and args.solver == "pcisph":
+            todo = args.developed_substeps - eng.stats().substeps
+            while todo > 0:
+                chunk = min(todo, 100)
+                if world > 1 and not args.no_rebalance:
+                    job.rebalance()
+                eng.step_many(dt, chunk, solver)
+                eng.synchronize()
+                todo -= chunk
+            dblocks, dms, dwall, _, dclocks = timed_blocks(job, solver, dt, args.steps, 3, local_rank, not args.no_rebalance)
+            dphase, dgap = phase_breakdown(job, solver, dt, args.steps, phase_ids)
+            dst = eng.stats()
+            developed = {"after_substeps": int(args.developed_substeps), "ms_per_step": dms, "ms_per_step_blocks": dblocks, "value": n_global / (dms * 1e-3),
+                         "phases_ms_per_step": {k: v[0] / args.steps for k, v in dphase.items()}, "clocks": dclocks,
+                         "stats": {"exact_passes": dst.exact_passes, "unstaged_tiles": dst.unstaged_tiles, "max_candidates": dst.max_candidates,
+                                   "occupied_cells": dst.occupied_cells, "clamped": dst.clamped, "nan_count": dst.nan_count}}
+            put("developed", developed)
+            if not args.no_parity:
+                developed["parity"] = parity_leg(job, dt)
+
+        # ---- single domain: e2e restarts from the initial block, so it runs after the legs that need the flow ---------
+        if world == 1:
+            put("e2e", e2e_leg(job, solver, dt, args.e2e_steps, args.solver == "sph"))
+        if line is not None:
+            line["config"]["rebalances"], line["config"]["rebalance_ms_rank0"] = job.rebalances, list(job.rebalance_ms)
+        job.close()
+
+        # ---- the other BASELINE configs this GPU count can hold ------------------------------------------------------
+        if not args.no_extra_configs and args.solver == "pcisph" and args.workload == "dam" and args.particles == 1.0e6:
+            extra = {1: [("sdf8m", 8.0e6, "sdf")], 2: [("dam32m", 32.0e6, "dam")], 4: [("dam32m", 32.0e6, "dam")], 8: [("dam100m", 100.0e6, "dam")]}.get(world, [])
+            for name, total, wl in extra:
+                res = extra_config(name, total, wl, rank, world, local_rank, min(args.steps, 30), 10, peak)
+                if line is not None:
+                    line["configs"][name] = res
+
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(n)
             line["reference_gpu"] = reference_gpu(n)
             line["reference_gpu"]["note"] = ("extra key, not the reference arm: the unmodified reference in its native GPU mode on this box; the "
                                              "`--impl reference` arm steps the CPU path (use_cpu = 1) and only touches the GPU while the reference's own setup code runs")
-        else:
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
-                                    "sample": "only measured at N = 1"}
+    except (Exception, SystemExit) as ex:  # a leg behind the headline failed on this rank: the line goes out as it stands, everybody leaves
+        import traceback
+        traceback.print_exc()
+        if world > 1:
+            time.sleep(2.0 if rank == 0 else 10.0)  # rank 0 prints first; the others give it that time, then leave too
+        guard.fail(f"rank {rank}: {type(ex).__name__}: {str(ex)[-300:]}")
+    guard.finish()
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1836,7 +1836,16 @@ int bbx_rebalance(bbx_engine *e, const int *z_bounds){
     const int r_lo = e->has_lo ? from_lo[0] : 0, r_hi = e->has_hi ? from_hi[0] : 0;
     if((nz0 >= z0 && r_lo > 0) || (nz1 <= z1 && r_hi > 0)) return set_error(BBX_ERR_INVALID, "the ranks of the slab group disagree about z_bounds");
     const long long n_new = (long long)n_keep + r_lo + r_hi;
-    if(n_new > e->cap) return set_error(BBX_ERR_CAPACITY, "after re-balancing rank %d would own %lld particles, max_particles is %d", rank, n_new, e->cap);
+    {   // a rank that cannot hold its new share must stop EVERY rank before the exchange (agreed like the plan check above:
+        // a lone early return would leave the neighbours waiting in the exchange)
+        unsigned full = n_new > e->cap ? 1u : 0u, any = 0;
+        CU(cudaMemcpyAsync(e->perm, &full, sizeof(unsigned), cudaMemcpyHostToDevice, e->stream));
+        COMM(e->comm->allreduce_max_u32(e->stream, (unsigned *)e->perm, 1));
+        CU(cudaMemcpyAsync(&any, e->perm, sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        if(full) return set_error(BBX_ERR_CAPACITY, "after re-balancing rank %d would own %lld particles, max_particles is %d", rank, n_new, e->cap);
+        if(any) return set_error(BBX_ERR_CAPACITY, "another rank of the slab group cannot hold its share of this plan (its max_particles is too small)");
+    }
     // the new grid of this rank (one ghost plane per neighbour, as at creation)
     const int zoff_new = nz0 - (e->has_lo ? 1 : 0);
     const long long plane = g.plane;
