@@ -30,6 +30,15 @@ compile_one() {
 }
 export -f compile_one; export REF OBJ NVCC FLAGS
 echo "$SRCS" | xargs -P "$JOBS" -I{} bash -c 'compile_one {}'
+# compile check of the reference-side binding against the unmodified reference headers + include/bbx.h
+BIND="$HERE/../bubbles_b200/host/reference_binding/pcisph_solver3_bbx.cpp"
+if [ -f "$BIND" ]; then
+  mkdir -p "$OUT/obj_bbx"
+  if [ ! -f "$OUT/obj_bbx/pcisph_solver3_bbx.o" ] || [ "$BIND" -nt "$OUT/obj_bbx/pcisph_solver3_bbx.o" ] || [ "$HERE/../include/bbx.h" -nt "$OUT/obj_bbx/pcisph_solver3_bbx.o" ]; then
+    $NVCC $FLAGS -I"$HERE/../include" -c "$BIND" -o "$OUT/obj_bbx/pcisph_solver3_bbx.o" || { echo "[build_ref] FAILED reference binding"; exit 1; }
+    echo "[build_ref] reference-side binding compiles against the reference headers"
+  fi
+fi
 # nothing to do when both binaries are newer than the harness source and every reference object
 NEWEST_OBJ=$(ls -t "$OBJ"/*.o 2>/dev/null | grep -v "/_harness.o" | head -1 || true)
 if [ -x "$OUT/bbref" ] && [ -x "$OUT/bbref_gpu" ] && [ "$OUT/bbref" -nt "$HERE/ref_harness.cpp" ] && [ "$OUT/bbref_gpu" -nt "$HERE/ref_harness.cpp" ] \

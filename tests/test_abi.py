@@ -82,3 +82,22 @@ def test_python_emitter_glibc_mode_reproduces_the_reference_emitter():
     em.Emit(b)
     assert b.GetParticleCount() == len(g["s0_pos"])
     assert np.array_equal(b.positions, g["s0_pos"]) and np.array_equal(b.velocities, g["s0_vel"])
+
+
+def test_reference_side_binding_compiles_against_the_reference_headers():
+    """INTEGRATION.md 2: bubbles_b200/host/reference_binding/pcisph_solver3_bbx.cpp (PciSphSolver3::Setup / SetColliders /
+    Advance re-routed through the C ABI) is compiled by oracle/build_ref.sh against the unmodified reference headers and
+    include/bbx.h; the object must exist, be newer than both sources and define the reference's member functions."""
+    import subprocess
+    src = os.path.join(ROOT, "bubbles_b200", "host", "reference_binding", "pcisph_solver3_bbx.cpp")
+    obj = os.path.join(ROOT, "oracle", "_ref", "obj_bbx", "pcisph_solver3_bbx.o")
+    if not os.path.isdir("/root/reference/src") and not os.path.exists(obj):
+        pytest.skip("reference sources not present and no prebuilt object")
+    if os.path.isdir("/root/reference/src"):
+        subprocess.check_call([os.path.join(ROOT, "oracle", "build_ref.sh")], cwd=ROOT)
+        assert os.path.getmtime(obj) >= os.path.getmtime(src) and os.path.getmtime(obj) >= os.path.getmtime(os.path.join(ROOT, "include", "bbx.h"))
+    syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
+    for want in ("PciSphSolver3::Setup(", "PciSphSolver3::SetColliders(", "PciSphSolver3::Advance(", "PciSphSolver3::SetViscosityCoefficient("):
+        assert any(want in l and " T " in l for l in syms.splitlines()), want
+    for used in ("bbx_create", "bbx_set_particles", "bbx_set_colliders", "bbx_advance", "bbx_download", "bbx_update_collider"):
+        assert any(l.strip().endswith(used) and " U " in l for l in syms.splitlines()), used
