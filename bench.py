@@ -658,6 +658,7 @@ def main():
         run_reference(args, rank)
         return
     args.warmup = max(args.warmup, 3)
+    guard = Deadline(args.deadline, rank)   # (counts from here: imports, scene generation and engine set-up included)
 
     import torch
     import torch.distributed as dist
@@ -680,7 +681,6 @@ def main():
     peak, peak_src = peaks()
 
     # ---- device-resident throughput: W warm-up sub-steps, then `repeats` blocks of exactly K sub-steps -------------
-    guard = Deadline(args.deadline, rank)
     eng.step_many(dt, args.warmup, solver)
     eng.synchronize()
     blocks, ms_per_step, wall_ms, launches, clocks = timed_blocks(job, solver, dt, args.steps, args.repeats, local_rank, not args.no_rebalance)
@@ -752,9 +752,10 @@ def main():
         }
         guard.line = line
 
-    def put(key, val):
+    def put(key, val, sub=None):
         if line is not None:
-            line[key] = val
+            with guard.lock:   # (the deadline thread serialises the line under the same lock)
+                (line if sub is None else line[sub])[key] = val
 
     try:
         # ---- end to end through the C ABI with host buffers (slab groups: from the state the timed region left) -------
@@ -784,28 +785,26 @@ def main():
                                    "occupied_cells": dst.occupied_cells, "clamped": dst.clamped, "nan_count": dst.nan_count}}
             put("developed", developed)
             if not args.no_parity:
-                developed["parity"] = parity_leg(job, dt)
+                put("parity", parity_leg(job, dt), "developed")
 
         # ---- single domain: e2e restarts from the initial block, so it runs after the legs that need the flow ---------
         if world == 1:
             put("e2e", e2e_leg(job, solver, dt, args.e2e_steps, args.solver == "sph"))
-        if line is not None:
-            line["config"]["rebalances"], line["config"]["rebalance_ms_rank0"] = job.rebalances, list(job.rebalance_ms)
+        put("rebalances", job.rebalances, "config"); put("rebalance_ms_rank0", list(job.rebalance_ms), "config")
         job.close()
 
         # ---- the other BASELINE configs this GPU count can hold ------------------------------------------------------
         if not args.no_extra_configs and args.solver == "pcisph" and args.workload == "dam" and args.particles == 1.0e6:
             extra = {1: [("sdf8m", 8.0e6, "sdf")], 2: [("dam32m", 32.0e6, "dam")], 4: [("dam32m", 32.0e6, "dam")], 8: [("dam100m", 100.0e6, "dam")]}.get(world, [])
             for name, total, wl in extra:
-                res = extra_config(name, total, wl, rank, world, local_rank, min(args.steps, 30), 10, peak)
-                if line is not None:
-                    line["configs"][name] = res
+                put(name, extra_config(name, total, wl, rank, world, local_rank, min(args.steps, 30), 10, peak), "configs")
 
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(n)
-            line["reference_gpu"] = reference_gpu(n)
-            line["reference_gpu"]["note"] = ("extra key, not the reference arm: the unmodified reference in its native GPU mode on this box; the "
-                                             "`--impl reference` arm steps the CPU path (use_cpu = 1) and only touches the GPU while the reference's own setup code runs")
+            put("cpu_baseline", cpu_baseline(n))
+            rg = reference_gpu(n)
+            rg["note"] = ("extra key, not the reference arm: the unmodified reference in its native GPU mode on this box; the "
+                          "`--impl reference` arm steps the CPU path (use_cpu = 1) and only touches the GPU while the reference's own setup code runs")
+            put("reference_gpu", rg)
     except (Exception, SystemExit) as ex:  # a leg behind the headline failed on this rank: the line goes out as it stands, everybody leaves
         import traceback
         traceback.print_exc()
