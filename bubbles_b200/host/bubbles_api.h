@@ -14,6 +14,8 @@
 //   core/util.cpp:269            UtilBuildGridForDomain
 //   third/serializer.h:36        SerializerSaveSphDataSet3 (text frames bbtool reads), SERIALIZER_* flags
 //   core/pcisph_solver.h:95      PciSphRunSimulation3 (the run loop, without the viewer)
+//   core/transform_sequence.h    TransformSequence, QuaternionSequence, InterpolatedTransform, Quaternion (transform_sequence.h here)
+//   core/shape.cpp:290-298       Shape::Update / SetVelocities + PciSphSolver3::UpdateCollider (hands the change to the engine)
 //
 // Differences by design: objects are ordinary C++ values / unique_ptrs (the reference bump-allocates from a
 // managed-memory arena and never frees, src/cuda/memory.h); errors throw bbx::Error instead of
@@ -29,6 +31,7 @@
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <limits>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -92,6 +95,9 @@ inline Transform Translate(const vec3f &v){ return Translate(v.x, v.y, v.z); }
 inline Transform Scale(Float x, Float y, Float z){
     Transform t; t.m[0][0] = x; t.m[1][1] = y; t.m[2][2] = z; t.mInv[0][0] = 1 / x; t.mInv[1][1] = 1 / y; t.mInv[2][2] = 1 / z; return t;
 }
+// Transform products, Rotate, Quaternion, InterpolatedTransform, TransformSequence, QuaternionSequence (keyframed collider
+// motion; src/core/transform_sequence.h, quaternion.h)
+#include "transform_sequence.h"
 
 // ------------------------------------------------------------------------------------------ shapes
 enum ShapeType { ShapeSphere = BBX_COLLIDER_SPHERE, ShapeBox = BBX_COLLIDER_BOX, ShapeSDF = BBX_COLLIDER_SDF };
@@ -102,6 +108,10 @@ struct Shape {
     bool reverseOrientation = false;
     Float radius = 0, sizex = 0, sizey = 0, sizez = 0;
     vec3f linearVelocity, angularVelocity;
+    // Shape::Update / SetVelocities (src/core/shape.cpp:290-298): a scene script moves the collider between frames (e.g. with a
+    // TransformSequence); PciSphSolver3::UpdateCollider hands the new state to the engine
+    void Update(const Transform &toWorld){ ObjectToWorld = toWorld; }
+    void SetVelocities(const vec3f &vel, const vec3f &angular){ linearVelocity = vel; angularVelocity = angular; }
     // baked SDF (FieldGrid3f, vertex centred): node counts, spacing, position of node (0, 0, 0), x-fastest values
     int sdfResolution[3] = {0, 0, 0};
     Float sdfSpacing = 0;
@@ -494,6 +504,14 @@ class SolverBase3 {
         Check(bbx_set_colliders(engine, (int)abi.size(), abi.data()));
     }
     std::shared_ptr<ColliderSet3> GetColliders(){ return data->collider; }
+    // after Shape::Update / SetVelocities / ColliderSet3::SetActive on collider `which` (the reference's kernels read the
+    // managed-memory Shape live; here the change is handed over explicitly): bbx_update_collider + bbx_set_collider_active
+    void UpdateCollider(int which){
+        if(!engine || !data->collider) return;
+        std::vector<bbx_collider> abi = data->collider->ToABI();
+        Check(bbx_update_collider(engine, which, &abi.at((size_t)which)));
+        Check(bbx_set_collider_active(engine, which, abi[(size_t)which].active));
+    }
     // the reference reads SphSolverData3 live every sub-step: setters called after Setup() reach the engine too
     void SetParam(int param, double value){ if(engine) Check(bbx_set_param(engine, param, value)); }
     void SetViscosityCoefficient(Float v){ data->cfg.viscosity = v > 0 ? v : 0; SetParam(BBX_PARAM_VISCOSITY, data->cfg.viscosity); }

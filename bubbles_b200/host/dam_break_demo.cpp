@@ -3,7 +3,7 @@
 // (MakeBox / VolumeParticleEmitter3 / UtilBuildGridForDomain / ColliderSetBuilder3 / PciSphSolver3 /
 // SerializerSaveSphDataSet3 / PciSphRunSimulation3), host code only -- every kernel runs inside libbbx.so.
 //
-//   dam_break_demo [--scaling S] [--frames N] [--steps N --dt X] [--jitter J] [--out DIR] [--dump FILE] [--sph] [--emit K] [--map-emit] [--load FRAME]
+//   dam_break_demo [--scaling S] [--frames N] [--steps N --dt X] [--jitter J] [--out DIR] [--dump FILE] [--sph] [--emit K] [--map-emit] [--load FRAME] [--keyframes]
 //     --scaling  domainScaling of the reference scene (2.5 there: ~0.9 M particles; default 0.6: ~12 k)
 //     --frames   frames of 1/240 s through Advance() (CFL sub-stepping), default 2
 //     --steps    instead of frames: N fixed-dt sub-steps (AdvanceTimeStep)
@@ -15,6 +15,9 @@
 //                test runs on the device (bbx_query_cells)
 //     --load     start from a frame file (positions and, when present, velocities: SerializerLoadSphDataSet3) instead of
 //                emitting the block, e.g. the reference's resources/dam_break_50
+//     --keyframes a sphere obstacle on the floor driven by a TransformSequence (three keyframes + AddRestore), updated every
+//                frame with Shape::Update / SetVelocities exactly as the reference's moving-container scene does
+//                (src/tests/test_pcisph3.cpp:82-136), handed to the engine by PciSphSolver3::UpdateCollider
 //     --dump     raw little-endian doubles: n, then n x 3 positions, n x 3 velocities (for the parity test)
 #include <cstdio>
 #include <cstdlib>
@@ -27,7 +30,7 @@ using namespace bbx;
 
 int main(int argc, char **argv){
     Float domainScaling = 0.6f, jitter = 0.001, dt = 0;
-    int frames = 2, steps = 0, emit = 0; bool sph = false, mapEmit = false;
+    int frames = 2, steps = 0, emit = 0; bool sph = false, mapEmit = false, keyframes = false;
     std::string out, dump, load;
     for(int i = 1; i < argc; i++){
         std::string a = argv[i];
@@ -43,6 +46,7 @@ int main(int argc, char **argv){
         else if(a == "--emit") emit = std::atoi(next().c_str());
         else if(a == "--map-emit") mapEmit = true;
         else if(a == "--load") load = next();
+        else if(a == "--keyframes") keyframes = true;
         else{ std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try{
@@ -78,6 +82,18 @@ int main(int argc, char **argv){
         auto domainGrid = UtilBuildGridForDomain(container->GetBounds(), spacing, spacingScale);
         ColliderSetBuilder3 cBuilder;
         cBuilder.AddCollider3(container);
+        // --keyframes: a sphere that slides across the floor and back (collider 1)
+        const Float ballR = 0.12 * domainScaling;
+        const vec3f ballA(-0.3 * boxLen, -0.5 * boxYLen + ballR, -0.3 * boxLen), ballB(0.3 * boxLen, -0.5 * boxYLen + ballR, 0.1 * boxLen);
+        ShapePtr ball = MakeSphere(Translate(ballA), ballR);
+        TransformSequence sequence;
+        if(keyframes){
+            cBuilder.AddCollider3(ball, 0.1);
+            Transform k0 = Translate(ballA), k1 = Translate(ballB) * Rotate(180, vec3f(0, 1, 0)), k2 = Translate(vec3f(ballB.x, ballB.y, ballA.z)) * Rotate(270, vec3f(0, 1, 0));
+            sequence.AddInterpolation(&k0, &k1, 0, 1);
+            sequence.AddInterpolation(&k1, &k2, 1, 2);
+            sequence.AddRestore(2, 3);
+        }
         auto colliders = cBuilder.GetColliderSet();
 
         auto sphSet = SphParticleSet3FromContinuousBuilder(&pBuilder);
@@ -110,6 +126,17 @@ int main(int argc, char **argv){
                     if(step == 0){ save(0); return 1; }
                     std::printf("Step (%d) : %g ms - Particles %d\n", step - 1, solver.GetAdvanceTime(), solver.GetParticleCount());
                     save(step);
+                    if(keyframes){
+                        // one loop of the sequence every 120 frames; velocities = displacement / rotation since the last frame over
+                        // the frame time (test_pcisph3.cpp:124-134)
+                        const int loop = 120;
+                        Float f = 3 * ((Float)(step % loop)) / (Float)loop;
+                        Transform transform; vec3f linear, angular;
+                        sequence.Interpolate(f, &transform, &linear, &angular);
+                        ball->Update(transform);
+                        ball->SetVelocities(linear * (1.0 / targetInterval), angular * (1.0 / targetInterval));
+                        solver.UpdateCollider(1);
+                    }
                     if(emit && step < frames){
                         // a sheet of K particles one spacing apart, dropped from above the block
                         int side = 1; while(side * side < emit) side++;

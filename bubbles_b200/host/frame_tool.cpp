@@ -81,7 +81,46 @@ static int mapemit_mode(const char *in, const char *out){
     return 0;
 }
 
+// frame_tool --tseq <job.txt> <out.bin>: the facade's TransformSequence / QuaternionSequence driven by the same job lines
+//   the reference harness takes (tseq_add, tseq_restore, tseq_eval, qseq_add, qseq_eval; the eval prefix argument is ignored).
+//   out.bin, per eval command in order: int64 n, double m[16 n], minv[16 n], linear[3 n], angular[3 n]
+static int tseq_mode(const char *job, const char *out){
+    std::ifstream in(job);
+    if(!in) return 1;
+    FILE *fp = std::fopen(out, "wb");
+    if(!fp) return 1;
+    bbx::TransformSequence tseq; bbx::QuaternionSequence qseq;
+    std::string cmd;
+    while(in >> cmd){
+        if(cmd == "tseq_add"){
+            double a[16]; for(int k = 0; k < 16; k++) in >> a[k];
+            double s0, s1; in >> s0 >> s1;
+            bbx::Transform k0 = bbx::Translate(bbx::vec3f(a[0], a[1], a[2])) * bbx::Rotate(a[3], bbx::vec3f(a[4], a[5], a[6])) * bbx::Scale(a[7]);
+            bbx::Transform k1 = bbx::Translate(bbx::vec3f(a[8], a[9], a[10])) * bbx::Rotate(a[11], bbx::vec3f(a[12], a[13], a[14])) * bbx::Scale(a[15]);
+            tseq.AddInterpolation(&k0, &k1, s0, s1);
+        }else if(cmd == "tseq_restore"){ double s0, s1; in >> s0 >> s1; tseq.AddRestore(s0, s1); }
+        else if(cmd == "qseq_add"){ double ang, x, y, z, t; in >> ang >> x >> y >> z >> t; qseq.AddQuaternion(ang, bbx::vec3f(x, y, z), t); }
+        else if(cmd == "tseq_eval" || cmd == "qseq_eval"){
+            double t0, dt; int64_t n; std::string prefix; in >> t0 >> dt >> n >> prefix;
+            std::vector<double> m(16 * (size_t)n), mi(16 * (size_t)n), lin(3 * (size_t)n), ang(3 * (size_t)n);
+            for(int64_t i = 0; i < n; i++){
+                bbx::Transform tr; bbx::vec3f l(0.0), w(0.0);
+                if(cmd == "tseq_eval") tseq.Interpolate(t0 + i * dt, &tr, &l, &w);
+                else qseq.Interpolate(t0 + i * dt, &tr, &w);
+                for(int r = 0; r < 4; r++) for(int c = 0; c < 4; c++){ m[16 * (size_t)i + 4 * r + c] = tr.m[r][c]; mi[16 * (size_t)i + 4 * r + c] = tr.mInv[r][c]; }
+                for(int k = 0; k < 3; k++){ lin[3 * (size_t)i + k] = l[k]; ang[3 * (size_t)i + k] = w[k]; }
+            }
+            std::fwrite(&n, 8, 1, fp);
+            std::fwrite(m.data(), 8, m.size(), fp); std::fwrite(mi.data(), 8, mi.size(), fp);
+            std::fwrite(lin.data(), 8, lin.size(), fp); std::fwrite(ang.data(), 8, ang.size(), fp);
+        }else{ std::fprintf(stderr, "unknown command %s\n", cmd.c_str()); std::fclose(fp); return 2; }
+    }
+    std::fclose(fp);
+    return 0;
+}
+
 int main(int argc, char **argv){
+    if(argc == 4 && std::string(argv[1]) == "--tseq") return tseq_mode(argv[2], argv[3]);
     if(argc == 4 && std::string(argv[1]) == "--load") return load_mode(argv[2], argv[3]);
     if(argc == 4 && std::string(argv[1]) == "--mapemit") return mapemit_mode(argv[2], argv[3]);
     if(argc >= 2 && std::string(argv[1]) == "--emit") return emit_mode(argc, argv);

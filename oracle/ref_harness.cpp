@@ -30,6 +30,7 @@
 #include <grid.h>
 #include <util.h>
 #include <memory.h>
+#include <transform_sequence.h>
 
 // BBREF_GPU: the same driver for the reference's GPU path (its native mode): the reference's own managed-memory
 // arena (src/cuda/memory.cpp) is linked instead of the shim, the system stays in GPU mode and every kernel of the
@@ -101,6 +102,8 @@ struct Harness{
     bool hasDomain = false;
     std::vector<Shape *> shapes;
     std::vector<Float> frictions;
+    TransformSequence tseq;          // `tseq_add` / `tseq_restore` / `tseq_eval`
+    QuaternionSequence qseq;         // `qseq_add` / `qseq_eval`
     ParticleSetBuilder3 builder;
     ContinuousParticleSetBuilder3 *cbuilder = nullptr; // `continuous <max>`: reserve room so that `append` can add particles between steps
     Grid3 *grid = nullptr;
@@ -569,6 +572,38 @@ int main(int argc, char **argv){
             int idx; in >> idx; FieldGrid3f *g = H.shapes[idx]->grid;
             printf("[bbref] sdf res=%u %u %u spacing=%.17g origin=%.17g %.17g %.17g\n", g->resolution.x,
                    g->resolution.y, g->resolution.z, g->spacing.x, g->minPoint.x, g->minPoint.y, g->minPoint.z);
+        }
+        else if(cmd == "tseq_add"){
+            // TransformSequence::AddInterpolation(&K0, &K1, s0, s1) (src/core/transform_sequence.cpp:30-47) between two
+            // keyframes K = Translate(t) * Rotate(angle [deg], axis) * Scale(s)
+            Float a[16]; for(int k = 0; k < 16; k++) in >> a[k];
+            Float s0, s1; in >> s0 >> s1;
+            Transform k0 = Translate(vec3f(a[0], a[1], a[2])) * Rotate(a[3], vec3f(a[4], a[5], a[6])) * Scale(a[7]);
+            Transform k1 = Translate(vec3f(a[8], a[9], a[10])) * Rotate(a[11], vec3f(a[12], a[13], a[14])) * Scale(a[15]);
+            H.tseq.AddInterpolation(&k0, &k1, s0, s1);
+        }
+        else if(cmd == "tseq_restore"){ Float s0, s1; in >> s0 >> s1; H.tseq.AddRestore(s0, s1); }
+        else if(cmd == "tseq_eval" || cmd == "qseq_eval"){
+            // Interpolate(t, &transform, &linear, &angular) at t = t0 + i dt, i < n, in call order (the sequence remembers
+            // its last result: transform_sequence.cpp:103-160)
+            Float t0, dt; int n; std::string prefix; in >> t0 >> dt >> n >> prefix;
+            std::vector<double> m(16 * (size_t)n), mi(16 * (size_t)n), lin(3 * (size_t)n), ang(3 * (size_t)n);
+            for(int i = 0; i < n; i++){
+                Transform tr; vec3f l(0), w(0);
+                if(cmd == "tseq_eval") H.tseq.Interpolate(t0 + i * dt, &tr, &l, &w);
+                else H.qseq.Interpolate(t0 + i * dt, &tr, &w);
+                for(int r = 0; r < 4; r++) for(int c = 0; c < 4; c++){ m[16 * (size_t)i + 4 * r + c] = tr.m.m[r][c]; mi[16 * (size_t)i + 4 * r + c] = tr.mInv.m[r][c]; }
+                for(int k = 0; k < 3; k++){ lin[3 * (size_t)i + k] = l[k]; ang[3 * (size_t)i + k] = w[k]; }
+            }
+            WriteNpy<double>(prefix + "m.npy", m.data(), n, 16);
+            WriteNpy<double>(prefix + "minv.npy", mi.data(), n, 16);
+            WriteNpy<double>(prefix + "linear.npy", lin.data(), n, 3);
+            WriteNpy<double>(prefix + "angular.npy", ang.data(), n, 3);
+        }
+        else if(cmd == "qseq_add"){
+            // QuaternionSequence::AddQuaternion(angle [deg], axis, t) (transform_sequence.cpp:170-177)
+            Float ang, x, y, z, t; in >> ang >> x >> y >> z >> t;
+            H.qseq.AddQuaternion(ang, vec3f(x, y, z), t);
         }
         else{ fprintf(stderr, "unknown command: %s\n", cmd.c_str()); return 2; }
     }

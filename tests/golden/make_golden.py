@@ -301,8 +301,37 @@ def grid_facts():
     print("grid_facts", len(rows))
 
 
+TSEQ_JOB = [  # keyframes K = Translate(t) * Rotate(angle [deg], axis) * Scale(s): t angle axis s | t angle axis s | s0 s1
+    "tseq_add 0 0 0 0 0 1 0 1   0.3 0.1 -0.2 0 0 1 0 1   0 1",                      # pure translation
+    "tseq_add 0.3 0.1 -0.2 0 0 1 0 1   0.3 0.1 -0.2 170 1 1 0 1   1 2",             # rotation up to 170 deg about (1, 1, 0)
+    "tseq_add 0.3 0.1 -0.2 170 1 1 0 1   0.5 0.4 0.0 350 1 1 0 1.5   2 3.5",        # through 180 deg (trace <= 0, quaternion flip) while scaling
+    "tseq_add 0.5 0.4 0.0 350 1 1 0 1.5   -0.2 0.0 0.1 20 0.3 -1 0.5 0.75   3.5 4",  # new axis, shrink
+    "tseq_restore 4 5",
+    "tseq_eval -0.25 0.0625 90 {wd}/t_",
+    "qseq_add 0 0 0 1 0", "qseq_add 120 0 1 1 1", "qseq_add 300 1 0 0 2", "qseq_add 181 0.2 0.3 -1 2.75",
+    "qseq_eval -0.5 0.125 32 {wd}/q_",
+]
+
+
+def transform_sequence():
+    """TransformSequence / QuaternionSequence of the unmodified reference (src/core/transform_sequence.cpp) on a keyframe
+    script: interpolated matrices, their inverses, and the linear / angular velocities it reports call by call."""
+    wd = tempfile.mkdtemp(prefix="bbref_")
+    O.run_ref([l.format(wd=wd) for l in TSEQ_JOB], wd)
+    data = {}
+    for pre in ("t_", "q_"):
+        data.update({pre + k: v for k, v in load_all(wd, pre, ["m", "minv", "linear", "angular"]).items()})
+    data["job"] = np.array(TSEQ_JOB)
+    np.savez_compressed(os.path.join(HERE, "transform_sequence.npz"), **data)
+    print("transform_sequence", data["t_m"].shape, data["q_m"].shape)
+
+
 if __name__ == "__main__":
     assert O.ref_available(), "run oracle/build_ref.sh first"
+    if "--only-transform-sequence" in sys.argv:
+        transform_sequence()
+        sys.exit(0)
+    transform_sequence()
     probe_trace()
     sph_run()
     mesh_collider()
