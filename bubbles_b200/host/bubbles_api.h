@@ -9,7 +9,7 @@
 //   solvers/sph_solver3.cpp:124  DefaultSphSolverData3     DefaultSphSolverData3
 //   core/particle.h:611-720      ParticleSetBuilder3, SphParticleSet3FromBuilder
 //   core/emitter.h:39-128        VolumeParticleEmitter3, VolumeParticleEmitterSet3
-//   core/shape.h:273-286         MakeBox, MakeSphere, MakeSDFShape
+//   core/shape.h:273-286         MakeBox, MakeSphere, MakeSDFShape; MakeMesh + GenerateShapeSDF (mesh_sdf.h here)
 //   core/collider.h:113-122      ColliderSetBuilder3
 //   core/util.cpp:269            UtilBuildGridForDomain
 //   third/serializer.h:36        SerializerSaveSphDataSet3 (text frames bbtool reads), SERIALIZER_* flags
@@ -100,7 +100,7 @@ inline Transform Scale(Float x, Float y, Float z){
 #include "transform_sequence.h"
 
 // ------------------------------------------------------------------------------------------ shapes
-enum ShapeType { ShapeSphere = BBX_COLLIDER_SPHERE, ShapeBox = BBX_COLLIDER_BOX, ShapeSDF = BBX_COLLIDER_SDF };
+enum ShapeType { ShapeSphere = BBX_COLLIDER_SPHERE, ShapeBox = BBX_COLLIDER_BOX, ShapeSDF = BBX_COLLIDER_SDF, ShapeMesh = BBX_COLLIDER_MESH };
 
 struct Shape {
     ShapeType type = ShapeBox;
@@ -118,9 +118,14 @@ struct Shape {
     vec3f sdfOrigin;
     std::vector<Float> sdfField;
     Bounds3f sdfBounds;
+    // triangle mesh (ShapeMesh; world space): vertices, 3 vertex indices per triangle, bounds (mesh_sdf.h)
+    std::vector<vec3f> meshPoints;
+    std::vector<int> meshIndices;
+    Bounds3f meshBounds;
 
     Bounds3f GetBounds() const {
         if(type == ShapeSDF) return sdfBounds;
+        if(type == ShapeMesh) return meshBounds;
         vec3f h = type == ShapeSphere ? vec3f(radius) : vec3f(sizex / 2, sizey / 2, sizez / 2);
         // transformed corners (Transform::operator()(Bounds3f))
         Bounds3f b(ObjectToWorld.Point(vec3f(-h.x, -h.y, -h.z)), ObjectToWorld.Point(vec3f(-h.x, -h.y, -h.z)));
@@ -206,6 +211,9 @@ inline ShapePtr MakeSDFShape(const Bounds3f &bounds, const std::function<Float(v
     return s;
 }
 
+// mesh colliders: MakeMesh, DistanceTriangle, MeshClosestDistance, MeshIsPointInside, GenerateShapeSDF
+#include "mesh_sdf.h"
+
 // --------------------------------------------------------------------------------------- colliders
 struct ColliderSet3 {
     std::vector<ShapePtr> shapes;
@@ -213,6 +221,8 @@ struct ColliderSet3 {
     std::vector<bool> active;
     int nColiders() const { return (int)shapes.size(); }
     void SetActive(int which, bool on){ active.at(which) = on; }
+    // ColliderSet3::GenerateSDFs -> Collider3::GenerateSDFs -> GenerateShapeSDF (src/core/collider.cpp:146-149, 238-264): bake the grid of every mesh collider that has none yet
+    void GenerateSDFs(Float dx = 0.01, Float margin = 0.1){ for(auto &s : shapes) if(s->type == ShapeMesh && s->sdfField.empty()) GenerateShapeSDF(s.get(), dx, margin); }
     std::vector<bbx_collider> ToABI() const {
         std::vector<bbx_collider> out(shapes.size());
         for(size_t i = 0; i < shapes.size(); i++){
@@ -222,7 +232,13 @@ struct ColliderSet3 {
             for(int r = 0; r < 4; r++) for(int c = 0; c < 4; c++){ b.object_to_world[4 * r + c] = s.ObjectToWorld.m[r][c]; b.world_to_object[4 * r + c] = s.ObjectToWorld.mInv[r][c]; }
             b.size[0] = s.sizex; b.size[1] = s.sizey; b.size[2] = s.sizez; b.radius = s.radius;
             for(int k = 0; k < 3; k++){ b.linear_velocity[k] = s.linearVelocity[k]; b.angular_velocity[k] = s.angularVelocity[k]; }
-            if(s.type == ShapeSDF){
+            if(s.type == ShapeMesh){   // the triangles pick the nearest collider, the baked grid answers the rest (GenerateSDFs first)
+                if(s.sdfField.empty()) throw std::invalid_argument("mesh collider without its SDF grid: call ColliderSet3::GenerateSDFs / GenerateShapeSDF first");
+                static_assert(sizeof(vec3f) == 3 * sizeof(double), "vec3f must be three packed doubles");
+                b.mesh_vertices = (int)s.meshPoints.size(); b.mesh_triangles = (int)(s.meshIndices.size() / 3);
+                b.mesh_points = reinterpret_cast<const double *>(s.meshPoints.data()); b.mesh_indices = s.meshIndices.data();
+            }
+            if(s.type == ShapeSDF || s.type == ShapeMesh){
                 for(int k = 0; k < 3; k++){ b.sdf_resolution[k] = s.sdfResolution[k]; b.sdf_spacing[k] = s.sdfSpacing; b.sdf_origin[k] = s.sdfOrigin[k]; }
                 b.sdf_field = s.sdfField.data();
             }

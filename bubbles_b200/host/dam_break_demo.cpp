@@ -3,7 +3,7 @@
 // (MakeBox / VolumeParticleEmitter3 / UtilBuildGridForDomain / ColliderSetBuilder3 / PciSphSolver3 /
 // SerializerSaveSphDataSet3 / PciSphRunSimulation3), host code only -- every kernel runs inside libbbx.so.
 //
-//   dam_break_demo [--scaling S] [--frames N] [--steps N --dt X] [--jitter J] [--out DIR] [--dump FILE] [--sph] [--emit K] [--map-emit] [--load FRAME] [--keyframes]
+//   dam_break_demo [--scaling S] [--frames N] [--steps N --dt X] [--jitter J] [--out DIR] [--dump FILE] [--sph] [--emit K] [--map-emit] [--load FRAME] [--keyframes] [--mesh]
 //     --scaling  domainScaling of the reference scene (2.5 there: ~0.9 M particles; default 0.6: ~12 k)
 //     --frames   frames of 1/240 s through Advance() (CFL sub-stepping), default 2
 //     --steps    instead of frames: N fixed-dt sub-steps (AdvanceTimeStep)
@@ -18,6 +18,8 @@
 //     --keyframes a sphere obstacle on the floor driven by a TransformSequence (three keyframes + AddRestore), updated every
 //                frame with Shape::Update / SetVelocities exactly as the reference's moving-container scene does
 //                (src/tests/test_pcisph3.cpp:82-136), handed to the engine by PciSphSolver3::UpdateCollider
+//     --mesh     a triangle-mesh obstacle (an octahedron standing on the floor in the path of the flow): MakeMesh +
+//                ColliderSet3::GenerateSDFs (host bake, mesh_sdf.h) -> BBX_COLLIDER_MESH
 //     --dump     raw little-endian doubles: n, then n x 3 positions, n x 3 velocities (for the parity test)
 #include <cstdio>
 #include <cstdlib>
@@ -30,7 +32,7 @@ using namespace bbx;
 
 int main(int argc, char **argv){
     Float domainScaling = 0.6f, jitter = 0.001, dt = 0;
-    int frames = 2, steps = 0, emit = 0; bool sph = false, mapEmit = false, keyframes = false;
+    int frames = 2, steps = 0, emit = 0; bool sph = false, mapEmit = false, keyframes = false, meshObstacle = false;
     std::string out, dump, load;
     for(int i = 1; i < argc; i++){
         std::string a = argv[i];
@@ -47,6 +49,7 @@ int main(int argc, char **argv){
         else if(a == "--map-emit") mapEmit = true;
         else if(a == "--load") load = next();
         else if(a == "--keyframes") keyframes = true;
+        else if(a == "--mesh") meshObstacle = true;
         else{ std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try{
@@ -94,7 +97,14 @@ int main(int argc, char **argv){
             sequence.AddInterpolation(&k1, &k2, 1, 2);
             sequence.AddRestore(2, 3);
         }
+        if(meshObstacle){
+            const Float r = 0.15 * domainScaling; const vec3f c(-0.15 * boxLen, -0.5 * boxYLen + r, 0.15 * boxLen);
+            std::vector<vec3f> pts = {c + vec3f(r, 0, 0), c + vec3f(-r, 0, 0), c + vec3f(0, r, 0), c + vec3f(0, -r, 0), c + vec3f(0, 0, r), c + vec3f(0, 0, -r)};
+            std::vector<int> tri = {0, 2, 4, 2, 1, 4, 1, 3, 4, 3, 0, 4, 2, 0, 5, 1, 2, 5, 3, 1, 5, 0, 3, 5};
+            cBuilder.AddCollider3(MakeMesh(pts, tri), 0.0);
+        }
         auto colliders = cBuilder.GetColliderSet();
+        colliders->GenerateSDFs();   // (bakes the grid of mesh colliders; nothing to do for the others)
 
         auto sphSet = SphParticleSet3FromContinuousBuilder(&pBuilder);
         if(!emit && !mapEmit) sphSet->reservedSize = 0;  // no emission: size the engine for the block alone

@@ -119,7 +119,40 @@ static int tseq_mode(const char *job, const char *out){
     return 0;
 }
 
+// frame_tool --bake <mesh.bin> <out.bin> dx margin [n_queries q.bin]: the facade's MakeMesh + GenerateShapeSDF.
+//   mesh.bin: int64 nv, nt; double points[3 nv]; int32 triangles[3 nt]
+//   out.bin: int64 res[3]; double spacing, origin[3], bounds[6]; double field[res0 res1 res2]
+//   optional q.bin (int64 n, double p[3n]) -> appended: double distance[n] (MeshClosestDistance)
+static int bake_mode(int argc, char **argv){
+    if(argc != 6 && argc != 7) return 2;
+    FILE *fp = std::fopen(argv[2], "rb");
+    if(!fp) return 1;
+    int64_t nv = 0, nt = 0; size_t r = std::fread(&nv, 8, 1, fp) + std::fread(&nt, 8, 1, fp);
+    std::vector<bbx::vec3f> pts((size_t)nv); std::vector<int> tri(3 * (size_t)nt);
+    r += std::fread(pts.data(), sizeof(bbx::vec3f), pts.size(), fp) + std::fread(tri.data(), 4, tri.size(), fp);
+    std::fclose(fp); (void)r;
+    bbx::ShapePtr s = bbx::MakeMesh(pts, tri);
+    bbx::GenerateShapeSDF(s.get(), std::atof(argv[4]), std::atof(argv[5]));
+    fp = std::fopen(argv[3], "wb");
+    if(!fp) return 1;
+    int64_t res[3] = {s->sdfResolution[0], s->sdfResolution[1], s->sdfResolution[2]};
+    bbx::Bounds3f b = s->GetBounds();
+    double meta[10] = {s->sdfSpacing, s->sdfOrigin.x, s->sdfOrigin.y, s->sdfOrigin.z, b.pMin.x, b.pMin.y, b.pMin.z, b.pMax.x, b.pMax.y, b.pMax.z};
+    std::fwrite(res, 8, 3, fp); std::fwrite(meta, 8, 10, fp);
+    std::fwrite(s->sdfField.data(), 8, s->sdfField.size(), fp);
+    if(argc == 7){
+        FILE *fq = std::fopen(argv[6], "rb");
+        if(!fq){ std::fclose(fp); return 1; }
+        int64_t n = 0; r = std::fread(&n, 8, 1, fq);
+        std::vector<bbx::vec3f> q((size_t)n); r += std::fread(q.data(), sizeof(bbx::vec3f), q.size(), fq); std::fclose(fq);
+        for(int64_t i = 0; i < n; i++){ double d = bbx::MeshClosestDistance(*s, q[(size_t)i]); std::fwrite(&d, 8, 1, fp); }
+    }
+    std::fclose(fp);
+    return 0;
+}
+
 int main(int argc, char **argv){
+    if(argc >= 2 && std::string(argv[1]) == "--bake") return bake_mode(argc, argv);
     if(argc == 4 && std::string(argv[1]) == "--tseq") return tseq_mode(argv[2], argv[3]);
     if(argc == 4 && std::string(argv[1]) == "--load") return load_mode(argv[2], argv[3]);
     if(argc == 4 && std::string(argv[1]) == "--mapemit") return mapemit_mode(argv[2], argv[3]);
