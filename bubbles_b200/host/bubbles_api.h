@@ -277,11 +277,17 @@ struct ParticleSetBuilder3 {
 struct ParticleSet3 {
     std::vector<vec3f> positions, velocities;
     std::vector<Float> densities;
+    std::vector<Float> v0s;        // boundary layer of each particle (ParticleSet3::v0s, particle.h:170): 0 = interior
+    std::vector<vec3f> normals;    // filled by a boundary / normal pass of the caller (src/boundaries/*, out of scope here); zeros otherwise
     Float mass = 0;
     int GetParticleCount() const { return (int)positions.size(); }
     vec3f GetParticlePosition(int i) const { return positions[i]; }
     vec3f GetParticleVelocity(int i) const { return velocities[i]; }
     Float GetParticleDensity(int i) const { return densities[i]; }
+    vec3f GetParticleNormal(int i) const { return (size_t)i < normals.size() ? normals[(size_t)i] : vec3f(); }
+    void SetParticleNormal(int i, const vec3f &n){ if(normals.size() < positions.size()) normals.resize(positions.size()); normals[(size_t)i] = n; }
+    Float GetParticleV0(int i) const { return (size_t)i < v0s.size() ? v0s[(size_t)i] : 0.0; }
+    void SetParticleV0(int i, Float v){ if(v0s.size() < positions.size()) v0s.resize(positions.size(), 0.0); v0s[(size_t)i] = v; }
     Float GetMass() const { return mass; }
 };
 struct SphParticleSet3 {
@@ -564,31 +570,56 @@ class SphSolver3 : public SolverBase3 {
 
 // --------------------------------------------------------------------------------------- serializer
 enum { SERIALIZER_POSITION = 0x01, SERIALIZER_VELOCITY = 0x02, SERIALIZER_DENSITY = 0x04, SERIALIZER_BOUNDARY = 0x08,
-       SERIALIZER_NORMAL = 0x10, SERIALIZER_MASS = 0x20 };
-inline std::string SerializerStringFromFlags(int flags){
+       SERIALIZER_NORMAL = 0x10, SERIALIZER_MASS = 0x20, SERIALIZER_LAYERS = 0x40, SERIALIZER_XYZ = 0x80,
+       SERIALIZER_RULE_BOUNDARY_EXCLUSIVE = 0x100 };   // src/third/serializer.h:7-17
+inline std::string SerializerStringFromFlags(int flags){   // serializer.cpp:48-59
     std::string s;
     if(flags & SERIALIZER_POSITION) s += "p";
     if(flags & SERIALIZER_VELOCITY) s += "v";
     if(flags & SERIALIZER_DENSITY) s += "d";
     if(flags & SERIALIZER_MASS) s += "m";
+    if(flags & SERIALIZER_BOUNDARY) s += "b";
+    if(flags & SERIALIZER_NORMAL) s += "n";
+    if(flags & SERIALIZER_LAYERS) s += "l";
+    if(flags & SERIALIZER_RULE_BOUNDARY_EXCLUSIVE) s += "o";
     return s;
 }
-// SaveSphParticleSet (src/third/serializer.cpp:884-921): the "FluidBegin ... DataEnd / FluidEnd" text frame, one
-// line per particle in id order, fields p v d m, "%g"; appended to `filename` like the reference ("a+").
-inline void SerializerSaveSphDataSet3(SphSolverData3 *data, const char *filename, int flags){
+// SaveSphParticleSet + PushParticleSetToFile (src/third/serializer.cpp:812-921): the "FluidBegin ... DataEnd / FluidEnd" text
+// frame, one line per particle in id order, columns p v d m b n, "%g" / "%d"; appended to `filename` like the reference
+// ("a+").  `boundary` = the per-particle boundary layer a classification pass produced (src/boundaries/*: the caller's, out of
+// scope here); SERIALIZER_RULE_BOUNDARY_EXCLUSIVE keeps only the particles with boundary > 0; normals come from
+// ParticleSet3::normals.  The quirks of the reference are kept: without a boundary vector the b column is dropped with a
+// warning while the format string still says "b", and the exclusive rule without a vector writes nothing.
+inline void SerializerSaveSphDataSet3(SphSolverData3 *data, const char *filename, int flags, std::vector<int> *boundary = nullptr){
     ParticleSet3 *ps = data->sphpSet->GetParticleSet();
     FILE *fp = std::fopen(filename, "a+");
     if(!fp){ std::printf("Error: Failed to open %s\n", filename); return; }
-    flags &= SERIALIZER_POSITION | SERIALIZER_VELOCITY | SERIALIZER_DENSITY | SERIALIZER_MASS;
+    int pCount = ps->GetParticleCount();
+    if((flags & SERIALIZER_RULE_BOUNDARY_EXCLUSIVE) && boundary){
+        pCount = 0;
+        for(size_t i = 0; i < boundary->size(); i++) pCount += boundary->at(i) > 0 ? 1 : 0;
+    }else if(flags & SERIALIZER_RULE_BOUNDARY_EXCLUSIVE){
+        std::printf("Invalid configuration for Serialized particles\n");
+        std::fclose(fp);
+        return;
+    }
     std::fprintf(fp, "FluidBegin\n\t\"Type\" particles\n\t\"Count\" %d\n\t\"Format\" %s\n\t\"Spacing\" %g\n\tDataBegin\n",
-                 ps->GetParticleCount(), SerializerStringFromFlags(flags).c_str(), data->sphpSet->GetTargetSpacing());
+                 pCount, SerializerStringFromFlags(flags).c_str(), data->sphpSet->GetTargetSpacing());
+    int logged = 0;
     for(int i = 0; i < ps->GetParticleCount(); i++){
         int sp = 0;
+        const int boundary_value = boundary ? boundary->at((size_t)i) : 0;
+        if((flags & SERIALIZER_RULE_BOUNDARY_EXCLUSIVE) && !boundary_value) continue;
         std::fprintf(fp, "\t\t");
         if(flags & SERIALIZER_POSITION){ vec3f p = ps->GetParticlePosition(i); std::fprintf(fp, "%g %g %g", p.x, p.y, p.z); sp = 1; }
         if(flags & SERIALIZER_VELOCITY){ vec3f v = ps->GetParticleVelocity(i); std::fprintf(fp, sp ? " %g %g %g" : "%g %g %g", v.x, v.y, v.z); sp = 1; }
         if(flags & SERIALIZER_DENSITY){ std::fprintf(fp, sp ? " %g" : "%g", ps->GetParticleDensity(i)); sp = 1; }
         if(flags & SERIALIZER_MASS){ std::fprintf(fp, sp ? " %g" : "%g", ps->GetMass()); sp = 1; }
+        if(flags & SERIALIZER_BOUNDARY){
+            if(!boundary && !logged){ std::printf("Warning: Not a valid boundary given\n"); logged = 1; }
+            else if(boundary){ std::fprintf(fp, sp ? " %d" : "%d", boundary_value); sp = 1; }
+        }
+        if(flags & SERIALIZER_NORMAL){ vec3f n = ps->GetParticleNormal(i); std::fprintf(fp, sp ? " %g %g %g" : "%g %g %g", n.x, n.y, n.z); sp = 1; }
         std::fprintf(fp, "\n");
     }
     std::fprintf(fp, "\tDataEnd\nFluidEnd\n");
@@ -640,7 +671,6 @@ inline Float ParseFloat(const char **token){
     return v;
 }
 inline vec3f ParseV3(const char **token){ Float a = ParseFloat(token), b = ParseFloat(token), c = ParseFloat(token); return vec3f(a, b, c); }
-enum { SERIALIZER_LAYERS = 0x40, SERIALIZER_RULE_BOUNDARY_EXCLUSIVE = 0x80, SERIALIZER_XYZ = 0x100 };
 inline int SerializerFlagsFromString(const char *spec){
     int flags = 0;
     for(const char *p = spec; *p; p++){
@@ -736,9 +766,19 @@ inline std::string ShapeSerialize(const Shape &s){
     ss << "ShapeEnd";
     return ss.str();
 }
+// UtilGetBoundaryState (src/core/util.h:708-725): the boundary column = the positive v0 values
+inline int UtilGetBoundaryState(ParticleSet3 *pSet, std::vector<int> *boundaries){
+    int n = 0; boundaries->clear();
+    for(int i = 0; i < pSet->GetParticleCount(); i++){
+        int b = 0; int v0 = (int)pSet->GetParticleV0(i);
+        if(v0 > 0){ b = v0; n++; }
+        boundaries->push_back(b);
+    }
+    return n;
+}
 // UtilSaveSimulation3 (src/core/util.h:296-328): the file is rewritten with the shape blocks of the active obstacle
 // colliders -- every collider but the LAST, which the reference takes to be the domain -- followed by the particle
-// block.  (The boundary column needs the boundary classification, which is out of scope: flags p, v, d, m.)
+// block.  (A boundary vector, when the caller has one, goes through SerializerSaveSphDataSet3's last argument.)
 inline void UtilSaveSimulation3(ColliderSet3 *colliders, SphSolverData3 *data, const char *filename, int flags){
     std::remove(filename);
     FILE *fp = std::fopen(filename, "a+");
@@ -747,7 +787,9 @@ inline void UtilSaveSimulation3(ColliderSet3 *colliders, SphSolverData3 *data, c
     if(colliders) for(int i = 0; i < colliders->nColiders() - 1; i++) if(colliders->active[i]) ss << ShapeSerialize(*colliders->shapes[i]) << std::endl;
     std::fprintf(fp, "%s", ss.str().c_str());
     std::fclose(fp);
-    SerializerSaveSphDataSet3(data, filename, flags);
+    std::vector<int> boundaries;
+    UtilGetBoundaryState(data->sphpSet->GetParticleSet(), &boundaries);
+    SerializerSaveSphDataSet3(data, filename, flags, &boundaries);
 }
 template<typename Solver, typename ParticleAccessor>
 inline void UtilSaveSimulation3(Solver *solver, ParticleAccessor *, const char *filename, int flags){

@@ -1,7 +1,9 @@
 // frame_tool: writes one bbtool-readable text frame with the facade's SerializerSaveSphDataSet3 from a raw state
 // file -- host only (no engine), used by tests/test_frame_writer.py to compare the writer byte for byte with the
 // reference's own (src/third/serializer.cpp:812-921) and to feed the reference's reader.
-//   frame_tool <state.bin> <out.txt> <flags> [--box tx ty tz sx sy sz | --sphere tx ty tz r] ...
+//   frame_tool <state.bin> <out.txt> <flags> [--boundary b.bin n.bin] [--box tx ty tz sx sy sz | --sphere tx ty tz r] ...
+//     --boundary: per-particle boundary layer (int64 n, double v0[n]) and normals (int64 n, double normal[3n]); without
+//     shapes the frame is written with the boundary vector UtilGetBoundaryState builds from them
 //     with shapes: UtilSaveSimulation3 (shape blocks of every collider but the last + the particle block)
 //   state.bin: int64 n, double spacing, double mass, double pos[3n], double vel[3n], double rho[n]
 #include <cstdint>
@@ -174,10 +176,19 @@ int main(int argc, char **argv){
     for(int64_t i = 0; i < n; i++) set->set.densities[(size_t)i] = rho[(size_t)i];
     auto data = bbx::DefaultSphSolverData3(true);
     data->sphpSet = set;
-    bbx::ColliderSetBuilder3 cb; int shapes = 0;
+    bbx::ColliderSetBuilder3 cb; int shapes = 0; bool withBoundary = false;
     for(int a = 4; a < argc; ){
         std::string k = argv[a];
-        if(k == "--box" && a + 6 < argc){
+        if(k == "--boundary" && a + 2 < argc){
+            FILE *fb = std::fopen(argv[a + 1], "rb"), *fn = std::fopen(argv[a + 2], "rb");
+            if(!fb || !fn){ std::fprintf(stderr, "cannot open the boundary files\n"); return 2; }
+            int64_t nb = 0; size_t q = std::fread(&nb, 8, 1, fb);
+            std::vector<double> v0((size_t)nb); q += std::fread(v0.data(), 8, v0.size(), fb); std::fclose(fb);
+            q += std::fread(&nb, 8, 1, fn);
+            std::vector<double> nr(3 * (size_t)nb); q += std::fread(nr.data(), 8, nr.size(), fn); std::fclose(fn); (void)q;
+            for(int64_t i = 0; i < nb; i++){ set->set.SetParticleV0((int)i, v0[(size_t)i]); set->set.SetParticleNormal((int)i, bbx::vec3f(nr[3*i], nr[3*i+1], nr[3*i+2])); }
+            withBoundary = true; a += 3;
+        }else if(k == "--box" && a + 6 < argc){
             cb.AddCollider3(bbx::MakeBox(bbx::Translate(std::atof(argv[a+1]), std::atof(argv[a+2]), std::atof(argv[a+3])),
                                          bbx::vec3f(std::atof(argv[a+4]), std::atof(argv[a+5]), std::atof(argv[a+6])))); a += 7; shapes++;
         }else if(k == "--sphere" && a + 4 < argc){
@@ -185,6 +196,10 @@ int main(int argc, char **argv){
         }else{ std::fprintf(stderr, "bad shape argument %s\n", argv[a]); return 2; }
     }
     if(shapes) bbx::UtilSaveSimulation3(cb.GetColliderSet().get(), data.get(), argv[2], std::atoi(argv[3]));
+    else if(withBoundary){
+        std::vector<int> boundaries; bbx::UtilGetBoundaryState(&set->set, &boundaries);
+        bbx::SerializerSaveSphDataSet3(data.get(), argv[2], std::atoi(argv[3]), &boundaries);
+    }
     else bbx::SerializerSaveSphDataSet3(data.get(), argv[2], std::atoi(argv[3]));
     return 0;
 }

@@ -573,6 +573,24 @@ int main(int argc, char **argv){
             printf("[bbref] sdf res=%u %u %u spacing=%.17g origin=%.17g %.17g %.17g\n", g->resolution.x,
                    g->resolution.y, g->resolution.z, g->spacing.x, g->minPoint.x, g->minPoint.y, g->minPoint.z);
         }
+        else if(cmd == "set_boundary"){
+            // per-particle boundary layer (ParticleSet3::v0s, what the boundary classifiers of src/boundaries/* leave there) and
+            // normals, from files: int64 n, double v0[n] | int64 n, double normal[3n]
+            std::string fb, fn; in >> fb >> fn;
+            ParticleSet3 *ps = H.sphSet->GetParticleSet();
+            FILE *fp = fopen(fb.c_str(), "rb"); int64_t n = 0; size_t r = fread(&n, 8, 1, fp);
+            std::vector<double> v0(n); r += fread(v0.data(), 8, n, fp); fclose(fp);
+            fp = fopen(fn.c_str(), "rb"); r += fread(&n, 8, 1, fp);
+            std::vector<double> nr(3 * n); r += fread(nr.data(), 8, 3 * n, fp); fclose(fp);
+            for(int64_t i = 0; i < n; i++){ ps->SetParticleV0((int)i, v0[i]); ps->SetParticleNormal((int)i, vec3f(nr[3*i], nr[3*i+1], nr[3*i+2])); }
+        }
+        else if(cmd == "save_frame_b"){
+            // SerializerSaveSphDataSet3 with the boundary vector UtilGetBoundaryState builds (src/core/util.h:708-725)
+            std::string file; int flags; in >> file >> flags;
+            std::vector<int> boundaries;
+            UtilGetBoundaryState(H.sphSet->GetParticleSet(), &boundaries);
+            SerializerSaveSphDataSet3(H.data, file.c_str(), flags, &boundaries);
+        }
         else if(cmd == "tseq_add"){
             // TransformSequence::AddInterpolation(&K0, &K1, s0, s1) (src/core/transform_sequence.cpp:30-47) between two
             // keyframes K = Translate(t) * Rotate(angle [deg], axis) * Scale(s)

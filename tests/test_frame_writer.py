@@ -77,8 +77,10 @@ def test_writer_is_byte_identical_to_the_reference_and_its_reader_loads_it(tmp_p
         assert same(np.load(tmp_path / "l_mass.npy"), np.full(n, float("%g" % mass)))
 
 
-def test_simulation_file_with_shape_blocks_is_byte_identical(tmp_path):
-    """UtilSaveSimulation3 (src/core/util.h:296-328): shape blocks (Shape::BoxSerialize / SphereSerialize,
+@pytest.mark.parametrize("sim_flags", [0x01 | 0x02, 0x01 | 0x02 | 0x08])
+def test_simulation_file_with_shape_blocks_is_byte_identical(tmp_path, sim_flags):
+    """(with the b flag the reference's UtilSaveSimulation3 always passes the boundary vector it builds from the particle set's
+    v0 values -- all zero for a set nobody classified -- so the column is there)  UtilSaveSimulation3 (src/core/util.h:296-328): shape blocks (Shape::BoxSerialize / SphereSerialize,
     box.cpp:37-57, sphere.cpp:11-31) of every collider but the last -- the domain -- then the particle block."""
     sc = scenes.probe_scene()
     O.write_particles(str(tmp_path / "p.bin"), sc["pos"], sc["vel"])
@@ -89,14 +91,14 @@ def test_simulation_file_with_shape_blocks_is_byte_identical(tmp_path):
            f"collider sphere {O.mat_str(O.translate(*sph_t))} 0.08 0 0.2",
            f"collider box {I} 0.6 0.6 0.6 1 0", "domain_from_collider 2",
            f"particles {tmp_path}/p.bin", "setup", f"step {sc['dt']} 2", f"dump {tmp_path}/s_",
-           f"save_sim {tmp_path}/ref.txt {P | V}"]
+           f"save_sim {tmp_path}/ref.txt {sim_flags}"]
     O.run_ref(job, str(tmp_path))
     pos, vel, rho = (np.load(tmp_path / f"s_{k}.npy") for k in ("pos", "vel", "density"))
     with open(tmp_path / "state.bin", "wb") as f:
         f.write(struct.pack("<qdd", len(pos), float(sc["spacing"]), 0.0))
         for a in (pos, vel, rho):
             f.write(np.ascontiguousarray(a, np.float64).tobytes())
-    args = [_tool(), str(tmp_path / "state.bin"), str(tmp_path / "bbx.txt"), str(P | V),
+    args = [_tool(), str(tmp_path / "state.bin"), str(tmp_path / "bbx.txt"), str(sim_flags),
             "--box", *[repr(float(x)) for x in box_t], "0.1", "0.125", "0.15",
             "--sphere", *[repr(float(x)) for x in sph_t], "0.08",
             "--box", "0", "0", "0", "0.6", "0.6", "0.6"]
@@ -137,3 +139,52 @@ def test_reader_loads_reference_frames_bit_identically_to_the_reference_reader(t
         assert np.array_equal(vel, np.load(tmp_path / f"{pre}vel.npy"))
         assert np.array_equal(rho, np.load(tmp_path / f"{pre}rho.npy"))
         assert np.array_equal(mass, np.load(tmp_path / f"{pre}mass.npy"))
+
+
+B, N, L, O_ = 0x08, 0x10, 0x40, 0x100   # boundary, normal, layers, boundary-exclusive rule (src/third/serializer.h:7-17)
+
+
+@pytest.mark.parametrize("flags", [P | B, P | V | D | M | B | N, P | N, P | B | O_, P | V | B | N | L | O_, P | B | N])
+def test_writer_boundary_and_normal_columns_are_byte_identical(tmp_path, flags):
+    """The b / n columns and the boundary-exclusive rule (PushParticleSetToFile, serializer.cpp:812-880) with a boundary layer
+    and normals a classification pass would have left in the particle set (here: synthetic values), written by the reference
+    (SerializerSaveSphDataSet3 with the vector UtilGetBoundaryState builds) and by the facade: byte-identical files."""
+    sc, job = _reference_state(tmp_path)
+    rng = np.random.default_rng(3)
+    n = len(sc["pos"])
+    v0 = np.where(rng.random(n) < 0.3, rng.integers(1, 4, n), 0).astype(np.float64)
+    nrm = rng.normal(size=(n, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True); nrm[v0 == 0] = 0.0
+    for name, arr in (("b.bin", v0), ("n.bin", nrm)):
+        with open(tmp_path / name, "wb") as f:
+            f.write(struct.pack("<q", n)); f.write(np.ascontiguousarray(arr, np.float64).tobytes())
+    ref_txt, our_txt = tmp_path / "ref.txt", tmp_path / "bbx.txt"
+    O.run_ref(job + [f"set_boundary {tmp_path}/b.bin {tmp_path}/n.bin", f"save_frame_b {ref_txt} {flags}"], str(tmp_path))
+    pos, vel, rho = (np.load(tmp_path / f"s_{k}.npy") for k in ("pos", "vel", "density"))
+    mass = float(scenes.make_oracle(sc).P.mass)
+    with open(tmp_path / "state.bin", "wb") as f:
+        f.write(struct.pack("<qdd", n, float(sc["spacing"]), mass))
+        for a in (pos, vel, rho):
+            f.write(np.ascontiguousarray(a, np.float64).tobytes())
+    r = subprocess.run([_tool(), str(tmp_path / "state.bin"), str(our_txt), str(flags), "--boundary", str(tmp_path / "b.bin"), str(tmp_path / "n.bin")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ours, ref = open(our_txt, "rb").read(), open(ref_txt, "rb").read()
+    assert ours == ref
+    count = int(re.search(rb'"Count" (\d+)', ref).group(1))
+    assert count == (int((v0 > 0).sum()) if flags & O_ else n) and 0 < (v0 > 0).sum() < n
+
+
+def test_writer_without_a_boundary_vector_keeps_the_reference_quirk(tmp_path):
+    """No vector + the b flag: the reference warns, writes "b" into the format string and leaves the column out; the plain
+    save_frame command of the harness does exactly that, and so does the facade."""
+    sc, job = _reference_state(tmp_path)
+    ref_txt, our_txt = tmp_path / "ref.txt", tmp_path / "bbx.txt"
+    O.run_ref(job + [f"save_frame {ref_txt} {P | B}"], str(tmp_path))
+    pos, vel, rho = (np.load(tmp_path / f"s_{k}.npy") for k in ("pos", "vel", "density"))
+    with open(tmp_path / "state.bin", "wb") as f:
+        f.write(struct.pack("<qdd", len(pos), float(sc["spacing"]), 0.0))
+        for a in (pos, vel, rho):
+            f.write(np.ascontiguousarray(a, np.float64).tobytes())
+    r = subprocess.run([_tool(), str(tmp_path / "state.bin"), str(our_txt), str(P | B)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(our_txt, "rb").read() == open(ref_txt, "rb").read() and b'"Format" pb' in open(ref_txt, "rb").read()
