@@ -806,4 +806,7 @@ inline void RunSimulation3(Solver *solver, Float targetInterval, const std::func
 }
 inline void PciSphRunSimulation3(PciSphSolver3 *solver, Float targetInterval, const std::function<int(int)> &callback){ RunSimulation3(solver, targetInterval, callback); }
 
+// Wavefront .obj files for mesh colliders: LoadObj, MakeMesh(path | mesh, toWorld)
+#include "obj_loader.h"
+
 } // namespace bbx

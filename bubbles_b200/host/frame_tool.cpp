@@ -153,7 +153,21 @@ static int bake_mode(int argc, char **argv){
     return 0;
 }
 
+// frame_tool --obj <file.obj> <out.bin>: the facade's LoadObj; out.bin: int64 nv, nt; double points[3 nv]; int32 triangles[3 nt]
+static int obj_mode(const char *in, const char *out){
+    bbx::ParsedMesh m = bbx::LoadObj(in);
+    FILE *fp = std::fopen(out, "wb");
+    if(!fp) return 1;
+    int64_t hdr[2] = {m.nVertices, m.nTriangles};
+    std::fwrite(hdr, 8, 2, fp);
+    std::fwrite(m.p.data(), sizeof(bbx::vec3f), m.p.size(), fp);
+    std::fwrite(m.indices.data(), 4, m.indices.size(), fp);
+    std::fclose(fp);
+    return 0;
+}
+
 int main(int argc, char **argv){
+    if(argc == 4 && std::string(argv[1]) == "--obj") return obj_mode(argv[2], argv[3]);
     if(argc >= 2 && std::string(argv[1]) == "--bake") return bake_mode(argc, argv);
     if(argc == 4 && std::string(argv[1]) == "--tseq") return tseq_mode(argv[2], argv[3]);
     if(argc == 4 && std::string(argv[1]) == "--load") return load_mode(argv[2], argv[3]);

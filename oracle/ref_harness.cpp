@@ -31,6 +31,7 @@
 #include <util.h>
 #include <memory.h>
 #include <transform_sequence.h>
+#include <obj_loader.h>
 
 // BBREF_GPU: the same driver for the reference's GPU path (its native mode): the reference's own managed-memory
 // arena (src/cuda/memory.cpp) is linked instead of the shim, the system stays in GPU mode and every kernel of the
@@ -572,6 +573,17 @@ int main(int argc, char **argv){
             int idx; in >> idx; FieldGrid3f *g = H.shapes[idx]->grid;
             printf("[bbref] sdf res=%u %u %u spacing=%.17g origin=%.17g %.17g %.17g\n", g->resolution.x,
                    g->resolution.y, g->resolution.z, g->spacing.x, g->minPoint.x, g->minPoint.y, g->minPoint.z);
+        }
+        else if(cmd == "load_obj"){
+            // the reference's .obj loader (src/third/obj_loader.cpp:434-625): vertices in first-use order and the vertex index
+            // of every triangle corner (mesh->indices[].x), as .npy
+            std::string file, prefix; in >> file >> prefix;
+            ParsedMesh *m = LoadObj(file.c_str());
+            std::vector<double> pts(3 * (size_t)m->nVertices); std::vector<int32_t> tri(3 * (size_t)m->nTriangles);
+            for(int i = 0; i < m->nVertices; i++) for(int k = 0; k < 3; k++) pts[3 * (size_t)i + k] = m->p[i][k];
+            for(int i = 0; i < 3 * m->nTriangles; i++) tri[(size_t)i] = m->indices[i].x;
+            WriteNpy<double>(prefix + "points.npy", pts.data(), m->nVertices, 3);
+            WriteNpy<int32_t>(prefix + "triangles.npy", tri.data(), m->nTriangles, 3);
         }
         else if(cmd == "set_boundary"){
             // per-particle boundary layer (ParticleSet3::v0s, what the boundary classifiers of src/boundaries/* leave there) and

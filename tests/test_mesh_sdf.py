@@ -69,3 +69,49 @@ def test_inside_test_is_direction_independent_on_a_closed_mesh():
     exact = np.abs(l1 - r) / np.sqrt(3.0)                      # distance to the face plane: exact wherever the foot point is on the face
     inner = l1 < r
     assert np.abs(np.abs(field[inner]) - np.maximum(exact[inner], 1e-5)).max() < 1e-12
+
+
+def test_obj_loader_matches_the_reference_loader():
+    """LoadObj (bubbles_b200/host/obj_loader.h) against the reference's loader (src/third/obj_loader.cpp) through the harness: a
+    file with comments, CRLF line ends, every corner syntax (i, i/j, i//k, i/j/k), negative indices, quads, unused vertices,
+    numbers in plain / exponent form -- vertices (first-use order, bit for bit) and triangle indices must agree."""
+    import pytest
+    from oracle import oracle as O
+    if not O.ref_available():
+        pytest.skip("oracle/_ref/bbref not built")
+    g = np.load(os.path.join(G, "mesh_collider.npz"))
+    v, t = g["vertices"], g["triangles"]
+    wd = tempfile.mkdtemp(prefix="obj_")
+    path = os.path.join(wd, "mesh.obj")
+    rng = np.random.default_rng(11)
+    lines = ["# generated by tests/test_mesh_sdf.py", "mtllib none.mtl", "o blob", "v 9.5 9.5 9.5", "v -1.25e-3 4.0E+1 .5"]   # two vertices no face uses
+    fmts = ["%.17g", "%.9f", "%.6e", "%g"]
+    for k, p in enumerate(v):
+        lines.append("v " + " ".join(fmts[k % 4] % x for x in p) + ("\r" if k % 7 == 0 else ""))
+    lines += ["vn 0 0 1", "vn 0 1 0", "vt 0.5 0.5", "vt 0.25 0.75", "usemtl skin"]
+    nv = len(v) + 2
+    for k, tri in enumerate(t[:600]):
+        a = tri + 3                                   # 1-based, behind the two unused vertices
+        style = k % 5
+        if style == 0: c = ["%d" % i for i in a]
+        elif style == 1: c = ["%d/%d" % (i, 1 + k % 2) for i in a]
+        elif style == 2: c = ["%d//%d" % (i, 1 + k % 2) for i in a]
+        elif style == 3: c = ["%d/%d/%d" % (i, 1 + k % 2, 2 - k % 2) for i in a]
+        else: c = ["%d" % (i - nv - 1) for i in a]      # negative: relative to the vertices read so far
+        lines.append("f " + " ".join(c) + ("  " if k % 3 == 0 else ""))
+    for k in range(40):                                # quads
+        q = rng.integers(3, nv + 1, 4)
+        lines.append("f " + " ".join("%d" % i for i in q))
+    open(path, "w", newline="").write("\n".join(lines) + "\n")
+    O.run_ref([f"load_obj {path} {wd}/r_"], wd)
+    out = os.path.join(wd, "out.bin")
+    r = subprocess.run([TOOL, "--obj", path, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = open(out, "rb").read()
+    n, m = np.frombuffer(raw, dtype=np.int64, count=2)
+    pts = np.frombuffer(raw, dtype=np.float64, count=3 * n, offset=16).reshape(n, 3)
+    tri = np.frombuffer(raw, dtype=np.int32, count=3 * m, offset=16 + 24 * n).reshape(m, 3)
+    rp, rt = np.load(os.path.join(wd, "r_points.npy")), np.load(os.path.join(wd, "r_triangles.npy"))
+    assert (n, m) == (len(rp), len(rt)) and m == 600 + 80
+    assert np.array_equal(bits(pts), bits(rp)) and np.array_equal(tri, rt)
+    assert n <= len(v)                                   # the two unused vertices are gone
