@@ -83,3 +83,27 @@ def test_world_size_2_gloo_rank_plumbing():
     assert plans0 == plans1 and plans0[0] == plans0[1]
     assert blob0 == blob1 == bytes([7]) * 128
     assert sum(counts0) == n0 == n1
+
+
+def test_plan_steps_walk_to_any_target_through_valid_neighbour_only_moves():
+    """bbx_slab_plan_step: from any cuts to any other cuts in steps bbx_rebalance can follow -- every intermediate plan keeps
+    at least one plane per rank, every cut stays strictly inside the two slabs it separates in the CURRENT plan (planes change
+    hands between neighbours only), and the walk ends at the target after at most a few steps."""
+    rng = np.random.default_rng(5)
+    for case in range(200):
+        nr = int(rng.integers(2, 9)); nplanes = int(rng.integers(nr, 120))
+        draw = lambda: [0] + sorted(rng.choice(np.arange(1, nplanes), nr - 1, replace=False).tolist()) + [nplanes]
+        cur, tgt = draw(), draw()
+        for steps in range(64):
+            if cur == tgt:
+                break
+            step, done = bb.plan_step(cur, tgt)
+            step = list(step)
+            assert step[0] == 0 and step[-1] == nplanes and all(b > a for a, b in zip(step[:-1], step[1:])), (cur, tgt, step)
+            for r in range(1, nr):
+                assert cur[r - 1] < step[r] < cur[r + 1], (cur, tgt, step)      # the cut stayed between its two slabs
+                assert abs(step[r] - tgt[r]) <= abs(cur[r] - tgt[r])             # and never moved away from its target
+            assert step != cur, "no progress"
+            assert bool(done) == (step == tgt)
+            cur = step
+        assert cur == tgt and steps <= nplanes
