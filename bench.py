@@ -325,7 +325,7 @@ class Job:
         bbx_slab_plan) and move there in neighbour-only steps (bbx_slab_plan_step, bbx_rebalance).  Host-synchronous;
         returns the wall-clock ms it took on this rank.  Policy: look at most once per `every` sub-steps (a look costs
         ~0.3 ms, a move ~2 ms: one to two sub-steps); plan on the histogram EXTRAPOLATED to the middle of the next
-        interval from the drift since the previous look (a dam break pushes ~10 % of the mass across a cut in 100
+        interval from the drift since the previous look (a dam break pushes ~5 % of the mass across a cut per 100
         sub-steps); move only when the fullest slab of the new plan is at least `gain` x the mean lighter than the
         fullest slab of the current one.  Every decision is a function of the GLOBAL histogram and of the capacities
         every rank can compute, so all ranks take the same one (bbx_rebalance is collective); a step that would bring a
